@@ -1,0 +1,79 @@
+"""festim_b200: B200-native solver backend behind the FESTIM API.
+
+The public names mirror reference ``src/festim/__init__.py:14-104`` for the hot
+path: problem, species, reactions, materials, boundary
+conditions, sources, step-size control and derived quantities.  ``ufl`` and
+``fem`` are the in-repo stand-ins for the UFL / dolfinx.fem names user scripts
+touch.  All numerics run in ``libfestim_b200.so`` (hand-written sm_100a CUDA,
+C ABI in ``include/festim_b200.h``); there is no CPU fallback.
+"""
+
+from festim_b200.constants import R, k_B, k_B_SI
+from festim_b200 import fem, ufl
+from festim_b200.advection import AdvectionTerm, VectorFunction, VelocityField
+from festim_b200.boundary_conditions import (
+    DirichletBC,
+    DirichletBCBase,
+    FixedConcentrationBC,
+    FixedTemperatureBC,
+    FluxBCBase,
+    HeatFluxBC,
+    HenrysBC,
+    ParticleFluxBC,
+    SievertsBC,
+    SurfaceReactionBC,
+)
+from festim_b200.exports import (
+    AverageSurface,
+    AverageVolume,
+    DerivedQuantity,
+    MaximumSurface,
+    MaximumVolume,
+    MinimumSurface,
+    MinimumVolume,
+    Profile1DExport,
+    SurfaceFlux,
+    SurfaceQuantity,
+    TotalSurface,
+    TotalVolume,
+    VolumeQuantity,
+)
+from festim_b200.helpers import Value, as_fenics_constant, is_it_time_to_export
+from festim_b200.hydrogen_transport_problem import HydrogenTransportProblem
+from festim_b200.initial_condition import (
+    InitialConcentration,
+    InitialConditionBase,
+    InitialTemperature,
+)
+from festim_b200.material import Material, SolubilityLaw
+from festim_b200.mesh import (
+    CoordinateSystem,
+    Mesh,
+    Mesh1D,
+    MeshTags,
+    SimplexMesh,
+    create_box,
+    create_interval,
+    create_rectangle,
+    create_unit_cube,
+    create_unit_interval,
+    create_unit_square,
+    locate_entities,
+    locate_entities_boundary,
+    meshtags,
+)
+from festim_b200.problem import ProblemBase
+from festim_b200.reaction import Reaction
+from festim_b200.settings import Settings
+from festim_b200.source import HeatSource, ParticleSource, SourceBase
+from festim_b200.species import ImplicitSpecies, Species, find_species_from_name
+from festim_b200.stepsize import Stepsize
+from festim_b200.subdomain import (
+    SurfaceSubdomain,
+    SurfaceSubdomain1D,
+    VolumeSubdomain,
+    VolumeSubdomain1D,
+    find_surface_from_id,
+    find_volume_from_id,
+)
+from festim_b200.trap import Trap

@@ -1,0 +1,404 @@
+"""Hydrogen transport problem (continuous formulation).
+
+Mirrors reference ``src/festim/hydrogen_transport_problem.py:58-1156``: the
+``initialise`` pipeline (314-344), temperature handling (364-425), species
+functions (672-751), strong Dirichlet BCs (769-807), initial conditions
+(840-868), the weak form (870-997), per-step updates (999-1034) and
+post-processing (1036-1156).  Unknowns live in one node-major blocked vector
+``u.x.array[v * ns + s]``.
+"""
+
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from festim_b200 import boundary_conditions as _bcs
+from festim_b200 import exports as _exports
+from festim_b200 import fem, forms, ufl
+from festim_b200 import species as _species
+from festim_b200.constants import k_B
+from festim_b200.helpers import as_fenics_constant, is_it_time_to_export
+from festim_b200.problem import DirichletBCForm, ProblemBase
+from festim_b200.source import ParticleSource
+
+
+class HydrogenTransportProblem(ProblemBase):
+    def __init__(self, mesh=None, subdomains=None, species=None, reactions=None,
+                 temperature=None, sources=None, initial_conditions=None,
+                 boundary_conditions=None, settings=None, exports=None, traps=None,
+                 advection_terms=None, petsc_options=None, element_immobile="CG"):
+        super().__init__(mesh=mesh, sources=sources, exports=exports, subdomains=subdomains,
+                         boundary_conditions=boundary_conditions, settings=settings,
+                         petsc_options=petsc_options)
+        self.species = species or []
+        self.temperature = temperature
+        self.reactions = reactions or []
+        self.initial_conditions = initial_conditions or []
+        self.traps = traps or []
+        self.advection_terms = advection_terms or []
+        self.temperature_fenics = None
+        self.element_immobile = element_immobile
+        self._species_to_D_global = None
+
+    # ---- properties ----------------------------------------------------------
+    @property
+    def temperature(self):
+        return self._temperature
+
+    @temperature.setter
+    def temperature(self, value):
+        if value is None or isinstance(value, (float, int, fem.Constant, fem.Function)) or callable(value):
+            self._temperature = value
+        else:
+            raise TypeError("Value must be a float, int, fem.Constant, fem.Function, or callable")
+
+    @property
+    def temperature_fenics(self):
+        return self._temperature_fenics
+
+    @temperature_fenics.setter
+    def temperature_fenics(self, value):
+        if value is not None and not isinstance(value, (fem.Constant, fem.Function)):
+            raise TypeError("Value must be a fem.Constant or fem.Function")
+        self._temperature_fenics = value
+
+    @property
+    def temperature_time_dependent(self):
+        """False for a ``fem.Function`` temperature even when it changes every
+        step (coupled runs)."""
+        if self.temperature is None or isinstance(self.temperature, (fem.Constant, fem.Function)):
+            return False
+        if callable(self.temperature):
+            return "t" in self.temperature.__code__.co_varnames
+        return False
+
+    @property
+    def species(self):
+        return self._species
+
+    @species.setter
+    def species(self, value):
+        for spe in value:
+            if not isinstance(spe, _species.Species):
+                raise TypeError(
+                    f"elements of species must be of type festim.Species not {type(spe)}"
+                )
+        self._species = value
+
+    @property
+    def element_immobile(self):
+        return self._element_immobile
+
+    @element_immobile.setter
+    def element_immobile(self, value):
+        allowed_values = ["DG", "CG", "P"]
+        if value not in allowed_values:
+            raise ValueError(f"element_immobile should be in {allowed_values}")
+        if value == "DG":
+            raise NotImplementedError("DG immobile species are out of scope (SURVEY section 2)")
+        self._element_immobile = "CG"
+
+    @property
+    def _unpacked_bcs(self):
+        return list(self.boundary_conditions)
+
+    # ---- initialise pipeline (reference :314-344) -----------------------------
+    def initialise(self):
+        self.create_species_from_traps()
+        self.define_function_spaces(element_degree=self.settings.element_degree)
+        self.define_meshtags_and_measures()
+        self.assign_functions_to_species()
+
+        self.t = fem.Constant(self.mesh.mesh, 0.0)
+        if self.settings.transient:
+            self._dt = as_fenics_constant(self.settings.stepsize.initial_value, self.mesh.mesh)
+
+        self.create_implicit_species_value_fenics()
+        self.define_temperature()
+        self.define_boundary_conditions()
+        self.convert_source_input_values_to_fenics_objects()
+        self.convert_advection_term_to_fenics_objects()
+        self.create_flux_values_fenics()
+        self.create_initial_conditions()
+        self.create_formulation()
+        self.create_solver()
+        self.initialise_exports()
+
+    def create_implicit_species_value_fenics(self):
+        for reaction in self.reactions:
+            for reactant in reaction.reactant:
+                if isinstance(reactant, _species.ImplicitSpecies):
+                    reactant.create_value_fenics(mesh=self.mesh.mesh, t=self.t)
+
+    def create_species_from_traps(self):
+        # appends on every call, as the reference does
+        for trap in self.traps:
+            trap.create_species_and_reaction()
+            self.species.append(trap.trapped_concentration)
+            self.reactions.append(trap.reaction)
+
+    def define_temperature(self):
+        """Reference :364-425: float / f(t) -> Constant; anything with x -> P1 field."""
+        mesh = self.mesh.mesh
+        if self.temperature is None:
+            raise ValueError("the temperature attribute needs to be defined")
+        if isinstance(self.temperature, (float, int)):
+            self.temperature_fenics = as_fenics_constant(self.temperature, mesh)
+        elif isinstance(self.temperature, (fem.Constant, fem.Function)):
+            self.temperature_fenics = self.temperature
+        elif callable(self.temperature):
+            arguments = self.temperature.__code__.co_varnames
+            if "t" in arguments and "x" not in arguments:
+                val = self.temperature(t=float(self.t))
+                if not isinstance(val, (float, int)):
+                    raise ValueError(
+                        f"self.temperature should return a float or an int, not {type(val)} "
+                    )
+                self.temperature_fenics = as_fenics_constant(val, mesh)
+            else:
+                self.temperature_fenics = fem.Function(self.V_CG_1, name="temperature")
+                kwargs = {}
+                if "t" in arguments:
+                    kwargs["t"] = self.t
+                if "x" in arguments:
+                    kwargs["x"] = ufl.SpatialCoordinate(mesh)
+                self.temperature_expr = fem.Expression(self.temperature(**kwargs))
+                self.temperature_fenics.interpolate(self.temperature_expr)
+
+    def define_function_spaces(self, element_degree=1):
+        mesh = self.mesh.mesh
+        ns = len(self.species)
+        self.function_space = fem.FunctionSpace(mesh, "Lagrange", 1, bs=ns)
+        self.V_CG_1 = fem.FunctionSpace(mesh, "Lagrange", 1)
+        self.V_DG_0 = fem.FunctionSpace(mesh, "DG", 0)
+        self.V_DG_1 = fem.FunctionSpace(mesh, "DG", 1)
+        self.u = fem.Function(self.function_space, name="u")
+        self.u_n = fem.Function(self.function_space, name="u_n")
+
+    def assign_functions_to_species(self):
+        for idx, spe in enumerate(self.species):
+            spe.sub_function_space = self.function_space.sub(idx)
+            spe.sub_function = self.u.sub(idx)
+            spe.post_processing_solution = fem.Function(self.V_CG_1, name=spe.name)
+            spe.collapsed_function_space, spe.map_sub_to_main_solution = (
+                self.function_space.sub(idx).collapse()
+            )
+            spe.solution = ufl.SpeciesRef(spe)
+            spe.prev_solution = ufl.SpeciesRef(spe, prev=True)
+            spe.test_function = idx
+
+    def define_boundary_conditions(self):
+        for bc in self._unpacked_bcs:
+            if isinstance(bc.species, str):
+                bc.species = _species.find_species_from_name(bc.species, self.species)
+            if isinstance(bc, _bcs.ParticleFluxBC):
+                bc.create_value_fenics(mesh=self.mesh.mesh, temperature=self.temperature_fenics,
+                                       t=self.t)
+        super().define_boundary_conditions()
+
+    def create_dirichletbc_form(self, bc):
+        """Reference :769-807."""
+        bc.create_value(temperature=self.temperature_fenics,
+                        function_space=bc.species.collapsed_function_space, t=self.t)
+        verts = bc.define_surface_subdomain_vertices(self.facet_meshtags, self.mesh.mesh)
+        return DirichletBCForm(self.species.index(bc.species), verts, bc.value_fenics,
+                               len(self.species))
+
+    def convert_source_input_values_to_fenics_objects(self):
+        for source in self.sources:
+            if isinstance(source, ParticleSource):
+                source.value.convert_input_value(function_space=self.function_space, t=self.t,
+                                                 temperature=self.temperature_fenics,
+                                                 up_to_ufl_expr=True)
+
+    def convert_advection_term_to_fenics_objects(self):
+        for advec_term in self.advection_terms:
+            advec_term.velocity.convert_input_value(function_space=self.function_space, t=self.t)
+
+    def create_flux_values_fenics(self):
+        for bc in self.boundary_conditions:
+            if isinstance(bc, _bcs.ParticleFluxBC):
+                bc.create_value_fenics(mesh=self.mesh.mesh, temperature=self.temperature_fenics,
+                                       t=self.t)
+
+    def create_initial_conditions(self):
+        """Reference :840-868: nodal interpolation into u_n on the tagged cells."""
+        if len(self.initial_conditions) > 0 and not self.settings.transient:
+            raise ValueError("Initial conditions can only be defined for transient simulations")
+        for condition in self.initial_conditions:
+            fs = condition.species.collapsed_function_space if callable(condition.value) else None
+            condition.create_expr_fenics(mesh=self.mesh.mesh, temperature=self.temperature_fenics,
+                                         function_space=fs)
+            entities = self.volume_meshtags.find(condition.volume.id)
+            idx = self.species.index(condition.species)
+            self.u_n.sub(idx).interpolate(condition.expr_fenics, cells0=entities)
+
+    # ---- the weak form (reference :870-997) -----------------------------------
+    def create_formulation(self):
+        F = forms.Form()
+        T = self.temperature_fenics
+
+        for spe in self.species:
+            u, u_n = spe.solution, spe.prev_solution
+            for vol in self.volume_subdomains:
+                if spe.mobile:
+                    D = vol.material.get_diffusion_coefficient(self.mesh.mesh, T, spe)
+                    meta = {}
+                    if not vol.material.D:
+                        meta = {"arrhenius": (vol.material.get_D_0(spe), vol.material.get_E_D(spe))}
+                    F += forms.DiffusionIntegral(spe, D, self.dx(vol.id), meta)
+                if self.settings.transient:
+                    F += forms.TestIntegral(spe, (u - u_n) / self.dt, self.dx(vol.id),
+                                            {"mass": 1.0})
+
+        for reaction in self.reactions:
+            term = reaction.reaction_term(T)
+            for reactant in reaction.reactant:
+                if isinstance(reactant, _species.Species):
+                    F += forms.TestIntegral(reactant, term, self.dx(reaction.volume.id),
+                                            {"reaction": reaction, "sign": 1.0})
+            for product in reaction.products:
+                F += forms.TestIntegral(product, -term, self.dx(reaction.volume.id),
+                                        {"reaction": reaction, "sign": -1.0})
+
+        for source in self.sources:
+            F += forms.TestIntegral(source.species, -ufl.as_expr(source.value.fenics_object),
+                                    self.dx(source.volume.id), {"source": source})
+
+        for bc in self.boundary_conditions:
+            if isinstance(bc, _bcs.ParticleFluxBC):
+                F += forms.TestIntegral(bc.species, -ufl.as_expr(bc.value_fenics),
+                                        self.ds(bc.subdomain.id), {"flux": bc})
+
+        for adv_term in self.advection_terms:
+            for spe in adv_term.species:
+                F += forms.AdvectionIntegral(spe, adv_term.velocity.fenics_object,
+                                             self.dx(adv_term.subdomain.id))
+
+        if not self.settings.transient:
+            # immobile species in volumes without any reaction: c = 0 (:980-997)
+            for spe in self.species:
+                if not spe.mobile:
+                    not_defined = list(self.volume_subdomains)
+                    for vol in self.volume_subdomains:
+                        for reaction in self.reactions:
+                            if vol == reaction.volume and vol in not_defined:
+                                not_defined.remove(vol)
+                    for vol in not_defined:
+                        F += forms.TestIntegral(spe, spe.solution, self.dx(vol.id), {"filler": 1.0})
+
+        self.formulation = F
+
+    # ---- per-step updates (reference :999-1042) --------------------------------
+    def update_time_dependent_values(self):
+        super().update_time_dependent_values()
+        t = float(self.t)
+        for reaction in self.reactions:
+            for reactant in reaction.reactant:
+                if isinstance(reactant, _species.ImplicitSpecies):
+                    reactant.update_density(t=t)
+
+        if isinstance(self.temperature, fem.Function) or self.temperature_time_dependent:
+            for bc in self.boundary_conditions:
+                if isinstance(bc, (_bcs.FixedConcentrationBC, _bcs.ParticleFluxBC)):
+                    if bc.temperature_dependent:
+                        bc.update(t=t)
+            for source in self.sources:
+                if source.value.temperature_dependent:
+                    source.value.update(t=t)
+
+        if self.temperature_time_dependent:
+            if isinstance(self.temperature_fenics, fem.Constant):
+                self.temperature_fenics.value = self.temperature(t=t)
+            elif isinstance(self.temperature_fenics, fem.Function):
+                self.temperature_fenics.interpolate(self.temperature_expr)
+
+        for advec_term in self.advection_terms:
+            if advec_term.velocity.explicit_time_dependent:
+                advec_term.velocity.update(t=t)
+
+    def update_post_processing_solutions(self):
+        ns = len(self.species)
+        arr = self.u.x.array.reshape(-1, ns)
+        for idx, spe in enumerate(self.species):
+            spe.post_processing_solution.x.array[:] = arr[:, idx]
+
+    # ---- exports ---------------------------------------------------------------
+    def initialise_exports(self):
+        """Reference :427-570 (derived quantities and 1D profiles only)."""
+        for export in self.exports:
+            times = getattr(export, "times", None)
+            if times and not isinstance(export, _exports.DerivedQuantity):
+                for time in times:
+                    if time not in self.settings.stepsize.milestones:
+                        warnings.warn(
+                            "To ensure that the exports data at the desired times"
+                            "the values in export.times are added to milestones"
+                        )
+                        self.settings.stepsize.milestones.append(time)
+                self.settings.stepsize.milestones.sort()
+            if hasattr(export, "field") and isinstance(export.field, str):
+                export.field = _species.find_species_from_name(export.field, self.species)
+            if isinstance(export, _exports.Profile1DExport):
+                export.data, export.t = [], []
+            if isinstance(export, _exports.DerivedQuantity):
+                export.t, export.data = [], []
+        # D_global snapshot: the temperature the DG1 diffusivity was last
+        # interpolated with (:632-670, refreshed per :1049-1056)
+        self.refresh_D_global()
+
+    def refresh_D_global(self):
+        T = self.temperature_fenics
+        if isinstance(T, fem.Function):
+            self._D_global_T = T.x.array.copy()
+        else:
+            self._D_global_T = float(T.value)
+        if self.solver is not None and hasattr(self.solver, "set_D_global_temperature"):
+            self.solver.set_D_global_temperature(self._D_global_T)
+
+    def post_processing(self):
+        """Reference :1044-1156."""
+        self.update_post_processing_solutions()
+        if self.temperature_time_dependent:
+            self.refresh_D_global()
+        for export in self.exports:
+            if hasattr(export, "times"):
+                if not is_it_time_to_export(current_time=float(self.t), times=export.times):
+                    continue
+            if isinstance(export, (_exports.SurfaceQuantity, _exports.VolumeQuantity)):
+                if isinstance(export, (_exports.SurfaceFlux, _exports.TotalSurface,
+                                       _exports.AverageSurface)) and self.advection_terms:
+                    warnings.warn(
+                        "Advection terms are not currently accounted for in the "
+                        "evaluation of surface flux values"
+                    )
+                export.compute(self)
+                export.t.append(float(self.t))
+                if export.filename is not None:
+                    export.write(t=float(self.t))
+            if isinstance(export, _exports.Profile1DExport):
+                if export.x is None:
+                    coords = self.mesh.mesh.coords[:, 0]
+                    export._sort_coords = np.argsort(coords)
+                    export.x = coords[export._sort_coords]
+                c = export.field.post_processing_solution.x.array[export._sort_coords]
+                export.data.append(c.copy())
+                export.t.append(float(self.t))
+
+    def diffusivity_tables(self):
+        """(D_0, E_D) per (volume subdomain, species), 0 for immobile species:
+        the piecewise-constant data behind ``define_D_global`` (:656-663)."""
+        nv, ns = len(self.volume_subdomains), len(self.species)
+        D0 = np.zeros((nv, ns))
+        ED = np.zeros((nv, ns))
+        for iv, vol in enumerate(self.volume_subdomains):
+            for s, spe in enumerate(self.species):
+                if spe.mobile and not vol.material.D:
+                    D0[iv, s] = vol.material.get_D_0(spe)
+                    ED[iv, s] = vol.material.get_E_D(spe)
+        return D0, ED
+
+
+__all__ = ["HydrogenTransportProblem", "k_B"]

@@ -1,0 +1,58 @@
+"""Initial conditions (reference ``src/festim/initial_condition.py``)."""
+
+import numpy as np
+
+from festim_b200 import fem, ufl
+from festim_b200.species import Species
+
+
+class InitialConditionBase:
+    def __init__(self, value, volume):
+        self.value = value
+        self.volume = volume
+        self.expr_fenics = None
+
+    def _create(self, mesh, temperature=None):
+        if isinstance(self.value, (int, float)):
+            val = self.value
+            self.expr_fenics = lambda x: np.full(x.shape[1], val)
+        elif isinstance(self.value, fem.Function):
+            self.expr_fenics = self.value
+        elif callable(self.value):
+            arguments = self.value.__code__.co_varnames
+            kwargs = {}
+            if "t" in arguments:
+                raise ValueError("Initial condition cannot be a function of time.")
+            if "x" in arguments:
+                kwargs["x"] = ufl.SpatialCoordinate(mesh)
+            if "T" in arguments and temperature is not None:
+                kwargs["T"] = temperature
+            self.expr_fenics = fem.Expression(self.value(**kwargs))
+
+
+class InitialConcentration(InitialConditionBase):
+    """``initial_condition.py:46-141``."""
+
+    def __init__(self, value, volume, species):
+        super().__init__(value=value, volume=volume)
+        self.species = species
+
+    @property
+    def species(self):
+        return self._species
+
+    @species.setter
+    def species(self, value):
+        if not isinstance(value, Species):
+            raise TypeError("species must be of type festim.Species")
+        self._species = value
+
+    def create_expr_fenics(self, mesh, temperature, function_space):
+        self._create(mesh, temperature)
+
+
+class InitialTemperature(InitialConditionBase):
+    """``initial_condition.py:144-203``."""
+
+    def create_expr_fenics(self, mesh, function_space):
+        self._create(mesh)
