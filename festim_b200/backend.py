@@ -1,0 +1,425 @@
+"""ctypes binding of ``libfestim_b200.so`` and the solver object that sits at the
+``create_solver`` seam (reference ``src/festim/problem.py:170-193``).
+
+``B200NewtonSolver`` exposes exactly what the reference time loop uses from
+``dolfinx.fem.petsc.NonlinearProblem``: ``solve()``, ``solver
+.getConvergedReason()``, ``solver.getIterationNumber()``, writable ``rtol`` /
+``atol``.  PyTorch provides device buffers and the stream only.  There is no
+CPU fallback: a missing library or GPU raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+
+import numpy as np
+
+from festim_b200 import fem
+from festim_b200.lowering import KernelSpec
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfestim_b200.so")
+
+FB_ASSEMBLE_F, FB_ASSEMBLE_J = 1, 2
+KSP = {"auto": 0, "preonly": 0, "cg": 1, "gmres": 2, "fgmres": 2, "tridiag": 3}
+PC = {"jacobi": 0, "bjacobi": 0, "pbjacobi": 0, "lu": 0, "chebyshev": 1}
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+
+
+def load_library():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make` or `python -c 'import "
+            "__graft_entry__ as g; g.build()'`. festim_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i, i64, d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    sig = {
+        "fb_create": (i, [i, vp, C.POINTER(vp)]),
+        "fb_destroy": (None, [vp]),
+        "fb_last_error": (C.c_char_p, [vp]),
+        "fb_launch_count": (i64, [vp]),
+        "fb_set_mesh": (i, [vp, i, i64, i64, _f64p, _i32p, _i32p, i64, _i32p, _i32p, _i32p]),
+        "fb_set_pattern": (i, [vp, _i32p, _i32p, i64, _i32p, _i32p]),
+        "fb_set_spec": (i, [vp, vp, C.c_size_t]),
+        "fb_set_dirichlet": (i, [vp, i64, _i64p]),
+        "fb_num_dofs": (i64, [vp]),
+        "fb_jacobian_nnz": (i64, [vp]),
+        "fb_set_scalars": (i, [vp, i, _f64p]),
+        "fb_set_temperature": (i, [vp, d, vp]),
+        "fb_set_field": (i, [vp, i, vp]),
+        "fb_set_velocity": (i, [vp, i, vp]),
+        "fb_set_dirichlet_values": (i, [vp, vp]),
+        "fb_update_load": (i, [vp]),
+        "fb_assemble": (i, [vp, vp, vp, vp, vp, i]),
+        "fb_spmv": (i, [vp, vp, vp, vp]),
+        "fb_dot": (i, [vp, vp, vp, _f64p]),
+        "fb_axpy": (i, [vp, d, vp, vp]),
+        "fb_linear_solve": (i, [vp, vp, vp, vp, i, i, d, d, i, C.POINTER(i), _f64p]),
+        "fb_newton_solve": (i, [vp, vp, vp, d, d, d, i, i, i, d, i, C.POINTER(i), C.POINTER(i),
+                                _f64p, C.POINTER(i)]),
+        "fb_last_timings": (i, [vp, _f64p]),
+        "fb_stepsize_modify": (d, [d, i, d, i, d, d, i, d, i, _f64p, d]),
+        "fb_total_volume": (i, [vp, vp, i, i, _f64p]),
+        "fb_total_surface": (i, [vp, vp, i, i, _f64p]),
+        "fb_surface_flux": (i, [vp, vp, i, i, d, vp, _f64p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "fb_create", "fb_destroy", "fb_last_error", "fb_launch_count", "fb_set_mesh", "fb_set_pattern",
+    "fb_set_spec", "fb_set_dirichlet", "fb_num_dofs", "fb_jacobian_nnz", "fb_set_scalars",
+    "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
+    "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
+    "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
+    "fb_total_surface", "fb_surface_flux",
+]
+
+
+def _np_ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Context:
+    """Owns an ``fb_ctx`` and the torch device buffers handed to it."""
+
+    def __init__(self, spec: KernelSpec, device=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("festim_b200 needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.lib = load_library()
+        self.spec = spec
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.h = C.c_void_p()
+        rc = self.lib.fb_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(self.h))
+        if rc:
+            raise RuntimeError(f"fb_create failed with status {rc}")
+        self._keep = {}
+        mesh = spec.mesh
+        coords = np.ascontiguousarray(mesh.coords, dtype=np.float64)
+        cells = np.ascontiguousarray(mesh.cells, dtype=np.int32)
+        bf = np.ascontiguousarray(mesh.bfacets, dtype=np.int32)
+        bfc = np.ascontiguousarray(mesh.bfacet_cell, dtype=np.int32)
+        self._check(self.lib.fb_set_mesh(
+            self.h, mesh.tdim, mesh.num_vertices, mesh.num_cells, _np_ptr(coords, C.c_double),
+            _np_ptr(cells, C.c_int32), _np_ptr(spec.cell_tag, C.c_int32), bf.shape[0],
+            _np_ptr(bf, C.c_int32), _np_ptr(bfc, C.c_int32), _np_ptr(spec.bfacet_tag, C.c_int32)))
+        rowptr, colidx = mesh.graph
+        v2c_ptr, v2c_idx = mesh.vertex_to_cell
+        self._check(self.lib.fb_set_pattern(
+            self.h, _np_ptr(rowptr, C.c_int32), _np_ptr(colidx, C.c_int32), len(colidx),
+            _np_ptr(v2c_ptr, C.c_int32), _np_ptr(v2c_idx, C.c_int32)))
+        blob = spec.blob()
+        self._check(self.lib.fb_set_spec(self.h, blob, len(blob)))
+        self.n_dofs = int(self.lib.fb_num_dofs(self.h))
+        self.nnz = int(self.lib.fb_jacobian_nnz(self.h))
+        self.nv = mesh.num_vertices
+
+    def _check(self, rc):
+        if rc < 0:
+            msg = self.lib.fb_last_error(self.h)
+            raise RuntimeError(f"libfestim_b200: {msg.decode() if msg else rc}")
+        return rc
+
+    def close(self):
+        if self.h:
+            self.lib.fb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- buffers ---------------------------------------------------------------
+    def zeros(self, n):
+        return self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+
+    def to_device(self, name, host_array):
+        """Copy a host array into a persistent device tensor (pinned staging)."""
+        torch = self.torch
+        arr = np.ascontiguousarray(host_array, dtype=np.float64).ravel()
+        slot = self._keep.get(name)
+        if slot is None or slot[0].numel() != arr.size:
+            pinned = torch.empty(arr.size, dtype=torch.float64).pin_memory()
+            dev = torch.empty(arr.size, dtype=torch.float64, device=self.device)
+            slot = self._keep[name] = (dev, pinned)
+        dev, pinned = slot
+        pinned.numpy()[:] = arr
+        dev.copy_(pinned, non_blocking=True)
+        return dev
+
+    @staticmethod
+    def ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    @property
+    def launches(self):
+        return int(self.lib.fb_launch_count(self.h))
+
+
+class _Snes:
+    def __init__(self):
+        self.reason = 0
+        self.its = 0
+        self.linear_its = 0
+        self.fnorm = 0.0
+
+    def getConvergedReason(self):
+        return self.reason
+
+    def getIterationNumber(self):
+        return self.its
+
+    def getLinearSolveIterations(self):
+        return self.linear_its
+
+    def getFunctionNorm(self):
+        return self.fnorm
+
+
+class B200NewtonSolver:
+    def __init__(self, problem, petsc_options, device=0):
+        self.problem = problem
+        self.spec = KernelSpec(problem)
+        self.ctx = Context(self.spec, device)
+        self.atol = petsc_options["snes_atol"]
+        self.rtol = petsc_options["snes_rtol"]
+        self.stol = float(petsc_options["snes_stol"])
+        self.max_it = int(petsc_options["snes_max_it"])
+        ksp = str(petsc_options.get("ksp_type", "preonly")).lower()
+        pc = str(petsc_options.get("pc_type", "lu")).lower()
+        known = {"snes_type", "snes_linesearch_type", "snes_stol", "snes_divergence_tolerance",
+                 "ksp_type", "pc_type", "pc_factor_mat_solver_type", "snes_error_if_not_converged",
+                 "ksp_error_if_not_converged", "snes_atol", "snes_rtol", "snes_max_it",
+                 "ksp_rtol", "ksp_max_it", "ksp_atol"}
+        for key in petsc_options:
+            if key not in known:
+                warnings.warn(f"PETSc option {key} is ignored by the B200 backend")
+        if ksp not in KSP:
+            warnings.warn(f"ksp_type {ksp} is not implemented, using gmres")
+            ksp = "gmres"
+        self.ksp = KSP[ksp]
+        self.pc = PC.get(pc, 0)
+        # the reference's default is an exact LU solve: use a Krylov tolerance far
+        # below the Newton tolerance so Newton iteration counts are unchanged
+        self.ksp_rtol = float(petsc_options.get("ksp_rtol", 1e-12 if ksp == "preonly" else 1e-10))
+        self.ksp_max_it = int(petsc_options.get("ksp_max_it", 20000))
+        self.solver = _Snes()
+        self.timings = np.zeros(4)
+        self._D_T = None
+        self._D_T_dev = None
+
+        ctx, spec = self.ctx, self.spec
+        # Dirichlet dofs (fixed), later BCs win on shared dofs
+        self._bc_forms = list(problem.bc_forms)
+        dofs = np.concatenate([bc.dofs for bc in self._bc_forms]) if self._bc_forms else \
+            np.zeros(0, dtype=np.int64)
+        uniq, first_rev = np.unique(dofs[::-1], return_index=True)
+        self._bc_pick = len(dofs) - 1 - first_rev
+        self._bc_dofs = np.ascontiguousarray(uniq, dtype=np.int64)
+        ctx._check(ctx.lib.fb_set_dirichlet(ctx.h, len(self._bc_dofs),
+                                            _np_ptr(self._bc_dofs, C.c_int64)))
+        self.u_dev = ctx.zeros(ctx.n_dofs)
+        self.un_dev = ctx.zeros(ctx.n_dofs)
+        self._signature = None
+
+    # -- per-step data -----------------------------------------------------------
+    def _push_state(self):
+        """Upload everything the residual depends on besides u (reference
+        ``update_time_dependent_values``) and refresh the cached coefficients when
+        any of it changed."""
+        ctx, spec, p = self.ctx, self.spec, self.problem
+        lib = ctx.lib
+        scal = spec.scalar_values()
+        parts = [scal.tobytes()]
+        T = spec.temperature
+        Tdev = None
+        if isinstance(T, fem.Function):
+            parts.append(T.x.array.tobytes())
+        elif T is not None:
+            parts.append(np.float64(T.value).tobytes())
+        for f in spec.fields:
+            parts.append(f.x.array.tobytes())
+        for _, _, vel in spec.adv:
+            parts.append(vel.array.tobytes())
+        sig = hash(b"".join(parts))
+        bc_vals = np.concatenate([bc.values() for bc in self._bc_forms])[self._bc_pick] \
+            if self._bc_forms else np.zeros(0)
+        bc_dev = ctx.to_device("bc_vals", bc_vals) if len(bc_vals) else None
+        ctx._check(lib.fb_set_dirichlet_values(ctx.h, ctx.ptr(bc_dev)))
+        if sig == self._signature:
+            return
+        self._signature = sig
+        ctx._check(lib.fb_set_scalars(ctx.h, len(scal), _np_ptr(scal, C.c_double)))
+        if isinstance(T, fem.Function):
+            Tdev = ctx.to_device("T", T.x.array)
+            ctx._check(lib.fb_set_temperature(ctx.h, 0.0, ctx.ptr(Tdev)))
+        elif T is not None:
+            ctx._check(lib.fb_set_temperature(ctx.h, float(T.value), C.c_void_p()))
+        for k, f in enumerate(spec.fields):
+            ctx._check(lib.fb_set_field(ctx.h, k, ctx.ptr(ctx.to_device(f"field{k}", f.x.array))))
+        for k, (_, _, vel) in enumerate(spec.adv):
+            ctx._check(lib.fb_set_velocity(ctx.h, k, ctx.ptr(ctx.to_device(f"vel{k}", vel.array))))
+        ctx._check(lib.fb_update_load(ctx.h))
+
+    def solve(self):
+        ctx, p = self.ctx, self.problem
+        self._push_state()
+        u_dev = ctx.to_device("u", p.u.x.array)
+        un_dev = ctx.to_device("u_n", p.u_n.x.array) if self.spec.transient else u_dev
+        t = float(p.t) if hasattr(p, "t") else 0.0
+        atol = self.atol(t) if callable(self.atol) else self.atol
+        rtol = self.rtol(t) if callable(self.rtol) else self.rtol
+        n_its, reason, lin = C.c_int(0), C.c_int(0), C.c_int(0)
+        fnorm = C.c_double(0.0)
+        rc = ctx.lib.fb_newton_solve(
+            ctx.h, ctx.ptr(u_dev), ctx.ptr(un_dev), float(atol), float(rtol), self.stol,
+            self.max_it, self.ksp, self.pc, self.ksp_rtol, self.ksp_max_it,
+            C.byref(n_its), C.byref(reason), C.byref(fnorm), C.byref(lin))
+        ctx._check(rc)
+        self.u_dev = u_dev
+        p.u.x.array[:] = u_dev.cpu().numpy()
+        self.solver.its = n_its.value
+        self.solver.reason = reason.value
+        self.solver.linear_its = lin.value
+        self.solver.fnorm = fnorm.value
+        tm = (C.c_double * 4)()
+        ctx.lib.fb_last_timings(ctx.h, tm)
+        self.timings = np.array(list(tm))
+        return n_its.value
+
+    # -- low-level access used by the parity tests and the benchmark -----------------
+    def jacobian_index(self):
+        """(rows, cols) of every stored Jacobian scalar, in storage order (the
+        layout documented in include/festim_b200.h)."""
+        spec = self.spec
+        rowptr, colidx = spec.mesh.graph
+        ns, npairs = spec.ns, spec.npairs
+        deg = np.diff(rowptr).astype(np.int64)
+        rows, cols = [], []
+        r0 = rowptr[:-1].astype(np.int64)
+        nv = len(deg)
+        # per vertex block: for s: for k: for j
+        for s in range(ns):
+            nc = int(spec.pair_nc[s])
+            cs = spec.pair_cs[spec.pair_pp[s]: spec.pair_pp[s + 1]].astype(np.int64)
+            # entries of (v, s): deg[v] * nc
+            cnt = deg * nc
+            start = r0 * npairs + deg * int(spec.pair_pp[s])
+            v_of = np.repeat(np.arange(nv, dtype=np.int64), cnt)
+            e = np.arange(cnt.sum(), dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+            k = e // nc
+            j = e - k * nc
+            pos = np.repeat(start, cnt) + e
+            rows.append((pos, v_of * ns + s, colidx[np.repeat(r0, cnt) + k].astype(np.int64) * ns + cs[j]))
+        pos = np.concatenate([r[0] for r in rows])
+        order = np.argsort(pos)
+        R = np.concatenate([r[1] for r in rows])[order]
+        Cc = np.concatenate([r[2] for r in rows])[order]
+        return R, Cc
+
+    def assemble_host(self, want_J=True):
+        """Assemble F (and J as scipy CSR) at the problem's current u, u_n."""
+        import scipy.sparse as sp
+
+        ctx, p = self.ctx, self.problem
+        self._push_state()
+        u_dev = ctx.to_device("u", p.u.x.array)
+        un_dev = ctx.to_device("u_n", p.u_n.x.array) if self.spec.transient else u_dev
+        F = ctx.zeros(ctx.n_dofs)
+        J = ctx.zeros(ctx.nnz) if want_J else None
+        flags = FB_ASSEMBLE_F | (FB_ASSEMBLE_J if want_J else 0)
+        ctx._check(ctx.lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(un_dev), ctx.ptr(F),
+                                       ctx.ptr(J), flags))
+        Fh = F.cpu().numpy()
+        if not want_J:
+            return Fh, None
+        R, Cc = self.jacobian_index()
+        Jh = sp.csr_matrix((J.cpu().numpy(), (R, Cc)), shape=(ctx.n_dofs, ctx.n_dofs))
+        return Fh, Jh
+
+    # -- derived quantities (device reductions) -------------------------------------
+    def set_D_global_temperature(self, T):
+        self._D_T = T
+        self._D_T_dev = None
+
+    def _current_u(self):
+        return self.ctx.to_device("u", self.problem.u.x.array)
+
+    def total_volume(self, species_index, vol_id):
+        out = C.c_double(0.0)
+        ctx = self.ctx
+        ctx._check(ctx.lib.fb_total_volume(ctx.h, ctx.ptr(self._current_u()), species_index,
+                                           self.spec.vol_ids.index(vol_id), C.byref(out)))
+        return out.value
+
+    def total_surface(self, species_index, surf_id):
+        out = C.c_double(0.0)
+        ctx = self.ctx
+        ctx._check(ctx.lib.fb_total_surface(ctx.h, ctx.ptr(self._current_u()), species_index,
+                                            self.spec.surf_ids.index(surf_id), C.byref(out)))
+        return out.value
+
+    def surface_flux(self, species_index, surf_id):
+        out = C.c_double(0.0)
+        ctx = self.ctx
+        Tn, Tc = C.c_void_p(), 0.0
+        if isinstance(self._D_T, np.ndarray):
+            if self._D_T_dev is None:
+                self._D_T_dev = ctx.to_device("D_T", self._D_T)
+            Tn = ctx.ptr(self._D_T_dev)
+        else:
+            Tc = float(self._D_T)
+        ctx._check(ctx.lib.fb_surface_flux(ctx.h, ctx.ptr(self._current_u()), species_index,
+                                           self.spec.surf_ids.index(surf_id), Tc, Tn, C.byref(out)))
+        return out.value
+
+    def measure_volume(self, vol_id):
+        mesh = self.spec.mesh
+        cells = self.problem.volume_meshtags.find(vol_id)
+        x = mesh.coords[mesh.cells[cells]]
+        J = x[:, 1:, :] - x[:, :1, :]
+        fact = {1: 1.0, 2: 2.0, 3: 6.0}[mesh.tdim]
+        return float(np.sum(np.abs(np.linalg.det(J))) / fact)
+
+    def measure_surface(self, surf_id):
+        mesh = self.spec.mesh
+        fv = mesh.bfacets[self.problem.facet_meshtags.find(surf_id)]
+        x = mesh.coords[fv]
+        if mesh.tdim == 1:
+            return float(len(fv))
+        if mesh.tdim == 2:
+            return float(np.linalg.norm(x[:, 1] - x[:, 0], axis=1).sum())
+        return float(0.5 * np.linalg.norm(np.cross(x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]), axis=1).sum())
+
+
+class B200Backend:
+    def __init__(self, device=0):
+        self.device = device
+
+    def create_newton_solver(self, problem, petsc_options):
+        solver = B200NewtonSolver(problem, petsc_options, self.device)
+        if getattr(problem, "_D_global_T", None) is not None:
+            solver.set_D_global_temperature(problem._D_global_T)
+        return solver

@@ -1,0 +1,266 @@
+// C ABI of libfestim_b200.so: context lifetime, problem definition, per-step data.
+// See include/festim_b200.h for the contract and INTEGRATION.md for the binding.
+#include <cmath>
+#include <cstring>
+
+#include "fb_internal.cuh"
+
+// spec section ids / int slots, shared with festim_b200/lowering.py
+enum {
+  S_INTS = 1, S_DIFF_D0, S_DIFF_SLOT, S_DIFF_ENERGIES, S_MASS_DT, S_MASS_C, S_PAIR_NC, S_PAIR_PP,
+  S_PAIR_CS, S_PAIR_IDX, S_PROG_OPS, S_PROG_IARGS, S_PROG_FARGS, S_PROG_OFFSETS, S_VTERM_HDR,
+  S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
+  S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_MAX
+};
+enum {
+  I_TDIM = 0, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
+  I_NVTERMS, I_NFTERMS, I_NADV, I_NPAIRS, I_NDIFFE, I_DT_SCALAR, I_NSLOTS
+};
+static const long long FB_MAGIC = 0xFB2000001LL;
+
+extern "C" int fb_create(int device, void* cuda_stream, fb_ctx** out) {
+  if (!out) return -1;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return -3;  // no GPU: fail loudly
+  if (device < 0 || device >= count) return -3;
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  fb_ctx* ctx = new fb_ctx();
+  ctx->device = device;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void fb_destroy(fb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->owned) cudaFree(p);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+  delete ctx;
+}
+
+extern "C" const char* fb_last_error(fb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t fb_launch_count(fb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t fb_num_dofs(fb_ctx* ctx) { return ctx ? ctx->S.n_dofs : 0; }
+extern "C" int64_t fb_jacobian_nnz(fb_ctx* ctx) { return ctx ? ctx->nnzb * ctx->S.npairs : 0; }
+
+extern "C" int fb_set_mesh(fb_ctx* ctx, int tdim, int64_t nv, int64_t nc, const double* coords,
+                           const int32_t* cells, const int32_t* cell_tag, int64_t nf,
+                           const int32_t* bfacets, const int32_t* bfacet_cell,
+                           const int32_t* bfacet_tag) {
+  if (!ctx) return -1;
+  if (tdim < 1 || tdim > 3) return fb_fail(ctx, "tdim must be 1, 2 or 3");
+  if (nv <= 0 || nc <= 0) return fb_fail(ctx, "empty mesh");
+  if (nv * (long long)FB_MAX_NS >= (1LL << 31)) return fb_fail(ctx, "mesh too large for int32 local indices");
+  cudaSetDevice(ctx->device);
+  DevSpec& S = ctx->S;
+  S.tdim = tdim; S.n_vertices = nv; S.n_cells = nc; S.n_bfacets = nf;
+  int rc;
+  if ((rc = fb_upload(ctx, &S.coords, coords, (size_t)nv * tdim))) return rc;
+  if ((rc = fb_upload(ctx, &S.cells, cells, (size_t)nc * (tdim + 1)))) return rc;
+  if ((rc = fb_upload(ctx, &S.cell_tag, cell_tag, (size_t)nc))) return rc;
+  if ((rc = fb_upload(ctx, &S.bfacets, bfacets, (size_t)nf * tdim))) return rc;
+  if ((rc = fb_upload(ctx, &S.bfacet_cell, bfacet_cell, (size_t)nf))) return rc;
+  if ((rc = fb_upload(ctx, &S.bfacet_tag, bfacet_tag, (size_t)nf))) return rc;
+  ctx->have_mesh = true;
+  return 0;
+}
+
+extern "C" int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, int64_t nnzb,
+                              const int32_t* v2c_ptr, const int32_t* v2c_idx) {
+  if (!ctx || !ctx->have_mesh) return ctx ? fb_fail(ctx, "fb_set_mesh first") : -1;
+  cudaSetDevice(ctx->device);
+  DevSpec& S = ctx->S;
+  int rc;
+  if ((rc = fb_upload(ctx, &S.rowptr, rowptr, (size_t)S.n_vertices + 1))) return rc;
+  if ((rc = fb_upload(ctx, &S.colidx, colidx, (size_t)nnzb))) return rc;
+  if ((rc = fb_upload(ctx, &S.v2c_ptr, v2c_ptr, (size_t)S.n_vertices + 1))) return rc;
+  if ((rc = fb_upload(ctx, &S.v2c_idx, v2c_idx, (size_t)S.n_cells * (S.tdim + 1)))) return rc;
+  ctx->nnzb = nnzb;
+  // block-tridiagonal in index order?  (1D meshes ordered along x)
+  bool tri = true;
+  for (long long v = 0; v < S.n_vertices && tri; ++v)
+    for (int k = rowptr[v]; k < rowptr[v + 1]; ++k)
+      if (std::llabs((long long)colidx[k] - v) > 1) { tri = false; break; }
+  ctx->tridiag = tri;
+  ctx->have_pattern = true;
+  return 0;
+}
+
+namespace {
+struct Section { long long id, code, count, offset; };
+
+template <typename T>
+int upload_section(fb_ctx* ctx, const char* blob, size_t nbytes, const Section* secs, int id, int code,
+                   const T** dst, long long* count_out = nullptr) {
+  const Section& s = secs[id];
+  if (s.id != id) { *dst = nullptr; if (count_out) *count_out = 0; return fb_upload(ctx, dst, (const T*)nullptr, 0); }
+  if (s.code != code) return fb_fail(ctx, "spec section has the wrong dtype");
+  if ((size_t)(s.offset + s.count * (long long)sizeof(T)) > nbytes) return fb_fail(ctx, "spec section out of bounds");
+  if (count_out) *count_out = s.count;
+  return fb_upload(ctx, dst, (const T*)(blob + s.offset), (size_t)s.count);
+}
+}  // namespace
+
+extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
+  if (!ctx || !ctx->have_pattern) return ctx ? fb_fail(ctx, "fb_set_pattern first") : -1;
+  cudaSetDevice(ctx->device);
+  const char* blob = (const char*)blob_;
+  if (nbytes < 16) return fb_fail(ctx, "spec blob too small");
+  long long hdr[2];
+  memcpy(hdr, blob, 16);
+  if (hdr[0] != FB_MAGIC) return fb_fail(ctx, "bad spec magic");
+  const long long nsec = hdr[1];
+  if (nsec < 1 || nsec > 64 || (size_t)(16 + nsec * 32) > nbytes) return fb_fail(ctx, "bad spec header");
+  Section secs[S_MAX];
+  for (int i = 0; i < S_MAX; ++i) secs[i] = Section{0, 0, 0, 0};
+  for (long long i = 0; i < nsec; ++i) {
+    Section s;
+    memcpy(&s, blob + 16 + i * 32, 32);
+    if (s.id <= 0 || s.id >= S_MAX) return fb_fail(ctx, "unknown spec section");
+    secs[s.id] = s;
+  }
+  if (secs[S_INTS].id != S_INTS || secs[S_INTS].count < 16) return fb_fail(ctx, "spec has no int table");
+  int ints[16];
+  memcpy(ints, blob + secs[S_INTS].offset, sizeof(ints));
+  DevSpec& S = ctx->S;
+  if (ints[I_TDIM] != S.tdim) return fb_fail(ctx, "spec tdim differs from the mesh");
+  S.ns = ints[I_NS];
+  if (S.ns < 1 || S.ns > FB_MAX_NS) return fb_fail(ctx, "unsupported number of species");
+  S.n_vtags = ints[I_NVTAGS]; S.n_stags = ints[I_NSTAGS];
+  S.transient = ints[I_TRANSIENT]; S.T_mode = ints[I_TMODE];
+  S.n_vterms = ints[I_NVTERMS]; S.n_fterms = ints[I_NFTERMS]; S.n_adv = ints[I_NADV];
+  S.npairs = ints[I_NPAIRS]; S.n_diffE = ints[I_NDIFFE]; S.n_slots = ints[I_NSLOTS];
+  S.n_fields = ints[I_NFIELDS];
+  ctx->dt_scalar = ints[I_DT_SCALAR];
+  S.n_dofs = S.n_vertices * S.ns;
+  const int n_scalars = ints[I_NSCALARS];
+  int rc;
+#define UP(id, code, field) if ((rc = upload_section(ctx, blob, nbytes, secs, id, code, &S.field))) return rc
+  UP(S_DIFF_D0, 1, diff_D0); UP(S_DIFF_SLOT, 0, diff_slot); UP(S_DIFF_ENERGIES, 1, diff_energies);
+  UP(S_DIFF_PROGS, 0, diff_progs); UP(S_MASS_DT, 1, mass_dt); UP(S_MASS_C, 1, mass_c);
+  UP(S_PAIR_NC, 0, pair_nc); UP(S_PAIR_PP, 0, pair_pp); UP(S_PAIR_CS, 0, pair_cs); UP(S_PAIR_IDX, 0, pair_idx);
+  UP(S_PROG_OPS, 0, prog_ops); UP(S_PROG_IARGS, 0, prog_iargs); UP(S_PROG_FARGS, 1, prog_fargs);
+  UP(S_PROG_OFFSETS, 0, prog_offsets);
+  UP(S_VTERM_HDR, 0, vterm_hdr); UP(S_FTERM_HDR, 0, fterm_hdr);
+  UP(S_ROW_SPECIES, 0, row_species); UP(S_ROW_COEF, 1, row_coef);
+  UP(S_DERIV_SPECIES, 0, deriv_species); UP(S_DERIV_PROG, 0, deriv_prog);
+  UP(S_QUAD_V, 0, quad_v); UP(S_QUAD_S, 0, quad_s); UP(S_QUAD_BARY, 1, quad_bary); UP(S_QUAD_W, 1, quad_w);
+  UP(S_ADV, 0, adv);
+#undef UP
+  // mutable per-step buffers
+  if ((rc = fb_alloc(ctx, &ctx->d_scalars, (size_t)n_scalars + 1))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_fields, (size_t)S.n_fields + 1))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_velocities, (size_t)S.n_adv + 1))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_bc_map, (size_t)S.n_dofs))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_dbar, (size_t)2 * (S.n_slots ? S.n_slots : 1) * S.n_cells))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_load, (size_t)S.n_dofs))) return rc;
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_bc_map, 0xFF, sizeof(int) * S.n_dofs, ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_load, 0, sizeof(double) * S.n_dofs, ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * (n_scalars + 1), ctx->stream));
+  ctx->h_fields.assign(S.n_fields + 1, nullptr);
+  ctx->h_velocities.assign(S.n_adv + 1, nullptr);
+  S.scalars = ctx->d_scalars; S.fields = ctx->d_fields; S.velocities = ctx->d_velocities;
+  S.bc_map = ctx->d_bc_map; S.bc_vals = nullptr; S.dbar = ctx->d_dbar; S.load = ctx->d_load;
+  S.T_const = 300.0; S.T_nodal = nullptr; S.inv_dt = 0.0;
+  ctx->have_spec = true;
+  return 0;
+}
+
+__global__ void k_fill_bc_map(long long n, const long long* __restrict__ dofs, int* __restrict__ map) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) map[dofs[i]] = (int)i;
+}
+
+extern "C" int fb_set_dirichlet(fb_ctx* ctx, int64_t n_bc, const int64_t* bc_dofs) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  DevSpec& S = ctx->S;
+  for (int64_t i = 0; i < n_bc; ++i)
+    if (bc_dofs[i] < 0 || bc_dofs[i] >= S.n_dofs) return fb_fail(ctx, "Dirichlet dof out of range");
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_bc_map, 0xFF, sizeof(int) * S.n_dofs, ctx->stream));
+  ctx->n_bc = n_bc;
+  if (n_bc == 0) return 0;
+  const long long* d = nullptr;
+  int rc = fb_upload(ctx, &d, (const long long*)bc_dofs, (size_t)n_bc);
+  if (rc) return rc;
+  FB_LAUNCH(ctx, k_fill_bc_map, (unsigned)((n_bc + 255) / 256), 256, 0, (long long)n_bc, d, ctx->d_bc_map);
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fb_set_scalars(fb_ctx* ctx, int n, const double* scalars) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  if (n > 0) {
+    FB_CHECK(ctx, cudaMemcpyAsync(ctx->d_scalars, scalars, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // scalars is caller stack/heap memory
+  }
+  if (ctx->dt_scalar >= 0 && ctx->dt_scalar < n) ctx->S.inv_dt = 1.0 / scalars[ctx->dt_scalar];
+  return 0;
+}
+
+extern "C" int fb_set_temperature(fb_ctx* ctx, double T_const, const double* T_nodal) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  if (ctx->S.T_mode && !T_nodal) return fb_fail(ctx, "spec expects a nodal temperature");
+  ctx->S.T_const = T_const;
+  ctx->S.T_nodal = T_nodal;
+  return 0;
+}
+
+static int push_ptrs(fb_ctx* ctx, const double** dev, const std::vector<const double*>& host) {
+  FB_CHECK(ctx, cudaMemcpyAsync(dev, host.data(), sizeof(double*) * host.size(), cudaMemcpyHostToDevice, ctx->stream));
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fb_set_field(fb_ctx* ctx, int k, const double* nodal) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  if (k < 0 || k >= ctx->S.n_fields) return fb_fail(ctx, "field index out of range");
+  ctx->h_fields[k] = nodal;
+  return push_ptrs(ctx, ctx->d_fields, ctx->h_fields);
+}
+
+extern "C" int fb_set_velocity(fb_ctx* ctx, int k, const double* nodal) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  if (k < 0 || k >= ctx->S.n_adv) return fb_fail(ctx, "velocity index out of range");
+  ctx->h_velocities[k] = nodal;
+  return push_ptrs(ctx, ctx->d_velocities, ctx->h_velocities);
+}
+
+extern "C" int fb_set_dirichlet_values(fb_ctx* ctx, const double* bc_vals) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  ctx->S.bc_vals = bc_vals;
+  return 0;
+}
+
+extern "C" int fb_update_load(fb_ctx* ctx) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  return fbi_update_coeffs(ctx);
+}
+
+extern "C" int fb_assemble(fb_ctx* ctx, const double* u, const double* u_n, double* F, double* Jvals,
+                           int flags) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  if (ctx->n_bc > 0 && !ctx->S.bc_vals) return fb_fail(ctx, "Dirichlet values not set");
+  return fbi_assemble(ctx, u, u_n, F, Jvals, flags);
+}
+
+extern "C" int fb_spmv(fb_ctx* ctx, const double* Jvals, const double* x, double* y) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  return fbi_spmv(ctx, Jvals, x, y);
+}
+
+extern "C" int fb_linear_solve(fb_ctx* ctx, const double* Jvals, const double* b, double* y, int ksp,
+                               int pc, double rtol, double atol, int max_it, int* iters, double* relres) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  return fbi_linear_solve(ctx, Jvals, b, y, ksp, pc, rtol, atol, max_it, iters, relres);
+}

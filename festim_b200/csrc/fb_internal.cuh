@@ -1,0 +1,166 @@
+// Internal declarations of libfestim_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/festim_b200.h"
+
+#define FB_MAX_NS 16
+#define FB_MAX_D1 4
+#define FB_KB 8.6173303e-5  // Boltzmann constant eV/K, reference src/festim/__init__.py:11
+#define FB_STACK 24
+
+// Everything a kernel needs, passed by value (lives in the constant bank).
+struct DevSpec {
+  int tdim, ns, n_vtags, n_stags, transient, T_mode, npairs, n_slots, n_diffE;
+  int n_vterms, n_fterms, n_adv, n_fields;
+  long long n_vertices, n_cells, n_bfacets, n_dofs;
+  // mesh + pattern
+  const double* coords;
+  const int* cells;
+  const int* cell_tag;
+  const int* bfacets;
+  const int* bfacet_cell;
+  const int* bfacet_tag;
+  const int* rowptr;
+  const int* colidx;
+  const int* v2c_ptr;
+  const int* v2c_idx;
+  // tables (spec)
+  const double* diff_D0;      // [n_vtags*ns]
+  const int* diff_slot;       // [n_vtags*ns] index into cell-coefficient slots, -1 none
+  const double* diff_energies;  // [n_diffE]
+  const int* diff_progs;      // [n_slots-n_diffE] program ids of generic diffusivities
+  const double* mass_dt;      // [n_vtags*ns]
+  const double* mass_c;
+  const int* pair_nc;         // [ns]
+  const int* pair_pp;         // [ns+1]
+  const int* pair_cs;         // [npairs]
+  const int* pair_idx;        // [ns*ns]
+  const int* prog_ops;
+  const int* prog_iargs;
+  const double* prog_fargs;
+  const int* prog_offsets;
+  const int* vterm_hdr;       // [n_vterms*8] tag, value_prog, rows_off, n_rows, derivs_off, n_derivs, u_dep
+  const int* fterm_hdr;
+  const int* row_species;
+  const double* row_coef;
+  const int* deriv_species;
+  const int* deriv_prog;
+  const int* quad_v;          // [n_vtags*4] offF, nqF, offJ, nqJ
+  const int* quad_s;
+  const double* quad_bary;
+  const double* quad_w;
+  const int* adv;             // [n_adv*2] tag, species
+  // per-step data
+  const double* scalars;
+  double T_const;
+  const double* T_nodal;
+  const double* const* fields;      // device array of device pointers
+  const double* const* velocities;
+  const int* bc_map;          // [n_dofs] index into bc_vals or -1
+  const double* bc_vals;
+  const double* dbar;         // [2][n_slots][n_cells] cell means of diffusivity factors
+  const double* load;         // [n_dofs] solution-independent part of the residual
+  double inv_dt;
+};
+
+struct fb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  int sm_count = 148;
+  DevSpec S{};
+  bool have_mesh = false, have_pattern = false, have_spec = false;
+  long long nnzb = 0, n_bc = 0;
+  bool tridiag = false;
+  int dt_scalar = -1;
+  std::vector<void*> owned;  // device allocations freed in fb_destroy
+  // mutable device buffers
+  double* d_scalars = nullptr;
+  const double** d_fields = nullptr;
+  const double** d_velocities = nullptr;
+  int* d_bc_map = nullptr;
+  double* d_dbar = nullptr;
+  double* d_load = nullptr;
+  std::vector<const double*> h_fields, h_velocities;
+  // solver workspace
+  double* d_F = nullptr;
+  double* d_J = nullptr;
+  double* d_y = nullptr;
+  double* d_work = nullptr;  // Krylov vectors
+  long long work_doubles = 0;
+  double* d_dinv = nullptr;  // block-Jacobi inverse blocks [n_vertices][ns][ns]
+  double* d_red = nullptr;   // reduction partials
+  long long red_doubles = 0;
+  double* d_sc = nullptr;    // device scalars of the Krylov loops
+  unsigned* d_ticket = nullptr;
+  int* d_flags = nullptr;    // done flag, iteration counter
+  double* h_pinned = nullptr;
+  double* d_tri = nullptr;   // dense block-tridiagonal workspace
+  double timings[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[8];
+};
+
+#define FB_CHECK(ctx, call)                                                                 \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return -2;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+#define FB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                      \
+  do {                                                                                      \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
+    (ctx)->launches++;                                                                      \
+  } while (0)
+
+static inline int fb_fail(fb_ctx* ctx, const char* msg) {
+  ctx->err = msg;
+  return -1;
+}
+
+template <typename T>
+int fb_alloc(fb_ctx* ctx, T** ptr, size_t count) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  ctx->owned.push_back(p);
+  *ptr = (T*)p;
+  return 0;
+}
+
+template <typename T>
+int fb_upload(fb_ctx* ctx, const T** dst, const T* host, size_t count) {
+  T* p = nullptr;
+  int rc = fb_alloc(ctx, &p, count);
+  if (rc) return rc;
+  if (count) {
+    cudaError_t e = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("upload: ") + cudaGetErrorString(e);
+      return -2;
+    }
+  }
+  *dst = p;
+  return 0;
+}
+
+// entry points implemented across translation units
+int fbi_update_coeffs(fb_ctx* ctx);
+int fbi_assemble(fb_ctx* ctx, const double* u, const double* un, double* F, double* J, int flags);
+int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y);
+int fbi_norm2(fb_ctx* ctx, const double* x, double* out_host);
+int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, int ksp, int pc,
+                     double rtol, double atol, int max_it, int* iters, double* relres);
+int fbi_ensure_workspace(fb_ctx* ctx);

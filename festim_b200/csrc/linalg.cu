@@ -1,0 +1,740 @@
+// Linear algebra on the species-sparse BSR Jacobian: SpMV, fused vector kernels
+// with warp-shuffle reductions, point-block Jacobi, single-reduction CG,
+// restarted GMRES (CGS2) and an exact block-tridiagonal solver for 1D meshes.
+//
+// Replaces PETSc KSP/PC/Vec behind SNES (reference src/festim/problem.py:271-289:
+// ksp preonly + pc lu by default).  Scalars of the Krylov recurrences stay on the
+// device: every reduction finishes in the last block of the kernel that produced
+// the partial sums (ticket counter), which also advances the recurrence, so an
+// iteration is two launches for CG and the host only polls a "done" flag.
+#include "fb_internal.cuh"
+
+#include "reduce.cuh"
+
+// ---------------------------------------------------------------------------
+// SpMV: G lanes per scalar row (v, s); values of the row are contiguous
+// ---------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ double spmv_row(const DevSpec& S, const double* __restrict__ J,
+                                           const double* __restrict__ x, long long row, int lane) {
+  const int ns = S.ns;
+  const long long v = row / ns;
+  const int s = (int)(row - v * ns);
+  const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+  const int nc = S.pair_nc[s], pp = S.pair_pp[s];
+  const double* __restrict__ vals = J + (long long)r0 * S.npairs + (long long)deg * pp;
+  const int n = deg * nc;
+  double sum = 0.0;
+  if (nc == 1) {
+    const int cs = S.pair_cs[pp];
+    for (int e = lane; e < n; e += G) sum += vals[e] * x[(long long)S.colidx[r0 + e] * ns + cs];
+  } else {
+    for (int e = lane; e < n; e += G) {
+      const int k = e / nc, j = e - k * nc;
+      sum += vals[e] * x[(long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]];
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  return sum;
+}
+
+template <int G>
+__global__ void __launch_bounds__(FB_TPB)
+k_spmv(DevSpec S, const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  if (row >= S.n_dofs) return;
+  const double sum = spmv_row<G>(S, J, x, row, lane);
+  if (lane == 0) y[row] = sum;
+}
+
+static int spmv_group(const DevSpec& S) {
+  // ~ average row length / 2, power of two
+  const double avg = (double)S.npairs / S.ns * 15.0;
+  (void)avg;
+  const double len = (S.tdim == 1 ? 3.0 : (S.tdim == 2 ? 7.0 : 15.0)) * S.npairs / S.ns;
+  if (len <= 6) return 4;
+  if (len <= 20) return 8;
+  if (len <= 48) return 16;
+  return 32;
+}
+
+int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y) {
+  const DevSpec& S = ctx->S;
+  const int G = spmv_group(S);
+  const long long threads = S.n_dofs * G;
+  const unsigned grid = (unsigned)((threads + FB_TPB - 1) / FB_TPB);
+  switch (G) {
+    case 4: FB_LAUNCH(ctx, k_spmv<4>, grid, FB_TPB, 0, S, J, x, y); break;
+    case 8: FB_LAUNCH(ctx, k_spmv<8>, grid, FB_TPB, 0, S, J, x, y); break;
+    case 16: FB_LAUNCH(ctx, k_spmv<16>, grid, FB_TPB, 0, S, J, x, y); break;
+    default: FB_LAUNCH(ctx, k_spmv<32>, grid, FB_TPB, 0, S, J, x, y); break;
+  }
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// fused vector kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FB_TPB)
+k_dot(long long n, const double* __restrict__ x, const double* __restrict__ y,
+      double* partials, unsigned* ticket, double* out) {
+  double v[1] = {0.0}, tot[1];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    v[0] += x[i] * y[i];
+  if (grid_reduce<1>(v, partials, ticket, tot) && threadIdx.x == 0) out[0] = tot[0];
+}
+
+__global__ void k_axpy(long long n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+
+static unsigned vec_grid(fb_ctx* ctx, long long n) {
+  long long g = (n + FB_TPB - 1) / FB_TPB;
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+static int dot_to_host(fb_ctx* ctx, const double* x, const double* y, double* out) {
+  const DevSpec& S = ctx->S;
+  FB_LAUNCH(ctx, k_dot, vec_grid(ctx, S.n_dofs), FB_TPB, 0, S.n_dofs, x, y, ctx->d_red, ctx->d_ticket,
+            ctx->d_sc + 60);
+  FB_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_sc + 60, sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = ctx->h_pinned[0];
+  return 0;
+}
+
+int fbi_norm2(fb_ctx* ctx, const double* x, double* out) {
+  double d;
+  int rc = dot_to_host(ctx, x, x, &d);
+  if (rc) return rc;
+  *out = sqrt(d);
+  return 0;
+}
+
+extern "C" int fb_dot(fb_ctx* ctx, const double* x, const double* y, double* out) {
+  int rc = fbi_ensure_workspace(ctx);
+  if (rc) return rc;
+  return dot_to_host(ctx, x, y, out);
+}
+
+extern "C" int fb_axpy(fb_ctx* ctx, double a, const double* x, double* y) {
+  FB_LAUNCH(ctx, k_axpy, vec_grid(ctx, ctx->S.n_dofs), FB_TPB, 0, ctx->S.n_dofs, a, x, y);
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// point-block Jacobi: invert the ns x ns diagonal block of every vertex
+// ---------------------------------------------------------------------------
+__global__ void k_bjacobi_setup(DevSpec S, const double* __restrict__ J, double* __restrict__ dinv,
+                                int* __restrict__ flags) {
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= S.n_vertices) return;
+  const int ns = S.ns;
+  const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+  int kself = 0;
+  for (int k = 0; k < deg; ++k)
+    if (S.colidx[r0 + k] == v) kself = k;
+  const long long base = (long long)r0 * S.npairs;
+  if (ns == 1) {
+    const double d = J[base + kself];
+    if (d == 0.0) flags[2] = 1;
+    dinv[v] = 1.0 / d;
+    return;
+  }
+  double A[FB_MAX_NS][FB_MAX_NS], B[FB_MAX_NS][FB_MAX_NS];
+  for (int s = 0; s < ns; ++s)
+    for (int c = 0; c < ns; ++c) {
+      const int jp = S.pair_idx[s * ns + c];
+      A[s][c] = jp < 0 ? 0.0
+                       : J[base + (long long)deg * S.pair_pp[s] + (long long)kself * S.pair_nc[s] + jp];
+      B[s][c] = (s == c) ? 1.0 : 0.0;
+    }
+  // Gauss-Jordan with partial pivoting
+  for (int col = 0; col < ns; ++col) {
+    int piv = col;
+    double best = fabs(A[col][col]);
+    for (int r = col + 1; r < ns; ++r)
+      if (fabs(A[r][col]) > best) { best = fabs(A[r][col]); piv = r; }
+    if (best == 0.0) { flags[2] = 1; best = 1.0; }
+    if (piv != col)
+      for (int c = 0; c < ns; ++c) {
+        double t = A[col][c]; A[col][c] = A[piv][c]; A[piv][c] = t;
+        t = B[col][c]; B[col][c] = B[piv][c]; B[piv][c] = t;
+      }
+    const double ip = 1.0 / A[col][col];
+    for (int c = 0; c < ns; ++c) { A[col][c] *= ip; B[col][c] *= ip; }
+    for (int r = 0; r < ns; ++r) {
+      if (r == col) continue;
+      const double f = A[r][col];
+      if (f == 0.0) continue;
+      for (int c = 0; c < ns; ++c) { A[r][c] -= f * A[col][c]; B[r][c] -= f * B[col][c]; }
+    }
+  }
+  for (int s = 0; s < ns; ++s)
+    for (int c = 0; c < ns; ++c) dinv[(v * ns + s) * ns + c] = B[s][c];
+}
+
+__device__ __forceinline__ void bjacobi_apply(int ns, const double* __restrict__ dinv, long long v,
+                                              const double* rin, double* zout) {
+  if (ns == 1) { zout[0] = dinv[v] * rin[0]; return; }
+  for (int s = 0; s < ns; ++s) {
+    double acc = 0.0;
+    for (int c = 0; c < ns; ++c) acc += dinv[(v * ns + s) * ns + c] * rin[c];
+    zout[s] = acc;
+  }
+}
+
+__global__ void k_precond(DevSpec S, const double* __restrict__ dinv, const double* __restrict__ r,
+                          double* __restrict__ z, const int* __restrict__ flags) {
+  if (flags && flags[0]) return;
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= S.n_vertices) return;
+  double rin[FB_MAX_NS], zo[FB_MAX_NS];
+  for (int s = 0; s < S.ns; ++s) rin[s] = r[v * S.ns + s];
+  bjacobi_apply(S.ns, dinv, v, rin, zo);
+  for (int s = 0; s < S.ns; ++s) z[v * S.ns + s] = zo[s];
+}
+
+// ---------------------------------------------------------------------------
+// CG, Chronopoulos-Gear single-reduction form, block-Jacobi preconditioned.
+//   sc[0]=alpha sc[1]=beta sc[2]=gamma sc[3]=rr sc[4]=threshold^2 sc[5]=rr0
+//   flags[0]=done flags[1]=iterations flags[2]=breakdown
+// ---------------------------------------------------------------------------
+__global__ void k_cg_init(DevSpec S, const double* __restrict__ dinv, const double* __restrict__ b,
+                          double* x, double* r, double* u, double* p, double* s_) {
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= S.n_vertices) return;
+  double rin[FB_MAX_NS], zo[FB_MAX_NS];
+  for (int s = 0; s < S.ns; ++s) {
+    const long long i = v * S.ns + s;
+    rin[s] = b[i];
+    r[i] = rin[s]; x[i] = 0.0; p[i] = 0.0; s_[i] = 0.0;
+  }
+  bjacobi_apply(S.ns, dinv, v, rin, zo);
+  for (int s = 0; s < S.ns; ++s) u[v * S.ns + s] = zo[s];
+}
+
+__global__ void __launch_bounds__(FB_TPB)
+k_cg_update(DevSpec S, const double* __restrict__ dinv, const double* __restrict__ sc,
+            const int* __restrict__ flags, double* __restrict__ x, double* __restrict__ r,
+            double* __restrict__ u, const double* __restrict__ w, double* __restrict__ p,
+            double* __restrict__ s_) {
+  if (flags[0]) return;
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= S.n_vertices) return;
+  const double alpha = sc[0], beta = sc[1];
+  double rin[FB_MAX_NS], zo[FB_MAX_NS];
+  for (int s = 0; s < S.ns; ++s) {
+    const long long i = v * S.ns + s;
+    const double pi = u[i] + beta * p[i];
+    const double si = w[i] + beta * s_[i];
+    p[i] = pi; s_[i] = si;
+    x[i] += alpha * pi;
+    rin[s] = r[i] - alpha * si;
+    r[i] = rin[s];
+  }
+  bjacobi_apply(S.ns, dinv, v, rin, zo);
+  for (int s = 0; s < S.ns; ++s) u[v * S.ns + s] = zo[s];
+}
+
+template <int G>
+__global__ void __launch_bounds__(FB_TPB)
+k_cg_spmv_dots(DevSpec S, const double* __restrict__ J, const double* __restrict__ u,
+               const double* __restrict__ r, double* __restrict__ w, double* partials,
+               unsigned* ticket, double* sc, int* flags) {
+  if (flags[0]) return;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  double v[3] = {0.0, 0.0, 0.0}, tot[3];
+  if (row < S.n_dofs) {
+    const double sum = spmv_row<G>(S, J, u, row, lane);
+    if (lane == 0) {
+      w[row] = sum;
+      const double ri = r[row], ui = u[row];
+      v[0] = ri * ui; v[1] = sum * ui; v[2] = ui * ui;  // (r,u), (w,u), ||M^-1 r||^2
+    }
+  }
+  if (grid_reduce<3>(v, partials, ticket, tot) && threadIdx.x == 0) {
+    const double gamma_new = tot[0], delta = tot[1], rr = tot[2];
+    const int it = flags[1];
+    sc[3] = rr;
+    if (it == 0) sc[5] = rr;
+    if (rr <= sc[4] || !(rr == rr)) {
+      flags[0] = 1;
+      if (!(rr == rr)) flags[2] = 1;
+    } else {
+      double alpha, beta;
+      if (it == 0) { beta = 0.0; alpha = gamma_new / delta; }
+      else {
+        beta = gamma_new / sc[2];
+        alpha = gamma_new / (delta - beta * gamma_new / sc[0]);
+      }
+      if (!(alpha == alpha) || isinf(alpha)) { flags[0] = 1; flags[2] = 1; }
+      sc[0] = alpha; sc[1] = beta; sc[2] = gamma_new;
+      flags[1] = it + 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// GMRES(m), right preconditioned, CGS2 orthogonalisation.
+//   gm layout in sc: H[(m+1)*m] at 128, cs[m], sn[m], g[m+1], hd1[m+1], hd2[m+1], misc
+// ---------------------------------------------------------------------------
+#define GM_M 30
+#define GM_H 128
+#define GM_CS (GM_H + (GM_M + 1) * GM_M)
+#define GM_SN (GM_CS + GM_M)
+#define GM_G (GM_SN + GM_M)
+#define GM_HD1 (GM_G + GM_M + 1)
+#define GM_HD2 (GM_HD1 + GM_M + 1)
+#define GM_MISC (GM_HD2 + GM_M + 1)  // [0]=norm2 of w, [1]=scale, [2]=residual, [3]=threshold, [4]=beta0
+#define GM_Y (GM_MISC + 8)
+#define GM_END (GM_Y + GM_M)
+
+// hd[i] = <V_i, w>, i < nv
+__global__ void __launch_bounds__(FB_TPB)
+k_multidot(long long n, int nv, const double* __restrict__ V, const double* __restrict__ w,
+           double* partials, unsigned* ticket, double* hd, const int* __restrict__ flags) {
+  if (flags[0]) return;
+  __shared__ double sm[FB_TPB / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = 0; i < nv; ++i) {
+    const double* __restrict__ vi = V + (size_t)i * n;
+    double acc = 0.0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x)
+      acc += vi[k] * w[k];
+    acc = warp_sum(acc);
+    if (lane == 0) sm[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int q = 0; q < nw; ++q) s += sm[q];
+      partials[(size_t)i * gridDim.x + blockIdx.x] = s;
+    }
+    __syncthreads();
+  }
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int i = wid; i < nv; i += nw) {
+    double s = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) s += partials[(size_t)i * gridDim.x + b];
+    s = warp_sum(s);
+    if (lane == 0) hd[i] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// w -= sum_i hd[i] V_i ; out_norm2 = <w, w>
+__global__ void __launch_bounds__(FB_TPB)
+k_multiaxpy_norm(long long n, int nv, const double* __restrict__ V, const double* __restrict__ hd,
+                 double* __restrict__ w, double* partials, unsigned* ticket, double* out_norm2,
+                 const int* __restrict__ flags) {
+  if (flags[0]) return;
+  double v[1] = {0.0}, tot[1];
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    double acc = w[k];
+    for (int i = 0; i < nv; ++i) acc -= hd[i] * V[(size_t)i * n + k];
+    w[k] = acc;
+    v[0] += acc * acc;
+  }
+  if (grid_reduce<1>(v, partials, ticket, tot) && threadIdx.x == 0) out_norm2[0] = tot[0];
+}
+
+__global__ void k_gmres_givens(int j, double* sc, int* flags) {
+  if (flags[0]) return;
+  double* H = sc + GM_H;
+  double* cs = sc + GM_CS; double* sn = sc + GM_SN; double* g = sc + GM_G;
+  double* col = H + (size_t)j * (GM_M + 1);
+  for (int i = 0; i <= j; ++i) col[i] = sc[GM_HD1 + i] + sc[GM_HD2 + i];
+  const double hn = sqrt(sc[GM_MISC + 0]);
+  col[j + 1] = hn;
+  sc[GM_MISC + 1] = hn > 0.0 ? 1.0 / hn : 0.0;
+  for (int i = 0; i < j; ++i) {
+    const double t = cs[i] * col[i] + sn[i] * col[i + 1];
+    col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
+    col[i] = t;
+  }
+  const double a = col[j], b = col[j + 1];
+  const double rho = sqrt(a * a + b * b);
+  const double c = rho > 0.0 ? a / rho : 1.0, s = rho > 0.0 ? b / rho : 0.0;
+  cs[j] = c; sn[j] = s;
+  col[j] = rho; col[j + 1] = 0.0;
+  g[j + 1] = -s * g[j];
+  g[j] = c * g[j];
+  const double res = fabs(g[j + 1]);
+  sc[GM_MISC + 2] = res;
+  flags[1] += 1;   // total iterations
+  flags[3] = j + 1;  // columns in this cycle
+  if (res <= sc[GM_MISC + 3] || !(res == res) || hn == 0.0) {
+    flags[0] = 1;
+    if (!(res == res)) flags[2] = 1;
+  }
+}
+
+__global__ void k_scale_to(long long n, const double* __restrict__ w, const double* __restrict__ scale,
+                           double* __restrict__ out, const int* __restrict__ flags) {
+  if (flags && flags[0]) return;
+  const double s = scale[0];
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x)
+    out[k] = w[k] * s;
+}
+
+__global__ void k_gmres_solve_y(double* sc, const int* flags) {
+  const int nc = flags[3];
+  const double* H = sc + GM_H; const double* g = sc + GM_G; double* y = sc + GM_Y;
+  for (int i = nc - 1; i >= 0; --i) {
+    double acc = g[i];
+    for (int k = i + 1; k < nc; ++k) acc -= H[(size_t)k * (GM_M + 1) + i] * y[k];
+    y[i] = acc / H[(size_t)i * (GM_M + 1) + i];
+  }
+  for (int i = nc; i < GM_M; ++i) y[i] = 0.0;
+}
+
+// t = sum_i y[i] V_i (i < ncols read from flags[3])
+__global__ void k_combine(long long n, const double* __restrict__ V, const double* __restrict__ y,
+                          const int* __restrict__ flags, double* __restrict__ t) {
+  const int nc = flags[3];
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int i = 0; i < nc; ++i) acc += y[i] * V[(size_t)i * n + k];
+    t[k] = acc;
+  }
+}
+
+__global__ void k_residual(long long n, const double* __restrict__ b, const double* __restrict__ Ax,
+                           double* __restrict__ r) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x)
+    r[k] = b[k] - Ax[k];
+}
+
+__global__ void k_gmres_begin(double* sc, int* flags, double thr) {
+  // sc[GM_MISC+0] holds ||r||^2 from the preceding reduction
+  const double beta = sqrt(sc[GM_MISC + 0]);
+  sc[GM_MISC + 4] = beta;
+  sc[GM_MISC + 1] = beta > 0.0 ? 1.0 / beta : 0.0;
+  sc[GM_MISC + 3] = thr;
+  for (int i = 0; i <= GM_M; ++i) sc[GM_G + i] = 0.0;
+  sc[GM_G] = beta;
+  flags[3] = 0;
+  flags[0] = (beta <= thr) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// exact block-tridiagonal LU for interval meshes (the reference's default
+// "preonly + lu" is an exact solve; in 1D the node graph is tridiagonal)
+// ---------------------------------------------------------------------------
+__global__ void k_tri_extract(DevSpec S, const double* __restrict__ J, double* __restrict__ T) {
+  // T[v][3][ns][ns]: sub, diag, super dense blocks
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= S.n_vertices) return;
+  const int ns = S.ns, r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+  double* out = T + v * 3 * ns * ns;
+  for (int i = 0; i < 3 * ns * ns; ++i) out[i] = 0.0;
+  const long long base = (long long)r0 * S.npairs;
+  for (int k = 0; k < deg; ++k) {
+    const int w = S.colidx[r0 + k];
+    const int pos = w - (int)v + 1;
+    if (pos < 0 || pos > 2) continue;
+    for (int s = 0; s < ns; ++s)
+      for (int j = 0; j < S.pair_nc[s]; ++j)
+        out[(pos * ns + s) * ns + S.pair_cs[S.pair_pp[s] + j]] =
+            J[base + (long long)deg * S.pair_pp[s] + (long long)k * S.pair_nc[s] + j];
+  }
+}
+
+// dense ns x ns solve helpers (single thread)
+__device__ void dense_lu_solve(int ns, double* A, double* B, int nrhs) {
+  // solves A X = B in place (B: ns x nrhs row-major), partial pivoting
+  for (int col = 0; col < ns; ++col) {
+    int piv = col;
+    double best = fabs(A[col * ns + col]);
+    for (int r = col + 1; r < ns; ++r)
+      if (fabs(A[r * ns + col]) > best) { best = fabs(A[r * ns + col]); piv = r; }
+    if (piv != col) {
+      for (int c = 0; c < ns; ++c) { double t = A[col * ns + c]; A[col * ns + c] = A[piv * ns + c]; A[piv * ns + c] = t; }
+      for (int c = 0; c < nrhs; ++c) { double t = B[col * nrhs + c]; B[col * nrhs + c] = B[piv * nrhs + c]; B[piv * nrhs + c] = t; }
+    }
+    const double ip = 1.0 / A[col * ns + col];
+    for (int r = col + 1; r < ns; ++r) {
+      const double f = A[r * ns + col] * ip;
+      if (f == 0.0) continue;
+      for (int c = col; c < ns; ++c) A[r * ns + c] -= f * A[col * ns + c];
+      for (int c = 0; c < nrhs; ++c) B[r * nrhs + c] -= f * B[col * nrhs + c];
+    }
+  }
+  for (int r = ns - 1; r >= 0; --r) {
+    for (int c = 0; c < nrhs; ++c) {
+      double acc = B[r * nrhs + c];
+      for (int k = r + 1; k < ns; ++k) acc -= A[r * ns + k] * B[k * nrhs + c];
+      B[r * nrhs + c] = acc / A[r * ns + r];
+    }
+  }
+}
+
+__global__ void k_tri_solve(DevSpec S, double* __restrict__ T, const double* __restrict__ b,
+                            double* __restrict__ y, double* __restrict__ Cp /*[nv][ns][ns]*/) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int ns = S.ns;
+  const long long nv = S.n_vertices;
+  double A[FB_MAX_NS * FB_MAX_NS], R[FB_MAX_NS * (FB_MAX_NS + 1)];
+  // forward: C'_v = (B_v - A_v C'_{v-1})^-1 C_v ; d'_v = (..)^-1 (d_v - A_v d'_{v-1})
+  for (long long v = 0; v < nv; ++v) {
+    const double* sub = T + (v * 3 + 0) * ns * ns;
+    const double* dia = T + (v * 3 + 1) * ns * ns;
+    const double* sup = T + (v * 3 + 2) * ns * ns;
+    for (int i = 0; i < ns * ns; ++i) A[i] = dia[i];
+    for (int r = 0; r < ns; ++r) {
+      for (int c = 0; c < ns; ++c) R[r * (ns + 1) + c] = sup[r * ns + c];
+      R[r * (ns + 1) + ns] = b[v * ns + r];
+    }
+    if (v > 0) {
+      const double* Cprev = Cp + (v - 1) * ns * ns;
+      for (int r = 0; r < ns; ++r) {
+        double accd = 0.0;
+        for (int k = 0; k < ns; ++k) {
+          const double a = sub[r * ns + k];
+          if (a == 0.0) continue;
+          for (int c = 0; c < ns; ++c) A[r * ns + c] -= a * Cprev[k * ns + c];
+          accd += a * y[(v - 1) * ns + k];
+        }
+        R[r * (ns + 1) + ns] -= accd;
+      }
+    }
+    dense_lu_solve(ns, A, R, ns + 1);
+    for (int r = 0; r < ns; ++r) {
+      for (int c = 0; c < ns; ++c) Cp[v * ns * ns + r * ns + c] = R[r * (ns + 1) + c];
+      y[v * ns + r] = R[r * (ns + 1) + ns];
+    }
+  }
+  for (long long v = nv - 2; v >= 0; --v) {
+    const double* C = Cp + v * ns * ns;
+    for (int r = 0; r < ns; ++r) {
+      double acc = y[v * ns + r];
+      for (int c = 0; c < ns; ++c) acc -= C[r * ns + c] * y[(v + 1) * ns + c];
+      y[v * ns + r] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------
+int fbi_ensure_workspace(fb_ctx* ctx) {
+  const DevSpec& S = ctx->S;
+  if (ctx->d_sc) return 0;
+  int rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_sc, GM_END + 64))) return rc;
+  // partial sums: (GM_M + 2) vectors x capped vector grid, or 3 x the SpMV grid
+  size_t red = (size_t)FB_RED_SLOTS * ctx->sm_count * 8;
+  const size_t spmv_blocks = (size_t)((S.n_dofs * 32 + FB_TPB - 1) / FB_TPB);
+  if (red < 3 * spmv_blocks + 16) red = 3 * spmv_blocks + 16;
+  ctx->red_doubles = (long long)red;
+  if ((rc = fb_alloc(ctx, &ctx->d_red, red))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_ticket, 4))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_flags, 8))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_dinv, (size_t)S.n_vertices * S.ns * S.ns))) return rc;
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_ticket, 0, 16, ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
+  FB_CHECK(ctx, cudaMallocHost((void**)&ctx->h_pinned, 64 * sizeof(double)));
+  return 0;
+}
+
+static int ensure_vectors(fb_ctx* ctx, int nvec) {
+  const long long need = (long long)nvec * ctx->S.n_dofs;
+  if (ctx->work_doubles >= need) return 0;
+  int rc = fb_alloc(ctx, &ctx->d_work, (size_t)need);  // old block stays owned until destroy
+  if (rc) return rc;
+  ctx->work_doubles = need;
+  return 0;
+}
+
+static int read_flags(fb_ctx* ctx, int* out4) {
+  FB_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int* f = (const int*)(ctx->h_pinned + 8);
+  for (int i = 0; i < 4; ++i) out4[i] = f[i];
+  return 0;
+}
+
+static int solve_cg(fb_ctx* ctx, const double* J, const double* b, double* y, double thr2, int max_it,
+                    int* iters) {
+  const DevSpec& S = ctx->S;
+  int rc = ensure_vectors(ctx, 5);
+  if (rc) return rc;
+  const long long N = S.n_dofs;
+  double* r = ctx->d_work; double* u = r + N; double* w = u + N; double* p = w + N; double* s_ = p + N;
+  const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
+  const int G = spmv_group(S);
+  const unsigned gs = (unsigned)((N * G + FB_TPB - 1) / FB_TPB);
+  if ((long long)gs * 3 > ctx->red_doubles) return fb_fail(ctx, "reduction buffer too small");
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
+  double hsc[8] = {0, 0, 0, 0, thr2, 0, 0, 0};
+  FB_CHECK(ctx, cudaMemcpyAsync(ctx->d_sc, hsc, sizeof(hsc), cudaMemcpyHostToDevice, ctx->stream));
+  FB_LAUNCH(ctx, k_cg_init, gn, FB_TPB, 0, S, ctx->d_dinv, b, y, r, u, p, s_);
+  int fl[4] = {0, 0, 0, 0};
+  int launched = 0;
+  const int chunk = 32;
+  while (launched <= max_it) {
+    for (int k = 0; k < chunk; ++k) {
+      switch (G) {
+        case 4: FB_LAUNCH(ctx, k_cg_spmv_dots<4>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, ctx->d_sc, ctx->d_flags); break;
+        case 8: FB_LAUNCH(ctx, k_cg_spmv_dots<8>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, ctx->d_sc, ctx->d_flags); break;
+        case 16: FB_LAUNCH(ctx, k_cg_spmv_dots<16>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, ctx->d_sc, ctx->d_flags); break;
+        default: FB_LAUNCH(ctx, k_cg_spmv_dots<32>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, ctx->d_sc, ctx->d_flags); break;
+      }
+      FB_LAUNCH(ctx, k_cg_update, gn, FB_TPB, 0, S, ctx->d_dinv, ctx->d_sc, ctx->d_flags, y, r, u, w, p, s_);
+    }
+    launched += chunk;
+    FB_CHECK(ctx, cudaGetLastError());
+    if ((rc = read_flags(ctx, fl))) return rc;
+    if (fl[0]) break;
+  }
+  *iters = fl[1];
+  if (fl[2]) return 1;      // breakdown
+  return fl[0] ? 0 : 2;     // 2: not converged within max_it
+}
+
+static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y, double thr, int max_it,
+                       int* iters) {
+  const DevSpec& S = ctx->S;
+  int rc = ensure_vectors(ctx, GM_M + 4);
+  if (rc) return rc;
+  const long long N = S.n_dofs;
+  double* V = ctx->d_work;                 // (GM_M+1) vectors
+  double* w = V + (size_t)(GM_M + 1) * N;
+  double* z = w + N;
+  double* r = z + N;
+  const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
+  const unsigned gv = vec_grid(ctx, N);
+  double* sc = ctx->d_sc;
+  FB_CHECK(ctx, cudaMemsetAsync(y, 0, sizeof(double) * N, ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
+  int total = 0;
+  int fl[4] = {0, 0, 0, 0};
+  bool first = true;
+  while (total < max_it) {
+    // r = M^-1 (b - A y)   (left preconditioning: the Arnoldi residual is the
+    // preconditioned one, PETSc's default norm for GMRES)
+    if (first) {
+      FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, b, r, (const int*)nullptr);
+    } else {
+      if ((rc = fbi_spmv(ctx, J, y, w))) return rc;
+      FB_LAUNCH(ctx, k_residual, gv, FB_TPB, 0, N, b, w, w);
+      FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, w, r, (const int*)nullptr);
+    }
+    first = false;
+    FB_LAUNCH(ctx, k_dot, gv, FB_TPB, 0, N, r, r, ctx->d_red, ctx->d_ticket, sc + GM_MISC);
+    FB_LAUNCH(ctx, k_gmres_begin, 1, 1, 0, sc, ctx->d_flags, thr);
+    FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, r, sc + GM_MISC + 1, V, (const int*)nullptr);
+    for (int j = 0; j < GM_M; ++j) {
+      if ((rc = fbi_spmv(ctx, J, V + (size_t)j * N, z))) return rc;
+      FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, z, w, ctx->d_flags);
+      FB_LAUNCH(ctx, k_multidot, gv, FB_TPB, 0, N, j + 1, V, w, ctx->d_red, ctx->d_ticket, sc + GM_HD1, ctx->d_flags);
+      FB_LAUNCH(ctx, k_multiaxpy_norm, gv, FB_TPB, 0, N, j + 1, V, sc + GM_HD1, w, ctx->d_red, ctx->d_ticket, sc + GM_MISC, ctx->d_flags);
+      FB_LAUNCH(ctx, k_multidot, gv, FB_TPB, 0, N, j + 1, V, w, ctx->d_red, ctx->d_ticket, sc + GM_HD2, ctx->d_flags);
+      FB_LAUNCH(ctx, k_multiaxpy_norm, gv, FB_TPB, 0, N, j + 1, V, sc + GM_HD2, w, ctx->d_red, ctx->d_ticket, sc + GM_MISC, ctx->d_flags);
+      FB_LAUNCH(ctx, k_gmres_givens, 1, 1, 0, j, sc, ctx->d_flags);
+      FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, w, sc + GM_MISC + 1, V + (size_t)(j + 1) * N, ctx->d_flags);
+      if (j % 10 == 9 || j == GM_M - 1) {
+        FB_CHECK(ctx, cudaGetLastError());
+        if ((rc = read_flags(ctx, fl))) return rc;
+        if (fl[0]) break;
+      }
+    }
+    total = fl[1];
+    // y += V yk
+    if (fl[3] > 0) {
+      FB_LAUNCH(ctx, k_gmres_solve_y, 1, 1, 0, sc, ctx->d_flags);
+      FB_LAUNCH(ctx, k_combine, gv, FB_TPB, 0, N, V, sc + GM_Y, ctx->d_flags, w);
+      FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, N, 1.0, w, y);
+    }
+    if (fl[0] || fl[2]) break;
+  }
+  *iters = total;
+  FB_CHECK(ctx, cudaGetLastError());
+  if (fl[2]) return 1;
+  return fl[0] ? 0 : 2;
+}
+
+static int solve_tridiag(fb_ctx* ctx, const double* J, const double* b, double* y) {
+  const DevSpec& S = ctx->S;
+  int rc;
+  if (!ctx->d_tri) {
+    if ((rc = fb_alloc(ctx, &ctx->d_tri, (size_t)S.n_vertices * 4 * S.ns * S.ns))) return rc;
+  }
+  const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
+  FB_LAUNCH(ctx, k_tri_extract, gn, FB_TPB, 0, S, J, ctx->d_tri);
+  FB_LAUNCH(ctx, k_tri_solve, 1, 32, 0, S, ctx->d_tri, b, y, ctx->d_tri + (size_t)S.n_vertices * 3 * S.ns * S.ns);
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, int ksp, int pc,
+                     double rtol, double atol, int max_it, int* iters, double* relres) {
+  const DevSpec& S = ctx->S;
+  int rc = fbi_ensure_workspace(ctx);
+  if (rc) return rc;
+  (void)pc;
+  *iters = 0;
+  *relres = 0.0;
+  if (ksp == FB_KSP_AUTO) ksp = ctx->tridiag ? FB_KSP_TRIDIAG : FB_KSP_GMRES;
+  if (ksp == FB_KSP_TRIDIAG) {
+    if (!ctx->tridiag) return fb_fail(ctx, "tridiagonal solver needs an interval mesh ordered along x");
+    return solve_tridiag(ctx, J, b, y);
+  }
+  double bnorm;
+  if ((rc = fbi_norm2(ctx, b, &bnorm))) return rc;
+  if (bnorm == 0.0) {
+    FB_CHECK(ctx, cudaMemsetAsync(y, 0, sizeof(double) * S.n_dofs, ctx->stream));
+    return 0;
+  }
+  const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
+  FB_LAUNCH(ctx, k_bjacobi_setup, gn, FB_TPB, 0, S, J, ctx->d_dinv, ctx->d_flags);
+  // stopping rule on the preconditioned residual, ||M^-1 r|| <= max(rtol ||M^-1 b||, atol)
+  // (PETSc default for left-preconditioned CG/GMRES); block-Jacobi makes it row-scaled,
+  // which matters when species equations differ by many orders of magnitude
+  if ((rc = ensure_vectors(ctx, 2))) return rc;
+  FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, b, ctx->d_work, (const int*)nullptr);
+  double pbnorm;
+  if ((rc = fbi_norm2(ctx, ctx->d_work, &pbnorm))) return rc;
+  double thr = rtol * pbnorm;
+  if (atol > thr) thr = atol;
+  int status;
+  if (ksp == FB_KSP_CG) status = solve_cg(ctx, J, b, y, thr * thr, max_it, iters);
+  else status = solve_gmres(ctx, J, b, y, thr, max_it, iters);
+  if (status < 0) return status;
+  // true residual
+  if ((rc = ensure_vectors(ctx, 2))) return rc;
+  double* t = ctx->d_work;
+  if ((rc = fbi_spmv(ctx, J, y, t))) return rc;
+  FB_LAUNCH(ctx, k_residual, vec_grid(ctx, S.n_dofs), FB_TPB, 0, S.n_dofs, b, t, t);
+  double rn;
+  if ((rc = fbi_norm2(ctx, t, &rn))) return rc;
+  *relres = rn / bnorm;
+  if (status == 1) { ctx->err = "Krylov breakdown"; return 1; }
+  if (status == 2) { ctx->err = "Krylov solver did not converge"; return 2; }
+  return 0;
+}

@@ -1,0 +1,304 @@
+"""Lowering: FESTIM problem -> flat per-cell kernel spec for the CUDA library.
+
+This replaces UFL/FFCx form compilation at the solver seam (reference
+``src/festim/problem.py:170-182``: ``NonlinearProblem(F, u, bcs, ...)``).  The
+residual form built by ``create_formulation`` is split into the term classes
+the device kernels implement (``festim_b200/csrc/assemble.cu``):
+
+* Arrhenius diffusion ``D_0 exp(-E_D/(k_B T)) grad u . grad v`` per (volume tag,
+  species): constants ``D_0`` and an index into the table of distinct activation
+  energies (cell averages of the Arrhenius factor are cached per temperature
+  update, for the F and the J quadrature rule separately);
+* mass terms ``m (u - u_n)/dt v`` and ``m u v`` (exact closed form);
+* advection ``(grad u . vel) v`` with a P1 vector velocity;
+* point terms: any other integrand ``expr v`` (reactions, sources, fluxes) as a
+  byte-code program for the value plus one program per species derivative
+  (the symbolic ``ufl.derivative`` analogue), applied to a list of
+  (row species, coefficient) - e.g. ``+R`` on every reactant, ``-R`` on every
+  product of a reaction;
+* which species pairs are structurally non-zero in a node block (the
+  species-sparse BSR layout documented in ``include/festim_b200.h``).
+
+Blob layout (little endian): int64 magic, int64 n_sections, then per section
+(int64 id, int64 dtype code [0=int32, 1=float64], int64 count, int64 byte
+offset), then the 8-byte aligned payloads.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from festim_b200 import fem, quadrature, ufl
+
+MAGIC = 0xFB200_0001
+
+# section ids (shared with csrc/spec.h)
+(S_INTS, S_DIFF_D0, S_DIFF_SLOT, S_DIFF_ENERGIES, S_MASS_DT, S_MASS_C, S_PAIR_NC, S_PAIR_PP,
+ S_PAIR_CS, S_PAIR_IDX, S_PROG_OPS, S_PROG_IARGS, S_PROG_FARGS, S_PROG_OFFSETS, S_VTERM_HDR,
+ S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
+ S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS) = range(1, 27)
+
+# S_INTS slots
+(I_TDIM, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
+ I_NVTERMS, I_NFTERMS, I_NADV, I_NPAIRS, I_NDIFFE, I_DT_SCALAR, I_NSLOTS) = range(16)
+
+MAX_NS = 16
+
+
+class PointTerm:
+    def __init__(self, tag, value_prog, rows, derivs, u_dependent):
+        self.tag = tag
+        self.value_prog = value_prog
+        self.rows = rows          # [(species index, coefficient)]
+        self.derivs = derivs      # [(dep species index, program id)]
+        self.u_dependent = u_dependent
+
+
+class KernelSpec:
+    """Host-side description; ``blob()`` serialises what the library needs."""
+
+    def __init__(self, problem):
+        self.problem = problem
+        mesh = problem.mesh.mesh
+        self.mesh = mesh
+        self.tdim = mesh.tdim
+        species = getattr(problem, "species", None) or [problem._unknown]
+        self.species = list(species)
+        ns = self.ns = len(self.species)
+        if ns > MAX_NS:
+            raise NotImplementedError(f"more than {MAX_NS} species")
+        self.vol_ids = [v.id for v in problem.volume_subdomains]
+        self.surf_ids = [s.id for s in problem.surface_subdomains]
+        nvt, nst = len(self.vol_ids), len(self.surf_ids)
+
+        # compact tags
+        vt = problem.volume_meshtags
+        ctag = np.zeros(mesh.num_cells, dtype=np.int64)
+        ctag[vt.indices] = vt.values
+        lut = {vid: i for i, vid in enumerate(self.vol_ids)}
+        self.cell_tag = np.array([lut[t] for t in ctag], dtype=np.int32) if nvt > 1 else \
+            np.zeros(mesh.num_cells, dtype=np.int32)
+        if nvt > 1:
+            pass
+        elif not np.all(ctag == self.vol_ids[0]):
+            raise ValueError("cells tagged with an id that is not a volume subdomain")
+        ft = problem.facet_meshtags
+        ftag = np.zeros(mesh.bfacets.shape[0], dtype=np.int64)
+        ftag[ft.indices] = ft.values
+        slut = {sid: i for i, sid in enumerate(self.surf_ids)}
+        self.bfacet_tag = np.array([slut.get(t, -1) for t in ftag], dtype=np.int32)
+
+        T = getattr(problem, "temperature_fenics", None)
+        self.temperature = T
+        self.T_mode = 1 if isinstance(T, fem.Function) else 0
+        sidx = {spe: i for i, spe in enumerate(self.species)}
+        self.programs = ufl.ProgramBuilder(species_index=sidx, temperature=T)
+        self.transient = bool(problem.settings.transient)
+        self.dt_scalar = -1
+        if self.transient:
+            self.dt_scalar = self.programs._scalar_id(problem.dt)
+
+        self.diff_D0 = np.zeros((nvt, ns))
+        # cell-coefficient slots: distinct activation energies first, then
+        # generic (program) diffusivities; diff_slot < 0 = no diffusion
+        self.diff_slot = np.full((nvt, ns), -1, dtype=np.int32)
+        self._generic_D = []   # (tag, s, program id), slots assigned after the energies
+        self.diff_energies = []
+        self.mass_dt = np.zeros((nvt, ns))
+        self.mass_c = np.zeros((nvt, ns))
+        self.vterms = []
+        self.fterms = []
+        self.adv = []          # (vtag index, species index, VectorFunction)
+        pairs = {(s, s) for s in range(ns)}
+
+        degrees = problem.formulation.quadrature_degrees()
+        self.degrees = degrees
+        reaction_terms = {}
+        for itg in problem.formulation.integrals:
+            kind, sid = itg.measure
+            s = sidx[itg.species]
+            if kind == "dx":
+                tag = self.vol_ids.index(sid)
+            else:
+                tag = self.surf_ids.index(sid)
+            if itg.kind == "diffusion":
+                if "arrhenius" in itg.meta:
+                    D0, E = itg.meta["arrhenius"]
+                    self.diff_D0[tag, s] = D0
+                    self.diff_slot[tag, s] = self._energy_index(float(E))
+                else:
+                    if ufl.species_in(itg.D):
+                        raise NotImplementedError("solution-dependent diffusivity")
+                    self.diff_D0[tag, s] = 1.0
+                    self._generic_D.append((tag, s, self.programs.add(itg.D)))
+            elif itg.kind == "advection":
+                self.adv.append((tag, s, itg.velocity))
+            elif "mass" in itg.meta and kind == "dx":
+                self.mass_dt[tag, s] += float(itg.meta["mass"])
+            elif "filler" in itg.meta and kind == "dx":
+                self.mass_c[tag, s] += float(itg.meta["filler"])
+            else:
+                terms = self.vterms if kind == "dx" else self.fterms
+                reaction = itg.meta.get("reaction")
+                if reaction is not None:
+                    key = (id(reaction), kind, tag)
+                    if key not in reaction_terms:
+                        # value program: the positive reaction term, evaluated once
+                        # per point and applied with +-1 to every reactant / product
+                        pos = itg.expr if itg.meta["sign"] > 0 else -itg.expr
+                        term = self._point_term(tag, pos, [], sidx)
+                        reaction_terms[key] = term
+                        terms.append(term)
+                    reaction_terms[key].rows.append((s, float(itg.meta["sign"])))
+                    for dep, _ in reaction_terms[key].derivs:
+                        pairs.add((s, dep))
+                else:
+                    term = self._point_term(tag, itg.expr, [(s, 1.0)], sidx)
+                    terms.append(term)
+                    for dep, _ in term.derivs:
+                        pairs.add((s, dep))
+
+        self.diff_progs = []
+        for tag, s, pid in self._generic_D:
+            if pid not in self.diff_progs:
+                self.diff_progs.append(pid)
+            self.diff_slot[tag, s] = len(self.diff_energies) + self.diff_progs.index(pid)
+        self.n_slots = len(self.diff_energies) + len(self.diff_progs)
+
+        # species pairs -> layout tables
+        self.pair_nc = np.zeros(ns, dtype=np.int32)
+        self.pair_pp = np.zeros(ns + 1, dtype=np.int32)
+        self.pair_idx = np.full((ns, ns), -1, dtype=np.int32)
+        cs = []
+        for s in range(ns):
+            cols = sorted(c for (r, c) in pairs if r == s)
+            self.pair_nc[s] = len(cols)
+            self.pair_pp[s + 1] = self.pair_pp[s] + len(cols)
+            for j, c in enumerate(cols):
+                self.pair_idx[s, c] = j
+            cs.extend(cols)
+        self.pair_cs = np.array(cs, dtype=np.int32)
+        self.npairs = int(self.pair_pp[-1])
+
+        # quadrature pools
+        self._qb, self._qw = [], []
+        self.quad_v = np.zeros((nvt, 4), dtype=np.int32)
+        self.quad_s = np.zeros((max(nst, 1), 4), dtype=np.int32)
+        for i, vid in enumerate(self.vol_ids):
+            dF, dJ = degrees.get(("dx", vid), (1, None))
+            self.quad_v[i] = self._add_rule(self.tdim, dF) + self._add_rule(
+                self.tdim, dF if dJ is None else dJ)
+        for i, sid in enumerate(self.surf_ids):
+            dF, dJ = degrees.get(("ds", sid), (1, None))
+            self.quad_s[i] = self._add_rule(self.tdim - 1, dF) + self._add_rule(
+                self.tdim - 1, dF if dJ is None else dJ)
+
+    # ------------------------------------------------------------------
+    def _energy_index(self, E):
+        for i, e in enumerate(self.diff_energies):
+            if e == E:
+                return i
+        self.diff_energies.append(E)
+        return len(self.diff_energies) - 1
+
+    def _point_term(self, tag, expr, rows, sidx):
+        if expr is None:
+            return None
+        deps = ufl.species_in(expr)
+        derivs = [(sidx[spe], self.programs.add(ufl.diff(expr, ("species", spe)))) for spe in deps]
+        u_dep = bool(deps) or ufl.depends_on(expr, ufl.SpeciesRef)
+        return PointTerm(tag, self.programs.add(expr), rows, derivs, u_dep)
+
+    def _add_rule(self, tdim, degree):
+        bary, w = quadrature.rule(tdim, degree)
+        off = sum(len(x) for x in self._qw)
+        self._qb.append(bary.ravel())
+        self._qw.append(w)
+        return [off, len(w)]
+
+    # ------------------------------------------------------------------
+    @property
+    def scalars(self):
+        return self.programs.scalars
+
+    @property
+    def fields(self):
+        return self.programs.fields
+
+    def scalar_values(self):
+        return np.array([float(s.value) for s in self.programs.scalars], dtype=np.float64)
+
+    def blob(self):
+        ops, iargs, fargs, offsets = self.programs.tables()
+        ints = np.zeros(16, dtype=np.int32)
+        ints[[I_TDIM, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE]] = [
+            self.tdim, self.ns, len(self.vol_ids), len(self.surf_ids), int(self.transient),
+            self.T_mode]
+        ints[[I_NPROGRAMS, I_NSCALARS, I_NFIELDS]] = [
+            self.programs.n_programs, len(self.programs.scalars), len(self.programs.fields)]
+        ints[[I_NVTERMS, I_NFTERMS, I_NADV, I_NPAIRS, I_NDIFFE, I_DT_SCALAR, I_NSLOTS]] = [
+            len(self.vterms), len(self.fterms), len(self.adv), self.npairs,
+            len(self.diff_energies), self.dt_scalar, self.n_slots]
+
+        row_species, row_coef, deriv_species, deriv_prog = [], [], [], []
+
+        def headers(terms):
+            hdr = np.zeros((max(len(terms), 1), 8), dtype=np.int32)
+            for i, t in enumerate(terms):
+                hdr[i] = [t.tag, t.value_prog, len(row_species), len(t.rows),
+                          len(deriv_species), len(t.derivs), int(t.u_dependent), 0]
+                for s, c in t.rows:
+                    row_species.append(s)
+                    row_coef.append(c)
+                for s, p in t.derivs:
+                    deriv_species.append(s)
+                    deriv_prog.append(p)
+            return hdr
+
+        vhdr = headers(self.vterms)
+        fhdr = headers(self.fterms)
+        adv = np.array([[t, s] for t, s, _ in self.adv], dtype=np.int32).reshape(-1, 2)
+        sections = {
+            S_INTS: ints,
+            S_DIFF_D0: self.diff_D0, S_DIFF_SLOT: self.diff_slot,
+            S_DIFF_ENERGIES: np.array(self.diff_energies, dtype=np.float64),
+            S_DIFF_PROGS: np.array(self.diff_progs, dtype=np.int32),
+            S_MASS_DT: self.mass_dt, S_MASS_C: self.mass_c,
+            S_PAIR_NC: self.pair_nc, S_PAIR_PP: self.pair_pp, S_PAIR_CS: self.pair_cs,
+            S_PAIR_IDX: self.pair_idx,
+            S_PROG_OPS: ops, S_PROG_IARGS: iargs, S_PROG_FARGS: fargs, S_PROG_OFFSETS: offsets,
+            S_VTERM_HDR: vhdr, S_FTERM_HDR: fhdr,
+            S_ROW_SPECIES: np.array(row_species, dtype=np.int32),
+            S_ROW_COEF: np.array(row_coef, dtype=np.float64),
+            S_DERIV_SPECIES: np.array(deriv_species, dtype=np.int32),
+            S_DERIV_PROG: np.array(deriv_prog, dtype=np.int32),
+            S_QUAD_V: self.quad_v, S_QUAD_S: self.quad_s,
+            S_QUAD_BARY: np.concatenate(self._qb) if self._qb else np.zeros(0),
+            S_QUAD_W: np.concatenate(self._qw) if self._qw else np.zeros(0),
+            S_ADV: adv,
+        }
+        return pack_sections(sections)
+
+
+def pack_sections(sections):
+    items = []
+    for sid, arr in sections.items():
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype == np.int32:
+            code = 0
+        elif arr.dtype == np.float64:
+            code = 1
+        else:
+            raise TypeError(f"section {sid}: dtype {arr.dtype}")
+        items.append((sid, code, arr))
+    header = 2 + 4 * len(items)
+    offset = header * 8
+    table = [MAGIC, len(items)]
+    payload = []
+    for sid, code, arr in items:
+        nbytes = arr.nbytes
+        table += [sid, code, arr.size, offset]
+        pad = (-nbytes) % 8
+        payload.append(arr.tobytes() + b"\0" * pad)
+        offset += nbytes + pad
+    return np.array(table, dtype=np.int64).tobytes() + b"".join(payload)

@@ -1,0 +1,151 @@
+/*
+ * festim_b200.h -- C ABI of libfestim_b200.so, the B200 (sm_100a) solver backend
+ * for FESTIM's hot path: residual/Jacobian assembly + Newton-Krylov solve of
+ * coupled diffusion-trapping-reaction systems on P1 interval/triangle/tet meshes.
+ *
+ * FESTIM has no plugin API; the replaceable seam is
+ *   ProblemBase.create_solver()            reference src/festim/problem.py:170-193
+ *   self.solver.solve()                    reference src/festim/problem.py:213,237
+ *   solver.solver.getConvergedReason()     reference src/festim/problem.py:238
+ *   solver.solver.getIterationNumber()     reference src/festim/problem.py:242
+ * Behind that seam the reference crosses into dolfinx (C++ assembly of FFCx
+ * kernels) and PETSc (SNES newtonls + KSP).  The entry points below are what a
+ * ctypes binding placed at that seam calls instead.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; fb_last_error(ctx) gives
+ *     the message (owned by ctx).  Non-convergence is NOT an error: it is reported
+ *     through `reason` (PETSc SNESConvergedReason numbering).
+ *   - pointers marked [host] are read during the call and copied; pointers marked
+ *     [dev] are device pointers owned by the caller (e.g. torch tensors) that must
+ *     stay valid until the next call that replaces them or fb_destroy.
+ *   - all reals are fp64, local indices int32, sizes int64.
+ *   - unknown layout: node-major blocked, u[v * ns + s].
+ *   - Jacobian layout ("species-sparse BSR"): node-graph CSR (rowptr, colidx) of
+ *     blocks; block row v stores, for each row species s, deg(v) * nc[s] values
+ *     ordered [k][j]: value(v,s,k,j) at
+ *       rowptr[v]*npairs + deg(v)*pp[s] + k*nc[s] + j ,
+ *     the entry d F_(v,s) / d u_(colidx[rowptr[v]+k], cs[pp[s]+j]).
+ *   - one host thread per ctx; all work is enqueued on the stream given to
+ *     fb_create.
+ */
+#ifndef FESTIM_B200_H
+#define FESTIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_ctx fb_ctx;
+
+/* assemble flags */
+#define FB_ASSEMBLE_F 1
+#define FB_ASSEMBLE_J 2
+
+/* linear solver kinds (maps PETSc ksp_type / pc_type, reference problem.py:279-289) */
+#define FB_KSP_AUTO 0     /* preonly+lu: exact block-tridiagonal LU in 1D, Krylov(tight) else */
+#define FB_KSP_CG 1
+#define FB_KSP_GMRES 2
+#define FB_KSP_TRIDIAG 3
+#define FB_PC_JACOBI 0    /* point-block Jacobi (ns x ns diagonal blocks) */
+#define FB_PC_CHEBYSHEV 1 /* Chebyshev polynomial smoother on block-Jacobi */
+
+/* SNES converged reasons used (PETSc numbering) */
+#define FB_CONVERGED_FNORM_ABS 2
+#define FB_CONVERGED_FNORM_RELATIVE 3
+#define FB_CONVERGED_SNORM_RELATIVE 4
+#define FB_DIVERGED_LINEAR_SOLVE -3
+#define FB_DIVERGED_FNORM_NAN -4
+#define FB_DIVERGED_MAX_IT -5
+
+/* -- lifetime ------------------------------------------------------------------ */
+int fb_create(int device, void* cuda_stream, fb_ctx** out);
+void fb_destroy(fb_ctx* ctx);
+const char* fb_last_error(fb_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py "gpu_launches") */
+int64_t fb_launch_count(fb_ctx* ctx);
+
+/* -- problem definition (replaces dolfinx mesh/functionspace/form compilation,
+ *    reference hydrogen_transport_problem.py:672-728, problem.py:173-182) ---------- */
+int fb_set_mesh(fb_ctx* ctx, int tdim, int64_t n_vertices, int64_t n_cells,
+                const double* coords /*[host] n_vertices*tdim*/,
+                const int32_t* cells /*[host] n_cells*(tdim+1)*/,
+                const int32_t* cell_tag /*[host] n_cells, compact 0..n_vtags-1*/,
+                int64_t n_bfacets, const int32_t* bfacets /*[host] n_bfacets*tdim*/,
+                const int32_t* bfacet_cell /*[host]*/,
+                const int32_t* bfacet_tag /*[host] compact, -1 = untagged*/);
+/* sparsity pattern of the vertex graph and vertex->cell adjacency (packed
+ * cell*(tdim+1)+local), the analogue of dolfinx's create_sparsity_pattern */
+int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr /*[host] n_vertices+1*/,
+                   const int32_t* colidx /*[host] nnzb*/, int64_t nnzb,
+                   const int32_t* v2c_ptr /*[host] n_vertices+1*/,
+                   const int32_t* v2c_idx /*[host] n_cells*(tdim+1)*/);
+/* flat kernel spec produced by festim_b200/lowering.py (layout documented there) */
+int fb_set_spec(fb_ctx* ctx, const void* blob /*[host]*/, size_t nbytes);
+/* strong Dirichlet dofs (reference problem.py:118-130, fem.dirichletbc) */
+int fb_set_dirichlet(fb_ctx* ctx, int64_t n_bc, const int64_t* bc_dofs /*[host]*/);
+int64_t fb_num_dofs(fb_ctx* ctx);
+int64_t fb_jacobian_nnz(fb_ctx* ctx); /* number of stored scalars = nnzb*npairs */
+
+/* -- per-step data (reference update_time_dependent_values,
+ *    hydrogen_transport_problem.py:999-1034) -------------------------------------- */
+int fb_set_scalars(fb_ctx* ctx, int n, const double* scalars /*[host]*/);
+int fb_set_temperature(fb_ctx* ctx, double T_const, const double* T_nodal /*[dev] or NULL*/);
+int fb_set_field(fb_ctx* ctx, int k, const double* nodal /*[dev] n_vertices*/);
+int fb_set_velocity(fb_ctx* ctx, int k, const double* nodal /*[dev] n_vertices*tdim*/);
+int fb_set_dirichlet_values(fb_ctx* ctx, const double* bc_vals /*[dev] n_bc*/);
+/* (re)compute the solution-independent load vector (sources, fluxes); call after
+ * any of the setters above changed and before fb_assemble / fb_newton_solve */
+int fb_update_load(fb_ctx* ctx);
+
+/* -- the hot path ------------------------------------------------------------------ */
+/* residual F(u) and/or Jacobian J(u) with strong Dirichlet conditions applied the
+ * dolfinx NonlinearProblem way: lifting (alpha=-1), F_B = u_B - g, identity rows and
+ * columns in J (replaces assemble_vector/apply_lifting/set_bc/assemble_matrix). */
+int fb_assemble(fb_ctx* ctx, const double* u /*[dev]*/, const double* u_n /*[dev]*/,
+                double* F /*[dev] N or NULL*/, double* Jvals /*[dev] nnz or NULL*/, int flags);
+/* y = J x (vectorised species-sparse BSR SpMV) */
+int fb_spmv(fb_ctx* ctx, const double* Jvals /*[dev]*/, const double* x /*[dev]*/,
+            double* y /*[dev]*/);
+/* fused vector kernels (warp-shuffle reductions); results land in out[] on host */
+int fb_dot(fb_ctx* ctx, const double* x, const double* y, double* out /*[host]*/);
+int fb_axpy(fb_ctx* ctx, double a, const double* x, double* y); /* y += a x */
+/* solve J y = b; returns iterations and final relative residual */
+int fb_linear_solve(fb_ctx* ctx, const double* Jvals /*[dev]*/, const double* b /*[dev]*/,
+                    double* y /*[dev]*/, int ksp, int pc, double rtol, double atol, int max_it,
+                    int* iters /*[host]*/, double* relres /*[host]*/);
+/* full Newton solve (SNES newtonls, line search none) with the FESTIM stopping rule
+ * (reference helpers.py:408-426).  u is updated in place. */
+int fb_newton_solve(fb_ctx* ctx, double* u /*[dev]*/, const double* u_n /*[dev]*/, double atol,
+                    double rtol, double stol, int max_it, int ksp, int pc, double ksp_rtol,
+                    int ksp_max_it, int* n_its, int* reason, double* fnorm,
+                    int* total_linear_its);
+/* timing of the last fb_newton_solve, CUDA events on ctx's stream, milliseconds:
+ * out[0]=assembly F, out[1]=assembly J(+F), out[2]=linear solve, out[3]=other */
+int fb_last_timings(fb_ctx* ctx, double* out /*[host] 4*/);
+
+/* adaptive step size (reference stepsize.py:144-167); milestones sorted ascending */
+double fb_stepsize_modify(double value, int nb_iterations, double t, int adaptive,
+                          double growth_factor, double cutback_factor, int target_nb_iterations,
+                          double max_stepsize /* <=0: none */, int n_milestones,
+                          const double* milestones, double milestone_tolerance);
+
+/* -- derived quantities (reference exports/total_volume.py:23-33,
+ *    exports/surface_flux.py:39-60) ------------------------------------------------- */
+int fb_total_volume(fb_ctx* ctx, const double* u /*[dev]*/, int species, int vtag,
+                    double* out /*[host]*/);
+int fb_total_surface(fb_ctx* ctx, const double* u /*[dev]*/, int species, int stag,
+                     double* out /*[host]*/);
+/* D_h = DG1 interpolant of D0[vtag]*exp(-ED[vtag]/kB/T_D(vertex)); T_D is the
+ * temperature snapshot of the last D_global refresh */
+int fb_surface_flux(fb_ctx* ctx, const double* u /*[dev]*/, int species, int stag,
+                    double T_D_const, const double* T_D_nodal /*[dev] or NULL*/,
+                    double* out /*[host]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FESTIM_B200_H */

@@ -38,6 +38,23 @@ def convergence_test(it, snorm, fnorm, f0, rtol, atol, stol, max_it):
     return ITERATING
 
 
+def lu_solve(J, b):
+    """Exact solve standing for KSP preonly + PC lu (MUMPS / SuperLU_dist scale
+    the matrix before factorising): row equilibration, SuperLU, one step of
+    iterative refinement so every species equation is solved to round-off even
+    when their scales differ by many orders of magnitude."""
+    import scipy.sparse as sp
+
+    J = J.tocsr()
+    scale = 1.0 / np.maximum(abs(J).max(axis=1).toarray().ravel(), 1e-300)
+    A = (sp.diags(scale) @ J).tocsc()
+    rhs = scale * b
+    lu = spla.splu(A)
+    y = lu.solve(rhs)
+    y += lu.solve(rhs - A @ y)
+    return y
+
+
 class _Snes:
     def __init__(self):
         self.reason = 0
@@ -110,7 +127,7 @@ class OracleNewtonSolver:
             if it >= self.max_it:
                 reason = DIVERGED_MAX_IT
                 break
-            y = spla.splu(J.tocsc()).solve(b)
+            y = lu_solve(J, b)
             if not np.all(np.isfinite(y)):
                 reason = DIVERGED_LINEAR_SOLVE
                 break
