@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the FESTIM hot path on B200: Newton-step DOFs/s.
+
+A "step" is one pass of the hot path over the workload: a full Newton solve of
+the configuration (assemble F and J, Krylov solve, update, residual check),
+timed on the device; the metric is dofs / (solve time / Newton iterations).
+Default workload: BASELINE.json configs[1] (C1), the 3D unit-cube MMS steady
+diffusion problem of reference test_1_mobile_MMS_3D on an n=55 Kuhn mesh
+(998 250 cells, 175 616 dofs).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--workload c1|c1small] [--n 55]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "newton_step_dofs_per_s"
+UNIT = "DOFs/s"
+
+
+def build_workload(name, n):
+    from cases import mms_1_mobile_steady
+
+    if name in ("c1", "c1small"):
+        return mms_1_mobile_steady(3, n)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def spmv_bytes(spec, nnzb):
+    nv, ns = spec.mesh.num_vertices, spec.ns
+    return 8 * spec.npairs * nnzb + 4 * nnzb + 4 * (nv + 1) + 16 * nv * ns
+
+
+def assembly_bytes(spec, nnzb):
+    m = spec.mesh
+    d = m.tdim
+    return (m.num_cells * (4 * (d + 1) + 4) + m.num_vertices * (8 * d + 8 * spec.T_mode + 16 * spec.ns)
+            + 8 * spec.npairs * nnzb + 8 * m.num_vertices * spec.ns)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", "0", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nme, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        import statistics
+
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_cpu_sample(n_small, steps=1):
+    """Oracle (restated reference path: numpy assembly + SuperLU) on a bounded sample."""
+    from oracle.newton import OracleBackend
+
+    best = None
+    ndofs = its = 0
+    for _ in range(steps):
+        m, H, _ = build_workload("c1", n_small)
+        m.solver_backend = OracleBackend()
+        m.initialise()
+        t0 = time.perf_counter()
+        m.run()
+        dt = time.perf_counter() - t0
+        its = max(m.solver.solver.getIterationNumber(), 1)
+        ndofs = m.u.x.array.size
+        best = dt if best is None else min(best, dt)
+    return ndofs / (best / its), ndofs, best, its
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c1")
+    ap.add_argument("--n", type=int, default=55)
+    ap.add_argument("--cpu-n", type=int, default=24)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"C1: 3D unit-cube MMS steady diffusion (reference test_1_mobile_MMS_3D), "
+                          f"P1 tets n={args.n}", "n": args.n,
+              "cells": 6 * args.n ** 3, "dofs": (args.n + 1) ** 3,
+              "l2": "L2 flushed (512 MiB write) between timed steps",
+              "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (weak)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        warm = max(args.warmup, 0)
+        for _ in range(min(warm, 1)):
+            run_cpu_sample(8)
+        vals = [run_cpu_sample(args.cpu_n) for _ in range(max(1, min(args.steps, 3)))]
+        v = max(x[0] for x in vals)
+        ndofs, secs, its = vals[0][1], min(x[2] for x in vals), vals[0][3]
+        sample = (f"same problem on an n={args.cpu_n} mesh ({ndofs} dofs): numpy assembly + SuperLU "
+                  f"Newton solve, {secs:.2f} s per solve, {its} Newton it")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / its,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "restated reference path (numpy/scipy SuperLU), NOT dolfinx+PETSc "
+                    "(absent from this image)"}))
+        return
+
+    import numpy as np
+    import torch
+
+    import __graft_entry__ as g
+
+    g.build()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    import ctypes as C
+
+    from festim_b200.backend import B200Backend
+
+    model, H, exact = build_workload(args.workload, args.n)
+    model.solver_backend = B200Backend(device=local_rank)
+    model.initialise()
+    solver = model.solver
+    ctx = solver.ctx
+    lib = ctx.lib
+    N = ctx.n_dofs
+    nnzb = len(solver.spec.mesh.graph[1])
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+    u0 = np.zeros(N)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps ("value") -----------------------------------------
+    solver._push_state()
+    u_dev = ctx.zeros(N)
+    n_its, reason, lin = C.c_int(0), C.c_int(0), C.c_int(0)
+    fnorm = C.c_double(0.0)
+
+    def device_step():
+        u_dev.zero_()
+        rc = lib.fb_newton_solve(ctx.h, ctx.ptr(u_dev), ctx.ptr(u_dev), float(solver.atol),
+                                 float(solver.rtol), solver.stol, solver.max_it, solver.ksp,
+                                 solver.pc, solver.ksp_rtol, solver.ksp_max_it, C.byref(n_its),
+                                 C.byref(reason), C.byref(fnorm), C.byref(lin))
+        ctx._check(rc)
+        assert reason.value > 0, reason.value
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler()
+    sampler.start()
+    barrier()
+    l0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    phase = np.zeros(4)
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        ev[k][0].record()
+        device_step()
+        ev[k][1].record()
+        tm = (C.c_double * 4)()
+        lib.fb_last_timings(ctx.h, tm)
+        phase += np.array(list(tm))
+    barrier()
+    launches = ctx.launches - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    newton_its = max(n_its.value, 1)
+    lin_its = lin.value
+    phase /= args.steps
+
+    # ---- end to end through the public API ("e2e") -------------------------------
+    def api_step():
+        model.u.x.array[:] = u0
+        solver.solve()
+        return float(model.u.x.array[0])
+
+    api_step()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        api_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d = 8 * N + 8 * len(solver._bc_dofs)
+    d2h = 8 * N
+
+    # ---- roofline of the dominant kernel (fused SpMV + dots of the CG iteration) ----
+    J = ctx.zeros(ctx.nnz)
+    Fv = ctx.zeros(N)
+    ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(u_dev), ctx.ptr(Fv), ctx.ptr(J), 3))
+    x = torch.rand(N, dtype=torch.float64, device=ctx.device)
+    y = ctx.zeros(N)
+    reps = 50
+    for _ in range(5):
+        lib.fb_spmv(ctx.h, ctx.ptr(J), ctx.ptr(x), ctx.ptr(y))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        lib.fb_spmv(ctx.h, ctx.ptr(J), ctx.ptr(x), ctx.ptr(y))
+    b.record()
+    torch.cuda.synchronize()
+    spmv_ms = a.elapsed_time(b) / reps
+    a.record()
+    for _ in range(reps):
+        lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(u_dev), ctx.ptr(Fv), ctx.ptr(J), 3)
+    b.record()
+    torch.cuda.synchronize()
+    asm_ms = a.elapsed_time(b) / reps
+    peak, peak_src = peaks()
+    B_spmv = spmv_bytes(solver.spec, nnzb)
+    B_asm = assembly_bytes(solver.spec, nnzb)
+    ach = B_spmv / (spmv_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_spmv (SpMV of the CG iteration)", "bound": "hbm", "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes": B_spmv, "ms": spmv_ms,
+                "note": "C1's 34 MB SpMV working set is L2-resident (126 MB L2): the fraction is "
+                        "against the HBM copy peak but the data comes from L2",
+                "assembly": {"kernel": "k_assemble_nodes<3> (F+J gather)", "algorithmic_bytes": B_asm,
+                             "ms": asm_ms, "achieved": B_asm / (asm_ms * 1e-3) / 1e9,
+                             "frac": B_asm / (asm_ms * 1e-3) / 1e9 / peak}}
+
+    val = N / (ms * 1e-3 / newton_its)
+    e2e_val = N / (e2e_s / newton_its)
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=ctx.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        val = world * N / (ms * 1e-3 / newton_its)
+        e2e_val = world * N / (e2e_s / newton_its)
+    if rank != 0:
+        return
+    out = {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "newton_iterations_per_step": newton_its, "linear_iterations_per_step": lin_its,
+        "phase_ms": {"assemble_F": phase[0], "assemble_J": phase[1], "linear_solve": phase[2],
+                     "update": phase[3]},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+    }
+    if world == 1:
+        t0 = time.perf_counter()
+        v, ndofs, secs, its = run_cpu_sample(args.cpu_n)
+        out["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"same problem on an n={args.cpu_n} mesh ({ndofs} dofs): numpy assembly + "
+                      f"SuperLU Newton solve, {secs:.2f} s per solve ({its} Newton it); "
+                      "restated reference path, not dolfinx+PETSc"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

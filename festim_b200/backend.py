@@ -223,7 +223,9 @@ class B200NewtonSolver:
         self.pc = PC.get(pc, 0)
         # the reference's default is an exact LU solve: use a Krylov tolerance far
         # below the Newton tolerance so Newton iteration counts are unchanged
-        self.ksp_rtol = float(petsc_options.get("ksp_rtol", 1e-12 if ksp == "preonly" else 1e-10))
+        snes_rtol = self.rtol if isinstance(self.rtol, (int, float)) else 1e-10
+        exact_like = min(1e-12, max(1e-2 * float(snes_rtol), 1e-15))
+        self.ksp_rtol = float(petsc_options.get("ksp_rtol", exact_like if ksp == "preonly" else 1e-10))
         self.ksp_max_it = int(petsc_options.get("ksp_max_it", 20000))
         self.solver = _Snes()
         self.timings = np.zeros(4)

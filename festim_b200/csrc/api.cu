@@ -137,6 +137,18 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   S.npairs = ints[I_NPAIRS]; S.n_diffE = ints[I_NDIFFE]; S.n_slots = ints[I_NSLOTS];
   S.n_fields = ints[I_NFIELDS];
   ctx->dt_scalar = ints[I_DT_SCALAR];
+  // J is symmetric positive definite when nothing but diffusion and mass contributes:
+  // no advection and no point term with a solution derivative (reactions couple species
+  // with different coefficients in each direction)
+  ctx->symmetric = (S.n_adv == 0);
+  for (int pass = 0; pass < 2; ++pass) {
+    const Section& hs = secs[pass == 0 ? S_VTERM_HDR : S_FTERM_HDR];
+    const int nterms = pass == 0 ? S.n_vterms : S.n_fterms;
+    if (hs.id == 0) continue;
+    const int* h = (const int*)(blob + hs.offset);
+    for (int t = 0; t < nterms; ++t)
+      if (h[t * 8 + 5] > 0) ctx->symmetric = false;
+  }
   S.n_dofs = S.n_vertices * S.ns;
   const int n_scalars = ints[I_NSCALARS];
   int rc;

@@ -78,6 +78,7 @@ struct fb_ctx {
   bool have_mesh = false, have_pattern = false, have_spec = false;
   long long nnzb = 0, n_bc = 0;
   bool tridiag = false;
+  bool symmetric = false;
   int dt_scalar = -1;
   std::vector<void*> owned;  // device allocations freed in fb_destroy
   // mutable device buffers

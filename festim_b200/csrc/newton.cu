@@ -4,6 +4,7 @@
 // reference configures it (src/festim/problem.py:279-289) together with FESTIM's
 // own stopping rule (src/festim/helpers.py:408-426).
 #include <cmath>
+#include <cstdlib>
 
 #include "fb_internal.cuh"
 #include "reduce.cuh"
@@ -62,7 +63,7 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
   if (!u_n) u_n = u;
   if (ksp == FB_KSP_AUTO) {
     if (ctx->tridiag) ksp = FB_KSP_TRIDIAG;
-    else ksp = ctx->S.n_adv == 0 && ctx->S.npairs == ctx->S.ns && !ctx->S.n_vterms ? FB_KSP_CG : FB_KSP_GMRES;
+    else ksp = ctx->symmetric ? FB_KSP_CG : FB_KSP_GMRES;
   }
   int it = 0, lin_total = 0, why = 0;
   double snorm = 0.0, f0 = 1.0, fn = 0.0;
@@ -94,6 +95,9 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
       t.stop();
     }
     lin_total += lin_its;
+    if (getenv("FB_VERBOSE"))
+      fprintf(stderr, "[fb] newton it=%d fnorm=%.6e (f0=%.3e) linear its=%d relres=%.3e rc=%d\n", it, fn, f0,
+              lin_its, relres, rc);
     if (rc < 0) return rc;
     if (rc > 0) { why = FB_DIVERGED_LINEAR_SOLVE; break; }
     {
