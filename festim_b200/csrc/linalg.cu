@@ -7,8 +7,9 @@
 // device: every reduction finishes in the last block of the kernel that produced
 // the partial sums (ticket counter), which also advances the recurrence, so an
 // iteration is two launches for CG and the host only polls a "done" flag.
-#include "fb_internal.cuh"
+#include <cstdlib>
 
+#include "fb_internal.cuh"
 #include "reduce.cuh"
 
 // ---------------------------------------------------------------------------
@@ -34,8 +35,11 @@ __device__ __forceinline__ double spmv_row(const DevSpec& S, const double* __res
       sum += vals[e] * x[(long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]];
     }
   }
+  // reduce over the G lanes of this row only: neighbouring groups of the warp may
+  // have left already (ragged tail), so the shuffle mask names just this group
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
   return sum;
 }
 
@@ -257,7 +261,7 @@ k_cg_spmv_dots(DevSpec S, const double* __restrict__ J, const double* __restrict
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
   const int lane = threadIdx.x % G;
   double v[3] = {0.0, 0.0, 0.0}, tot[3];
-  if (row < S.n_dofs) {
+  if (row < S.n_dofs) {  // uniform within each G-lane group
     const double sum = spmv_row<G>(S, J, u, row, lane);
     if (lane == 0) {
       w[row] = sum;
@@ -284,6 +288,215 @@ k_cg_spmv_dots(DevSpec S, const double* __restrict__ J, const double* __restrict
       sc[0] = alpha; sc[1] = beta; sc[2] = gamma_new;
       flags[1] = it + 1;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Persistent CG: the whole Chronopoulos-Gear iteration in ONE cooperative kernel.
+// Each block owns a contiguous range of vertices (and their dof rows) for the
+// life of the solve; two grid barriers per iteration (after the vector update,
+// after SpMV + partial dots); every block reduces the per-block partial sums in
+// the same order, so alpha/beta are bitwise identical everywhere and no scalar
+// is broadcast.  When the operator fits, the rows a block owns are staged ONCE
+// into shared memory (values + column indices, up to 227 KB per SM = 33 MB per
+// B200) and every iteration after that reads only the gathered vector entries
+// from L2: for the L2-resident configs the SpMV leaves the L2/HBM roofline
+// behind and the iteration cost is the two grid barriers.
+// ---------------------------------------------------------------------------
+struct CgArgs {
+  const double* J; const double* dinv; const double* b;
+  double* x; double* r; double* u; double* w; double* p; double* s;
+  double* partials; unsigned* bar; double* sc; int* flags;
+  double thr2; int max_it; int rows_in_smem;  // rows_in_smem: 1 = stage owned rows in smem
+  long long smem_entries;                       // capacity (values) of the staging area
+};
+
+// Grid barrier for a cooperative (co-resident) launch: arrival counter + generation.
+// A bounded spin turns a scheduling problem into an error code instead of a hang:
+// bar[64] is an abort flag every later barrier honours.  Returns false on abort.
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks) {
+  __shared__ int ok_s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* gen = bar + 32;
+    volatile unsigned* abort_flag = bar + 64;
+    int ok = (*abort_flag == 0u);
+    if (ok) {
+      const unsigned g = *gen;
+      __threadfence();
+      if (atomicAdd(bar, 1u) == nblocks - 1) {
+        *((volatile unsigned*)bar) = 0u;
+        __threadfence();
+        atomicAdd((unsigned*)gen, 1u);
+      } else {
+        unsigned long long spins = 0;
+        while (*gen == g) {
+          if (++spins > (1ull << 24)) { atomicExch((unsigned*)abort_flag, 1u); break; }
+          if ((spins & 1023u) == 0u && *abort_flag) break;
+        }
+        if (*abort_flag) ok = 0;
+      }
+      __threadfence();
+    }
+    ok_s = ok;
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+
+template <int G>
+__global__ void __launch_bounds__(1024, 1)
+k_cg_persistent(DevSpec S, CgArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[3][32];
+  __shared__ double tot[3];
+  const int ns = S.ns;
+  const unsigned nb = gridDim.x;
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  // vertex / row ownership
+  const long long vper = (S.n_vertices + nb - 1) / nb;
+  const long long v0 = (long long)blockIdx.x * vper;
+  const long long v1 = (v0 + vper < S.n_vertices) ? v0 + vper : S.n_vertices;
+  const long long row0 = v0 * ns, row1 = (v1 > v0 ? v1 : v0) * ns;
+  // ---- stage the owned rows in shared memory -------------------------------
+  // layout: vals[cap] (double) | cols[cap] (int: scalar column index) | rstart[nrows+1] (int)
+  double* svals = (double*)smem_raw;
+  int* scols = (int*)(svals + A.smem_entries);
+  int* rstart = scols + A.smem_entries;
+  const long long nrows = row1 - row0;
+  bool staged = false;
+  if (A.rows_in_smem && nrows > 0) {
+    const long long e0 = (long long)S.rowptr[v0] * S.npairs;
+    const long long e1 = (long long)S.rowptr[v1] * S.npairs;
+    staged = (e1 - e0) <= A.smem_entries;
+    if (staged) {
+      for (long long e = tid; e < e1 - e0; e += T) svals[e] = A.J[e0 + e];
+      for (long long rr = tid; rr < nrows; rr += T) {
+        const long long row = row0 + rr;
+        const long long v = row / ns;
+        const int sp = (int)(row - v * ns);
+        const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+        const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
+        const long long start = (long long)r0 * S.npairs + (long long)deg * pp - e0;
+        rstart[rr] = (int)start;
+        for (int e = 0; e < deg * nc; ++e) {
+          const int k = e / nc, j = e - k * nc;
+          scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
+        }
+        if (rr == nrows - 1) rstart[nrows] = (int)(start + (long long)deg * nc);
+      }
+    }
+  }
+  // rows of one vertex block are contiguous but a row's end is the next row's
+  // start only within the same (v, s) ordering, which is how rstart was filled
+  // ---- init ------------------------------------------------------------------
+  for (long long v = v0 + tid; v < v1; v += T) {
+    double rin[FB_MAX_NS], zo[FB_MAX_NS];
+    for (int sp = 0; sp < ns; ++sp) {
+      const long long i = v * ns + sp;
+      rin[sp] = A.b[i];
+      A.r[i] = rin[sp]; A.x[i] = 0.0; A.p[i] = 0.0; A.s[i] = 0.0;
+    }
+    bjacobi_apply(ns, A.dinv, v, rin, zo);
+    for (int sp = 0; sp < ns; ++sp) A.u[v * ns + sp] = zo[sp];
+  }
+  if (!grid_barrier(A.bar, nb)) return;
+  double alpha = 0.0, beta = 0.0, gamma_old = 0.0;
+  int it = 0, done = 0, breakdown = 0;
+  const int ngroups = T / G, grp = tid / G, gl = tid % G;
+  while (true) {
+    // ---- phase B: w = A u on owned rows + partial dots ----------------------
+    double v3[3] = {0.0, 0.0, 0.0};
+    for (long long rr = grp; rr < nrows; rr += ngroups) {
+      const long long row = row0 + rr;
+      double sum = 0.0;
+      if (staged) {
+        const int a0 = rstart[rr];
+        // end of this row: rows are stored back to back in (v, s) order
+        const long long v = row / ns;
+        const int sp = (int)(row - v * ns);
+        const int n = (S.rowptr[v + 1] - S.rowptr[v]) * S.pair_nc[sp];
+        for (int e = gl; e < n; e += G) sum += svals[a0 + e] * __ldcg(A.u + scols[a0 + e]);
+      } else {
+        const long long v = row / ns;
+        const int sp = (int)(row - v * ns);
+        const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+        const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
+        const double* __restrict__ vals = A.J + (long long)r0 * S.npairs + (long long)deg * pp;
+        const int n = deg * nc;
+        for (int e = gl; e < n; e += G) {
+          const int k = e / nc, j = e - k * nc;
+          sum += vals[e] * __ldcg(A.u + (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]);
+        }
+      }
+      const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
+      if (gl == 0) {
+        A.w[row] = sum;
+        const double ri = __ldcg(A.r + row), ui = __ldcg(A.u + row);
+        v3[0] += ri * ui; v3[1] += sum * ui; v3[2] += ui * ui;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double sred = warp_sum(v3[k]);
+      if (lane == 0) red[k][wid] = sred;
+    }
+    __syncthreads();
+    if (tid < 3) {
+      double sacc = 0.0;
+      for (int q = 0; q < nw; ++q) sacc += red[tid][q];
+      A.partials[(size_t)tid * nb + blockIdx.x] = sacc;
+    }
+    if (!grid_barrier(A.bar, nb)) return;
+    // ---- every block: identical reduction of the partials ----------------------
+    for (int k = 0; k < 3; ++k) {
+      double sacc = 0.0;
+      for (unsigned bq = tid; bq < nb; bq += T) sacc += __ldcg(A.partials + (size_t)k * nb + bq);
+      sacc = warp_sum(sacc);
+      if (lane == 0) red[k][wid] = sacc;
+    }
+    __syncthreads();
+    if (tid < 3) {
+      double sacc = 0.0;
+      for (int q = 0; q < nw; ++q) sacc += red[tid][q];
+      tot[tid] = sacc;
+    }
+    __syncthreads();
+    const double gamma_new = tot[0], delta = tot[1], uu = tot[2];
+    __syncthreads();
+    if (uu <= A.thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
+    else if (it >= A.max_it) { done = 2; }
+    else {
+      if (it == 0) { beta = 0.0; alpha = gamma_new / delta; }
+      else { beta = gamma_new / gamma_old; alpha = gamma_new / (delta - beta * gamma_new / alpha); }
+      if (!(alpha == alpha) || isinf(alpha)) { done = 1; breakdown = 1; }
+      gamma_old = gamma_new;
+    }
+    if (done) {
+      if (blockIdx.x == 0 && tid == 0) {
+        A.flags[0] = (done == 1); A.flags[1] = it; A.flags[2] = breakdown; A.sc[3] = uu;
+      }
+      break;
+    }
+    ++it;
+    // ---- phase A: vector update on owned vertices ------------------------------
+    for (long long v = v0 + tid; v < v1; v += T) {
+      double rin[FB_MAX_NS], zo[FB_MAX_NS];
+      for (int sp = 0; sp < ns; ++sp) {
+        const long long i = v * ns + sp;
+        const double pi = __ldcg(A.u + i) + beta * A.p[i];
+        const double si = __ldcg(A.w + i) + beta * A.s[i];
+        A.p[i] = pi; A.s[i] = si;
+        A.x[i] += alpha * pi;
+        rin[sp] = __ldcg(A.r + i) - alpha * si;
+        A.r[i] = rin[sp];
+      }
+      bjacobi_apply(ns, A.dinv, v, rin, zo);
+      for (int sp = 0; sp < ns; ++sp) A.u[v * ns + sp] = zo[sp];
+    }
+    if (!grid_barrier(A.bar, nb)) return;
   }
 }
 
@@ -552,10 +765,10 @@ int fbi_ensure_workspace(fb_ctx* ctx) {
   if (red < 3 * spmv_blocks + 16) red = 3 * spmv_blocks + 16;
   ctx->red_doubles = (long long)red;
   if ((rc = fb_alloc(ctx, &ctx->d_red, red))) return rc;
-  if ((rc = fb_alloc(ctx, &ctx->d_ticket, 4))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_ticket, 256))) return rc;
   if ((rc = fb_alloc(ctx, &ctx->d_flags, 8))) return rc;
   if ((rc = fb_alloc(ctx, &ctx->d_dinv, (size_t)S.n_vertices * S.ns * S.ns))) return rc;
-  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_ticket, 0, 16, ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_ticket, 0, 256 * sizeof(unsigned), ctx->stream));
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
   FB_CHECK(ctx, cudaMallocHost((void**)&ctx->h_pinned, 64 * sizeof(double)));
   return 0;
@@ -577,6 +790,64 @@ static int read_flags(fb_ctx* ctx, int* out4) {
   const int* f = (const int*)(ctx->h_pinned + 8);
   for (int i = 0; i < 4; ++i) out4[i] = f[i];
   return 0;
+}
+
+static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, double* y, double thr2,
+                               int max_it, int* iters) {
+  const DevSpec& S = ctx->S;
+  int rc = ensure_vectors(ctx, 5);
+  if (rc) return rc;
+  const long long N = S.n_dofs;
+  CgArgs A;
+  A.J = J; A.dinv = ctx->d_dinv; A.b = b; A.x = y;
+  A.r = ctx->d_work; A.u = A.r + N; A.w = A.u + N; A.p = A.w + N; A.s = A.p + N;
+  A.partials = ctx->d_red; A.bar = ctx->d_ticket + 64; A.sc = ctx->d_sc; A.flags = ctx->d_flags;
+  A.thr2 = thr2; A.max_it = max_it;
+  const int G = spmv_group(S);
+  const int T = 1024;
+  const unsigned nb = (unsigned)ctx->sm_count;
+  // staging capacity: 12 bytes per stored value + 4 bytes per owned row
+  const long long vper = (S.n_vertices + nb - 1) / nb;
+  const long long rows_per_block = vper * S.ns;
+  size_t smem_max = 0;
+  {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    smem_max = (size_t)v - 1024;  // static shared (reduction scratch)
+  }
+  long long cap = ((long long)smem_max - 4 * (rows_per_block + 2)) / 12;
+  cap &= ~1LL;
+  const long long avg_entries = ctx->nnzb * S.npairs / nb + 1;
+  A.rows_in_smem = (cap >= avg_entries) && !getenv("FB_NO_SMEM_OPERATOR");
+  A.smem_entries = A.rows_in_smem ? cap : 0;
+  const size_t smem = A.rows_in_smem ? (size_t)(12 * cap + 4 * (rows_per_block + 2)) : 0;
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
+  void* args[] = {(void*)&S, (void*)&A};
+  const void* fn = nullptr;
+  switch (G) {
+    case 4: fn = (const void*)k_cg_persistent<4>; break;
+    case 8: fn = (const void*)k_cg_persistent<8>; break;
+    case 16: fn = (const void*)k_cg_persistent<16>; break;
+    default: fn = (const void*)k_cg_persistent<32>; break;
+  }
+  FB_CHECK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FB_CHECK(ctx, cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(T), args, smem, ctx->stream));
+  ctx->launches++;
+  int fl[4];
+  if ((rc = read_flags(ctx, fl))) return rc;
+  unsigned hb[3] = {0, 0, 0};
+  FB_CHECK(ctx, cudaMemcpy(&hb[0], A.bar, 4, cudaMemcpyDeviceToHost));
+  FB_CHECK(ctx, cudaMemcpy(&hb[1], A.bar + 32, 4, cudaMemcpyDeviceToHost));
+  FB_CHECK(ctx, cudaMemcpy(&hb[2], A.bar + 64, 4, cudaMemcpyDeviceToHost));
+  if (hb[2]) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "persistent CG: grid barrier timed out (count=%u gen=%u blocks=%u)", hb[0], hb[1], nb);
+    FB_CHECK(ctx, cudaMemset(A.bar, 0, 130 * sizeof(unsigned)));
+    return fb_fail(ctx, msg);
+  }
+  *iters = fl[1];
+  if (fl[2]) return 1;
+  return fl[0] ? 0 : 2;
 }
 
 static int solve_cg(fb_ctx* ctx, const double* J, const double* b, double* y, double thr2, int max_it,
@@ -744,7 +1015,9 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
       if ((rc = fbi_norm2(ctx, corr, &pn))) return rc;
       thr_r = 1e-3 * pn;
     }
-    if (ksp == FB_KSP_CG) status = solve_cg(ctx, J, rhs, sol, thr_r * thr_r, max_it, &its);
+    if (ksp == FB_KSP_CG)
+      status = getenv("FB_CG_MULTIKERNEL") ? solve_cg(ctx, J, rhs, sol, thr_r * thr_r, max_it, &its)
+                                           : solve_cg_persistent(ctx, J, rhs, sol, thr_r * thr_r, max_it, &its);
     else status = solve_gmres(ctx, J, rhs, sol, thr_r, max_it, &its);
     *iters += its;
     if (status < 0) return status;
