@@ -308,35 +308,49 @@ struct CgArgs {
   double* x; double* r; double* u; double* w; double* p; double* s;
   double* partials; unsigned* bar; double* sc; int* flags;
   double thr2; int max_it; int rows_in_smem;  // rows_in_smem: 1 = stage owned rows in smem
+  unsigned bar_base;                            // value of the arrival counter at launch
   long long smem_entries;                       // capacity (values) of the staging area
 };
 
-// Grid barrier for a cooperative (co-resident) launch: arrival counter + generation.
-// A bounded spin turns a scheduling problem into an error code instead of a hang:
-// bar[64] is an abort flag every later barrier honours.  Returns false on abort.
-__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks) {
+// Grid barrier for a cooperative (co-resident) launch.  bar[0] is a monotonically
+// increasing arrival counter (release-add), bar[32] the generation the last arriver
+// publishes (release store) and everybody else polls (acquire load); the caller keeps
+// its generation number in a register, so a barrier costs one atomic round trip plus
+// one poll round trip.  A bounded spin turns a scheduling problem into an error code
+// instead of a hang (bar[64] = abort flag).  Returns false on abort.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_add_release_u32(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen,
+                                             unsigned base_count) {
   __shared__ int ok_s;
   __syncthreads();
+  ++gen;
   if (threadIdx.x == 0) {
-    volatile unsigned* gen = bar + 32;
-    volatile unsigned* abort_flag = bar + 64;
-    int ok = (*abort_flag == 0u);
-    if (ok) {
-      const unsigned g = *gen;
-      __threadfence();
-      if (atomicAdd(bar, 1u) == nblocks - 1) {
-        *((volatile unsigned*)bar) = 0u;
-        __threadfence();
-        atomicAdd((unsigned*)gen, 1u);
-      } else {
-        unsigned long long spins = 0;
-        while (*gen == g) {
-          if (++spins > (1ull << 24)) { atomicExch((unsigned*)abort_flag, 1u); break; }
-          if ((spins & 1023u) == 0u && *abort_flag) break;
+    int ok = 1;
+    const unsigned old = atom_add_release_u32(bar, 1u);
+    if (old - base_count == gen * nblocks - 1u) {
+      st_release_u32(bar + 32, gen);
+    } else {
+      unsigned spins = 0;
+      while (ld_acquire_u32(bar + 32) != gen) {
+        __nanosleep(64);  // keep the pollers off the L2 slice the workers still need
+        if ((++spins & 0xfffu) == 0u) {
+          if (spins > (1u << 24)) { atomicExch(bar + 64, 1u); ok = 0; break; }
+          if (ld_acquire_u32(bar + 64)) { ok = 0; break; }
         }
-        if (*abort_flag) ok = 0;
       }
-      __threadfence();
     }
     ok_s = ok;
   }
@@ -353,17 +367,19 @@ k_cg_persistent(DevSpec S, CgArgs A) {
   const int ns = S.ns;
   const unsigned nb = gridDim.x;
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
-  // vertex / row ownership
+  // vertex / row ownership: a contiguous range per block
   const long long vper = (S.n_vertices + nb - 1) / nb;
   const long long v0 = (long long)blockIdx.x * vper;
   const long long v1 = (v0 + vper < S.n_vertices) ? v0 + vper : S.n_vertices;
-  const long long row0 = v0 * ns, row1 = (v1 > v0 ? v1 : v0) * ns;
-  // ---- stage the owned rows in shared memory -------------------------------
-  // layout: vals[cap] (double) | cols[cap] (int: scalar column index) | rstart[nrows+1] (int)
+  const int nvloc = v1 > v0 ? (int)(v1 - v0) : 0;
+  const int nrows = nvloc * ns;
+  const long long row0 = v0 * ns;
+  // ---- stage the owned rows in shared memory ---------------------------------
+  // layout: vals[cap] (double) | cols[cap] (int, scalar column) | rstart[rows] | rlen[rows]
   double* svals = (double*)smem_raw;
   int* scols = (int*)(svals + A.smem_entries);
   int* rstart = scols + A.smem_entries;
-  const long long nrows = row1 - row0;
+  int* rlen = rstart + vper * ns;
   bool staged = false;
   if (A.rows_in_smem && nrows > 0) {
     const long long e0 = (long long)S.rowptr[v0] * S.npairs;
@@ -371,25 +387,22 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     staged = (e1 - e0) <= A.smem_entries;
     if (staged) {
       for (long long e = tid; e < e1 - e0; e += T) svals[e] = A.J[e0 + e];
-      for (long long rr = tid; rr < nrows; rr += T) {
-        const long long row = row0 + rr;
-        const long long v = row / ns;
-        const int sp = (int)(row - v * ns);
+      for (int rr = tid; rr < nrows; rr += T) {
+        const int vl = rr / ns, sp = rr - vl * ns;
+        const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
         const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
-        const long long start = (long long)r0 * S.npairs + (long long)deg * pp - e0;
-        rstart[rr] = (int)start;
+        const int start = (int)((long long)r0 * S.npairs + (long long)deg * pp - e0);
+        rstart[rr] = start;
+        rlen[rr] = deg * nc;
         for (int e = 0; e < deg * nc; ++e) {
           const int k = e / nc, j = e - k * nc;
           scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
         }
-        if (rr == nrows - 1) rstart[nrows] = (int)(start + (long long)deg * nc);
       }
     }
   }
-  // rows of one vertex block are contiguous but a row's end is the next row's
-  // start only within the same (v, s) ordering, which is how rstart was filled
-  // ---- init ------------------------------------------------------------------
+  // ---- init --------------------------------------------------------------------
   for (long long v = v0 + tid; v < v1; v += T) {
     double rin[FB_MAX_NS], zo[FB_MAX_NS];
     for (int sp = 0; sp < ns; ++sp) {
@@ -400,41 +413,61 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     bjacobi_apply(ns, A.dinv, v, rin, zo);
     for (int sp = 0; sp < ns; ++sp) A.u[v * ns + sp] = zo[sp];
   }
-  if (!grid_barrier(A.bar, nb)) return;
+  unsigned gen = 0;
+  const unsigned base_count = A.bar_base;
+  if (!grid_barrier(A.bar, nb, gen, base_count)) return;
   double alpha = 0.0, beta = 0.0, gamma_old = 0.0;
   int it = 0, done = 0, breakdown = 0;
   const int ngroups = T / G, grp = tid / G, gl = tid % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  const double* __restrict__ uvec = A.u;
+  long long tph[5] = {0, 0, 0, 0, 0};  // cycles per phase (block 0), reported in sc[8..12]
   while (true) {
-    // ---- phase B: w = A u on owned rows + partial dots ----------------------
+    long long c0 = clock64();
+    // ---- phase B: w = A u on owned rows + partial dots -------------------------
     double v3[3] = {0.0, 0.0, 0.0};
-    for (long long rr = grp; rr < nrows; rr += ngroups) {
-      const long long row = row0 + rr;
+    for (int rr = grp; rr < nrows; rr += ngroups) {
       double sum = 0.0;
+      const long long row = row0 + rr;
+      const double ri = __ldcg(A.r + row), ui = __ldcg(uvec + row);  // issued before the gathers
       if (staged) {
-        const int a0 = rstart[rr];
-        // end of this row: rows are stored back to back in (v, s) order
-        const long long v = row / ns;
-        const int sp = (int)(row - v * ns);
-        const int n = (S.rowptr[v + 1] - S.rowptr[v]) * S.pair_nc[sp];
-        for (int e = gl; e < n; e += G) sum += svals[a0 + e] * __ldcg(A.u + scols[a0 + e]);
+        const int a0 = rstart[rr], n = rlen[rr];
+        // all gathers of a batch are in flight before the first use (L2 latency once per batch)
+        for (int eb = gl; eb < n; eb += 8 * G) {
+          double uv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int e = eb + q * G;
+            uv[q] = e < n ? __ldcg(uvec + scols[a0 + e]) : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int e = eb + q * G;
+            if (e < n) sum += svals[a0 + e] * uv[q];
+          }
+        }
       } else {
-        const long long v = row / ns;
-        const int sp = (int)(row - v * ns);
+        const int vl = rr / ns, sp = rr - vl * ns;
+        const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
         const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
         const double* __restrict__ vals = A.J + (long long)r0 * S.npairs + (long long)deg * pp;
         const int n = deg * nc;
-        for (int e = gl; e < n; e += G) {
-          const int k = e / nc, j = e - k * nc;
-          sum += vals[e] * __ldcg(A.u + (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]);
+        if (nc == 1) {
+          const int cs = S.pair_cs[pp];
+          for (int e = gl; e < n; e += G)
+            sum += vals[e] * __ldcg(uvec + (long long)S.colidx[r0 + e] * ns + cs);
+        } else {
+          for (int e = gl; e < n; e += G) {
+            const int k = e / nc, j = e - k * nc;
+            sum += vals[e] * __ldcg(uvec + (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]);
+          }
         }
       }
-      const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
 #pragma unroll
       for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
       if (gl == 0) {
         A.w[row] = sum;
-        const double ri = __ldcg(A.r + row), ui = __ldcg(A.u + row);
         v3[0] += ri * ui; v3[1] += sum * ui; v3[2] += ui * ui;
       }
     }
@@ -449,23 +482,18 @@ k_cg_persistent(DevSpec S, CgArgs A) {
       for (int q = 0; q < nw; ++q) sacc += red[tid][q];
       A.partials[(size_t)tid * nb + blockIdx.x] = sacc;
     }
-    if (!grid_barrier(A.bar, nb)) return;
-    // ---- every block: identical reduction of the partials ----------------------
-    for (int k = 0; k < 3; ++k) {
+    long long c1 = clock64();
+    if (!grid_barrier(A.bar, nb, gen, base_count)) return;
+    long long c2 = clock64();
+    // ---- every block: identical reduction of the partials ------------------------
+    if (wid < 3) {
       double sacc = 0.0;
-      for (unsigned bq = tid; bq < nb; bq += T) sacc += __ldcg(A.partials + (size_t)k * nb + bq);
+      for (unsigned bq = lane; bq < nb; bq += 32) sacc += __ldcg(A.partials + (size_t)wid * nb + bq);
       sacc = warp_sum(sacc);
-      if (lane == 0) red[k][wid] = sacc;
-    }
-    __syncthreads();
-    if (tid < 3) {
-      double sacc = 0.0;
-      for (int q = 0; q < nw; ++q) sacc += red[tid][q];
-      tot[tid] = sacc;
+      if (lane == 0) tot[wid] = sacc;
     }
     __syncthreads();
     const double gamma_new = tot[0], delta = tot[1], uu = tot[2];
-    __syncthreads();
     if (uu <= A.thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
     else if (it >= A.max_it) { done = 2; }
     else {
@@ -477,26 +505,33 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     if (done) {
       if (blockIdx.x == 0 && tid == 0) {
         A.flags[0] = (done == 1); A.flags[1] = it; A.flags[2] = breakdown; A.sc[3] = uu;
+        for (int k = 0; k < 5; ++k) A.sc[8 + k] = (double)tph[k];
       }
       break;
     }
     ++it;
-    // ---- phase A: vector update on owned vertices ------------------------------
+    long long c3 = clock64();
+    // ---- phase A: vector update on owned vertices --------------------------------
     for (long long v = v0 + tid; v < v1; v += T) {
       double rin[FB_MAX_NS], zo[FB_MAX_NS];
       for (int sp = 0; sp < ns; ++sp) {
         const long long i = v * ns + sp;
-        const double pi = __ldcg(A.u + i) + beta * A.p[i];
-        const double si = __ldcg(A.w + i) + beta * A.s[i];
+        const double ui = __ldcg(A.u + i), wi = __ldcg(A.w + i), ri = __ldcg(A.r + i);
+        const double p_old = __ldcg(A.p + i), s_old = __ldcg(A.s + i), x_old = __ldcg(A.x + i);
+        const double pi = ui + beta * p_old;
+        const double si = wi + beta * s_old;
         A.p[i] = pi; A.s[i] = si;
-        A.x[i] += alpha * pi;
-        rin[sp] = __ldcg(A.r + i) - alpha * si;
+        A.x[i] = x_old + alpha * pi;
+        rin[sp] = ri - alpha * si;
         A.r[i] = rin[sp];
       }
       bjacobi_apply(ns, A.dinv, v, rin, zo);
       for (int sp = 0; sp < ns; ++sp) A.u[v * ns + sp] = zo[sp];
     }
-    if (!grid_barrier(A.bar, nb)) return;
+    long long c4 = clock64();
+    if (!grid_barrier(A.bar, nb, gen, base_count)) return;  // also protects tot[]
+    long long c5 = clock64();
+    tph[0] += c1 - c0; tph[1] += c2 - c1; tph[2] += c3 - c2; tph[3] += c4 - c3; tph[4] += c5 - c4;
   }
 }
 
@@ -803,10 +838,13 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
   A.r = ctx->d_work; A.u = A.r + N; A.w = A.u + N; A.p = A.w + N; A.s = A.p + N;
   A.partials = ctx->d_red; A.bar = ctx->d_ticket + 64; A.sc = ctx->d_sc; A.flags = ctx->d_flags;
   A.thr2 = thr2; A.max_it = max_it;
-  const int G = spmv_group(S);
+  // lanes per row: ~8 entries per lane keeps many independent gathers in flight
+  const double rowlen = (double)ctx->nnzb * S.npairs / (double)N;
+  int G = rowlen <= 20 ? 2 : rowlen <= 40 ? 4 : rowlen <= 80 ? 8 : rowlen <= 160 ? 16 : 32;
+  if (getenv("FB_CG_G")) G = atoi(getenv("FB_CG_G"));
   const int T = 1024;
   const unsigned nb = (unsigned)ctx->sm_count;
-  // staging capacity: 12 bytes per stored value + 4 bytes per owned row
+  // staging capacity: 12 bytes per stored value + 8 bytes per owned row
   const long long vper = (S.n_vertices + nb - 1) / nb;
   const long long rows_per_block = vper * S.ns;
   size_t smem_max = 0;
@@ -815,16 +853,19 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     smem_max = (size_t)v - 1024;  // static shared (reduction scratch)
   }
-  long long cap = ((long long)smem_max - 4 * (rows_per_block + 2)) / 12;
+  long long cap = ((long long)smem_max - 8 * (rows_per_block + 2)) / 12;
   cap &= ~1LL;
   const long long avg_entries = ctx->nnzb * S.npairs / nb + 1;
   A.rows_in_smem = (cap >= avg_entries) && !getenv("FB_NO_SMEM_OPERATOR");
   A.smem_entries = A.rows_in_smem ? cap : 0;
-  const size_t smem = A.rows_in_smem ? (size_t)(12 * cap + 4 * (rows_per_block + 2)) : 0;
+  const size_t smem = A.rows_in_smem ? (size_t)(12 * cap + 8 * (rows_per_block + 2)) : 0;
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(A.bar, 0, 130 * sizeof(unsigned), ctx->stream));
+  A.bar_base = 0u;
   void* args[] = {(void*)&S, (void*)&A};
   const void* fn = nullptr;
   switch (G) {
+    case 2: fn = (const void*)k_cg_persistent<2>; break;
     case 4: fn = (const void*)k_cg_persistent<4>; break;
     case 8: fn = (const void*)k_cg_persistent<8>; break;
     case 16: fn = (const void*)k_cg_persistent<16>; break;
@@ -846,6 +887,13 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
     return fb_fail(ctx, msg);
   }
   *iters = fl[1];
+  if (getenv("FB_VERBOSE") && fl[1] > 0) {
+    double ph[5];
+    FB_CHECK(ctx, cudaMemcpy(ph, ctx->d_sc + 8, sizeof(ph), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[fb] persistent CG G=%d smem=%d: cycles/iteration spmv+dots %.0f, barrier %.0f, reduce %.0f, "
+            "update %.0f, barrier %.0f\n", G, A.rows_in_smem, ph[0] / fl[1], ph[1] / fl[1], ph[2] / fl[1],
+            ph[3] / fl[1], ph[4] / fl[1]);
+  }
   if (fl[2]) return 1;
   return fl[0] ? 0 : 2;
 }

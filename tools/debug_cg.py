@@ -19,7 +19,7 @@ s._push_state()
 u = ctx.zeros(ctx.n_dofs); F = ctx.zeros(ctx.n_dofs); J = ctx.zeros(ctx.nnz); y = ctx.zeros(ctx.n_dofs)
 ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u), ctx.ptr(u), ctx.ptr(F), ctx.ptr(J), 3))
 torch.cuda.synchronize(); log("assembled")
-for mode in ("multi", "persistent-nosmem", "persistent"):
+for mode in sys.argv[4].split(","):
     os.environ.pop("FB_CG_MULTIKERNEL", None); os.environ.pop("FB_NO_SMEM_OPERATOR", None)
     if mode == "multi": os.environ["FB_CG_MULTIKERNEL"] = "1"
     if mode == "persistent-nosmem": os.environ["FB_NO_SMEM_OPERATOR"] = "1"
@@ -29,3 +29,10 @@ for mode in ("multi", "persistent-nosmem", "persistent"):
     rc = lib.fb_linear_solve(ctx.h, ctx.ptr(J), ctx.ptr(F), ctx.ptr(y), 1, 0, 1e-12, 0.0, maxit, C.byref(its), C.byref(rr))
     torch.cuda.synchronize()
     log(mode, "rc", rc, "its", its.value, "relres", rr.value, "time", time.time() - t1, lib.fb_last_error(ctx.h))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        lib.fb_linear_solve(ctx.h, ctx.ptr(J), ctx.ptr(F), ctx.ptr(y), 1, 0, 1e-12, 0.0, maxit, C.byref(its), C.byref(rr))
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    log(mode, f"avg {ms:.3f} ms per solve, {1e3*ms/max(its.value,1):.2f} us per iteration")
