@@ -96,3 +96,43 @@ def test_spmv_and_dot_against_scipy():
     out = C.c_double()
     ctx._check(ctx.lib.fb_dot(ctx.h, ctx.ptr(xd), ctx.ptr(yd), C.byref(out)))
     assert abs(out.value - x @ yr) <= 1e-12 * abs(x @ yr)
+
+
+def test_transient_mms_1d():
+    from cases import mms_1_mobile_transient
+
+    (gm, Hg, _), (rm, Hr, _) = _pair(mms_1_mobile_transient, 500, 0.1, 20)
+    gm.run()
+    rm.run()
+    assert gm.timesteps == rm.timesteps
+    assert _rel(Hg.post_processing_solution.x.array, Hr.post_processing_solution.x.array) < 1e-8
+
+
+def test_permeation_flux():
+    """SurfaceFlux export through the device reduction vs the oracle (1e-6)."""
+    from cases import permeation_1d
+
+    g, r = _pair(permeation_1d, 201, 10.0, 0.5)
+    g[0].run()
+    r[0].run()
+    fg, fr = np.array(g[2].data), np.array(r[2].data)
+    assert g[2].t == r[2].t
+    assert np.abs(fg - fr).max() <= 1e-6 * np.abs(fr).max()
+    assert _rel(g[1].post_processing_solution.x.array, r[1].post_processing_solution.x.array) < 1e-8
+
+
+def test_tds_adaptive_stepping_parity():
+    """C0-style TDS (mobile + trap, T(t) ramp, adaptive dt with milestones): the
+    Newton iteration counts drive dt, so the recorded time steps must be identical
+    (SURVEY F5); fields 1e-8, fluxes and inventory 1e-6."""
+    from cases import tds_1d
+
+    g, r = _pair(tds_1d, 100, 45.0)
+    g[0].run()
+    r[0].run()
+    assert g[0].timesteps == r[0].timesteps
+    for a, b in zip(g[0].species, r[0].species):
+        assert _rel(a.post_processing_solution.x.array, b.post_processing_solution.x.array) < 1e-8
+    for eg, er in zip(g[3], r[3]):
+        dg, dr = np.array(eg.data), np.array(er.data)
+        assert np.abs(dg - dr).max() <= 1e-6 * max(np.abs(dr).max(), 1e-300)

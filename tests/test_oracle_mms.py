@@ -45,3 +45,43 @@ def test_1_mobile_1_trap_MMS_steady_state_1d():
     mesh = m.mesh.mesh
     assert error_L2(mesh, mobile.post_processing_solution.x.array, ue) < 2e-7
     assert error_L2(mesh, trapped.post_processing_solution.x.array, ve) < 1e-7
+
+
+def test_1_mobile_MMS_transient():
+    """reference test/system_tests/test_1_mobile_species.py:83-145 (L2 < 5e-4);
+    a 2000-cell mesh keeps the CPU suite short, the error is time-discretisation
+    dominated (50 implicit-Euler steps) and unchanged on the 9999-cell mesh."""
+    from cases import mms_1_mobile_transient
+
+    m, H, exact = mms_1_mobile_transient(n=2000)
+    _run(m)
+    assert len(m.timesteps) == 50
+    assert error_L2(m.mesh.mesh, H.post_processing_solution.x.array, exact) < 5e-4
+
+
+def test_permeation_problem():
+    """reference test/test_permeation_problem.py:35-113 (mean relative error < 1 %)."""
+    from cases import permeation_1d, permeation_relative_error
+
+    import festim_b200 as F
+
+    m, H, flux, mat, L = permeation_1d()
+    _run(m)
+    D = 1.9e-7 * np.exp(-0.2 / F.k_B / 500)
+    S = 4.02e21 * np.exp(-1.04 / F.k_B / 500)
+    err = permeation_relative_error(D, D * S, np.abs(np.array(flux.data)), L, np.array(flux.t), 100)
+    assert err < 0.01
+
+
+def test_tds_adaptive_stepping_runs():
+    """C0-style TDS: adaptive stepping hits its milestones and the trap empties
+    during the ramp (qualitative pin of the driver, reference problem.py:195-255)."""
+    from cases import tds_1d
+
+    m, H, trap, (fl, fr, inv) = tds_1d()
+    _run(m)
+    t = np.array(m.timesteps)
+    assert np.isclose(t, 20.0).any() and np.isclose(t, 30.0).any()
+    assert float(m.t) >= 60.0
+    trapped = trap.trapped_concentration.post_processing_solution.x.array
+    assert trapped.max() < 1e-3 * 8.19e22

@@ -1,0 +1,225 @@
+"""Generate golden vectors from the REAL reference (/root/reference/src/festim).
+
+dolfinx / ufl / petsc4py / mpi4py / basix / scifem are absent from this image, so
+they are replaced by inert stub modules; only the reference's pure-Python logic
+runs: Stepsize.modify_value (stepsize.py:144-167), convergenceTest
+(helpers.py:408-426), Reaction.reaction_term (reaction.py:117-224, with ufl.exp
+bound to numpy) and Material.get_diffusion_coefficient (material.py:262-318).
+Outputs: tests/golden/*.json (committed; the GPU box has no /root/reference).
+
+    python tools/make_golden.py
+"""
+import importlib.abc
+import importlib.machinery
+import json
+import math
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STUBBED = ("dolfinx", "ufl", "basix", "petsc4py", "mpi4py", "scifem", "io4dolfinx", "adios2",
+           "adios4dolfinx", "pyvista", "tqdm")
+
+
+class StubMeta(type):
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        sub = StubMeta(name, (Stub,), {})
+        setattr(cls, name, sub)
+        return sub
+
+    def __call__(cls, *a, **k):
+        return type.__call__(cls)
+
+    def __or__(cls, other):
+        return U((cls,)) | other
+
+    def __ror__(cls, other):
+        return U((cls,)).__ror__(other)
+
+
+class U(tuple):
+    """`A | B | None` on stub classes: a tuple usable by isinstance()."""
+
+    @staticmethod
+    def _items(other):
+        if isinstance(other, tuple):
+            return tuple(other)
+        if other is None:
+            return (type(None),)
+        if hasattr(other, "__args__"):
+            return tuple(other.__args__)
+        return (other,)
+
+    def __or__(self, other):
+        return U(tuple(self) + self._items(other))
+
+    def __ror__(self, other):
+        return U(self._items(other) + tuple(self))
+
+
+class Stub(metaclass=StubMeta):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return Stub()
+
+    def __call__(self, *a, **k):
+        return Stub()
+
+    def __bool__(self):
+        return False
+
+
+class Constant(float):
+    """fem.Constant stand-in: a float that ignores the mesh argument."""
+
+    def __new__(cls, mesh, value):
+        return float.__new__(cls, value)
+
+    @property
+    def value(self):
+        return float(self)
+
+
+class Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split(".")[0] in STUBBED:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        mod = types.ModuleType(spec.name)
+        mod.__path__ = []
+        cache = {}
+
+        def getattr_(name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            if name not in cache:
+                cache[name] = StubMeta(name, (Stub,), {})
+            return cache[name]
+
+        mod.__getattr__ = getattr_
+        return mod
+
+    def exec_module(self, module):
+        name = module.__name__
+        if name == "dolfinx":
+            module.default_scalar_type = np.float64
+            module.default_real_type = np.float64
+            module.__version__ = "0.10.0"
+            import importlib
+
+            module.fem = importlib.import_module("dolfinx.fem")
+        if name == "dolfinx.fem":
+            module.Constant = Constant
+        if name == "ufl":
+            module.exp = np.exp
+        if name == "petsc4py.PETSc":
+            module.IntType = np.int32
+
+
+def main():
+    sys.meta_path.insert(0, Finder())
+    sys.path.insert(0, "/root/reference/src")
+    import festim as F  # the real reference package, numerics stubbed out
+
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(20261019)
+
+    # --- Stepsize.modify_value -------------------------------------------------
+    cases = []
+    configs = [
+        dict(initial_value=0.1, growth_factor=1.2, cutback_factor=0.8, target_nb_iterations=4),
+        dict(initial_value=0.5, growth_factor=1.1, cutback_factor=0.9, target_nb_iterations=4,
+             max_stepsize=2.0),
+        dict(initial_value=1.0, growth_factor=1.5, cutback_factor=0.5, target_nb_iterations=3,
+             milestones=[1.0, 2.5, 7.0, 20.0]),
+        dict(initial_value=0.2, growth_factor=1.2, cutback_factor=0.9, target_nb_iterations=5,
+             max_stepsize=3.0, milestones=[0.5, 4.0, 4.00001, 9.0], milestone_tolerance=1e-4),
+    ]
+    for cfg in configs:
+        st = F.Stepsize(**cfg)
+        for _ in range(60):
+            value = float(rng.uniform(0.01, 4.0))
+            t = float(rng.uniform(0.0, 22.0))
+            if rng.random() < 0.2 and cfg.get("milestones"):
+                t = float(rng.choice(cfg["milestones"])) * (1 + float(rng.uniform(-2e-5, 2e-5)))
+            its = int(rng.integers(1, 9))
+            cases.append({"config": cfg, "value": value, "nb_iterations": its, "t": t,
+                          "expected": float(st.modify_value(value, its, t))})
+    json.dump(cases, open(os.path.join(out_dir, "stepsize_modify_value.json"), "w"), indent=0)
+
+    # --- convergenceTest -----------------------------------------------------------
+    class Reasons:
+        DIVERGED_MAX_IT, CONVERGED_FNORM_ABS, CONVERGED_FNORM_RELATIVE = -5, 2, 3
+        CONVERGED_SNORM_RELATIVE, ITERATING = 4, 0
+
+    class FakeSnes:
+        ConvergedReason = Reasons
+
+        def __init__(self, tol):
+            self.tol = tol
+
+        def getTolerances(self):
+            return self.tol
+
+    import festim.helpers as H
+
+    seqs = []
+    for _ in range(40):
+        rtol = float(10 ** rng.uniform(-12, -6))
+        atol = float(10 ** rng.uniform(-12, 2))
+        stol = 1.4901161193847656e-10
+        max_it = int(rng.integers(2, 8))
+        snes = FakeSnes((rtol, atol, stol, max_it))
+        f = float(10 ** rng.uniform(-3, 6))
+        rows = []
+        for it in range(max_it + 2):
+            gnorm = 0.0 if it == 0 else float(10 ** rng.uniform(-13, 2))
+            reason = H.convergenceTest(snes, it, (1.0, gnorm, f))
+            rows.append({"it": it, "snorm": gnorm, "fnorm": f, "reason": int(reason)})
+            f *= float(10 ** rng.uniform(-5, -0.5))
+        seqs.append({"rtol": rtol, "atol": atol, "stol": stol, "max_it": max_it, "rows": rows})
+    json.dump(seqs, open(os.path.join(out_dir, "convergence_test.json"), "w"), indent=0)
+
+    # --- Reaction.reaction_term and Arrhenius diffusivity ---------------------------
+    mat = F.Material(D_0=1.0, E_D=0.1)
+    vol = F.VolumeSubdomain(id=1, material=mat)
+    react = []
+    for _ in range(60):
+        k_0, E_k = float(10 ** rng.uniform(-20, 2)), float(rng.uniform(0.0, 1.5))
+        mode = int(rng.integers(0, 3))
+        p_0 = [0.0, float(10 ** rng.uniform(-3, 13)), float(10 ** rng.uniform(-3, 13))][mode]
+        E_p = [0.0, 0.0, float(rng.uniform(0.1, 1.5))][mode]
+        T = float(rng.uniform(300, 1200))
+        cm, ct, n = (float(10 ** rng.uniform(0, 22)) for _ in range(3))
+        A, B = F.Species("A"), F.Species("B", mobile=False)
+        A.solution, B.solution = cm, ct
+        imp = F.ImplicitSpecies(n=n, others=[B])
+        imp.value_fenics = n
+        r = F.Reaction(reactant=[A, imp], product=B, k_0=k_0, E_k=E_k, p_0=p_0, E_p=E_p, volume=vol)
+        react.append({"k_0": k_0, "E_k": E_k, "p_0": p_0, "E_p": E_p, "T": T, "c_mobile": cm,
+                      "c_trapped": ct, "n": n, "expected": float(r.reaction_term(T))})
+    json.dump(react, open(os.path.join(out_dir, "reaction_term.json"), "w"), indent=0)
+
+    diff = []
+    for _ in range(40):
+        D_0, E_D, T = float(10 ** rng.uniform(-9, 1)), float(rng.uniform(0, 1.5)), float(rng.uniform(250, 1500))
+        m = F.Material(D_0=D_0, E_D=E_D)
+        diff.append({"D_0": D_0, "E_D": E_D, "T": T,
+                     "expected": float(m.get_diffusion_coefficient(None, T, None))})
+    json.dump(diff, open(os.path.join(out_dir, "diffusion_coefficient.json"), "w"), indent=0)
+    json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
+              open(os.path.join(out_dir, "constants.json"), "w"))
+    print("golden vectors written to", out_dir)
+
+
+if __name__ == "__main__":
+    main()
