@@ -9,7 +9,7 @@ LIB := festim_b200/libfestim_b200.so
 all: $(LIB)
 
 $(LIB): $(SRC) $(HDR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) 2> build_ptxas.log || (cat build_ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -ldl 2> build_ptxas.log || (cat build_ptxas.log; false)
 
 clean:
 	rm -f $(LIB) build_ptxas.log

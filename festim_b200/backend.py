@@ -51,6 +51,7 @@ def load_library():
         "fb_set_mesh": (i, [vp, i, i64, i64, _f64p, _i32p, _i32p, i64, _i32p, _i32p, _i32p]),
         "fb_set_pattern": (i, [vp, _i32p, _i32p, i64, _i32p, _i32p]),
         "fb_set_spec": (i, [vp, vp, C.c_size_t]),
+        "fb_jit_load": (i, [vp, vp, C.c_size_t]),
         "fb_set_dirichlet": (i, [vp, i64, _i64p]),
         "fb_num_dofs": (i64, [vp]),
         "fb_jacobian_nnz": (i64, [vp]),
@@ -83,7 +84,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_launch_count", "fb_set_mesh", "fb_set_pattern",
-    "fb_set_spec", "fb_set_dirichlet", "fb_num_dofs", "fb_jacobian_nnz", "fb_set_scalars",
+    "fb_set_spec", "fb_jit_load", "fb_set_dirichlet", "fb_num_dofs", "fb_jacobian_nnz", "fb_set_scalars",
     "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
     "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
     "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
@@ -130,6 +131,13 @@ class Context:
             _np_ptr(v2c_ptr, C.c_int32), _np_ptr(v2c_idx, C.c_int32)))
         blob = spec.blob()
         self._check(self.lib.fb_set_spec(self.h, blob, len(blob)))
+        self.jit = False
+        from festim_b200 import jit
+
+        if jit.needed(spec):
+            cubin = jit.compile_cubin(jit.generate_source(spec))
+            self._check(self.lib.fb_jit_load(self.h, cubin, len(cubin)))
+            self.jit = True
         self.n_dofs = int(self.lib.fb_num_dofs(self.h))
         self.nnz = int(self.lib.fb_jacobian_nnz(self.h))
         self.nv = mesh.num_vertices

@@ -146,8 +146,10 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     const int nterms = pass == 0 ? S.n_vterms : S.n_fterms;
     if (hs.id == 0) continue;
     const int* h = (const int*)(blob + hs.offset);
-    for (int t = 0; t < nterms; ++t)
+    for (int t = 0; t < nterms; ++t) {
       if (h[t * 8 + 5] > 0) ctx->symmetric = false;
+      if (pass == 1 && h[t * 8 + 6]) ctx->facet_u_terms = true;
+    }
   }
   S.n_dofs = S.n_vertices * S.ns;
   const int n_scalars = ints[I_NSCALARS];

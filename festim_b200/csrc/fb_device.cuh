@@ -1,0 +1,85 @@
+// Device-side declarations shared by the ahead-of-time build (nvcc) and the
+// run-time specialisation of the element kernels (NVRTC, festim_b200/jit.py).
+// No host headers here.
+#pragma once
+
+#ifndef FB_ASSEMBLE_F
+#define FB_ASSEMBLE_F 1
+#define FB_ASSEMBLE_J 2
+#endif
+#define FB_MAX_NS 16
+#define FB_MAX_D1 4
+#define FB_KB 8.6173303e-5  // Boltzmann constant eV/K, reference src/festim/__init__.py:11
+#define FB_STACK 24
+
+// Everything a kernel needs, passed by value (lives in the constant bank).
+struct DevSpec {
+  int tdim, ns, n_vtags, n_stags, transient, T_mode, npairs, n_slots, n_diffE;
+  int n_vterms, n_fterms, n_adv, n_fields;
+  long long n_vertices, n_cells, n_bfacets, n_dofs;
+  // mesh + pattern
+  const double* coords;
+  const int* cells;
+  const int* cell_tag;
+  const int* bfacets;
+  const int* bfacet_cell;
+  const int* bfacet_tag;
+  const int* rowptr;
+  const int* colidx;
+  const int* v2c_ptr;
+  const int* v2c_idx;
+  // tables (spec)
+  const double* diff_D0;      // [n_vtags*ns]
+  const int* diff_slot;       // [n_vtags*ns] index into cell-coefficient slots, -1 none
+  const double* diff_energies;  // [n_diffE]
+  const int* diff_progs;      // [n_slots-n_diffE] program ids of generic diffusivities
+  const double* mass_dt;      // [n_vtags*ns]
+  const double* mass_c;
+  const int* pair_nc;         // [ns]
+  const int* pair_pp;         // [ns+1]
+  const int* pair_cs;         // [npairs]
+  const int* pair_idx;        // [ns*ns]
+  const int* prog_ops;
+  const int* prog_iargs;
+  const double* prog_fargs;
+  const int* prog_offsets;
+  const int* vterm_hdr;       // [n_vterms*8] tag, value_prog, rows_off, n_rows, derivs_off, n_derivs, u_dep
+  const int* fterm_hdr;
+  const int* row_species;
+  const double* row_coef;
+  const int* deriv_species;
+  const int* deriv_prog;
+  const int* quad_v;          // [n_vtags*4] offF, nqF, offJ, nqJ
+  const int* quad_s;
+  const double* quad_bary;
+  const double* quad_w;
+  const int* adv;             // [n_adv*2] tag, species
+  // per-step data
+  const double* scalars;
+  double T_const;
+  const double* T_nodal;
+  const double* const* fields;      // device array of device pointers
+  const double* const* velocities;
+  const int* bc_map;          // [n_dofs] index into bc_vals or -1
+  const double* bc_vals;
+  const double* dbar;         // [2][n_slots][n_cells] cell means of diffusivity factors
+  const double* load;         // [n_dofs] solution-independent part of the residual
+  double inv_dt;
+};
+
+// Evaluation point: physical coordinates, temperature, species values and the
+// entity (cell or facet) it lies in, for lazy P1-field interpolation.
+struct PointCtx {
+  double x[3];
+  double T;
+  const double* c;       // [ns] species at the point
+  const double* cprev;   // [ns] previous-step species at the point
+  const int* verts;      // vertices of the integration entity
+  const double* bary;    // barycentric coordinates w.r.t. verts
+  int nverts;
+  const int* cverts;     // vertices of the owning cell
+  const double* G;       // [ncverts][tdim] basis gradients of the owning cell
+  int ncverts;
+  int tdim;
+};
+

@@ -759,6 +759,8 @@ OP_LT, OP_GT, OP_LE, OP_GE, OP_EQ, OP_NE, OP_AND, OP_OR, OP_NOT = 30, 31, 32, 33
 OP_SELECT, OP_MAX, OP_MIN = 40, 41, 42
 OP_T = 6  # temperature at the point (T constant or P1 field of the problem)
 OP_SPECIES_PREV = 7
+OP_STORE, OP_LOAD = 50, 51  # common-subexpression temporaries
+MAX_TEMPS = 16
 
 MAX_STACK = 24
 
@@ -779,6 +781,7 @@ class ProgramBuilder:
         self.species_index = species_index or {}
         self.temperature = temperature  # object standing for T (Constant or Function)
         self._cache = {}
+        self.expressions = []  # expression of every program (run-time code generation)
 
     def _scalar_id(self, c):
         for i, s in enumerate(self.scalars):
@@ -794,6 +797,54 @@ class ProgramBuilder:
         self.fields.append(f)
         return len(self.fields) - 1
 
+    # -- common-subexpression elimination -------------------------------------
+    def _skey(self, ex, memo):
+        """Structural key of a node (equal keys <=> same value at a point)."""
+        k = memo.get(id(ex))
+        if k is not None:
+            return k
+        if isinstance(ex, Condition):
+            k = ("cond", ex.op, self._skey(ex.a, memo), None if ex.b is None else self._skey(ex.b, memo))
+        elif isinstance(ex, Const):
+            k = ("c", ex.value)
+        elif isinstance(ex, Coord):
+            k = ("x", ex.i)
+        elif isinstance(ex, ConstantRef):
+            k = ("k", id(ex.constant))
+        elif isinstance(ex, FieldRef):
+            k = ("f", id(ex.function))
+        elif isinstance(ex, FieldGrad):
+            k = ("g", id(ex.function), ex.i)
+        elif isinstance(ex, SpeciesRef):
+            k = ("s", id(ex.species), ex.prev)
+        elif isinstance(ex, Neg):
+            k = ("neg", self._skey(ex.a, memo))
+        elif isinstance(ex, Math):
+            k = ("m", ex.name, self._skey(ex.a, memo))
+        elif isinstance(ex, Conditional):
+            k = ("sel", self._skey(ex.cond, memo), self._skey(ex.a, memo), self._skey(ex.b, memo))
+        elif isinstance(ex, MinMax):
+            k = (ex.kind, self._skey(ex.a, memo), self._skey(ex.b, memo))
+        else:
+            k = (type(ex).__name__, self._skey(ex.a, memo), self._skey(ex.b, memo))
+        k = hash(k) if len(repr(k)) > 200 else k
+        memo[id(ex)] = k
+        return k
+
+    def _count(self, ex, memo, counts):
+        k = self._skey(ex, memo)
+        counts[k] = counts.get(k, 0) + 1
+        if counts[k] > 1:
+            return  # children already counted once; a repeat costs one LOAD
+        for name in ("cond", "a", "b"):
+            child = getattr(ex, name, None)
+            if isinstance(child, (Expr, Condition)):
+                self._count(child, memo, counts)
+
+    @staticmethod
+    def _worth_caching(ex):
+        return isinstance(ex, (Math, Division, Power, FieldRef, FieldGrad, Product, Sum, Conditional))
+
     def add(self, ex):
         """Compile ``ex``; returns the program id."""
         ex = as_expr(ex)
@@ -801,11 +852,14 @@ class ProgramBuilder:
         if key in self._cache and self._cache[key][0] is ex:
             return self._cache[key][1]
         out = []
+        self._memo, self._counts, self._slots = {}, {}, {}
+        self._count(ex, self._memo, self._counts)
         depth = self._emit(ex, out)
         if depth[1] > MAX_STACK:
             raise ValueError(f"expression needs a stack of {depth[1]} > {MAX_STACK}")
         self.code.extend(out)
         self.offsets.append(len(self.code))
+        self.expressions.append(ex)
         pid = len(self.offsets) - 2
         self._cache[key] = (ex, pid)
         return pid
@@ -815,9 +869,25 @@ class ProgramBuilder:
         return len(self.offsets) - 1
 
     def _emit(self, ex, out):
-        """Returns (net pushes == 1, max stack depth)."""
+        """Returns (net pushes == 1, max stack depth); repeated subtrees are
+        evaluated once, stored in a temporary and re-loaded."""
         if isinstance(ex, Condition):
             return self._emit_cond(ex, out)
+        k = self._memo.get(id(ex))
+        if k is None:
+            k = self._skey(ex, self._memo)
+        if self._counts.get(k, 0) > 1 and self._worth_caching(ex):
+            if k in self._slots:
+                out.append((OP_LOAD, self._slots[k], 0.0))
+                return (1, 1)
+            d = self._emit_node(ex, out)
+            if len(self._slots) < MAX_TEMPS:
+                self._slots[k] = len(self._slots)
+                out.append((OP_STORE, self._slots[k], 0.0))
+            return d
+        return self._emit_node(ex, out)
+
+    def _emit_node(self, ex, out):
         if isinstance(ex, Const):
             out.append((OP_CONST, 0, ex.value))
             return (1, 1)

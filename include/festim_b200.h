@@ -85,6 +85,11 @@ int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr /*[host] n_vertices+1*/,
                    const int32_t* v2c_idx /*[host] n_cells*(tdim+1)*/);
 /* flat kernel spec produced by festim_b200/lowering.py (layout documented there) */
 int fb_set_spec(fb_ctx* ctx, const void* blob /*[host]*/, size_t nbytes);
+/* optional: cubin of the element kernels specialised for this spec at run time
+ * (NVRTC, festim_b200/jit.py) - the analogue of the FFCx JIT the reference triggers
+ * in NonlinearProblem (problem.py:173-182; hydrogen_transport_problem.py:2025-2040).
+ * Without it the ahead-of-time kernels interpret the spec's byte-code programs. */
+int fb_jit_load(fb_ctx* ctx, const void* cubin /*[host]*/, size_t nbytes);
 /* strong Dirichlet dofs (reference problem.py:118-130, fem.dirichletbc) */
 int fb_set_dirichlet(fb_ctx* ctx, int64_t n_bc, const int64_t* bc_dofs /*[host]*/);
 int64_t fb_num_dofs(fb_ctx* ctx);
