@@ -39,6 +39,8 @@ from festim_b200.exports import (
     VolumeQuantity,
 )
 from festim_b200.helpers import Value, as_fenics_constant, is_it_time_to_export
+from festim_b200.coupled_heat_hydrogen_problem import CoupledTransientHeatTransferHydrogenTransport
+from festim_b200.heat_transfer_problem import HeatTransferProblem
 from festim_b200.hydrogen_transport_problem import HydrogenTransportProblem
 from festim_b200.initial_condition import (
     InitialConcentration,

@@ -10,7 +10,7 @@ enum {
   S_INTS = 1, S_DIFF_D0, S_DIFF_SLOT, S_DIFF_ENERGIES, S_MASS_DT, S_MASS_C, S_PAIR_NC, S_PAIR_PP,
   S_PAIR_CS, S_PAIR_IDX, S_PROG_OPS, S_PROG_IARGS, S_PROG_FARGS, S_PROG_OFFSETS, S_VTERM_HDR,
   S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
-  S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_MAX
+  S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_MAX
 };
 enum {
   I_TDIM = 0, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -164,7 +164,13 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   UP(S_ROW_SPECIES, 0, row_species); UP(S_ROW_COEF, 1, row_coef);
   UP(S_DERIV_SPECIES, 0, deriv_species); UP(S_DERIV_PROG, 0, deriv_prog);
   UP(S_QUAD_V, 0, quad_v); UP(S_QUAD_S, 0, quad_s); UP(S_QUAD_BARY, 1, quad_bary); UP(S_QUAD_W, 1, quad_w);
-  UP(S_ADV, 0, adv);
+  UP(S_ADV, 0, adv); UP(S_DIFF_UPROG, 0, diff_uprog);
+  S.n_udiff = 0;
+  if (secs[S_DIFF_UPROG].id == S_DIFF_UPROG) {
+    const int* up = (const int*)(blob + secs[S_DIFF_UPROG].offset);
+    for (long long i = 0; i < secs[S_DIFF_UPROG].count / 3; ++i)
+      if (up[3 * i] >= 0) { S.n_udiff++; ctx->symmetric = false; }
+  }
 #undef UP
   // mutable per-step buffers
   if ((rc = fb_alloc(ctx, &ctx->d_scalars, (size_t)n_scalars + 1))) return rc;

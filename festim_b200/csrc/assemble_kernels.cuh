@@ -365,6 +365,67 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
         kF = D0 * S.dbar[(long long)ds * S.n_cells + c];
         kJ = D0 * S.dbar[((long long)S.n_slots + ds) * S.n_cells + c];
       }
+      if (S.n_udiff > 0 && S.diff_uprog[(tag * ns + s) * 3] >= 0) {
+        // solution-dependent diffusivity D(u): F uses mean(D) with the F rule; J adds
+        // mean(D) G_i.G_j with the J rule plus (dD/du_dep)(q) phi_j(q) G_i.grad(u_s)
+        const int* up = S.diff_uprog + (tag * ns + s) * 3;
+        double ucl[FB_MAX_D1][FB_MAX_NS], uncl[FB_MAX_D1][FB_MAX_NS], Gf[FB_MAX_D1 * 3];
+        for (int j = 0; j < D1; ++j) {
+          for (int k = 0; k < DIM; ++k) Gf[j * DIM + k] = G[j][k];
+          for (int s2 = 0; s2 < ns; ++s2) {
+            ucl[j][s2] = u[(long long)a[j] * ns + s2];
+            uncl[j][s2] = S.transient ? un[(long long)a[j] * ns + s2] : 0.0;
+          }
+        }
+        double giu = 0.0;  // G_i . grad(u_s)
+        for (int k = 0; k < DIM; ++k) {
+          double gk = 0.0;
+          for (int j = 0; j < D1; ++j) gk += ucl[j][s] * G[j][k];
+          giu += G[i][k] * gk;
+        }
+        double cqs[FB_MAX_NS], cpqs[FB_MAX_NS];
+        for (int pass = 0; pass < 2; ++pass) {
+          if (pass == 0 && !doF) continue;
+          const int off = S.quad_v[tag * 4 + 2 * pass], nq = S.quad_v[tag * 4 + 2 * pass + 1];
+          double Dm = 0.0;
+          for (int q = 0; q < nq; ++q) {
+            const double* bary = S.quad_bary + (long long)(off + q) * D1;
+            PointCtx P;
+            for (int k = 0; k < DIM; ++k) {
+              double x = 0.0;
+              for (int j = 0; j < D1; ++j) x += bary[j] * X[j][k];
+              P.x[k] = x;
+            }
+            P.T = fb_temperature(S, a, bary, D1);
+            for (int s2 = 0; s2 < ns; ++s2) {
+              double cv = 0.0, cp = 0.0;
+              for (int j = 0; j < D1; ++j) { cv += bary[j] * ucl[j][s2]; cp += bary[j] * uncl[j][s2]; }
+              cqs[s2] = cv; cpqs[s2] = cp;
+            }
+            P.c = cqs; P.cprev = cpqs; P.verts = a; P.bary = bary; P.nverts = D1;
+            P.cverts = a; P.G = Gf; P.ncverts = D1; P.tdim = DIM;
+            const double wq = S.quad_w[off + q];
+            Dm += wq * fb_prog_eval(S, up[0], P);
+            if (pass == 1) {
+              for (int dd = 0; dd < up[2]; ++dd) {
+                const int dep = S.deriv_species[up[1] + dd];
+                const double dv = wq * vol * giu * fb_prog_eval(S, S.deriv_prog[up[1] + dd], P);
+                const int jp2 = S.pair_idx[s * ns + dep];
+                for (int j = 0; j < D1; ++j) {
+                  const double aij = dv * bary[j];
+                  const int bcj = S.bc_map[(long long)a[j] * ns + dep];
+                  if (bcj >= 0) {
+                    if (doF) Facc[s] += aij * (S.bc_vals[bcj] - ucl[j][dep]);
+                  } else if (doJ) {
+                    J[rowbase + (long long)deg * S.pair_pp[s] + (long long)slot[j] * S.pair_nc[s] + jp2] += aij;
+                  }
+                }
+              }
+            }
+          }
+          if (pass == 0) kF += vol * Dm; else kJ += vol * Dm;
+        }
+      }
       const double m = S.transient ? S.mass_dt[tag * ns + s] * S.inv_dt * vol * mscale : 0.0;
       const double mc = S.mass_c[tag * ns + s] * vol * mscale;
       // advection: sum_q w_q phi_i(q) vel_q . G_j = sum_a (vel_a . G_j) int(phi_i phi_a)

@@ -33,6 +33,8 @@ struct DevSpec {
   const int* diff_slot;       // [n_vtags*ns] index into cell-coefficient slots, -1 none
   const double* diff_energies;  // [n_diffE]
   const int* diff_progs;      // [n_slots-n_diffE] program ids of generic diffusivities
+  const int* diff_uprog;      // [n_vtags*ns*3] solution-dependent diffusivity: prog, derivs off, count (-1 none)
+  int n_udiff;                // number of (tag, species) with a solution-dependent diffusivity
   const double* mass_dt;      // [n_vtags*ns]
   const double* mass_c;
   const int* pair_nc;         // [ns]

@@ -163,8 +163,19 @@ jit_assemble_nodes(DevSpec S, const double* __restrict__ u, const double* __rest
 '''
 
 
+_CACHE = {}
+
+
 def compile_cubin(source, arch="sm_100a"):
-    """NVRTC: CUDA source -> cubin for ``arch``.  Raises with the compiler log."""
+    """NVRTC: CUDA source -> cubin for ``arch`` (memoised per source text)."""
+    key = (arch, source)
+    if key not in _CACHE:
+        _CACHE[key] = _compile(source, arch)
+    return _CACHE[key]
+
+
+def _compile(source, arch):
+    """Raises with the compiler log on failure."""
     from cuda.bindings import nvrtc
 
     def check(res):

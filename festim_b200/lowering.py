@@ -36,7 +36,7 @@ MAGIC = 0xFB200_0001
 (S_INTS, S_DIFF_D0, S_DIFF_SLOT, S_DIFF_ENERGIES, S_MASS_DT, S_MASS_C, S_PAIR_NC, S_PAIR_PP,
  S_PAIR_CS, S_PAIR_IDX, S_PROG_OPS, S_PROG_IARGS, S_PROG_FARGS, S_PROG_OFFSETS, S_VTERM_HDR,
  S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
- S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS) = range(1, 27)
+ S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG) = range(1, 28)
 
 # S_INTS slots
 (I_TDIM, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -104,6 +104,7 @@ class KernelSpec:
         self.diff_slot = np.full((nvt, ns), -1, dtype=np.int32)
         self._generic_D = []   # (tag, s, program id), slots assigned after the energies
         self.diff_energies = []
+        self.diff_udep = {}    # (tag, s) -> (value program, [(dep species, derivative program)])
         self.mass_dt = np.zeros((nvt, ns))
         self.mass_c = np.zeros((nvt, ns))
         self.vterms = []
@@ -126,9 +127,15 @@ class KernelSpec:
                     D0, E = itg.meta["arrhenius"]
                     self.diff_D0[tag, s] = D0
                     self.diff_slot[tag, s] = self._energy_index(float(E))
+                elif ufl.species_in(itg.D):
+                    # solution-dependent diffusivity (e.g. lambda(T) of the heat problem):
+                    # value program + derivative programs, evaluated while gathering
+                    derivs = [(sidx[spe], self.programs.add(ufl.diff(itg.D, ("species", spe))))
+                              for spe in ufl.species_in(itg.D)]
+                    self.diff_udep[(tag, s)] = (self.programs.add(itg.D), derivs)
+                    for dep, _ in derivs:
+                        pairs.add((s, dep))
                 else:
-                    if ufl.species_in(itg.D):
-                        raise NotImplementedError("solution-dependent diffusivity")
                     self.diff_D0[tag, s] = 1.0
                     self._generic_D.append((tag, s, self.programs.add(itg.D)))
             elif itg.kind == "advection":
@@ -257,6 +264,14 @@ class KernelSpec:
 
         vhdr = headers(self.vterms)
         fhdr = headers(self.fterms)
+        # solution-dependent diffusivities: per (tag, s): program, derivs offset, count
+        nvt = len(self.vol_ids)
+        uprog = np.full((nvt, self.ns, 3), -1, dtype=np.int32)
+        for (tag, s), (pid, derivs) in self.diff_udep.items():
+            uprog[tag, s] = [pid, len(deriv_species), len(derivs)]
+            for dep, dp in derivs:
+                deriv_species.append(dep)
+                deriv_prog.append(dp)
         adv = np.array([[t, s] for t, s, _ in self.adv], dtype=np.int32).reshape(-1, 2)
         sections = {
             S_INTS: ints,
@@ -275,7 +290,7 @@ class KernelSpec:
             S_QUAD_V: self.quad_v, S_QUAD_S: self.quad_s,
             S_QUAD_BARY: np.concatenate(self._qb) if self._qb else np.zeros(0),
             S_QUAD_W: np.concatenate(self._qw) if self._qw else np.zeros(0),
-            S_ADV: adv,
+            S_ADV: adv, S_DIFF_UPROG: uprog,
         }
         return pack_sections(sections)
 

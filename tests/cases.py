@@ -213,3 +213,163 @@ def tds_1d(n_cells=200, final_time=60.0):
         initial_value=0.5, growth_factor=1.2, cutback_factor=0.9, target_nb_iterations=4,
         max_stepsize=lambda t: 2.0 if t < 30.0 else 1.0, milestones=[20.0, 30.0, final_time])
     return m, H, trap, (flux_l, flux_r, inv)
+
+
+def heat_mms(T_dependent=False, n=1999):
+    """reference test/test_heat_transfer_problem.py:67-110 (constant conductivity)
+    and :113-165 (conductivity 3T + 2); L2 < 1e-7."""
+    p = F.HeatTransferProblem()
+    p.mesh = F.Mesh1D(vertices=np.linspace(0, 1, n + 1))
+    left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=1)
+    mat = F.Material(D_0=1, E_D=None)
+    if T_dependent:
+        mat.thermal_conductivity = lambda T: 3 * T + 2
+        exact = lambda x: 2 * x[0] ** 2 + 1
+        source = lambda x: -(72 * x[0] ** 2 + 20)
+    else:
+        mat.thermal_conductivity = 4.0
+        exact = lambda x: 2 * x[0] ** 2
+        source = -4 * 4.0
+    vol = F.VolumeSubdomain1D(id=1, borders=[0, 1], material=mat)
+    p.subdomains = [left, right, vol]
+    p.boundary_conditions = [F.FixedTemperatureBC(subdomain=left, value=exact),
+                             F.FixedTemperatureBC(subdomain=right, value=exact)]
+    p.sources = [F.HeatSource(value=source, volume=vol)]
+    p.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    return p, exact
+
+
+def flux_bc_mms(heat=False, n=9999):
+    """reference test/system_tests/test_fluxes.py:13-57 (particle flux) and :60-95
+    (heat flux); L2 < 1e-7."""
+    mesh = F.Mesh1D(np.linspace(0, 1, n + 1))
+    x = ufl.SpatialCoordinate(mesh.mesh)
+    u_exact = lambda x: 1 + 2 * x[0] ** 2
+    left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=1)
+    if heat:
+        lam = 2.3
+        m = F.HeatTransferProblem()
+        vol = F.VolumeSubdomain1D(id=1, borders=[0, 1],
+                                  material=F.Material(D_0=1, E_D=1, thermal_conductivity=lam))
+        m.boundary_conditions = [F.FixedTemperatureBC(subdomain=left, value=u_exact),
+                                 F.HeatFluxBC(subdomain=right, value=4 * lam)]
+        m.sources = [F.HeatSource(value=-ufl.div(lam * ufl.grad(u_exact(x))), volume=vol)]
+        field = None
+    else:
+        D = 1 * ufl.exp(-0.1 / (F.k_B * 500))
+        m = F.HydrogenTransportProblem()
+        vol = F.VolumeSubdomain1D(id=1, borders=[0, 1], material=F.Material(D_0=1, E_D=0.1))
+        H = F.Species("H")
+        m.species = [H]
+        m.temperature = 500
+        m.boundary_conditions = [F.DirichletBC(subdomain=left, value=u_exact, species=H),
+                                 F.ParticleFluxBC(subdomain=right, value=4 * D, species=H)]
+        m.sources = [F.ParticleSource(value=-ufl.div(D * ufl.grad(u_exact(x))), volume=vol, species=H)]
+        field = H
+    m.mesh = mesh
+    m.subdomains = [vol, left, right]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    return m, field, u_exact
+
+
+def coupled_heat_hydrogen_mms(n=1999, nsteps=20, traps_others_includes_mobile=True):
+    """reference test/system_tests/test_coupled_heat_hydrogen.py:9-207 (all three
+    L2 errors < 2e-7)."""
+    density, heat_capacity, lam = 1.2, 2.6, 4.2
+    D_0, E_D, k_0, E_k, p_0, E_p, n_trap = 1.2, 0.1, 2.2, 0.2, 0.5, 0.1, 5
+    k_B, final_time = F.k_B, 1
+    mesh = F.Mesh1D(vertices=np.linspace(0, 1, n + 1))
+    mat = F.Material(D_0=D_0, E_D=E_D, thermal_conductivity=lam, density=density,
+                     heat_capacity=heat_capacity)
+    vol = F.VolumeSubdomain1D(id=1, borders=[0, 1], material=mat)
+    left, right = F.SurfaceSubdomain1D(id=2, x=0), F.SurfaceSubdomain1D(id=3, x=1)
+    mobile = F.Species("mobile", mobile=True)
+    trapped = F.Species(name="trapped", mobile=False, subdomains=[vol])
+    others = [mobile, trapped] if traps_others_includes_mobile else [trapped]
+    traps = F.ImplicitSpecies(n=n_trap, others=others)
+    exact_T = lambda x, t: 3 * x[0] ** 2 + 10 * t
+    heat = F.HeatTransferProblem(
+        mesh=mesh, subdomains=[vol, left, right],
+        boundary_conditions=[F.FixedTemperatureBC(subdomain=left, value=exact_T),
+                             F.FixedTemperatureBC(subdomain=right, value=exact_T)],
+        sources=[F.HeatSource(value=density * heat_capacity * 10 - lam * 6, volume=vol)],
+        initial_condition=F.InitialTemperature(value=lambda x: exact_T(x, 0), volume=vol),
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, stepsize=final_time / nsteps,
+                            final_time=final_time))
+    ex_m = lambda x, t: 2 * x[0] ** 2 + 15 * t
+    ex_t = lambda x, t: 4 * x[0] ** 2 + 12 * t
+    D = lambda x, t: D_0 * ufl.exp(-E_D / (k_B * exact_T(x, t)))
+    k = lambda x, t: k_0 * ufl.exp(-E_k / (k_B * exact_T(x, t)))
+    p = lambda x, t: p_0 * ufl.exp(-E_p / (k_B * exact_T(x, t)))
+
+    def src_m(x, t):
+        return (15 - ufl.div(D(x, t) * ufl.grad(ex_m(x, t)))
+                + k(x, t) * ex_m(x, t) * (n_trap - ex_t(x, t)) - p(x, t) * ex_t(x, t))
+
+    def src_t(x, t):
+        return 12 - k(x, t) * ex_m(x, t) * (n_trap - ex_t(x, t)) + p(x, t) * ex_t(x, t)
+
+    hyd = F.HydrogenTransportProblem(
+        mesh=mesh, subdomains=[vol, left, right],
+        boundary_conditions=[
+            F.FixedConcentrationBC(subdomain=left, value=ex_m, species=mobile),
+            F.FixedConcentrationBC(subdomain=right, value=ex_m, species=mobile),
+            F.FixedConcentrationBC(subdomain=left, value=ex_t, species=trapped),
+            F.FixedConcentrationBC(subdomain=right, value=ex_t, species=trapped)],
+        species=[mobile, trapped],
+        reactions=[F.Reaction(reactant=[mobile, traps], product=trapped, k_0=k_0, E_k=E_k,
+                              p_0=p_0, E_p=E_p, volume=vol)],
+        initial_conditions=[
+            F.InitialConcentration(value=lambda x: ex_m(x, t=0), species=mobile, volume=vol),
+            F.InitialConcentration(value=lambda x: ex_t(x, t=0), species=trapped, volume=vol)],
+        sources=[F.ParticleSource(value=src_m, volume=vol, species=mobile),
+                 F.ParticleSource(value=src_t, volume=vol, species=trapped)],
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, stepsize=final_time / nsteps,
+                            final_time=final_time))
+    coupled = F.CoupledTransientHeatTransferHydrogenTransport(heat_problem=heat, hydrogen_problem=hyd)
+    exact = (lambda x: exact_T(x, final_time), lambda x: ex_m(x, final_time), lambda x: ex_t(x, final_time))
+    return coupled, (mobile, trapped), exact
+
+
+def advection_trap_mms_2d(n=200):
+    """reference test/system_tests/test_advection_term_integration.py:15-142
+    (mobile < 2e-3, trapped < 7e-5 on the 200 x 200 square)."""
+    D_0, E_D, k_0, E_k, p_0, E_p, n_trap = 1.2, 0.1, 2.2, 0.6, 0.5, 0.1, 100
+    raw = F.create_unit_square(n, n)
+    x = ufl.SpatialCoordinate(raw)
+    mat = F.Material(D_0=D_0, E_D=E_D)
+    vol = F.VolumeSubdomain(id=1, material=mat)
+    boundary = F.SurfaceSubdomain(id=1)
+    mobile = F.Species("mobile", mobile=True)
+    trapped = F.Species(name="trapped", mobile=True)
+    empty = F.ImplicitSpecies(n=n_trap, others=[trapped])
+    T = fem.Function(fem.functionspace(raw, ("Lagrange", 1)))
+    T.interpolate(lambda x: 100 + 200 * x[0] + 100 * x[1])
+
+    def velocity_func(x):
+        values = np.zeros((2, x.shape[1]))
+        values[0] = x[1] * (x[1] - 1)
+        return values
+
+    vel = F.VectorFunction(raw, velocity_func)
+    ex_m = lambda x: 200 * x[0] ** 2 + 300 * x[1] ** 2
+    ex_t = lambda x: 10 * x[0] ** 2 + 10 * x[1] ** 2
+    D = D_0 * ufl.exp(-E_D / (F.k_B * T))
+    k = k_0 * ufl.exp(-E_k / (F.k_B * T))
+    p = p_0 * ufl.exp(-E_p / (F.k_B * T))
+    u_sym = ufl.as_vector([x[1] * (x[1] - 1), 0.0])  # the exact velocity, as in the MMS source
+    f = (-ufl.div(D * ufl.grad(ex_m(x))) + ufl.inner(u_sym, ufl.grad(ex_m(x)))
+         + k * ex_m(x) * (n_trap - ex_t(x)) - p * ex_t(x))
+    g = -ufl.div(D * ufl.grad(ex_t(x))) - k * ex_m(x) * (n_trap - ex_t(x)) + p * ex_t(x)
+    bcs = [F.FixedConcentrationBC(subdomain=boundary, value=v, species=s)
+           for s, v in zip([mobile, trapped], [ex_m, ex_t])]
+    m = F.HydrogenTransportProblem(
+        mesh=F.Mesh(raw), subdomains=[vol, boundary], boundary_conditions=bcs,
+        species=[mobile, trapped], temperature=T,
+        reactions=[F.Reaction(reactant=[mobile, empty], product=trapped, k_0=k_0, E_k=E_k,
+                              p_0=p_0, E_p=E_p, volume=vol)],
+        sources=[F.ParticleSource(value=f, volume=vol, species=mobile),
+                 F.ParticleSource(value=g, volume=vol, species=trapped)],
+        advection_terms=[F.AdvectionTerm(velocity=vel, subdomain=vol, species=mobile)],
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=False))
+    return m, (mobile, trapped), (ex_m, ex_t)

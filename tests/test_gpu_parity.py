@@ -136,3 +136,64 @@ def test_tds_adaptive_stepping_parity():
     for eg, er in zip(g[3], r[3]):
         dg, dr = np.array(eg.data), np.array(er.data)
         assert np.abs(dg - dr).max() <= 1e-6 * max(np.abs(dr).max(), 1e-300)
+
+
+@pytest.mark.parametrize("T_dependent", [False, True])
+def test_heat_transfer_parity(T_dependent):
+    """a16: heat problem, constant and solution-dependent conductivity."""
+    from cases import heat_mms
+
+    (gm, _), (rm, _) = _pair(heat_mms, T_dependent, 400)
+    _check_assembly(gm, rm, seed=2)
+    gm.u.x.array[:] = 0.0
+    rm.u.x.array[:] = 0.0
+    gm.run()
+    rm.run()
+    assert gm.solver.solver.getIterationNumber() == rm.solver.solver.getIterationNumber()
+    assert _rel(gm.u.x.array, rm.u.x.array) < 1e-8
+
+
+@pytest.mark.parametrize("heat", [False, True])
+def test_flux_bc_parity(heat):
+    """a7: facet (flux) terms."""
+    from cases import flux_bc_mms
+
+    (gm, _, _), (rm, _, _) = _pair(flux_bc_mms, heat, 300)
+    _check_assembly(gm, rm, seed=3)
+    gm.u.x.array[:] = 0.0
+    rm.u.x.array[:] = 0.0
+    gm.run()
+    rm.run()
+    assert _rel(gm.u.x.array, rm.u.x.array) < 1e-8
+
+
+def test_coupled_heat_hydrogen_parity():
+    """a17: staggered coupling, T aliased between the two problems."""
+    from cases import coupled_heat_hydrogen_mms
+
+    cg, sg, _ = coupled_heat_hydrogen_mms(300, 10)
+    cr, sr, _ = coupled_heat_hydrogen_mms(300, 10)
+    cr.heat_problem.solver_backend = OracleBackend()
+    cr.hydrogen_problem.solver_backend = OracleBackend()
+    for c in (cg, cr):
+        c.initialise()
+        c.run()
+    assert cg.hydrogen_problem.timesteps == cr.hydrogen_problem.timesteps
+    assert _rel(cg.heat_problem.u.x.array, cr.heat_problem.u.x.array) < 1e-8
+    for a, b in zip(sg, sr):
+        assert _rel(a.post_processing_solution.x.array, b.post_processing_solution.x.array) < 1e-8
+
+
+def test_advection_trap_parity_2d():
+    """a8: advection (non-symmetric J -> GMRES) with a trap, T given as a Function."""
+    from cases import advection_trap_mms_2d
+
+    (gm, sg, _), (rm, sr, _) = _pair(advection_trap_mms_2d, 24)
+    _check_assembly(gm, rm, seed=4)
+    gm.u.x.array[:] = 0.0
+    rm.u.x.array[:] = 0.0
+    gm.run()
+    rm.run()
+    assert gm.solver.solver.getIterationNumber() == rm.solver.solver.getIterationNumber()
+    for a, b in zip(sg, sr):
+        assert _rel(a.post_processing_solution.x.array, b.post_processing_solution.x.array) < 1e-8

@@ -85,3 +85,54 @@ def test_tds_adaptive_stepping_runs():
     assert float(m.t) >= 60.0
     trapped = trap.trapped_concentration.post_processing_solution.x.array
     assert trapped.max() < 1e-3 * 8.19e22
+
+
+@pytest.mark.parametrize("T_dependent", [False, True])
+def test_heat_transfer_MMS(T_dependent):
+    """reference test/test_heat_transfer_problem.py:67-110 and :113-165 (L2 < 1e-7)."""
+    from cases import heat_mms
+
+    p, exact = heat_mms(T_dependent)
+    _run(p)
+    assert p.solver.solver.getConvergedReason() > 0
+    assert error_L2(p.mesh.mesh, p.u.x.array, exact) < 1e-7
+
+
+@pytest.mark.parametrize("heat", [False, True])
+def test_flux_bc_MMS_steady_state(heat):
+    """reference test/system_tests/test_fluxes.py:13-57, :60-95 (L2 < 1e-7)."""
+    from cases import flux_bc_mms
+
+    m, field, exact = flux_bc_mms(heat)
+    _run(m)
+    arr = m.u.x.array if heat else field.post_processing_solution.x.array
+    assert error_L2(m.mesh.mesh, arr, exact) < 1e-7
+
+
+def test_MMS_coupled_problem():
+    """reference test/system_tests/test_coupled_heat_hydrogen.py:9-207 (< 2e-7 x 3)."""
+    from cases import coupled_heat_hydrogen_mms
+
+    c, (mobile, trapped), exact = coupled_heat_hydrogen_mms()
+    c.heat_problem.solver_backend = OracleBackend()
+    c.hydrogen_problem.solver_backend = OracleBackend()
+    c.initialise()
+    c.run()
+    mesh = c.heat_problem.mesh.mesh
+    assert c.hydrogen_problem.temperature_fenics is c.heat_problem.u
+    assert error_L2(mesh, c.heat_problem.u.x.array, exact[0]) < 2e-7
+    assert error_L2(mesh, mobile.post_processing_solution.x.array, exact[1]) < 2e-7
+    assert error_L2(mesh, trapped.post_processing_solution.x.array, exact[2]) < 2e-7
+
+
+def test_MMS_1_species_1_trap_with_advection():
+    """reference test/system_tests/test_advection_term_integration.py:15-142 on a
+    100 x 100 square (the reference uses 200 x 200 with thresholds 2e-3 / 7e-5; the
+    error is O(h^2), hence 4x the thresholds here to keep the CPU suite short)."""
+    from cases import advection_trap_mms_2d
+
+    m, (mobile, trapped), (em, et) = advection_trap_mms_2d(100)
+    _run(m)
+    mesh = m.mesh.mesh
+    assert error_L2(mesh, mobile.post_processing_solution.x.array, em) < 4 * 2e-3
+    assert error_L2(mesh, trapped.post_processing_solution.x.array, et) < 4 * 7e-5
