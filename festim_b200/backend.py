@@ -73,6 +73,12 @@ def load_library():
         "fb_total_volume": (i, [vp, vp, i, i, _f64p]),
         "fb_total_surface": (i, [vp, vp, i, i, _f64p]),
         "fb_surface_flux": (i, [vp, vp, i, i, d, vp, _f64p]),
+        "fb_set_owned": (i, [vp, i64]),
+        "fb_bjacobi_setup": (i, [vp, vp]),
+        "fb_precond": (i, [vp, vp, vp]),
+        "fb_dcg_init": (i, [vp, vp, vp, vp, vp, vp, vp]),
+        "fb_dcg_spmv_dots": (i, [vp, vp, vp, vp, vp, vp]),
+        "fb_dcg_update": (i, [vp, d, d, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -88,7 +94,8 @@ EXPORTED_SYMBOLS = [
     "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
     "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
     "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
-    "fb_total_surface", "fb_surface_flux",
+    "fb_total_surface", "fb_surface_flux", "fb_set_owned", "fb_bjacobi_setup", "fb_precond",
+    "fb_dcg_init", "fb_dcg_spmv_dots", "fb_dcg_update",
 ]
 
 

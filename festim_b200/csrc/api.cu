@@ -58,7 +58,7 @@ extern "C" int fb_set_mesh(fb_ctx* ctx, int tdim, int64_t nv, int64_t nc, const 
   if (nv * (long long)FB_MAX_NS >= (1LL << 31)) return fb_fail(ctx, "mesh too large for int32 local indices");
   cudaSetDevice(ctx->device);
   DevSpec& S = ctx->S;
-  S.tdim = tdim; S.n_vertices = nv; S.n_cells = nc; S.n_bfacets = nf;
+  S.tdim = tdim; S.n_vertices = nv; S.n_cells = nc; S.n_bfacets = nf; S.n_owned = nv;
   int rc;
   if ((rc = fb_upload(ctx, &S.coords, coords, (size_t)nv * tdim))) return rc;
   if ((rc = fb_upload(ctx, &S.cells, cells, (size_t)nc * (tdim + 1)))) return rc;
@@ -152,6 +152,8 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     }
   }
   S.n_dofs = S.n_vertices * S.ns;
+  if (S.n_owned <= 0 || S.n_owned > S.n_vertices) S.n_owned = S.n_vertices;
+  S.n_owned_dofs = S.n_owned * S.ns;
   const int n_scalars = ints[I_NSCALARS];
   int rc;
 #define UP(id, code, field) if ((rc = upload_section(ctx, blob, nbytes, secs, id, code, &S.field))) return rc
@@ -283,4 +285,15 @@ extern "C" int fb_linear_solve(fb_ctx* ctx, const double* Jvals, const double* b
   if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
   cudaSetDevice(ctx->device);
   return fbi_linear_solve(ctx, Jvals, b, y, ksp, pc, rtol, atol, max_it, iters, relres);
+}
+
+// vertices [0, n_owned) are owned by this rank; the rest are ghosts whose values the
+// caller refreshes (halo exchange) before fb_assemble / fb_spmv.  Kernels then only
+// produce owned rows and reductions only cover owned entries.
+extern "C" int fb_set_owned(fb_ctx* ctx, int64_t n_owned_vertices) {
+  if (!ctx || !ctx->have_mesh) return ctx ? fb_fail(ctx, "fb_set_mesh first") : -1;
+  if (n_owned_vertices <= 0 || n_owned_vertices > ctx->S.n_vertices) return fb_fail(ctx, "bad owned count");
+  ctx->S.n_owned = n_owned_vertices;
+  ctx->S.n_owned_dofs = n_owned_vertices * (ctx->S.ns > 0 ? ctx->S.ns : 1);
+  return 0;
 }

@@ -326,7 +326,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
                                                        int flags) {
   constexpr int D1 = DIM + 1;
   const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= S.n_vertices) return;
+  if (v >= S.n_owned) return;  // ghost rows belong to another rank
   const int ns = S.ns;
   const bool doF = (flags & FB_ASSEMBLE_F) != 0, doJ = (flags & FB_ASSEMBLE_J) != 0;
   const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;

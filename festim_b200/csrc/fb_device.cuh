@@ -17,6 +17,8 @@ struct DevSpec {
   int tdim, ns, n_vtags, n_stags, transient, T_mode, npairs, n_slots, n_diffE;
   int n_vterms, n_fterms, n_adv, n_fields;
   long long n_vertices, n_cells, n_bfacets, n_dofs;
+  long long n_owned;   // vertices [0, n_owned) are owned by this rank, the rest are ghosts
+  long long n_owned_dofs;
   // mesh + pattern
   const double* coords;
   const int* cells;

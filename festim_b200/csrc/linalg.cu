@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(FB_TPB)
 k_spmv(DevSpec S, const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y) {
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
   const int lane = threadIdx.x % G;
-  if (row >= S.n_dofs) return;
+  if (row >= S.n_owned_dofs) return;
   const double sum = spmv_row<G>(S, J, x, row, lane);
   if (lane == 0) y[row] = sum;
 }
@@ -108,7 +108,7 @@ static unsigned vec_grid(fb_ctx* ctx, long long n) {
 
 static int dot_to_host(fb_ctx* ctx, const double* x, const double* y, double* out) {
   const DevSpec& S = ctx->S;
-  FB_LAUNCH(ctx, k_dot, vec_grid(ctx, S.n_dofs), FB_TPB, 0, S.n_dofs, x, y, ctx->d_red, ctx->d_ticket,
+  FB_LAUNCH(ctx, k_dot, vec_grid(ctx, S.n_owned_dofs), FB_TPB, 0, S.n_owned_dofs, x, y, ctx->d_red, ctx->d_ticket,
             ctx->d_sc + 60);
   FB_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_sc + 60, sizeof(double), cudaMemcpyDeviceToHost,
                                 ctx->stream));
@@ -132,7 +132,7 @@ extern "C" int fb_dot(fb_ctx* ctx, const double* x, const double* y, double* out
 }
 
 extern "C" int fb_axpy(fb_ctx* ctx, double a, const double* x, double* y) {
-  FB_LAUNCH(ctx, k_axpy, vec_grid(ctx, ctx->S.n_dofs), FB_TPB, 0, ctx->S.n_dofs, a, x, y);
+  FB_LAUNCH(ctx, k_axpy, vec_grid(ctx, ctx->S.n_owned_dofs), FB_TPB, 0, ctx->S.n_owned_dofs, a, x, y);
   FB_CHECK(ctx, cudaGetLastError());
   return 0;
 }
@@ -143,7 +143,7 @@ extern "C" int fb_axpy(fb_ctx* ctx, double a, const double* x, double* y) {
 __global__ void k_bjacobi_setup(DevSpec S, const double* __restrict__ J, double* __restrict__ dinv,
                                 int* __restrict__ flags) {
   const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= S.n_vertices) return;
+  if (v >= S.n_owned) return;
   const int ns = S.ns;
   const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
   int kself = 0;
@@ -203,7 +203,7 @@ __global__ void k_precond(DevSpec S, const double* __restrict__ dinv, const doub
                           double* __restrict__ z, const int* __restrict__ flags) {
   if (flags && flags[0]) return;
   const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= S.n_vertices) return;
+  if (v >= S.n_owned) return;
   double rin[FB_MAX_NS], zo[FB_MAX_NS];
   for (int s = 0; s < S.ns; ++s) rin[s] = r[v * S.ns + s];
   bjacobi_apply(S.ns, dinv, v, rin, zo);
@@ -218,7 +218,7 @@ __global__ void k_precond(DevSpec S, const double* __restrict__ dinv, const doub
 __global__ void k_cg_init(DevSpec S, const double* __restrict__ dinv, const double* __restrict__ b,
                           double* x, double* r, double* u, double* p, double* s_) {
   const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= S.n_vertices) return;
+  if (v >= S.n_owned) return;
   double rin[FB_MAX_NS], zo[FB_MAX_NS];
   for (int s = 0; s < S.ns; ++s) {
     const long long i = v * S.ns + s;
@@ -236,7 +236,7 @@ k_cg_update(DevSpec S, const double* __restrict__ dinv, const double* __restrict
             double* __restrict__ s_) {
   if (flags[0]) return;
   const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= S.n_vertices) return;
+  if (v >= S.n_owned) return;
   const double alpha = sc[0], beta = sc[1];
   double rin[FB_MAX_NS], zo[FB_MAX_NS];
   for (int s = 0; s < S.ns; ++s) {
@@ -261,7 +261,7 @@ k_cg_spmv_dots(DevSpec S, const double* __restrict__ J, const double* __restrict
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
   const int lane = threadIdx.x % G;
   double v[3] = {0.0, 0.0, 0.0}, tot[3];
-  if (row < S.n_dofs) {  // uniform within each G-lane group
+  if (row < S.n_owned_dofs) {  // uniform within each G-lane group
     const double sum = spmv_row<G>(S, J, u, row, lane);
     if (lane == 0) {
       w[row] = sum;
@@ -1078,5 +1078,108 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   }
   if (status == 1) { ctx->err = "Krylov breakdown"; return 1; }
   if (status == 2) { ctx->err = "Krylov solver did not converge"; return 2; }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Building blocks of the partitioned (multi-GPU) CG.  Every rank owns the vertices
+// [0, n_owned) of its local numbering (fb_set_owned); the host driver
+// (festim_b200/distributed.py) refreshes the ghost entries of u through NCCL before
+// fb_dcg_spmv_dots and all-reduces the three partial dot products it returns.  The
+// recurrence is the same single-reduction (Chronopoulos-Gear) form the single-GPU
+// kernels use, so one all-reduce of three doubles per iteration is all that crosses
+// NVLink besides the halo.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FB_TPB)
+k_dcg_update(DevSpec S, const double* __restrict__ dinv, double alpha, double beta, double* __restrict__ x,
+             double* __restrict__ r, double* __restrict__ u, const double* __restrict__ w,
+             double* __restrict__ p, double* __restrict__ s_) {
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= S.n_owned) return;
+  double rin[FB_MAX_NS], zo[FB_MAX_NS];
+  for (int s = 0; s < S.ns; ++s) {
+    const long long i = v * S.ns + s;
+    const double pi = u[i] + beta * p[i];
+    const double si = w[i] + beta * s_[i];
+    p[i] = pi; s_[i] = si;
+    x[i] += alpha * pi;
+    rin[s] = r[i] - alpha * si;
+    r[i] = rin[s];
+  }
+  bjacobi_apply(S.ns, dinv, v, rin, zo);
+  for (int s = 0; s < S.ns; ++s) u[v * S.ns + s] = zo[s];
+}
+
+template <int G>
+__global__ void __launch_bounds__(FB_TPB)
+k_dcg_spmv_dots(DevSpec S, const double* __restrict__ J, const double* __restrict__ u,
+                const double* __restrict__ r, double* __restrict__ w, double* partials, unsigned* ticket,
+                double* out3) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  double v[3] = {0.0, 0.0, 0.0}, tot[3];
+  if (row < S.n_owned_dofs) {
+    const double sum = spmv_row<G>(S, J, u, row, lane);
+    if (lane == 0) {
+      w[row] = sum;
+      const double ri = r[row], ui = u[row];
+      v[0] = ri * ui; v[1] = sum * ui; v[2] = ui * ui;
+    }
+  }
+  if (grid_reduce<3>(v, partials, ticket, tot) && threadIdx.x == 0) {
+    out3[0] = tot[0]; out3[1] = tot[1]; out3[2] = tot[2];
+  }
+}
+
+extern "C" int fb_bjacobi_setup(fb_ctx* ctx, const double* J) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  int rc = fbi_ensure_workspace(ctx);
+  if (rc) return rc;
+  const DevSpec& S = ctx->S;
+  FB_LAUNCH(ctx, k_bjacobi_setup, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, J, ctx->d_dinv, ctx->d_flags);
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_precond(fb_ctx* ctx, const double* r, double* z) {
+  if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
+  const DevSpec& S = ctx->S;
+  FB_LAUNCH(ctx, k_precond, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, ctx->d_dinv, r, z, (const int*)nullptr);
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_dcg_init(fb_ctx* ctx, const double* b, double* x, double* r, double* u, double* p, double* s) {
+  if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
+  const DevSpec& S = ctx->S;
+  FB_LAUNCH(ctx, k_cg_init, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, ctx->d_dinv, b, x, r, u, p, s);
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_dcg_spmv_dots(fb_ctx* ctx, const double* J, const double* u, const double* r, double* w,
+                                double* out3_dev) {
+  if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
+  const DevSpec& S = ctx->S;
+  const int G = spmv_group(S);
+  const unsigned gs = (unsigned)((S.n_owned_dofs * G + FB_TPB - 1) / FB_TPB);
+  if ((long long)gs * 3 > ctx->red_doubles) return fb_fail(ctx, "reduction buffer too small");
+  switch (G) {
+    case 4: FB_LAUNCH(ctx, k_dcg_spmv_dots<4>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, out3_dev); break;
+    case 8: FB_LAUNCH(ctx, k_dcg_spmv_dots<8>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, out3_dev); break;
+    case 16: FB_LAUNCH(ctx, k_dcg_spmv_dots<16>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, out3_dev); break;
+    default: FB_LAUNCH(ctx, k_dcg_spmv_dots<32>, gs, FB_TPB, 0, S, J, u, r, w, ctx->d_red, ctx->d_ticket, out3_dev); break;
+  }
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fb_dcg_update(fb_ctx* ctx, double alpha, double beta, double* x, double* r, double* u,
+                             const double* w, double* p, double* s) {
+  if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
+  const DevSpec& S = ctx->S;
+  FB_LAUNCH(ctx, k_dcg_update, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, ctx->d_dinv, alpha, beta, x, r, u, w, p, s);
+  FB_CHECK(ctx, cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,379 @@
+"""Mesh partitioning and the multi-GPU Newton-CG driver (one process per GPU).
+
+Replaces what the reference inherits from dolfinx/PETSc when run under ``mpirun``
+(SURVEY 2.3, 8e): mesh partition, ``IndexMap`` ghost scatter, ``MPI_Allreduce`` in
+norms and dot products.  Design:
+
+* vertex-owned decomposition by recursive coordinate bisection (NVSwitch is
+  uniform, so the partition need not be topology-aware);
+* every rank numbers its owned vertices first and its ghosts after, grouped by
+  owner, and keeps **all cells touching an owned vertex**; the gather assembly
+  writes owned rows only, so there is no reverse (ADD) scatter of partial sums -
+  unlike dolfinx's ``ghostUpdate(ADD, REVERSE)`` - only the forward owner->ghost
+  exchange of ``u`` before assembly and of the CG vector before each SpMV;
+* the Krylov recurrence is the single-reduction CG of the single-GPU path, split
+  at its two communication points (``fb_dcg_*`` in ``include/festim_b200.h``):
+  one halo exchange and one all-reduce of three doubles per iteration;
+* collectives go through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU
+  tests of the host logic); all arithmetic runs in the CUDA library.
+
+Round-1 limits: the host keeps the global problem on every rank (only device work
+is partitioned); symmetric systems (CG) only; derived quantities are evaluated on
+the gathered global field.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import types
+
+import numpy as np
+
+from festim_b200 import fem
+from festim_b200.mesh import MeshTags, SimplexMesh
+
+
+# --------------------------------------------------------------------------
+# partitioning (pure numpy: also exercised by the gloo CPU tests)
+# --------------------------------------------------------------------------
+def partition_rcb(coords, nparts):
+    """Recursive coordinate bisection; returns the part id of every vertex.
+    Splits are proportional, so any ``nparts`` gives balanced parts."""
+    part = np.zeros(len(coords), dtype=np.int32)
+
+    def split(idx, first, count):
+        if count == 1:
+            part[idx] = first
+            return
+        left = count // 2
+        ext = coords[idx].max(axis=0) - coords[idx].min(axis=0)
+        axis = int(np.argmax(ext))
+        order = idx[np.argsort(coords[idx, axis], kind="stable")]
+        cut = (len(order) * left) // count
+        split(order[:cut], first, left)
+        split(order[cut:], first + left, count - left)
+
+    split(np.arange(len(coords)), 0, nparts)
+    return part
+
+
+class LocalPartition:
+    """Local view of rank ``rank``: numbering, cells, facets, halo lists."""
+
+    def __init__(self, mesh, part, rank, nranks):
+        self.rank, self.nranks = rank, nranks
+        cells = mesh.cells
+        owned_mask = part == rank
+        self.owned = np.nonzero(owned_mask)[0].astype(np.int64)
+        cell_local = owned_mask[cells].any(axis=1)
+        self.local_cells = np.nonzero(cell_local)[0]
+        verts = np.unique(cells[self.local_cells].ravel())
+        ghosts = verts[~owned_mask[verts]]
+        order = np.lexsort((ghosts, part[ghosts]))       # by owner, then global id
+        self.ghosts = ghosts[order].astype(np.int64)
+        self.ghost_owner = part[self.ghosts]
+        self.l2g = np.concatenate([self.owned, self.ghosts])
+        self.n_owned = len(self.owned)
+        g2l = np.full(mesh.num_vertices, -1, dtype=np.int64)
+        g2l[self.l2g] = np.arange(len(self.l2g))
+        self.g2l = g2l
+        # receive segments: contiguous ranges of the ghost block, one per owner
+        self.recv = {}
+        for q in np.unique(self.ghost_owner):
+            sel = np.nonzero(self.ghost_owner == q)[0]
+            self.recv[int(q)] = (self.n_owned + int(sel[0]), self.n_owned + int(sel[-1]) + 1)
+        # send lists: my owned vertices that are ghosts of rank q, in q's ghost order
+        self.send = {}
+        for q in range(nranks):
+            if q == rank:
+                continue
+            q_mask = part == q
+            q_cells = q_mask[cells].any(axis=1)
+            qv = np.unique(cells[q_cells].ravel())
+            mine = qv[owned_mask[qv]]                        # sorted by global id
+            if len(mine):
+                self.send[q] = g2l[mine]
+        # local mesh (exterior facets: the global ones that touch an owned vertex)
+        lcells = g2l[cells[self.local_cells]]
+        self.mesh = SimplexMesh(mesh.coords[self.l2g], lcells)
+        gcell_to_local = np.full(mesh.num_cells, -1, dtype=np.int64)
+        gcell_to_local[self.local_cells] = np.arange(len(self.local_cells))
+        bf, bfc = mesh.bfacets, mesh.bfacet_cell
+        keep = owned_mask[bf].any(axis=1) & (gcell_to_local[bfc] >= 0)
+        self.local_bfacets = np.nonzero(keep)[0]
+        self.mesh._bfacets = g2l[bf[keep]].astype(np.int32)
+        self.mesh._bfacet_cell = gcell_to_local[bfc[keep]].astype(np.int32)
+
+    def local_dofs(self, ns):
+        return (self.l2g[:, None] * ns + np.arange(ns)[None, :]).ravel()
+
+
+class HaloExchange:
+    """Owner -> ghost update of a node-major blocked vector over torch.distributed."""
+
+    def __init__(self, part: LocalPartition, ns, torch, device):
+        self.p, self.ns, self.torch = part, ns, torch
+        self.send_idx = {q: torch.as_tensor(idx, dtype=torch.long, device=device)
+                         for q, idx in part.send.items()}
+        self.bytes_per_exchange = 8 * ns * sum(len(v) for v in part.send.values())
+
+    def __call__(self, vec):
+        import torch.distributed as dist
+
+        if self.p.nranks == 1:
+            return
+        v2 = vec.view(-1, self.ns)
+        ops, keep = [], []
+        for q, idx in self.send_idx.items():
+            buf = v2.index_select(0, idx).contiguous()
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, q))
+        for q, (a, b) in self.p.recv.items():
+            ops.append(dist.P2POp(dist.irecv, v2[a:b], q))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+def allreduce_sum(values, torch, device):
+    import torch.distributed as dist
+
+    t = torch.as_tensor(np.asarray(values, dtype=np.float64), device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+# --------------------------------------------------------------------------
+# the solver object at the create_solver seam, partitioned
+# --------------------------------------------------------------------------
+class _Snes:
+    def __init__(self):
+        self.reason, self.its, self.linear_its, self.fnorm = 0, 0, 0, 0.0
+
+    def getConvergedReason(self):
+        return self.reason
+
+    def getIterationNumber(self):
+        return self.its
+
+    def getLinearSolveIterations(self):
+        return self.linear_its
+
+
+class DistributedNewtonSolver:
+    def __init__(self, problem, petsc_options, device=0):
+        import torch
+        import torch.distributed as dist
+
+        from festim_b200.backend import Context, _np_ptr
+        from festim_b200.lowering import KernelSpec
+
+        self.torch, self.dist = torch, dist
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.nranks = dist.get_world_size() if dist.is_initialized() else 1
+        self.problem = problem
+        gmesh = problem.mesh.mesh
+        species = getattr(problem, "species", None) or [problem._unknown]
+        self.ns = ns = len(species)
+        self.part_of = partition_rcb(gmesh.coords, self.nranks)
+        self.part = lp = LocalPartition(gmesh, self.part_of, self.rank, self.nranks)
+        # local tags
+        ctag = np.zeros(gmesh.num_cells, dtype=np.int32)
+        ctag[problem.volume_meshtags.indices] = problem.volume_meshtags.values
+        ftag = np.zeros(gmesh.bfacets.shape[0], dtype=np.int32)
+        ftag[problem.facet_meshtags.indices] = problem.facet_meshtags.values
+        vt = MeshTags(lp.mesh, gmesh.tdim, np.arange(len(lp.local_cells)), ctag[lp.local_cells])
+        ft = MeshTags(lp.mesh, gmesh.tdim - 1, np.arange(len(lp.local_bfacets)), ftag[lp.local_bfacets])
+        view = _ProblemView(problem, lp.mesh, vt, ft)
+        self.spec = KernelSpec(view)
+        self.ctx = ctx = Context(self.spec, device)
+        ctx._check(ctx.lib.fb_set_owned(ctx.h, lp.n_owned))
+        self.halo = HaloExchange(lp, ns, torch, ctx.device)
+        self.atol = petsc_options["snes_atol"]
+        self.rtol = petsc_options["snes_rtol"]
+        self.stol = float(petsc_options["snes_stol"])
+        self.max_it = int(petsc_options["snes_max_it"])
+        snes_rtol = self.rtol if isinstance(self.rtol, (int, float)) else 1e-10
+        self.ksp_rtol = float(petsc_options.get("ksp_rtol", min(1e-12, max(1e-2 * snes_rtol, 1e-15))))
+        self.ksp_max_it = int(petsc_options.get("ksp_max_it", 20000))
+        self.solver = _Snes()
+        # Dirichlet dofs restricted to local vertices (owned and ghost columns)
+        self._bc_forms = list(problem.bc_forms)
+        gd = np.concatenate([bc.dofs for bc in self._bc_forms]) if self._bc_forms else np.zeros(0, np.int64)
+        uniq, first_rev = np.unique(gd[::-1], return_index=True)
+        pick = len(gd) - 1 - first_rev
+        lv = lp.g2l[uniq // ns]
+        loc = lv >= 0
+        self._bc_pick = pick[loc]
+        self._bc_dofs = np.ascontiguousarray(lv[loc] * ns + uniq[loc] % ns, dtype=np.int64)
+        ctx._check(ctx.lib.fb_set_dirichlet(ctx.h, len(self._bc_dofs), _np_ptr(self._bc_dofs, C.c_int64)))
+        self.ldofs = lp.local_dofs(ns)
+        self.owned_gdofs = self.ldofs[: lp.n_owned * ns]
+        self._signature = None
+        n = ctx.n_dofs
+        z = ctx.zeros
+        self.F, self.J, self.y = z(n), z(ctx.nnz), z(n)
+        self.r, self.uv, self.w, self.p, self.s, self.tmp = z(n), z(n), z(n), z(n), z(n), z(n)
+        self.out3 = z(3)
+        self.cg_iterations = 0
+        self.launches_python = 0
+
+    # ---- data movement -----------------------------------------------------------
+    def _push_state(self):
+        from festim_b200.backend import _np_ptr
+
+        ctx, spec, lp, lib = self.ctx, self.spec, self.part, self.ctx.lib
+        scal = spec.scalar_values()
+        T = spec.temperature
+        parts = [scal.tobytes()]
+        if isinstance(T, fem.Function):
+            parts.append(T.x.array.tobytes())
+        elif T is not None:
+            parts.append(np.float64(T.value).tobytes())
+        for f in spec.fields:
+            parts.append(f.x.array.tobytes())
+        sig = hash(b"".join(parts))
+        bc_vals = np.concatenate([bc.values() for bc in self._bc_forms])[self._bc_pick] \
+            if self._bc_forms else np.zeros(0)
+        bc_dev = ctx.to_device("bc_vals", bc_vals) if len(bc_vals) else None
+        ctx._check(lib.fb_set_dirichlet_values(ctx.h, ctx.ptr(bc_dev)))
+        if sig == self._signature:
+            return
+        self._signature = sig
+        ctx._check(lib.fb_set_scalars(ctx.h, len(scal), _np_ptr(scal, C.c_double)))
+        if isinstance(T, fem.Function):
+            ctx._check(lib.fb_set_temperature(ctx.h, 0.0, ctx.ptr(ctx.to_device("T", T.x.array[lp.l2g]))))
+        elif T is not None:
+            ctx._check(lib.fb_set_temperature(ctx.h, float(T.value), C.c_void_p()))
+        for k, f in enumerate(spec.fields):
+            ctx._check(lib.fb_set_field(ctx.h, k, ctx.ptr(ctx.to_device(f"field{k}", f.x.array[lp.l2g]))))
+        if spec.adv:
+            raise NotImplementedError("partitioned advection problems need the GMRES path")
+        ctx._check(lib.fb_update_load(ctx.h))
+
+    def _dot(self, a, b):
+        out = C.c_double()
+        self.ctx._check(self.ctx.lib.fb_dot(self.ctx.h, self.ctx.ptr(a), self.ctx.ptr(b), C.byref(out)))
+        return out.value
+
+    def _norm(self, a):
+        return float(np.sqrt(allreduce_sum([self._dot(a, a)], self.torch, self.ctx.device)[0]))
+
+    # ---- partitioned CG (block-Jacobi preconditioned, single reduction) -------------
+    def linear_solve(self, J, b, x, rtol, max_it):
+        ctx, lib, ptr = self.ctx, self.ctx.lib, self.ctx.ptr
+        ctx._check(lib.fb_bjacobi_setup(ctx.h, ptr(J)))
+        ctx._check(lib.fb_precond(ctx.h, ptr(b), ptr(self.tmp)))
+        thr2 = (rtol * self._norm(self.tmp)) ** 2
+        r, u, w, p, s = self.r, self.uv, self.w, self.p, self.s
+        ctx._check(lib.fb_dcg_init(ctx.h, ptr(b), ptr(x), ptr(r), ptr(u), ptr(p), ptr(s)))
+        alpha = beta = gamma_old = 0.0
+        it = 0
+        while True:
+            self.halo(u)
+            ctx._check(lib.fb_dcg_spmv_dots(ctx.h, ptr(J), ptr(u), ptr(r), ptr(w), ptr(self.out3)))
+            if self.nranks > 1:
+                self.dist.all_reduce(self.out3)
+            gamma, delta, uu = self.out3.cpu().numpy()
+            if uu <= thr2 or not np.isfinite(uu) or it >= max_it:
+                break
+            if it == 0:
+                beta, alpha = 0.0, gamma / delta
+            else:
+                beta = gamma / gamma_old
+                alpha = gamma / (delta - beta * gamma / alpha)
+            gamma_old = gamma
+            ctx._check(lib.fb_dcg_update(ctx.h, float(alpha), float(beta), ptr(x), ptr(r), ptr(u),
+                                         ptr(w), ptr(p), ptr(s)))
+            it += 1
+        self.cg_iterations += it
+        return it, bool(uu <= thr2)
+
+    # ---- Newton (reference problem.py:271-289, helpers.py:408-426) --------------------
+    def solve(self):
+        ctx, lib, ptr, p = self.ctx, self.ctx.lib, self.ctx.ptr, self.problem
+        if not self._is_symmetric():
+            raise NotImplementedError("the partitioned path implements CG (SPD systems) only")
+        self._push_state()
+        u = ctx.to_device("u", p.u.x.array[self.ldofs])
+        un = ctx.to_device("u_n", p.u_n.x.array[self.ldofs]) if self.spec.transient else u
+        t = float(p.t) if hasattr(p, "t") else 0.0
+        atol = self.atol(t) if callable(self.atol) else self.atol
+        rtol = self.rtol(t) if callable(self.rtol) else self.rtol
+        it, snorm, f0, lin_total, reason = 0, 0.0, 1.0, 0, 0
+        while True:
+            self.halo(u)
+            if un is not u:
+                self.halo(un)
+            ctx._check(lib.fb_assemble(ctx.h, ptr(u), ptr(un), ptr(self.F), ptr(self.J), 3 if it == 0 else 1))
+            fn = self._norm(self.F)
+            if it == 0:
+                f0 = fn
+            if not np.isfinite(fn):
+                reason = -4
+                break
+            if f0 == 0.0 or fn < atol:
+                reason = 2
+                break
+            if fn / f0 < rtol:
+                reason = 3
+                break
+            if snorm < self.stol and it > 0:
+                reason = 4
+                break
+            if it >= self.max_it:
+                reason = -5
+                break
+            if it > 0:
+                ctx._check(lib.fb_assemble(ctx.h, ptr(u), ptr(un), C.c_void_p(), ptr(self.J), 2))
+            its, ok = self.linear_solve(self.J, self.F, self.y, self.ksp_rtol, self.ksp_max_it)
+            lin_total += its
+            if not ok:
+                reason = -3
+                break
+            ctx._check(lib.fb_axpy(ctx.h, -1.0, ptr(self.y), ptr(u)))
+            snorm = self._norm(self.y)
+            it += 1
+        self.solver.its, self.solver.reason, self.solver.linear_its, self.solver.fnorm = it, reason, lin_total, fn
+        self.u_dev = u
+        self._gather(u)
+        return it
+
+    def _is_symmetric(self):
+        spec = self.spec
+        return not spec.adv and not spec.diff_udep and all(
+            not t.derivs for t in spec.vterms + spec.fterms)
+
+    def _gather(self, u):
+        """Owned values of every rank -> the global host vector on every rank."""
+        torch, dist, p = self.torch, self.dist, self.problem
+        mine = u[: self.part.n_owned * self.ns].cpu().numpy()
+        if self.nranks == 1:
+            p.u.x.array[self.owned_gdofs] = mine
+            return
+        objs = [None] * self.nranks
+        dist.all_gather_object(objs, (self.owned_gdofs, mine))
+        for gd, vals in objs:
+            p.u.x.array[gd] = vals
+
+
+class _ProblemView:
+    """The problem with its mesh and tags replaced by the local partition."""
+
+    def __init__(self, problem, local_mesh, vt, ft):
+        self._problem = problem
+        self.mesh = types.SimpleNamespace(mesh=local_mesh)
+        self.volume_meshtags = vt
+        self.facet_meshtags = ft
+
+    def __getattr__(self, name):
+        return getattr(self._problem, name)
+
+
+class DistributedBackend:
+    def __init__(self, device=0):
+        self.device = device
+
+    def create_newton_solver(self, problem, petsc_options):
+        return DistributedNewtonSolver(problem, petsc_options, self.device)

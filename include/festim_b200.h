@@ -150,6 +150,21 @@ int fb_surface_flux(fb_ctx* ctx, const double* u /*[dev]*/, int species, int sta
                     double T_D_const, const double* T_D_nodal /*[dev] or NULL*/,
                     double* out /*[host]*/);
 
+/* -- partitioned meshes (one process per GPU; replaces dolfinx IndexMap ghost updates and
+ *    PETSc's MPI reductions).  The first n_owned vertices of the local
+ *    numbering are owned, the rest are ghosts refreshed by the caller (NCCL) before
+ *    fb_assemble / fb_spmv / fb_dcg_spmv_dots; kernels write owned rows only and reductions
+ *    cover owned entries only. ---------------------------------------------------------- */
+int fb_set_owned(fb_ctx* ctx, int64_t n_owned_vertices);
+int fb_bjacobi_setup(fb_ctx* ctx, const double* Jvals /*[dev]*/);
+int fb_precond(fb_ctx* ctx, const double* r /*[dev]*/, double* z /*[dev]*/); /* z = M^-1 r */
+/* single-reduction CG split at its two communication points */
+int fb_dcg_init(fb_ctx* ctx, const double* b, double* x, double* r, double* u, double* p, double* s);
+int fb_dcg_spmv_dots(fb_ctx* ctx, const double* Jvals, const double* u, const double* r, double* w,
+                     double* out3 /*[dev] local (r,u), (w,u), (u,u)*/);
+int fb_dcg_update(fb_ctx* ctx, double alpha, double beta, double* x, double* r, double* u,
+                  const double* w, double* p, double* s);
+
 #ifdef __cplusplus
 }
 #endif

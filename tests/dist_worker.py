@@ -1,0 +1,45 @@
+"""torchrun worker: partitioned solve of the 3D MMS diffusion problem on WORLD_SIZE
+GPUs, compared with the single-process oracle on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from cases import mms_1_mobile_steady  # noqa: E402
+from festim_b200.distributed import DistributedBackend  # noqa: E402
+from oracle.newton import OracleBackend  # noqa: E402
+
+
+def main():
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    m, H, _ = mms_1_mobile_steady(3, n)
+    m.solver_backend = DistributedBackend(device=local)
+    m.initialise()
+    m.run()
+    ok = True
+    if rank == 0:
+        r, Hr, _ = mms_1_mobile_steady(3, n)
+        r.solver_backend = OracleBackend()
+        r.initialise()
+        r.run()
+        a, b = H.post_processing_solution.x.array, Hr.post_processing_solution.x.array
+        rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+        ok = rel < 1e-8 and m.solver.solver.getIterationNumber() == r.solver.solver.getIterationNumber()
+        print(f"DIST world={dist.get_world_size()} rel={rel:.3e} newton={m.solver.solver.its} "
+              f"cg={m.solver.solver.linear_its} ok={ok}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,82 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo processes check
+the partition, the owner->ghost halo exchange and that owned-row SpMV + halo +
+all-reduce reproduce the global operator (no CUDA involved)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import festim_b200 as F
+from festim_b200.distributed import HaloExchange, LocalPartition, allreduce_sum, partition_rcb
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, dim, ns):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mesh = F.create_unit_square(9, 7) if dim == 2 else F.create_unit_cube(5, 4, 6)
+        part = partition_rcb(mesh.coords, world)
+        lp = LocalPartition(mesh, part, rank, world)
+        # 1. ownership is a partition of the vertices
+        owned = [None] * world
+        dist.all_gather_object(owned, lp.owned)
+        allv = np.concatenate(owned)
+        assert len(allv) == mesh.num_vertices and len(np.unique(allv)) == mesh.num_vertices
+        sizes = [len(o) for o in owned]
+        assert max(sizes) - min(sizes) <= 1
+        # 2. halo exchange delivers the owner's values to every ghost
+        halo = HaloExchange(lp, ns, torch, "cpu")
+        f = lambda g: np.sin(g[:, None] * 0.37 + np.arange(ns)[None, :])
+        vec = torch.zeros(len(lp.l2g) * ns, dtype=torch.float64)
+        vec.view(-1, ns)[: lp.n_owned] = torch.from_numpy(f(lp.owned))
+        halo(vec)
+        assert np.array_equal(vec.view(-1, ns).numpy(), f(lp.l2g))
+        # 3. owned rows of a global operator only reference owned + ghost vertices, and the
+        #    local SpMV after the halo equals the global one
+        rowptr, colidx = mesh.graph
+        rng = np.random.default_rng(7)
+        A = sp.csr_matrix((rng.standard_normal(len(colidx)), colidx, rowptr),
+                          shape=(mesh.num_vertices,) * 2)
+        x = rng.standard_normal(mesh.num_vertices)
+        rows = A[lp.owned]
+        assert np.all(lp.g2l[rows.indices] >= 0)
+        xl = torch.zeros(len(lp.l2g), dtype=torch.float64)
+        xl[: lp.n_owned] = torch.from_numpy(x[lp.owned])
+        HaloExchange(lp, 1, torch, "cpu")(xl)
+        y_local = rows[:, lp.l2g] @ xl.numpy()
+        assert np.allclose(y_local, (A @ x)[lp.owned], rtol=1e-14, atol=1e-14)
+        # 4. all-reduced owned dot products equal the global ones
+        tot = allreduce_sum([float(x[lp.owned] @ x[lp.owned])], torch, "cpu")[0]
+        assert abs(tot - x @ x) < 1e-12 * (x @ x)
+        # 5. every local cell touches an owned vertex; local facets touch an owned vertex
+        assert (lp.mesh.cells < lp.n_owned).any(axis=1).all()
+        assert (lp.mesh.bfacets < lp.n_owned).any(axis=1).all()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dim,ns", [(2, 1), (3, 2)])
+def test_partition_halo_spmv_world2(dim, ns):
+    mp.spawn(_worker, args=(2, _free_port(), dim, ns), nprocs=2, join=True)
+
+
+def test_rcb_balanced_any_count():
+    mesh = F.create_unit_cube(6, 5, 4)
+    for nparts in (1, 2, 3, 4, 5, 8):
+        part = partition_rcb(mesh.coords, nparts)
+        counts = np.bincount(part, minlength=nparts)
+        assert counts.sum() == mesh.num_vertices and counts.max() - counts.min() <= 1
