@@ -27,12 +27,46 @@ METRIC = "newton_step_dofs_per_s"
 UNIT = "DOFs/s"
 
 
-def build_workload(name, n):
+def proc_grid(world):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
+
+
+def build_workload(name, n, grid=(1, 1, 1)):
+    """C1, or its weak-scaling extension: the same problem on the box
+    [0,px] x [0,py] x [0,pz] with n cells per unit length (one C1 per GPU)."""
     from cases import mms_1_mobile_steady
 
-    if name in ("c1", "c1small"):
+    if name not in ("c1", "c1small"):
+        raise SystemExit(f"unknown workload {name}")
+    if grid == (1, 1, 1):
         return mms_1_mobile_steady(3, n)
-    raise SystemExit(f"unknown workload {name}")
+    import numpy as np
+
+    import festim_b200 as F
+    from festim_b200 import fem, ufl
+
+    px, py, pz = grid
+    raw = F.create_box(((0.0, 0.0, 0.0), (float(px), float(py), float(pz))), (n * px, n * py, n * pz))
+    u_exact = lambda mod: (lambda x: 1 + mod.sin(2 * mod.pi * x[0]) + mod.cos(2 * mod.pi * x[1]))
+    T_expr = lambda x: 500 + 100 * x[0]
+    x = ufl.SpatialCoordinate(raw)
+    T = fem.Function(fem.functionspace(raw, ("Lagrange", 1)))
+    T.interpolate(T_expr)
+    D = 1 * ufl.exp(-0.1 / (F.k_B * T))
+    m = F.HydrogenTransportProblem()
+    m.mesh = F.Mesh(raw)
+    vol = F.VolumeSubdomain(id=1, material=F.Material(D_0=1, E_D=0.1))
+    left = F.SurfaceSubdomain(id=1, locator=lambda x: np.isclose(x[0], 0))
+    right = F.SurfaceSubdomain(id=2, locator=lambda x: np.isclose(x[0], float(px)))
+    m.subdomains = [vol, left, right]
+    H = F.Species("H")
+    m.species = [H]
+    m.temperature = T_expr
+    m.boundary_conditions = [F.DirichletBC(subdomain=left, value=u_exact(ufl), species=H),
+                             F.DirichletBC(subdomain=right, value=u_exact(ufl), species=H)]
+    m.sources = [F.ParticleSource(value=-ufl.div(D * ufl.grad(u_exact(ufl)(x))), volume=vol, species=H)]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    return m, H, u_exact(np)
 
 
 def spmv_bytes(spec, nnzb):
@@ -104,6 +138,95 @@ def run_cpu_sample(n_small, steps=1):
     return ndofs / (best / its), ndofs, best, its
 
 
+def run_partitioned(args, rank, world, local_rank, config):
+    """N > 1: the mesh is partitioned over the ranks (weak scaling: one C1 per GPU);
+    halo exchange + all-reduce over NCCL, max-over-ranks device timing."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from festim_b200.distributed import DistributedBackend
+
+    grid = proc_grid(world)
+    model, H, exact = build_workload(args.workload, args.n, grid)
+    model.solver_backend = DistributedBackend(device=local_rank)
+    model.initialise()
+    solver = model.solver
+    ctx = solver.ctx
+    N_global = model.u.x.array.size
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+    solver._push_state()
+    u = ctx.zeros(ctx.n_dofs)
+
+    def device_step():
+        u.zero_()
+        ctx._check(ctx.lib.fb_update_load(ctx.h))
+        solver.newton_device(u, u, float(solver.atol), float(solver.rtol))
+        assert solver.solver.reason > 0, solver.solver.reason
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        ev[k][0].record()
+        device_step()
+        ev[k][1].record()
+    barrier()
+    launches = ctx.launches - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    its, lin = max(solver.solver.its, 1), solver.solver.linear_its
+
+    def api_step():
+        model.u.x.array[:] = 0.0
+        solver._signature = None
+        solver.solve()
+
+    api_step()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        api_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=ctx.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    sampler.stop_flag = True
+    if rank == 0:
+        config = dict(config)
+        config.update({"parallelism": f"mesh partitioned over {world} GPUs (RCB, grid {grid}), "
+                                      "halo exchange + all-reduce over NCCL",
+                       "cells": 6 * args.n ** 3 * world, "dofs": int(N_global),
+                       "halo_bytes_per_exchange_rank0": solver.halo.bytes_per_exchange})
+        nloc = solver.part.n_owned
+        print(json.dumps({
+            "metric": METRIC, "value": N_global / (ms * 1e-3 / its), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "newton_iterations_per_step": its, "linear_iterations_per_step": lin,
+            "e2e": {"value": N_global / (e2e_s / its), "unit": UNIT,
+                    "h2d_bytes_per_step": 8 * ctx.n_dofs + 8 * len(solver._bc_dofs),
+                    "d2h_bytes_per_step": 8 * int(N_global), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": None, "owned_vertices_rank0": int(nloc),
+            "note": "partitioned CG is the multi-launch form (one halo exchange and one 3-double "
+                    "all-reduce per iteration); the single-GPU number uses the persistent kernel"}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +283,8 @@ def main():
 
     from festim_b200.backend import B200Backend
 
+    if world > 1:
+        return run_partitioned(args, rank, world, local_rank, config)
     model, H, exact = build_workload(args.workload, args.n)
     model.solver_backend = B200Backend(device=local_rank)
     model.initialise()

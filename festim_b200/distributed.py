@@ -292,7 +292,7 @@ class DistributedNewtonSolver:
 
     # ---- Newton (reference problem.py:271-289, helpers.py:408-426) --------------------
     def solve(self):
-        ctx, lib, ptr, p = self.ctx, self.ctx.lib, self.ctx.ptr, self.problem
+        ctx, p = self.ctx, self.problem
         if not self._is_symmetric():
             raise NotImplementedError("the partitioned path implements CG (SPD systems) only")
         self._push_state()
@@ -301,6 +301,14 @@ class DistributedNewtonSolver:
         t = float(p.t) if hasattr(p, "t") else 0.0
         atol = self.atol(t) if callable(self.atol) else self.atol
         rtol = self.rtol(t) if callable(self.rtol) else self.rtol
+        it = self.newton_device(u, un, atol, rtol)
+        self.u_dev = u
+        self._gather(u)
+        return it
+
+    def newton_device(self, u, un, atol, rtol):
+        """Newton iteration on device-resident local vectors (no host copies of fields)."""
+        ctx, lib, ptr = self.ctx, self.ctx.lib, self.ctx.ptr
         it, snorm, f0, lin_total, reason = 0, 0.0, 1.0, 0, 0
         while True:
             self.halo(u)
@@ -336,8 +344,6 @@ class DistributedNewtonSolver:
             snorm = self._norm(self.y)
             it += 1
         self.solver.its, self.solver.reason, self.solver.linear_its, self.solver.fnorm = it, reason, lin_total, fn
-        self.u_dev = u
-        self._gather(u)
         return it
 
     def _is_symmetric(self):
@@ -346,16 +352,27 @@ class DistributedNewtonSolver:
             not t.derivs for t in spec.vterms + spec.fterms)
 
     def _gather(self, u):
-        """Owned values of every rank -> the global host vector on every rank."""
+        """Owned values of every rank -> the global host vector on every rank
+        (one padded NCCL all-gather, then a device->host copy)."""
         torch, dist, p = self.torch, self.dist, self.problem
-        mine = u[: self.part.n_owned * self.ns].cpu().numpy()
+        n_own = self.part.n_owned * self.ns
         if self.nranks == 1:
-            p.u.x.array[self.owned_gdofs] = mine
+            p.u.x.array[self.owned_gdofs] = u[:n_own].cpu().numpy()
             return
-        objs = [None] * self.nranks
-        dist.all_gather_object(objs, (self.owned_gdofs, mine))
-        for gd, vals in objs:
-            p.u.x.array[gd] = vals
+        if not hasattr(self, "_gather_index"):
+            counts = [None] * self.nranks
+            dist.all_gather_object(counts, self.owned_gdofs)
+            self._gather_counts = [len(c) for c in counts]
+            self._gather_index = counts
+            self._gather_pad = max(self._gather_counts)
+        pad = self._gather_pad
+        send = torch.zeros(pad, dtype=torch.float64, device=u.device)
+        send[:n_own] = u[:n_own]
+        recv = torch.empty(pad * self.nranks, dtype=torch.float64, device=u.device)
+        dist.all_gather_into_tensor(recv, send)
+        host = recv.cpu().numpy().reshape(self.nranks, pad)
+        for q in range(self.nranks):
+            p.u.x.array[self._gather_index[q]] = host[q, : self._gather_counts[q]]
 
 
 class _ProblemView:
