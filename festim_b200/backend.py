@@ -74,6 +74,7 @@ def load_library():
         "fb_total_surface": (i, [vp, vp, i, i, _f64p]),
         "fb_surface_flux": (i, [vp, vp, i, i, d, vp, _f64p]),
         "fb_set_owned": (i, [vp, i64]),
+        "fb_set_sm_partition": (i, [vp, i, _i32p, _i32p, _i32p, C.POINTER(C.c_uint16), i64]),
         "fb_bjacobi_setup": (i, [vp, vp]),
         "fb_precond": (i, [vp, vp, vp]),
         "fb_dcg_init": (i, [vp, vp, vp, vp, vp, vp, vp]),
@@ -94,7 +95,8 @@ EXPORTED_SYMBOLS = [
     "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
     "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
     "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
-    "fb_total_surface", "fb_surface_flux", "fb_set_owned", "fb_bjacobi_setup", "fb_precond",
+    "fb_total_surface", "fb_surface_flux", "fb_set_owned", "fb_set_sm_partition",
+    "fb_bjacobi_setup", "fb_precond",
     "fb_dcg_init", "fb_dcg_spmv_dots", "fb_dcg_update",
 ]
 
@@ -106,7 +108,7 @@ def _np_ptr(a, ctype):
 class Context:
     """Owns an ``fb_ctx`` and the torch device buffers handed to it."""
 
-    def __init__(self, spec: KernelSpec, device=0):
+    def __init__(self, spec: KernelSpec, device=0, renumber=True):
         import torch
 
         if not torch.cuda.is_available():
@@ -123,16 +125,42 @@ class Context:
             raise RuntimeError(f"fb_create failed with status {rc}")
         self._keep = {}
         mesh = spec.mesh
-        coords = np.ascontiguousarray(mesh.coords, dtype=np.float64)
-        cells = np.ascontiguousarray(mesh.cells, dtype=np.int32)
-        bf = np.ascontiguousarray(mesh.bfacets, dtype=np.int32)
-        bfc = np.ascontiguousarray(mesh.bfacet_cell, dtype=np.int32)
+        self.nv = mesh.num_vertices
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        # Vertex renumbering by recursive coordinate bisection into one compact part
+        # per SM: contiguous vertex ranges are then compact subdomains, which is what
+        # the persistent CG stages in shared memory (operator rows + a small halo of
+        # the iterate).  dolfinx reorders dofs too; the user-facing arrays keep the
+        # mesh numbering (perm is applied on every upload / download).
+        self.perm = self.inv = None
+        self.block_ranges = None
+        if renumber and mesh.tdim > 1 and mesh.num_vertices >= 4 * self.sm_count:
+            from festim_b200.distributed import partition_rcb
+
+            part = partition_rcb(mesh.coords, self.sm_count)
+            self.perm = np.argsort(part, kind="stable").astype(np.int64)   # new -> old
+            self.inv = np.empty_like(self.perm)
+            self.inv[self.perm] = np.arange(len(self.perm))
+            counts = np.bincount(part, minlength=self.sm_count)
+            self.block_ranges = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+            from festim_b200.mesh import SimplexMesh
+
+            dmesh = SimplexMesh(mesh.coords[self.perm], self.inv[mesh.cells])
+            dmesh._bfacets = self.inv[mesh.bfacets].astype(np.int32)
+            dmesh._bfacet_cell = mesh.bfacet_cell
+        else:
+            dmesh = mesh
+        self.dmesh = dmesh
+        coords = np.ascontiguousarray(dmesh.coords, dtype=np.float64)
+        cells = np.ascontiguousarray(dmesh.cells, dtype=np.int32)
+        bf = np.ascontiguousarray(dmesh.bfacets, dtype=np.int32)
+        bfc = np.ascontiguousarray(dmesh.bfacet_cell, dtype=np.int32)
         self._check(self.lib.fb_set_mesh(
             self.h, mesh.tdim, mesh.num_vertices, mesh.num_cells, _np_ptr(coords, C.c_double),
             _np_ptr(cells, C.c_int32), _np_ptr(spec.cell_tag, C.c_int32), bf.shape[0],
             _np_ptr(bf, C.c_int32), _np_ptr(bfc, C.c_int32), _np_ptr(spec.bfacet_tag, C.c_int32)))
-        rowptr, colidx = mesh.graph
-        v2c_ptr, v2c_idx = mesh.vertex_to_cell
+        rowptr, colidx = dmesh.graph
+        v2c_ptr, v2c_idx = dmesh.vertex_to_cell
         self._check(self.lib.fb_set_pattern(
             self.h, _np_ptr(rowptr, C.c_int32), _np_ptr(colidx, C.c_int32), len(colidx),
             _np_ptr(v2c_ptr, C.c_int32), _np_ptr(v2c_idx, C.c_int32)))
@@ -147,7 +175,60 @@ class Context:
             self.jit = True
         self.n_dofs = int(self.lib.fb_num_dofs(self.h))
         self.nnz = int(self.lib.fb_jacobian_nnz(self.h))
-        self.nv = mesh.num_vertices
+        if self.block_ranges is not None:
+            self._set_sm_partition(rowptr, colidx)
+
+    def _set_sm_partition(self, rowptr, colidx):
+        """Per-SM block: halo vertex list and 16-bit local column of every block entry."""
+        nb = self.sm_count
+        rng = self.block_ranges
+        halo_ptr = np.zeros(nb + 1, dtype=np.int32)
+        halos, lcols = [], []
+        for b in range(nb):
+            a, e = int(rng[b]), int(rng[b + 1])
+            cols = colidx[rowptr[a]:rowptr[e]].astype(np.int64)
+            inside = (cols >= a) & (cols < e)
+            halo = np.unique(cols[~inside])
+            if (e - a) + len(halo) > 65535:
+                return  # local index does not fit 16 bits: keep the streaming path
+            lc = np.where(inside, cols - a, 0)
+            lc[~inside] = (e - a) + np.searchsorted(halo, cols[~inside])
+            halos.append(halo.astype(np.int32))
+            lcols.append(lc.astype(np.uint16))
+            halo_ptr[b + 1] = halo_ptr[b] + len(halo)
+        halo_idx = np.ascontiguousarray(np.concatenate(halos)) if halos else np.zeros(0, np.int32)
+        lcol = np.ascontiguousarray(np.concatenate(lcols))
+        self._check(self.lib.fb_set_sm_partition(
+            self.h, nb, _np_ptr(rng, C.c_int32), _np_ptr(halo_ptr, C.c_int32),
+            _np_ptr(halo_idx, C.c_int32), _np_ptr(lcol, C.c_uint16), len(lcol)))
+
+    # -- numbering ----------------------------------------------------------------
+    def nodal_to_device(self, name, host_array, width=1):
+        """Upload a per-vertex array (``width`` values per vertex) in device numbering."""
+        arr = np.asarray(host_array, dtype=np.float64).reshape(self.nv, width)
+        if self.perm is not None:
+            arr = arr[self.perm]
+        return self.to_device(name, arr)
+
+    def nodal_from_device(self, tensor, width=1):
+        out = tensor.cpu().numpy().reshape(self.nv, width)
+        if self.perm is not None:
+            user = np.empty_like(out)
+            user[self.perm] = out
+            out = user
+        return out.ravel()
+
+    def dofs_to_device_numbering(self, dofs, ns):
+        dofs = np.asarray(dofs, dtype=np.int64)
+        if self.inv is None:
+            return dofs
+        return self.inv[dofs // ns] * ns + dofs % ns
+
+    def dofs_to_user_numbering(self, dofs, ns):
+        dofs = np.asarray(dofs, dtype=np.int64)
+        if self.perm is None:
+            return dofs
+        return self.perm[dofs // ns] * ns + dofs % ns
 
     def _check(self, rc):
         if rc < 0:
@@ -254,7 +335,7 @@ class B200NewtonSolver:
             np.zeros(0, dtype=np.int64)
         uniq, first_rev = np.unique(dofs[::-1], return_index=True)
         self._bc_pick = len(dofs) - 1 - first_rev
-        self._bc_dofs = np.ascontiguousarray(uniq, dtype=np.int64)
+        self._bc_dofs = np.ascontiguousarray(ctx.dofs_to_device_numbering(uniq, spec.ns), dtype=np.int64)
         ctx._check(ctx.lib.fb_set_dirichlet(ctx.h, len(self._bc_dofs),
                                             _np_ptr(self._bc_dofs, C.c_int64)))
         self.u_dev = ctx.zeros(ctx.n_dofs)
@@ -290,21 +371,22 @@ class B200NewtonSolver:
         self._signature = sig
         ctx._check(lib.fb_set_scalars(ctx.h, len(scal), _np_ptr(scal, C.c_double)))
         if isinstance(T, fem.Function):
-            Tdev = ctx.to_device("T", T.x.array)
+            Tdev = ctx.nodal_to_device("T", T.x.array)
             ctx._check(lib.fb_set_temperature(ctx.h, 0.0, ctx.ptr(Tdev)))
         elif T is not None:
             ctx._check(lib.fb_set_temperature(ctx.h, float(T.value), C.c_void_p()))
         for k, f in enumerate(spec.fields):
-            ctx._check(lib.fb_set_field(ctx.h, k, ctx.ptr(ctx.to_device(f"field{k}", f.x.array))))
+            ctx._check(lib.fb_set_field(ctx.h, k, ctx.ptr(ctx.nodal_to_device(f"field{k}", f.x.array))))
         for k, (_, _, vel) in enumerate(spec.adv):
-            ctx._check(lib.fb_set_velocity(ctx.h, k, ctx.ptr(ctx.to_device(f"vel{k}", vel.array))))
+            ctx._check(lib.fb_set_velocity(ctx.h, k, ctx.ptr(ctx.nodal_to_device(f"vel{k}", vel.array, spec.tdim))))
         ctx._check(lib.fb_update_load(ctx.h))
 
     def solve(self):
         ctx, p = self.ctx, self.problem
         self._push_state()
-        u_dev = ctx.to_device("u", p.u.x.array)
-        un_dev = ctx.to_device("u_n", p.u_n.x.array) if self.spec.transient else u_dev
+        ns = self.spec.ns
+        u_dev = ctx.nodal_to_device("u", p.u.x.array, ns)
+        un_dev = ctx.nodal_to_device("u_n", p.u_n.x.array, ns) if self.spec.transient else u_dev
         t = float(p.t) if hasattr(p, "t") else 0.0
         atol = self.atol(t) if callable(self.atol) else self.atol
         rtol = self.rtol(t) if callable(self.rtol) else self.rtol
@@ -316,7 +398,7 @@ class B200NewtonSolver:
             C.byref(n_its), C.byref(reason), C.byref(fnorm), C.byref(lin))
         ctx._check(rc)
         self.u_dev = u_dev
-        p.u.x.array[:] = u_dev.cpu().numpy()
+        p.u.x.array[:] = ctx.nodal_from_device(u_dev, ns)
         self.solver.its = n_its.value
         self.solver.reason = reason.value
         self.solver.linear_its = lin.value
@@ -331,7 +413,7 @@ class B200NewtonSolver:
         """(rows, cols) of every stored Jacobian scalar, in storage order (the
         layout documented in include/festim_b200.h)."""
         spec = self.spec
-        rowptr, colidx = spec.mesh.graph
+        rowptr, colidx = self.ctx.dmesh.graph
         ns, npairs = spec.ns, spec.npairs
         deg = np.diff(rowptr).astype(np.int64)
         rows, cols = [], []
@@ -354,7 +436,7 @@ class B200NewtonSolver:
         order = np.argsort(pos)
         R = np.concatenate([r[1] for r in rows])[order]
         Cc = np.concatenate([r[2] for r in rows])[order]
-        return R, Cc
+        return self.ctx.dofs_to_user_numbering(R, ns), self.ctx.dofs_to_user_numbering(Cc, ns)
 
     def assemble_host(self, want_J=True):
         """Assemble F (and J as scipy CSR) at the problem's current u, u_n."""
@@ -362,14 +444,15 @@ class B200NewtonSolver:
 
         ctx, p = self.ctx, self.problem
         self._push_state()
-        u_dev = ctx.to_device("u", p.u.x.array)
-        un_dev = ctx.to_device("u_n", p.u_n.x.array) if self.spec.transient else u_dev
+        ns = self.spec.ns
+        u_dev = ctx.nodal_to_device("u", p.u.x.array, ns)
+        un_dev = ctx.nodal_to_device("u_n", p.u_n.x.array, ns) if self.spec.transient else u_dev
         F = ctx.zeros(ctx.n_dofs)
         J = ctx.zeros(ctx.nnz) if want_J else None
         flags = FB_ASSEMBLE_F | (FB_ASSEMBLE_J if want_J else 0)
         ctx._check(ctx.lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(un_dev), ctx.ptr(F),
                                        ctx.ptr(J), flags))
-        Fh = F.cpu().numpy()
+        Fh = ctx.nodal_from_device(F, ns)
         if not want_J:
             return Fh, None
         R, Cc = self.jacobian_index()
@@ -382,7 +465,7 @@ class B200NewtonSolver:
         self._D_T_dev = None
 
     def _current_u(self):
-        return self.ctx.to_device("u", self.problem.u.x.array)
+        return self.ctx.nodal_to_device("u", self.problem.u.x.array, self.spec.ns)
 
     def total_volume(self, species_index, vol_id):
         out = C.c_double(0.0)
@@ -404,7 +487,7 @@ class B200NewtonSolver:
         Tn, Tc = C.c_void_p(), 0.0
         if isinstance(self._D_T, np.ndarray):
             if self._D_T_dev is None:
-                self._D_T_dev = ctx.to_device("D_T", self._D_T)
+                self._D_T_dev = ctx.nodal_to_device("D_T", self._D_T)
             Tn = ctx.ptr(self._D_T_dev)
         else:
             Tc = float(self._D_T)

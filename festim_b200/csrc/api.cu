@@ -81,6 +81,7 @@ extern "C" int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr, const int32_t*
   if ((rc = fb_upload(ctx, &S.v2c_ptr, v2c_ptr, (size_t)S.n_vertices + 1))) return rc;
   if ((rc = fb_upload(ctx, &S.v2c_idx, v2c_idx, (size_t)S.n_cells * (S.tdim + 1)))) return rc;
   ctx->nnzb = nnzb;
+  ctx->h_rowptr.assign(rowptr, rowptr + S.n_vertices + 1);
   // block-tridiagonal in index order?  (1D meshes ordered along x)
   bool tri = true;
   for (long long v = 0; v < S.n_vertices && tri; ++v)
@@ -295,5 +296,33 @@ extern "C" int fb_set_owned(fb_ctx* ctx, int64_t n_owned_vertices) {
   if (n_owned_vertices <= 0 || n_owned_vertices > ctx->S.n_vertices) return fb_fail(ctx, "bad owned count");
   ctx->S.n_owned = n_owned_vertices;
   ctx->S.n_owned_dofs = n_owned_vertices * (ctx->S.ns > 0 ? ctx->S.ns : 1);
+  return 0;
+}
+
+// Compact per-SM partition for the persistent CG (vertices are numbered so that block b
+// owns the contiguous range [rng[b], rng[b+1])): halo vertex list of every block and the
+// 16-bit local column (owned first, then halo) of every block entry of its rows.
+extern "C" int fb_set_sm_partition(fb_ctx* ctx, int nblocks, const int32_t* rng, const int32_t* halo_ptr,
+                                   const int32_t* halo_idx, const uint16_t* lcol, int64_t n_lcol) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  if (nblocks != ctx->sm_count) return fb_fail(ctx, "one block per SM expected");
+  if (n_lcol != ctx->nnzb) return fb_fail(ctx, "lcol must have one entry per block entry");
+  const DevSpec& S = ctx->S;
+  int rc;
+  if ((rc = fb_upload(ctx, &ctx->d_blk_rng, rng, (size_t)nblocks + 1))) return rc;
+  if ((rc = fb_upload(ctx, &ctx->d_halo_ptr, halo_ptr, (size_t)nblocks + 1))) return rc;
+  if ((rc = fb_upload(ctx, &ctx->d_halo_idx, halo_idx, (size_t)halo_ptr[nblocks]))) return rc;
+  if ((rc = fb_upload(ctx, &ctx->d_lcol, (const unsigned short*)lcol, (size_t)n_lcol))) return rc;
+  ctx->part_max_entries = ctx->part_max_bentries = ctx->part_max_su = ctx->part_max_rows = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    const long long nown = rng[b + 1] - rng[b], nhalo = halo_ptr[b + 1] - halo_ptr[b];
+    const long long be = ctx->h_rowptr[rng[b + 1]] - ctx->h_rowptr[rng[b]];
+    if (be * S.npairs > ctx->part_max_entries) ctx->part_max_entries = be * S.npairs;
+    if (be > ctx->part_max_bentries) ctx->part_max_bentries = be;
+    if ((nown + nhalo) * S.ns > ctx->part_max_su) ctx->part_max_su = (nown + nhalo) * S.ns;
+    if (nown * S.ns > ctx->part_max_rows) ctx->part_max_rows = nown * S.ns;
+  }
+  ctx->part_blocks = nblocks;
   return 0;
 }

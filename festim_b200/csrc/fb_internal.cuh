@@ -20,6 +20,14 @@ struct fb_ctx {
   bool have_mesh = false, have_pattern = false, have_spec = false;
   long long nnzb = 0, n_bc = 0;
   bool tridiag = false;
+  // per-SM compact partition (fb_set_sm_partition)
+  std::vector<int> h_rowptr;
+  int part_blocks = 0;
+  const int* d_blk_rng = nullptr;
+  const int* d_halo_ptr = nullptr;
+  const int* d_halo_idx = nullptr;
+  const unsigned short* d_lcol = nullptr;
+  long long part_max_entries = 0, part_max_bentries = 0, part_max_su = 0, part_max_rows = 0;
   bool symmetric = false;
   bool facet_u_terms = false;  // any solution-dependent facet term
   bool have_jit = false;

@@ -309,6 +309,9 @@ struct CgArgs {
   double* partials; unsigned* bar; double* sc; int* flags;
   double thr2; int max_it; int rows_in_smem;  // rows_in_smem: 1 = stage owned rows in smem
   unsigned bar_base;                            // value of the arrival counter at launch
+  // compact per-SM partition (nullptr: contiguous equal ranges, gathers from L2)
+  const int* blk_rng; const int* halo_ptr; const int* halo_idx; const unsigned short* lcol;
+  long long su_doubles, bentries, rows_cap;     // smem capacities: iterate cache, block entries, rows
   long long smem_entries;                       // capacity (values) of the staging area
 };
 
@@ -368,25 +371,44 @@ k_cg_persistent(DevSpec S, CgArgs A) {
   const unsigned nb = gridDim.x;
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   // vertex / row ownership: a contiguous range per block
+  const bool part = A.blk_rng != nullptr;
   const long long vper = (S.n_vertices + nb - 1) / nb;
-  const long long v0 = (long long)blockIdx.x * vper;
-  const long long v1 = (v0 + vper < S.n_vertices) ? v0 + vper : S.n_vertices;
+  const long long v0 = part ? A.blk_rng[blockIdx.x] : (long long)blockIdx.x * vper;
+  const long long v1 = part ? A.blk_rng[blockIdx.x + 1]
+                            : ((v0 + vper < S.n_vertices) ? v0 + vper : S.n_vertices);
   const int nvloc = v1 > v0 ? (int)(v1 - v0) : 0;
   const int nrows = nvloc * ns;
   const long long row0 = v0 * ns;
-  // ---- stage the owned rows in shared memory ---------------------------------
-  // layout: vals[cap] (double) | cols[cap] (int, scalar column) | rstart[rows] | rlen[rows]
+  // ---- shared-memory staging ------------------------------------------------------
+  // vals[cap] f64 | su[su_doubles] f64 | cols: int[cap] (range mode) or u16[bentries]
+  // (partition mode) | rstart[rows] | rlen[rows] | rbst[rows]
+  const long long rows_cap = part ? A.rows_cap : vper * ns;
   double* svals = (double*)smem_raw;
-  int* scols = (int*)(svals + A.smem_entries);
-  int* rstart = scols + A.smem_entries;
-  int* rlen = rstart + vper * ns;
+  double* su = svals + A.smem_entries;
+  int* scols = (int*)(su + A.su_doubles);
+  unsigned short* slcol = (unsigned short*)scols;
+  int* rstart = part ? (int*)(slcol + ((A.bentries + 1) & ~1LL)) : scols + A.smem_entries;
+  int* rlen = rstart + rows_cap;
+  int* rbst = rlen + rows_cap;
   bool staged = false;
+  int nhalo = 0;
+  const int* hidx = nullptr;
   if (A.rows_in_smem && nrows > 0) {
     const long long e0 = (long long)S.rowptr[v0] * S.npairs;
     const long long e1 = (long long)S.rowptr[v1] * S.npairs;
     staged = (e1 - e0) <= A.smem_entries;
+    if (part) {
+      nhalo = A.halo_ptr[blockIdx.x + 1] - A.halo_ptr[blockIdx.x];
+      hidx = A.halo_idx + A.halo_ptr[blockIdx.x];
+      staged = staged && (long long)(nvloc + nhalo) * ns <= A.su_doubles &&
+               (long long)(S.rowptr[v1] - S.rowptr[v0]) <= A.bentries;
+    }
     if (staged) {
       for (long long e = tid; e < e1 - e0; e += T) svals[e] = A.J[e0 + e];
+      if (part) {
+        const long long b0 = S.rowptr[v0], nbe = S.rowptr[v1] - b0;
+        for (long long e = tid; e < nbe; e += T) slcol[e] = A.lcol[b0 + e];
+      }
       for (int rr = tid; rr < nrows; rr += T) {
         const int vl = rr / ns, sp = rr - vl * ns;
         const long long v = v0 + vl;
@@ -395,14 +417,17 @@ k_cg_persistent(DevSpec S, CgArgs A) {
         const int start = (int)((long long)r0 * S.npairs + (long long)deg * pp - e0);
         rstart[rr] = start;
         rlen[rr] = deg * nc;
-        for (int e = 0; e < deg * nc; ++e) {
-          const int k = e / nc, j = e - k * nc;
-          scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
-        }
+        rbst[rr] = r0 - S.rowptr[v0];
+        if (!part)
+          for (int e = 0; e < deg * nc; ++e) {
+            const int k = e / nc, j = e - k * nc;
+            scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
+          }
       }
     }
   }
-  // ---- init --------------------------------------------------------------------
+  const bool cached = staged && part;  // iterate gathered from shared memory
+  // ---- init ------------------------------------------------------------------------
   for (long long v = v0 + tid; v < v1; v += T) {
     double rin[FB_MAX_NS], zo[FB_MAX_NS];
     for (int sp = 0; sp < ns; ++sp) {
@@ -411,7 +436,10 @@ k_cg_persistent(DevSpec S, CgArgs A) {
       A.r[i] = rin[sp]; A.x[i] = 0.0; A.p[i] = 0.0; A.s[i] = 0.0;
     }
     bjacobi_apply(ns, A.dinv, v, rin, zo);
-    for (int sp = 0; sp < ns; ++sp) A.u[v * ns + sp] = zo[sp];
+    for (int sp = 0; sp < ns; ++sp) {
+      A.u[v * ns + sp] = zo[sp];
+      if (cached) su[(v - v0) * ns + sp] = zo[sp];
+    }
   }
   unsigned gen = 0;
   const unsigned base_count = A.bar_base;
@@ -424,13 +452,36 @@ k_cg_persistent(DevSpec S, CgArgs A) {
   long long tph[5] = {0, 0, 0, 0, 0};  // cycles per phase (block 0), reported in sc[8..12]
   while (true) {
     long long c0 = clock64();
-    // ---- phase B: w = A u on owned rows + partial dots -------------------------
+    // ---- halo of the iterate into shared memory ---------------------------------------
+    if (cached) {
+      for (int h = tid; h < nhalo * ns; h += T) {
+        const int hv = h / ns, sp = h - hv * ns;
+        su[nrows + h] = __ldcg(uvec + (long long)hidx[hv] * ns + sp);
+      }
+      __syncthreads();
+    }
+    // ---- phase B: w = A u on owned rows + partial dots -----------------------------------
     double v3[3] = {0.0, 0.0, 0.0};
     for (int rr = grp; rr < nrows; rr += ngroups) {
       double sum = 0.0;
       const long long row = row0 + rr;
-      const double ri = __ldcg(A.r + row), ui = __ldcg(uvec + row);  // issued before the gathers
-      if (staged) {
+      double ri, ui;
+      if (cached) {
+        ri = __ldcg(A.r + row);
+        ui = su[rr];
+        const int a0 = rstart[rr], n = rlen[rr], bs = rbst[rr];
+        if (ns == 1) {
+          for (int e = gl; e < n; e += G) sum += svals[a0 + e] * su[slcol[bs + e]];
+        } else {
+          const int vl = rr / ns, sp = rr - vl * ns;
+          const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
+          for (int e = gl; e < n; e += G) {
+            const int k = e / nc, j = e - k * nc;
+            sum += svals[a0 + e] * su[(int)slcol[bs + k] * ns + S.pair_cs[pp + j]];
+          }
+        }
+      } else if (staged) {
+        ri = __ldcg(A.r + row); ui = __ldcg(uvec + row);  // issued before the gathers
         const int a0 = rstart[rr], n = rlen[rr];
         // all gathers of a batch are in flight before the first use (L2 latency once per batch)
         for (int eb = gl; eb < n; eb += 8 * G) {
@@ -447,6 +498,7 @@ k_cg_persistent(DevSpec S, CgArgs A) {
           }
         }
       } else {
+        ri = __ldcg(A.r + row); ui = __ldcg(uvec + row);
         const int vl = rr / ns, sp = rr - vl * ns;
         const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
@@ -485,7 +537,7 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     long long c1 = clock64();
     if (!grid_barrier(A.bar, nb, gen, base_count)) return;
     long long c2 = clock64();
-    // ---- every block: identical reduction of the partials ------------------------
+    // ---- every block: identical reduction of the partials --------------------------------
     if (wid < 3) {
       double sacc = 0.0;
       for (unsigned bq = lane; bq < nb; bq += 32) sacc += __ldcg(A.partials + (size_t)wid * nb + bq);
@@ -511,12 +563,13 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     }
     ++it;
     long long c3 = clock64();
-    // ---- phase A: vector update on owned vertices --------------------------------
+    // ---- phase A: vector update on owned vertices ------------------------------------------
     for (long long v = v0 + tid; v < v1; v += T) {
       double rin[FB_MAX_NS], zo[FB_MAX_NS];
       for (int sp = 0; sp < ns; ++sp) {
         const long long i = v * ns + sp;
-        const double ui = __ldcg(A.u + i), wi = __ldcg(A.w + i), ri = __ldcg(A.r + i);
+        const double ui = cached ? su[(v - v0) * ns + sp] : __ldcg(A.u + i);
+        const double wi = __ldcg(A.w + i), ri = __ldcg(A.r + i);
         const double p_old = __ldcg(A.p + i), s_old = __ldcg(A.s + i), x_old = __ldcg(A.x + i);
         const double pi = ui + beta * p_old;
         const double si = wi + beta * s_old;
@@ -526,7 +579,10 @@ k_cg_persistent(DevSpec S, CgArgs A) {
         A.r[i] = rin[sp];
       }
       bjacobi_apply(ns, A.dinv, v, rin, zo);
-      for (int sp = 0; sp < ns; ++sp) A.u[v * ns + sp] = zo[sp];
+      for (int sp = 0; sp < ns; ++sp) {
+        A.u[v * ns + sp] = zo[sp];
+        if (cached) su[(v - v0) * ns + sp] = zo[sp];
+      }
     }
     long long c4 = clock64();
     if (!grid_barrier(A.bar, nb, gen, base_count)) return;  // also protects tot[]
@@ -844,21 +900,42 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
   if (getenv("FB_CG_G")) G = atoi(getenv("FB_CG_G"));
   const int T = 1024;
   const unsigned nb = (unsigned)ctx->sm_count;
-  // staging capacity: 12 bytes per stored value + 8 bytes per owned row
-  const long long vper = (S.n_vertices + nb - 1) / nb;
-  const long long rows_per_block = vper * S.ns;
   size_t smem_max = 0;
   {
     int v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     smem_max = (size_t)v - 1024;  // static shared (reduction scratch)
   }
-  long long cap = ((long long)smem_max - 8 * (rows_per_block + 2)) / 12;
-  cap &= ~1LL;
-  const long long avg_entries = ctx->nnzb * S.npairs / nb + 1;
-  A.rows_in_smem = (cap >= avg_entries) && !getenv("FB_NO_SMEM_OPERATOR");
-  A.smem_entries = A.rows_in_smem ? cap : 0;
-  const size_t smem = A.rows_in_smem ? (size_t)(12 * cap + 8 * (rows_per_block + 2)) : 0;
+  A.blk_rng = nullptr; A.halo_ptr = nullptr; A.halo_idx = nullptr; A.lcol = nullptr;
+  A.su_doubles = 0; A.bentries = 0; A.rows_cap = 0;
+  size_t smem = 0;
+  const bool no_smem = getenv("FB_NO_SMEM_OPERATOR") != nullptr;
+  if (ctx->part_blocks == (int)nb && !getenv("FB_NO_SM_PARTITION")) {
+    // compact per-SM partition: operator rows + iterate cache (owned + halo) on chip
+    A.blk_rng = ctx->d_blk_rng; A.halo_ptr = ctx->d_halo_ptr; A.halo_idx = ctx->d_halo_idx;
+    A.lcol = ctx->d_lcol;
+    const long long cap = (ctx->part_max_entries + 1) & ~1LL;
+    const long long su = (ctx->part_max_su + 1) & ~1LL;
+    const long long be = (ctx->part_max_bentries + 1) & ~1LL;
+    const long long rows = ctx->part_max_rows;
+    const size_t need = (size_t)(8 * cap + 8 * su + 2 * be + 12 * rows + 16);
+    if (need <= smem_max && !no_smem) {
+      A.rows_in_smem = 1; A.smem_entries = cap; A.su_doubles = su; A.bentries = be; A.rows_cap = rows;
+      smem = need;
+    } else {
+      A.rows_in_smem = 0; A.smem_entries = 0;
+    }
+  } else {
+    // staging capacity: 12 bytes per stored value + 12 bytes per owned row
+    const long long vper = (S.n_vertices + nb - 1) / nb;
+    const long long rows_per_block = vper * S.ns;
+    long long cap = ((long long)smem_max - 12 * (rows_per_block + 2)) / 12;
+    cap &= ~1LL;
+    const long long avg_entries = ctx->nnzb * S.npairs / nb + 1;
+    A.rows_in_smem = (cap >= avg_entries) && !no_smem;
+    A.smem_entries = A.rows_in_smem ? cap : 0;
+    smem = A.rows_in_smem ? (size_t)(12 * cap + 12 * (rows_per_block + 2)) : 0;
+  }
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
   FB_CHECK(ctx, cudaMemsetAsync(A.bar, 0, 130 * sizeof(unsigned), ctx->stream));
   A.bar_base = 0u;

@@ -187,7 +187,7 @@ class DistributedNewtonSolver:
         ft = MeshTags(lp.mesh, gmesh.tdim - 1, np.arange(len(lp.local_bfacets)), ftag[lp.local_bfacets])
         view = _ProblemView(problem, lp.mesh, vt, ft)
         self.spec = KernelSpec(view)
-        self.ctx = ctx = Context(self.spec, device)
+        self.ctx = ctx = Context(self.spec, device, renumber=False)  # owned-first numbering is fixed
         ctx._check(ctx.lib.fb_set_owned(ctx.h, lp.n_owned))
         self.halo = HaloExchange(lp, ns, torch, ctx.device)
         self.atol = petsc_options["snes_atol"]

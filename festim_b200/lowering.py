@@ -71,22 +71,15 @@ class KernelSpec:
         self.surf_ids = [s.id for s in problem.surface_subdomains]
         nvt, nst = len(self.vol_ids), len(self.surf_ids)
 
-        # compact tags
+        # compact tags (vectorised: configs reach 10^7 cells)
         vt = problem.volume_meshtags
         ctag = np.zeros(mesh.num_cells, dtype=np.int64)
         ctag[vt.indices] = vt.values
-        lut = {vid: i for i, vid in enumerate(self.vol_ids)}
-        self.cell_tag = np.array([lut[t] for t in ctag], dtype=np.int32) if nvt > 1 else \
-            np.zeros(mesh.num_cells, dtype=np.int32)
-        if nvt > 1:
-            pass
-        elif not np.all(ctag == self.vol_ids[0]):
-            raise ValueError("cells tagged with an id that is not a volume subdomain")
+        self.cell_tag = self._compact(ctag, self.vol_ids, required=True)
         ft = problem.facet_meshtags
         ftag = np.zeros(mesh.bfacets.shape[0], dtype=np.int64)
         ftag[ft.indices] = ft.values
-        slut = {sid: i for i, sid in enumerate(self.surf_ids)}
-        self.bfacet_tag = np.array([slut.get(t, -1) for t in ftag], dtype=np.int32)
+        self.bfacet_tag = self._compact(ftag, self.surf_ids, required=False)
 
         T = getattr(problem, "temperature_fenics", None)
         self.temperature = T
@@ -201,6 +194,16 @@ class KernelSpec:
                 self.tdim - 1, dF if dJ is None else dJ)
 
     # ------------------------------------------------------------------
+    @staticmethod
+    def _compact(tags, ids, required):
+        """Map subdomain ids to their position in ``ids`` (-1: not a subdomain)."""
+        out = np.full(len(tags), -1, dtype=np.int32)
+        for i, sid in enumerate(ids):
+            out[tags == sid] = i
+        if required and len(tags) and out.min() < 0:
+            raise ValueError("cells tagged with an id that is not a volume subdomain")
+        return out
+
     def _energy_index(self, E):
         for i, e in enumerate(self.diff_energies):
             if e == E:

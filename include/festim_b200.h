@@ -156,6 +156,12 @@ int fb_surface_flux(fb_ctx* ctx, const double* u /*[dev]*/, int species, int sta
  *    fb_assemble / fb_spmv / fb_dcg_spmv_dots; kernels write owned rows only and reductions
  *    cover owned entries only. ---------------------------------------------------------- */
 int fb_set_owned(fb_ctx* ctx, int64_t n_owned_vertices);
+/* single GPU: compact per-SM vertex blocks (contiguous ranges after renumbering) with their
+ * halo lists and 16-bit local columns, so the persistent CG keeps operator rows and the
+ * gathered part of the iterate in shared memory */
+int fb_set_sm_partition(fb_ctx* ctx, int nblocks, const int32_t* block_ranges /*[host] nblocks+1*/,
+                        const int32_t* halo_ptr /*[host] nblocks+1*/, const int32_t* halo_idx /*[host]*/,
+                        const uint16_t* local_col /*[host] nnzb*/, int64_t n_local_col);
 int fb_bjacobi_setup(fb_ctx* ctx, const double* Jvals /*[dev]*/);
 int fb_precond(fb_ctx* ctx, const double* r /*[dev]*/, double* z /*[dev]*/); /* z = M^-1 r */
 /* single-reduction CG split at its two communication points */

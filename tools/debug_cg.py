@@ -16,13 +16,16 @@ m.initialise()
 s = m.solver; ctx = s.ctx; lib = ctx.lib
 log("initialised", ctx.n_dofs)
 s._push_state()
+print("renumbered:", ctx.perm is not None, file=sys.stderr)
 u = ctx.zeros(ctx.n_dofs); F = ctx.zeros(ctx.n_dofs); J = ctx.zeros(ctx.nnz); y = ctx.zeros(ctx.n_dofs)
 ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u), ctx.ptr(u), ctx.ptr(F), ctx.ptr(J), 3))
 torch.cuda.synchronize(); log("assembled")
 for mode in sys.argv[4].split(","):
     os.environ.pop("FB_CG_MULTIKERNEL", None); os.environ.pop("FB_NO_SMEM_OPERATOR", None)
     if mode == "multi": os.environ["FB_CG_MULTIKERNEL"] = "1"
+    os.environ.pop("FB_NO_SM_PARTITION", None)
     if mode == "persistent-nosmem": os.environ["FB_NO_SMEM_OPERATOR"] = "1"
+    if mode == "persistent-range": os.environ["FB_NO_SM_PARTITION"] = "1"
     its = C.c_int(0); rr = C.c_double(0)
     log("solve", mode)
     t1 = time.time()
