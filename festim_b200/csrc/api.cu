@@ -10,13 +10,41 @@ enum {
   S_INTS = 1, S_DIFF_D0, S_DIFF_SLOT, S_DIFF_ENERGIES, S_MASS_DT, S_MASS_C, S_PAIR_NC, S_PAIR_PP,
   S_PAIR_CS, S_PAIR_IDX, S_PROG_OPS, S_PROG_IARGS, S_PROG_FARGS, S_PROG_OFFSETS, S_VTERM_HDR,
   S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
-  S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_MAX
+  S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_RSLOT_E, S_FAC_HDR, S_FAC_A0,
+  S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
+  S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_MAX
 };
 enum {
   I_TDIM = 0, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
   I_NVTERMS, I_NFTERMS, I_NADV, I_NPAIRS, I_NDIFFE, I_DT_SCALAR, I_NSLOTS
 };
 static const long long FB_MAGIC = 0xFB2000001LL;
+
+// element -> row-slot map of the gather kernels: for every (vertex v, incident cell) entry of
+// the vertex->cell adjacency, the position of each cell vertex in v's sorted column list
+__global__ void k_fill_slots(int d1, long long n_vertices, const int* __restrict__ cells,
+                             const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                             const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                             unsigned* __restrict__ out) {
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= n_vertices) return;
+  const int r0 = rowptr[v], r1 = rowptr[v + 1];
+  for (int e = v2c_ptr[v]; e < v2c_ptr[v + 1]; ++e) {
+    const long long c = v2c_idx[e] / d1;
+    unsigned packed = 0;
+    for (int j = 0; j < d1; ++j) {
+      const int col = cells[c * d1 + j];
+      int lo = r0, hi = r1 - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (colidx[mid] < col) lo = mid + 1; else hi = mid;
+      }
+      packed |= (unsigned)((lo - r0) & 0xff) << (8 * j);
+    }
+    out[e] = packed;
+  }
+}
+
 
 extern "C" int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   if (!out) return -1;
@@ -88,6 +116,18 @@ extern "C" int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr, const int32_t*
     for (int k = rowptr[v]; k < rowptr[v + 1]; ++k)
       if (std::llabs((long long)colidx[k] - v) > 1) { tri = false; break; }
   ctx->tridiag = tri;
+  int maxdeg = 0;
+  for (long long v = 0; v < S.n_vertices; ++v)
+    if (rowptr[v + 1] - rowptr[v] > maxdeg) maxdeg = rowptr[v + 1] - rowptr[v];
+  S.v2c_slot = nullptr;
+  if (maxdeg <= 256) {
+    unsigned* slots = nullptr;
+    if ((rc = fb_alloc(ctx, &slots, (size_t)S.n_cells * (S.tdim + 1)))) return rc;
+    FB_LAUNCH(ctx, k_fill_slots, (unsigned)((S.n_vertices + 127) / 128), 128, 0, S.tdim + 1, S.n_vertices,
+              S.cells, S.rowptr, S.colidx, S.v2c_ptr, S.v2c_idx, slots);
+    FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    S.v2c_slot = slots;
+  }
   ctx->have_pattern = true;
   return 0;
 }
@@ -150,6 +190,7 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     for (int t = 0; t < nterms; ++t) {
       if (h[t * 8 + 5] > 0) ctx->symmetric = false;
       if (pass == 1 && h[t * 8 + 6]) ctx->facet_u_terms = true;
+      if (pass == 0 && h[t * 8 + 6]) ctx->generic_u_vterms = true;
     }
   }
   S.n_dofs = S.n_vertices * S.ns;
@@ -168,6 +209,27 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   UP(S_DERIV_SPECIES, 0, deriv_species); UP(S_DERIV_PROG, 0, deriv_prog);
   UP(S_QUAD_V, 0, quad_v); UP(S_QUAD_S, 0, quad_s); UP(S_QUAD_BARY, 1, quad_bary); UP(S_QUAD_W, 1, quad_w);
   UP(S_ADV, 0, adv); UP(S_DIFF_UPROG, 0, diff_uprog);
+  S.n_rslots = S.n_factors = S.n_monos = S.nsym = S.nq_max = 0;
+  if (secs[S_STRUCT_INTS].id == S_STRUCT_INTS) {
+    const int* si = (const int*)(blob + secs[S_STRUCT_INTS].offset);
+    S.n_rslots = si[0]; S.n_factors = si[1]; S.n_monos = si[2]; S.nsym = si[3];
+    UP(S_RSLOT_E, 1, rslot_E); UP(S_FAC_HDR, 0, fac_hdr); UP(S_FAC_A0, 1, fac_a0);
+    UP(S_FAC_SPECIES, 0, fac_species); UP(S_FAC_COEF, 1, fac_coef); UP(S_MONO, 0, mono);
+    UP(S_MONO_COEF, 1, mono_coef); UP(S_FC_PTR, 0, fc_ptr); UP(S_FC_MONO, 0, fc_mono);
+    UP(S_FC_SIGN, 1, fc_sign); UP(S_JC_PTR, 0, jc_ptr); UP(S_JC, 0, jc); UP(S_JC_COEF, 1, jc_coef);
+    UP(S_WTAB, 1, wtab); UP(S_WTAB_OFF, 0, wtab_off);
+    const int* wo = (const int*)(blob + secs[S_WTAB_OFF].offset);
+    for (int t = 0; t < S.n_vtags; ++t) {
+      if (wo[4 * t + 1] > S.nq_max) S.nq_max = wo[4 * t + 1];
+      if (wo[4 * t + 3] > S.nq_max) S.nq_max = wo[4 * t + 3];
+    }
+    ctx->symmetric = false;
+  }
+  S.maxdeg = 0;
+  for (long long v = 0; v < S.n_vertices; ++v) {
+    const int dg = ctx->h_rowptr[v + 1] - ctx->h_rowptr[v];
+    if (dg > S.maxdeg) S.maxdeg = dg;
+  }
   S.n_udiff = 0;
   if (secs[S_DIFF_UPROG].id == S_DIFF_UPROG) {
     const int* up = (const int*)(blob + secs[S_DIFF_UPROG].offset);

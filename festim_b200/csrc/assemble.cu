@@ -25,9 +25,12 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <cstdlib>
+
 #include "fb_internal.cuh"
 #include "program.cuh"
 #include "assemble_kernels.cuh"
+#include "assemble_rows.cuh"
 
 // ---------------------------------------------------------------------------
 // kernels: thin wrappers around the bodies of assemble_kernels.cuh
@@ -49,6 +52,14 @@ __global__ void __launch_bounds__(128)
 k_assemble_nodes(DevSpec S, const double* __restrict__ u, const double* __restrict__ un,
                  double* __restrict__ F, double* __restrict__ J, int flags) {
   fb_assemble_nodes_body<DIM>(S, u, un, F, J, flags);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_assemble_rows(DevSpec S, const double* __restrict__ u, const double* __restrict__ un,
+                double* __restrict__ F, double* __restrict__ J, int flags, int per_warp) {
+  extern __shared__ double fb_rows_smem[];
+  fb_assemble_rows_body<DIM>(S, u, un, F, J, flags, fb_rows_smem, per_warp);
 }
 
 // ---------------------------------------------------------------------------
@@ -183,7 +194,22 @@ static int assemble_dim(fb_ctx* ctx, const double* u, const double* un, double* 
   DevSpec& S = ctx->S;
   const unsigned B = 128;
   const unsigned gn = (unsigned)((S.n_vertices + B - 1) / B);
-  if (ctx->have_jit) {
+  const bool structured = S.n_monos > 0 && !ctx->generic_u_vterms && S.n_udiff == 0 &&
+                          !getenv("FB_NO_ROWS_KERNEL");
+  if (structured) {
+    // warp per vertex, block row accumulated in shared memory (assemble_rows.cuh)
+    constexpr int D1 = DIM + 1, NSYM = D1 * (D1 + 1) / 2;
+    const int per_warp = ((S.maxdeg * S.npairs + 2 * D1 * S.ns + S.n_factors * D1 + S.n_rslots * S.nq_max +
+                           2 * S.n_rslots * NSYM + S.ns + 1) & ~1);
+    int wpb = 8;
+    while (wpb > 1 && (size_t)wpb * per_warp * 8 > 200 * 1024) wpb >>= 1;
+    const size_t smem = (size_t)wpb * per_warp * 8;
+    if (smem > 220 * 1024) return fb_fail(ctx, "block row does not fit in shared memory");
+    FB_CHECK(ctx, cudaFuncSetAttribute(k_assemble_rows<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned gr = (unsigned)((S.n_owned + wpb - 1) / wpb);
+    k_assemble_rows<DIM><<<gr, wpb * 32, smem, ctx->stream>>>(S, u, un, F, J, flags, per_warp);
+    ctx->launches++;
+  } else if (ctx->have_jit) {
     void* args[] = {(void*)&S, (void*)&u, (void*)&un, (void*)&F, (void*)&J, (void*)&flags};
     int rc = jit_launch(ctx, JIT_ASSEMBLE_NODES, gn, B, args);
     if (rc) return rc;

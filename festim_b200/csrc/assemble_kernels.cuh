@@ -352,8 +352,14 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
     const double vol = fb_geometry<DIM>(X, G);
     const int tag = S.cell_tag[c];
     int slot[FB_MAX_D1];
+    if (S.v2c_slot != nullptr) {
+      const unsigned ps = S.v2c_slot[e];
 #pragma unroll
-    for (int j = 0; j < D1; ++j) slot[j] = fb_find_slot(S, (int)v, a[j]);
+      for (int j = 0; j < D1; ++j) slot[j] = (ps >> (8 * j)) & 0xffu;
+    } else {
+#pragma unroll
+      for (int j = 0; j < D1; ++j) slot[j] = fb_find_slot(S, (int)v, a[j]);
+    }
 
     // ---- diffusion + mass + advection (species-diagonal, closed form) ----
     for (int s = 0; s < ns; ++s) {

@@ -30,6 +30,7 @@ struct DevSpec {
   const int* colidx;
   const int* v2c_ptr;
   const int* v2c_idx;
+  const unsigned* v2c_slot;   // per (vertex, incident cell): row slot of each cell vertex, 8 bits each
   // tables (spec)
   const double* diff_D0;      // [n_vtags*ns]
   const int* diff_slot;       // [n_vtags*ns] index into cell-coefficient slots, -1 none
@@ -58,6 +59,23 @@ struct DevSpec {
   const double* quad_bary;
   const double* quad_w;
   const int* adv;             // [n_adv*2] tag, species
+  // structured reactions (moment-based assembly, assemble_rows.cuh)
+  int n_rslots, n_factors, n_monos, nsym, nq_max, maxdeg;
+  const double* rslot_E;      // [n_rslots] activation energies of the rate slots
+  const int* fac_hdr;         // [n_factors*4] a0 kind (0 const, 1 scalar), scalar id, coef offset, count
+  const double* fac_a0;
+  const int* fac_species;
+  const double* fac_coef;
+  const int* mono;            // [n_monos*6] tag, slot, nfac, f1, f2, -
+  const double* mono_coef;
+  const int* fc_ptr;          // [n_vtags*ns+1] residual contributions per (tag, row species)
+  const int* fc_mono;
+  const double* fc_sign;
+  const int* jc_ptr;          // [n_vtags*npairs+1] Jacobian contributions per (tag, pair)
+  const int* jc;              // [n*2] slot, other factor (-1 none)
+  const double* jc_coef;
+  const double* wtab;         // per tag and rule: W[i][q][sym] then its q-sum W0[i][sym]
+  const int* wtab_off;        // [n_vtags*4] offF, nqF, offJ, nqJ
   // per-step data
   const double* scalars;
   double T_const;

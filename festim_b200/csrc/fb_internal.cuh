@@ -30,6 +30,7 @@ struct fb_ctx {
   long long part_max_entries = 0, part_max_bentries = 0, part_max_su = 0, part_max_rows = 0;
   bool symmetric = false;
   bool facet_u_terms = false;  // any solution-dependent facet term
+  bool generic_u_vterms = false;  // any solution-dependent volume term evaluated point-wise
   bool have_jit = false;
   void* jit_module = nullptr;
   void* jit_fn[4] = {nullptr, nullptr, nullptr, nullptr};

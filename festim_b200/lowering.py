@@ -36,7 +36,9 @@ MAGIC = 0xFB200_0001
 (S_INTS, S_DIFF_D0, S_DIFF_SLOT, S_DIFF_ENERGIES, S_MASS_DT, S_MASS_C, S_PAIR_NC, S_PAIR_PP,
  S_PAIR_CS, S_PAIR_IDX, S_PROG_OPS, S_PROG_IARGS, S_PROG_FARGS, S_PROG_OFFSETS, S_VTERM_HDR,
  S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
- S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG) = range(1, 28)
+ S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_RSLOT_E, S_FAC_HDR, S_FAC_A0,
+ S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
+ S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS) = range(1, 44)
 
 # S_INTS slots
 (I_TDIM, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -102,6 +104,7 @@ class KernelSpec:
         self.mass_c = np.zeros((nvt, ns))
         self.vterms = []
         self.fterms = []
+        self.struct_reactions = {}   # (id(reaction), tag) -> (reaction, tag, [(row species, sign)])
         self.adv = []          # (vtag index, species index, VectorFunction)
         pairs = {(s, s) for s in range(ns)}
 
@@ -140,7 +143,12 @@ class KernelSpec:
             else:
                 terms = self.vterms if kind == "dx" else self.fterms
                 reaction = itg.meta.get("reaction")
-                if reaction is not None:
+                if reaction is not None and kind == "dx" and self.structured_ok(reaction):
+                    self.struct_reactions.setdefault((id(reaction), tag), (reaction, tag, []))[2].append(
+                        (s, float(itg.meta["sign"])))
+                    for dep in self._reaction_species(reaction, sidx):
+                        pairs.add((s, dep))
+                elif reaction is not None:
                     key = (id(reaction), kind, tag)
                     if key not in reaction_terms:
                         # value program: the positive reaction term, evaluated once
@@ -179,6 +187,9 @@ class KernelSpec:
             cs.extend(cols)
         self.pair_cs = np.array(cs, dtype=np.int32)
         self.npairs = int(self.pair_pp[-1])
+        self.struct = None
+        if self.struct_reactions:
+            self._build_structured(sidx)
 
         # quadrature pools
         self._qb, self._qw = [], []
@@ -194,6 +205,155 @@ class KernelSpec:
                 self.tdim - 1, dF if dJ is None else dJ)
 
     # ------------------------------------------------------------------
+    # structured reactions: k0 exp(-Ek/kT) f1 [f2] - p(T) g1 [g2] with every factor an
+    # affine function of the species (a Species, or an ImplicitSpecies n - sum(others)
+    # with n a constant); assembled from rate-weighted basis moments
+    # (csrc/assemble_rows.cuh) instead of point-wise program evaluation
+    @staticmethod
+    def structured_ok(reaction):
+        import os
+
+        from festim_b200.species import ImplicitSpecies, Species
+
+        if os.environ.get("FB_NO_STRUCTURED"):
+            return False
+        if len(reaction.reactant) > 2 or len(reaction.products) > 2:
+            return False
+        for r in reaction.reactant:
+            if isinstance(r, ImplicitSpecies):
+                if not isinstance(r.value_fenics, fem.Constant):
+                    return False
+            elif not isinstance(r, Species):
+                return False
+        return all(isinstance(x, (int, float)) for x in (reaction.k_0, reaction.E_k)) and \
+            all(x is None or isinstance(x, (int, float)) for x in (reaction.p_0, reaction.E_p))
+
+    @staticmethod
+    def _reaction_species(reaction, sidx):
+        from festim_b200.species import ImplicitSpecies
+
+        out = []
+        for r in list(reaction.reactant) + list(reaction.products):
+            members = r.others if isinstance(r, ImplicitSpecies) else [r]
+            for m in members:
+                if sidx[m] not in out:
+                    out.append(sidx[m])
+        return out
+
+    def _build_structured(self, sidx):
+        """Tables for the moment-based reaction assembly."""
+        from festim_b200.species import ImplicitSpecies
+
+        ns, nvt = self.ns, len(self.vol_ids)
+        self.rslot_E = []
+        factors = {}      # key -> id
+        fac_rows = []     # (a0_kind, a0_scalar, a0_const, [(species, coef)])
+        monos = []        # (tag, slot, [factor ids], coef, [(row, sign)])
+
+        def slot_of(E):
+            E = float(E or 0.0)
+            if E not in self.rslot_E:
+                self.rslot_E.append(E)
+            return self.rslot_E.index(E)
+
+        def factor_of(obj):
+            if isinstance(obj, ImplicitSpecies):
+                key = ("imp", id(obj.value_fenics), tuple(sidx[o] for o in obj.others))
+                if key not in factors:
+                    factors[key] = len(fac_rows)
+                    fac_rows.append((1, self.programs._scalar_id(obj.value_fenics), 0.0,
+                                     [(sidx[o], -1.0) for o in obj.others]))
+            else:
+                key = ("spe", sidx[obj])
+                if key not in factors:
+                    factors[key] = len(fac_rows)
+                    fac_rows.append((0, -1, 0.0, [(sidx[obj], 1.0)]))
+            return factors[key]
+
+        for reaction, tag, rows in self.struct_reactions.values():
+            reaction.check_rates()
+            monos.append((tag, slot_of(reaction.E_k), [factor_of(r) for r in reaction.reactant],
+                          float(reaction.k_0), rows))
+            mode = reaction.rate_mode()
+            if mode and reaction.products:
+                monos.append((tag, slot_of(reaction.E_p if mode == 2 else 0.0),
+                              [factor_of(pr) for pr in reaction.products], -float(reaction.p_0), rows))
+        # contribution lists
+        fc = [[] for _ in range(nvt * ns)]                 # (mono, sign)
+        jc = [[] for _ in range(nvt * self.npairs)]        # (slot, other factor, coef)
+        for im, (tag, slot, facs, coef, rows) in enumerate(monos):
+            for row, sign in rows:
+                fc[tag * ns + row].append((im, sign))
+                for pos, f in enumerate(facs):
+                    other = facs[1 - pos] if len(facs) == 2 else -1
+                    for spe, a in fac_rows[f][3]:
+                        p = int(self.pair_pp[row]) + int(self.pair_idx[row, spe])
+                        jc[tag * self.npairs + p].append((slot, other, sign * coef * a))
+        self.struct = dict(monos=monos, fac_rows=fac_rows, fc=fc, jc=jc)
+
+    def _structured_sections(self):
+        st = self.struct
+        nsym = (self.tdim + 1) * (self.tdim + 2) // 2
+        d1 = self.tdim + 1
+        fac_hdr = np.zeros((max(len(st["fac_rows"]), 1), 4), dtype=np.int32)
+        fac_a0 = np.zeros(max(len(st["fac_rows"]), 1))
+        fsp, fco = [], []
+        for i, (kind, scal, a0, coefs) in enumerate(st["fac_rows"]):
+            fac_hdr[i] = [kind, scal, len(fsp), len(coefs)]
+            fac_a0[i] = a0
+            for spe, c in coefs:
+                fsp.append(spe)
+                fco.append(c)
+        mono = np.full((max(len(st["monos"]), 1), 6), -1, dtype=np.int32)
+        mono_coef = np.zeros(max(len(st["monos"]), 1))
+        for i, (tag, slot, facs, coef, rows) in enumerate(st["monos"]):
+            mono[i, :3] = [tag, slot, len(facs)]
+            for k, f in enumerate(facs):
+                mono[i, 3 + k] = f
+            mono_coef[i] = coef
+        fc_ptr, fc_mono, fc_sign = [0], [], []
+        for lst in st["fc"]:
+            for im, sg in lst:
+                fc_mono.append(im)
+                fc_sign.append(sg)
+            fc_ptr.append(len(fc_mono))
+        jc_ptr, jc_tab, jc_coef = [0], [], []
+        for lst in st["jc"]:
+            for slot, other, c in lst:
+                jc_tab.append([slot, other])
+                jc_coef.append(c)
+            jc_ptr.append(len(jc_coef))
+        # W tables: W[which][i][q][ab] = w_q phi_i phi_a phi_b (a <= b), then its q-sum
+        wtab, woff = [], np.zeros((len(self.vol_ids), 4), dtype=np.int32)
+        sym = [(a, b) for a in range(d1) for b in range(a, d1)]
+        for t, vid in enumerate(self.vol_ids):
+            dF, dJ = self.degrees.get(("dx", vid), (1, None))
+            for which, deg in enumerate((dF, dF if dJ is None else dJ)):
+                bary, w = quadrature.rule(self.tdim, deg)
+                W = np.zeros((d1, len(w), nsym))
+                for i in range(d1):
+                    for k, (a, b) in enumerate(sym):
+                        W[i, :, k] = w * bary[:, i] * bary[:, a] * bary[:, b]
+                if which == 1 and (dJ is None or dJ == dF):
+                    woff[t, 2:4] = woff[t, 0:2]      # same rule: share the table
+                    continue
+                woff[t, 2 * which] = sum(len(x) for x in wtab)
+                woff[t, 2 * which + 1] = len(w)
+                wtab.append(W.ravel())
+                wtab.append(W.sum(axis=1).ravel())
+        ints = np.zeros(8, dtype=np.int32)
+        ints[:4] = [len(self.rslot_E), len(st["fac_rows"]), len(st["monos"]), nsym]
+        return {
+            S_STRUCT_INTS: ints, S_RSLOT_E: np.array(self.rslot_E, dtype=np.float64),
+            S_FAC_HDR: fac_hdr, S_FAC_A0: fac_a0, S_FAC_SPECIES: np.array(fsp, dtype=np.int32),
+            S_FAC_COEF: np.array(fco, dtype=np.float64), S_MONO: mono, S_MONO_COEF: mono_coef,
+            S_FC_PTR: np.array(fc_ptr, dtype=np.int32), S_FC_MONO: np.array(fc_mono, dtype=np.int32),
+            S_FC_SIGN: np.array(fc_sign, dtype=np.float64),
+            S_JC_PTR: np.array(jc_ptr, dtype=np.int32),
+            S_JC: np.array(jc_tab, dtype=np.int32).reshape(-1, 2), S_JC_COEF: np.array(jc_coef, dtype=np.float64),
+            S_WTAB: np.concatenate(wtab) if wtab else np.zeros(0), S_WTAB_OFF: woff,
+        }
+
     @staticmethod
     def _compact(tags, ids, required):
         """Map subdomain ids to their position in ``ids`` (-1: not a subdomain)."""
@@ -295,6 +455,8 @@ class KernelSpec:
             S_QUAD_W: np.concatenate(self._qw) if self._qw else np.zeros(0),
             S_ADV: adv, S_DIFF_UPROG: uprog,
         }
+        if self.struct is not None:
+            sections.update(self._structured_sections())
         return pack_sections(sections)
 
 

@@ -373,3 +373,41 @@ def advection_trap_mms_2d(n=200):
         advection_terms=[F.AdvectionTerm(velocity=vel, subdomain=vol, species=mobile)],
         settings=F.Settings(atol=1e-10, rtol=1e-10, transient=False))
     return m, (mobile, trapped), (ex_m, ex_t)
+
+
+def multi_isotope_traps_3d(n=4, dt=1e-2, final_time=3e-2, exchange=False):
+    """BASELINE configs[2] (C2): 3D H/D/T transient with 3 trap types: mobile H, D, T
+    (D_0 scaled by 1/sqrt(mass)), 9 trapped species, 9 trapping reactions sharing the
+    trap sites of each type between the isotopes; T = 600 + 100 x (P1 field); Sieverts
+    BC at x=0 for every isotope, c=0 at x=1."""
+    raw = F.create_unit_cube(n, n, n)
+    mat = F.Material(D_0={"H": 4.1e-7, "D": 4.1e-7 / np.sqrt(2), "T": 4.1e-7 / np.sqrt(3)},
+                     E_D={"H": 0.39, "D": 0.39, "T": 0.39})
+    vol = F.VolumeSubdomain(id=1, material=mat)
+    left = F.SurfaceSubdomain(id=1, locator=lambda x: np.isclose(x[0], 0))
+    right = F.SurfaceSubdomain(id=2, locator=lambda x: np.isclose(x[0], 1))
+    iso = [F.Species(nm) for nm in ("H", "D", "T")]
+    trap_par = [(8.9e-17, 0.39, 1e13, 0.87, 1e23), (8.9e-17, 0.39, 1e13, 1.0, 4e23),
+                (8.9e-17, 0.39, 1e13, 1.5, 2e23)]
+    trapped, reactions = [], []
+    for i, (k0, Ek, p0, Ep, dens) in enumerate(trap_par):
+        group = [F.Species(f"t{s.name}_{i}", mobile=False) for s in iso]
+        trapped += group
+        for s, ts, mass in zip(iso, group, (1.0, 2.0, 3.0)):
+            empty = F.ImplicitSpecies(n=dens, others=list(group))
+            reactions.append(F.Reaction(reactant=[s, empty], product=ts, k_0=k0 / np.sqrt(mass),
+                                        E_k=Ek, p_0=p0, E_p=Ep, volume=vol))
+    m = F.HydrogenTransportProblem()
+    m.mesh = F.Mesh(raw)
+    m.subdomains = [vol, left, right]
+    m.species = iso + trapped
+    m.reactions = reactions
+    m.temperature = lambda x: 600 + 100 * x[0]
+    m.boundary_conditions = []
+    for s, P in zip(iso, (100.0, 50.0, 25.0)):
+        m.boundary_conditions.append(F.SievertsBC(subdomain=left, S_0=4.02e21, E_S=1.04,
+                                                  pressure=P, species=s))
+        m.boundary_conditions.append(F.FixedConcentrationBC(subdomain=right, value=0, species=s))
+    m.settings = F.Settings(atol=1e8, rtol=1e-10, final_time=final_time)
+    m.settings.stepsize = F.Stepsize(initial_value=dt)
+    return m, iso, trapped

@@ -197,3 +197,21 @@ def test_advection_trap_parity_2d():
     assert gm.solver.solver.getIterationNumber() == rm.solver.solver.getIterationNumber()
     for a, b in zip(sg, sr):
         assert _rel(a.post_processing_solution.x.array, b.post_processing_solution.x.array) < 1e-8
+
+
+def test_multi_isotope_three_traps_3d():
+    """C2 in small: 12 species, 9 reactions, species-sparse Jacobian (66 of 144 pairs)."""
+    from cases import multi_isotope_traps_3d
+
+    (gm, _, _), (rm, _, _) = _pair(multi_isotope_traps_3d, 3)
+    assert gm.solver.spec.npairs == 66
+    _check_assembly(gm, rm, seed=5)
+    for m in (gm, rm):
+        m.u.x.array[:] = 0.0
+        m.u_n.x.array[:] = 0.0
+    gm.run()
+    rm.run()
+    assert gm.timesteps == rm.timesteps
+    for a, b in zip(gm.species, rm.species):
+        ref = b.post_processing_solution.x.array
+        assert np.linalg.norm(a.post_processing_solution.x.array - ref) <= 1e-8 * max(np.linalg.norm(ref), 1e-300)
