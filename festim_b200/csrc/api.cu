@@ -237,6 +237,23 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
       if (up[3 * i] >= 0) { S.n_udiff++; ctx->symmetric = false; }
   }
 #undef UP
+  // SpMV gather table (multi-species rows), one line per block-row degree
+  S.spmv_tab = nullptr; S.spmv_tab_stride = 0;
+  if (S.ns > 1 && (long long)S.maxdeg * S.ns < 65536) {
+    std::vector<int> nc(S.ns), pp(S.ns + 1), cs(S.npairs);
+    memcpy(nc.data(), blob + secs[S_PAIR_NC].offset, sizeof(int) * S.ns);
+    memcpy(pp.data(), blob + secs[S_PAIR_PP].offset, sizeof(int) * (S.ns + 1));
+    memcpy(cs.data(), blob + secs[S_PAIR_CS].offset, sizeof(int) * S.npairs);
+    const int stride = S.maxdeg * S.npairs;
+    std::vector<unsigned short> tab((size_t)(S.maxdeg + 1) * stride, 0);
+    for (int d = 1; d <= S.maxdeg; ++d)
+      for (int s = 0; s < S.ns; ++s)
+        for (int k = 0; k < d; ++k)
+          for (int j = 0; j < nc[s]; ++j)
+            tab[(size_t)d * stride + (size_t)d * pp[s] + (size_t)k * nc[s] + j] = (unsigned short)(k * S.ns + cs[pp[s] + j]);
+    if ((rc = fb_upload(ctx, &S.spmv_tab, tab.data(), tab.size()))) return rc;
+    S.spmv_tab_stride = stride;
+  }
   // mutable per-step buffers
   if ((rc = fb_alloc(ctx, &ctx->d_scalars, (size_t)n_scalars + 1))) return rc;
   if ((rc = fb_alloc(ctx, &ctx->d_fields, (size_t)S.n_fields + 1))) return rc;

@@ -76,6 +76,10 @@ struct DevSpec {
   const double* jc_coef;
   const double* wtab;         // per tag and rule: W[i][q][sym] then its q-sum W0[i][sym]
   const int* wtab_off;        // [n_vtags*4] offF, nqF, offJ, nqJ
+  // SpMV gather table: for a block row of degree d, entry t -> index into the staged
+  // neighbour values (k*ns + column species); [ (maxdeg+1) x maxdeg*npairs ] uint16
+  const unsigned short* spmv_tab;
+  int spmv_tab_stride;
   // per-step data
   const double* scalars;
   double T_const;

@@ -53,6 +53,44 @@ k_spmv(DevSpec S, const double* __restrict__ J, const double* __restrict__ x, do
   if (lane == 0) y[row] = sum;
 }
 
+// Multi-species SpMV: one warp per vertex.  The ns values of every neighbour are staged
+// once in shared memory (deg x ns doubles, coalesced 8*ns-byte segments) and reused by all
+// ns scalar rows of the vertex; the row values stream from HBM exactly once, fully
+// coalesced (the block row is contiguous), with the lanes laid out as (neighbour, column
+// species) so no integer division sits in the inner loop.
+__global__ void __launch_bounds__(256)
+k_spmv_node(DevSpec S, const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y,
+            int xs_stride) {
+  extern __shared__ double xs_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long v = (long long)blockIdx.x * wpb + warp;
+  if (v >= S.n_owned) return;
+  const int ns = S.ns;
+  double* xs = xs_all + (size_t)warp * xs_stride;
+  const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+  for (int t = lane; t < deg * ns; t += 32) {
+    const int k = t / ns;
+    xs[t] = x[(long long)S.colidx[r0 + k] * ns + (t - k * ns)];
+  }
+  __syncwarp();
+  const double* __restrict__ vals = J + (long long)r0 * S.npairs;
+  for (int s = 0; s < ns; ++s) {
+    const int nc = S.pair_nc[s], pp = S.pair_pp[s];
+    const double* __restrict__ rv = vals + (long long)deg * pp;
+    const int kper = 32 / nc;                 // neighbours handled per sweep
+    const int kl = lane / nc, j = lane - kl * nc;
+    const bool active = kl < kper;
+    const int cs = active ? S.pair_cs[pp + j] : 0;
+    double sum = 0.0;
+    if (active) {
+#pragma unroll 4
+      for (int k = kl; k < deg; k += kper) sum += rv[k * nc + j] * xs[k * ns + cs];
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) y[v * ns + s] = sum;
+  }
+}
+
 static int spmv_group(const DevSpec& S) {
   // ~ average row length / 2, power of two
   const double avg = (double)S.npairs / S.ns * 15.0;
@@ -66,6 +104,20 @@ static int spmv_group(const DevSpec& S) {
 
 int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y) {
   const DevSpec& S = ctx->S;
+  if (S.ns > 1 && S.spmv_tab != nullptr && !getenv("FB_SPMV_ROWWISE")) {
+    const int wpb = 8;
+    const int stride = (S.maxdeg * S.ns + 1) & ~1;
+    const size_t smem = (size_t)wpb * stride * sizeof(double);
+    if (smem <= 200 * 1024) {
+      if (smem > 48 * 1024)
+        FB_CHECK(ctx, cudaFuncSetAttribute(k_spmv_node, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned grid = (unsigned)((S.n_owned + wpb - 1) / wpb);
+      k_spmv_node<<<grid, wpb * 32, smem, ctx->stream>>>(S, J, x, y, stride);
+      ctx->launches++;
+      FB_CHECK(ctx, cudaGetLastError());
+      return 0;
+    }
+  }
   const int G = spmv_group(S);
   const long long threads = S.n_dofs * G;
   const unsigned grid = (unsigned)((threads + FB_TPB - 1) / FB_TPB);
