@@ -411,3 +411,68 @@ def multi_isotope_traps_3d(n=4, dt=1e-2, final_time=3e-2, exchange=False):
     m.settings = F.Settings(atol=1e8, rtol=1e-10, final_time=final_time)
     m.settings.stepsize = F.Stepsize(initial_value=dt)
     return m, iso, trapped
+
+
+def complex_reaction(stepsize=0.5, k=350e-4, p=120e-4, c_A_0=3, final_time=200):
+    """reference test/test_complex_reaction.py:39-135: A + B <-> C + D, constant rates
+    (E_k = E_p = 0, the constant-p branch of reaction.py:182-187), no boundary
+    conditions, TotalVolume exports."""
+    m = F.HydrogenTransportProblem()
+    L = 1
+    m.mesh = F.Mesh1D(np.linspace(0, L, num=10))
+    mat = F.Material(D_0=1, E_D=0, name="mat")
+    vol = F.VolumeSubdomain1D(id=1, borders=[0, L], material=mat)
+    m.subdomains = [vol, F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=L)]
+    A, B, Cc, D = (F.Species(nm) for nm in "ABCD")
+    m.species = [A, B, Cc, D]
+    m.reactions = [F.Reaction(k_0=k, E_k=0, p_0=p, E_p=0, reactant=[A, B], product=[Cc, D], volume=vol)]
+    m.temperature = 400
+    m.boundary_conditions = []
+    m.initial_conditions = [F.InitialConcentration(value=c_A_0, species=A, volume=vol),
+                            F.InitialConcentration(value=c_A_0, species=B, volume=vol)]
+    m.exports = [F.TotalVolume(s, vol) for s in (A, B, Cc, D)]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, max_iterations=30, final_time=final_time)
+    m.settings.stepsize = F.Stepsize(initial_value=stepsize)
+    return m
+
+
+def concentration_A_exact(t, c_A_0, k, p):
+    """reference test/test_complex_reaction.py:7-36."""
+    A = 1 - p / k
+    B = 2 * p / k * c_A_0
+    Cq = -p / k * c_A_0**2
+    roots = np.roots([A, B, Cq])
+    a, b = (roots[0], roots[0]) if len(roots) == 1 else (roots[0], roots[1])
+    Fq = ((c_A_0 - a) / (c_A_0 - b)) * np.exp(-(a - b) * (k - p) * t)
+    return (a - b * Fq) / (1 - Fq)
+
+
+def non_homogeneous_density(density_func, final_time=100):
+    """reference test/system_tests/test_non_homogeneous_density.py:26-85: trap filling
+    with a space/time dependent trap density, no detrapping (p_0 = 0)."""
+    m = F.HydrogenTransportProblem()
+    m.mesh = F.Mesh1D(np.linspace(0, 1, 100))
+    vol = F.VolumeSubdomain1D(id=1, borders=[0, 1], material=F.Material(name="mat", D_0=1, E_D=0))
+    left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=1)
+    m.subdomains = [vol, left, right]
+    H = F.Species("H")
+    trapped = F.Species("trapped_H", mobile=False)
+    empty = F.ImplicitSpecies(n=density_func, name="empty", others=[trapped])
+    m.species = [H, trapped]
+    m.reactions = [F.Reaction(reactant=[H, empty], product=trapped, k_0=1, E_k=0, p_0=0, E_p=0, volume=vol)]
+    m.temperature = 600
+    m.boundary_conditions = [F.DirichletBC(subdomain=left, value=1, species=H),
+                             F.DirichletBC(subdomain=right, value=1, species=H)]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, final_time=final_time)
+    m.settings.stepsize = 1
+    total = F.TotalVolume(field=trapped, volume=vol)
+    m.exports = [total]
+    return m, total
+
+
+DENSITIES = {
+    "step_space": (lambda x: ufl.conditional(ufl.gt(x[0], 0.5), 10, 0.0), 5.0),
+    "simple_space": (lambda x: 10 - 10 * x[0], 5.0),
+    "step_time_space": (lambda x, t: ufl.conditional(ufl.gt(t, 50), 10 - 10 * x[0], 0.0), 5.0),
+    "step_time": (lambda t: 10.0 if t > 50 else 2.0, 10.0),
+}

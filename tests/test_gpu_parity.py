@@ -215,3 +215,37 @@ def test_multi_isotope_three_traps_3d():
     for a, b in zip(gm.species, rm.species):
         ref = b.post_processing_solution.x.array
         assert np.linalg.norm(a.post_processing_solution.x.array - ref) <= 1e-8 * max(np.linalg.norm(ref), 1e-300)
+
+
+def test_complex_reaction_parity():
+    """A + B <-> C + D (two-factor products, no Dirichlet BC): TotalVolume histories."""
+    from cases import complex_reaction
+
+    gm = complex_reaction(0.5, 350e-4, 120e-4, 3, 20)
+    rm = complex_reaction(0.5, 350e-4, 120e-4, 3, 20)
+    rm.solver_backend = OracleBackend()
+    for m in (gm, rm):
+        m.initialise()
+        m.run()
+    assert gm.timesteps == rm.timesteps
+    for eg, er in zip(gm.exports, rm.exports):
+        dg, dr = np.array(eg.data), np.array(er.data)
+        assert np.abs(dg - dr).max() <= 1e-6 * max(np.abs(dr).max(), 1e-300)
+    assert _rel(gm.u.x.array, rm.u.x.array) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["step_space", "step_time_space", "step_time"])
+def test_non_homogeneous_density_parity(name):
+    """Trap density as an expression of x, t (point-wise path) or of t (structured path)."""
+    from cases import DENSITIES, non_homogeneous_density
+
+    func, _ = DENSITIES[name]
+    gm, tg = non_homogeneous_density(func, 60)
+    rm, tr = non_homogeneous_density(func, 60)
+    rm.solver_backend = OracleBackend()
+    for m in (gm, rm):
+        m.initialise()
+        m.run()
+    assert gm.timesteps == rm.timesteps
+    assert np.abs(np.array(tg.data) - np.array(tr.data)).max() <= 1e-6 * np.abs(np.array(tr.data)).max()
+    assert _rel(gm.u.x.array, rm.u.x.array) < 1e-8

@@ -136,3 +136,28 @@ def test_MMS_1_species_1_trap_with_advection():
     mesh = m.mesh.mesh
     assert error_L2(mesh, mobile.post_processing_solution.x.array, em) < 4 * 2e-3
     assert error_L2(mesh, trapped.post_processing_solution.x.array, et) < 4 * 7e-5
+
+
+@pytest.mark.parametrize("k, p, c_A_0", [(350e-4, 120e-4, 3), (200e-4, 100e-4, 2)])
+def test_reaction(k, p, c_A_0):
+    """reference test/test_complex_reaction.py:157-178 (relative L2 error < 1e-2)."""
+    from cases import complex_reaction, concentration_A_exact
+
+    m = complex_reaction(0.5, k, p, c_A_0)
+    _run(m)
+    total_A = m.exports[0]
+    times, data = np.array(total_A.t), np.array(total_A.data)
+    exact = concentration_A_exact(times, c_A_0, k, p)
+    err = np.sqrt(np.sum((exact - data) ** 2)) / np.sqrt(np.sum(exact**2))
+    assert err < 1e-2
+
+
+@pytest.mark.parametrize("name", ["step_space", "simple_space", "step_time_space", "step_time"])
+def test_non_homogeneous_density(name):
+    """reference test/system_tests/test_non_homogeneous_density.py:16-85."""
+    from cases import DENSITIES, non_homogeneous_density
+
+    func, expected = DENSITIES[name]
+    m, total = non_homogeneous_density(func)
+    _run(m)
+    assert np.isclose(total.value, expected)
