@@ -80,6 +80,8 @@ def load_library():
         "fb_dcg_init": (i, [vp, vp, vp, vp, vp, vp, vp]),
         "fb_dcg_spmv_dots": (i, [vp, vp, vp, vp, vp, vp]),
         "fb_dcg_update": (i, [vp, d, d, vp, vp, vp, vp, vp, vp]),
+        "fb_dcg_scalars": (i, [vp, vp, vp, i]),
+        "fb_dcg_update_dev": (i, [vp, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -97,7 +99,7 @@ EXPORTED_SYMBOLS = [
     "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
     "fb_total_surface", "fb_surface_flux", "fb_set_owned", "fb_set_sm_partition",
     "fb_bjacobi_setup", "fb_precond",
-    "fb_dcg_init", "fb_dcg_spmv_dots", "fb_dcg_update",
+    "fb_dcg_init", "fb_dcg_spmv_dots", "fb_dcg_update", "fb_dcg_scalars", "fb_dcg_update_dev",
 ]
 
 

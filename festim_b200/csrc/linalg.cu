@@ -1312,3 +1312,56 @@ extern "C" int fb_dcg_update(fb_ctx* ctx, double alpha, double beta, double* x, 
   FB_CHECK(ctx, cudaGetLastError());
   return 0;
 }
+
+// Device-resident recurrence scalars for the partitioned CG, so an iteration
+// (halo exchange, SpMV + dots, all-reduce, scalars, update) has no host round trip and
+// can be captured once in a CUDA graph and replayed.
+//   state: [0]=alpha [1]=beta [2]=gamma_old [3]=iterations [4]=done [5]=threshold^2 [6]=uu
+__global__ void k_dcg_scalars(const double* __restrict__ red3, double* __restrict__ st, int max_it) {
+  if (st[4] != 0.0) return;
+  const double gamma = red3[0], delta = red3[1], uu = red3[2];
+  st[6] = uu;
+  const int it = (int)st[3];
+  if (uu <= st[5] || !(uu == uu) || it >= max_it) { st[4] = (uu <= st[5]) ? 1.0 : 2.0; return; }
+  double alpha, beta;
+  if (it == 0) { beta = 0.0; alpha = gamma / delta; }
+  else { beta = gamma / st[2]; alpha = gamma / (delta - beta * gamma / st[0]); }
+  st[0] = alpha; st[1] = beta; st[2] = gamma; st[3] = (double)(it + 1);
+}
+
+__global__ void __launch_bounds__(FB_TPB)
+k_dcg_update_dev(DevSpec S, const double* __restrict__ dinv, const double* __restrict__ st,
+                 double* __restrict__ x, double* __restrict__ r, double* __restrict__ u,
+                 const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s_) {
+  if (st[4] != 0.0) return;
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= S.n_owned) return;
+  const double alpha = st[0], beta = st[1];
+  double rin[FB_MAX_NS], zo[FB_MAX_NS];
+  for (int s = 0; s < S.ns; ++s) {
+    const long long i = v * S.ns + s;
+    const double pi = u[i] + beta * p[i];
+    const double si = w[i] + beta * s_[i];
+    p[i] = pi; s_[i] = si;
+    x[i] += alpha * pi;
+    rin[s] = r[i] - alpha * si;
+    r[i] = rin[s];
+  }
+  bjacobi_apply(S.ns, dinv, v, rin, zo);
+  for (int s = 0; s < S.ns; ++s) u[v * S.ns + s] = zo[s];
+}
+
+extern "C" int fb_dcg_scalars(fb_ctx* ctx, const double* red3_dev, double* state_dev, int max_it) {
+  if (!ctx) return -1;
+  FB_LAUNCH(ctx, k_dcg_scalars, 1, 1, 0, red3_dev, state_dev, max_it);
+  return 0;
+}
+
+extern "C" int fb_dcg_update_dev(fb_ctx* ctx, const double* state_dev, double* x, double* r, double* u,
+                                 const double* w, double* p, double* s) {
+  if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
+  const DevSpec& S = ctx->S;
+  FB_LAUNCH(ctx, k_dcg_update_dev, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, ctx->d_dinv,
+            state_dev, x, r, u, w, p, s);
+  return 0;
+}

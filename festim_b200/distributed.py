@@ -187,7 +187,11 @@ class DistributedNewtonSolver:
         ft = MeshTags(lp.mesh, gmesh.tdim - 1, np.arange(len(lp.local_bfacets)), ftag[lp.local_bfacets])
         view = _ProblemView(problem, lp.mesh, vt, ft)
         self.spec = KernelSpec(view)
-        self.ctx = ctx = Context(self.spec, device, renumber=False)  # owned-first numbering is fixed
+        # a dedicated (capturable) stream: library launches, torch copies and NCCL all use it
+        torch.cuda.set_device(device)
+        self.stream = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(self.stream):
+            self.ctx = ctx = Context(self.spec, device, renumber=False)  # owned-first numbering is fixed
         ctx._check(ctx.lib.fb_set_owned(ctx.h, lp.n_owned))
         self.halo = HaloExchange(lp, ns, torch, ctx.device)
         self.atol = petsc_options["snes_atol"]
@@ -216,6 +220,9 @@ class DistributedNewtonSolver:
         self.F, self.J, self.y = z(n), z(ctx.nnz), z(n)
         self.r, self.uv, self.w, self.p, self.s, self.tmp = z(n), z(n), z(n), z(n), z(n), z(n)
         self.out3 = z(3)
+        self.state = z(8)
+        self._graph = None
+        self.use_graph = not bool(__import__("os").environ.get("FB_NO_CUDA_GRAPH"))
         self.cg_iterations = 0
         self.launches_python = 0
 
@@ -261,49 +268,78 @@ class DistributedNewtonSolver:
         return float(np.sqrt(allreduce_sum([self._dot(a, a)], self.torch, self.ctx.device)[0]))
 
     # ---- partitioned CG (block-Jacobi preconditioned, single reduction) -------------
-    def linear_solve(self, J, b, x, rtol, max_it):
+    def _cg_iteration(self, J, x):
+        """One CG iteration with device-resident scalars (capturable in a CUDA graph)."""
         ctx, lib, ptr = self.ctx, self.ctx.lib, self.ctx.ptr
+        r, u, w, p, s = self.r, self.uv, self.w, self.p, self.s
+        self.halo(u)
+        lib.fb_dcg_spmv_dots(ctx.h, ptr(J), ptr(u), ptr(r), ptr(w), ptr(self.out3))
+        if self.nranks > 1:
+            self.dist.all_reduce(self.out3)
+        lib.fb_dcg_scalars(ctx.h, ptr(self.out3), ptr(self.state), int(self._max_it))
+        lib.fb_dcg_update_dev(ctx.h, ptr(self.state), ptr(x), ptr(r), ptr(u), ptr(w), ptr(p), ptr(s))
+
+    def linear_solve(self, J, b, x, rtol, max_it):
+        torch, ctx, lib, ptr = self.torch, self.ctx, self.ctx.lib, self.ctx.ptr
         ctx._check(lib.fb_bjacobi_setup(ctx.h, ptr(J)))
         ctx._check(lib.fb_precond(ctx.h, ptr(b), ptr(self.tmp)))
         thr2 = (rtol * self._norm(self.tmp)) ** 2
         r, u, w, p, s = self.r, self.uv, self.w, self.p, self.s
         ctx._check(lib.fb_dcg_init(ctx.h, ptr(b), ptr(x), ptr(r), ptr(u), ptr(p), ptr(s)))
-        alpha = beta = gamma_old = 0.0
-        it = 0
+        self._max_it = max_it
+        st = torch.zeros(8, dtype=torch.float64)
+        st[5] = thr2
+        self.state.copy_(st.to(self.state.device))
+        key = (J.data_ptr(), x.data_ptr(), max_it)
+        if self.use_graph and (self._graph is None or self._graph[0] != key):
+            try:
+                self._cg_iteration(J, x)               # eager warm-up (NCCL channels, allocator)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._cg_iteration(J, x)
+                self._graph = (key, g)
+                # the warm-up iteration advanced the recurrence: restart it
+                ctx._check(lib.fb_dcg_init(ctx.h, ptr(b), ptr(x), ptr(r), ptr(u), ptr(p), ptr(s)))
+                self.state.copy_(st.to(self.state.device))
+            except Exception as exc:  # capture not supported here: eager iterations
+                import warnings
+
+                warnings.warn(f"CUDA-graph capture of the CG iteration failed ({exc}); running eagerly")
+                self.use_graph = False
+                self._graph = None
+                ctx._check(lib.fb_dcg_init(ctx.h, ptr(b), ptr(x), ptr(r), ptr(u), ptr(p), ptr(s)))
+                self.state.copy_(st.to(self.state.device))
+        chunk = 16
         while True:
-            self.halo(u)
-            ctx._check(lib.fb_dcg_spmv_dots(ctx.h, ptr(J), ptr(u), ptr(r), ptr(w), ptr(self.out3)))
-            if self.nranks > 1:
-                self.dist.all_reduce(self.out3)
-            gamma, delta, uu = self.out3.cpu().numpy()
-            if uu <= thr2 or not np.isfinite(uu) or it >= max_it:
+            for _ in range(chunk):
+                if self._graph is not None:
+                    self._graph[1].replay()
+                else:
+                    self._cg_iteration(J, x)
+            sth = self.state.cpu().numpy()
+            if sth[4] != 0.0:
                 break
-            if it == 0:
-                beta, alpha = 0.0, gamma / delta
-            else:
-                beta = gamma / gamma_old
-                alpha = gamma / (delta - beta * gamma / alpha)
-            gamma_old = gamma
-            ctx._check(lib.fb_dcg_update(ctx.h, float(alpha), float(beta), ptr(x), ptr(r), ptr(u),
-                                         ptr(w), ptr(p), ptr(s)))
-            it += 1
+        it = int(sth[3])
         self.cg_iterations += it
-        return it, bool(uu <= thr2)
+        return it, bool(sth[4] == 1.0)
 
     # ---- Newton (reference problem.py:271-289, helpers.py:408-426) --------------------
     def solve(self):
         ctx, p = self.ctx, self.problem
         if not self._is_symmetric():
             raise NotImplementedError("the partitioned path implements CG (SPD systems) only")
-        self._push_state()
-        u = ctx.to_device("u", p.u.x.array[self.ldofs])
-        un = ctx.to_device("u_n", p.u_n.x.array[self.ldofs]) if self.spec.transient else u
-        t = float(p.t) if hasattr(p, "t") else 0.0
-        atol = self.atol(t) if callable(self.atol) else self.atol
-        rtol = self.rtol(t) if callable(self.rtol) else self.rtol
-        it = self.newton_device(u, un, atol, rtol)
-        self.u_dev = u
-        self._gather(u)
+        with self.torch.cuda.stream(self.stream):
+            self._push_state()
+            u = ctx.to_device("u", p.u.x.array[self.ldofs])
+            un = ctx.to_device("u_n", p.u_n.x.array[self.ldofs]) if self.spec.transient else u
+            t = float(p.t) if hasattr(p, "t") else 0.0
+            atol = self.atol(t) if callable(self.atol) else self.atol
+            rtol = self.rtol(t) if callable(self.rtol) else self.rtol
+            it = self.newton_device(u, un, atol, rtol)
+            self.u_dev = u
+            self._gather(u)
+            self.stream.synchronize()
         return it
 
     def newton_device(self, u, un, atol, rtol):

@@ -170,6 +170,12 @@ int fb_dcg_spmv_dots(fb_ctx* ctx, const double* Jvals, const double* u, const do
                      double* out3 /*[dev] local (r,u), (w,u), (u,u)*/);
 int fb_dcg_update(fb_ctx* ctx, double alpha, double beta, double* x, double* r, double* u,
                   const double* w, double* p, double* s);
+/* the same with the recurrence scalars kept on the device (state[7]: alpha, beta, gamma,
+ * iterations, done, threshold^2, last ||M^-1 r||^2), so a whole iteration can be captured in
+ * a CUDA graph: no host round trip between the all-reduce and the update */
+int fb_dcg_scalars(fb_ctx* ctx, const double* reduced3 /*[dev]*/, double* state /*[dev]*/, int max_it);
+int fb_dcg_update_dev(fb_ctx* ctx, const double* state /*[dev]*/, double* x, double* r, double* u,
+                      const double* w, double* p, double* s);
 
 #ifdef __cplusplus
 }
