@@ -228,9 +228,9 @@ def run_partitioned(args, rank, world, local_rank, config):
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": None, "owned_vertices_rank0": int(nloc),
             "cuda_graph": bool(solver._graph is not None),
-            "note": "partitioned CG: one halo exchange and one 3-double all-reduce per iteration, the "
-                    "iteration captured in a CUDA graph (scalars stay on the device); the single-GPU "
-                    "number uses the persistent kernel"}))
+            "note": "partitioned CG: one halo exchange and one 3-double all-reduce per iteration, "
+                    "recurrence scalars stay on the device (host checks a done flag every 16 "
+                    "iterations); the single-GPU number uses the persistent kernel"}))
     dist.barrier()
     dist.destroy_process_group()
 

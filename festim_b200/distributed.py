@@ -222,7 +222,12 @@ class DistributedNewtonSolver:
         self.out3 = z(3)
         self.state = z(8)
         self._graph = None
-        self.use_graph = not bool(__import__("os").environ.get("FB_NO_CUDA_GRAPH"))
+        # CUDA-graph replay of the iteration: on by default for a single rank; with NCCL
+        # traffic inside the capture it is opt-in (FB_DIST_CUDA_GRAPH=1) until validated
+        import os
+
+        self.use_graph = (self.nranks == 1 and not os.environ.get("FB_NO_CUDA_GRAPH")) or \
+            bool(os.environ.get("FB_DIST_CUDA_GRAPH"))
         self.cg_iterations = 0
         self.launches_python = 0
 
