@@ -23,7 +23,9 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, dim, ns):
+def _worker(rank, world, port, dim, ns, p2p=False):
+    if p2p:
+        os.environ["FB_HALO_P2P"] = "1"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -69,9 +71,13 @@ def _worker(rank, world, port, dim, ns):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dim,ns", [(2, 1), (3, 2)])
-def test_partition_halo_spmv_world2(dim, ns):
-    mp.spawn(_worker, args=(2, _free_port(), dim, ns), nprocs=2, join=True)
+@pytest.mark.parametrize("dim,ns,p2p", [(2, 1, False), (3, 2, False), (3, 2, True)])
+def test_partition_halo_spmv_world2(dim, ns, p2p):
+    mp.spawn(_worker, args=(2, _free_port(), dim, ns, p2p), nprocs=2, join=True)
+
+
+def test_halo_all_gather_world3():
+    mp.spawn(_worker, args=(3, _free_port(), 3, 1, False), nprocs=3, join=True)
 
 
 def test_rcb_balanced_any_count():
