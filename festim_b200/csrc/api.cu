@@ -12,7 +12,7 @@ enum {
   S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
   S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_RSLOT_E, S_FAC_HDR, S_FAC_A0,
   S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
-  S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_MAX
+  S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW, S_MAX
 };
 enum {
   I_TDIM = 0, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -209,10 +209,11 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   UP(S_DERIV_SPECIES, 0, deriv_species); UP(S_DERIV_PROG, 0, deriv_prog);
   UP(S_QUAD_V, 0, quad_v); UP(S_QUAD_S, 0, quad_s); UP(S_QUAD_BARY, 1, quad_bary); UP(S_QUAD_W, 1, quad_w);
   UP(S_ADV, 0, adv); UP(S_DIFF_UPROG, 0, diff_uprog);
-  S.n_rslots = S.n_factors = S.n_monos = S.nsym = S.nq_max = 0;
+  S.n_rslots = S.n_factors = S.n_monos = S.nsym = S.nq_max = S.n_combos = 0;
   if (secs[S_STRUCT_INTS].id == S_STRUCT_INTS) {
     const int* si = (const int*)(blob + secs[S_STRUCT_INTS].offset);
-    S.n_rslots = si[0]; S.n_factors = si[1]; S.n_monos = si[2]; S.nsym = si[3];
+    S.n_rslots = si[0]; S.n_factors = si[1]; S.n_monos = si[2]; S.nsym = si[3]; S.n_combos = si[4];
+    UP(S_COMBO, 0, combo); UP(S_PAIR_ROW, 0, pair_row);
     UP(S_RSLOT_E, 1, rslot_E); UP(S_FAC_HDR, 0, fac_hdr); UP(S_FAC_A0, 1, fac_a0);
     UP(S_FAC_SPECIES, 0, fac_species); UP(S_FAC_COEF, 1, fac_coef); UP(S_MONO, 0, mono);
     UP(S_MONO_COEF, 1, mono_coef); UP(S_FC_PTR, 0, fc_ptr); UP(S_FC_MONO, 0, fc_mono);

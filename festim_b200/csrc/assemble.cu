@@ -55,7 +55,7 @@ k_assemble_nodes(DevSpec S, const double* __restrict__ u, const double* __restri
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_assemble_rows(DevSpec S, const double* __restrict__ u, const double* __restrict__ un,
                 double* __restrict__ F, double* __restrict__ J, int flags, int per_warp) {
   extern __shared__ double fb_rows_smem[];
@@ -198,9 +198,7 @@ static int assemble_dim(fb_ctx* ctx, const double* u, const double* un, double* 
                           !getenv("FB_NO_ROWS_KERNEL");
   if (structured) {
     // warp per vertex, block row accumulated in shared memory (assemble_rows.cuh)
-    constexpr int D1 = DIM + 1, NSYM = D1 * (D1 + 1) / 2;
-    const int per_warp = ((S.maxdeg * S.npairs + 2 * D1 * S.ns + S.n_factors * D1 + S.n_rslots * S.nq_max +
-                           2 * S.n_rslots * NSYM + S.ns + 1) & ~1);
+    const int per_warp = fb_rows_per_warp<DIM>(S);
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * per_warp * 8 > 200 * 1024) wpb >>= 1;
     const size_t smem = (size_t)wpb * per_warp * 8;

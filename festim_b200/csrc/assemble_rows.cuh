@@ -26,6 +26,15 @@ __device__ __forceinline__ int fb_sym(int a, int b) {
   return a * D1 - (a * (a - 1)) / 2 + (b - a);
 }
 
+// per-warp shared-memory need (doubles) of fb_assemble_rows_body
+template <int DIM>
+__host__ __device__ inline int fb_rows_per_warp(const DevSpec& S) {
+  constexpr int D1 = DIM + 1;
+  const int n = S.maxdeg * S.npairs + 2 * D1 * S.ns + S.n_factors * D1 + S.n_rslots * S.nq_max +
+                2 * (S.n_rslots * D1 * D1 + S.n_rslots * D1 + S.n_combos * D1) + S.ns + 2;
+  return (n + 1) & ~1;
+}
+
 template <int DIM>
 __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const double* __restrict__ u,
                                                       const double* __restrict__ un,
@@ -33,10 +42,11 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
                                                       int flags, double* smem, int per_warp) {
   constexpr int D1 = DIM + 1;
   constexpr int NSYM = D1 * (D1 + 1) / 2;
+  constexpr int DD = D1 * D1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const long long v = (long long)blockIdx.x * wpb + warp;
   if (v >= S.n_owned) return;
-  const int ns = S.ns, npairs = S.npairs, NR = S.n_rslots, NF = S.n_factors;
+  const int ns = S.ns, npairs = S.npairs, NR = S.n_rslots, NF = S.n_factors, NC = S.n_combos;
   const bool doF = (flags & FB_ASSEMBLE_F) != 0, doJ = (flags & FB_ASSEMBLE_J) != 0;
   const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
   const long long rowbase = (long long)r0 * npairs;
@@ -47,9 +57,13 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
   double* unc = uc + D1 * ns;
   double* fac = unc + D1 * ns;                        // [NF][D1]
   double* rho = fac + NF * D1;                        // [NR][nq_max]
-  double* momJ = rho + NR * S.nq_max;                 // [NR][NSYM]
-  double* momF = momJ + NR * NSYM;
-  double* flift = momF + NR * NSYM;                   // [ns]
+  double* MJ = rho + NR * S.nq_max;                   // [NR][D1][D1]  moments, J rule
+  double* MF = MJ + NR * DD;                          //               moments, F rule
+  double* M1J = MF + NR * DD;                         // [NR][D1]      first-order moments
+  double* M1F = M1J + NR * D1;
+  double* VJ = M1F + NR * D1;                         // [NC][D1]      V = M fac  per (slot, factor)
+  double* VF = VJ + NC * D1;
+  double* flift = VF + NC * D1;                       // [ns]
   for (int t = lane; t < nrow; t += 32) rowbuf[t] = 0.0;
   if (lane < ns) flift[lane] = 0.0;
   // Dirichlet rows of this vertex, any Dirichlet column in the row
@@ -68,9 +82,19 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
     const long long c = packed / D1;
     const int i = packed - (int)c * D1;
     int a[FB_MAX_D1], slot[FB_MAX_D1];
-    double X[FB_MAX_D1][3], G[FB_MAX_D1][3];
-    fb_load_cell<DIM>(S, c, a, X);
-    const double vol = fb_geometry<DIM>(X, G);
+    double gg[FB_MAX_D1], vol;
+    {
+      double X[FB_MAX_D1][3], G[FB_MAX_D1][3];
+      fb_load_cell<DIM>(S, c, a, X);
+      vol = fb_geometry<DIM>(X, G);
+#pragma unroll
+      for (int j = 0; j < D1; ++j) {
+        double d = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) d += G[i][k] * G[j][k];
+        gg[j] = d;
+      }
+    }
     const int tag = S.cell_tag[c];
     if (S.v2c_slot != nullptr) {
       const unsigned ps = S.v2c_slot[e];
@@ -94,7 +118,7 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
       for (int k = 0; k < h[3]; ++k) val += S.fac_coef[h[2] + k] * uc[b * ns + S.fac_species[h[2] + k]];
       fac[t] = val;
     }
-    // ---- rate-weighted moments for the J rule (and the F rule when it differs) ----
+    // ---- rate-weighted moments (J rule, and the F rule when it differs) ----------------
     const int* wo = S.wtab_off + 4 * tag;
     const bool same_rule = wo[0] == wo[2];
     for (int which = 1; which >= 0; --which) {
@@ -103,7 +127,9 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
       const int woff = wo[2 * which], nq = wo[2 * which + 1];
       const double* W = S.wtab + woff + (size_t)i * nq * NSYM;          // W[i][q][sym]
       const double* W0 = S.wtab + woff + (size_t)D1 * nq * NSYM + i * NSYM;
-      double* mom = which ? momJ : momF;
+      double* M = which ? MJ : MF;
+      double* M1 = which ? M1J : M1F;
+      double* V = which ? VJ : VF;
       if (S.T_mode) {
         const int qoff = S.quad_v[tag * 4 + 2 * which];
         __syncwarp();
@@ -116,27 +142,46 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
           for (int m = 0; m < NR; ++m) rho[m * S.nq_max + q] = exp(-S.rslot_E[m] * ikT);
         }
         __syncwarp();
-        for (int t = lane; t < NR * NSYM; t += 32) {
-          const int m = t / NSYM, ab = t - m * NSYM;
+        for (int t = lane; t < NR * DD; t += 32) {
+          const int m = t / DD, ab = t - m * DD;
+          const int sym = fb_sym<D1>(ab / D1, ab % D1);
+          const double* rm = rho + m * S.nq_max;
           double acc = 0.0;
-          for (int q = 0; q < nq; ++q) acc += rho[m * S.nq_max + q] * W[q * NSYM + ab];
-          mom[t] = acc * vol;
+#pragma unroll 4
+          for (int q = 0; q < nq; ++q) acc += rm[q] * W[q * NSYM + sym];
+          M[t] = acc * vol;
         }
       } else {
-        for (int t = lane; t < NR * NSYM; t += 32) {
-          const int m = t / NSYM, ab = t - m * NSYM;
-          mom[t] = exp(-S.rslot_E[m] / (FB_KB * S.T_const)) * W0[ab] * vol;
+        for (int t = lane; t < NR * DD; t += 32) {
+          const int m = t / DD, ab = t - m * DD;
+          M[t] = exp(-S.rslot_E[m] / (FB_KB * S.T_const)) * W0[fb_sym<D1>(ab / D1, ab % D1)] * vol;
         }
+      }
+      __syncwarp();
+      for (int t = lane; t < NR * D1; t += 32) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < D1; ++b) acc += M[t * D1 + b];
+        M1[t] = acc;
+      }
+      for (int t = lane; t < NC * D1; t += 32) {
+        const int cidx = t / D1, j = t - cidx * D1;
+        const double* Mm = M + S.combo[2 * cidx] * DD + j * D1;
+        const double* fv = fac + S.combo[2 * cidx + 1] * D1;
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < D1; ++b) acc += fv[b] * Mm[b];
+        V[t] = acc;
       }
     }
     __syncwarp();
-    const double* mF = same_rule ? momJ : momF;
+    const double* M1f = same_rule ? M1J : M1F;
+    const double* Vf = same_rule ? VJ : VF;
 
     // ---- Jacobian: lanes over species pairs ------------------------------------------
     if (needJ) {
       for (int p = lane; p < npairs; p += 32) {
-        int s = 0;
-        while (S.pair_pp[s + 1] <= p) ++s;
+        const int s = S.pair_row[p];
         if (rowbc >> s & 1u) continue;
         const int jidx = p - S.pair_pp[s];
         const int sc = S.pair_cs[p];
@@ -144,32 +189,27 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
 #pragma unroll
         for (int j = 0; j < D1; ++j) acc[j] = 0.0;
         for (int k = S.jc_ptr[tag * npairs + p]; k < S.jc_ptr[tag * npairs + p + 1]; ++k) {
-          const int m = S.jc[2 * k], other = S.jc[2 * k + 1];
+          const int cidx = S.jc[2 * k + 1];
           const double coef = S.jc_coef[k];
-          const double* M = momJ + m * NSYM;
+          const double* Vc = cidx >= 0 ? VJ + cidx * D1 : M1J + (-cidx - 1) * D1;
 #pragma unroll
-          for (int j = 0; j < D1; ++j) {
-            double Vj = 0.0;
-#pragma unroll
-            for (int b = 0; b < D1; ++b) Vj += (other < 0 ? 1.0 : fac[other * D1 + b]) * M[fb_sym<D1>(j, b)];
-            acc[j] += coef * Vj;
-          }
+          for (int j = 0; j < D1; ++j) acc[j] += coef * Vc[j];
         }
         if (s == sc) {
           const int ds = S.diff_slot[tag * ns + s];
           double kJ = 0.0;
           if (ds >= 0) kJ = S.diff_D0[tag * ns + s] * vol * S.dbar[((long long)S.n_slots + ds) * S.n_cells + c];
-          const double mm = (S.transient ? S.mass_dt[tag * ns + s] * S.inv_dt : 0.0) + S.mass_c[tag * ns + s];
+          const double mm = ((S.transient ? S.mass_dt[tag * ns + s] * S.inv_dt : 0.0) + S.mass_c[tag * ns + s]) *
+                            vol * mscale;
 #pragma unroll
-          for (int j = 0; j < D1; ++j) {
-            double gg = 0.0;
-#pragma unroll
-            for (int k = 0; k < DIM; ++k) gg += G[i][k] * G[j][k];
-            acc[j] += kJ * gg + mm * vol * mscale * ((i == j) ? 2.0 : 1.0);
-          }
+          for (int j = 0; j < D1; ++j) acc[j] += kJ * gg[j] + mm * ((i == j) ? 2.0 : 1.0);
           for (int t = 0; t < S.n_adv; ++t) {
             if (S.adv[2 * t] != tag || S.adv[2 * t + 1] != s) continue;
             const double* vel = S.velocities[t];
+            double X[FB_MAX_D1][3], G[FB_MAX_D1][3];   // recomputed: keeps G out of the hot loop's registers
+            int a2[FB_MAX_D1];
+            fb_load_cell<DIM>(S, c, a2, X);
+            fb_geometry<DIM>(X, G);
 #pragma unroll
             for (int j = 0; j < D1; ++j) {
               double accv = 0.0;
@@ -200,17 +240,18 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
       const double mc = S.mass_c[tag * ns + s] * vol * mscale;
 #pragma unroll
       for (int j = 0; j < D1; ++j) {
-        double gg = 0.0;
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) gg += G[i][k] * G[j][k];
         const double Mij = (i == j) ? 2.0 : 1.0;
         const double uj = uc[j * ns + s];
-        Facc += (kF * gg + mc * Mij) * uj;
+        Facc += (kF * gg[j] + mc * Mij) * uj;
         if (S.transient) Facc += m * Mij * (uj - unc[j * ns + s]);
       }
       for (int t = 0; t < S.n_adv; ++t) {
         if (S.adv[2 * t] != tag || S.adv[2 * t + 1] != s) continue;
         const double* vel = S.velocities[t];
+        double X[FB_MAX_D1][3], G[FB_MAX_D1][3];
+        int a2[FB_MAX_D1];
+        fb_load_cell<DIM>(S, c, a2, X);
+        fb_geometry<DIM>(X, G);
 #pragma unroll
         for (int j = 0; j < D1; ++j) {
           double accv = 0.0;
@@ -227,22 +268,16 @@ __device__ __forceinline__ void fb_assemble_rows_body(const DevSpec& S, const do
       for (int k = S.fc_ptr[tag * ns + s]; k < S.fc_ptr[tag * ns + s + 1]; ++k) {
         const int im = S.fc_mono[k];
         const int* mo = S.mono + 6 * im;
-        const double* M = mF + mo[1] * NSYM;
         double val = 0.0;
         if (mo[2] == 2) {
+          const double* Vc = Vf + mo[5] * D1;
+          const double* f1 = fac + mo[3] * D1;
 #pragma unroll
-          for (int p1 = 0; p1 < D1; ++p1)
-#pragma unroll
-            for (int p2 = 0; p2 < D1; ++p2)
-              val += fac[mo[3] * D1 + p1] * fac[mo[4] * D1 + p2] * M[fb_sym<D1>(p1, p2)];
+          for (int p1 = 0; p1 < D1; ++p1) val += f1[p1] * Vc[p1];
         } else {
+          const double* M1 = M1f + mo[1] * D1;
 #pragma unroll
-          for (int p1 = 0; p1 < D1; ++p1) {
-            double M1 = 0.0;
-#pragma unroll
-            for (int p2 = 0; p2 < D1; ++p2) M1 += M[fb_sym<D1>(p1, p2)];
-            val += (mo[2] == 1 ? fac[mo[3] * D1 + p1] : 1.0) * M1;
-          }
+          for (int p1 = 0; p1 < D1; ++p1) val += (mo[2] == 1 ? fac[mo[3] * D1 + p1] : 1.0) * M1[p1];
         }
         Facc += S.fc_sign[k] * S.mono_coef[im] * val;
       }

@@ -60,19 +60,21 @@ struct DevSpec {
   const double* quad_w;
   const int* adv;             // [n_adv*2] tag, species
   // structured reactions (moment-based assembly, assemble_rows.cuh)
-  int n_rslots, n_factors, n_monos, nsym, nq_max, maxdeg;
+  int n_rslots, n_factors, n_monos, nsym, nq_max, maxdeg, n_combos;
+  const int* combo;           // [n_combos*2] rate slot, factor
+  const int* pair_row;        // [npairs] row species of every stored pair
   const double* rslot_E;      // [n_rslots] activation energies of the rate slots
   const int* fac_hdr;         // [n_factors*4] a0 kind (0 const, 1 scalar), scalar id, coef offset, count
   const double* fac_a0;
   const int* fac_species;
   const double* fac_coef;
-  const int* mono;            // [n_monos*6] tag, slot, nfac, f1, f2, -
+  const int* mono;            // [n_monos*6] tag, slot, nfac, f1, f2, combo(slot, f2)
   const double* mono_coef;
   const int* fc_ptr;          // [n_vtags*ns+1] residual contributions per (tag, row species)
   const int* fc_mono;
   const double* fc_sign;
   const int* jc_ptr;          // [n_vtags*npairs+1] Jacobian contributions per (tag, pair)
-  const int* jc;              // [n*2] slot, other factor (-1 none)
+  const int* jc;              // [n*2] slot, combo index or -(slot+1) for the first-order moment
   const double* jc_coef;
   const double* wtab;         // per tag and rule: W[i][q][sym] then its q-sum W0[i][sym]
   const int* wtab_off;        // [n_vtags*4] offF, nqF, offJ, nqJ

@@ -38,7 +38,7 @@ MAGIC = 0xFB200_0001
  S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
  S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_RSLOT_E, S_FAC_HDR, S_FAC_A0,
  S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
- S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS) = range(1, 44)
+ S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW) = range(1, 46)
 
 # S_INTS slots
 (I_TDIM, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -304,12 +304,23 @@ class KernelSpec:
             for spe, c in coefs:
                 fsp.append(spe)
                 fco.append(c)
+        # (rate slot, factor) combinations whose moment-weighted nodal vectors
+        # V[j] = sum_b fac[b] M[j][b] are shared by residual and Jacobian contributions
+        combos = []
+
+        def combo_of(slot, f):
+            if (slot, f) not in combos:
+                combos.append((slot, f))
+            return combos.index((slot, f))
+
         mono = np.full((max(len(st["monos"]), 1), 6), -1, dtype=np.int32)
         mono_coef = np.zeros(max(len(st["monos"]), 1))
         for i, (tag, slot, facs, coef, rows) in enumerate(st["monos"]):
             mono[i, :3] = [tag, slot, len(facs)]
             for k, f in enumerate(facs):
                 mono[i, 3 + k] = f
+            if len(facs) == 2:
+                mono[i, 5] = combo_of(slot, facs[1])
             mono_coef[i] = coef
         fc_ptr, fc_mono, fc_sign = [0], [], []
         for lst in st["fc"]:
@@ -320,7 +331,8 @@ class KernelSpec:
         jc_ptr, jc_tab, jc_coef = [0], [], []
         for lst in st["jc"]:
             for slot, other, c in lst:
-                jc_tab.append([slot, other])
+                # second column: combo index, or -(slot+1) for the plain first-order moment
+                jc_tab.append([slot, combo_of(slot, other) if other >= 0 else -(slot + 1)])
                 jc_coef.append(c)
             jc_ptr.append(len(jc_coef))
         # W tables: W[which][i][q][ab] = w_q phi_i phi_a phi_b (a <= b), then its q-sum
@@ -342,7 +354,8 @@ class KernelSpec:
                 wtab.append(W.ravel())
                 wtab.append(W.sum(axis=1).ravel())
         ints = np.zeros(8, dtype=np.int32)
-        ints[:4] = [len(self.rslot_E), len(st["fac_rows"]), len(st["monos"]), nsym]
+        ints[:5] = [len(self.rslot_E), len(st["fac_rows"]), len(st["monos"]), nsym, len(combos)]
+        pair_row = np.repeat(np.arange(self.ns, dtype=np.int32), self.pair_nc)
         return {
             S_STRUCT_INTS: ints, S_RSLOT_E: np.array(self.rslot_E, dtype=np.float64),
             S_FAC_HDR: fac_hdr, S_FAC_A0: fac_a0, S_FAC_SPECIES: np.array(fsp, dtype=np.int32),
@@ -352,6 +365,7 @@ class KernelSpec:
             S_JC_PTR: np.array(jc_ptr, dtype=np.int32),
             S_JC: np.array(jc_tab, dtype=np.int32).reshape(-1, 2), S_JC_COEF: np.array(jc_coef, dtype=np.float64),
             S_WTAB: np.concatenate(wtab) if wtab else np.zeros(0), S_WTAB_OFF: woff,
+            S_COMBO: np.array(combos, dtype=np.int32).reshape(-1, 2), S_PAIR_ROW: pair_row,
         }
 
     @staticmethod
