@@ -1,6 +1,8 @@
 // C ABI of libfestim_b200.so: context lifetime, problem definition, per-step data.
 // See include/festim_b200.h for the contract and INTEGRATION.md for the binding.
+#include <algorithm>
 #include <cmath>
+#include <utility>
 #include <cstring>
 
 #include "fb_internal.cuh"
@@ -110,6 +112,7 @@ extern "C" int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr, const int32_t*
   if ((rc = fb_upload(ctx, &S.v2c_idx, v2c_idx, (size_t)S.n_cells * (S.tdim + 1)))) return rc;
   ctx->nnzb = nnzb;
   ctx->h_rowptr.assign(rowptr, rowptr + S.n_vertices + 1);
+  ctx->h_colidx.assign(colidx, colidx + nnzb);
   // block-tridiagonal in index order?  (1D meshes ordered along x)
   bool tri = true;
   for (long long v = 0; v < S.n_vertices && tri; ++v)
@@ -287,6 +290,7 @@ extern "C" int fb_set_dirichlet(fb_ctx* ctx, int64_t n_bc, const int64_t* bc_dof
     if (bc_dofs[i] < 0 || bc_dofs[i] >= S.n_dofs) return fb_fail(ctx, "Dirichlet dof out of range");
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_bc_map, 0xFF, sizeof(int) * S.n_dofs, ctx->stream));
   ctx->n_bc = n_bc;
+  ctx->coarse_masks_dirty = true;
   if (n_bc == 0) return 0;
   const long long* d = nullptr;
   int rc = fb_upload(ctx, &d, (const long long*)bc_dofs, (size_t)n_bc);
@@ -395,6 +399,7 @@ extern "C" int fb_set_sm_partition(fb_ctx* ctx, int nblocks, const int32_t* rng,
   if ((rc = fb_upload(ctx, &ctx->d_halo_idx, halo_idx, (size_t)halo_ptr[nblocks]))) return rc;
   if ((rc = fb_upload(ctx, &ctx->d_lcol, (const unsigned short*)lcol, (size_t)n_lcol))) return rc;
   ctx->part_max_entries = ctx->part_max_bentries = ctx->part_max_su = ctx->part_max_rows = 0;
+  ctx->part_min_rows = 1LL << 60;
   for (int b = 0; b < nblocks; ++b) {
     const long long nown = rng[b + 1] - rng[b], nhalo = halo_ptr[b + 1] - halo_ptr[b];
     const long long be = ctx->h_rowptr[rng[b + 1]] - ctx->h_rowptr[rng[b]];
@@ -402,6 +407,49 @@ extern "C" int fb_set_sm_partition(fb_ctx* ctx, int nblocks, const int32_t* rng,
     if (be > ctx->part_max_bentries) ctx->part_max_bentries = be;
     if ((nown + nhalo) * S.ns > ctx->part_max_su) ctx->part_max_su = (nown + nhalo) * S.ns;
     if (nown * S.ns > ctx->part_max_rows) ctx->part_max_rows = nown * S.ns;
+    if (nown * S.ns < ctx->part_min_rows) ctx->part_min_rows = nown * S.ns;
+  }
+  // coarse space of the two-level preconditioner (one constant per block): block id of
+  // every halo vertex, and per block the entries coupling to each neighbour block
+  if (S.ns == 1 && nblocks <= 160) {
+    auto block_of = [&](int w) {
+      int lo = 0, hi = nblocks;  // rng[lo] <= w < rng[hi]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rng[mid] <= w) lo = mid; else hi = mid; }
+      return lo;
+    };
+    std::vector<unsigned short> hb((size_t)halo_ptr[nblocks] + 1);
+    for (int h = 0; h < halo_ptr[nblocks]; ++h) hb[h] = (unsigned short)block_of(halo_idx[h]);
+    std::vector<int> cn_ptr(nblocks + 1, 0), cn_blk, cn_eptr(1, 0), cn_ent;
+    std::vector<std::pair<int, int>> off;  // (neighbour block, entry)
+    for (int b = 0; b < nblocks; ++b) {
+      off.clear();
+      for (int e = ctx->h_rowptr[rng[b]]; e < ctx->h_rowptr[rng[b + 1]]; ++e) {
+        const int w = ctx->h_colidx[e];
+        if (w < rng[b] || w >= rng[b + 1]) off.emplace_back(block_of(w), e);
+      }
+      std::stable_sort(off.begin(), off.end(),
+                       [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first < y.first; });
+      for (size_t k = 0; k < off.size(); ++k) {
+        if (k == 0 || off[k].first != off[k - 1].first) {
+          if (k) cn_eptr.push_back((int)cn_ent.size());
+          cn_blk.push_back(off[k].first);
+        }
+        cn_ent.push_back(off[k].second);
+      }
+      if (!off.empty()) cn_eptr.push_back((int)cn_ent.size());
+      cn_ptr[b + 1] = (int)cn_blk.size();
+    }
+    if ((rc = fb_upload(ctx, &ctx->d_halo_blk, hb.data(), hb.size()))) return rc;
+    if ((rc = fb_alloc(ctx, &ctx->d_halo_blk_eff, hb.size()))) return rc;
+    ctx->part_nhalo = halo_ptr[nblocks];
+    ctx->coarse_masks_dirty = true;
+    if ((rc = fb_upload(ctx, &ctx->d_cn_ptr, cn_ptr.data(), cn_ptr.size()))) return rc;
+    if ((rc = fb_upload(ctx, &ctx->d_cn_blk, cn_blk.data(), cn_blk.size()))) return rc;
+    if ((rc = fb_upload(ctx, &ctx->d_cn_eptr, cn_eptr.data(), cn_eptr.size()))) return rc;
+    if ((rc = fb_upload(ctx, &ctx->d_cn_ent, cn_ent.data(), cn_ent.size()))) return rc;
+    const size_t nco = (size_t)2 * nblocks * nblocks + 2 * nblocks + 8;
+    if ((rc = fb_alloc(ctx, &ctx->d_coarse, nco))) return rc;
+    FB_CHECK(ctx, cudaMemset(ctx->d_coarse, 0, nco * sizeof(double)));  // E keeps its structural zeros
   }
   ctx->part_blocks = nblocks;
   return 0;

@@ -21,13 +21,22 @@ struct fb_ctx {
   long long nnzb = 0, n_bc = 0;
   bool tridiag = false;
   // per-SM compact partition (fb_set_sm_partition)
-  std::vector<int> h_rowptr;
+  std::vector<int> h_rowptr, h_colidx;
+  const unsigned short* d_halo_blk = nullptr;   // block id of every halo vertex
+  // neighbour blocks of every block (CSR) and the block entries that couple to each of them
+  const int* d_cn_ptr = nullptr; const int* d_cn_blk = nullptr;
+  const int* d_cn_eptr = nullptr; const int* d_cn_ent = nullptr;
+  double* d_coarse = nullptr;                   // E (nb*nb), E^-1 (nb*nb), rc (nb)
+  unsigned short* d_halo_blk_eff = nullptr;     // halo block ids with Dirichlet vertices masked out
+  int part_nhalo = 0;
+  bool coarse_masks_dirty = true;
+  bool coarse_ready = false;                    // E^-1 matches the matrix being solved
   int part_blocks = 0;
   const int* d_blk_rng = nullptr;
   const int* d_halo_ptr = nullptr;
   const int* d_halo_idx = nullptr;
   const unsigned short* d_lcol = nullptr;
-  long long part_max_entries = 0, part_max_bentries = 0, part_max_su = 0, part_max_rows = 0;
+  long long part_max_entries = 0, part_max_bentries = 0, part_max_su = 0, part_max_rows = 0, part_min_rows = 0;
   bool symmetric = false;
   bool facet_u_terms = false;  // any solution-dependent facet term
   bool generic_u_vterms = false;  // any solution-dependent volume term evaluated point-wise

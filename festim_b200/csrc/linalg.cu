@@ -364,6 +364,9 @@ struct CgArgs {
   // compact per-SM partition (nullptr: contiguous equal ranges, gathers from L2)
   const int* blk_rng; const int* halo_ptr; const int* halo_idx; const unsigned short* lcol;
   long long su_doubles, bentries, rows_cap;     // smem capacities: iterate cache, block entries, rows
+  // two-level preconditioner: coarse space = one constant per block (nullptr: Jacobi only)
+  const double* Einv; double* rc; const unsigned short* halo_blk;
+  const int* cn_ptr; const int* cn_blk; double rel2;  // rel2: threshold relative to ||M^-1 b||^2
   long long smem_entries;                       // capacity (values) of the staging area
 };
 
@@ -413,6 +416,138 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks, un
   return ok_s != 0;
 }
 
+// ---------------------------------------------------------------------------
+// Two-level preconditioner of the persistent CG: M^-1 = D^-1 + Z E^-1 Z^T with Z the
+// piecewise-constant prolongation from the per-SM blocks (one coarse unknown per SM) and
+// E = Z^T A Z (nb x nb, SPD).  The restriction Z^T r is a block sum each SM already owns,
+// the coarse solve is one row of E^-1 per block, the prolongation adds one number to the
+// block's rows: the coarse correction rides on the two grid barriers the iteration has
+// anyway and removes the ~nb smoothest modes that make Jacobi-CG slow.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_coarse_build(DevSpec S, const double* __restrict__ J, const int* __restrict__ blk_rng,
+               const unsigned short* __restrict__ lcol, const int* __restrict__ cn_ptr,
+               const int* __restrict__ cn_blk, const int* __restrict__ cn_eptr,
+               const int* __restrict__ cn_ent, double* __restrict__ E) {
+  // E[b][b]: entries of block b's rows whose column is owned (local column < rows of the
+  // block); E[b][c]: the precomputed entry list of the neighbour pair, one warp per pair.
+  // Fixed summation orders: the preconditioner is bit-reproducible.
+  __shared__ double part[32];
+  const int nb = gridDim.x, b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int v0 = blk_rng[b], nvloc = blk_rng[b + 1] - v0;
+  const int e0 = S.rowptr[v0], e1 = S.rowptr[v0 + nvloc];
+  (void)e0; (void)e1;
+  double acc = 0.0;
+  for (int rr = tid; rr < nvloc; rr += blockDim.x) {
+    if (S.bc_map[v0 + rr] >= 0) continue;  // Dirichlet rows are not in the coarse space
+    for (int e = S.rowptr[v0 + rr]; e < S.rowptr[v0 + rr + 1]; ++e)
+      if ((int)lcol[e] < nvloc) acc += J[e];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) part[wid] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int q = 0; q < nw; ++q) s += part[q];
+    E[(size_t)b * nb + b] = s > 0.0 ? s : 1.0;  // block of Dirichlet rows only: decoupled dummy
+  }
+  for (int k = cn_ptr[b] + wid; k < cn_ptr[b + 1]; k += nw) {
+    double a2 = 0.0;
+    for (int q = cn_eptr[k] + lane; q < cn_eptr[k + 1]; q += 32) a2 += J[cn_ent[q]];
+    a2 = warp_sum(a2);
+    if (lane == 0) E[(size_t)b * nb + cn_blk[k]] = a2;
+  }
+}
+
+// block id of every halo vertex, FB_COARSE_NONE for Dirichlet vertices (their y slot is 0)
+#define FB_COARSE_NONE 159
+__global__ void k_coarse_halo_blocks(int n, const int* __restrict__ halo_idx, const unsigned short* __restrict__ blk,
+                                     const int* __restrict__ bc_map, unsigned short* __restrict__ out) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < n) out[h] = bc_map[halo_idx[h]] >= 0 ? (unsigned short)FB_COARSE_NONE : blk[h];
+}
+
+// In-place Gauss-Jordan inversion of the coarse operator (SPD: no pivoting) by ONE thread
+// block.  A single SM moves 128 B/clk through shared memory, so a matrix kept there costs
+// 3 accesses x nb^2 x nb steps = 0.4 ms; here every thread keeps a GJ_T x GJ_T tile in
+// registers and only the pivot row and column travel through (double-buffered) shared
+// memory: one __syncthreads and GJ_T^2 DFMA per thread and step.  The pivot loop is
+// unrolled GJ_T times so that the position of the pivot inside a tile is a compile-time
+// constant (register tiles cannot be indexed dynamically).
+#define GJ_T 6
+#define GJ_THREADS 640   // 25 x 25 tiles of 6 x 6 cover 150 x 150
+#define GJ_MAX 150
+__device__ __forceinline__ double gj_rcp(double d) {
+  double x = (double)(1.0f / (float)d);  // 24 bits, then two Newton steps in fp64
+  if (!(fabs(x) > 0.0) || isinf(x)) return 1.0 / d;
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  return x;
+}
+
+__global__ void __launch_bounds__(GJ_THREADS, 1)
+k_coarse_invert(int nb, const double* __restrict__ E, double* __restrict__ Einv) {
+  __shared__ double prow[2][GJ_MAX + GJ_T], fcol[2][GJ_MAX + GJ_T];
+  const int nt = (nb + GJ_T - 1) / GJ_T;  // tiles per dimension
+  const int ty = threadIdx.x / nt, tx = threadIdx.x - ty * nt;
+  const int r0 = ty * GJ_T, c0 = tx * GJ_T;
+  const bool active = ty < nt;
+  double a[GJ_T][GJ_T];
+#pragma unroll
+  for (int i = 0; i < GJ_T; ++i)
+#pragma unroll
+    for (int j = 0; j < GJ_T; ++j) {
+      const int r = r0 + i, c = c0 + j;
+      a[i][j] = (active && r < nb && c < nb) ? E[(size_t)r * nb + c] : (r == c ? 1.0 : 0.0);  // identity padding
+    }
+  int buf = 0;
+  for (int tb = 0; tb < nt; ++tb) {  // tile holding the pivot
+    const bool has_row = active && ty == tb, has_col = active && tx == tb;
+#pragma unroll
+    for (int k = 0; k < GJ_T; ++k) {  // pivot (tb * GJ_T + k): local index k in its tile
+      const int col = tb * GJ_T + k;
+      if (col >= nb) break;
+      if (has_row) {
+#pragma unroll
+        for (int j = 0; j < GJ_T; ++j) prow[buf][c0 + j] = a[k][j];
+      }
+      if (has_col) {
+#pragma unroll
+        for (int i = 0; i < GJ_T; ++i) {
+          fcol[buf][r0 + i] = a[i][k];
+          a[i][k] = 0.0;  // the pivot column restarts from zero: a = -f * ip below
+        }
+      }
+      __syncthreads();  // one barrier per step: the other buffer is not rewritten before the next one
+      if (active) {
+        const double ip = gj_rcp(prow[buf][col]);
+        double f[GJ_T];
+#pragma unroll
+        for (int i = 0; i < GJ_T; ++i) f[i] = fcol[buf][r0 + i];
+#pragma unroll
+        for (int j = 0; j < GJ_T; ++j) {
+          double pr = prow[buf][c0 + j] * ip;
+          if (j == k && has_col) pr = ip;
+#pragma unroll
+          for (int i = 0; i < GJ_T; ++i) a[i][j] = fma(-f[i], pr, a[i][j]);
+          if (has_row) a[k][j] = pr;  // the pivot row itself
+        }
+      }
+      buf ^= 1;
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < GJ_T; ++i)
+#pragma unroll
+      for (int j = 0; j < GJ_T; ++j) {
+        const int r = r0 + i, c = c0 + j;
+        if (r < nb && c < nb) Einv[(size_t)r * nb + c] = a[i][j];
+      }
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(1024, 1)
 k_cg_persistent(DevSpec S, CgArgs A) {
@@ -442,6 +577,7 @@ k_cg_persistent(DevSpec S, CgArgs A) {
   int* rstart = part ? (int*)(slcol + ((A.bentries + 1) & ~1LL)) : scols + A.smem_entries;
   int* rlen = rstart + rows_cap;
   int* rbst = rlen + rows_cap;
+  unsigned char* rfree = (unsigned char*)(rbst + rows_cap);  // 1: row is in the coarse space
   bool staged = false;
   int nhalo = 0;
   const int* hidx = nullptr;
@@ -479,6 +615,28 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     }
   }
   const bool cached = staged && part;  // iterate gathered from shared memory
+  // ---- coarse space (one constant per block): this block needs y = E^-1 rc at itself and
+  // at its neighbour blocks; warp k keeps row k of that set of E^-1 in registers ----------
+  __shared__ double ysm[160], rcs[160];
+  const bool coarse = A.Einv != nullptr && cached && ns == 1;
+  if (coarse) {
+    for (int rr = tid; rr < nrows; rr += T) rfree[rr] = S.bc_map[row0 + rr] < 0;
+    if (tid == 0) ysm[FB_COARSE_NONE] = 0.0;
+  }
+  const int cn0 = coarse ? A.cn_ptr[blockIdx.x] : 0;
+  const int nneed = coarse ? A.cn_ptr[blockIdx.x + 1] - cn0 + 1 : 0;  // self + neighbours
+  const unsigned short* hblk = coarse ? A.halo_blk + A.halo_ptr[blockIdx.x] : nullptr;
+  int ctarget = -1;
+  double erow[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (coarse && wid < nneed) {
+    ctarget = wid == 0 ? (int)blockIdx.x : A.cn_blk[cn0 + wid - 1];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const unsigned c = lane + 32 * q;
+      erow[q] = c < nb ? A.Einv[(size_t)ctarget * nb + c] : 0.0;
+    }
+  }
+  double rsum = 0.0;  // this thread's share of the block sum of r (restriction)
   // ---- init ------------------------------------------------------------------------
   for (long long v = v0 + tid; v < v1; v += T) {
     double rin[FB_MAX_NS], zo[FB_MAX_NS];
@@ -487,16 +645,27 @@ k_cg_persistent(DevSpec S, CgArgs A) {
       rin[sp] = A.b[i];
       A.r[i] = rin[sp]; A.x[i] = 0.0; A.p[i] = 0.0; A.s[i] = 0.0;
     }
+    if (coarse && rfree[v - v0]) rsum += rin[0];
     bjacobi_apply(ns, A.dinv, v, rin, zo);
     for (int sp = 0; sp < ns; ++sp) {
       A.u[v * ns + sp] = zo[sp];
       if (cached) su[(v - v0) * ns + sp] = zo[sp];
     }
   }
+  if (coarse) {  // (rfree[rr] is always read by the thread that staged it)
+    rsum = warp_sum(rsum);
+    if (lane == 0) red[0][wid] = rsum;
+    __syncthreads();
+    if (wid == 0) {
+      double sacc = lane < nw ? red[0][lane] : 0.0;
+      sacc = warp_sum(sacc);
+      if (lane == 0) A.rc[blockIdx.x] = sacc;
+    }
+  }
   unsigned gen = 0;
   const unsigned base_count = A.bar_base;
   if (!grid_barrier(A.bar, nb, gen, base_count)) return;
-  double alpha = 0.0, beta = 0.0, gamma_old = 0.0;
+  double alpha = 0.0, beta = 0.0, gamma_old = 0.0, thr2 = A.thr2;
   int it = 0, done = 0, breakdown = 0;
   const int ngroups = T / G, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
@@ -504,11 +673,59 @@ k_cg_persistent(DevSpec S, CgArgs A) {
   long long tph[5] = {0, 0, 0, 0, 0};  // cycles per phase (block 0), reported in sc[8..12]
   while (true) {
     long long c0 = clock64();
+    // ---- coarse correction: u = D^-1 r + Z E^-1 Z^T r -------------------------------------
+    double hval0 = 0.0;
+    int hb0 = FB_COARSE_NONE;
+    if (coarse && tid < nhalo) {  // first halo value per thread in flight during the coarse solve
+      hval0 = __ldcg(uvec + hidx[tid]);
+      hb0 = hblk[tid];
+    }
+    if (coarse) {
+      // one warp fetches the restricted residual (148 blocks polling the same 10 sectors
+      // from every warp would serialise in one L2 slice)
+      if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const unsigned c = lane + 32 * q;
+          if (c < nb) rcs[c] = __ldcg(A.rc + c);
+        }
+      }
+      __syncthreads();
+      for (int k = wid; k < nneed; k += nw) {
+        double d = 0.0;
+        int tb = ctarget;
+        if (k == wid) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const unsigned c = lane + 32 * q;
+            if (c < nb) d += erow[q] * rcs[c];
+          }
+        } else {  // more neighbours than warps: rows from L2
+          tb = A.cn_blk[cn0 + k - 1];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const unsigned c = lane + 32 * q;
+            if (c < nb) d += A.Einv[(size_t)tb * nb + c] * rcs[c];
+          }
+        }
+        d = warp_sum(d);
+        if (lane == 0) ysm[tb] = d;
+      }
+      __syncthreads();
+      const double yself = ysm[blockIdx.x];
+      for (int rr = tid; rr < nrows; rr += T)
+        if (rfree[rr]) su[rr] += yself;
+    }
     // ---- halo of the iterate into shared memory ---------------------------------------
     if (cached) {
-      for (int h = tid; h < nhalo * ns; h += T) {
-        const int hv = h / ns, sp = h - hv * ns;
-        su[nrows + h] = __ldcg(uvec + (long long)hidx[hv] * ns + sp);
+      if (coarse) {
+        if (tid < nhalo) su[nrows + tid] = hval0 + ysm[hb0];
+        for (int h = tid + T; h < nhalo; h += T) su[nrows + h] = __ldcg(uvec + hidx[h]) + ysm[hblk[h]];
+      } else {
+        for (int h = tid; h < nhalo * ns; h += T) {
+          const int hv = h / ns, sp = h - hv * ns;
+          su[nrows + h] = __ldcg(uvec + (long long)hidx[hv] * ns + sp);
+        }
       }
       __syncthreads();
     }
@@ -581,10 +798,10 @@ k_cg_persistent(DevSpec S, CgArgs A) {
       if (lane == 0) red[k][wid] = sred;
     }
     __syncthreads();
-    if (tid < 3) {
-      double sacc = 0.0;
-      for (int q = 0; q < nw; ++q) sacc += red[tid][q];
-      A.partials[(size_t)tid * nb + blockIdx.x] = sacc;
+    if (wid < 3) {
+      double sacc = lane < nw ? red[wid][lane] : 0.0;
+      sacc = warp_sum(sacc);
+      if (lane == 0) A.partials[(size_t)wid * nb + blockIdx.x] = sacc;
     }
     long long c1 = clock64();
     if (!grid_barrier(A.bar, nb, gen, base_count)) return;
@@ -598,7 +815,8 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     }
     __syncthreads();
     const double gamma_new = tot[0], delta = tot[1], uu = tot[2];
-    if (uu <= A.thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
+    if (it == 0 && A.Einv != nullptr) thr2 = A.rel2 * uu;  // relative to ||M^-1 b|| of this M
+    if (uu <= thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
     else if (it >= A.max_it) { done = 2; }
     else {
       if (it == 0) { beta = 0.0; alpha = gamma_new / delta; }
@@ -616,6 +834,7 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     ++it;
     long long c3 = clock64();
     // ---- phase A: vector update on owned vertices ------------------------------------------
+    rsum = 0.0;
     for (long long v = v0 + tid; v < v1; v += T) {
       double rin[FB_MAX_NS], zo[FB_MAX_NS];
       for (int sp = 0; sp < ns; ++sp) {
@@ -630,10 +849,21 @@ k_cg_persistent(DevSpec S, CgArgs A) {
         rin[sp] = ri - alpha * si;
         A.r[i] = rin[sp];
       }
+      if (coarse && rfree[v - v0]) rsum += rin[0];
       bjacobi_apply(ns, A.dinv, v, rin, zo);
       for (int sp = 0; sp < ns; ++sp) {
         A.u[v * ns + sp] = zo[sp];
         if (cached) su[(v - v0) * ns + sp] = zo[sp];
+      }
+    }
+    if (coarse) {
+      rsum = warp_sum(rsum);
+      if (lane == 0) red[0][wid] = rsum;
+      __syncthreads();
+      if (wid == 0) {
+        double sacc = lane < nw ? red[0][lane] : 0.0;
+        sacc = warp_sum(sacc);
+        if (lane == 0) A.rc[blockIdx.x] = sacc;
       }
     }
     long long c4 = clock64();
@@ -935,7 +1165,30 @@ static int read_flags(fb_ctx* ctx, int* out4) {
   return 0;
 }
 
-static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, double* y, double thr2,
+// E = Z^T J Z and its inverse for the two-level preconditioner (once per matrix)
+static int coarse_setup(fb_ctx* ctx, const double* J) {
+  ctx->coarse_ready = false;
+  if (!ctx->d_coarse || ctx->part_min_rows <= 0 || ctx->part_blocks > GJ_MAX || getenv("FB_NO_COARSE") || getenv("FB_NO_SM_PARTITION") ||
+      getenv("FB_NO_SMEM_OPERATOR") || getenv("FB_CG_MULTIKERNEL"))
+    return 0;
+  const int nb = ctx->part_blocks;
+  if (ctx->coarse_masks_dirty) {
+    const int nh = ctx->part_nhalo;
+    if (nh > 0)
+      FB_LAUNCH(ctx, k_coarse_halo_blocks, (unsigned)((nh + 255) / 256), 256, 0, nh, ctx->d_halo_idx, ctx->d_halo_blk,
+                (const int*)ctx->d_bc_map, ctx->d_halo_blk_eff);
+    ctx->coarse_masks_dirty = false;
+  }
+  double* E = ctx->d_coarse;
+  double* Einv = E + (size_t)nb * nb;
+  FB_LAUNCH(ctx, k_coarse_build, nb, 1024, 0, ctx->S, J, ctx->d_blk_rng, ctx->d_lcol, ctx->d_cn_ptr, ctx->d_cn_blk,
+            ctx->d_cn_eptr, ctx->d_cn_ent, E);
+  FB_LAUNCH(ctx, k_coarse_invert, 1, GJ_THREADS, 0, nb, (const double*)E, Einv);
+  ctx->coarse_ready = true;
+  return 0;
+}
+
+static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, double* y, double thr2, double rel2,
                                int max_it, int* iters) {
   const DevSpec& S = ctx->S;
   int rc = ensure_vectors(ctx, 5);
@@ -956,10 +1209,11 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
   {
     int v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    smem_max = (size_t)v - 1024;  // static shared (reduction scratch)
+    smem_max = (size_t)v - 3584;  // static shared (reduction scratch, coarse solution)
   }
   A.blk_rng = nullptr; A.halo_ptr = nullptr; A.halo_idx = nullptr; A.lcol = nullptr;
   A.su_doubles = 0; A.bentries = 0; A.rows_cap = 0;
+  A.Einv = nullptr; A.rc = nullptr; A.halo_blk = nullptr; A.cn_ptr = nullptr; A.cn_blk = nullptr; A.rel2 = rel2;
   size_t smem = 0;
   const bool no_smem = getenv("FB_NO_SMEM_OPERATOR") != nullptr;
   if (ctx->part_blocks == (int)nb && !getenv("FB_NO_SM_PARTITION")) {
@@ -970,10 +1224,14 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
     const long long su = (ctx->part_max_su + 1) & ~1LL;
     const long long be = (ctx->part_max_bentries + 1) & ~1LL;
     const long long rows = ctx->part_max_rows;
-    const size_t need = (size_t)(8 * cap + 8 * su + 2 * be + 12 * rows + 16);
+    const size_t need = (size_t)(8 * cap + 8 * su + 2 * be + 13 * rows + 32);
     if (need <= smem_max && !no_smem) {
       A.rows_in_smem = 1; A.smem_entries = cap; A.su_doubles = su; A.bentries = be; A.rows_cap = rows;
       smem = need;
+      if (ctx->coarse_ready) {  // every block has its rows on chip: two-level preconditioner
+        A.Einv = ctx->d_coarse + (size_t)nb * nb; A.rc = ctx->d_coarse + (size_t)2 * nb * nb;
+        A.halo_blk = ctx->d_halo_blk_eff; A.cn_ptr = ctx->d_cn_ptr; A.cn_blk = ctx->d_cn_blk;
+      }
     } else {
       A.rows_in_smem = 0; A.smem_entries = 0;
     }
@@ -1019,8 +1277,8 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
   if (getenv("FB_VERBOSE") && fl[1] > 0) {
     double ph[5];
     FB_CHECK(ctx, cudaMemcpy(ph, ctx->d_sc + 8, sizeof(ph), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[fb] persistent CG G=%d smem=%d: cycles/iteration spmv+dots %.0f, barrier %.0f, reduce %.0f, "
-            "update %.0f, barrier %.0f\n", G, A.rows_in_smem, ph[0] / fl[1], ph[1] / fl[1], ph[2] / fl[1],
+    fprintf(stderr, "[fb] persistent CG G=%d smem=%d coarse=%d its=%d: cycles/iteration spmv+dots %.0f, barrier %.0f, reduce %.0f, "
+            "update %.0f, barrier %.0f\n", G, A.rows_in_smem, A.Einv != nullptr, fl[1], ph[0] / fl[1], ph[1] / fl[1], ph[2] / fl[1],
             ph[3] / fl[1], ph[4] / fl[1]);
   }
   if (fl[2]) return 1;
@@ -1161,6 +1419,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   }
   const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
   FB_LAUNCH(ctx, k_bjacobi_setup, gn, FB_TPB, 0, S, J, ctx->d_dinv, ctx->d_flags);
+  if (ksp == FB_KSP_CG && (rc = coarse_setup(ctx, J))) return rc;
   // stopping rule on the preconditioned residual, ||M^-1 r|| <= max(rtol ||M^-1 b||, atol)
   // (PETSc default for left-preconditioned CG/GMRES); block-Jacobi makes it row-scaled,
   // which matters when species equations differ by many orders of magnitude
@@ -1183,7 +1442,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
     int its = 0;
     const double* rhs = b;
     double* sol = y;
-    double thr_r = thr;
+    double thr_r = thr, rel = thr / pbnorm;
     if (round > 0) {
       // correction equation J d = b - J y, solved to 1e-3 of its own preconditioned norm
       rhs = t; sol = corr;
@@ -1191,10 +1450,20 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
       double pn;
       if ((rc = fbi_norm2(ctx, corr, &pn))) return rc;
       thr_r = 1e-3 * pn;
+      rel = 1e-3;
     }
-    if (ksp == FB_KSP_CG)
-      status = getenv("FB_CG_MULTIKERNEL") ? solve_cg(ctx, J, rhs, sol, thr_r * thr_r, max_it, &its)
-                                           : solve_cg_persistent(ctx, J, rhs, sol, thr_r * thr_r, max_it, &its);
+    if (ksp == FB_KSP_CG) {
+      if (getenv("FB_CG_MULTIKERNEL")) {
+        status = solve_cg(ctx, J, rhs, sol, thr_r * thr_r, max_it, &its);
+      } else {
+        status = solve_cg_persistent(ctx, J, rhs, sol, thr_r * thr_r, rel * rel, max_it, &its);
+        if (status == 1 && ctx->coarse_ready) {  // singular coarse operator: one-level fallback
+          ctx->coarse_ready = false;
+          *iters += its;
+          status = solve_cg_persistent(ctx, J, rhs, sol, thr_r * thr_r, rel * rel, max_it, &its);
+        }
+      }
+    }
     else status = solve_gmres(ctx, J, rhs, sol, thr_r, max_it, &its);
     *iters += its;
     if (status < 0) return status;

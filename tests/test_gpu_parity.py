@@ -249,3 +249,37 @@ def test_non_homogeneous_density_parity(name):
     assert gm.timesteps == rm.timesteps
     assert np.abs(np.array(tg.data) - np.array(tr.data)).max() <= 1e-6 * np.abs(np.array(tr.data)).max()
     assert _rel(gm.u.x.array, rm.u.x.array) < 1e-8
+
+
+@pytest.mark.parametrize("n", [4, 16])
+def test_cg_two_level_preconditioner(n, monkeypatch):
+    """Persistent CG: block-Jacobi + per-SM coarse space against block-Jacobi alone and
+    against scipy's direct solve of the same assembled system.  n=4 has fewer vertices than
+    SMs (empty blocks): the coarse space must switch itself off."""
+    import ctypes as C
+
+    import scipy.sparse.linalg as spl
+
+    (gm, _, _), _ = _pair(mms_1_mobile_steady, 3, n)
+    s = gm.solver
+    ctx = s.ctx
+    s._push_state()
+    Fg, Jg = s.assemble_host(want_J=True)
+    ref = spl.spsolve(Jg.tocsc(), Fg)
+    u = ctx.nodal_to_device("u", gm.u.x.array, 1)
+    Fd, Jd, yd = ctx.zeros(ctx.n_dofs), ctx.zeros(ctx.nnz), ctx.zeros(ctx.n_dofs)
+    ctx._check(ctx.lib.fb_assemble(ctx.h, ctx.ptr(u), ctx.ptr(u), ctx.ptr(Fd), ctx.ptr(Jd), 3))
+    sols, iters = [], []
+    for no_coarse in (False, True):
+        if no_coarse:
+            monkeypatch.setenv("FB_NO_COARSE", "1")
+        its, rr = C.c_int(0), C.c_double(0)
+        ctx._check(ctx.lib.fb_linear_solve(ctx.h, ctx.ptr(Jd), ctx.ptr(Fd), ctx.ptr(yd), 1, 0, 1e-12, 0.0, 4000,
+                                           C.byref(its), C.byref(rr)))
+        sols.append(ctx.nodal_from_device(yd))
+        iters.append(its.value)
+        assert rr.value < 1e-11
+    assert _rel(sols[0], sols[1]) < 1e-9
+    assert _rel(sols[0], ref) < 1e-9
+    if n == 16:
+        assert iters[0] < iters[1]

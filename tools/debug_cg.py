@@ -26,6 +26,8 @@ for mode in sys.argv[4].split(","):
     os.environ.pop("FB_NO_SM_PARTITION", None)
     if mode == "persistent-nosmem": os.environ["FB_NO_SMEM_OPERATOR"] = "1"
     if mode == "persistent-range": os.environ["FB_NO_SM_PARTITION"] = "1"
+    os.environ.pop("FB_NO_COARSE", None)
+    if mode == "persistent-nocoarse": os.environ["FB_NO_COARSE"] = "1"
     its = C.c_int(0); rr = C.c_double(0)
     log("solve", mode)
     t1 = time.time()
