@@ -78,6 +78,10 @@ def load_library():
         "fb_bjacobi_setup": (i, [vp, vp]),
         "fb_precond": (i, [vp, vp, vp]),
         "fb_dcg_init": (i, [vp, vp, vp, vp, vp, vp, vp]),
+        "fb_peer_alloc": (i, [vp, i, i, vp]),
+        "fb_peer_open": (i, [vp, i, vp]),
+        "fb_peer_set_send": (i, [vp, i64, vp, vp, vp]),
+        "fb_dcg_persistent": (i, [vp, vp, vp, vp, C.c_double, i, vp, vp]),
         "fb_dcg_spmv_dots": (i, [vp, vp, vp, vp, vp, vp]),
         "fb_dcg_update": (i, [vp, d, d, vp, vp, vp, vp, vp, vp]),
         "fb_dcg_scalars": (i, [vp, vp, vp, i]),
@@ -99,6 +103,7 @@ EXPORTED_SYMBOLS = [
     "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
     "fb_total_surface", "fb_surface_flux", "fb_set_owned", "fb_set_sm_partition",
     "fb_bjacobi_setup", "fb_precond",
+    "fb_peer_alloc", "fb_peer_open", "fb_peer_set_send", "fb_dcg_persistent",
     "fb_dcg_init", "fb_dcg_spmv_dots", "fb_dcg_update", "fb_dcg_scalars", "fb_dcg_update_dev",
 ]
 

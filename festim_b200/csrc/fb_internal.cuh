@@ -37,6 +37,14 @@ struct fb_ctx {
   const int* d_halo_idx = nullptr;
   const unsigned short* d_lcol = nullptr;
   long long part_max_entries = 0, part_max_bentries = 0, part_max_su = 0, part_max_rows = 0, part_min_rows = 0;
+  // peer-memory exchange area of the partitioned persistent CG (fb_peer_*)
+  double* d_xchg = nullptr;            // [0,64) reduction slots, [64,80) arrival flags, [128,..) iterate u
+  long long xchg_u_doubles = 0;
+  void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int peer_rank = 0, peer_n = 0;
+  unsigned long long peer_epoch = 0;
+  const int* d_send_v = nullptr; const int* d_send_rank = nullptr; const int* d_send_dst = nullptr;
+  int n_send = 0;
   bool symmetric = false;
   bool facet_u_terms = false;  // any solution-dependent facet term
   bool generic_u_vterms = false;  // any solution-dependent volume term evaluated point-wise

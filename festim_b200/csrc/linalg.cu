@@ -1508,6 +1508,279 @@ k_dcg_update(DevSpec S, const double* __restrict__ dinv, double alpha, double be
   for (int s = 0; s < S.ns; ++s) u[v * S.ns + s] = zo[s];
 }
 
+// ---------------------------------------------------------------------------
+// Partitioned persistent CG over peer memory (NVLink / NVSwitch).  One cooperative
+// launch per rank runs the whole solve; ranks meet at the two synchronisation points
+// of the single-reduction recurrence through flags in each other's memory:
+//   * halo: after the vector update every block PUSHES the entries of u that other
+//     ranks hold as ghosts straight into their iterate (remote stores, no round trip);
+//   * reduction: the last block to arrive at the local grid barrier sums the rank's
+//     partial dot products, stores the three totals into a slot of EVERY rank's
+//     exchange area, raises its flag there (st.release.sys) and waits for the flags of
+//     the other ranks before it opens the local barrier.
+// Every rank adds the per-rank totals in rank order, so all ranks take bit-identical
+// decisions (convergence, breakdown) and leave together.  No NCCL call, no host
+// round trip inside the solve.
+// ---------------------------------------------------------------------------
+#define FB_XR 0       // exchange area: reduction slots [2 parities][8 ranks][4]
+#define FB_XFLAG 64   // arrival flags [8] (u64)
+#define FB_XU 128     // iterate (owned + ghost entries)
+struct PeerArgs {
+  int rank, nranks;
+  unsigned long long epoch;   // high half of the flag values: stale flags of earlier solves never match
+  double* base[8];            // exchange area of every rank (own one included)
+  const int* send_v; const int* send_rank; const int* send_dst; int n_send;  // sorted by send_v
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Local grid barrier + cross-rank rendezvous, run by warp 0 of every block.  with_data:
+// the rank's partial dot products (partials[3][nblocks]) are summed and published.
+__device__ __forceinline__ bool xgrid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen, unsigned base_count,
+                                              const PeerArgs& P, const double* partials, bool with_data) {
+  __shared__ int xok_s;
+  __syncthreads();
+  ++gen;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned old = 0;
+    if (lane == 0) old = atom_add_release_u32(bar, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    int ok = 1;
+    if (old - base_count == gen * nblocks - 1u) {  // last block of this rank
+      const unsigned long long tag = (P.epoch << 32) | gen;
+      double t[3] = {0.0, 0.0, 0.0};
+      if (with_data) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double sacc = 0.0;
+          for (unsigned b = lane; b < nblocks; b += 32) sacc += __ldcg(partials + (size_t)k * nblocks + b);
+          t[k] = warp_sum(sacc);
+        }
+      }
+      if (lane < P.nranks) {
+        if (with_data) {
+          volatile double* dst = P.base[lane] + FB_XR + (((gen >> 1) & 1u) * 8 + P.rank) * 4;
+          dst[0] = t[0]; dst[1] = t[1]; dst[2] = t[2];
+        }
+        __threadfence_system();
+        st_release_sys_u64((unsigned long long*)(P.base[lane] + FB_XFLAG) + P.rank, tag);
+        const unsigned long long* mine = (const unsigned long long*)(P.base[P.rank] + FB_XFLAG) + lane;
+        unsigned spins = 0;
+        while (ld_acquire_sys_u64(mine) < tag) {
+          __nanosleep(32);
+          if ((++spins & 0xfffu) == 0u) {
+            if (spins > (1u << 23) || ld_acquire_u32(bar + 64)) { atomicExch(bar + 64, 1u); ok = 0; break; }
+          }
+        }
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      if (lane == 0) st_release_u32(bar + 32, gen);  // opens the local barrier (also on failure: bar[64] is set)
+    } else if (lane == 0) {
+      unsigned spins = 0;
+      while (ld_acquire_u32(bar + 32) != gen) {
+        __nanosleep(64);
+        if ((++spins & 0xfffu) == 0u) {
+          if (spins > (1u << 24)) { atomicExch(bar + 64, 1u); ok = 0; break; }
+          if (ld_acquire_u32(bar + 64)) { ok = 0; break; }
+        }
+      }
+      if (ok && ld_acquire_u32(bar + 64)) ok = 0;
+    }
+    if (lane == 0) xok_s = ok;
+  }
+  __syncthreads();
+  return xok_s != 0;
+}
+
+template <int G>
+__global__ void __launch_bounds__(1024, 1)
+k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[3][32];
+  __shared__ double tot[3];
+  __shared__ int srange[2];
+  const int ns = S.ns;
+  const unsigned nb = gridDim.x;
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  const long long n_own = S.n_owned;
+  const long long vper = (n_own + nb - 1) / nb;
+  const long long v0 = (long long)blockIdx.x * vper < n_own ? (long long)blockIdx.x * vper : n_own;
+  const long long v1 = (v0 + vper < n_own) ? v0 + vper : n_own;
+  const int nrows = (int)(v1 - v0) * ns;
+  const long long row0 = v0 * ns;
+  double* const uvec = P.base[P.rank] + FB_XU;  // owned entries written here, ghost entries by the peers
+  // operator rows of this block in shared memory when they fit: vals | cols | rstart | rlen
+  double* svals = (double*)smem_raw;
+  int* scols = (int*)(svals + A.smem_entries);
+  int* rstart = scols + A.smem_entries;
+  int* rlen = rstart + vper * ns;
+  bool staged = false;
+  if (A.rows_in_smem && nrows > 0) {
+    const long long e0 = (long long)S.rowptr[v0] * S.npairs, e1 = (long long)S.rowptr[v1] * S.npairs;
+    staged = (e1 - e0) <= A.smem_entries;
+    if (staged) {
+      for (long long e = tid; e < e1 - e0; e += T) svals[e] = A.J[e0 + e];
+      for (int rr = tid; rr < nrows; rr += T) {
+        const int vl = rr / ns, sp = rr - vl * ns;
+        const long long v = v0 + vl;
+        const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+        const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
+        const int start = (int)((long long)r0 * S.npairs + (long long)deg * pp - e0);
+        rstart[rr] = start;
+        rlen[rr] = deg * nc;
+        for (int e = 0; e < deg * nc; ++e) {
+          const int k = e / nc, j = e - k * nc;
+          scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
+        }
+      }
+    }
+  }
+  // this block's slice of the send table (entries sorted by owned vertex)
+  if (tid < 2) {
+    const long long key = tid == 0 ? v0 : v1;
+    int lo = 0, hi = P.n_send;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.send_v[mid] < key) lo = mid + 1; else hi = mid; }
+    srange[tid] = lo;
+  }
+  // ---- init ------------------------------------------------------------------------
+  for (long long v = v0 + tid; v < v1; v += T) {
+    double rin[FB_MAX_NS], zo[FB_MAX_NS];
+    for (int sp = 0; sp < ns; ++sp) {
+      const long long i = v * ns + sp;
+      rin[sp] = A.b[i];
+      A.r[i] = rin[sp]; A.x[i] = 0.0; A.p[i] = 0.0; A.s[i] = 0.0;
+    }
+    bjacobi_apply(ns, A.dinv, v, rin, zo);
+    for (int sp = 0; sp < ns; ++sp) uvec[v * ns + sp] = zo[sp];
+  }
+  __syncthreads();
+  const int s0 = srange[0], s1 = srange[1];
+  for (int q = s0 + tid; q < s1; q += T) {
+    double* dst = P.base[P.send_rank[q]] + FB_XU + (long long)P.send_dst[q] * ns;
+    const long long src = (long long)P.send_v[q] * ns;
+    for (int sp = 0; sp < ns; ++sp) dst[sp] = uvec[src + sp];
+  }
+  if (s1 > s0) __threadfence_system();
+  unsigned gen = 0;
+  const unsigned base_count = A.bar_base;
+  if (!xgrid_barrier(A.bar, nb, gen, base_count, P, A.partials, false)) return;
+  double alpha = 0.0, beta = 0.0, gamma_old = 0.0;
+  int it = 0, done = 0, breakdown = 0;
+  const int ngroups = T / G, grp = tid / G, gl = tid % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  while (true) {
+    // ---- phase B: w = A u on owned rows + partial dots -----------------------------------
+    double v3[3] = {0.0, 0.0, 0.0};
+    for (int rr = grp; rr < nrows; rr += ngroups) {
+      double sum = 0.0;
+      const long long row = row0 + rr;
+      const double ri = __ldcg(A.r + row), ui = __ldcg(uvec + row);
+      if (staged) {
+        const int a0 = rstart[rr], n = rlen[rr];
+        for (int eb = gl; eb < n; eb += 8 * G) {
+          double uv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int e = eb + q * G;
+            uv[q] = e < n ? __ldcg(uvec + scols[a0 + e]) : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int e = eb + q * G;
+            if (e < n) sum += svals[a0 + e] * uv[q];
+          }
+        }
+      } else {
+        const int vl = rr / ns, sp = rr - vl * ns;
+        const long long v = v0 + vl;
+        const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+        const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
+        const double* __restrict__ vals = A.J + (long long)r0 * S.npairs + (long long)deg * pp;
+        const int n = deg * nc;
+        for (int e = gl; e < n; e += G) {
+          const int k = e / nc, j = e - k * nc;
+          sum += vals[e] * __ldcg(uvec + (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]);
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
+      if (gl == 0) {
+        A.w[row] = sum;
+        v3[0] += ri * ui; v3[1] += sum * ui; v3[2] += ui * ui;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double sred = warp_sum(v3[k]);
+      if (lane == 0) red[k][wid] = sred;
+    }
+    __syncthreads();
+    if (wid < 3) {
+      double sacc = lane < nw ? red[wid][lane] : 0.0;
+      sacc = warp_sum(sacc);
+      if (lane == 0) A.partials[(size_t)wid * nb + blockIdx.x] = sacc;
+    }
+    if (!xgrid_barrier(A.bar, nb, gen, base_count, P, A.partials, true)) return;
+    // ---- totals over ranks, same order everywhere ------------------------------------------
+    if (tid < 3) {
+      const double* xr = P.base[P.rank] + FB_XR + ((gen >> 1) & 1u) * 32;
+      double sacc = 0.0;
+      for (int q = 0; q < P.nranks; ++q) sacc += __ldcg(xr + q * 4 + tid);
+      tot[tid] = sacc;
+    }
+    __syncthreads();
+    const double gamma_new = tot[0], delta = tot[1], uu = tot[2];
+    if (uu <= A.thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
+    else if (it >= A.max_it) { done = 2; }
+    else {
+      if (it == 0) { beta = 0.0; alpha = gamma_new / delta; }
+      else { beta = gamma_new / gamma_old; alpha = gamma_new / (delta - beta * gamma_new / alpha); }
+      if (!(alpha == alpha) || isinf(alpha)) { done = 1; breakdown = 1; }
+      gamma_old = gamma_new;
+    }
+    if (done) {
+      if (blockIdx.x == 0 && tid == 0) {
+        A.flags[0] = (done == 1); A.flags[1] = it; A.flags[2] = breakdown; A.sc[3] = uu;
+      }
+      break;
+    }
+    ++it;
+    // ---- phase A: vector update on owned vertices, then push the boundary entries ----------
+    for (long long v = v0 + tid; v < v1; v += T) {
+      double rin[FB_MAX_NS], zo[FB_MAX_NS];
+      for (int sp = 0; sp < ns; ++sp) {
+        const long long i = v * ns + sp;
+        const double ui = __ldcg(uvec + i), wi = __ldcg(A.w + i), ri = __ldcg(A.r + i);
+        const double p_old = __ldcg(A.p + i), s_old = __ldcg(A.s + i), x_old = __ldcg(A.x + i);
+        const double pi = ui + beta * p_old;
+        const double si = wi + beta * s_old;
+        A.p[i] = pi; A.s[i] = si;
+        A.x[i] = x_old + alpha * pi;
+        rin[sp] = ri - alpha * si;
+        A.r[i] = rin[sp];
+      }
+      bjacobi_apply(ns, A.dinv, v, rin, zo);
+      for (int sp = 0; sp < ns; ++sp) uvec[v * ns + sp] = zo[sp];
+    }
+    __syncthreads();
+    for (int q = s0 + tid; q < s1; q += T) {
+      double* dst = P.base[P.send_rank[q]] + FB_XU + (long long)P.send_dst[q] * ns;
+      const long long src = (long long)P.send_v[q] * ns;
+      for (int sp = 0; sp < ns; ++sp) dst[sp] = uvec[src + sp];
+    }
+    if (s1 > s0) __threadfence_system();
+    if (!xgrid_barrier(A.bar, nb, gen, base_count, P, A.partials, false)) return;  // also protects tot[]
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(FB_TPB)
 k_dcg_spmv_dots(DevSpec S, const double* __restrict__ J, const double* __restrict__ u,
@@ -1632,5 +1905,127 @@ extern "C" int fb_dcg_update_dev(fb_ctx* ctx, const double* state_dev, double* x
   const DevSpec& S = ctx->S;
   FB_LAUNCH(ctx, k_dcg_update_dev, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, ctx->d_dinv,
             state_dev, x, r, u, w, p, s);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Peer-memory setup and launch of the partitioned persistent CG (k_dcg_persistent).
+// ---------------------------------------------------------------------------
+extern "C" int fb_peer_alloc(fb_ctx* ctx, int rank, int nranks, unsigned char* handle64) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fb_fail(ctx, "1..8 ranks on one node");
+  cudaSetDevice(ctx->device);
+  if (!ctx->d_xchg) {
+    ctx->xchg_u_doubles = ctx->S.n_dofs;
+    const size_t n = (size_t)FB_XU + (size_t)ctx->xchg_u_doubles;
+    int rc = fb_alloc(ctx, &ctx->d_xchg, n);  // its own cudaMalloc block: exportable as a whole
+    if (rc) return rc;
+    FB_CHECK(ctx, cudaMemset(ctx->d_xchg, 0, n * sizeof(double)));
+  }
+  ctx->peer_rank = rank;
+  ctx->peer_n = nranks;
+  for (int q = 0; q < 8; ++q) ctx->peer_base[q] = nullptr;
+  ctx->peer_base[rank] = ctx->d_xchg;
+  if (handle64) {
+    cudaIpcMemHandle_t h;
+    FB_CHECK(ctx, cudaIpcGetMemHandle(&h, ctx->d_xchg));
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+  }
+  return 0;
+}
+
+extern "C" int fb_peer_open(fb_ctx* ctx, int peer, const unsigned char* handle64) {
+  if (!ctx || !ctx->d_xchg) return ctx ? fb_fail(ctx, "fb_peer_alloc first") : -1;
+  if (peer < 0 || peer >= ctx->peer_n) return fb_fail(ctx, "peer rank out of range");
+  if (peer == ctx->peer_rank) return 0;
+  cudaSetDevice(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  FB_CHECK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->peer_base[peer] = p;
+  return 0;
+}
+
+// send table: owned vertex v (local numbering) is ghost vertex dst of rank `rank`; sorted by v
+extern "C" int fb_peer_set_send(fb_ctx* ctx, int64_t n, const int32_t* v, const int32_t* rank, const int32_t* dst) {
+  if (!ctx || !ctx->d_xchg) return ctx ? fb_fail(ctx, "fb_peer_alloc first") : -1;
+  cudaSetDevice(ctx->device);
+  for (int64_t i = 0; i < n; ++i) {
+    if (v[i] < 0 || v[i] >= ctx->S.n_owned) return fb_fail(ctx, "send vertex is not owned");
+    if (rank[i] < 0 || rank[i] >= ctx->peer_n || rank[i] == ctx->peer_rank) return fb_fail(ctx, "bad destination rank");
+    if (i && v[i] < v[i - 1]) return fb_fail(ctx, "send table must be sorted by vertex");
+  }
+  int rc;
+  if ((rc = fb_upload(ctx, &ctx->d_send_v, (const int*)v, (size_t)n))) return rc;
+  if ((rc = fb_upload(ctx, &ctx->d_send_rank, (const int*)rank, (size_t)n))) return rc;
+  if ((rc = fb_upload(ctx, &ctx->d_send_dst, (const int*)dst, (size_t)n))) return rc;
+  ctx->n_send = (int)n;
+  return 0;
+}
+
+extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, double* x, double thr2,
+                                 int max_it, int* iters, int* converged) {
+  if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
+  if (!ctx->d_xchg) return fb_fail(ctx, "fb_peer_alloc first");
+  for (int q = 0; q < ctx->peer_n; ++q)
+    if (!ctx->peer_base[q]) return fb_fail(ctx, "fb_peer_open for every rank first");
+  cudaSetDevice(ctx->device);
+  const DevSpec& S = ctx->S;
+  int rc = fbi_ensure_workspace(ctx);
+  if (rc) return rc;
+  if ((rc = ensure_vectors(ctx, 5))) return rc;
+  const long long N = S.n_dofs;
+  CgArgs A;
+  memset(&A, 0, sizeof(A));
+  A.J = J; A.dinv = ctx->d_dinv; A.b = b; A.x = x;
+  A.r = ctx->d_work; A.u = nullptr; A.w = A.r + 2 * N; A.p = A.w + N; A.s = A.p + N;
+  A.partials = ctx->d_red; A.bar = ctx->d_ticket + 64; A.sc = ctx->d_sc; A.flags = ctx->d_flags;
+  A.thr2 = thr2; A.max_it = max_it;
+  PeerArgs P;
+  memset(&P, 0, sizeof(P));
+  P.rank = ctx->peer_rank; P.nranks = ctx->peer_n; P.epoch = ++ctx->peer_epoch;
+  for (int q = 0; q < 8; ++q) P.base[q] = (double*)ctx->peer_base[q];
+  P.send_v = ctx->d_send_v; P.send_rank = ctx->d_send_rank; P.send_dst = ctx->d_send_dst; P.n_send = ctx->n_send;
+  const long long n_own_dofs = S.n_owned * (long long)S.ns;
+  const double rowlen = (double)ctx->nnzb * S.npairs / (double)N;
+  int G = rowlen <= 20 ? 2 : rowlen <= 40 ? 4 : rowlen <= 80 ? 8 : rowlen <= 160 ? 16 : 32;
+  if (getenv("FB_CG_G")) G = atoi(getenv("FB_CG_G"));
+  const int T = 1024;
+  const unsigned nb = (unsigned)ctx->sm_count;
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+  const size_t smem_max = (size_t)v - 2048;
+  const long long vper = (S.n_owned + nb - 1) / nb;
+  const long long rows_per_block = vper * S.ns;
+  long long cap = ((long long)smem_max - 8 * (rows_per_block + 2)) / 12;
+  cap &= ~1LL;
+  const long long avg_entries = (long long)((double)ctx->nnzb * S.npairs * ((double)n_own_dofs / (double)N) / nb) + 1;
+  A.rows_in_smem = cap >= avg_entries && !getenv("FB_NO_SMEM_OPERATOR");
+  A.smem_entries = A.rows_in_smem ? cap : 0;
+  const size_t smem = A.rows_in_smem ? (size_t)(12 * cap + 8 * (rows_per_block + 2)) : 0;
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(A.bar, 0, 130 * sizeof(unsigned), ctx->stream));
+  A.bar_base = 0u;
+  void* args[] = {(void*)&S, (void*)&A, (void*)&P};
+  const void* fn = nullptr;
+  switch (G) {
+    case 2: fn = (const void*)k_dcg_persistent<2>; break;
+    case 4: fn = (const void*)k_dcg_persistent<4>; break;
+    case 8: fn = (const void*)k_dcg_persistent<8>; break;
+    case 16: fn = (const void*)k_dcg_persistent<16>; break;
+    default: fn = (const void*)k_dcg_persistent<32>; break;
+  }
+  FB_CHECK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FB_CHECK(ctx, cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(T), args, smem, ctx->stream));
+  ctx->launches++;
+  int fl[4];
+  if ((rc = read_flags(ctx, fl))) return rc;
+  unsigned aborted = 0;
+  FB_CHECK(ctx, cudaMemcpy(&aborted, A.bar + 64, 4, cudaMemcpyDeviceToHost));
+  if (aborted) return fb_fail(ctx, "partitioned persistent CG: rendezvous timed out (a rank did not arrive)");
+  *iters = fl[1];
+  *converged = fl[0] && !fl[2];
   return 0;
 }

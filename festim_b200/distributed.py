@@ -275,6 +275,44 @@ class DistributedNewtonSolver:
             bool(os.environ.get("FB_DIST_CUDA_GRAPH"))
         self.cg_iterations = 0
         self.launches_python = 0
+        # whole-solve persistent CG over peer memory (NVLink): default for ranks of one node
+        self.peer = False
+        if self.nranks > 1 and not os.environ.get("FB_NO_PEER_CG"):
+            self._setup_peer()
+
+    def _setup_peer(self):
+        """Exchange CUDA IPC handles of the per-rank exchange areas and build the send
+        table (owned vertex -> ghost slot on the neighbour) of the push-style halo."""
+        from festim_b200.backend import _np_ptr
+
+        ctx, lib, lp, dist = self.ctx, self.ctx.lib, self.part, self.dist
+        if self.nranks > 8:
+            return
+        handle = (C.c_ubyte * 64)()
+        ctx._check(lib.fb_peer_alloc(ctx.h, self.rank, self.nranks, handle))
+        infos = [None] * self.nranks
+        dist.all_gather_object(infos, (bytes(handle), {int(q): seg for q, seg in lp.recv.items()}))
+        for q, (h, _) in enumerate(infos):
+            if q != self.rank:
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                ctx._check(lib.fb_peer_open(ctx.h, q, buf))
+        v, rk, dst = [], [], []
+        for q, idx in lp.send.items():
+            a, b = infos[q][1][self.rank]          # my segment of q's ghost block
+            assert b - a == len(idx), "send list and the neighbour's ghost segment disagree"
+            v.append(np.asarray(idx, dtype=np.int64))
+            rk.append(np.full(len(idx), q, dtype=np.int64))
+            dst.append(np.arange(a, b, dtype=np.int64))
+        if v:
+            v, rk, dst = np.concatenate(v), np.concatenate(rk), np.concatenate(dst)
+            order = np.argsort(v, kind="stable")
+            v, rk, dst = (np.ascontiguousarray(x[order], dtype=np.int32) for x in (v, rk, dst))
+        else:
+            v = rk = dst = np.zeros(0, dtype=np.int32)
+        ctx._check(lib.fb_peer_set_send(ctx.h, len(v), _np_ptr(v, C.c_int32), _np_ptr(rk, C.c_int32),
+                                        _np_ptr(dst, C.c_int32)))
+        dist.barrier()                              # every rank has mapped every exchange area
+        self.peer = True
 
     # ---- data movement -----------------------------------------------------------
     def _push_state(self):
@@ -334,6 +372,12 @@ class DistributedNewtonSolver:
         ctx._check(lib.fb_bjacobi_setup(ctx.h, ptr(J)))
         ctx._check(lib.fb_precond(ctx.h, ptr(b), ptr(self.tmp)))
         thr2 = (rtol * self._norm(self.tmp)) ** 2
+        if self.peer:
+            its, conv = C.c_int(0), C.c_int(0)
+            ctx._check(lib.fb_dcg_persistent(ctx.h, ptr(J), ptr(b), ptr(x), float(thr2), int(max_it),
+                                             C.byref(its), C.byref(conv)))
+            self.cg_iterations += its.value
+            return its.value, bool(conv.value)
         r, u, w, p, s = self.r, self.uv, self.w, self.p, self.s
         ctx._check(lib.fb_dcg_init(ctx.h, ptr(b), ptr(x), ptr(r), ptr(u), ptr(p), ptr(s)))
         self._max_it = max_it

@@ -177,6 +177,25 @@ int fb_dcg_scalars(fb_ctx* ctx, const double* reduced3 /*[dev]*/, double* state 
 int fb_dcg_update_dev(fb_ctx* ctx, const double* state /*[dev]*/, double* x, double* r, double* u,
                       const double* w, double* p, double* s);
 
+/* -- partitioned persistent CG over peer memory (NVLink / NVSwitch, ranks of one node).
+ *    Replaces, for the whole Krylov solve, what PETSc does per iteration with
+ *    VecScatter ghost updates and MPI_Allreduce (reference: KSPSolve inside
+ *    NonlinearProblem.solve, src/festim/problem.py:262-289): one cooperative launch per
+ *    rank; boundary entries of the iterate are pushed into the neighbours' memory and
+ *    the dot products meet in every rank's exchange area, synchronised by flags.
+ *    fb_peer_alloc creates this rank's exchange area and returns its CUDA IPC handle
+ *    (64 bytes) for the host to distribute; fb_peer_open maps a peer's area;
+ *    fb_peer_set_send lists, sorted by vertex, every owned vertex another rank holds as
+ *    ghost (dst = its local index there). --------------------------------------------- */
+int fb_peer_alloc(fb_ctx* ctx, int rank, int nranks /*<= 8*/, unsigned char* ipc_handle /*[host] 64 bytes*/);
+int fb_peer_open(fb_ctx* ctx, int peer_rank, const unsigned char* ipc_handle /*[host] 64 bytes*/);
+int fb_peer_set_send(fb_ctx* ctx, int64_t n, const int32_t* vertex /*[host]*/, const int32_t* rank /*[host]*/,
+                     const int32_t* dst_vertex /*[host]*/);
+/* solves J x = b on the owned rows to ||M^-1 r||^2 <= thr2 (M = point-block Jacobi from
+ * fb_bjacobi_setup); every rank must call it with the same thr2 and max_it */
+int fb_dcg_persistent(fb_ctx* ctx, const double* Jvals /*[dev]*/, const double* b /*[dev]*/, double* x /*[dev]*/,
+                      double thr2, int max_it, int* iters /*[host]*/, int* converged /*[host]*/);
+
 #ifdef __cplusplus
 }
 #endif

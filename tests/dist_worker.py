@@ -35,7 +35,7 @@ def main():
         rel = np.linalg.norm(a - b) / np.linalg.norm(b)
         ok = rel < 1e-8 and m.solver.solver.getIterationNumber() == r.solver.solver.getIterationNumber()
         print(f"DIST world={dist.get_world_size()} rel={rel:.3e} newton={m.solver.solver.its} "
-              f"cg={m.solver.solver.linear_its} ok={ok}", flush=True)
+              f"cg={m.solver.solver.linear_its} peer={m.solver.peer} ok={ok}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

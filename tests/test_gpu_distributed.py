@@ -32,14 +32,22 @@ def test_partitioned_driver_single_rank(dim, n):
     assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-8
 
 
-def test_partitioned_two_ranks_nccl():
+@pytest.mark.parametrize("peer", [True, False])
+def test_partitioned_two_ranks(peer):
+    """peer=True: whole-solve persistent CG over NVLink peer memory (default);
+    peer=False: per-iteration NCCL halo exchange + all-reduce (FB_NO_PEER_CG=1)."""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517",
-           os.path.join(ROOT, "tests", "dist_worker.py"), "10"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+           os.path.join(ROOT, "tests", "dist_worker.py"), "14" if peer else "10"]
+    env = dict(os.environ)
+    env.pop("FB_NO_PEER_CG", None)
+    if not peer:
+        env["FB_NO_PEER_CG"] = "1"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "ok=True" in out.stdout
+    assert f"peer={peer}" in out.stdout
