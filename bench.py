@@ -212,8 +212,10 @@ def run_partitioned(args, rank, world, local_rank, config):
     sampler.stop_flag = True
     if rank == 0:
         config = dict(config)
-        config.update({"parallelism": f"mesh partitioned over {world} GPUs (RCB, grid {grid}), "
-                                      "halo exchange + all-reduce over NCCL",
+        how = ("whole-solve persistent CG per rank, halo pushed and dot products exchanged through "
+               "NVLink peer memory (no NCCL inside the solve)") if solver.peer else \
+            "halo exchange + all-reduce over NCCL per iteration"
+        config.update({"parallelism": f"mesh partitioned over {world} GPUs (RCB, grid {grid}), " + how,
                        "cells": 6 * args.n ** 3 * world, "dofs": int(N_global),
                        "halo_bytes_per_exchange_rank0": solver.halo.bytes_per_exchange})
         nloc = solver.part.n_owned
@@ -227,10 +229,10 @@ def run_partitioned(args, rank, world, local_rank, config):
                     "d2h_bytes_per_step": 8 * int(N_global), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": None, "owned_vertices_rank0": int(nloc),
-            "cuda_graph": bool(solver._graph is not None),
-            "note": "partitioned CG: one halo exchange and one 3-double all-reduce per iteration, "
-                    "recurrence scalars stay on the device (host checks a done flag every 16 "
-                    "iterations); the single-GPU number uses the persistent kernel"}))
+            "cuda_graph": bool(solver._graph is not None), "peer_memory_cg": bool(solver.peer),
+            "note": "weak scaling: one C1-sized block of the domain per GPU, so the global problem and "
+                    "its CG iteration count grow with N; block-Jacobi preconditioner (the per-SM coarse "
+                    "space of the single-GPU kernel is not used across ranks yet)"}))
     dist.barrier()
     dist.destroy_process_group()
 

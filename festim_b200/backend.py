@@ -205,7 +205,9 @@ class Context:
             lcols.append(lc.astype(np.uint16))
             halo_ptr[b + 1] = halo_ptr[b] + len(halo)
         halo_idx = np.ascontiguousarray(np.concatenate(halos)) if halos else np.zeros(0, np.int32)
-        lcol = np.ascontiguousarray(np.concatenate(lcols))
+        lcol = np.concatenate(lcols)
+        # partitioned meshes: the blocks cover the owned vertices; ghost rows are never swept
+        lcol = np.ascontiguousarray(np.concatenate([lcol, np.zeros(len(colidx) - len(lcol), np.uint16)]))
         self._check(self.lib.fb_set_sm_partition(
             self.h, nb, _np_ptr(rng, C.c_int32), _np_ptr(halo_ptr, C.c_int32),
             _np_ptr(halo_idx, C.c_int32), _np_ptr(lcol, C.c_uint16), len(lcol)))

@@ -411,7 +411,10 @@ extern "C" int fb_set_sm_partition(fb_ctx* ctx, int nblocks, const int32_t* rng,
   }
   // coarse space of the two-level preconditioner (one constant per block): block id of
   // every halo vertex, and per block the entries coupling to each neighbour block
-  if (S.ns == 1 && nblocks <= 160) {
+  ctx->part_owned_only = rng[nblocks] != S.n_vertices;
+  if (rng[nblocks] != S.n_vertices && rng[nblocks] != S.n_owned)
+    return fb_fail(ctx, "blocks must cover all vertices or exactly the owned ones");
+  if (S.ns == 1 && nblocks <= 160 && !ctx->part_owned_only) {
     auto block_of = [&](int w) {
       int lo = 0, hi = nblocks;  // rng[lo] <= w < rng[hi]
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rng[mid] <= w) lo = mid; else hi = mid; }

@@ -32,17 +32,18 @@ struct fb_ctx {
   bool coarse_masks_dirty = true;
   bool coarse_ready = false;                    // E^-1 matches the matrix being solved
   int part_blocks = 0;
+  bool part_owned_only = false;  // the blocks cover the owned vertices of a partitioned mesh only
   const int* d_blk_rng = nullptr;
   const int* d_halo_ptr = nullptr;
   const int* d_halo_idx = nullptr;
   const unsigned short* d_lcol = nullptr;
   long long part_max_entries = 0, part_max_bentries = 0, part_max_su = 0, part_max_rows = 0, part_min_rows = 0;
   // peer-memory exchange area of the partitioned persistent CG (fb_peer_*)
-  double* d_xchg = nullptr;            // [0,64) reduction slots, [64,80) arrival flags, [128,..) iterate u
+  double* d_xchg = nullptr;            // u64 words: [0,128) reduction slots, [128,..) two per ghost dof
   long long xchg_u_doubles = 0;
   void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int peer_rank = 0, peer_n = 0;
-  unsigned long long peer_epoch = 0;
+  unsigned peer_seq = 1;               // next unused tag of the LL words
   const int* d_send_v = nullptr; const int* d_send_rank = nullptr; const int* d_send_dst = nullptr;
   int n_send = 0;
   bool symmetric = false;

@@ -1216,7 +1216,7 @@ static int solve_cg_persistent(fb_ctx* ctx, const double* J, const double* b, do
   A.Einv = nullptr; A.rc = nullptr; A.halo_blk = nullptr; A.cn_ptr = nullptr; A.cn_blk = nullptr; A.rel2 = rel2;
   size_t smem = 0;
   const bool no_smem = getenv("FB_NO_SMEM_OPERATOR") != nullptr;
-  if (ctx->part_blocks == (int)nb && !getenv("FB_NO_SM_PARTITION")) {
+  if (ctx->part_blocks == (int)nb && !ctx->part_owned_only && !getenv("FB_NO_SM_PARTITION")) {
     // compact per-SM partition: operator rows + iterate cache (owned + halo) on chip
     A.blk_rng = ctx->d_blk_rng; A.halo_ptr = ctx->d_halo_ptr; A.halo_idx = ctx->d_halo_idx;
     A.lcol = ctx->d_lcol;
@@ -1510,41 +1510,64 @@ k_dcg_update(DevSpec S, const double* __restrict__ dinv, double alpha, double be
 
 // ---------------------------------------------------------------------------
 // Partitioned persistent CG over peer memory (NVLink / NVSwitch).  One cooperative
-// launch per rank runs the whole solve; ranks meet at the two synchronisation points
-// of the single-reduction recurrence through flags in each other's memory:
-//   * halo: after the vector update every block PUSHES the entries of u that other
-//     ranks hold as ghosts straight into their iterate (remote stores, no round trip);
+// launch per rank runs the whole solve.  Everything that crosses NVLink is written as
+// self-validating 8-byte words {tag : 32 | half a double : 32} straight into the
+// consumer's memory (the protocol NCCL calls LL): no fence, no flag, no round trip -
+// the reader spins until both halves carry the tag of the iteration it is in.
+//   * halo: in the vector update every block pushes the entries of u that other ranks
+//     hold as ghosts into their halo words; the neighbour's SpMV reads a ghost column
+//     from its halo words.  A push of version k+1 cannot overtake a reader of version
+//     k, because pushes happen after the reduction of iteration k, which every rank
+//     enters only after its SpMV k.
 //   * reduction: the last block to arrive at the local grid barrier sums the rank's
-//     partial dot products, stores the three totals into a slot of EVERY rank's
-//     exchange area, raises its flag there (st.release.sys) and waits for the flags of
-//     the other ranks before it opens the local barrier.
-// Every rank adds the per-rank totals in rank order, so all ranks take bit-identical
-// decisions (convergence, breakdown) and leave together.  No NCCL call, no host
-// round trip inside the solve.
+//     partial dot products, writes the three totals into a slot of EVERY rank's
+//     exchange area and collects the slots of the other ranks before it opens the
+//     local barrier.  Every rank adds the per-rank totals in rank order, so all ranks
+//     take bit-identical decisions (convergence, breakdown) and leave together.
+// Per iteration: one local grid barrier and one cross-rank rendezvous; no NCCL call and
+// no host round trip inside the solve.
 // ---------------------------------------------------------------------------
-#define FB_XR 0       // exchange area: reduction slots [2 parities][8 ranks][4]
-#define FB_XFLAG 64   // arrival flags [8] (u64)
-#define FB_XU 128     // iterate (owned + ghost entries)
+#define FB_XR 0       // u64 words: reduction slots [2 parities][8 ranks][3 values][2 halves]
+#define FB_XH 128     // u64 words: halo, two per ghost dof
 struct PeerArgs {
   int rank, nranks;
-  unsigned long long epoch;   // high half of the flag values: stale flags of earlier solves never match
+  unsigned seq;               // tag of version 0 of this solve (tags never repeat across solves)
   double* base[8];            // exchange area of every rank (own one included)
   const int* send_v; const int* send_rank; const int* send_dst; int n_send;  // sorted by send_v
 };
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned tag, double v) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long t = (unsigned long long)tag << 32;
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(t | (bits & 0xffffffffull)) : "memory");
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + 1), "l"(t | (bits >> 32)) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ll_word(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// spins until both halves carry `tag`; false on timeout / abort (bar[64])
+__device__ __forceinline__ bool ll_load(const unsigned long long* p, unsigned tag, unsigned* bar, double& out) {
+  unsigned spins = 0;
+  while (true) {
+    const unsigned long long lo = ll_word(p), hi = ll_word(p + 1);
+    if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) {
+      out = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+      return true;
+    }
+    if ((++spins & 0x3ffu) == 0u) {
+      __nanosleep(64);
+      if (spins > (1u << 23) || ld_acquire_u32(bar + 64)) { atomicExch(bar + 64, 1u); out = 0.0; return false; }
+    }
+  }
+}
 
-// Local grid barrier + cross-rank rendezvous, run by warp 0 of every block.  with_data:
-// the rank's partial dot products (partials[3][nblocks]) are summed and published.
-__device__ __forceinline__ bool xgrid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen, unsigned base_count,
-                                              const PeerArgs& P, const double* partials, bool with_data) {
+// Local grid barrier + cross-rank exchange of the three dot products, run by warp 0 of
+// every block.  On return tot3 (shared) holds the sums over all ranks.
+__device__ __forceinline__ bool xgrid_reduce(unsigned* bar, unsigned nblocks, unsigned& gen, unsigned base_count,
+                                             const PeerArgs& P, const double* partials, unsigned tag, unsigned parity,
+                                             double* tot3) {
   __shared__ int xok_s;
   __syncthreads();
   ++gen;
@@ -1555,34 +1578,29 @@ __device__ __forceinline__ bool xgrid_barrier(unsigned* bar, unsigned nblocks, u
     old = __shfl_sync(0xffffffffu, old, 0);
     int ok = 1;
     if (old - base_count == gen * nblocks - 1u) {  // last block of this rank
-      const unsigned long long tag = (P.epoch << 32) | gen;
-      double t[3] = {0.0, 0.0, 0.0};
-      if (with_data) {
+      double t[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          double sacc = 0.0;
-          for (unsigned b = lane; b < nblocks; b += 32) sacc += __ldcg(partials + (size_t)k * nblocks + b);
-          t[k] = warp_sum(sacc);
-        }
+      for (int k = 0; k < 3; ++k) {
+        double sacc = 0.0;
+        for (unsigned b = lane; b < nblocks; b += 32) sacc += __ldcg(partials + (size_t)k * nblocks + b);
+        t[k] = warp_sum(sacc);
       }
-      if (lane < P.nranks) {
-        if (with_data) {
-          volatile double* dst = P.base[lane] + FB_XR + (((gen >> 1) & 1u) * 8 + P.rank) * 4;
-          dst[0] = t[0]; dst[1] = t[1]; dst[2] = t[2];
-        }
-        __threadfence_system();
-        st_release_sys_u64((unsigned long long*)(P.base[lane] + FB_XFLAG) + P.rank, tag);
-        const unsigned long long* mine = (const unsigned long long*)(P.base[P.rank] + FB_XFLAG) + lane;
-        unsigned spins = 0;
-        while (ld_acquire_sys_u64(mine) < tag) {
-          __nanosleep(32);
-          if ((++spins & 0xfffu) == 0u) {
-            if (spins > (1u << 23) || ld_acquire_u32(bar + 64)) { atomicExch(bar + 64, 1u); ok = 0; break; }
-          }
-        }
+      // lane -> (destination rank q, value k): slot [parity][my rank][k] of rank q
+      if (lane < 3 * P.nranks) {
+        const int q = lane / 3, k = lane - 3 * q;
+        unsigned long long* dst = (unsigned long long*)P.base[q] + FB_XR + ((parity * 8 + P.rank) * 3 + k) * 2;
+        ll_store(dst, tag, k == 0 ? t[0] : (k == 1 ? t[1] : t[2]));
+      }
+      // collect: slot [parity][q][k] of my own area
+      if (lane < 3 * P.nranks) {
+        const int q = lane / 3, k = lane - 3 * q;
+        const unsigned long long* src =
+            (const unsigned long long*)P.base[P.rank] + FB_XR + ((parity * 8 + q) * 3 + k) * 2;
+        double v;
+        ok = ll_load(src, tag, bar, v);
       }
       ok = __all_sync(0xffffffffu, ok);
-      if (lane == 0) st_release_u32(bar + 32, gen);  // opens the local barrier (also on failure: bar[64] is set)
+      if (lane == 0) st_release_u32(bar + 32, gen);  // opens the local barrier (on failure bar[64] is set)
     } else if (lane == 0) {
       unsigned spins = 0;
       while (ld_acquire_u32(bar + 32) != gen) {
@@ -1593,6 +1611,19 @@ __device__ __forceinline__ bool xgrid_barrier(unsigned* bar, unsigned nblocks, u
         }
       }
       if (ok && ld_acquire_u32(bar + 64)) ok = 0;
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    // every block adds the per-rank totals in rank order (the words are complete: the last
+    // block saw them before it opened the barrier)
+    if (ok && lane < 3) {
+      double sacc = 0.0;
+      for (int q = 0; q < P.nranks; ++q) {
+        const unsigned long long* src =
+            (const unsigned long long*)P.base[P.rank] + FB_XR + ((parity * 8 + q) * 3 + lane) * 2;
+        const unsigned long long lo = ll_word(src), hi = ll_word(src + 1);
+        sacc += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+      }
+      tot3[lane] = sacc;
     }
     if (lane == 0) xok_s = ok;
   }
@@ -1611,23 +1642,46 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
   const unsigned nb = gridDim.x;
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   const long long n_own = S.n_owned;
+  // owned rows of this block: a compact RCB part (fb_set_sm_partition over the owned
+  // vertices) or, without one, a contiguous equal range
+  const bool part = A.blk_rng != nullptr;
   const long long vper = (n_own + nb - 1) / nb;
-  const long long v0 = (long long)blockIdx.x * vper < n_own ? (long long)blockIdx.x * vper : n_own;
-  const long long v1 = (v0 + vper < n_own) ? v0 + vper : n_own;
-  const int nrows = (int)(v1 - v0) * ns;
+  const long long v0 = part ? A.blk_rng[blockIdx.x] : ((long long)blockIdx.x * vper < n_own ? (long long)blockIdx.x * vper : n_own);
+  const long long v1 = part ? A.blk_rng[blockIdx.x + 1] : ((v0 + vper < n_own) ? v0 + vper : n_own);
+  const int nvloc = (int)(v1 - v0);
+  const int nrows = nvloc * ns;
   const long long row0 = v0 * ns;
-  double* const uvec = P.base[P.rank] + FB_XU;  // owned entries written here, ghost entries by the peers
-  // operator rows of this block in shared memory when they fit: vals | cols | rstart | rlen
+  double* const uvec = A.u;                      // owned entries of the iterate
+  const long long n_own_dofs = n_own * ns;
+  const unsigned long long* const halo = (const unsigned long long*)P.base[P.rank] + FB_XH;  // ghost entries
+  // shared memory: vals[cap] f64 | su[su_doubles] f64 | cols: int[cap] (range mode) or
+  // u16[bentries] (partition mode) | rstart[rows] | rlen[rows] | rbst[rows]
+  const long long rows_cap = part ? A.rows_cap : vper * ns;
   double* svals = (double*)smem_raw;
-  int* scols = (int*)(svals + A.smem_entries);
-  int* rstart = scols + A.smem_entries;
-  int* rlen = rstart + vper * ns;
+  double* su = svals + A.smem_entries;
+  int* scols = (int*)(su + A.su_doubles);
+  unsigned short* slcol = (unsigned short*)scols;
+  int* rstart = part ? (int*)(slcol + ((A.bentries + 1) & ~1LL)) : scols + A.smem_entries;
+  int* rlen = rstart + rows_cap;
+  int* rbst = rlen + rows_cap;
   bool staged = false;
+  int nhalo = 0;
+  const int* hidx = nullptr;
   if (A.rows_in_smem && nrows > 0) {
     const long long e0 = (long long)S.rowptr[v0] * S.npairs, e1 = (long long)S.rowptr[v1] * S.npairs;
     staged = (e1 - e0) <= A.smem_entries;
+    if (part) {
+      nhalo = A.halo_ptr[blockIdx.x + 1] - A.halo_ptr[blockIdx.x];
+      hidx = A.halo_idx + A.halo_ptr[blockIdx.x];
+      staged = staged && (long long)(nvloc + nhalo) * ns <= A.su_doubles &&
+               (long long)(S.rowptr[v1] - S.rowptr[v0]) <= A.bentries;
+    }
     if (staged) {
       for (long long e = tid; e < e1 - e0; e += T) svals[e] = A.J[e0 + e];
+      if (part) {
+        const long long b0 = S.rowptr[v0], nbe = S.rowptr[v1] - b0;
+        for (long long e = tid; e < nbe; e += T) slcol[e] = A.lcol[b0 + e];
+      }
       for (int rr = tid; rr < nrows; rr += T) {
         const int vl = rr / ns, sp = rr - vl * ns;
         const long long v = v0 + vl;
@@ -1636,13 +1690,16 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
         const int start = (int)((long long)r0 * S.npairs + (long long)deg * pp - e0);
         rstart[rr] = start;
         rlen[rr] = deg * nc;
-        for (int e = 0; e < deg * nc; ++e) {
-          const int k = e / nc, j = e - k * nc;
-          scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
-        }
+        rbst[rr] = r0 - S.rowptr[v0];
+        if (!part)
+          for (int e = 0; e < deg * nc; ++e) {
+            const int k = e / nc, j = e - k * nc;
+            scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
+          }
       }
     }
   }
+  const bool cached = staged && part;  // iterate gathered from shared memory
   // this block's slice of the send table (entries sorted by owned vertex)
   if (tid < 2) {
     const long long key = tid == 0 ? v0 : v1;
@@ -1659,38 +1716,77 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
       A.r[i] = rin[sp]; A.x[i] = 0.0; A.p[i] = 0.0; A.s[i] = 0.0;
     }
     bjacobi_apply(ns, A.dinv, v, rin, zo);
-    for (int sp = 0; sp < ns; ++sp) uvec[v * ns + sp] = zo[sp];
+    for (int sp = 0; sp < ns; ++sp) {
+      uvec[v * ns + sp] = zo[sp];
+      if (cached) su[(v - v0) * ns + sp] = zo[sp];
+    }
   }
   __syncthreads();
   const int s0 = srange[0], s1 = srange[1];
   for (int q = s0 + tid; q < s1; q += T) {
-    double* dst = P.base[P.send_rank[q]] + FB_XU + (long long)P.send_dst[q] * ns;
+    unsigned long long* dst = (unsigned long long*)P.base[P.send_rank[q]] + FB_XH + (long long)P.send_dst[q] * ns * 2;
     const long long src = (long long)P.send_v[q] * ns;
-    for (int sp = 0; sp < ns; ++sp) dst[sp] = uvec[src + sp];
+    for (int sp = 0; sp < ns; ++sp) ll_store(dst + 2 * sp, P.seq, uvec[src + sp]);
   }
-  if (s1 > s0) __threadfence_system();
   unsigned gen = 0;
   const unsigned base_count = A.bar_base;
-  if (!xgrid_barrier(A.bar, nb, gen, base_count, P, A.partials, false)) return;
+  if (!grid_barrier(A.bar, nb, gen, base_count)) return;
   double alpha = 0.0, beta = 0.0, gamma_old = 0.0;
   int it = 0, done = 0, breakdown = 0;
   const int ngroups = T / G, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  long long tph[5] = {0, 0, 0, 0, 0};  // cycles per phase (block 0), reported in sc[8..12]
   while (true) {
+    const long long c0 = clock64();
+    const unsigned utag = P.seq + (unsigned)it;  // version of u this SpMV reads
+    int failed = 0;
+    // ---- halo of the iterate into shared memory: other blocks' entries from L2, other
+    // ranks' entries from the halo words they pushed ------------------------------------------
+    if (cached) {
+      for (int h = tid; h < nhalo * ns; h += T) {
+        const int hv = h / ns, sp = h - hv * ns;
+        const long long c = (long long)hidx[hv] * ns + sp;
+        double val;
+        if (c < n_own_dofs) val = __ldcg(uvec + c);
+        else if (!ll_load(halo + 2 * (c - n_own_dofs), utag, A.bar, val)) failed = 1;
+        su[nrows + h] = val;
+      }
+      __syncthreads();
+    }
     // ---- phase B: w = A u on owned rows + partial dots -----------------------------------
     double v3[3] = {0.0, 0.0, 0.0};
     for (int rr = grp; rr < nrows; rr += ngroups) {
       double sum = 0.0;
       const long long row = row0 + rr;
-      const double ri = __ldcg(A.r + row), ui = __ldcg(uvec + row);
-      if (staged) {
+      double ri, ui;
+      if (cached) {
+        ri = __ldcg(A.r + row);
+        ui = su[rr];
+        const int a0 = rstart[rr], n = rlen[rr], bs = rbst[rr];
+        if (ns == 1) {
+          for (int e = gl; e < n; e += G) sum += svals[a0 + e] * su[slcol[bs + e]];
+        } else {
+          const int vl = rr / ns, sp = rr - vl * ns;
+          const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
+          for (int e = gl; e < n; e += G) {
+            const int k = e / nc, j = e - k * nc;
+            sum += svals[a0 + e] * su[(int)slcol[bs + k] * ns + S.pair_cs[pp + j]];
+          }
+        }
+      } else if (staged) {
+        ri = __ldcg(A.r + row); ui = __ldcg(uvec + row);
         const int a0 = rstart[rr], n = rlen[rr];
         for (int eb = gl; eb < n; eb += 8 * G) {
           double uv[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int e = eb + q * G;
-            uv[q] = e < n ? __ldcg(uvec + scols[a0 + e]) : 0.0;
+            uv[q] = 0.0;
+            if (e < n) {
+              const int c = scols[a0 + e];
+              if (c < n_own_dofs) uv[q] = __ldcg(uvec + c);
+              else if (!ll_load(halo + 2 * (c - n_own_dofs), utag, A.bar, uv[q])) failed = 1;
+            }
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -1699,6 +1795,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
           }
         }
       } else {
+        ri = __ldcg(A.r + row); ui = __ldcg(uvec + row);
         const int vl = rr / ns, sp = rr - vl * ns;
         const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
@@ -1707,7 +1804,11 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
         const int n = deg * nc;
         for (int e = gl; e < n; e += G) {
           const int k = e / nc, j = e - k * nc;
-          sum += vals[e] * __ldcg(uvec + (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]);
+          const long long c = (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
+          double uc;
+          if (c < n_own_dofs) uc = __ldcg(uvec + c);
+          else if (!ll_load(halo + 2 * (c - n_own_dofs), utag, A.bar, uc)) failed = 1;
+          sum += vals[e] * uc;
         }
       }
 #pragma unroll
@@ -1728,15 +1829,10 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
       sacc = warp_sum(sacc);
       if (lane == 0) A.partials[(size_t)wid * nb + blockIdx.x] = sacc;
     }
-    if (!xgrid_barrier(A.bar, nb, gen, base_count, P, A.partials, true)) return;
-    // ---- totals over ranks, same order everywhere ------------------------------------------
-    if (tid < 3) {
-      const double* xr = P.base[P.rank] + FB_XR + ((gen >> 1) & 1u) * 32;
-      double sacc = 0.0;
-      for (int q = 0; q < P.nranks; ++q) sacc += __ldcg(xr + q * 4 + tid);
-      tot[tid] = sacc;
-    }
-    __syncthreads();
+    const long long c1 = clock64();
+    if (failed) atomicExch(A.bar + 64, 1u);  // a halo word never arrived: everybody leaves at the rendezvous
+    if (!xgrid_reduce(A.bar, nb, gen, base_count, P, A.partials, utag, (unsigned)it & 1u, tot)) return;
+    const long long c2 = clock64();
     const double gamma_new = tot[0], delta = tot[1], uu = tot[2];
     if (uu <= A.thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
     else if (it >= A.max_it) { done = 2; }
@@ -1749,16 +1845,19 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
     if (done) {
       if (blockIdx.x == 0 && tid == 0) {
         A.flags[0] = (done == 1); A.flags[1] = it; A.flags[2] = breakdown; A.sc[3] = uu;
+        for (int k = 0; k < 5; ++k) A.sc[8 + k] = (double)tph[k];
       }
       break;
     }
     ++it;
+    const long long c3 = clock64();
     // ---- phase A: vector update on owned vertices, then push the boundary entries ----------
     for (long long v = v0 + tid; v < v1; v += T) {
       double rin[FB_MAX_NS], zo[FB_MAX_NS];
       for (int sp = 0; sp < ns; ++sp) {
         const long long i = v * ns + sp;
-        const double ui = __ldcg(uvec + i), wi = __ldcg(A.w + i), ri = __ldcg(A.r + i);
+        const double ui = cached ? su[(v - v0) * ns + sp] : __ldcg(uvec + i);
+        const double wi = __ldcg(A.w + i), ri = __ldcg(A.r + i);
         const double p_old = __ldcg(A.p + i), s_old = __ldcg(A.s + i), x_old = __ldcg(A.x + i);
         const double pi = ui + beta * p_old;
         const double si = wi + beta * s_old;
@@ -1768,16 +1867,22 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
         A.r[i] = rin[sp];
       }
       bjacobi_apply(ns, A.dinv, v, rin, zo);
-      for (int sp = 0; sp < ns; ++sp) uvec[v * ns + sp] = zo[sp];
+      for (int sp = 0; sp < ns; ++sp) {
+        uvec[v * ns + sp] = zo[sp];
+        if (cached) su[(v - v0) * ns + sp] = zo[sp];
+      }
     }
     __syncthreads();
     for (int q = s0 + tid; q < s1; q += T) {
-      double* dst = P.base[P.send_rank[q]] + FB_XU + (long long)P.send_dst[q] * ns;
+      unsigned long long* dst =
+          (unsigned long long*)P.base[P.send_rank[q]] + FB_XH + (long long)P.send_dst[q] * ns * 2;
       const long long src = (long long)P.send_v[q] * ns;
-      for (int sp = 0; sp < ns; ++sp) dst[sp] = uvec[src + sp];
+      for (int sp = 0; sp < ns; ++sp) ll_store(dst + 2 * sp, P.seq + (unsigned)it, uvec[src + sp]);
     }
-    if (s1 > s0) __threadfence_system();
-    if (!xgrid_barrier(A.bar, nb, gen, base_count, P, A.partials, false)) return;  // also protects tot[]
+    const long long c4 = clock64();
+    if (!grid_barrier(A.bar, nb, gen, base_count)) return;  // local: u of the other blocks; also protects tot[]
+    const long long c5 = clock64();
+    tph[0] += c1 - c0; tph[1] += c2 - c1; tph[2] += c3 - c2; tph[3] += c4 - c3; tph[4] += c5 - c4;
   }
 }
 
@@ -1916,8 +2021,8 @@ extern "C" int fb_peer_alloc(fb_ctx* ctx, int rank, int nranks, unsigned char* h
   if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fb_fail(ctx, "1..8 ranks on one node");
   cudaSetDevice(ctx->device);
   if (!ctx->d_xchg) {
-    ctx->xchg_u_doubles = ctx->S.n_dofs;
-    const size_t n = (size_t)FB_XU + (size_t)ctx->xchg_u_doubles;
+    ctx->xchg_u_doubles = 2 * (ctx->S.n_dofs - ctx->S.n_owned * (long long)ctx->S.ns);  // two words per ghost dof
+    const size_t n = (size_t)FB_XH + (size_t)ctx->xchg_u_doubles + 2;
     int rc = fb_alloc(ctx, &ctx->d_xchg, n);  // its own cudaMalloc block: exportable as a whole
     if (rc) return rc;
     FB_CHECK(ctx, cudaMemset(ctx->d_xchg, 0, n * sizeof(double)));
@@ -1980,12 +2085,12 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
   CgArgs A;
   memset(&A, 0, sizeof(A));
   A.J = J; A.dinv = ctx->d_dinv; A.b = b; A.x = x;
-  A.r = ctx->d_work; A.u = nullptr; A.w = A.r + 2 * N; A.p = A.w + N; A.s = A.p + N;
+  A.r = ctx->d_work; A.u = A.r + N; A.w = A.u + N; A.p = A.w + N; A.s = A.p + N;
   A.partials = ctx->d_red; A.bar = ctx->d_ticket + 64; A.sc = ctx->d_sc; A.flags = ctx->d_flags;
   A.thr2 = thr2; A.max_it = max_it;
   PeerArgs P;
   memset(&P, 0, sizeof(P));
-  P.rank = ctx->peer_rank; P.nranks = ctx->peer_n; P.epoch = ++ctx->peer_epoch;
+  P.rank = ctx->peer_rank; P.nranks = ctx->peer_n; P.seq = ctx->peer_seq;
   for (int q = 0; q < 8; ++q) P.base[q] = (double*)ctx->peer_base[q];
   P.send_v = ctx->d_send_v; P.send_rank = ctx->d_send_rank; P.send_dst = ctx->d_send_dst; P.n_send = ctx->n_send;
   const long long n_own_dofs = S.n_owned * (long long)S.ns;
@@ -1999,12 +2104,30 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
   const size_t smem_max = (size_t)v - 2048;
   const long long vper = (S.n_owned + nb - 1) / nb;
   const long long rows_per_block = vper * S.ns;
-  long long cap = ((long long)smem_max - 8 * (rows_per_block + 2)) / 12;
-  cap &= ~1LL;
-  const long long avg_entries = (long long)((double)ctx->nnzb * S.npairs * ((double)n_own_dofs / (double)N) / nb) + 1;
-  A.rows_in_smem = cap >= avg_entries && !getenv("FB_NO_SMEM_OPERATOR");
-  A.smem_entries = A.rows_in_smem ? cap : 0;
-  const size_t smem = A.rows_in_smem ? (size_t)(12 * cap + 8 * (rows_per_block + 2)) : 0;
+  size_t smem = 0;
+  const bool no_smem = getenv("FB_NO_SMEM_OPERATOR") != nullptr;
+  if (ctx->part_blocks == (int)nb && ctx->part_owned_only && !getenv("FB_NO_SM_PARTITION")) {
+    // compact per-SM parts of the owned vertices: operator rows + iterate cache on chip
+    A.blk_rng = ctx->d_blk_rng; A.halo_ptr = ctx->d_halo_ptr; A.halo_idx = ctx->d_halo_idx; A.lcol = ctx->d_lcol;
+    const long long capp = (ctx->part_max_entries + 1) & ~1LL;
+    const long long su = (ctx->part_max_su + 1) & ~1LL;
+    const long long be = (ctx->part_max_bentries + 1) & ~1LL;
+    const long long rows = ctx->part_max_rows;
+    const size_t need = (size_t)(8 * capp + 8 * su + 2 * be + 12 * rows + 16);
+    if (need <= smem_max && !no_smem) {
+      A.rows_in_smem = 1; A.smem_entries = capp; A.su_doubles = su; A.bentries = be; A.rows_cap = rows;
+      smem = need;
+    }
+  } else {
+    // contiguous equal ranges: operator rows in shared memory when they fit, gathers from L2
+    const bool rows_fit = 12 * (rows_per_block + 2) <= (long long)smem_max / 2;
+    long long cap = rows_fit ? ((long long)smem_max - 12 * (rows_per_block + 2)) / 12 : 0;
+    cap &= ~1LL;
+    const long long avg_entries = (long long)((double)ctx->nnzb * S.npairs * ((double)n_own_dofs / (double)N) / nb) + 1;
+    A.rows_in_smem = rows_fit && cap >= avg_entries && !no_smem;
+    A.smem_entries = A.rows_in_smem ? cap : 0;
+    smem = A.rows_in_smem ? (size_t)(12 * A.smem_entries + 12 * (rows_per_block + 2)) : 0;
+  }
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
   FB_CHECK(ctx, cudaMemsetAsync(A.bar, 0, 130 * sizeof(unsigned), ctx->stream));
   A.bar_base = 0u;
@@ -2027,5 +2150,13 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
   if (aborted) return fb_fail(ctx, "partitioned persistent CG: rendezvous timed out (a rank did not arrive)");
   *iters = fl[1];
   *converged = fl[0] && !fl[2];
+  ctx->peer_seq += (unsigned)fl[1] + 2u;  // same on every rank: the iteration count is
+  if (getenv("FB_VERBOSE") && fl[1] > 0 && ctx->peer_rank == 0) {
+    double ph[5];
+    FB_CHECK(ctx, cudaMemcpy(ph, ctx->d_sc + 8, sizeof(ph), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[fb] peer CG ranks=%d G=%d smem=%d parts=%d its=%d: cycles/iteration spmv+dots %.0f, rendezvous %.0f, "
+            "scalars %.0f, update+push %.0f, local barrier %.0f\n", ctx->peer_n, G, A.rows_in_smem, A.blk_rng != nullptr, fl[1], ph[0] / fl[1],
+            ph[1] / fl[1], ph[2] / fl[1], ph[3] / fl[1], ph[4] / fl[1]);
+  }
   return 0;
 }

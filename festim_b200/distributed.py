@@ -25,6 +25,7 @@ the gathered global field.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import types
 
 import numpy as np
@@ -60,11 +61,21 @@ def partition_rcb(coords, nparts):
 class LocalPartition:
     """Local view of rank ``rank``: numbering, cells, facets, halo lists."""
 
-    def __init__(self, mesh, part, rank, nranks):
+    def __init__(self, mesh, part, rank, nranks, sm_blocks=None):
         self.rank, self.nranks = rank, nranks
         cells = mesh.cells
         owned_mask = part == rank
         self.owned = np.nonzero(owned_mask)[0].astype(np.int64)
+        # optional second level: the owned vertices ordered as ``sm_blocks`` compact RCB
+        # parts (one per SM), so that contiguous ranges of the local numbering are compact
+        # subdomains the persistent CG can keep in shared memory.  Ghost order, send lists
+        # and receive segments are defined through global ids and do not change.
+        self.block_ranges = None
+        if sm_blocks and mesh.tdim > 1 and len(self.owned) >= 4 * sm_blocks:
+            sub = partition_rcb(mesh.coords[self.owned], sm_blocks)
+            self.owned = self.owned[np.argsort(sub, kind="stable")]
+            counts = np.bincount(sub, minlength=sm_blocks)
+            self.block_ranges = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
         cell_local = owned_mask[cells].any(axis=1)
         self.local_cells = np.nonzero(cell_local)[0]
         verts = np.unique(cells[self.local_cells].ravel())
@@ -119,8 +130,6 @@ class HaloExchange:
     """
 
     def __init__(self, part: LocalPartition, ns, torch, device):
-        import os
-
         import torch.distributed as dist
 
         self.p, self.ns, self.torch, self.device = part, ns, torch, device
@@ -222,7 +231,10 @@ class DistributedNewtonSolver:
         species = getattr(problem, "species", None) or [problem._unknown]
         self.ns = ns = len(species)
         self.part_of = partition_rcb(gmesh.coords, self.nranks)
-        self.part = lp = LocalPartition(gmesh, self.part_of, self.rank, self.nranks)
+        sm_blocks = None
+        if self.nranks > 1 and torch.cuda.is_available() and not os.environ.get("FB_NO_SM_PARTITION"):
+            sm_blocks = torch.cuda.get_device_properties(device).multi_processor_count
+        self.part = lp = LocalPartition(gmesh, self.part_of, self.rank, self.nranks, sm_blocks)
         # local tags
         ctag = np.zeros(gmesh.num_cells, dtype=np.int32)
         ctag[problem.volume_meshtags.indices] = problem.volume_meshtags.values
@@ -238,6 +250,9 @@ class DistributedNewtonSolver:
         with torch.cuda.stream(self.stream):
             self.ctx = ctx = Context(self.spec, device, renumber=False)  # owned-first numbering is fixed
         ctx._check(ctx.lib.fb_set_owned(ctx.h, lp.n_owned))
+        if lp.block_ranges is not None:
+            ctx.block_ranges = lp.block_ranges
+            ctx._set_sm_partition(*ctx.dmesh.graph)
         self.halo = HaloExchange(lp, ns, torch, ctx.device)
         self.atol = petsc_options["snes_atol"]
         self.rtol = petsc_options["snes_rtol"]
@@ -269,8 +284,6 @@ class DistributedNewtonSolver:
         self._graph = None
         # CUDA-graph replay of the iteration: on by default for a single rank; with NCCL
         # traffic inside the capture it is opt-in (FB_DIST_CUDA_GRAPH=1) until validated
-        import os
-
         self.use_graph = (self.nranks == 1 and not os.environ.get("FB_NO_CUDA_GRAPH")) or \
             bool(os.environ.get("FB_DIST_CUDA_GRAPH"))
         self.cg_iterations = 0
@@ -282,7 +295,7 @@ class DistributedNewtonSolver:
 
     def _setup_peer(self):
         """Exchange CUDA IPC handles of the per-rank exchange areas and build the send
-        table (owned vertex -> ghost slot on the neighbour) of the push-style halo."""
+        table (owned vertex -> ghost ordinal on the neighbour) of the push-style halo."""
         from festim_b200.backend import _np_ptr
 
         ctx, lib, lp, dist = self.ctx, self.ctx.lib, self.part, self.dist
@@ -291,8 +304,8 @@ class DistributedNewtonSolver:
         handle = (C.c_ubyte * 64)()
         ctx._check(lib.fb_peer_alloc(ctx.h, self.rank, self.nranks, handle))
         infos = [None] * self.nranks
-        dist.all_gather_object(infos, (bytes(handle), {int(q): seg for q, seg in lp.recv.items()}))
-        for q, (h, _) in enumerate(infos):
+        dist.all_gather_object(infos, (bytes(handle), {int(q): seg for q, seg in lp.recv.items()}, int(lp.n_owned)))
+        for q, (h, _, _) in enumerate(infos):
             if q != self.rank:
                 buf = (C.c_ubyte * 64).from_buffer_copy(h)
                 ctx._check(lib.fb_peer_open(ctx.h, q, buf))
@@ -302,7 +315,7 @@ class DistributedNewtonSolver:
             assert b - a == len(idx), "send list and the neighbour's ghost segment disagree"
             v.append(np.asarray(idx, dtype=np.int64))
             rk.append(np.full(len(idx), q, dtype=np.int64))
-            dst.append(np.arange(a, b, dtype=np.int64))
+            dst.append(np.arange(a, b, dtype=np.int64) - infos[q][2])   # ghost ordinal on rank q
         if v:
             v, rk, dst = np.concatenate(v), np.concatenate(rk), np.concatenate(dst)
             order = np.argsort(v, kind="stable")

@@ -182,11 +182,12 @@ int fb_dcg_update_dev(fb_ctx* ctx, const double* state /*[dev]*/, double* x, dou
  *    VecScatter ghost updates and MPI_Allreduce (reference: KSPSolve inside
  *    NonlinearProblem.solve, src/festim/problem.py:262-289): one cooperative launch per
  *    rank; boundary entries of the iterate are pushed into the neighbours' memory and
- *    the dot products meet in every rank's exchange area, synchronised by flags.
+ *    the dot products meet in every rank's exchange area, as self-validating
+ *    {tag, half double} words (no fences, flags or NCCL calls inside the solve).
  *    fb_peer_alloc creates this rank's exchange area and returns its CUDA IPC handle
  *    (64 bytes) for the host to distribute; fb_peer_open maps a peer's area;
  *    fb_peer_set_send lists, sorted by vertex, every owned vertex another rank holds as
- *    ghost (dst = its local index there). --------------------------------------------- */
+ *    ghost (dst = its ordinal in that rank's ghost block). --------------------------------------------- */
 int fb_peer_alloc(fb_ctx* ctx, int rank, int nranks /*<= 8*/, unsigned char* ipc_handle /*[host] 64 bytes*/);
 int fb_peer_open(fb_ctx* ctx, int peer_rank, const unsigned char* ipc_handle /*[host] 64 bytes*/);
 int fb_peer_set_send(fb_ctx* ctx, int64_t n, const int32_t* vertex /*[host]*/, const int32_t* rank /*[host]*/,

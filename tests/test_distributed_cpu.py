@@ -86,3 +86,24 @@ def test_rcb_balanced_any_count():
         part = partition_rcb(mesh.coords, nparts)
         counts = np.bincount(part, minlength=nparts)
         assert counts.sum() == mesh.num_vertices and counts.max() - counts.min() <= 1
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sm_block_ordering_keeps_halo_lists_consistent(world):
+    """Second-level (per-SM) RCB ordering of the owned vertices: block ranges cover the
+    owned vertices, and every send list still addresses the neighbour's ghost segment in
+    the same global-id order (what the push-style peer halo relies on)."""
+    from festim_b200.mesh import create_unit_cube
+
+    mesh = create_unit_cube(7, 6, 5)
+    part = partition_rcb(mesh.coords, world)
+    lps = [LocalPartition(mesh, part, r, world, sm_blocks=8) for r in range(world)]
+    for p in lps:
+        assert p.block_ranges is not None and p.block_ranges[0] == 0 and p.block_ranges[-1] == p.n_owned
+        assert sorted(p.l2g[: p.n_owned]) == sorted(np.nonzero(part == p.rank)[0])
+        # every block is a contiguous index range whose vertices are spatially compact
+        plain = LocalPartition(mesh, part, p.rank, world)
+        assert np.array_equal(p.ghosts, plain.ghosts)
+        for q, idx in p.send.items():
+            a, b = lps[q].recv[p.rank]
+            assert np.array_equal(p.l2g[idx], lps[q].l2g[a:b])
