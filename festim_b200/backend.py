@@ -81,7 +81,7 @@ def load_library():
         "fb_peer_alloc": (i, [vp, i, i, vp]),
         "fb_peer_open": (i, [vp, i, vp]),
         "fb_peer_set_send": (i, [vp, i64, vp, vp, vp]),
-        "fb_dcg_persistent": (i, [vp, vp, vp, vp, C.c_double, i, vp, vp]),
+        "fb_dcg_persistent": (i, [vp, vp, vp, vp, C.c_double, C.c_double, i, vp, vp]),
         "fb_dcg_spmv_dots": (i, [vp, vp, vp, vp, vp, vp]),
         "fb_dcg_update": (i, [vp, d, d, vp, vp, vp, vp, vp, vp]),
         "fb_dcg_scalars": (i, [vp, vp, vp, i]),
@@ -368,26 +368,26 @@ class B200NewtonSolver:
         ctx, spec, p = self.ctx, self.spec, self.problem
         lib = ctx.lib
         scal = spec.scalar_values()
-        parts = [scal.tobytes()]
         T = spec.temperature
         Tdev = None
+        # change detection on everything the cached coefficients depend on: a memcmp against
+        # the last uploaded copy (users mutate ``x.array`` in place, so identity is no proof)
+        parts = [scal]
         if isinstance(T, fem.Function):
-            parts.append(T.x.array.tobytes())
+            parts.append(T.x.array)
         elif T is not None:
-            parts.append(np.float64(T.value).tobytes())
-        for f in spec.fields:
-            parts.append(f.x.array.tobytes())
-        for _, _, vel in spec.adv:
-            parts.append(vel.array.tobytes())
-        import zlib
-
-        sig = tuple(zlib.adler32(b) for b in parts)
+            parts.append(np.float64(T.value))
+        parts += [f.x.array for f in spec.fields]
+        parts += [vel.array for _, _, vel in spec.adv]
         bc_vals = np.concatenate([bc.values() for bc in self._bc_forms])[self._bc_pick] \
             if self._bc_forms else np.zeros(0)
         bc_dev = ctx.to_device("bc_vals", bc_vals) if len(bc_vals) else None
         ctx._check(lib.fb_set_dirichlet_values(ctx.h, ctx.ptr(bc_dev)))
-        if sig == self._signature:
+        last = self._signature
+        if last is not None and len(last) == len(parts) and all(
+                np.array_equal(a, b) for a, b in zip(last, parts)):
             return
+        sig = [np.array(a, copy=True) for a in parts]
         self._signature = sig
         ctx._check(lib.fb_set_scalars(ctx.h, len(scal), _np_ptr(scal, C.c_double)))
         if isinstance(T, fem.Function):

@@ -414,21 +414,23 @@ extern "C" int fb_set_sm_partition(fb_ctx* ctx, int nblocks, const int32_t* rng,
   ctx->part_owned_only = rng[nblocks] != S.n_vertices;
   if (rng[nblocks] != S.n_vertices && rng[nblocks] != S.n_owned)
     return fb_fail(ctx, "blocks must cover all vertices or exactly the owned ones");
-  if (S.ns == 1 && nblocks <= 160 && !ctx->part_owned_only) {
+  if (S.ns == 1 && nblocks <= 160) {
     auto block_of = [&](int w) {
       int lo = 0, hi = nblocks;  // rng[lo] <= w < rng[hi]
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rng[mid] <= w) lo = mid; else hi = mid; }
       return lo;
     };
     std::vector<unsigned short> hb((size_t)halo_ptr[nblocks] + 1);
-    for (int h = 0; h < halo_ptr[nblocks]; ++h) hb[h] = (unsigned short)block_of(halo_idx[h]);
+    const int n_cov = rng[nblocks];  // vertices beyond are ghosts of a partitioned mesh: not in the coarse space
+    for (int h = 0; h < halo_ptr[nblocks]; ++h)
+      hb[h] = halo_idx[h] < n_cov ? (unsigned short)block_of(halo_idx[h]) : (unsigned short)159;
     std::vector<int> cn_ptr(nblocks + 1, 0), cn_blk, cn_eptr(1, 0), cn_ent;
     std::vector<std::pair<int, int>> off;  // (neighbour block, entry)
     for (int b = 0; b < nblocks; ++b) {
       off.clear();
       for (int e = ctx->h_rowptr[rng[b]]; e < ctx->h_rowptr[rng[b + 1]]; ++e) {
         const int w = ctx->h_colidx[e];
-        if (w < rng[b] || w >= rng[b + 1]) off.emplace_back(block_of(w), e);
+        if ((w < rng[b] || w >= rng[b + 1]) && w < n_cov) off.emplace_back(block_of(w), e);
       }
       std::stable_sort(off.begin(), off.end(),
                        [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first < y.first; });

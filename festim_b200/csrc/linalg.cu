@@ -1664,6 +1664,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
   int* rstart = part ? (int*)(slcol + ((A.bentries + 1) & ~1LL)) : scols + A.smem_entries;
   int* rlen = rstart + rows_cap;
   int* rbst = rlen + rows_cap;
+  unsigned char* rfree = (unsigned char*)(rbst + rows_cap);  // 1: row is in the coarse space
   bool staged = false;
   int nhalo = 0;
   const int* hidx = nullptr;
@@ -1700,6 +1701,28 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
     }
   }
   const bool cached = staged && part;  // iterate gathered from shared memory
+  // ---- rank-local coarse space (one constant per block of THIS rank; couplings to other
+  // ranks are left to the Jacobi part): same construction as in k_cg_persistent ----------
+  __shared__ double ysm[160], rcs[160];
+  const bool coarse = A.Einv != nullptr && cached && ns == 1;
+  const int cn0 = coarse ? A.cn_ptr[blockIdx.x] : 0;
+  const int nneed = coarse ? A.cn_ptr[blockIdx.x + 1] - cn0 + 1 : 0;  // self + neighbours
+  const unsigned short* hblk = coarse ? A.halo_blk + A.halo_ptr[blockIdx.x] : nullptr;
+  int ctarget = -1;
+  double erow[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (coarse) {
+    for (int rr = tid; rr < nrows; rr += T) rfree[rr] = S.bc_map[row0 + rr] < 0;
+    if (tid == 0) ysm[FB_COARSE_NONE] = 0.0;
+    if (wid < nneed) {
+      ctarget = wid == 0 ? (int)blockIdx.x : A.cn_blk[cn0 + wid - 1];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const unsigned c = lane + 32 * q;
+        erow[q] = c < nb ? A.Einv[(size_t)ctarget * nb + c] : 0.0;
+      }
+    }
+  }
+  double rsum = 0.0;
   // this block's slice of the send table (entries sorted by owned vertex)
   if (tid < 2) {
     const long long key = tid == 0 ? v0 : v1;
@@ -1715,15 +1738,28 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
       rin[sp] = A.b[i];
       A.r[i] = rin[sp]; A.x[i] = 0.0; A.p[i] = 0.0; A.s[i] = 0.0;
     }
+    if (coarse && rfree[v - v0]) rsum += rin[0];
     bjacobi_apply(ns, A.dinv, v, rin, zo);
     for (int sp = 0; sp < ns; ++sp) {
       uvec[v * ns + sp] = zo[sp];
       if (cached) su[(v - v0) * ns + sp] = zo[sp];
     }
   }
+  if (coarse) {  // restriction: block sum of r
+    rsum = warp_sum(rsum);
+    if (lane == 0) red[0][wid] = rsum;
+    __syncthreads();
+    if (wid == 0) {
+      double sacc = lane < nw ? red[0][lane] : 0.0;
+      sacc = warp_sum(sacc);
+      if (lane == 0) A.rc[blockIdx.x] = sacc;
+    }
+  }
   __syncthreads();
   const int s0 = srange[0], s1 = srange[1];
-  for (int q = s0 + tid; q < s1; q += T) {
+  // with the coarse space the entries other ranks need are complete only after the coarse
+  // solve at the top of the loop: they are pushed there
+  for (int q = s0 + tid; q < (coarse ? s0 : s1); q += T) {
     unsigned long long* dst = (unsigned long long*)P.base[P.send_rank[q]] + FB_XH + (long long)P.send_dst[q] * ns * 2;
     const long long src = (long long)P.send_v[q] * ns;
     for (int sp = 0; sp < ns; ++sp) ll_store(dst + 2 * sp, P.seq, uvec[src + sp]);
@@ -1731,7 +1767,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
   unsigned gen = 0;
   const unsigned base_count = A.bar_base;
   if (!grid_barrier(A.bar, nb, gen, base_count)) return;
-  double alpha = 0.0, beta = 0.0, gamma_old = 0.0;
+  double alpha = 0.0, beta = 0.0, gamma_old = 0.0, thr2 = A.thr2;
   int it = 0, done = 0, breakdown = 0;
   const int ngroups = T / G, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
@@ -1740,6 +1776,46 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
     const long long c0 = clock64();
     const unsigned utag = P.seq + (unsigned)it;  // version of u this SpMV reads
     int failed = 0;
+    // ---- coarse correction u = D^-1 r + Z E^-1 Z^T r, then the boundary entries go out ----
+    if (coarse) {
+      if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const unsigned c = lane + 32 * q;
+          if (c < nb) rcs[c] = __ldcg(A.rc + c);
+        }
+      }
+      __syncthreads();
+      for (int k = wid; k < nneed; k += nw) {
+        double d = 0.0;
+        int tb = ctarget;
+        if (k == wid) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const unsigned c = lane + 32 * q;
+            if (c < nb) d += erow[q] * rcs[c];
+          }
+        } else {
+          tb = A.cn_blk[cn0 + k - 1];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const unsigned c = lane + 32 * q;
+            if (c < nb) d += A.Einv[(size_t)tb * nb + c] * rcs[c];
+          }
+        }
+        d = warp_sum(d);
+        if (lane == 0) ysm[tb] = d;
+      }
+      __syncthreads();
+      const double yself = ysm[blockIdx.x];
+      for (int rr = tid; rr < nrows; rr += T)
+        if (rfree[rr]) su[rr] += yself;
+      __syncthreads();
+      for (int q = s0 + tid; q < s1; q += T) {
+        unsigned long long* dst = (unsigned long long*)P.base[P.send_rank[q]] + FB_XH + (long long)P.send_dst[q] * 2;
+        ll_store(dst, utag, su[P.send_v[q] - v0]);
+      }
+    }
     // ---- halo of the iterate into shared memory: other blocks' entries from L2, other
     // ranks' entries from the halo words they pushed ------------------------------------------
     if (cached) {
@@ -1747,7 +1823,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
         const int hv = h / ns, sp = h - hv * ns;
         const long long c = (long long)hidx[hv] * ns + sp;
         double val;
-        if (c < n_own_dofs) val = __ldcg(uvec + c);
+        if (c < n_own_dofs) val = __ldcg(uvec + c) + (coarse ? ysm[hblk[hv]] : 0.0);
         else if (!ll_load(halo + 2 * (c - n_own_dofs), utag, A.bar, val)) failed = 1;
         su[nrows + h] = val;
       }
@@ -1834,7 +1910,8 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
     if (!xgrid_reduce(A.bar, nb, gen, base_count, P, A.partials, utag, (unsigned)it & 1u, tot)) return;
     const long long c2 = clock64();
     const double gamma_new = tot[0], delta = tot[1], uu = tot[2];
-    if (uu <= A.thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
+    if (it == 0 && A.Einv != nullptr) thr2 = A.rel2 * uu;  // relative to ||M^-1 b|| of this M
+    if (uu <= thr2 || !(uu == uu)) { done = 1; breakdown = !(uu == uu); }
     else if (it >= A.max_it) { done = 2; }
     else {
       if (it == 0) { beta = 0.0; alpha = gamma_new / delta; }
@@ -1852,6 +1929,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
     ++it;
     const long long c3 = clock64();
     // ---- phase A: vector update on owned vertices, then push the boundary entries ----------
+    rsum = 0.0;
     for (long long v = v0 + tid; v < v1; v += T) {
       double rin[FB_MAX_NS], zo[FB_MAX_NS];
       for (int sp = 0; sp < ns; ++sp) {
@@ -1866,18 +1944,30 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
         rin[sp] = ri - alpha * si;
         A.r[i] = rin[sp];
       }
+      if (coarse && rfree[v - v0]) rsum += rin[0];
       bjacobi_apply(ns, A.dinv, v, rin, zo);
       for (int sp = 0; sp < ns; ++sp) {
         uvec[v * ns + sp] = zo[sp];
         if (cached) su[(v - v0) * ns + sp] = zo[sp];
       }
     }
-    __syncthreads();
-    for (int q = s0 + tid; q < s1; q += T) {
-      unsigned long long* dst =
-          (unsigned long long*)P.base[P.send_rank[q]] + FB_XH + (long long)P.send_dst[q] * ns * 2;
-      const long long src = (long long)P.send_v[q] * ns;
-      for (int sp = 0; sp < ns; ++sp) ll_store(dst + 2 * sp, P.seq + (unsigned)it, uvec[src + sp]);
+    if (coarse) {
+      rsum = warp_sum(rsum);
+      if (lane == 0) red[0][wid] = rsum;
+      __syncthreads();
+      if (wid == 0) {
+        double sacc = lane < nw ? red[0][lane] : 0.0;
+        sacc = warp_sum(sacc);
+        if (lane == 0) A.rc[blockIdx.x] = sacc;
+      }
+    } else {
+      __syncthreads();
+      for (int q = s0 + tid; q < s1; q += T) {
+        unsigned long long* dst =
+            (unsigned long long*)P.base[P.send_rank[q]] + FB_XH + (long long)P.send_dst[q] * ns * 2;
+        const long long src = (long long)P.send_v[q] * ns;
+        for (int sp = 0; sp < ns; ++sp) ll_store(dst + 2 * sp, P.seq + (unsigned)it, uvec[src + sp]);
+      }
     }
     const long long c4 = clock64();
     if (!grid_barrier(A.bar, nb, gen, base_count)) return;  // local: u of the other blocks; also protects tot[]
@@ -2071,7 +2161,7 @@ extern "C" int fb_peer_set_send(fb_ctx* ctx, int64_t n, const int32_t* v, const 
 }
 
 extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, double* x, double thr2,
-                                 int max_it, int* iters, int* converged) {
+                                 double rtol, int max_it, int* iters, int* converged) {
   if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
   if (!ctx->d_xchg) return fb_fail(ctx, "fb_peer_alloc first");
   for (int q = 0; q < ctx->peer_n; ++q)
@@ -2101,7 +2191,7 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
   const unsigned nb = (unsigned)ctx->sm_count;
   int v = 0;
   cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-  const size_t smem_max = (size_t)v - 2048;
+  const size_t smem_max = (size_t)v - 4096;  // static shared: reductions, coarse solution
   const long long vper = (S.n_owned + nb - 1) / nb;
   const long long rows_per_block = vper * S.ns;
   size_t smem = 0;
@@ -2113,10 +2203,16 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
     const long long su = (ctx->part_max_su + 1) & ~1LL;
     const long long be = (ctx->part_max_bentries + 1) & ~1LL;
     const long long rows = ctx->part_max_rows;
-    const size_t need = (size_t)(8 * capp + 8 * su + 2 * be + 12 * rows + 16);
+    const size_t need = (size_t)(8 * capp + 8 * su + 2 * be + 13 * rows + 32);
     if (need <= smem_max && !no_smem) {
       A.rows_in_smem = 1; A.smem_entries = capp; A.su_doubles = su; A.bentries = be; A.rows_cap = rows;
       smem = need;
+      if ((rc = coarse_setup(ctx, J))) return rc;
+      if (ctx->coarse_ready) {  // rank-local two-level preconditioner
+        A.Einv = ctx->d_coarse + (size_t)nb * nb; A.rc = ctx->d_coarse + (size_t)2 * nb * nb;
+        A.halo_blk = ctx->d_halo_blk_eff; A.cn_ptr = ctx->d_cn_ptr; A.cn_blk = ctx->d_cn_blk;
+        A.rel2 = rtol * rtol;
+      }
     }
   } else {
     // contiguous equal ranges: operator rows in shared memory when they fit, gathers from L2
@@ -2154,8 +2250,8 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
   if (getenv("FB_VERBOSE") && fl[1] > 0 && ctx->peer_rank == 0) {
     double ph[5];
     FB_CHECK(ctx, cudaMemcpy(ph, ctx->d_sc + 8, sizeof(ph), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[fb] peer CG ranks=%d G=%d smem=%d parts=%d its=%d: cycles/iteration spmv+dots %.0f, rendezvous %.0f, "
-            "scalars %.0f, update+push %.0f, local barrier %.0f\n", ctx->peer_n, G, A.rows_in_smem, A.blk_rng != nullptr, fl[1], ph[0] / fl[1],
+    fprintf(stderr, "[fb] peer CG ranks=%d G=%d smem=%d parts=%d coarse=%d its=%d: cycles/iteration spmv+dots %.0f, rendezvous %.0f, "
+            "scalars %.0f, update+push %.0f, local barrier %.0f\n", ctx->peer_n, G, A.rows_in_smem, A.blk_rng != nullptr, A.Einv != nullptr, fl[1], ph[0] / fl[1],
             ph[1] / fl[1], ph[2] / fl[1], ph[3] / fl[1], ph[4] / fl[1]);
   }
   return 0;

@@ -387,7 +387,7 @@ class DistributedNewtonSolver:
         thr2 = (rtol * self._norm(self.tmp)) ** 2
         if self.peer:
             its, conv = C.c_int(0), C.c_int(0)
-            ctx._check(lib.fb_dcg_persistent(ctx.h, ptr(J), ptr(b), ptr(x), float(thr2), int(max_it),
+            ctx._check(lib.fb_dcg_persistent(ctx.h, ptr(J), ptr(b), ptr(x), float(thr2), float(rtol), int(max_it),
                                              C.byref(its), C.byref(conv)))
             self.cg_iterations += its.value
             return its.value, bool(conv.value)

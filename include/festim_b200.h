@@ -192,10 +192,12 @@ int fb_peer_alloc(fb_ctx* ctx, int rank, int nranks /*<= 8*/, unsigned char* ipc
 int fb_peer_open(fb_ctx* ctx, int peer_rank, const unsigned char* ipc_handle /*[host] 64 bytes*/);
 int fb_peer_set_send(fb_ctx* ctx, int64_t n, const int32_t* vertex /*[host]*/, const int32_t* rank /*[host]*/,
                      const int32_t* dst_vertex /*[host]*/);
-/* solves J x = b on the owned rows to ||M^-1 r||^2 <= thr2 (M = point-block Jacobi from
- * fb_bjacobi_setup); every rank must call it with the same thr2 and max_it */
+/* solves J x = b on the owned rows; every rank must call it with the same arguments.
+ * Preconditioner M: point-block Jacobi (fb_bjacobi_setup) plus, when the rank's owned
+ * vertices are grouped in per-SM blocks (fb_set_sm_partition), a rank-local coarse space.
+ * Stops at ||M^-1 r|| <= rtol ||M^-1 b|| (thr2 = that bound squared for the Jacobi-only M). */
 int fb_dcg_persistent(fb_ctx* ctx, const double* Jvals /*[dev]*/, const double* b /*[dev]*/, double* x /*[dev]*/,
-                      double thr2, int max_it, int* iters /*[host]*/, int* converged /*[host]*/);
+                      double thr2, double rtol, int max_it, int* iters /*[host]*/, int* converged /*[host]*/);
 
 #ifdef __cplusplus
 }
