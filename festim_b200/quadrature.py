@@ -63,6 +63,8 @@ def rule(tdim, degree):
         key = (name, 4)
     if tdim == 3 and degree == 4:
         key = (name, 5)
+    if tdim == 3 and degree == 8 and (name, 8) not in TABLES:
+        key = (name, 9)  # fewer points than the collapsed degree-8 rule
     if tdim == 2 and degree == 7:
         key = (name, 8)  # 16 points: smaller than any degree-7 rule found
     if key in TABLES:

@@ -6,7 +6,7 @@ exactness with damped Gauss-Newton steps (minimum-norm least squares on points A
 weights) in an orthonormal polynomial basis.  Stops when no point can be removed with all
 weights positive and all points inside.  Output: a table entry for _quadrature_tables.py.
 
-usage: python tools/reduce_quadrature.py tet 9 [target_points]
+usage: python tools/reduce_quadrature.py tet 9 [target_points [tries [previous_output]]]
 """
 import itertools, os, sys
 import numpy as np
@@ -116,9 +116,12 @@ def solve(B, X, w, tol=3e-16, iters=60):
     return best
 
 
-def reduce(d, deg, target=0, tries=12, seed=0):
+def reduce(d, deg, target=0, tries=12, seed=0, start=None):
     B = Basis(d, deg)
-    P, W = quadrature.rule(d, deg)
+    if start is not None:
+        P, W = start
+    else:
+        P, W = quadrature.rule(d, deg)
     X, w = P[:, 1:].copy(), W / W.sum()
     rng = np.random.default_rng(seed)
     while len(w) > target:
@@ -143,8 +146,15 @@ def reduce(d, deg, target=0, tries=12, seed=0):
 if __name__ == "__main__":
     name, deg = sys.argv[1], int(sys.argv[2])
     target = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    tries = int(sys.argv[4]) if len(sys.argv) > 4 else 12
     d = 2 if name == "tri" else 3
-    X, w = reduce(d, deg, target)
+    start = None
+    if len(sys.argv) > 5:  # continue from a rule printed by an earlier run
+        txt = open(sys.argv[5]).read()
+        body = txt[txt.index("): (") + 3:].rstrip().rstrip(",")
+        pts, wts = eval(body)
+        start = (np.array(pts), np.array(wts))
+    X, w = reduce(d, deg, target, tries=tries, start=start)
     P = np.concatenate([1.0 - X.sum(1, keepdims=True), X], axis=1)
     # verify with raw monomials against the big rule
     Pr, Wr = quadrature.rule(d, deg + 2)
