@@ -76,7 +76,10 @@ __device__ __forceinline__ void fb_cell_coeffs_body(const DevSpec& S, double* __
   if (c >= S.n_cells) return;
   int a[FB_MAX_D1];
   double X[FB_MAX_D1][3], G[FB_MAX_D1][3];
-  fb_load_cell<DIM>(S, c, a, X);
+  // uniform temperature and Arrhenius slots only: the cell means are the same number
+  // everywhere, no geometry or nodal data needed
+  const bool uniform = !S.T_mode && S.n_slots == S.n_diffE;
+  if (!uniform) fb_load_cell<DIM>(S, c, a, X);
   const int tag = S.cell_tag[c];
   const bool need_G = S.n_slots > S.n_diffE;
   if (need_G) fb_geometry<DIM>(X, G);
