@@ -254,13 +254,65 @@ class HeatFluxBC(FluxBCBase):
     """-lambda grad(T).n = value  (``flux_bc.py:255-295``)."""
 
 
+class SurfaceReactionBCpartial(ParticleFluxBC):
+    """Flux of ONE reactant of a surface reaction A + B <-> C
+    (``surface_reaction.py:9-85``): ``K_d P_C - K_r c_A c_B`` with Arrhenius ``K_r``,
+    ``K_d``.  The value depends on the reactants' concentrations, so the lowering
+    differentiates it with respect to every species (facet Jacobian blocks)."""
+
+    def __init__(self, reactant, gas_pressure, k_r0, E_kr, k_d0, E_kd, subdomain, species):
+        self.reactant = reactant
+        self.gas_pressure = gas_pressure
+        self.k_r0 = k_r0
+        self.E_kr = E_kr
+        self.k_d0 = k_d0
+        self.E_kd = E_kd
+        super().__init__(subdomain=subdomain, value=None, species=species)
+
+    def create_value_fenics(self, mesh, temperature, t):
+        from festim_b200 import k_B
+
+        kr = self.k_r0 * ufl.exp(-self.E_kr / (k_B * ufl.as_expr(temperature)))
+        kd = self.k_d0 * ufl.exp(-self.E_kd / (k_B * ufl.as_expr(temperature)))
+        if hasattr(self.gas_pressure, "solution") and not callable(self.gas_pressure):
+            raise NotImplementedError("gas enclosures (GasSpecies pressures) are out of scope (SURVEY 2/8)")
+        if callable(self.gas_pressure):
+            gas_pressure = self.gas_pressure(t=t)
+        else:
+            gas_pressure = self.gas_pressure
+        product_of_reactants = self.reactant[0].concentration
+        for reactant in self.reactant[1:]:
+            product_of_reactants = product_of_reactants * reactant.concentration
+        self.value_fenics = kd * ufl.as_expr(gas_pressure) - kr * product_of_reactants
+
+
 class SurfaceReactionBC:
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("SurfaceReactionBC is not lowered yet (SURVEY 8f2)")
+    """Surface reaction A + B <-> C on a boundary (``surface_reaction.py:88-151``): one
+    :class:`SurfaceReactionBCpartial` flux per reactant (a reactant listed twice gets the
+    flux twice: A + A <-> A2 removes two particles per event)."""
+
+    def __init__(self, reactant, gas_pressure, k_r0, E_kr, k_d0, E_kd, subdomain):
+        self.reactant = reactant
+        self.gas_pressure = gas_pressure
+        self.k_r0 = k_r0
+        self.E_kr = E_kr
+        self.k_d0 = k_d0
+        self.E_kd = E_kd
+        self.subdomain = subdomain
+        self.flux_bcs = [
+            SurfaceReactionBCpartial(reactant=self.reactant, gas_pressure=self.gas_pressure,
+                                     k_r0=self.k_r0, E_kr=self.E_kr, k_d0=self.k_d0, E_kd=self.E_kd,
+                                     subdomain=self.subdomain, species=species)
+            for species in self.reactant
+        ]
+
+    @property
+    def time_dependent(self):
+        return False  # as the reference: the value is an expression of t, nothing to update
 
 
 __all__ = [
     "DirichletBC", "DirichletBCBase", "FixedConcentrationBC", "FixedTemperatureBC",
     "SievertsBC", "HenrysBC", "FluxBCBase", "ParticleFluxBC", "HeatFluxBC",
-    "SurfaceReactionBC", "SurfaceSubdomain",
+    "SurfaceReactionBC", "SurfaceReactionBCpartial", "SurfaceSubdomain",
 ]

@@ -236,7 +236,7 @@ __device__ __forceinline__ void fb_facets_body(const DevSpec& S, int mode, const
     // value
     double acc[3] = {0.0, 0.0, 0.0};
     for (int q = 0; q < (F != nullptr ? nqF : 0); ++q) {
-      const double* bary = S.quad_bary + (long long)(offF + q) * DIM;
+      const double* bary = S.quad_bary + (long long)(offF + q) * (DIM + 1);  // uniform pool stride; DIM entries used
       PointCtx P;
       for (int k = 0; k < DIM; ++k) {
         double x = 0.0;
@@ -274,7 +274,7 @@ __device__ __forceinline__ void fb_facets_body(const DevSpec& S, int mode, const
       const int dep = S.deriv_species[h[4] + dd];
       double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
       for (int q = 0; q < nqJ; ++q) {
-        const double* bary = S.quad_bary + (long long)(offJ + q) * DIM;
+        const double* bary = S.quad_bary + (long long)(offJ + q) * (DIM + 1);
         PointCtx P;
         for (int k = 0; k < DIM; ++k) {
           double x = 0.0;

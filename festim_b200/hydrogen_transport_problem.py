@@ -102,7 +102,14 @@ class HydrogenTransportProblem(ProblemBase):
 
     @property
     def _unpacked_bcs(self):
-        return list(self.boundary_conditions)
+        """All boundary conditions, the fluxes of surface reactions included (reference :289-298)."""
+        out = []
+        for bc in self.boundary_conditions:
+            if isinstance(bc, _bcs.SurfaceReactionBC):
+                out.extend(bc.flux_bcs)
+            else:
+                out.append(bc)
+        return out
 
     # ---- initialise pipeline (reference :314-344) -----------------------------
     def initialise(self):
@@ -218,7 +225,7 @@ class HydrogenTransportProblem(ProblemBase):
             advec_term.velocity.convert_input_value(function_space=self.function_space, t=self.t)
 
     def create_flux_values_fenics(self):
-        for bc in self.boundary_conditions:
+        for bc in self._unpacked_bcs:
             if isinstance(bc, _bcs.ParticleFluxBC):
                 bc.create_value_fenics(mesh=self.mesh.mesh, temperature=self.temperature_fenics,
                                        t=self.t)
@@ -267,7 +274,7 @@ class HydrogenTransportProblem(ProblemBase):
             F += forms.TestIntegral(source.species, -ufl.as_expr(source.value.fenics_object),
                                     self.dx(source.volume.id), {"source": source})
 
-        for bc in self.boundary_conditions:
+        for bc in self._unpacked_bcs:  # surface reactions contribute one flux per reactant (:949-956)
             if isinstance(bc, _bcs.ParticleFluxBC):
                 F += forms.TestIntegral(bc.species, -ufl.as_expr(bc.value_fenics),
                                         self.ds(bc.subdomain.id), {"flux": bc})
@@ -301,7 +308,7 @@ class HydrogenTransportProblem(ProblemBase):
                     reactant.update_density(t=t)
 
         if isinstance(self.temperature, fem.Function) or self.temperature_time_dependent:
-            for bc in self.boundary_conditions:
+            for bc in self._unpacked_bcs:
                 if isinstance(bc, (_bcs.FixedConcentrationBC, _bcs.ParticleFluxBC)):
                     if bc.temperature_dependent:
                         bc.update(t=t)

@@ -396,6 +396,10 @@ class KernelSpec:
     def _add_rule(self, tdim, degree):
         bary, w = quadrature.rule(tdim, degree)
         off = sum(len(x) for x in self._qw)
+        # one pool for cell and facet rules, addressed by point offset: every point takes
+        # tdim+1 doubles (facet rules are padded with a zero)
+        if bary.shape[1] < self.tdim + 1:
+            bary = np.concatenate([bary, np.zeros((bary.shape[0], self.tdim + 1 - bary.shape[1]))], axis=1)
         self._qb.append(bary.ravel())
         self._qw.append(w)
         return [off, len(w)]
