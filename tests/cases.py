@@ -476,3 +476,36 @@ DENSITIES = {
     "step_time_space": (lambda x, t: ufl.conditional(ufl.gt(t, 50), 10 - 10 * x[0], 0.0), 5.0),
     "step_time": (lambda t: 10.0 if t > 50 else 2.0, 10.0),
 }
+
+
+def recombination_flux(dim, n):
+    """Two isotopes in 2D/3D with a T-dependent prescribed influx g(x, T) on the left face and
+    surface reactions H + D <-> HD, H + H <-> H2 (recombination K_r c^2 and dissociation
+    K_d P) on the right face; T = 500 + 100 y.  Exercises facet terms that depend on x, T and
+    on several species (facet Jacobian blocks) away from 1D, where a facet is a point.
+    Transient (three implicit Euler steps from zero): the steady problem with flux conditions
+    only has a spurious negative root Newton finds from a zero guess."""
+    raw = F.create_unit_square(n, n) if dim == 2 else F.create_unit_cube(n, n, n)
+    mesh = F.Mesh(raw)
+    vol = F.VolumeSubdomain(id=1, material=F.Material(D_0=1.5, E_D=0.05))
+    left = F.SurfaceSubdomain(id=1, locator=lambda x: np.isclose(x[0], 0))
+    right = F.SurfaceSubdomain(id=2, locator=lambda x: np.isclose(x[0], 1))
+    m = F.HydrogenTransportProblem()
+    m.mesh = mesh
+    m.subdomains = [vol, left, right]
+    H, D = F.Species("H"), F.Species("D")
+    m.species = [H, D]
+    m.temperature = lambda x: 500 + 100 * x[1]
+    m.boundary_conditions = [
+        F.ParticleFluxBC(subdomain=left, value=lambda x, T: 2.0 + x[1] + 1e-3 * T, species=H),
+        F.ParticleFluxBC(subdomain=left, value=lambda x: 1.0 + 0.5 * x[1] ** 2, species=D),
+        F.SurfaceReactionBC(reactant=[H, D], gas_pressure=0.5, k_r0=0.3, E_kr=0.02, k_d0=0.2, E_kd=0.01,
+                            subdomain=right),
+        F.SurfaceReactionBC(reactant=[H, H], gas_pressure=1.0, k_r0=0.5, E_kr=0.03, k_d0=0.1, E_kd=0.0,
+                            subdomain=right),
+        F.SurfaceReactionBC(reactant=[D, D], gas_pressure=0.0, k_r0=0.4, E_kr=0.0, k_d0=0.0, E_kd=0.0,
+                            subdomain=right),
+    ]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=True, final_time=0.3)
+    m.settings.stepsize = F.Stepsize(0.1)
+    return m, (H, D), None

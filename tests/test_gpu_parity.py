@@ -283,3 +283,22 @@ def test_cg_two_level_preconditioner(n, monkeypatch):
     assert _rel(sols[0], ref) < 1e-9
     if n == 16:
         assert iters[0] < iters[1]
+
+
+@pytest.mark.parametrize("dim,n", [(2, 12), (3, 5)])
+def test_recombination_flux_parity(dim, n):
+    """Facet terms depending on x, T and two species (surface reactions) on triangles and
+    tetrahedra: assembled F / J and the steady solution against the oracle."""
+    from cases import recombination_flux
+
+    (gm, sg, _), (rm, sr, _) = _pair(recombination_flux, dim, n)
+    _check_assembly(gm, rm, seed=3)
+    for m in (gm, rm):
+        m.u.x.array[:] = 0.0
+        m.u_n.x.array[:] = 0.0
+    gm.run()
+    rm.run()
+    assert gm.solver.solver.getConvergedReason() > 0
+    assert gm.solver.solver.getIterationNumber() == rm.solver.solver.getIterationNumber()
+    for a, b in zip(sg, sr):
+        assert _rel(a.post_processing_solution.x.array, b.post_processing_solution.x.array) < 1e-8
