@@ -390,6 +390,37 @@ __device__ __forceinline__ unsigned atom_add_release_u32(unsigned* p, unsigned v
   return old;
 }
 
+// Self-validating 8-byte words {tag : 32 | half a double : 32} (the protocol NCCL calls LL):
+// the writer needs no fence or flag, the reader spins until both halves carry the tag it
+// expects.  Used for data another block (or, over NVLink, another GPU) consumes right after
+// it is produced: it replaces a barrier by point-to-point waiting.
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned tag, double v) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long t = (unsigned long long)tag << 32;
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(t | (bits & 0xffffffffull)) : "memory");
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + 1), "l"(t | (bits >> 32)) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_word(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spins until both halves carry `tag`; false on timeout / abort (bar[64])
+__device__ __forceinline__ bool ll_load(const unsigned long long* p, unsigned tag, unsigned* bar, double& out) {
+  unsigned spins = 0;
+  while (true) {
+    const unsigned long long lo = ll_word(p), hi = ll_word(p + 1);
+    if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) {
+      out = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+      return true;
+    }
+    if ((++spins & 0x3ffu) == 0u) {
+      __nanosleep(64);
+      if (spins > (1u << 23) || ld_acquire_u32(bar + 64)) { atomicExch(bar + 64, 1u); out = 0.0; return false; }
+    }
+  }
+}
+
 __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen,
                                              unsigned base_count) {
   __shared__ int ok_s;
@@ -1535,33 +1566,6 @@ struct PeerArgs {
   double* base[8];            // exchange area of every rank (own one included)
   const int* send_v; const int* send_rank; const int* send_dst; int n_send;  // sorted by send_v
 };
-
-__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned tag, double v) {
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-  const unsigned long long t = (unsigned long long)tag << 32;
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(t | (bits & 0xffffffffull)) : "memory");
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + 1), "l"(t | (bits >> 32)) : "memory");
-}
-__device__ __forceinline__ unsigned long long ll_word(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// spins until both halves carry `tag`; false on timeout / abort (bar[64])
-__device__ __forceinline__ bool ll_load(const unsigned long long* p, unsigned tag, unsigned* bar, double& out) {
-  unsigned spins = 0;
-  while (true) {
-    const unsigned long long lo = ll_word(p), hi = ll_word(p + 1);
-    if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) {
-      out = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
-      return true;
-    }
-    if ((++spins & 0x3ffu) == 0u) {
-      __nanosleep(64);
-      if (spins > (1u << 23) || ld_acquire_u32(bar + 64)) { atomicExch(bar + 64, 1u); out = 0.0; return false; }
-    }
-  }
-}
 
 // Local grid barrier + cross-rank exchange of the three dot products, run by warp 0 of
 // every block.  On return tot3 (shared) holds the sums over all ranks.
