@@ -715,10 +715,16 @@ k_cg_persistent(DevSpec S, CgArgs A) {
       // one warp fetches the restricted residual (148 blocks polling the same 10 sectors
       // from every warp would serialise in one L2 slice)
       if (wid == 0) {
+        double rv[5];  // loads first, stores after (in-order warp: one round trip, not five)
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
           const unsigned c = lane + 32 * q;
-          if (c < nb) rcs[c] = __ldcg(A.rc + c);
+          rv[q] = c < nb ? __ldcg(A.rc + c) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const unsigned c = lane + 32 * q;
+          if (c < nb) rcs[c] = rv[q];
         }
       }
       __syncthreads();
@@ -839,8 +845,14 @@ k_cg_persistent(DevSpec S, CgArgs A) {
     long long c2 = clock64();
     // ---- every block: identical reduction of the partials --------------------------------
     if (wid < 3) {
-      double sacc = 0.0;
-      for (unsigned bq = lane; bq < nb; bq += 32) sacc += __ldcg(A.partials + (size_t)wid * nb + bq);
+      double pv[5];  // loads first, adds after: one L2 round trip instead of five
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const unsigned bq = lane + 32 * j;
+        pv[j] = bq < nb ? __ldcg(A.partials + (size_t)wid * nb + bq) : 0.0;
+      }
+      double sacc = (((pv[0] + pv[1]) + pv[2]) + pv[3]) + pv[4];
+      for (unsigned bq = lane + 160; bq < nb; bq += 32) sacc += __ldcg(A.partials + (size_t)wid * nb + bq);
       sacc = warp_sum(sacc);
       if (lane == 0) tot[wid] = sacc;
     }
@@ -1571,7 +1583,7 @@ struct PeerArgs {
 // every block.  On return tot3 (shared) holds the sums over all ranks.
 __device__ __forceinline__ bool xgrid_reduce(unsigned* bar, unsigned nblocks, unsigned& gen, unsigned base_count,
                                              const PeerArgs& P, const double* partials, unsigned tag, unsigned parity,
-                                             double* tot3) {
+                                             double* tot3, unsigned long long* dbg) {
   __shared__ int xok_s;
   __syncthreads();
   ++gen;
@@ -1582,13 +1594,24 @@ __device__ __forceinline__ bool xgrid_reduce(unsigned* bar, unsigned nblocks, un
     old = __shfl_sync(0xffffffffu, old, 0);
     int ok = 1;
     if (old - base_count == gen * nblocks - 1u) {  // last block of this rank
-      double t[3];
+      const long long d0 = clock64();
+      // all loads in flight before the first add: a warp executes in order, so a
+      // load-add loop would pay one L2 round trip per term (15 of them)
+      double t[3], pv[3][5];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const unsigned b = lane + 32 * j;
+          pv[k][j] = b < nblocks ? __ldcg(partials + (size_t)k * nblocks + b) : 0.0;
+        }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        double sacc = 0.0;
-        for (unsigned b = lane; b < nblocks; b += 32) sacc += __ldcg(partials + (size_t)k * nblocks + b);
+        double sacc = (((pv[k][0] + pv[k][1]) + pv[k][2]) + pv[k][3]) + pv[k][4];
+        for (unsigned b = lane + 160; b < nblocks; b += 32) sacc += __ldcg(partials + (size_t)k * nblocks + b);
         t[k] = warp_sum(sacc);
       }
+      const long long d1 = clock64();
       // lane -> (destination rank q, value k): slot [parity][my rank][k] of rank q
       if (lane < 3 * P.nranks) {
         const int q = lane / 3, k = lane - 3 * q;
@@ -1604,6 +1627,11 @@ __device__ __forceinline__ bool xgrid_reduce(unsigned* bar, unsigned nblocks, un
         ok = ll_load(src, tag, bar, v);
       }
       ok = __all_sync(0xffffffffu, ok);
+      if (lane == 0 && dbg) {  // FB_VERBOSE: where the last block spends the rendezvous
+        const long long d2 = clock64();
+        atomicAdd(dbg, (unsigned long long)(d1 - d0));
+        atomicAdd(dbg + 1, (unsigned long long)(d2 - d1));
+      }
       if (lane == 0) st_release_u32(bar + 32, gen);  // opens the local barrier (on failure bar[64] is set)
     } else if (lane == 0) {
       unsigned spins = 0;
@@ -1619,15 +1647,18 @@ __device__ __forceinline__ bool xgrid_reduce(unsigned* bar, unsigned nblocks, un
     ok = __shfl_sync(0xffffffffu, ok, 0);
     // every block adds the per-rank totals in rank order (the words are complete: the last
     // block saw them before it opened the barrier)
-    if (ok && lane < 3) {
-      double sacc = 0.0;
-      for (int q = 0; q < P.nranks; ++q) {
+    {
+      double val = 0.0;  // lane -> (rank q, value k): every word is fetched at once
+      if (ok && lane < 3 * P.nranks) {
+        const int q = lane / 3, k = lane - 3 * q;
         const unsigned long long* src =
-            (const unsigned long long*)P.base[P.rank] + FB_XR + ((parity * 8 + q) * 3 + lane) * 2;
+            (const unsigned long long*)P.base[P.rank] + FB_XR + ((parity * 8 + q) * 3 + k) * 2;
         const unsigned long long lo = ll_word(src), hi = ll_word(src + 1);
-        sacc += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+        val = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
       }
-      tot3[lane] = sacc;
+      double sacc = 0.0;
+      for (int q = 0; q < P.nranks; ++q) sacc += __shfl_sync(0xffffffffu, val, q * 3 + (lane % 3));  // rank order
+      if (ok && lane < 3) tot3[lane] = sacc;
     }
     if (lane == 0) xok_s = ok;
   }
@@ -1783,10 +1814,16 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
     // ---- coarse correction u = D^-1 r + Z E^-1 Z^T r, then the boundary entries go out ----
     if (coarse) {
       if (wid == 0) {
+        double rv[5];  // loads first, stores after (in-order warp: one round trip, not five)
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
           const unsigned c = lane + 32 * q;
-          if (c < nb) rcs[c] = __ldcg(A.rc + c);
+          rv[q] = c < nb ? __ldcg(A.rc + c) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const unsigned c = lane + 32 * q;
+          if (c < nb) rcs[c] = rv[q];
         }
       }
       __syncthreads();
@@ -1911,7 +1948,8 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
     }
     const long long c1 = clock64();
     if (failed) atomicExch(A.bar + 64, 1u);  // a halo word never arrived: everybody leaves at the rendezvous
-    if (!xgrid_reduce(A.bar, nb, gen, base_count, P, A.partials, utag, (unsigned)it & 1u, tot)) return;
+    if (!xgrid_reduce(A.bar, nb, gen, base_count, P, A.partials, utag, (unsigned)it & 1u, tot,
+                      (unsigned long long*)(A.sc + 16))) return;
     const long long c2 = clock64();
     const double gamma_new = tot[0], delta = tot[1], uu = tot[2];
     if (it == 0 && A.Einv != nullptr) thr2 = A.rel2 * uu;  // relative to ||M^-1 b|| of this M
@@ -2230,6 +2268,7 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
   }
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
   FB_CHECK(ctx, cudaMemsetAsync(A.bar, 0, 130 * sizeof(unsigned), ctx->stream));
+  FB_CHECK(ctx, cudaMemsetAsync(ctx->d_sc + 16, 0, 2 * sizeof(double), ctx->stream));
   A.bar_base = 0u;
   void* args[] = {(void*)&S, (void*)&A, (void*)&P};
   const void* fn = nullptr;
@@ -2253,7 +2292,11 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
   ctx->peer_seq += (unsigned)fl[1] + 2u;  // same on every rank: the iteration count is
   if (getenv("FB_VERBOSE") && fl[1] > 0 && ctx->peer_rank == 0) {
     double ph[5];
+    unsigned long long dbg[2];
     FB_CHECK(ctx, cudaMemcpy(ph, ctx->d_sc + 8, sizeof(ph), cudaMemcpyDeviceToHost));
+    FB_CHECK(ctx, cudaMemcpy(dbg, ctx->d_sc + 16, sizeof(dbg), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[fb] peer CG last block per rendezvous: sum of partials %.0f cycles, exchange (store + wait for "
+            "all ranks) %.0f cycles\n", (double)dbg[0] / fl[1], (double)dbg[1] / fl[1]);
     fprintf(stderr, "[fb] peer CG ranks=%d G=%d smem=%d parts=%d coarse=%d its=%d: cycles/iteration spmv+dots %.0f, rendezvous %.0f, "
             "scalars %.0f, update+push %.0f, local barrier %.0f\n", ctx->peer_n, G, A.rows_in_smem, A.blk_rng != nullptr, A.Einv != nullptr, fl[1], ph[0] / fl[1],
             ph[1] / fl[1], ph[2] / fl[1], ph[3] / fl[1], ph[4] / fl[1]);
