@@ -227,14 +227,26 @@ class Context:
         self.torch.index_select(raw.view(self.nv, width), 0, self._perm_dev, out=slot[0].view(self.nv, width))
         return slot[0]
 
-    def nodal_from_device(self, tensor, width=1):
-        if self.perm is None:
-            return tensor.cpu().numpy()
-        if self._perm_dev is None:
-            self._perm_dev = self.torch.as_tensor(self.perm, dtype=self.torch.long, device=self.device)
-        user = self.torch.empty_like(tensor)
-        user.view(self.nv, width).index_copy_(0, self._perm_dev, tensor.view(self.nv, width))
-        return user.cpu().numpy()
+    def nodal_from_device(self, tensor, width=1, out=None):
+        """Device vector -> host array in the user's numbering (scatter on the device, then
+        one copy through a pinned staging buffer into ``out``, or into a new array)."""
+        torch = self.torch
+        if self.perm is not None:
+            if self._perm_dev is None:
+                self._perm_dev = torch.as_tensor(self.perm, dtype=torch.long, device=self.device)
+            user = torch.empty_like(tensor)
+            user.view(self.nv, width).index_copy_(0, self._perm_dev, tensor.view(self.nv, width))
+            tensor = user
+        key = ("download", tensor.numel())
+        pinned = self._keep.get(key)
+        if pinned is None:
+            pinned = self._keep[key] = torch.empty(tensor.numel(), dtype=torch.float64).pin_memory()
+        pinned.copy_(tensor, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        if out is None:
+            return pinned.numpy().copy()
+        out[:] = pinned.numpy()
+        return out
 
     def dofs_to_device_numbering(self, dofs, ns):
         dofs = np.asarray(dofs, dtype=np.int64)
@@ -418,7 +430,7 @@ class B200NewtonSolver:
             C.byref(n_its), C.byref(reason), C.byref(fnorm), C.byref(lin))
         ctx._check(rc)
         self.u_dev = u_dev
-        p.u.x.array[:] = ctx.nodal_from_device(u_dev, ns)
+        ctx.nodal_from_device(u_dev, ns, out=p.u.x.array)
         self.solver.its = n_its.value
         self.solver.reason = reason.value
         self.solver.linear_its = lin.value

@@ -345,13 +345,36 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
     for (long long e = 0; e < (long long)deg * S.npairs; ++e) J[rowbase + e] = 0.0;
 
   const double mscale = 1.0 / (double)(D1 * (D1 + 1));
-  for (int e = S.v2c_ptr[v]; e < S.v2c_ptr[v + 1]; ++e) {
-    const int packed = S.v2c_idx[e];
+  // The chain  v2c_idx -> cells -> coords  is three dependent global loads per cell and a
+  // thread issues in order, so it is software-pipelined by hand: the cell index is fetched
+  // two iterations ahead and the cell's vertex ids one iteration ahead; only the coordinate
+  // loads of the current cell remain on the critical path.
+  const int e_begin = S.v2c_ptr[v], e_end = S.v2c_ptr[v + 1];
+  int pk_cur = e_begin < e_end ? S.v2c_idx[e_begin] : 0;
+  int pk_nxt = e_begin + 1 < e_end ? S.v2c_idx[e_begin + 1] : pk_cur;
+  int a_cur[FB_MAX_D1];
+#pragma unroll
+  for (int j = 0; j < D1; ++j) a_cur[j] = S.cells[(long long)(pk_cur / D1) * D1 + j];
+  for (int e = e_begin; e < e_end; ++e) {
+    const int packed = pk_cur;
     const long long c = packed / D1;
     const int i = packed - (int)c * D1;
     int a[FB_MAX_D1];
     double X[FB_MAX_D1][3], G[FB_MAX_D1][3];
-    fb_load_cell<DIM>(S, c, a, X);
+#pragma unroll
+    for (int j = 0; j < D1; ++j) {
+      a[j] = a_cur[j];
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) X[j][k] = S.coords[(long long)a[j] * DIM + k];
+    }
+    {  // prefetch for the next two iterations
+      const int pk_far = e + 2 < e_end ? S.v2c_idx[e + 2] : pk_nxt;
+      const long long c_nxt = pk_nxt / D1;
+#pragma unroll
+      for (int j = 0; j < D1; ++j) a_cur[j] = S.cells[c_nxt * D1 + j];
+      pk_cur = pk_nxt;
+      pk_nxt = pk_far;
+    }
     const double vol = fb_geometry<DIM>(X, G);
     const int tag = S.cell_tag[c];
     int slot[FB_MAX_D1];
