@@ -262,17 +262,32 @@ def main():
         warm = max(args.warmup, 0)
         for _ in range(min(warm, 1)):
             run_cpu_sample(8)
-        vals = [run_cpu_sample(args.cpu_n) for _ in range(max(1, min(args.steps, 3)))]
-        v = max(x[0] for x in vals)
-        ndofs, secs, its = vals[0][1], min(x[2] for x in vals), vals[0][3]
-        sample = (f"same problem on an n={args.cpu_n} mesh ({ndofs} dofs): numpy assembly + SuperLU "
-                  f"Newton solve, {secs:.2f} s per solve, {its} Newton it")
+        # all host cores: the port is single-threaded (numpy + SuperLU), so one independent
+        # replica of the sample per core, started together; throughput = work of all / wall
+        import multiprocessing as mp
+
+        cores = max(1, min(os.cpu_count() or 1, 64))
+        os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+        reps = max(1, min(args.steps, 3))
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            with mp.get_context("fork").Pool(cores) as pool:
+                vals = pool.map(run_cpu_sample, [args.cpu_n] * cores)
+            wall = time.perf_counter() - t0
+            best = wall if best is None else min(best, wall)
+        ndofs, its = vals[0][1], vals[0][3]
+        secs = best
+        v = cores * ndofs * its / best
+        sample = (f"{cores} independent replicas (one per host core) of the same problem on an "
+                  f"n={args.cpu_n} mesh ({ndofs} dofs each): numpy assembly + SuperLU Newton solve, "
+                  f"{secs:.2f} s wall for all, {its} Newton it")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / its,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "restated reference path (numpy/scipy SuperLU), NOT dolfinx+PETSc "
                     "(absent from this image)"}))
