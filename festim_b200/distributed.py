@@ -334,20 +334,22 @@ class DistributedNewtonSolver:
         ctx, spec, lp, lib = self.ctx, self.spec, self.part, self.ctx.lib
         scal = spec.scalar_values()
         T = spec.temperature
-        parts = [scal.tobytes()]
+        # change detection: memcmp against the last uploaded copy (as the single-GPU solver)
+        parts = [scal]
         if isinstance(T, fem.Function):
-            parts.append(T.x.array.tobytes())
+            parts.append(T.x.array)
         elif T is not None:
-            parts.append(np.float64(T.value).tobytes())
-        for f in spec.fields:
-            parts.append(f.x.array.tobytes())
-        sig = hash(b"".join(parts))
+            parts.append(np.float64(T.value))
+        parts += [f.x.array for f in spec.fields]
         bc_vals = np.concatenate([bc.values() for bc in self._bc_forms])[self._bc_pick] \
             if self._bc_forms else np.zeros(0)
         bc_dev = ctx.to_device("bc_vals", bc_vals) if len(bc_vals) else None
         ctx._check(lib.fb_set_dirichlet_values(ctx.h, ctx.ptr(bc_dev)))
-        if sig == self._signature:
+        last = self._signature
+        if last is not None and len(last) == len(parts) and all(
+                np.array_equal(a, b) for a, b in zip(last, parts)):
             return
+        sig = [np.array(a, copy=True) for a in parts]
         self._signature = sig
         ctx._check(lib.fb_set_scalars(ctx.h, len(scal), _np_ptr(scal, C.c_double)))
         if isinstance(T, fem.Function):
@@ -495,27 +497,34 @@ class DistributedNewtonSolver:
             not t.derivs for t in spec.vterms + spec.fterms)
 
     def _gather(self, u):
-        """Owned values of every rank -> the global host vector on every rank
-        (one padded NCCL all-gather, then a device->host copy)."""
+        """Owned values of every rank -> the global host vector on every rank: one padded
+        NCCL all-gather, a device-side scatter into global dof order and one copy through a
+        pinned buffer (no per-rank host indexing)."""
         torch, dist, p = self.torch, self.dist, self.problem
         n_own = self.part.n_owned * self.ns
         if self.nranks == 1:
             p.u.x.array[self.owned_gdofs] = u[:n_own].cpu().numpy()
             return
-        if not hasattr(self, "_gather_index"):
+        if not hasattr(self, "_gather_perm"):
             counts = [None] * self.nranks
             dist.all_gather_object(counts, self.owned_gdofs)
-            self._gather_counts = [len(c) for c in counts]
-            self._gather_index = counts
-            self._gather_pad = max(self._gather_counts)
-        pad = self._gather_pad
-        send = torch.zeros(pad, dtype=torch.float64, device=u.device)
-        send[:n_own] = u[:n_own]
-        recv = torch.empty(pad * self.nranks, dtype=torch.float64, device=u.device)
-        dist.all_gather_into_tensor(recv, send)
-        host = recv.cpu().numpy().reshape(self.nranks, pad)
-        for q in range(self.nranks):
-            p.u.x.array[self._gather_index[q]] = host[q, : self._gather_counts[q]]
+            pad = max(len(c) for c in counts)
+            n_glob = p.u.x.array.size
+            perm = np.full(pad * self.nranks, n_glob, dtype=np.int64)   # padding -> a dummy slot
+            for q, c in enumerate(counts):
+                perm[q * pad: q * pad + len(c)] = c
+            self._gather_pad = pad
+            self._gather_perm = torch.as_tensor(perm, device=u.device)
+            self._gather_send = torch.zeros(pad, dtype=torch.float64, device=u.device)
+            self._gather_recv = torch.empty(pad * self.nranks, dtype=torch.float64, device=u.device)
+            self._gather_glob = torch.empty(n_glob + 1, dtype=torch.float64, device=u.device)
+            self._gather_host = torch.empty(n_glob + 1, dtype=torch.float64).pin_memory()
+        self._gather_send[:n_own] = u[:n_own]
+        dist.all_gather_into_tensor(self._gather_recv, self._gather_send)
+        self._gather_glob.index_copy_(0, self._gather_perm, self._gather_recv)
+        self._gather_host.copy_(self._gather_glob, non_blocking=True)
+        torch.cuda.current_stream(u.device).synchronize()
+        p.u.x.array[:] = self._gather_host.numpy()[:-1]
 
 
 class _ProblemView:
