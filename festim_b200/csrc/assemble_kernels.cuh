@@ -103,6 +103,7 @@ __device__ __forceinline__ void fb_cell_coeffs_body(const DevSpec& S, double* __
             acc += S.quad_w[off + q] * exp(-S.diff_energies[slot] / (FB_KB * T));
           } else {
             PointCtx P;
+        P.cgrad = nullptr;
             for (int k = 0; k < DIM; ++k) {
               double x = 0.0;
               for (int j = 0; j <= DIM; ++j) x += bary[j] * X[j][k];
@@ -149,6 +150,7 @@ __device__ __forceinline__ void fb_load_cells_body(const DevSpec& S, double* __r
     for (int q = 0; q < nq; ++q) {
       const double* bary = S.quad_bary + (long long)(off + q) * (DIM + 1);
       PointCtx P;
+        P.cgrad = nullptr;
       for (int k = 0; k < DIM; ++k) {
         double x = 0.0;
         for (int j = 0; j <= DIM; ++j) x += bary[j] * X[j][k];
@@ -238,6 +240,7 @@ __device__ __forceinline__ void fb_facets_body(const DevSpec& S, int mode, const
     for (int q = 0; q < (F != nullptr ? nqF : 0); ++q) {
       const double* bary = S.quad_bary + (long long)(offF + q) * (DIM + 1);  // uniform pool stride; DIM entries used
       PointCtx P;
+        P.cgrad = nullptr;
       for (int k = 0; k < DIM; ++k) {
         double x = 0.0;
         for (int j = 0; j < DIM; ++j) x += bary[j] * Y[j][k];
@@ -276,6 +279,7 @@ __device__ __forceinline__ void fb_facets_body(const DevSpec& S, int mode, const
       for (int q = 0; q < nqJ; ++q) {
         const double* bary = S.quad_bary + (long long)(offJ + q) * (DIM + 1);
         PointCtx P;
+        P.cgrad = nullptr;
         for (int k = 0; k < DIM; ++k) {
           double x = 0.0;
           for (int j = 0; j < DIM; ++j) x += bary[j] * Y[j][k];
@@ -423,6 +427,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
           for (int q = 0; q < nq; ++q) {
             const double* bary = S.quad_bary + (long long)(off + q) * D1;
             PointCtx P;
+        P.cgrad = nullptr;
             for (int k = 0; k < DIM; ++k) {
               double x = 0.0;
               for (int j = 0; j < D1; ++j) x += bary[j] * X[j][k];
@@ -523,6 +528,14 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
     for (int j = 0; j < D1; ++j)
       for (int k = 0; k < DIM; ++k) Gflat[j * DIM + k] = G[j][k];
     double cq[FB_MAX_NS], cpq[FB_MAX_NS];
+    double cgr[FB_MAX_NS * 3];  // cell gradient of every species (constant on a P1 cell)
+    for (int s = 0; s < ns; ++s)
+      for (int k = 0; k < 3; ++k) {
+        double gk = 0.0;
+        if (k < DIM)
+          for (int j = 0; j < D1; ++j) gk += uc[j][s] * G[j][k];
+        cgr[s * 3 + k] = gk;
+      }
     for (int pass = 0; pass < 2; ++pass) {
       // pass 0: residual with the F rule; pass 1: derivatives with the J rule
       if (pass == 0 && !doF) continue;
@@ -532,6 +545,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
         const double* bary = S.quad_bary + (long long)(off + q) * D1;
         const double wq = S.quad_w[off + q] * vol * bary[i];
         PointCtx P;
+        P.cgrad = nullptr;
         for (int k = 0; k < DIM; ++k) {
           double x = 0.0;
           for (int j = 0; j < D1; ++j) x += bary[j] * X[j][k];
@@ -544,7 +558,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
           cq[s] = cv; cpq[s] = cp;
         }
         P.c = cq; P.cprev = cpq; P.verts = a; P.bary = bary; P.nverts = D1;
-        P.cverts = a; P.G = Gflat; P.ncverts = D1; P.tdim = DIM;
+        P.cverts = a; P.G = Gflat; P.ncverts = D1; P.tdim = DIM; P.cgrad = cgr;
         for (int t = 0; t < S.n_vterms; ++t) {
           const int* h = S.vterm_hdr + t * 8;
           if (h[0] != tag || !h[6]) continue;
@@ -556,7 +570,10 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
             }
           } else {
             for (int dd = 0; dd < h[5]; ++dd) {
-              const int dep = S.deriv_species[h[4] + dd];
+              // code = species (derivative w.r.t. the value at the point, weight phi_j) or
+              // species + ns * (1 + k) (w.r.t. component k of its cell gradient, weight d_k phi_j)
+              const int code = S.deriv_species[h[4] + dd];
+              const int dep = code % ns, gcomp = code / ns - 1;
               const double dv = wq * fb_prog_eval(S, S.deriv_prog[h[4] + dd], P);
               for (int r = 0; r < h[3]; ++r) {
                 const int s = S.row_species[h[2] + r];
@@ -564,7 +581,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
                 const double coef = S.row_coef[h[2] + r] * dv;
                 const int jp = S.pair_idx[s * ns + dep];
                 for (int j = 0; j < D1; ++j) {
-                  const double aij = coef * bary[j];
+                  const double aij = coef * (gcomp < 0 ? bary[j] : G[j][gcomp]);
                   const int bcj = S.bc_map[(long long)a[j] * ns + dep];
                   if (bcj >= 0) {
                     if (doF) Facc[s] += aij * (S.bc_vals[bcj] - uc[j][dep]);

@@ -102,6 +102,7 @@ struct PointCtx {
   double T;
   const double* c;       // [ns] species at the point
   const double* cprev;   // [ns] previous-step species at the point
+  const double* cgrad;   // [ns][3] gradient of the species in the owning cell (P1: constant), or nullptr
   const int* verts;      // vertices of the integration entity
   const double* bary;    // barycentric coordinates w.r.t. verts
   int nverts;

@@ -71,11 +71,17 @@ class TestIntegral:
             ]
         return self._derivs
 
+    def grad_derivatives(self):
+        """[((species, component), d expr / d (d_component c_species))]: dependence on the
+        cell gradient of an unknown."""
+        return [(key, ufl.diff(self.expr, ("species_grad", key))) for key in ufl.species_grads_in(self.expr)]
+
     def degree_F(self):
         return ufl.estimate_degree(self.expr) + 1
 
     def degree_J(self):
         degs = [ufl.estimate_degree(d) + 2 for _, d in self.derivatives()]
+        degs += [ufl.estimate_degree(d) + 1 for _, d in self.grad_derivatives()]  # trial gradient: degree 0
         return max(degs) if degs else None
 
 

@@ -15,6 +15,7 @@ import warnings
 import numpy as np
 
 from festim_b200 import boundary_conditions as _bcs
+from festim_b200.mesh import CoordinateSystem
 from festim_b200 import exports as _exports
 from festim_b200 import fem, forms, ufl
 from festim_b200 import species as _species
@@ -256,6 +257,16 @@ class HydrogenTransportProblem(ProblemBase):
                     if not vol.material.D:
                         meta = {"arrhenius": (vol.material.get_D_0(spe), vol.material.get_E_D(spe))}
                     F += forms.DiffusionIntegral(spe, D, self.dx(vol.id), meta)
+                    # cylindrical / spherical coordinates (reference :886-908):
+                    #   r^m D grad(u).grad(v / r^m) = D grad(u).grad(v) - (m D / r) d_r u v,
+                    # m = 1 (cylindrical), 2 (spherical), r = x[0]: the cartesian term above
+                    # plus a metric term that depends on the gradient of the unknown
+                    csys = self.mesh.coordinate_system
+                    if csys != CoordinateSystem.CARTESIAN:
+                        m = {CoordinateSystem.CYLINDRICAL: 1.0, CoordinateSystem.SPHERICAL: 2.0}[csys]
+                        r = ufl.SpatialCoordinate(self.mesh.mesh)[0]
+                        F += forms.TestIntegral(spe, -(m * ufl.as_expr(D) / r) * ufl.SpeciesGrad(spe, 0),
+                                                self.dx(vol.id), {"metric": m})
                 if self.settings.transient:
                     F += forms.TestIntegral(spe, (u - u_n) / self.dt, self.dx(vol.id),
                                             {"mass": 1.0})
@@ -351,6 +362,10 @@ class HydrogenTransportProblem(ProblemBase):
             if isinstance(export, _exports.Profile1DExport):
                 export.data, export.t = [], []
             if isinstance(export, _exports.DerivedQuantity):
+                if self.mesh.coordinate_system != CoordinateSystem.CARTESIAN:   # reference :486-493
+                    raise NotImplementedError(
+                        "Derived quantity exports are not implemented for "
+                        f"{self.mesh.coordinate_system!s} meshes")
                 export.t, export.data = [], []
         # D_global snapshot: the temperature the DG1 diffusivity was last
         # interpolated with (:632-670, refreshed per :1049-1056)

@@ -81,6 +81,8 @@ class _Gen:
         elif isinstance(ex, ufl.SpeciesRef):
             arr = "P.cprev" if ex.prev else "P.c"
             r = f"{arr}[{pb.species_index[ex.species]}]"
+        elif isinstance(ex, ufl.SpeciesGrad):
+            r = f"(P.cgrad ? P.cgrad[{pb.species_index[ex.species] * 3 + ex.i}] : 0.0)"
         elif isinstance(ex, ufl.Neg):
             r = self.tmp(f"-{self.emit(ex.a)}")
         elif isinstance(ex, ufl.Math):

@@ -159,12 +159,16 @@ class KernelSpec:
                         terms.append(term)
                     reaction_terms[key].rows.append((s, float(itg.meta["sign"])))
                     for dep, _ in reaction_terms[key].derivs:
-                        pairs.add((s, dep))
+                        pairs.add((s, dep % ns))
                 else:
                     term = self._point_term(tag, itg.expr, [(s, 1.0)], sidx)
+                    if kind != "dx" and any(dep >= ns for dep, _ in term.derivs):
+                        raise NotImplementedError(
+                            "boundary terms depending on the gradient of an unknown (weak Dirichlet, "
+                            "SURVEY 8f2) are not lowered yet")
                     terms.append(term)
                     for dep, _ in term.derivs:
-                        pairs.add((s, dep))
+                        pairs.add((s, dep % ns))
 
         self.diff_progs = []
         for tag, s, pid in self._generic_D:
@@ -390,7 +394,14 @@ class KernelSpec:
             return None
         deps = ufl.species_in(expr)
         derivs = [(sidx[spe], self.programs.add(ufl.diff(expr, ("species", spe)))) for spe in deps]
-        u_dep = bool(deps) or ufl.depends_on(expr, ufl.SpeciesRef)
+        # dependence on the cell gradient of a species (metric terms of cylindrical /
+        # spherical coordinates): derivative code = species + ns * (1 + component); the
+        # Jacobian weight of column vertex j is d_k phi_j instead of phi_j
+        gdeps = ufl.species_grads_in(expr)
+        ns = len(sidx)
+        derivs += [(sidx[spe] + ns * (1 + comp),
+                    self.programs.add(ufl.diff(expr, ("species_grad", (spe, comp))))) for spe, comp in gdeps]
+        u_dep = bool(deps) or bool(gdeps) or ufl.depends_on(expr, ufl.SpeciesRef)
         return PointTerm(tag, self.programs.add(expr), rows, derivs, u_dep)
 
     def _add_rule(self, tdim, degree):

@@ -304,10 +304,15 @@ class Mesh:
             self._coordinate_system = CoordinateSystem.from_string(value)
         else:
             raise ValueError("coordinate_system must be of type str or CoordinateSystem")
-        if self._coordinate_system != CoordinateSystem.CARTESIAN:
-            raise NotImplementedError(
-                "only cartesian coordinates are in scope of the B200 backend (SURVEY 8f4)"
-            )
+        if self._mesh is not None:
+            self.check_mesh_dim_coords()
+
+    def check_mesh_dim_coords(self):
+        """Reference ``mesh.py:221-233``."""
+        if self.coordinate_system == CoordinateSystem.SPHERICAL and self.vdim != 1:
+            raise AttributeError("spherical coordinates can be used for one-dimensional domains only")
+        if self.coordinate_system == CoordinateSystem.CYLINDRICAL and self.vdim == 3:
+            raise AttributeError("cylindrical coordinates cannot be used for 3D domains")
 
     @property
     def vdim(self):

@@ -158,6 +158,19 @@ class SpeciesRef(Expr):
         return f"c{'_n' if self.prev else ''}[{getattr(self.species, 'name', None)}]"
 
 
+class SpeciesGrad(Expr):
+    """Component ``i`` of the gradient of an unknown species (cell-wise constant for P1):
+    what ``ufl.grad(u)[i]`` is inside an integrand.  Used by the metric terms of cylindrical
+    and spherical coordinates (reference hydrogen_transport_problem.py:886-908)."""
+
+    def __init__(self, species, i):
+        self.species = species
+        self.i = int(i)
+
+    def __repr__(self):
+        return f"d{self.i}(c[{getattr(self.species, 'name', None)}])"
+
+
 class Sum(Expr):
     def __init__(self, a, b):
         self.a, self.b = a, b
@@ -511,7 +524,15 @@ def diff(expr, var):
     if isinstance(ex, SpeciesRef):
         if kind == "species":
             return Const(1.0 if (ex.species is key and not ex.prev) else 0.0)
-        raise NotImplementedError("spatial gradient of an unknown inside an expression")
+        if kind == "species_grad":
+            return Const(0.0)
+        if ex.prev:
+            raise NotImplementedError("spatial gradient of the previous solution inside an expression")
+        return SpeciesGrad(ex.species, key)
+    if isinstance(ex, SpeciesGrad):
+        if kind == "species_grad":  # key = (species, component)
+            return Const(1.0 if (ex.species is key[0] and ex.i == key[1]) else 0.0)
+        return Const(0.0)  # P1: second derivatives vanish; no dependence on the point value
     if isinstance(ex, Sum):
         return diff(ex.a, var) + diff(ex.b, var)
     if isinstance(ex, Neg):
@@ -639,6 +660,18 @@ def species_in(ex):
     return out
 
 
+def species_grads_in(ex):
+    """(species, component) pairs whose gradient the expression depends on."""
+    out = []
+
+    def visit(node):
+        if isinstance(node, SpeciesGrad) and (node.species, node.i) not in out:
+            out.append((node.species, node.i))
+
+    walk(as_expr(ex), visit)
+    return out
+
+
 # --------------------------------------------------------------------------
 # numpy evaluation
 # --------------------------------------------------------------------------
@@ -676,6 +709,8 @@ def evaluate(ex, env):
         return env["field_grad"](ex.function, ex.i)
     if isinstance(ex, SpeciesRef):
         return env["species_prev" if ex.prev else "species"](ex.species)
+    if isinstance(ex, SpeciesGrad):
+        return env["species_grad"](ex.species, ex.i)
     if isinstance(ex, Sum):
         return evaluate(ex.a, env) + evaluate(ex.b, env)
     if isinstance(ex, Product):
@@ -725,6 +760,8 @@ def estimate_degree(ex, field_degree=1, species_degree=1):
         return max(field_degree - 1, 0)
     if isinstance(ex, SpeciesRef):
         return species_degree
+    if isinstance(ex, SpeciesGrad):
+        return max(species_degree - 1, 0)
     if isinstance(ex, Sum):
         return max(estimate_degree(ex.a), estimate_degree(ex.b))
     if isinstance(ex, (Product, Division)):
@@ -759,6 +796,7 @@ OP_LT, OP_GT, OP_LE, OP_GE, OP_EQ, OP_NE, OP_AND, OP_OR, OP_NOT = 30, 31, 32, 33
 OP_SELECT, OP_MAX, OP_MIN = 40, 41, 42
 OP_T = 6  # temperature at the point (T constant or P1 field of the problem)
 OP_SPECIES_PREV = 7
+OP_SPECIES_GRAD = 8   # iarg = species * 4 + component
 OP_STORE, OP_LOAD = 50, 51  # common-subexpression temporaries
 MAX_TEMPS = 16
 
@@ -817,6 +855,8 @@ class ProgramBuilder:
             k = ("g", id(ex.function), ex.i)
         elif isinstance(ex, SpeciesRef):
             k = ("s", id(ex.species), ex.prev)
+        elif isinstance(ex, SpeciesGrad):
+            k = ("sg", id(ex.species), ex.i)
         elif isinstance(ex, Neg):
             k = ("neg", self._skey(ex.a, memo))
         elif isinstance(ex, Math):
@@ -912,6 +952,9 @@ class ProgramBuilder:
         if isinstance(ex, SpeciesRef):
             out.append((OP_SPECIES_PREV if ex.prev else OP_SPECIES,
                         self.species_index[ex.species], 0.0))
+            return (1, 1)
+        if isinstance(ex, SpeciesGrad):
+            out.append((OP_SPECIES_GRAD, self.species_index[ex.species] * 4 + ex.i, 0.0))
             return (1, 1)
         if isinstance(ex, Neg):
             d = self._emit(ex.a, out)

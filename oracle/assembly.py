@@ -67,8 +67,13 @@ class FormAssembler:
         def species_prev(spe):
             return interp(u_n.reshape(-1, ns)[:, self.species.index(spe)])
 
+        def species_grad(spe, i):
+            # P1: constant on the owning cell (metric terms of curvilinear coordinates)
+            nodal = u.reshape(-1, ns)[:, self.species.index(spe)]
+            return np.einsum("ea,ea->e", nodal[self._cell_verts], G[:, :, i])[:, None]
+
         return {"x": xq, "field": field, "field_grad": field_grad,
-                "species": species, "species_prev": species_prev}
+                "species": species, "species_prev": species_prev, "species_grad": species_grad}
 
     def assemble(self, u, u_n, want_J=True):
         """Returns (F, J) without boundary conditions; J is CSR or None."""
@@ -136,6 +141,13 @@ class FormAssembler:
                                         for j in range(d + 1):
                                             add_J(verts[:, i], s, verts[:, j], s2,
                                                   vol * ((dq * bary[:, i] * bary[:, j]) @ w))
+                                for (spe2, comp), dex in itg.grad_derivatives():
+                                    s2 = self.species.index(spe2)
+                                    dq = np.broadcast_to(ufl.evaluate(dex, env), (len(cells), len(w)))
+                                    for i in range(d + 1):
+                                        for j in range(d + 1):   # d_comp phi_j is constant on the cell
+                                            add_J(verts[:, i], s, verts[:, j], s2,
+                                                  vol * G[:, j, comp] * ((dq * bary[:, i]) @ w))
                         elif itg.kind == "advection":
                             velq = np.einsum("qa,ead->eqd", bary, itg.velocity.array[verts])
                             if which == "F":
