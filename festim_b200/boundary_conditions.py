@@ -16,10 +16,6 @@ class DirichletBCBase:
     def __init__(self, subdomain, value, enforce_weakly=False, penalty=None):
         self.subdomain = subdomain
         self.value = value
-        if enforce_weakly:
-            raise NotImplementedError(
-                "weakly enforced (Nitsche) Dirichlet BCs are not lowered yet (SURVEY 8f2)"
-            )
         self.enforce_weakly = enforce_weakly
         self.penalty = penalty
         self.value_fenics = None
@@ -55,6 +51,32 @@ class DirichletBCBase:
         if callable(self.value) and not isinstance(self.value, ufl.Expr):
             return "T" in self.value.__code__.co_varnames
         return False
+
+    def numerical_flux(self, u, D, mesh, species):
+        """Numerical flux leaving the domain through a weakly enforced boundary
+        (``dirichlet_bc.py:170-209``): ``-D n.grad(u) + penalty D / h (u - value)``."""
+        assert self.penalty is not None, "Penalty parameter must be given for weakly enforced Dirichlet BCs"
+        assert self.value_fenics is not None, "value_fenics must be defined for weakly enforced Dirichlet BCs"
+        n = ufl.FacetNormal(gdim=mesh.gdim)
+        h = ufl.Circumradius(mesh)
+        gradu = [ufl.SpeciesGrad(species, i) for i in range(mesh.gdim)]
+        ndotgrad = n[0] * gradu[0]
+        for i in range(1, mesh.gdim):
+            ndotgrad = ndotgrad + n[i] * gradu[i]
+        D = ufl.as_expr(D)
+        return -D * ndotgrad + self.penalty * D / h * (u - ufl.as_expr(self.value_fenics))
+
+    def weak_formulation(self, species, u, ds, D, mesh):
+        """Symmetric Nitsche terms (``dirichlet_bc.py:211-244``) as integrals of the form
+        machinery: consistency + penalty tested with v, symmetry term tested with n.grad(v)."""
+        from festim_b200 import forms
+
+        ds_bc = ds(self.subdomain.id)
+        return [
+            forms.TestIntegral(species, self.numerical_flux(u, D, mesh, species), ds_bc, {"nitsche": "flux"}),
+            forms.NormalGradTestIntegral(species, -ufl.as_expr(D) * (u - ufl.as_expr(self.value_fenics)), ds_bc,
+                                         {"nitsche": "symmetry"}),
+        ]
 
     def define_surface_subdomain_vertices(self, facet_meshtags, mesh):
         """Vertices of the facets tagged with this BC's surface id

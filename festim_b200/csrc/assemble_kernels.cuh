@@ -58,6 +58,29 @@ __device__ __forceinline__ void fb_load_cell(const DevSpec& S, long long c, int*
   }
 }
 
+// circumradius of a simplex (what ufl.Circumradius evaluates to on affine cells)
+template <int DIM>
+__device__ __forceinline__ double fb_circumradius(const double (*X)[3]) {
+  auto dist = [&](int p, int q) {
+    double d = 0.0;
+    for (int k = 0; k < DIM; ++k) d += (X[p][k] - X[q][k]) * (X[p][k] - X[q][k]);
+    return sqrt(d);
+  };
+  if (DIM == 1) return 0.5 * dist(0, 1);
+  if (DIM == 2) {
+    const double a = dist(1, 2), b = dist(0, 2), c = dist(0, 1);
+    const double area = 0.5 * fabs((X[1][0] - X[0][0]) * (X[2][1] - X[0][1]) - (X[2][0] - X[0][0]) * (X[1][1] - X[0][1]));
+    return a * b * c / (4.0 * area);
+  }
+  // tetrahedron: edges from vertex 0 (a, b, c) times their opposite edges (A, B, C)
+  const double aA = dist(0, 1) * dist(2, 3), bB = dist(0, 2) * dist(1, 3), cC = dist(0, 3) * dist(1, 2);
+  const double ux = X[1][0] - X[0][0], uy = X[1][1] - X[0][1], uz = X[1][2] - X[0][2];
+  const double vx = X[2][0] - X[0][0], vy = X[2][1] - X[0][1], vz = X[2][2] - X[0][2];
+  const double wx = X[3][0] - X[0][0], wy = X[3][1] - X[0][1], wz = X[3][2] - X[0][2];
+  const double vol = fabs(ux * (vy * wz - vz * wy) - uy * (vx * wz - vz * wx) + uz * (vx * wy - vy * wx)) / 6.0;
+  return sqrt((aA + bB + cC) * (aA + bB - cC) * (aA - bB + cC) * (-aA + bB + cC)) / (24.0 * vol);
+}
+
 __device__ __forceinline__ double fb_temperature(const DevSpec& S, const int* verts, const double* bary,
                                                  int n) {
   if (!S.T_mode) return S.T_const;
@@ -103,7 +126,7 @@ __device__ __forceinline__ void fb_cell_coeffs_body(const DevSpec& S, double* __
             acc += S.quad_w[off + q] * exp(-S.diff_energies[slot] / (FB_KB * T));
           } else {
             PointCtx P;
-        P.cgrad = nullptr;
+        P.cgrad = nullptr; P.n[0] = P.n[1] = P.n[2] = 0.0; P.h = 0.0;
             for (int k = 0; k < DIM; ++k) {
               double x = 0.0;
               for (int j = 0; j <= DIM; ++j) x += bary[j] * X[j][k];
@@ -150,7 +173,7 @@ __device__ __forceinline__ void fb_load_cells_body(const DevSpec& S, double* __r
     for (int q = 0; q < nq; ++q) {
       const double* bary = S.quad_bary + (long long)(off + q) * (DIM + 1);
       PointCtx P;
-        P.cgrad = nullptr;
+        P.cgrad = nullptr; P.n[0] = P.n[1] = P.n[2] = 0.0; P.h = 0.0;
       for (int k = 0; k < DIM; ++k) {
         double x = 0.0;
         for (int j = 0; j <= DIM; ++j) x += bary[j] * X[j][k];
@@ -231,16 +254,48 @@ __device__ __forceinline__ void fb_facets_body(const DevSpec& S, int mode, const
     for (int k = 0; k < DIM; ++k) Gflat[j * DIM + k] = G[j][k];
   const int offF = S.quad_s[tag * 4], nqF = S.quad_s[tag * 4 + 1];
   const int offJ = S.quad_s[tag * 4 + 2], nqJ = S.quad_s[tag * 4 + 3];
+  // outward unit normal (minus the direction of the gradient of the basis function of the
+  // vertex opposite to the facet), circumradius of the cell, n . grad(phi_i) of every cell
+  // vertex, and - for solution-dependent terms - the cell gradient of every species
+  double nrm[3] = {0.0, 0.0, 0.0}, ng[FB_MAX_D1], cgr[FB_MAX_NS * 3];
+  {
+    int opp = 0;
+    for (int j = 0; j <= DIM; ++j) {
+      bool onf = false;
+      for (int k = 0; k < DIM; ++k) onf |= (a[j] == fv[k]);
+      if (!onf) opp = j;
+    }
+    double l = 0.0;
+    for (int k = 0; k < DIM; ++k) l += G[opp][k] * G[opp][k];
+    l = sqrt(l);
+    for (int k = 0; k < DIM; ++k) nrm[k] = -G[opp][k] / l;
+    for (int j = 0; j <= DIM; ++j) {
+      double d = 0.0;
+      for (int k = 0; k < DIM; ++k) d += nrm[k] * G[j][k];
+      ng[j] = d;
+    }
+  }
+  const double hcell = fb_circumradius<DIM>(X);
+  for (int s = 0; s < ns; ++s)
+    for (int k = 0; k < 3; ++k) {
+      double gk = 0.0;
+      if (mode == 1 && k < DIM)
+        for (int j = 0; j <= DIM; ++j) gk += u[(long long)a[j] * ns + s] * G[j][k];
+      cgr[s * 3 + k] = gk;
+    }
   double cq[FB_MAX_NS], cpq[FB_MAX_NS];
   for (int t = 0; t < S.n_fterms; ++t) {
     const int* h = S.fterm_hdr + t * 8;
     if (h[0] != tag || (h[6] != 0) != (mode == 1)) continue;
+    // rows: the facet vertices weighted by phi_i (test function v), or every vertex of the
+    // cell weighted by n . grad(phi_i) (test function entering through n . grad(v))
+    const bool gradtest = h[7] == 1;
+    const int nrow = gradtest ? DIM + 1 : DIM;
     // value
-    double acc[3] = {0.0, 0.0, 0.0};
+    double acc[FB_MAX_D1] = {0.0, 0.0, 0.0, 0.0};
     for (int q = 0; q < (F != nullptr ? nqF : 0); ++q) {
       const double* bary = S.quad_bary + (long long)(offF + q) * (DIM + 1);  // uniform pool stride; DIM entries used
       PointCtx P;
-        P.cgrad = nullptr;
       for (int k = 0; k < DIM; ++k) {
         double x = 0.0;
         for (int j = 0; j < DIM; ++j) x += bary[j] * Y[j][k];
@@ -258,28 +313,34 @@ __device__ __forceinline__ void fb_facets_body(const DevSpec& S, int mode, const
       }
       P.c = cq; P.cprev = cpq; P.verts = fv; P.bary = bary; P.nverts = DIM;
       P.cverts = a; P.G = Gflat; P.ncverts = DIM + 1; P.tdim = DIM;
+      P.cgrad = cgr; P.n[0] = nrm[0]; P.n[1] = nrm[1]; P.n[2] = nrm[2]; P.h = hcell;
       const double val = S.quad_w[offF + q] * fb_prog_eval(S, h[1], P);
-      for (int j = 0; j < DIM; ++j) acc[j] += val * bary[j];
+      for (int i = 0; i < nrow; ++i) acc[i] += val * (gradtest ? ng[i] : bary[i]);
     }
     if (F != nullptr)
       for (int r = 0; r < h[3]; ++r) {
         const int s = S.row_species[h[2] + r];
         const double coef = S.row_coef[h[2] + r] * area;
-        for (int j = 0; j < DIM; ++j) {
-          const long long dof = (long long)fv[j] * ns + s;
+        for (int i = 0; i < nrow; ++i) {
+          const long long dof = (long long)(gradtest ? a[i] : fv[i]) * ns + s;
           if (mode == 1 && S.bc_map[dof] >= 0) continue;
-          atomicAdd(&F[dof], coef * acc[j]);
+          atomicAdd(&F[dof], coef * acc[i]);
         }
       }
     if (mode != 1 || h[5] == 0) continue;
-    // derivatives: J entries and Dirichlet lifting
+    // derivatives: J entries and Dirichlet lifting.  Columns: the facet vertices weighted by
+    // phi_j (dependence on the value of a species at the point) or every vertex of the cell
+    // weighted by d_k phi_j (dependence on component k of its cell gradient)
     for (int dd = 0; dd < h[5]; ++dd) {
-      const int dep = S.deriv_species[h[4] + dd];
-      double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      const int code = S.deriv_species[h[4] + dd];
+      const int dep = code % ns, gcomp = code / ns - 1;
+      const int ncol = gcomp < 0 ? DIM : DIM + 1;
+      double M[FB_MAX_D1][FB_MAX_D1];
+      for (int i = 0; i < FB_MAX_D1; ++i)
+        for (int j = 0; j < FB_MAX_D1; ++j) M[i][j] = 0.0;
       for (int q = 0; q < nqJ; ++q) {
         const double* bary = S.quad_bary + (long long)(offJ + q) * (DIM + 1);
         PointCtx P;
-        P.cgrad = nullptr;
         for (int k = 0; k < DIM; ++k) {
           double x = 0.0;
           for (int j = 0; j < DIM; ++j) x += bary[j] * Y[j][k];
@@ -296,25 +357,30 @@ __device__ __forceinline__ void fb_facets_body(const DevSpec& S, int mode, const
         }
         P.c = cq; P.cprev = cpq; P.verts = fv; P.bary = bary; P.nverts = DIM;
         P.cverts = a; P.G = Gflat; P.ncverts = DIM + 1; P.tdim = DIM;
+        P.cgrad = cgr; P.n[0] = nrm[0]; P.n[1] = nrm[1]; P.n[2] = nrm[2]; P.h = hcell;
         const double dv = S.quad_w[offJ + q] * fb_prog_eval(S, S.deriv_prog[h[4] + dd], P);
-        for (int i = 0; i < DIM; ++i)
-          for (int j = 0; j < DIM; ++j) M[i][j] += dv * bary[i] * bary[j];
+        for (int i = 0; i < nrow; ++i) {
+          const double wi = dv * (gradtest ? ng[i] : bary[i]);
+          for (int j = 0; j < ncol; ++j) M[i][j] += wi * (gcomp < 0 ? bary[j] : G[j][gcomp]);
+        }
       }
       for (int r = 0; r < h[3]; ++r) {
         const int s = S.row_species[h[2] + r];
         const double coef = S.row_coef[h[2] + r] * area;
         const int jp = S.pair_idx[s * ns + dep];
-        for (int i = 0; i < DIM; ++i) {
-          const long long rdof = (long long)fv[i] * ns + s;
+        for (int i = 0; i < nrow; ++i) {
+          const int vi = gradtest ? a[i] : fv[i];
+          const long long rdof = (long long)vi * ns + s;
           if (S.bc_map[rdof] >= 0) continue;
-          for (int j = 0; j < DIM; ++j) {
-            const long long cdof = (long long)fv[j] * ns + dep;
+          for (int j = 0; j < ncol; ++j) {
+            const int vj = gcomp < 0 ? fv[j] : a[j];
+            const long long cdof = (long long)vj * ns + dep;
             const int bcj = S.bc_map[cdof];
             const double aij = coef * M[i][j];
             if (bcj >= 0) {
               if (F != nullptr) atomicAdd(&F[rdof], aij * (S.bc_vals[bcj] - u[cdof]));
             } else if (J != nullptr) {
-              atomicAdd(&J[fb_entry(S, fv[i], s, fb_find_slot(S, fv[i], fv[j]), jp)], aij);
+              atomicAdd(&J[fb_entry(S, vi, s, fb_find_slot(S, vi, vj), jp)], aij);
             }
           }
         }
@@ -427,7 +493,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
           for (int q = 0; q < nq; ++q) {
             const double* bary = S.quad_bary + (long long)(off + q) * D1;
             PointCtx P;
-        P.cgrad = nullptr;
+        P.cgrad = nullptr; P.n[0] = P.n[1] = P.n[2] = 0.0; P.h = 0.0;
             for (int k = 0; k < DIM; ++k) {
               double x = 0.0;
               for (int j = 0; j < D1; ++j) x += bary[j] * X[j][k];
@@ -545,7 +611,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
         const double* bary = S.quad_bary + (long long)(off + q) * D1;
         const double wq = S.quad_w[off + q] * vol * bary[i];
         PointCtx P;
-        P.cgrad = nullptr;
+        P.cgrad = nullptr; P.n[0] = P.n[1] = P.n[2] = 0.0; P.h = 0.0;
         for (int k = 0; k < DIM; ++k) {
           double x = 0.0;
           for (int j = 0; j < D1; ++j) x += bary[j] * X[j][k];

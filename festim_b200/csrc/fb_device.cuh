@@ -103,6 +103,8 @@ struct PointCtx {
   const double* c;       // [ns] species at the point
   const double* cprev;   // [ns] previous-step species at the point
   const double* cgrad;   // [ns][3] gradient of the species in the owning cell (P1: constant), or nullptr
+  double n[3];           // outward unit normal of the boundary facet (facet terms)
+  double h;              // circumradius of the owning cell
   const int* verts;      // vertices of the integration entity
   const double* bary;    // barycentric coordinates w.r.t. verts
   int nverts;

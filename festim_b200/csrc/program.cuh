@@ -6,7 +6,7 @@
 
 enum {
   OP_CONST = 0, OP_X = 1, OP_SCALAR = 2, OP_FIELD = 3, OP_FIELDGRAD = 4, OP_SPECIES = 5,
-  OP_T = 6, OP_SPECIES_PREV = 7, OP_SPECIES_GRAD = 8,
+  OP_T = 6, OP_SPECIES_PREV = 7, OP_SPECIES_GRAD = 8, OP_NORMAL = 9, OP_CIRCUMRADIUS = 15,
   OP_ADD = 10, OP_MUL = 11, OP_DIV = 12, OP_POW = 13, OP_NEG = 14,
   OP_MATH = 20,
   OP_LT = 30, OP_GT = 31, OP_LE = 32, OP_GE = 33, OP_EQ = 34, OP_NE = 35, OP_AND = 36,
@@ -56,6 +56,8 @@ __device__ inline double fb_prog_eval(const DevSpec& S, int pid, const PointCtx&
       case OP_SPECIES: FB_PUSH(P.c[ia]); break;
       case OP_SPECIES_PREV: FB_PUSH(P.cprev[ia]); break;
       case OP_SPECIES_GRAD: FB_PUSH(P.cgrad ? P.cgrad[(ia >> 2) * 3 + (ia & 3)] : 0.0); break;
+      case OP_NORMAL: FB_PUSH(P.n[ia]); break;
+      case OP_CIRCUMRADIUS: FB_PUSH(P.h); break;
       case OP_LOAD: FB_PUSH(tmp[ia]); break;
       case OP_STORE: tmp[ia] = t; break;
       case OP_FIELD: {

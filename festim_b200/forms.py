@@ -85,6 +85,22 @@ class TestIntegral:
         return max(degs) if degs else None
 
 
+class NormalGradTestIntegral(TestIntegral):
+    """``expr * (n . grad(v)) ds``: the symmetry term of Nitsche's method.  The test
+    function enters through its normal derivative, so every vertex of the cell behind the
+    facet gets a row (reference ``dirichlet_bc.py:239-241``)."""
+
+    kind = "ngradtest"
+
+    def degree_F(self):
+        return ufl.estimate_degree(self.expr)          # grad(v) is constant on the cell
+
+    def degree_J(self):
+        degs = [ufl.estimate_degree(d) + 1 for _, d in self.derivatives()]
+        degs += [ufl.estimate_degree(d) for _, d in self.grad_derivatives()]
+        return max(degs) if degs else None
+
+
 class AdvectionIntegral:
     kind = "advection"
 

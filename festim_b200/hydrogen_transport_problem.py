@@ -290,6 +290,13 @@ class HydrogenTransportProblem(ProblemBase):
                 F += forms.TestIntegral(bc.species, -ufl.as_expr(bc.value_fenics),
                                         self.ds(bc.subdomain.id), {"flux": bc})
 
+        for bc in self.boundary_conditions:  # weakly enforced Dirichlet conditions (:956-966)
+            if isinstance(bc, _bcs.FixedConcentrationBC) and bc.enforce_weakly:
+                vol = self.volume_subdomain_of_surface(bc.subdomain)
+                D = vol.material.get_diffusion_coefficient(self.mesh.mesh, T, bc.species)
+                for itg in bc.weak_formulation(bc.species, bc.species.solution, self.ds, D, self.mesh.mesh):
+                    F += itg
+
         for adv_term in self.advection_terms:
             for spe in adv_term.species:
                 F += forms.AdvectionIntegral(spe, adv_term.velocity.fenics_object,
@@ -308,6 +315,23 @@ class HydrogenTransportProblem(ProblemBase):
                         F += forms.TestIntegral(spe, spe.solution, self.dx(vol.id), {"filler": 1.0})
 
         self.formulation = F
+
+    def volume_subdomain_of_surface(self, surface):
+        """Volume subdomain the tagged boundary facets of ``surface`` belong to
+        (reference :595-626: deduced from the facet -> cell connectivity and the tags)."""
+        mesh = self.mesh.mesh
+        facets = self.facet_meshtags.find(surface.id)
+        if len(facets) == 0:
+            raise ValueError(f"surface subdomain {surface.id} has no facets")
+        ctag = np.zeros(mesh.num_cells, dtype=np.int64)
+        ctag[self.volume_meshtags.indices] = self.volume_meshtags.values
+        ids = np.unique(ctag[mesh.bfacet_cell[facets]])
+        if len(ids) != 1:
+            raise ValueError(f"surface subdomain {surface.id} touches several volume subdomains: {ids}")
+        for vol in self.volume_subdomains:
+            if vol.id == ids[0]:
+                return vol
+        raise ValueError(f"surface subdomain {surface.id} cannot be mapped to a volume subdomain")
 
     # ---- per-step updates (reference :999-1042) --------------------------------
     def update_time_dependent_values(self):

@@ -83,6 +83,10 @@ class _Gen:
             r = f"{arr}[{pb.species_index[ex.species]}]"
         elif isinstance(ex, ufl.SpeciesGrad):
             r = f"(P.cgrad ? P.cgrad[{pb.species_index[ex.species] * 3 + ex.i}] : 0.0)"
+        elif isinstance(ex, ufl.NormalComp):
+            r = f"P.n[{ex.i}]"
+        elif isinstance(ex, ufl.CellCircumradius):
+            r = "P.h"
         elif isinstance(ex, ufl.Neg):
             r = self.tmp(f"-{self.emit(ex.a)}")
         elif isinstance(ex, ufl.Math):

@@ -48,7 +48,8 @@ MAX_NS = 16
 
 
 class PointTerm:
-    def __init__(self, tag, value_prog, rows, derivs, u_dependent):
+    def __init__(self, tag, value_prog, rows, derivs, u_dependent, test_kind=0):
+        self.test_kind = test_kind  # 0: v, 1: n . grad(v) (facet terms only)
         self.tag = tag
         self.value_prog = value_prog
         self.rows = rows          # [(species index, coefficient)]
@@ -162,10 +163,11 @@ class KernelSpec:
                         pairs.add((s, dep % ns))
                 else:
                     term = self._point_term(tag, itg.expr, [(s, 1.0)], sidx)
-                    if kind != "dx" and any(dep >= ns for dep, _ in term.derivs):
-                        raise NotImplementedError(
-                            "boundary terms depending on the gradient of an unknown (weak Dirichlet, "
-                            "SURVEY 8f2) are not lowered yet")
+                    if itg.kind == "ngradtest":
+                        if kind == "dx":
+                            raise NotImplementedError("n . grad(v) test functions exist on facets only")
+                        term.test_kind = 1
+                        term.u_dependent = True   # evaluated by the facet kernel with the cell data
                     terms.append(term)
                     for dep, _ in term.derivs:
                         pairs.add((s, dep % ns))
@@ -445,7 +447,7 @@ class KernelSpec:
             hdr = np.zeros((max(len(terms), 1), 8), dtype=np.int32)
             for i, t in enumerate(terms):
                 hdr[i] = [t.tag, t.value_prog, len(row_species), len(t.rows),
-                          len(deriv_species), len(t.derivs), int(t.u_dependent), 0]
+                          len(deriv_species), len(t.derivs), int(t.u_dependent), int(t.test_kind)]
                 for s, c in t.rows:
                     row_species.append(s)
                     row_coef.append(c)

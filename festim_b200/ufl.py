@@ -171,6 +171,24 @@ class SpeciesGrad(Expr):
         return f"d{self.i}(c[{getattr(self.species, 'name', None)}])"
 
 
+class NormalComp(Expr):
+    """Component ``i`` of the outward unit normal of the boundary facet being integrated
+    (``ufl.FacetNormal(mesh)[i]``)."""
+
+    def __init__(self, i):
+        self.i = int(i)
+
+    def __repr__(self):
+        return f"n[{self.i}]"
+
+
+class CellCircumradius(Expr):
+    """Circumradius of the cell owning the integration entity (``ufl.Circumradius(mesh)``)."""
+
+    def __repr__(self):
+        return "h"
+
+
 class Sum(Expr):
     def __init__(self, a, b):
         self.a, self.b = a, b
@@ -515,7 +533,7 @@ def diff(expr, var):
     """d expr / d var.  ``var`` is ("x", i) or ("species", species_object)."""
     ex = as_expr(expr)
     kind, key = var
-    if isinstance(ex, Const) or isinstance(ex, ConstantRef) or isinstance(ex, FieldGrad):
+    if isinstance(ex, (Const, ConstantRef, FieldGrad, NormalComp, CellCircumradius)):
         return Const(0.0)
     if isinstance(ex, Coord):
         return Const(1.0 if (kind == "x" and ex.i == key) else 0.0)
@@ -589,6 +607,16 @@ def grad(expr, gdim=None):
         raise NotImplementedError("gradient of a vector expression")
     gdim = gdim or _infer_gdim(expr)
     return Vector([diff(expr, ("x", i)) for i in range(gdim)])
+
+
+def FacetNormal(mesh=None, gdim=None):
+    """Outward unit normal of the exterior facet (vector expression)."""
+    g = gdim or getattr(mesh, "gdim", None) or _default_gdim[0] or 3
+    return Vector([NormalComp(i) for i in range(g)])
+
+
+def Circumradius(mesh=None):
+    return CellCircumradius()
 
 
 def div(vec):
@@ -711,6 +739,10 @@ def evaluate(ex, env):
         return env["species_prev" if ex.prev else "species"](ex.species)
     if isinstance(ex, SpeciesGrad):
         return env["species_grad"](ex.species, ex.i)
+    if isinstance(ex, NormalComp):
+        return env["normal"](ex.i)
+    if isinstance(ex, CellCircumradius):
+        return env["circumradius"]()
     if isinstance(ex, Sum):
         return evaluate(ex.a, env) + evaluate(ex.b, env)
     if isinstance(ex, Product):
@@ -762,6 +794,8 @@ def estimate_degree(ex, field_degree=1, species_degree=1):
         return species_degree
     if isinstance(ex, SpeciesGrad):
         return max(species_degree - 1, 0)
+    if isinstance(ex, (NormalComp, CellCircumradius)):
+        return 0  # affine simplices: piecewise constant
     if isinstance(ex, Sum):
         return max(estimate_degree(ex.a), estimate_degree(ex.b))
     if isinstance(ex, (Product, Division)):
@@ -797,6 +831,7 @@ OP_SELECT, OP_MAX, OP_MIN = 40, 41, 42
 OP_T = 6  # temperature at the point (T constant or P1 field of the problem)
 OP_SPECIES_PREV = 7
 OP_SPECIES_GRAD = 8   # iarg = species * 4 + component
+OP_NORMAL, OP_CIRCUMRADIUS = 9, 15  # facet normal component / circumradius of the owning cell
 OP_STORE, OP_LOAD = 50, 51  # common-subexpression temporaries
 MAX_TEMPS = 16
 
@@ -857,6 +892,10 @@ class ProgramBuilder:
             k = ("s", id(ex.species), ex.prev)
         elif isinstance(ex, SpeciesGrad):
             k = ("sg", id(ex.species), ex.i)
+        elif isinstance(ex, NormalComp):
+            k = ("n", ex.i)
+        elif isinstance(ex, CellCircumradius):
+            k = ("h",)
         elif isinstance(ex, Neg):
             k = ("neg", self._skey(ex.a, memo))
         elif isinstance(ex, Math):
@@ -955,6 +994,12 @@ class ProgramBuilder:
             return (1, 1)
         if isinstance(ex, SpeciesGrad):
             out.append((OP_SPECIES_GRAD, self.species_index[ex.species] * 4 + ex.i, 0.0))
+            return (1, 1)
+        if isinstance(ex, NormalComp):
+            out.append((OP_NORMAL, ex.i, 0.0))
+            return (1, 1)
+        if isinstance(ex, CellCircumradius):
+            out.append((OP_CIRCUMRADIUS, 0, 0.0))
             return (1, 1)
         if isinstance(ex, Neg):
             d = self._emit(ex.a, out)

@@ -46,7 +46,7 @@ class FormAssembler:
         self.degrees = form.quadrature_degrees()
 
     # -- evaluation environment at points given by barycentric coords ------------
-    def _env(self, verts, bary, G, u, u_n):
+    def _env(self, verts, bary, G, u, u_n, normal=None, circumradius=None):
         """verts (ne, k) vertex ids of each entity, bary (nq, k)."""
         mesh, ns = self.mesh, self.ns
         xq = np.einsum("qa,ead->eqd", bary, mesh.coords[verts])
@@ -73,7 +73,9 @@ class FormAssembler:
             return np.einsum("ea,ea->e", nodal[self._cell_verts], G[:, :, i])[:, None]
 
         return {"x": xq, "field": field, "field_grad": field_grad,
-                "species": species, "species_prev": species_prev, "species_grad": species_grad}
+                "species": species, "species_prev": species_prev, "species_grad": species_grad,
+                "normal": (lambda i: normal[:, i][:, None]),
+                "circumradius": (lambda: circumradius[:, None])}
 
     def assemble(self, u, u_n, want_J=True):
         """Returns (F, J) without boundary conditions; J is CSR or None."""
@@ -168,28 +170,49 @@ class FormAssembler:
                 fverts = mesh.bfacets[facets]                       # (nf, d)
                 fcells = mesh.bfacet_cell[facets]
                 _, G, _ = cell_geometry(mesh, fcells)
-                self._cell_verts = mesh.cells[fcells]
+                cverts = mesh.cells[fcells]                          # (nf, d+1)
+                self._cell_verts = cverts
                 area = facet_measures(mesh, fverts)
+                # outward unit normal: minus the direction of grad(phi) of the vertex opposite
+                # to the facet; n . grad(phi_i) for every vertex of the cell; circumradius
+                opp = np.array([[v not in fv for v in cv] for cv, fv in zip(cverts, fverts)])
+                gopp = G[opp]
+                normal = -gopp / np.linalg.norm(gopp, axis=1)[:, None]
+                ng = np.einsum("ed,ead->ea", normal, G)               # (nf, d+1)
+                hcell = circumradius(mesh, fcells)
                 for which, deg in (("F", degF), ("J", degJ)):
                     if which == "J" and (not want_J or degJ is None):
                         continue
                     bary, w = quadrature.rule(d - 1, deg)
-                    env = self._env(fverts, bary, G, u, u_n)
+                    env = self._env(fverts, bary, G, u, u_n, normal, hcell)
                     for itg in itgs:
-                        assert itg.kind == "test"
+                        assert itg.kind in ("test", "ngradtest")
                         s = self.species.index(itg.species)
+                        gradtest = itg.kind == "ngradtest"
+                        # rows: facet vertices weighted by phi_i(q), or cell vertices weighted by
+                        # the constant n . grad(phi_i)
+                        if gradtest:
+                            rverts = cverts
+                            rw = [np.repeat(ng[:, i][:, None], len(w), axis=1) for i in range(d + 1)]
+                        else:
+                            rverts = fverts
+                            rw = [np.repeat(bary[:, i][None, :], len(facets), axis=0) for i in range(d)]
                         if which == "F":
                             vq = np.broadcast_to(ufl.evaluate(itg.expr, env), (len(facets), len(w)))
-                            for i in range(d):
-                                add_F(fverts[:, i], s, area * ((vq * bary[:, i]) @ w))
+                            for i in range(rverts.shape[1]):
+                                add_F(rverts[:, i], s, area * ((vq * rw[i]) @ w))
                         else:
-                            for spe2, dex in itg.derivatives():
-                                s2 = self.species.index(spe2)
+                            colsets = [(self.species.index(spe2), dex, fverts,
+                                     [np.repeat(bary[:, j][None, :], len(facets), axis=0) for j in range(d)])
+                                    for spe2, dex in itg.derivatives()]
+                            colsets += [(self.species.index(spe2), dex, cverts,
+                                      [np.repeat(G[:, j, comp][:, None], len(w), axis=1) for j in range(d + 1)])
+                                     for (spe2, comp), dex in itg.grad_derivatives()]
+                            for s2, dex, cv, cw in colsets:
                                 dq = np.broadcast_to(ufl.evaluate(dex, env), (len(facets), len(w)))
-                                for i in range(d):
-                                    for j in range(d):
-                                        add_J(fverts[:, i], s, fverts[:, j], s2,
-                                              area * ((dq * bary[:, i] * bary[:, j]) @ w))
+                                for i in range(rverts.shape[1]):
+                                    for j in range(cv.shape[1]):
+                                        add_J(rverts[:, i], s, cv[:, j], s2, area * ((dq * rw[i] * cw[j]) @ w))
         J = None
         if want_J:
             if rows:
@@ -199,6 +222,22 @@ class FormAssembler:
                 J = sp.csr_matrix((self.N, self.N))
             J.sum_duplicates()
         return F, J
+
+
+def circumradius(mesh, cells):
+    """Circumradius of affine simplices (``ufl.Circumradius``)."""
+    x = mesh.coords[mesh.cells[cells]]
+    d = mesh.tdim
+    dist = lambda p, q: np.linalg.norm(x[:, p] - x[:, q], axis=1)
+    if d == 1:
+        return 0.5 * dist(0, 1)
+    if d == 2:
+        e1, e2 = x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]
+        area = 0.5 * np.abs(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0])
+        return dist(1, 2) * dist(0, 2) * dist(0, 1) / (4.0 * area)
+    aA, bB, cC = dist(0, 1) * dist(2, 3), dist(0, 2) * dist(1, 3), dist(0, 3) * dist(1, 2)
+    vol = np.abs(np.linalg.det(x[:, 1:] - x[:, :1])) / 6.0
+    return np.sqrt((aA + bB + cC) * (aA + bB - cC) * (aA - bB + cC) * (-aA + bB + cC)) / (24.0 * vol)
 
 
 def facet_measures(mesh, fverts):
