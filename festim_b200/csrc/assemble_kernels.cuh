@@ -102,9 +102,16 @@ __device__ __forceinline__ void fb_cell_coeffs_body(const DevSpec& S, double* __
   // uniform temperature and Arrhenius slots only: the cell means are the same number
   // everywhere, no geometry or nodal data needed
   const bool uniform = !S.T_mode && S.n_slots == S.n_diffE;
-  if (!uniform) fb_load_cell<DIM>(S, c, a, X);
+  const bool need_G = S.n_slots > S.n_diffE;  // generic D(x, T, ...) programs need the geometry
+  if (!uniform) {
+    if (need_G) {
+      fb_load_cell<DIM>(S, c, a, X);
+    } else {  // Arrhenius slots of a nodal temperature: vertex ids only, no coordinates
+#pragma unroll
+      for (int j = 0; j <= DIM; ++j) a[j] = S.cells[c * (DIM + 1) + j];
+    }
+  }
   const int tag = S.cell_tag[c];
-  const bool need_G = S.n_slots > S.n_diffE;
   if (need_G) fb_geometry<DIM>(X, G);
   double Gflat[FB_MAX_D1 * 3];
   if (need_G)
