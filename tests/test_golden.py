@@ -75,3 +75,46 @@ def test_diffusion_coefficient_matches_reference():
         m = F.Material(D_0=case["D_0"], E_D=case["E_D"])
         got = float(ufl.evaluate(m.get_diffusion_coefficient(None, case["T"], None), {}))
         assert got == pytest.approx(case["expected"], rel=1e-15)
+
+
+def test_surface_reaction_flux_matches_reference():
+    """reference src/festim/boundary_conditions/surface_reaction.py:57-85 and :129-146: the
+    flux K_d P - K_r c_A c_B of every reactant, A + A listed twice."""
+    surf = F.SurfaceSubdomain1D(id=2, x=1.0)
+    for case in load("surface_reaction_flux.json"):
+        A, B = F.Species("A"), F.Species("B")
+        A.solution, B.solution = ufl.Const(case["cA"]), ufl.Const(case["cB"])
+        reactants = [A, A] if case["same"] else [A, B]
+        bc = F.SurfaceReactionBC(reactant=reactants, gas_pressure=case["P"], k_r0=case["k_r0"],
+                                 E_kr=case["E_kr"], k_d0=case["k_d0"], E_kd=case["E_kd"], subdomain=surf)
+        assert len(bc.flux_bcs) == case["n_fluxes"]
+        assert [fb.species.name for fb in bc.flux_bcs] == case["flux_species"]
+        for fb, expected in zip(bc.flux_bcs, case["expected"]):
+            fb.create_value_fenics(None, ufl.Const(case["T"]), None)
+            got = float(ufl.evaluate(fb.value_fenics, {}))
+            assert got == pytest.approx(expected, rel=1e-13, abs=0.0)
+
+
+def test_nitsche_terms_match_reference():
+    """reference src/festim/boundary_conditions/dirichlet_bc.py:170-244: numerical flux
+    -D n.grad(u) + penalty D / h (u - g) and the full symmetric weak form at a point, for a
+    given u, v and their gradients."""
+    surf = F.SurfaceSubdomain1D(id=2, x=1.0)
+    for case in load("nitsche_terms.json"):
+        H = F.Species("H")
+        bc = F.FixedConcentrationBC(subdomain=surf, value=case["g"], species=H, enforce_weakly=True,
+                                    penalty=case["penalty"])
+        bc.value_fenics = ufl.Const(case["g"])
+        mesh = type("M", (), {"gdim": case["gdim"]})()
+        u = ufl.SpeciesRef(H)
+        n, gu, gv = np.array(case["n"]), np.array(case["grad_u"]), np.array(case["grad_v"])
+        env = {"species": lambda s: case["u"], "species_grad": lambda s, i: gu[i],
+               "normal": lambda i: n[i], "circumradius": lambda: case["h"]}
+        flux = float(ufl.evaluate(bc.numerical_flux(u, case["D"], mesh, H), env))
+        assert flux == pytest.approx(case["numerical_flux"], rel=1e-12)
+        terms = bc.weak_formulation(H, u, lambda sid: ("ds", sid), case["D"], mesh)
+        assert [t.kind for t in terms] == ["test", "ngradtest"]
+        # integrand at the point: (term tested with v) * v + (term tested with n.grad v) * n.grad(v)
+        total = float(ufl.evaluate(terms[0].expr, env)) * case["v"] + \
+            float(ufl.evaluate(terms[1].expr, env)) * float(n @ gv)
+        assert total == pytest.approx(case["weak_form"], rel=1e-11)

@@ -120,8 +120,42 @@ class Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             module.Constant = Constant
         if name == "ufl":
             module.exp = np.exp
+            # enough of ufl for the boundary-condition formulas pinned below: the unknown and
+            # the test function are floats carrying their gradient, geometry comes from CTX
+            module.FacetNormal = lambda mesh: CTX["n"]
+            module.Circumradius = lambda mesh: CTX["h"]
+            module.inner = lambda a, b: float(np.dot(a, b))
+            module.grad = lambda u: u.grad
         if name == "petsc4py.PETSc":
             module.IntType = np.int32
+
+
+CTX = {}
+
+
+class WithGrad(float):
+    """A number that also knows its gradient (stands in for a P1 function at a point)."""
+
+    def __new__(cls, value, grad):
+        obj = float.__new__(cls, value)
+        obj.grad = np.asarray(grad, dtype=float)
+        return obj
+
+
+class Immutable(np.ndarray):
+    """ndarray whose in-place operators return new arrays, like (immutable) UFL expressions:
+    the reference writes ``product *= concentration`` on the species' own solution object."""
+
+    def __imul__(self, other):
+        return np.multiply(np.asarray(self), other).view(Immutable)
+
+
+class FakeMeasure:
+    def ufl_domain(self):
+        return None
+
+    def __call__(self, subdomain_id):
+        return 1.0
 
 
 def main():
@@ -216,6 +250,48 @@ def main():
         diff.append({"D_0": D_0, "E_D": E_D, "T": T,
                      "expected": float(m.get_diffusion_coefficient(None, T, None))})
     json.dump(diff, open(os.path.join(out_dir, "diffusion_coefficient.json"), "w"), indent=0)
+    # --- SurfaceReactionBC flux (surface_reaction.py:57-85) ---------------------------------
+    surf = F.SurfaceSubdomain(id=2)
+    sreac = []
+    for _ in range(40):
+        k_r0, E_kr = float(10 ** rng.uniform(-30, 0)), float(rng.uniform(0, 1.5))
+        k_d0, E_kd = float(10 ** rng.uniform(-10, 20)), float(rng.uniform(0, 1.5))
+        T, P = float(rng.uniform(300, 1200)), float(10 ** rng.uniform(-3, 5))
+        cA, cB = float(10 ** rng.uniform(0, 22)), float(10 ** rng.uniform(0, 22))
+        same = bool(rng.random() < 0.3)
+        A, B = F.Species("A"), F.Species("B")
+        # ndarray: accepted by the value_fenics setter
+        A.solution, B.solution = np.array([cA]).view(Immutable), np.array([cB]).view(Immutable)
+        reactants = [A, A] if same else [A, B]
+        bc = F.SurfaceReactionBC(reactant=reactants, gas_pressure=P, k_r0=k_r0, E_kr=E_kr, k_d0=k_d0,
+                                 E_kd=E_kd, subdomain=surf)
+        for fb in bc.flux_bcs:
+            fb.create_value_fenics(None, T, None)
+        sreac.append({"k_r0": k_r0, "E_kr": E_kr, "k_d0": k_d0, "E_kd": E_kd, "T": T, "P": P, "cA": cA,
+                      "cB": cB, "same": same, "n_fluxes": len(bc.flux_bcs),
+                      "flux_species": [fb.species.name for fb in bc.flux_bcs],
+                      "expected": [float(np.ravel(fb.value_fenics)[0]) for fb in bc.flux_bcs]})
+    json.dump(sreac, open(os.path.join(out_dir, "surface_reaction_flux.json"), "w"), indent=0)
+
+    # --- Nitsche terms of a weakly enforced Dirichlet BC (dirichlet_bc.py:170-244) -----------
+    nitsche = []
+    for _ in range(40):
+        gdim = int(rng.integers(1, 4))
+        n = rng.standard_normal(gdim)
+        n /= np.linalg.norm(n)
+        CTX["n"], CTX["h"] = n, float(10 ** rng.uniform(-4, 0))
+        u = WithGrad(rng.uniform(0.1, 10.0), rng.standard_normal(gdim) * 10)
+        v = WithGrad(rng.uniform(0.0, 1.0), rng.standard_normal(gdim) * 10)
+        D, g, penalty = float(10 ** rng.uniform(-10, 1)), float(rng.uniform(0.1, 10.0)), float(10 ** rng.uniform(0, 3))
+        bc = F.FixedConcentrationBC(subdomain=surf, value=g, species=F.Species("H"), enforce_weakly=True,
+                                    penalty=penalty)
+        bc._value_fenics = g
+        nitsche.append({"gdim": gdim, "n": n.tolist(), "h": CTX["h"], "u": float(u), "grad_u": u.grad.tolist(),
+                        "v": float(v), "grad_v": v.grad.tolist(), "D": D, "g": g, "penalty": penalty,
+                        "numerical_flux": float(bc.numerical_flux(u, D, None)),
+                        "weak_form": float(bc.weak_formulation(u, v, FakeMeasure(), D))})
+    json.dump(nitsche, open(os.path.join(out_dir, "nitsche_terms.json"), "w"), indent=0)
+
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
     print("golden vectors written to", out_dir)
