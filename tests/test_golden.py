@@ -118,3 +118,13 @@ def test_nitsche_terms_match_reference():
         total = float(ufl.evaluate(terms[0].expr, env)) * case["v"] + \
             float(ufl.evaluate(terms[1].expr, env)) * float(n @ gv)
         assert total == pytest.approx(case["weak_form"], rel=1e-11)
+
+
+def test_solubility_laws_match_reference():
+    """reference sieverts_bc.py:8-11 (S_0 exp(-E_S/k_B/T) sqrt(P)) and henrys_bc.py:8-11."""
+    from festim_b200.boundary_conditions import henrys_law, sieverts_law
+
+    for case in load("solubility_laws.json"):
+        args = (ufl.Const(case["T"]), case["c0"], case["E"], case["P"])
+        assert float(ufl.evaluate(sieverts_law(*args), {})) == pytest.approx(case["sieverts"], rel=1e-14)
+        assert float(ufl.evaluate(henrys_law(*args), {})) == pytest.approx(case["henry"], rel=1e-14)

@@ -292,6 +292,18 @@ def main():
                         "weak_form": float(bc.weak_formulation(u, v, FakeMeasure(), D))})
     json.dump(nitsche, open(os.path.join(out_dir, "nitsche_terms.json"), "w"), indent=0)
 
+    # --- Sieverts' and Henry's laws (sieverts_bc.py:8-11, henrys_bc.py:8-11) ----------------
+    from festim.boundary_conditions.henrys_bc import henrys_law
+    from festim.boundary_conditions.sieverts_bc import sieverts_law
+
+    laws = []
+    for _ in range(40):
+        T, c0, E, P = (float(rng.uniform(250, 1500)), float(10 ** rng.uniform(15, 24)), float(rng.uniform(0, 1.5)),
+                       float(10 ** rng.uniform(-3, 6)))
+        laws.append({"T": T, "c0": c0, "E": E, "P": P, "sieverts": float(sieverts_law(T, c0, E, P)),
+                     "henry": float(henrys_law(T, c0, E, P))})
+    json.dump(laws, open(os.path.join(out_dir, "solubility_laws.json"), "w"), indent=0)
+
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
     print("golden vectors written to", out_dir)
