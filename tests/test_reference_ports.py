@@ -134,3 +134,106 @@ def test_derived_quantities_on_prescribed_field_gpu():
     vals_g = _check_prescribed_1d(*_prescribed_1d(None))
     vals_r = _check_prescribed_1d(*_prescribed_1d(OracleBackend()))
     assert np.allclose(vals_g, vals_r, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------
+# D_global (reference test/test_h_transport_problem.py:245-320): the diffusivity the surface
+# flux uses is the DG1 interpolant of the owning cell's Arrhenius law at the vertex
+# temperature - different temperatures and different materials at the two ends.  Observed
+# through SurfaceFlux on u = x (du/dx = 1): flux(x=L) = -D(L), flux(x=0) = +D(0).
+# ---------------------------------------------------------------------------------------
+def _d_global_case(kind, backend):
+    if kind == "temperatures":
+        mats = [F.Material(D_0=1.5, E_D=0.1, name="m")] * 2
+        temperature = lambda x: 100.0 * x[0] + 50
+        expected = [1.5 * np.exp(-0.1 / (F.k_B * 50)), 1.5 * np.exp(-0.1 / (F.k_B * 450))]
+    else:
+        mats = [F.Material(D_0=1.0, E_D=0.1, name="L"), F.Material(D_0=2.0, E_D=0.2, name="R")]
+        temperature = 500
+        expected = [1.0 * np.exp(-0.1 / (F.k_B * 500)), 2.0 * np.exp(-0.2 / (F.k_B * 500))]
+    m = F.HydrogenTransportProblem()
+    m.mesh = F.Mesh1D(np.linspace(0, 4, num=101))
+    vols = [F.VolumeSubdomain1D(id=1, borders=[0, 2], material=mats[0]),
+            F.VolumeSubdomain1D(id=2, borders=[2, 4], material=mats[1])]
+    left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=4)
+    m.subdomains = vols + [left, right]
+    H = F.Species("H")
+    m.species = [H]
+    m.temperature = temperature
+    m.boundary_conditions = [F.DirichletBC(subdomain=left, value=0, species=H)]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    if backend is not None:
+        m.solver_backend = backend
+    m.initialise()
+    m.u.x.array[:] = m.mesh.mesh.coords[:, 0]
+    m.update_post_processing_solutions()
+    out = []
+    for surf in (left, right):
+        sf = F.SurfaceFlux(field=H, surface=surf)
+        sf.compute(m)
+        out.append(sf.value)
+    return out, expected
+
+
+@pytest.mark.parametrize("kind", ["temperatures", "materials"])
+def test_D_global_through_surface_flux_oracle(kind):
+    (f_left, f_right), (D_left, D_right) = _d_global_case(kind, OracleBackend())
+    assert np.isclose(f_left, D_left) and np.isclose(f_right, -D_right)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["temperatures", "materials"])
+def test_D_global_through_surface_flux_gpu(kind):
+    (f_left, f_right), (D_left, D_right) = _d_global_case(kind, None)
+    assert np.isclose(f_left, D_left, rtol=1e-10) and np.isclose(f_right, -D_right, rtol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------
+# reference test/system_tests/test_reaction_not_in_every_volume.py: a steady problem whose
+# reaction exists in one of two volumes only (the immobile species gets the filler term
+# c v dx in the other one, hydrogen_transport_problem.py:980-997)
+# ---------------------------------------------------------------------------------------
+def _reaction_not_everywhere(backend, with_bc=False):
+    m = F.HydrogenTransportProblem()
+    m.mesh = F.Mesh1D(np.linspace(0, 2e-04, num=1001))
+    mat = F.Material(D_0=4.1e-07, E_D=0.37, name="my_mat")
+    vol_1 = F.VolumeSubdomain1D(id=1, borders=[0, 1e-04], material=mat)
+    vol_2 = F.VolumeSubdomain1D(id=2, borders=[1e-04, 2e-04], material=mat)
+    left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=2e-04)
+    m.subdomains = [vol_1, vol_2, left, right]
+    cm, ct = F.Species("cm"), F.Species("ct", mobile=False)
+    m.species = [cm, ct]
+    trap = F.ImplicitSpecies(n=8.19e25, others=[ct])
+    m.reactions = [F.Reaction(reactant=[cm, trap], product=ct, k_0=8.9e-17, E_k=0.39, p_0=1e13, E_p=0.87,
+                              volume=vol_1)]
+    m.temperature = 600
+    if with_bc:   # something to solve: fixed mobile concentration at both ends
+        m.boundary_conditions = [F.DirichletBC(subdomain=left, value=1e20, species=cm),
+                                 F.DirichletBC(subdomain=right, value=0, species=cm)]
+    m.settings = F.Settings(atol=1e10, rtol=1e-10, transient=False)
+    if backend is not None:
+        m.solver_backend = backend
+    m.initialise()
+    m.run()
+    return m, cm, ct
+
+
+def test_sim_reaction_not_in_every_volume():
+    _reaction_not_everywhere(OracleBackend())
+    m, cm, ct = _reaction_not_everywhere(OracleBackend(), with_bc=True)
+    x = m.mesh.mesh.coords[:, 0]
+    trapped = ct.post_processing_solution.x.array
+    # no trapping where there is no reaction (the P1 field decays over a few vertices past the
+    # interface: the shared vertex belongs to both volumes)
+    assert np.abs(trapped[x > 1.1e-4]).max() <= 1e-12 * trapped.max()
+    assert trapped[x < 0.5e-4].min() > 0
+
+
+@pytest.mark.gpu
+def test_sim_reaction_not_in_every_volume_gpu():
+    _reaction_not_everywhere(None)
+    g, cmg, ctg = _reaction_not_everywhere(None, with_bc=True)
+    r, cmr, ctr = _reaction_not_everywhere(OracleBackend(), with_bc=True)
+    for a, b in ((cmg, cmr), (ctg, ctr)):
+        ua, ub = a.post_processing_solution.x.array, b.post_processing_solution.x.array
+        assert np.linalg.norm(ua - ub) / np.linalg.norm(ub) < 1e-8
