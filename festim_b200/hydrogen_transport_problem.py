@@ -166,7 +166,10 @@ class HydrogenTransportProblem(ProblemBase):
                     )
                 self.temperature_fenics = as_fenics_constant(val, mesh)
             else:
-                self.temperature_fenics = fem.Function(self.V_CG_1, name="temperature")
+                # its own P1 space, as the reference (:401-411): define_temperature does not
+                # need define_function_spaces to have run
+                self.temperature_fenics = fem.Function(fem.FunctionSpace(mesh, "Lagrange", 1),
+                                                       name="temperature")
                 kwargs = {}
                 if "t" in arguments:
                     kwargs["t"] = self.t

@@ -49,6 +49,16 @@ class SimplexMesh:
     def dim(self):
         return self.tdim
 
+    @property
+    def geometry(self):
+        """``mesh.geometry.x`` (coordinates padded to three columns) and ``.dim``, as user
+        scripts written against dolfinx read them."""
+        import types
+
+        x = np.zeros((self.num_vertices, 3))
+        x[:, : self.gdim] = self.coords
+        return types.SimpleNamespace(x=x, dim=self.gdim)
+
     # exterior facets ----------------------------------------------------------
     def _build_facets(self):
         d = self.tdim
@@ -272,6 +282,9 @@ class CoordinateSystem(Enum):
             return cls[s.upper()]
         except KeyError:
             raise ValueError("Invalid CoordinateSystem value")
+
+    def __str__(self):
+        return self.name.lower()
 
 
 class Mesh:

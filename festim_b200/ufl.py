@@ -73,7 +73,7 @@ class Expr:
         return as_expr(self)
 
     def __abs__(self):
-        return Math("abs", as_expr(self))
+        return _math("abs", self)
 
     # comparisons build conditions (as in UFL, usable inside conditional())
     def __lt__(self, o):
@@ -101,6 +101,11 @@ class Expr:
 class Const(Expr):
     def __init__(self, value):
         self.value = float(value)
+
+    def __array__(self, dtype=None, copy=None):
+        # a literal converts to a number for numpy (np.isclose(value, expected) in user code),
+        # like ufl's FloatValue
+        return np.asarray(self.value, dtype=dtype)
 
     def __repr__(self):
         return repr(self.value)
