@@ -214,8 +214,24 @@ class FluxBCBase:
         self.species_dependent_value = {}
 
     @property
+    def value_fenics(self):
+        return self._value_fenics
+
+    @value_fenics.setter
+    def value_fenics(self, value):
+        if value is not None and not isinstance(value, (fem.Function, fem.Constant, np.ndarray, ufl.Expr)):
+            raise TypeError(                                   # reference flux_bc.py:51-62
+                "Value must be a dolfinx.fem.Function, dolfinx.fem.Constant,"
+                f" np.ndarray or ufl.core.expr.Expr not {type(value)}")
+        self._value_fenics = value
+
+    @property
     def time_dependent(self):
-        if self.value is None or isinstance(self.value, fem.Constant):
+        if self.value is None:
+            if type(self).__name__.startswith("SurfaceReaction"):
+                return False
+            raise TypeError("Value must be given to determine if its time dependent")
+        if isinstance(self.value, fem.Constant):
             return False
         if callable(self.value) and not isinstance(self.value, ufl.Expr):
             return "t" in self.value.__code__.co_varnames

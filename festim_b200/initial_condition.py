@@ -12,6 +12,18 @@ class InitialConditionBase:
         self.volume = volume
         self.expr_fenics = None
 
+    @property
+    def volume(self):
+        return self._volume
+
+    @volume.setter
+    def volume(self, value):
+        from festim_b200.subdomain import VolumeSubdomain
+
+        if not isinstance(value, VolumeSubdomain):   # reference initial_condition.py:59-64
+            raise TypeError("volume must be of type festim.VolumeSubdomain")
+        self._volume = value
+
     def _create(self, mesh, temperature=None):
         if isinstance(self.value, (int, float)):
             val = self.value

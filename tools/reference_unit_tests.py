@@ -87,6 +87,23 @@ sys.modules["dolfinx.io"] = _io; dolfinx.io = _io
 for stub in ("io4dolfinx", "adios4dolfinx", "basix", "basix.ufl", "scifem", "petsc4py", "petsc4py.PETSc",
              "dolfinx.fem.petsc", "dolfinx.nls", "dolfinx.nls.petsc"):
     sys.modules.setdefault(stub, types.ModuleType(stub))
+def _evaluate_function(u, points):
+    """scifem.evaluate_function: P1 interpolation of a fem.Function at points (brute-force
+    search of the containing cell)."""
+    mesh = u.function_space.mesh
+    vals = np.asarray(u.x.array).reshape(mesh.num_vertices, -1)
+    pts = np.asarray(points, dtype=float).reshape(-1, np.asarray(points).shape[-1])[:, : mesh.gdim]
+    X = mesh.coords[mesh.cells]                                   # (nc, d+1, d)
+    out = []
+    for p in pts:
+        A = np.transpose(X[:, 1:] - X[:, :1], (0, 2, 1))          # (nc, d, d)
+        lam = np.linalg.solve(A, (p - X[:, 0])[:, :, None])[:, :, 0]
+        bary = np.concatenate([1 - lam.sum(1, keepdims=True), lam], axis=1)
+        c = int(np.argmax(bary.min(axis=1)))
+        out.append(bary[c] @ vals[mesh.cells[c]])
+    return np.array(out)
+
+sys.modules["scifem"].evaluate_function = _evaluate_function
 mpi4py = types.ModuleType("mpi4py"); mpi4py.__path__ = []
 MPI = types.ModuleType("mpi4py.MPI"); MPI.COMM_WORLD = None; MPI.SUM = "sum"
 mpi4py.MPI = MPI
