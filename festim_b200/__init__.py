@@ -37,6 +37,9 @@ from festim_b200.exports import (
     TotalSurface,
     TotalVolume,
     VolumeQuantity,
+    VTXSpeciesExport,
+    VTXTemperatureExport,
+    XDMFExport,
 )
 from festim_b200.helpers import Value, as_fenics_constant, is_it_time_to_export
 from festim_b200.coupled_heat_hydrogen_problem import CoupledTransientHeatTransferHydrogenTransport

@@ -231,3 +231,72 @@ class Profile1DExport:
         self.x = None
         self.data = []
         self.t = []
+
+
+# ---------------------------------------------------------------------------------------
+# Field output (reference exports/vtx.py, exports/xdmf.py).  Writing ADIOS2 / XDMF+HDF5 files
+# is file I/O outside the hot path: the classes exist so that scripts
+# written for the reference run unchanged - arguments, file-name handling and `times`
+# (which become milestones of the time stepping) behave as in the reference; nothing is
+# written and a warning says so once.
+# ---------------------------------------------------------------------------------------
+class ExportBaseClass:
+    """``vtx.py:16-54``: file name with the writer's extension, optional export times."""
+
+    _warned = False
+
+    def __init__(self, filename, ext, times=None):
+        import warnings
+        from pathlib import Path
+
+        name = Path(filename)
+        if name.suffix != ext:
+            warnings.warn(f"Filename {filename} does not have {ext} extension, adding it.")
+            name = name.with_suffix(ext)
+        self._filename = name
+        self.times = sorted(times) if times else times
+
+    @property
+    def filename(self):
+        return self._filename
+
+    def write(self, t):
+        import warnings
+
+        if not ExportBaseClass._warned:
+            warnings.warn(f"{type(self).__name__}: field output (VTX / XDMF) is not written by the B200 "
+                          "backend; use derived quantities or read `species.post_processing_solution`")
+            ExportBaseClass._warned = True
+
+
+def _species_list(value):
+    fields = value if isinstance(value, list) else [value]
+    for f in fields:
+        if not isinstance(f, (Species, str)):
+            raise TypeError("field must be of type festim.Species or a list of festim.Species or str")
+    return fields
+
+
+class XDMFExport(ExportBaseClass):
+    """``xdmf.py:12-74``."""
+
+    def __init__(self, filename, field):
+        super().__init__(filename, ".xdmf")
+        self.field = _species_list(field)
+
+
+class VTXSpeciesExport(ExportBaseClass):
+    """``vtx.py:83-180``."""
+
+    def __init__(self, filename, field, subdomain=None, checkpoint=False, times=None):
+        super().__init__(filename, ".bp", times)
+        self.field = _species_list(field)
+        self._subdomain = subdomain
+        self._checkpoint = checkpoint
+
+
+class VTXTemperatureExport(ExportBaseClass):
+    """``vtx.py:57-80``."""
+
+    def __init__(self, filename, times=None):
+        super().__init__(filename, ".bp", times)

@@ -427,6 +427,9 @@ class HydrogenTransportProblem(ProblemBase):
                 export.t.append(float(self.t))
                 if export.filename is not None:
                     export.write(t=float(self.t))
+            if isinstance(export, _exports.ExportBaseClass):   # field output: accepted, not written
+                if export.times is None or is_it_time_to_export(current_time=float(self.t), times=export.times):
+                    export.write(float(self.t))
             if isinstance(export, _exports.Profile1DExport):
                 if export.x is None:
                     coords = self.mesh.mesh.coords[:, 0]

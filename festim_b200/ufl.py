@@ -111,6 +111,30 @@ class Const(Expr):
         return repr(self.value)
 
 
+# arithmetic of a literal with numpy arrays is plain numpy arithmetic (post-processing code
+# mixes folded constants such as exp(-E / k_B / 500.0) with arrays of times)
+def _const_numpy_ops():
+    import operator
+
+    def make(name, op, reflected):
+        base = getattr(Expr, name)
+
+        def method(self, o):
+            if isinstance(o, np.ndarray):
+                return op(o, self.value) if reflected else op(self.value, o)
+            return base(self, o)
+
+        return method
+
+    for name, op in (("add", operator.add), ("sub", operator.sub), ("mul", operator.mul),
+                     ("truediv", operator.truediv), ("pow", operator.pow)):
+        setattr(Const, f"__{name}__", make(f"__{name}__", op, False))
+        setattr(Const, f"__r{name}__", make(f"__r{name}__", op, True))
+
+
+_const_numpy_ops()
+
+
 class Coord(Expr):
     """Component ``i`` of the spatial coordinate."""
 
