@@ -4,6 +4,10 @@ stand-ins, everything solves through the CPU oracle.  A compatibility report, no
 `tests/` (the GPU box has no /root/reference):
 
     python tools/reference_unit_tests.py [test_species.py test_reaction.py ...]
+    python tools/reference_unit_tests.py --system [test_fluxes.py ...]   (test/system_tests)
+
+For the system tests, only `tools.error_L2` is replaced (the reference interpolates into a
+degree-raised dolfinx space; here the error is integrated with a degree-8 rule).
 """
 import os
 import shutil
@@ -121,18 +125,57 @@ for sub, names in {"conditional": {"Conditional": _ufl.Conditional}, "indexed": 
 '''
 
 
+SYSTEM_DEFAULT = ["test_1_mobile_species.py", "test_1_mobile_1_trap.py", "test_fluxes.py",
+                  "test_advection_term_integration.py", "test_coupled_heat_hydrogen.py", "test_heat_transfer.py",
+                  "test_misc.py", "test_non_homogeneous_density.py", "test_reaction_not_in_every_volume.py",
+                  "test_surface_reactions.py", "test_cylindrical_coordinates.py", "test_spherical_coordinates.py"]
+
+SYSTEM_TOOLS = r'''
+import numpy as np
+import ufl
+from dolfinx.mesh import create_unit_cube, create_unit_square
+from festim import Mesh1D
+import sys
+sys.path.insert(0, %(root)r + "/tests")
+from cases import error_L2 as _error_L2
+
+test_mesh_1d = Mesh1D(np.linspace(0, 1, 10000))
+test_mesh_2d = create_unit_square(None, 50, 50)
+test_mesh_3d = create_unit_cube(None, 20, 20, 20)
+x_1d = ufl.SpatialCoordinate(test_mesh_1d.mesh)
+x_2d = ufl.SpatialCoordinate(test_mesh_2d)
+x_3d = ufl.SpatialCoordinate(test_mesh_3d)
+
+
+def error_L2(u_computed, u_exact, degree_raise=3):
+    mesh = u_computed.function_space.mesh
+    if isinstance(u_exact, ufl.Expr):
+        expr = u_exact
+        u_exact = lambda x: ufl.evaluate(expr, {"x": np.moveaxis(np.asarray(x), 0, -1)})
+    return _error_L2(mesh, np.asarray(u_computed.x.array), u_exact)
+'''
+
+
 def main():
-    files = sys.argv[1:] or DEFAULT
+    system = "--system" in sys.argv
+    if system:
+        sys.argv.remove("--system")
+    files = sys.argv[1:] or (SYSTEM_DEFAULT if system else DEFAULT)
     top = tempfile.mkdtemp(prefix="reftests_")
     tmp = os.path.join(top, "test")          # a package, so that `from .utils import ...` works
     os.makedirs(tmp)
     open(os.path.join(tmp, "__init__.py"), "w").close()
     with open(os.path.join(top, "conftest.py"), "w") as fh:
         fh.write(CONFTEST % {"root": ROOT})
-    for f in files + ["utils.py", "markers.py"]:
-        src = os.path.join(REF, f)
+    ref = os.path.join(REF, "system_tests") if system else REF
+    for f in files + (["test_multi_mat_penalty.py"] if system and "test_misc.py" in files else []) + \
+            ([] if system else ["utils.py", "markers.py"]):
+        src = os.path.join(ref, f)
         if os.path.exists(src):
             shutil.copy(src, tmp)
+    if system:
+        with open(os.path.join(tmp, "tools.py"), "w") as fh:
+            fh.write(SYSTEM_TOOLS % {"root": ROOT})
     cmd = [sys.executable, "-m", "pytest", tmp, "--rootdir", top, "-q", "--no-header", "-p", "no:cacheprovider",
            "--continue-on-collection-errors", "--tb=" + os.environ.get("TB", "line")] + (["-x"] if os.environ.get("X") else [])
     out = subprocess.run(cmd, cwd=top, capture_output=True, text=True)
