@@ -26,6 +26,7 @@ from festim_b200.boundary_conditions import (
 from festim_b200.exports import (
     AverageSurface,
     AverageVolume,
+    CustomQuantity,
     DerivedQuantity,
     MaximumSurface,
     MaximumVolume,

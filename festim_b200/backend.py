@@ -73,6 +73,7 @@ def load_library():
         "fb_total_volume": (i, [vp, vp, i, i, _f64p]),
         "fb_total_surface": (i, [vp, vp, i, i, _f64p]),
         "fb_surface_flux": (i, [vp, vp, i, i, d, vp, _f64p]),
+        "fb_integrate": (i, [vp, vp, i, i, i, i, i, _f64p]),
         "fb_set_owned": (i, [vp, i64]),
         "fb_set_sm_partition": (i, [vp, i, _i32p, _i32p, _i32p, C.POINTER(C.c_uint16), i64]),
         "fb_bjacobi_setup": (i, [vp, vp]),
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
     "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
     "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
-    "fb_total_surface", "fb_surface_flux", "fb_set_owned", "fb_set_sm_partition",
+    "fb_total_surface", "fb_surface_flux", "fb_integrate", "fb_set_owned", "fb_set_sm_partition",
     "fb_bjacobi_setup", "fb_precond",
     "fb_peer_alloc", "fb_peer_open", "fb_peer_set_send", "fb_dcg_persistent",
     "fb_dcg_init", "fb_dcg_spmv_dots", "fb_dcg_update", "fb_dcg_scalars", "fb_dcg_update_dev",
@@ -504,6 +505,15 @@ class B200NewtonSolver:
         ctx = self.ctx
         ctx._check(ctx.lib.fb_total_volume(ctx.h, ctx.ptr(self._current_u()), species_index,
                                            self.spec.vol_ids.index(vol_id), C.byref(out)))
+        return out.value
+
+    def integrate_custom(self, export):
+        """Integral of a CustomQuantity's expression over its subdomain (device kernel)."""
+        kind, tag, prog, off, nq, _ = self.spec.custom[id(export)]
+        self._push_state()   # fields the expression reads (e.g. the diffusivities) may have changed
+        out = C.c_double(0.0)
+        ctx = self.ctx
+        ctx._check(ctx.lib.fb_integrate(ctx.h, ctx.ptr(self._current_u()), kind, tag, prog, off, nq, C.byref(out)))
         return out.value
 
     def total_surface(self, species_index, surf_id):

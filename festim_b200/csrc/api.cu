@@ -181,6 +181,7 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   S.npairs = ints[I_NPAIRS]; S.n_diffE = ints[I_NDIFFE]; S.n_slots = ints[I_NSLOTS];
   S.n_fields = ints[I_NFIELDS];
   ctx->dt_scalar = ints[I_DT_SCALAR];
+  ctx->n_programs = ints[I_NPROGRAMS];
   // J is symmetric positive definite when nothing but diffusion and mass contributes:
   // no advection and no point term with a solution derivative (reactions couple species
   // with different coefficients in each direction)

@@ -31,6 +31,7 @@
 #include "program.cuh"
 #include "assemble_kernels.cuh"
 #include "assemble_rows.cuh"
+#include "reduce.cuh"
 
 // ---------------------------------------------------------------------------
 // kernels: thin wrappers around the bodies of assemble_kernels.cuh
@@ -242,4 +243,114 @@ int fbi_assemble(fb_ctx* ctx, const double* u, const double* un, double* F, doub
     case 3: return assemble_dim<3>(ctx, u, un, F, J, flags);
   }
   return fb_fail(ctx, "bad tdim");
+}
+
+// ---------------------------------------------------------------------------
+// User-defined derived quantity (reference exports/custom_quantity.py:117-132): the integral of
+// a compiled expression of x, t, T, the species, their cell gradients and the facet normal
+// over one volume (kind 0) or surface (kind 1) subdomain.  The expression is one of the
+// problem's programs (byte-code: an export, not a hot kernel), the rule is given by its
+// offset in the quadrature pool.
+// ---------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(FB_TPB)
+k_integrate(DevSpec S, const double* __restrict__ u, int kind, int tag, int prog, int qoff, int nq,
+            double* partials, unsigned* ticket, double* out) {
+  constexpr int D1 = DIM + 1;
+  const int ns = S.ns;
+  const long long n_ent = kind == 0 ? S.n_cells : S.n_bfacets;
+  double v[1] = {0.0}, tot[1];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_ent;
+       e += (long long)gridDim.x * blockDim.x) {
+    if ((kind == 0 ? S.cell_tag[e] : S.bfacet_tag[e]) != tag) continue;
+    const long long c = kind == 0 ? e : S.bfacet_cell[e];
+    int a[FB_MAX_D1], ev[FB_MAX_D1];
+    double X[FB_MAX_D1][3], G[FB_MAX_D1][3], Gflat[FB_MAX_D1 * 3], Y[FB_MAX_D1][3];
+    fb_load_cell<DIM>(S, c, a, X);
+    const double vol = fb_geometry<DIM>(X, G);
+    for (int j = 0; j < D1; ++j)
+      for (int k = 0; k < DIM; ++k) Gflat[j * DIM + k] = G[j][k];
+    const int nev = kind == 0 ? D1 : DIM;   // vertices of the integration entity
+    double measure = vol, nrm[3] = {0.0, 0.0, 0.0};
+    if (kind == 0) {
+      for (int j = 0; j < D1; ++j) {
+        ev[j] = a[j];
+        for (int k = 0; k < DIM; ++k) Y[j][k] = X[j][k];
+      }
+    } else {
+      for (int j = 0; j < DIM; ++j) {
+        ev[j] = S.bfacets[e * DIM + j];
+        for (int k = 0; k < DIM; ++k) Y[j][k] = S.coords[(long long)ev[j] * DIM + k];
+      }
+      measure = fb_facet_measure<DIM>(Y);
+      int opp = 0;
+      for (int j = 0; j < D1; ++j) {
+        bool onf = false;
+        for (int k = 0; k < DIM; ++k) onf |= (a[j] == ev[k]);
+        if (!onf) opp = j;
+      }
+      double l = 0.0;
+      for (int k = 0; k < DIM; ++k) l += G[opp][k] * G[opp][k];
+      l = sqrt(l);
+      for (int k = 0; k < DIM; ++k) nrm[k] = -G[opp][k] / l;
+    }
+    double cgr[FB_MAX_NS * 3], cq[FB_MAX_NS], zero[FB_MAX_NS];
+    for (int s = 0; s < ns; ++s) {
+      zero[s] = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        double gk = 0.0;
+        if (k < DIM)
+          for (int j = 0; j < D1; ++j) gk += u[(long long)a[j] * ns + s] * G[j][k];
+        cgr[s * 3 + k] = gk;
+      }
+    }
+    const double hcell = fb_circumradius<DIM>(X);
+    double acc = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      const double* bary = S.quad_bary + (long long)(qoff + q) * D1;
+      PointCtx P;
+      for (int k = 0; k < DIM; ++k) {
+        double x = 0.0;
+        for (int j = 0; j < nev; ++j) x += bary[j] * Y[j][k];
+        P.x[k] = x;
+      }
+      P.T = fb_temperature(S, ev, bary, nev);
+      for (int s = 0; s < ns; ++s) {
+        double cv = 0.0;
+        for (int j = 0; j < nev; ++j) cv += bary[j] * u[(long long)ev[j] * ns + s];
+        cq[s] = cv;
+      }
+      P.c = cq; P.cprev = zero; P.verts = ev; P.bary = bary; P.nverts = nev;
+      P.cverts = a; P.G = Gflat; P.ncverts = D1; P.tdim = DIM;
+      P.cgrad = cgr; P.n[0] = nrm[0]; P.n[1] = nrm[1]; P.n[2] = nrm[2]; P.h = hcell;
+      acc += S.quad_w[qoff + q] * fb_prog_eval(S, prog, P);
+    }
+    v[0] += acc * measure;
+  }
+  if (grid_reduce<1>(v, partials, ticket, tot) && threadIdx.x == 0) out[0] = tot[0];
+}
+
+extern "C" int fb_integrate(fb_ctx* ctx, const double* u, int kind, int tag, int prog, int quad_offset, int nq,
+                            double* out) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  if (!u || !out) return fb_fail(ctx, "null argument");
+  cudaSetDevice(ctx->device);
+  int rc = fbi_ensure_workspace(ctx);
+  if (rc) return rc;
+  const DevSpec& S = ctx->S;
+  if (kind < 0 || kind > 1 || prog < 0 || prog >= ctx->n_programs || nq < 1) return fb_fail(ctx, "bad integrand");
+  const long long n_ent = kind == 0 ? S.n_cells : S.n_bfacets;
+  long long g = (n_ent + FB_TPB - 1) / FB_TPB;
+  if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+  if (g < 1) g = 1;
+  switch (S.tdim) {
+    case 1: FB_LAUNCH(ctx, k_integrate<1>, (unsigned)g, FB_TPB, 0, S, u, kind, tag, prog, quad_offset, nq, ctx->d_red, ctx->d_ticket, ctx->d_sc + 61); break;
+    case 2: FB_LAUNCH(ctx, k_integrate<2>, (unsigned)g, FB_TPB, 0, S, u, kind, tag, prog, quad_offset, nq, ctx->d_red, ctx->d_ticket, ctx->d_sc + 61); break;
+    default: FB_LAUNCH(ctx, k_integrate<3>, (unsigned)g, FB_TPB, 0, S, u, kind, tag, prog, quad_offset, nq, ctx->d_red, ctx->d_ticket, ctx->d_sc + 61); break;
+  }
+  FB_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_sc + 61, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  FB_CHECK(ctx, cudaGetLastError());
+  *out = ctx->h_pinned[0];
+  return 0;
 }

@@ -46,6 +46,7 @@ struct fb_ctx {
   unsigned peer_seq = 1;               // next unused tag of the LL words
   const int* d_send_v = nullptr; const int* d_send_rank = nullptr; const int* d_send_dst = nullptr;
   int n_send = 0;
+  int n_programs = 0;                  // compiled expressions of the spec (fb_integrate checks its argument)
   bool symmetric = false;
   bool facet_u_terms = false;  // any solution-dependent facet term
   bool generic_u_vterms = false;  // any solution-dependent volume term evaluated point-wise

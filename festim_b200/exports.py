@@ -233,6 +233,30 @@ class Profile1DExport:
         self.t = []
 
 
+class CustomQuantity(DerivedQuantity):
+    """Integral of a user expression over a volume or surface subdomain (reference
+    ``exports/custom_quantity.py``).  ``expr(**kwargs)`` receives the species by name, ``n``
+    (facet normal), ``t``, ``T``, ``x``, ``D_<species>`` and ``D``; the expression is compiled
+    with the problem's other expressions and integrated on the device (``fb_integrate``)."""
+
+    def __init__(self, expr, subdomain, title="Custom Quantity", filename=None):
+        super().__init__(filename=filename)
+        self.expr = expr
+        self.subdomain = subdomain
+        self._title = title
+        self.ufl_expr = None
+
+    @property
+    def title(self):
+        return self._title
+
+    def compute(self, problem):
+        if self.ufl_expr is None:
+            raise ValueError("The UFL expression has not been evaluated yet.")
+        self.value = problem.solver.integrate_custom(self)
+        self.data.append(self.value)
+
+
 # ---------------------------------------------------------------------------------------
 # Field output (reference exports/vtx.py, exports/xdmf.py).  Writing ADIOS2 / XDMF+HDF5 files
 # is file I/O outside the hot path (DESIGN.md section 7): the classes exist so that scripts

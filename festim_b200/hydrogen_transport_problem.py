@@ -131,6 +131,7 @@ class HydrogenTransportProblem(ProblemBase):
         self.create_flux_values_fenics()
         self.create_initial_conditions()
         self.create_formulation()
+        self.prepare_custom_quantities()   # their expressions are compiled with the problem's
         self.create_solver()
         self.initialise_exports()
 
@@ -398,7 +399,44 @@ class HydrogenTransportProblem(ProblemBase):
         # interpolated with (:632-670, refreshed per :1049-1056)
         self.refresh_D_global()
 
+    def prepare_custom_quantities(self):
+        """Reference :545-571: keyword arguments handed to ``CustomQuantity.expr``.  The
+        diffusivities ``D_<species>`` are P1 nodal fields of the Arrhenius law of the material
+        the quantity's subdomain belongs to, evaluated with the vertex temperatures (the
+        restriction of the reference's DG1 ``D_global`` to that subdomain)."""
+        self._custom_D_fields = []
+        for export in self.exports:
+            if not isinstance(export, _exports.CustomQuantity):
+                continue
+            sub = export.subdomain
+            is_surface = not hasattr(sub, "material")
+            vol = self.volume_subdomain_of_surface(sub) if is_surface else sub
+            kwargs = {spe.name: spe.solution for spe in self.species}
+            kwargs["n"] = ufl.FacetNormal(gdim=self.mesh.mesh.gdim)
+            kwargs["t"] = self.t
+            kwargs["T"] = self.temperature_fenics
+            D_kwargs = {}
+            for spe in self.species:
+                if spe.mobile and not vol.material.D:
+                    fn = fem.Function(fem.FunctionSpace(self.mesh.mesh, "Lagrange", 1), name=f"D_{spe.name}")
+                    self._custom_D_fields.append((fn, vol.material.get_D_0(spe), vol.material.get_E_D(spe)))
+                    D_kwargs[f"D_{spe.name}"] = fn
+            kwargs.update(D_kwargs)
+            kwargs["D"] = {name[2:]: fn for name, fn in D_kwargs.items()}
+            if len(self.species) == 1 and D_kwargs:
+                kwargs["D"] = next(iter(D_kwargs.values()))
+            kwargs["x"] = ufl.SpatialCoordinate(self.mesh.mesh)
+            export.ufl_expr = ufl.as_expr(export.expr(**kwargs))
+        self._update_custom_D_fields()
+
+    def _update_custom_D_fields(self):
+        T = self.temperature_fenics
+        Tn = T.x.array if isinstance(T, fem.Function) else float(T.value)
+        for fn, D_0, E_D in getattr(self, "_custom_D_fields", []):
+            fn.x.array[:] = float(D_0) * np.exp(-float(E_D) / (k_B * Tn))
+
     def refresh_D_global(self):
+        self._update_custom_D_fields()
         T = self.temperature_fenics
         if isinstance(T, fem.Function):
             self._D_global_T = T.x.array.copy()
@@ -427,6 +465,12 @@ class HydrogenTransportProblem(ProblemBase):
                 export.t.append(float(self.t))
                 if export.filename is not None:
                     export.write(t=float(self.t))
+            if isinstance(export, _exports.CustomQuantity):
+                export.compute(self)
+                export.t.append(float(self.t))
+                if export.filename is not None:
+                    export.write(t=float(self.t))
+                continue
             if isinstance(export, _exports.ExportBaseClass):   # field output: accepted, not written
                 if export.times is None or is_it_time_to_export(current_time=float(self.t), times=export.times):
                     export.write(float(self.t))

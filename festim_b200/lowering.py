@@ -209,6 +209,17 @@ class KernelSpec:
             dF, dJ = degrees.get(("ds", sid), (1, None))
             self.quad_s[i] = self._add_rule(self.tdim - 1, dF) + self._add_rule(
                 self.tdim - 1, dF if dJ is None else dJ)
+        # user-defined derived quantities (CustomQuantity): one program and one rule each
+        self.custom = {}
+        for export in getattr(problem, "exports", None) or []:
+            if type(export).__name__ != "CustomQuantity" or getattr(export, "ufl_expr", None) is None:
+                continue
+            sub = export.subdomain
+            surface = not hasattr(sub, "material")
+            tag = (self.surf_ids if surface else self.vol_ids).index(sub.id)
+            degree = ufl.estimate_degree(export.ufl_expr)
+            off, nq = self._add_rule(self.tdim - 1 if surface else self.tdim, degree)
+            self.custom[id(export)] = (int(surface), tag, self.programs.add(export.ufl_expr), off, nq, degree)
 
     # ------------------------------------------------------------------
     # structured reactions: k0 exp(-Ek/kT) f1 [f2] - p(T) g1 [g2] with every factor an

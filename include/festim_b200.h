@@ -150,6 +150,13 @@ int fb_surface_flux(fb_ctx* ctx, const double* u /*[dev]*/, int species, int sta
                     double T_D_const, const double* T_D_nodal /*[dev] or NULL*/,
                     double* out /*[host]*/);
 
+/* user-defined derived quantity (reference exports/custom_quantity.py:117-132): integral over
+ * one volume (kind 0) or surface (kind 1) subdomain of program `prog` of the spec - an
+ * expression of x, t, T, the species, their cell gradients and the facet normal - with the
+ * quadrature rule at `quad_offset` (nq points) of the spec's pool */
+int fb_integrate(fb_ctx* ctx, const double* u /*[dev]*/, int kind, int tag, int prog, int quad_offset, int nq,
+                 double* out /*[host]*/);
+
 /* -- partitioned meshes (one process per GPU; replaces dolfinx IndexMap ghost updates and
  *    PETSc's MPI reductions).  The first n_owned vertices of the local
  *    numbering are owned, the rest are ghosts refreshed by the caller (NCCL) before

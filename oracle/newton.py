@@ -169,6 +169,39 @@ class OracleNewtonSolver:
         us = p.u.x.array.reshape(-1, ns)[:, species_index][fverts]
         return float(np.sum(facet_measures(mesh, fverts) * us.mean(axis=1)))
 
+    def integrate_custom(self, export):
+        """Integral of a CustomQuantity's expression over its subdomain: numpy evaluation of the
+        symbolic expression at the quadrature points of its estimated degree."""
+        from festim_b200 import quadrature, ufl
+        from oracle.assembly import cell_geometry, circumradius, facet_measures
+
+        p, asm = self.problem, self.assembler
+        mesh, d = p.mesh.mesh, p.mesh.mesh.tdim
+        sub = export.subdomain
+        surface = not hasattr(sub, "material")
+        degree = ufl.estimate_degree(export.ufl_expr)
+        u = p.u.x.array
+        if surface:
+            facets = p.facet_meshtags.find(sub.id)
+            fverts, fcells = mesh.bfacets[facets], mesh.bfacet_cell[facets]
+            _, G, _ = cell_geometry(mesh, fcells)
+            cverts = mesh.cells[fcells]
+            asm._cell_verts = cverts
+            opp = np.array([[v not in fv for v in cv] for cv, fv in zip(cverts, fverts)])
+            normal = -G[opp] / np.linalg.norm(G[opp], axis=1)[:, None]
+            bary, w = quadrature.rule(d - 1, degree)
+            env = asm._env(fverts, bary, G, u, u, normal, circumradius(mesh, fcells))
+            measure = facet_measures(mesh, fverts)
+        else:
+            cells = p.volume_meshtags.find(sub.id)
+            measure, G, _ = cell_geometry(mesh, cells)
+            verts = mesh.cells[cells]
+            asm._cell_verts = verts
+            bary, w = quadrature.rule(d, degree)
+            env = asm._env(verts, bary, G, u, u, np.zeros((len(cells), 3)), circumradius(mesh, cells))
+        vq = np.broadcast_to(ufl.evaluate(export.ufl_expr, env), (len(measure), len(w)))
+        return float(np.sum(measure * (vq @ w)))
+
     def surface_flux(self, species_index, surf_id):
         """int -D_h grad(u).n ds with D_h the DG1 interpolant of the Arrhenius
         diffusivity (reference ``exports/surface_flux.py:39-60``,

@@ -237,3 +237,69 @@ def test_sim_reaction_not_in_every_volume_gpu():
     for a, b in ((cmg, cmr), (ctg, ctr)):
         ua, ub = a.post_processing_solution.x.array, b.post_processing_solution.x.array
         assert np.linalg.norm(ua - ub) / np.linalg.norm(ub) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------
+# CustomQuantity (reference exports/custom_quantity.py; docs example and
+# test/system_tests/test_misc.py: custom quantities on volumes and surfaces)
+# ---------------------------------------------------------------------------------------
+def _custom_quantity_case(dim, backend):
+    from festim_b200 import ufl
+
+    if dim == 1:
+        mesh = F.Mesh1D(np.linspace(0, 2, 401))
+        vol = F.VolumeSubdomain1D(id=1, borders=[0, 2], material=F.Material(D_0=1.5, E_D=0.1, name="m"))
+        left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=2)
+    else:
+        raw = F.create_unit_square(12, 12) if dim == 2 else F.create_unit_cube(5, 5, 5)
+        mesh = F.Mesh(raw)
+        vol = F.VolumeSubdomain(id=1, material=F.Material(D_0=1.5, E_D=0.1, name="m"))
+        left = F.SurfaceSubdomain(id=1, locator=lambda x: np.isclose(x[0], 0))
+        right = F.SurfaceSubdomain(id=2, locator=lambda x: np.isclose(x[0], 1))
+    m = F.HydrogenTransportProblem()
+    m.mesh = mesh
+    m.subdomains = [vol, left, right]
+    A, B = F.Species("A"), F.Species("B")
+    m.species = [A, B]
+    m.temperature = lambda x: 500 + 100 * x[0]
+    m.boundary_conditions = [F.DirichletBC(subdomain=left, value=1, species=A),
+                             F.DirichletBC(subdomain=left, value=2, species=B)]
+    total = F.CustomQuantity(expr=lambda **kw: kw["A"] + 2 * kw["B"], subdomain=vol, title="Total quantity")
+    flux = F.CustomQuantity(expr=lambda **kw: -kw["D_A"] * ufl.dot(ufl.grad(kw["A"]), kw["n"]), subdomain=right,
+                            title="Surface flux")
+    weighted = F.CustomQuantity(expr=lambda **kw: kw["x"][0] * kw["A"] * ufl.exp(-0.05 / (F.k_B * kw["T"])),
+                                subdomain=vol, title="weighted")
+    builtin_flux = F.SurfaceFlux(field=A, surface=right)
+    builtin_total = F.TotalVolume(field=A, volume=vol)
+    m.exports = [total, flux, weighted, builtin_flux, builtin_total]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    if backend is not None:
+        m.solver_backend = backend
+    m.initialise()
+    x = m.mesh.mesh.coords
+    ns = 2
+    m.u.x.array[0::ns] = 1 + x[:, 0] ** 2 + (x[:, 1] if dim > 1 else 0.0)
+    m.u.x.array[1::ns] = 2 - 0.5 * x[:, 0]
+    m.update_post_processing_solutions()
+    for e in m.exports:
+        e.compute(m)
+    return [e.value for e in m.exports], m
+
+
+def test_custom_quantity_oracle():
+    (total, flux, weighted, bflux, btotal), m = _custom_quantity_case(1, OracleBackend())
+    # int_0^2 (1 + x^2) + 2 (2 - x/2) dx = (2 + 8/3) + (8 - 2)
+    assert np.isclose(total, 2 + 8 / 3 + 6, rtol=1e-5)
+    # the custom surface flux -D_A grad(A).n reproduces the built-in SurfaceFlux
+    assert np.isclose(flux, bflux, rtol=1e-12)
+    assert np.isclose(flux, -1.5 * np.exp(-0.1 / (F.k_B * 700)) * 4.0, rtol=1e-2)
+    assert weighted > 0 and np.isclose(btotal, 2 + 8 / 3, rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_custom_quantity_gpu_parity(dim):
+    vals_g, _ = _custom_quantity_case(dim, None)
+    vals_r, _ = _custom_quantity_case(dim, OracleBackend())
+    assert np.allclose(vals_g, vals_r, rtol=1e-10)
+    assert np.isclose(vals_g[1], vals_g[3], rtol=1e-10)   # custom flux == built-in flux
