@@ -9,7 +9,7 @@ C ABI in ``include/festim_b200.h``); there is no CPU fallback.
 """
 
 from festim_b200.constants import R, k_B, k_B_SI
-from festim_b200 import fem, ufl
+from festim_b200 import fem, field_io, ufl
 from festim_b200.advection import AdvectionTerm, VectorFunction, VelocityField
 from festim_b200.boundary_conditions import (
     DirichletBC,
@@ -26,13 +26,16 @@ from festim_b200.boundary_conditions import (
 from festim_b200.exports import (
     AverageSurface,
     AverageVolume,
+    CustomFieldExport,
     CustomQuantity,
     DerivedQuantity,
+    ExportBaseClass,
     MaximumSurface,
     MaximumVolume,
     MinimumSurface,
     MinimumVolume,
     Profile1DExport,
+    ReactionRateExport,
     SurfaceFlux,
     SurfaceQuantity,
     TotalSurface,
@@ -56,6 +59,7 @@ from festim_b200.mesh import (
     CoordinateSystem,
     Mesh,
     Mesh1D,
+    MeshFromXDMF,
     MeshTags,
     SimplexMesh,
     create_box,

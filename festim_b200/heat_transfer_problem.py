@@ -132,7 +132,15 @@ class HeatTransferProblem(ProblemBase):
         self.formulation = F
 
     def initialise_exports(self):
+        """Reference ``heat_transfer_problem.py:220-236``."""
+        from festim_b200 import field_io
+
         for export in self.exports:
+            if isinstance(export, _exports.XDMFExport):
+                raise NotImplementedError("XDMF export is not implemented yet for heat transfer problems")
+            if isinstance(export, _exports.VTXTemperatureExport):
+                export.writer = (field_io.VTUSeriesWriter(export.filename, self.mesh.mesh)
+                                 if field_io.is_io_rank() else field_io.NullWriter())
             if isinstance(export, _exports.DerivedQuantity):
                 export.t, export.data = [], []
 
@@ -145,3 +153,5 @@ class HeatTransferProblem(ProblemBase):
                 raise NotImplementedError(
                     "SurfaceQuantity export is not implemented yet for heat transfer problems"
                 )
+            if isinstance(export, _exports.VTXTemperatureExport):   # reference :266-267
+                export.writer.write(float(self.t), {"T": self.u.x.array})

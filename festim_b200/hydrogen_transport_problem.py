@@ -385,8 +385,14 @@ class HydrogenTransportProblem(ProblemBase):
                         )
                         self.settings.stepsize.milestones.append(time)
                 self.settings.stepsize.milestones.sort()
-            if hasattr(export, "field") and isinstance(export.field, str):
-                export.field = _species.find_species_from_name(export.field, self.species)
+            if hasattr(export, "field"):
+                if isinstance(export.field, list):
+                    for idx, field in enumerate(export.field):
+                        if isinstance(field, str):
+                            export.field[idx] = _species.find_species_from_name(field, self.species)
+                elif isinstance(export.field, str):
+                    export.field = _species.find_species_from_name(export.field, self.species)
+            self._define_field_writer(export)
             if isinstance(export, _exports.Profile1DExport):
                 export.data, export.t = [], []
             if isinstance(export, _exports.DerivedQuantity):
@@ -398,6 +404,40 @@ class HydrogenTransportProblem(ProblemBase):
         # D_global snapshot: the temperature the DG1 diffusivity was last
         # interpolated with (:632-670, refreshed per :1049-1056)
         self.refresh_D_global()
+
+    def _define_field_writer(self, export):
+        """Reference :442-483, :508-510: one writer per field export (``field_io``: VTK XML series
+        at the ``.bp`` path, XDMF with raw side-car data)."""
+        from festim_b200 import field_io
+
+        def VTUSeriesWriter(path, mesh):
+            return field_io.VTUSeriesWriter(path, mesh) if field_io.is_io_rank() else field_io.NullWriter()
+
+        if isinstance(export, _exports.VTXTemperatureExport):
+            self._temperature_as_function = self._get_temperature_field_as_function()
+            export.writer = VTUSeriesWriter(export.filename, self.mesh.mesh)
+        elif isinstance(export, _exports.VTXSpeciesExport):
+            if export._checkpoint:
+                raise NotImplementedError(
+                    "checkpoint=True writes adios4dolfinx restart files, which need ADIOS2 "
+                    "(not in this image); use checkpoint=False or XDMFExport")
+            export.writer = VTUSeriesWriter(export.filename, self.mesh.mesh)
+        elif isinstance(export, _exports.CustomFieldExport):
+            if export.checkpoint:
+                raise NotImplementedError("checkpoint=True needs ADIOS2 (not in this image)")
+            export.function = fem.Function(fem.FunctionSpace(self.mesh.mesh, "Lagrange", 1), name="f")
+            export.set_dolfinx_expression(temperature=self.temperature_fenics, time=self.t)
+            export.writer = VTUSeriesWriter(export.filename, self.mesh.mesh)
+        elif isinstance(export, _exports.XDMFExport):
+            export.define_writer()
+
+    def _get_temperature_field_as_function(self):
+        """Reference :572-593."""
+        if isinstance(self.temperature_fenics, fem.Function):
+            return self.temperature_fenics
+        fn = fem.Function(fem.FunctionSpace(self.mesh.mesh, "Lagrange", 1), name="T")
+        fn.x.array[:] = float(self.temperature_fenics.value)
+        return fn
 
     def prepare_custom_quantities(self):
         """Reference :545-571: keyword arguments handed to ``CustomQuantity.expr``.  The
@@ -471,9 +511,17 @@ class HydrogenTransportProblem(ProblemBase):
                 if export.filename is not None:
                     export.write(t=float(self.t))
                 continue
-            if isinstance(export, _exports.ExportBaseClass):   # field output: accepted, not written
-                if export.times is None or is_it_time_to_export(current_time=float(self.t), times=export.times):
-                    export.write(float(self.t))
+            if isinstance(export, _exports.VTXSpeciesExport):
+                export.write(float(self.t))
+            elif isinstance(export, _exports.VTXTemperatureExport):
+                if self.temperature_time_dependent:   # reference :1079-1086: a steady T is not rewritten
+                    self._temperature_as_function = self._get_temperature_field_as_function()
+                    export.writer.write(float(self.t), {"T": self._temperature_as_function.x.array})
+            elif isinstance(export, _exports.CustomFieldExport):
+                export.update(self.species)
+                export.write(float(self.t))
+            if isinstance(export, _exports.XDMFExport):
+                export.write(float(self.t))
             if isinstance(export, _exports.Profile1DExport):
                 if export.x is None:
                     coords = self.mesh.mesh.coords[:, 0]

@@ -444,3 +444,38 @@ class Mesh1D(Mesh):
     def define_meshtags(self, surface_subdomains, volume_subdomains, interfaces=None):
         self.check_borders(volume_subdomains)
         return super().define_meshtags(surface_subdomains, volume_subdomains, interfaces)
+
+
+class MeshFromXDMF(Mesh):
+    """Mesh and tags read from XDMF files, reference ``mesh/mesh_from_xdmf.py:8-75``.
+    The files are read by ``festim_b200.field_io.XDMFFile`` (inline, raw binary or - with h5py -
+    HDF5 heavy data).  Facet tags are kept on exterior facets."""
+
+    def __init__(self, volume_file, facet_file, mesh_name="Grid", surface_meshtags_name="Grid",
+                 volume_meshtags_name="Grid"):
+        from festim_b200.field_io import XDMFFile
+
+        self.volume_file = volume_file
+        self.facet_file = facet_file
+        self.mesh_name = mesh_name
+        self.surface_meshtags_name = surface_meshtags_name
+        self.volume_meshtags_name = volume_meshtags_name
+        mesh = XDMFFile(self.volume_file, "r").read_mesh(name=f"{self.mesh_name}")
+        super().__init__(mesh=mesh)
+
+    def define_surface_meshtags(self):
+        """Exterior facets the file does not tag get 0 (integrated over by no ``ds(id)``)."""
+        from festim_b200.field_io import XDMFFile
+
+        read = XDMFFile(self.facet_file, "r").read_meshtags(self.mesh, name=f"{self.surface_meshtags_name}")
+        values = np.zeros(self.mesh.bfacets.shape[0], dtype=np.int32)
+        values[read.indices] = read.values
+        return MeshTags(self.mesh, self.mesh.tdim - 1, np.arange(len(values)), values)
+
+    def define_volume_meshtags(self):
+        from festim_b200.field_io import XDMFFile
+
+        read = XDMFFile(self.volume_file, "r").read_meshtags(self.mesh, name=f"{self.volume_meshtags_name}")
+        values = np.zeros(self.mesh.num_cells, dtype=np.int32)
+        values[read.indices] = read.values
+        return MeshTags(self.mesh, self.mesh.tdim, np.arange(len(values)), values)

@@ -121,7 +121,10 @@ class ProblemBase:
             raise TypeError("value must be of type dolfinx.mesh.MeshTags")
 
     def define_meshtags_and_measures(self):
-        if (isinstance(self.mesh, _mesh.Mesh) and self.facet_meshtags is None
+        if isinstance(self.mesh, _mesh.MeshFromXDMF):   # reference problem.py:88-91
+            self.facet_meshtags = self.mesh.define_surface_meshtags()
+            self.volume_meshtags = self.mesh.define_volume_meshtags()
+        elif (isinstance(self.mesh, _mesh.Mesh) and self.facet_meshtags is None
                 and self.volume_meshtags is None):
             self.facet_meshtags, self.volume_meshtags = self.mesh.define_meshtags(
                 surface_subdomains=self.surface_subdomains,

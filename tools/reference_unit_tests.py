@@ -25,7 +25,8 @@ DEFAULT = ["test_species.py", "test_reaction.py", "test_settings.py", "test_step
            "test_average_surface.py", "test_maximum_volume.py", "test_minimum_volume.py",
            "test_maximum_surface.py", "test_minimum_surface.py", "test_total_surface.py",
            "test_permeation_problem.py", "test_multispecies_problem.py", "test_complex_reaction.py",
-           "test_coupled_heat_hydrogen_problem.py", "test_initial_condition.py", "test_derived_quantities.py"]
+           "test_coupled_heat_hydrogen_problem.py", "test_initial_condition.py", "test_derived_quantities.py",
+           "test_vtx.py", "test_xdmf.py", "test_profile.py"]
 
 CONFTEST = r'''
 import sys, types
