@@ -106,6 +106,11 @@ class Function(_ufl.Expr):
     def _as_expr(self):
         return _ufl.FieldRef(self)
 
+    def __bool__(self):
+        # a field object is truthy, as a dolfinx Function is (`if material.D:`); only
+        # expressions built from it have no truth value
+        return True
+
     def interpolate(self, f, cells0=None):
         """Nodal interpolation of a callable ``f(x)`` (x of shape (3, n), the
         dolfinx convention), an expression, or another Function."""

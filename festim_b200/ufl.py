@@ -91,11 +91,46 @@ class Expr:
     def __bool__(self):
         raise TypeError("a symbolic expression has no truth value; use conditional()")
 
+    # `==` is structural equality and returns a bool, as in UFL (ufl/exprequals.py); the
+    # condition `a == b` for conditional() is `eq(a, b)`
+    def __eq__(self, o):
+        return expr_equals(self, o)
+
+    def __ne__(self, o):
+        return not expr_equals(self, o)
+
     __hash__ = object.__hash__
 
     def __float__(self):
         v = evaluate(self, {})
         return float(v)
+
+
+def expr_equals(a, b):
+    """Same tree: same node types and operators, leaves (fields, constants, species) by identity,
+    literals by value."""
+    if a is b:
+        return True
+    try:
+        a, b = as_expr(a), as_expr(b)
+    except Exception:
+        return False
+    return _same(a, b)
+
+
+def _same(a, b):
+    if a is b:
+        return True
+    if type(a) is not type(b):
+        return False
+    if hasattr(a, "_as_expr"):   # fem.Function / fem.Constant held by a reference node
+        return False
+    if isinstance(a, (Expr, Condition)):
+        va, vb = vars(a), vars(b)
+        return va.keys() == vb.keys() and all(_same(va[k], vb[k]) for k in va)
+    if isinstance(a, (bool, int, float, str)):
+        return a == b
+    return False   # any other leaf object (Function, Constant, Species): identity only
 
 
 class Const(Expr):
@@ -1071,3 +1106,12 @@ class ProgramBuilder:
         iargs = np.array([c[1] for c in self.code], dtype=np.int32)
         fargs = np.array([c[2] for c in self.code], dtype=np.float64)
         return ops, iargs, fargs, np.array(self.offsets, dtype=np.int32)
+
+
+# Error messages of the reference print `type(value)`; report the UFL module paths the
+# reference's users (and tests) see, e.g. <class 'ufl.conditional.Conditional'>.
+for _cls, _mod in ((Sum, "ufl.algebra"), (Product, "ufl.algebra"), (Division, "ufl.algebra"),
+                   (Power, "ufl.algebra"), (Conditional, "ufl.conditional"), (MinMax, "ufl.conditional"),
+                   (Math, "ufl.mathfunctions")):
+    _cls.__module__ = _mod
+del _cls, _mod

@@ -123,3 +123,24 @@ def test_degree_estimates_follow_ufl_rules():
     assert ufl.estimate_degree(ufl.sin(x[0])) == 3 and ufl.estimate_degree(ufl.sin(Tc)) == 0
     assert ufl.estimate_degree(ufl.conditional(ufl.lt(x[0], 1), x[0] ** 2, x[1])) == 2
     assert ufl.estimate_degree(ufl.grad(Tf * 2.0, 3)[0]) == 0
+
+
+def test_structural_equality_like_ufl():
+    """`==` on expressions is UFL's structural equality returning a bool (the reference's unit
+    tests compare `reaction.reaction_term(T) == expected` this way); leaves compare by identity,
+    literals by value; the condition for conditional() is `eq(a, b)`."""
+    from festim_b200 import fem, ufl
+    from festim_b200.mesh import create_unit_interval
+
+    V = fem.functionspace(create_unit_interval(4), ("Lagrange", 1))
+    f, g = fem.Function(V), fem.Function(V)
+    c1, c2 = fem.Constant(None, 2.0), fem.Constant(None, 2.0)
+    assert (2.0 * f * ufl.exp(-g / 3.0) - c1 * g) == (2.0 * f * ufl.exp(-g / 3.0) - c1 * g)
+    assert (f * g) != (g * f)
+    assert (f + 1.0) != (f + 2.0)
+    assert (f * c1) != (f * c2)            # two constants with the same value stay different leaves
+    assert f == f and f != g and not (f == 3) and not (f == "f") and f != None   # noqa: E711
+    assert ufl.conditional(ufl.lt(f, 1.0), f, g) == ufl.conditional(ufl.lt(f, 1.0), f, g)
+    assert ufl.conditional(ufl.lt(f, 1.0), f, g) != ufl.conditional(ufl.gt(f, 1.0), f, g)
+    assert isinstance(ufl.eq(f, g), ufl.Condition)
+    assert len({f: 1, g: 2}) == 2 and f in [g, f]
