@@ -17,9 +17,12 @@ norms and dot products.  Design:
 * collectives go through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU
   tests of the host logic); all arithmetic runs in the CUDA library.
 
+Non-symmetric Jacobians (traps, reactions, advection) take the partitioned GMRES of
+``festim_b200/krylov_dist.py`` (library SpMV / preconditioner, orthogonalisation as
+tensor products - functional, not yet a fused kernel).
+
 Round-1 limits: the host keeps the global problem on every rank (only device work
-is partitioned); symmetric systems (CG) only; derived quantities are evaluated on
-the gathered global field.
+is partitioned); derived quantities are evaluated on the gathered global field.
 """
 
 from __future__ import annotations
@@ -287,10 +290,11 @@ class DistributedNewtonSolver:
         self.use_graph = (self.nranks == 1 and not os.environ.get("FB_NO_CUDA_GRAPH")) or \
             bool(os.environ.get("FB_DIST_CUDA_GRAPH"))
         self.cg_iterations = 0
+        self.gmres_iterations = 0
         self.launches_python = 0
         # whole-solve persistent CG over peer memory (NVLink): default for ranks of one node
         self.peer = False
-        if self.nranks > 1 and not os.environ.get("FB_NO_PEER_CG"):
+        if self.nranks > 1 and not os.environ.get("FB_NO_PEER_CG") and self._is_symmetric():
             self._setup_peer()
 
     def _setup_peer(self):
@@ -341,6 +345,7 @@ class DistributedNewtonSolver:
         elif T is not None:
             parts.append(np.float64(T.value))
         parts += [f.x.array for f in spec.fields]
+        parts += [vel.array for _, _, vel in spec.adv]
         bc_vals = np.concatenate([bc.values() for bc in self._bc_forms])[self._bc_pick] \
             if self._bc_forms else np.zeros(0)
         bc_dev = ctx.to_device("bc_vals", bc_vals) if len(bc_vals) else None
@@ -358,8 +363,8 @@ class DistributedNewtonSolver:
             ctx._check(lib.fb_set_temperature(ctx.h, float(T.value), C.c_void_p()))
         for k, f in enumerate(spec.fields):
             ctx._check(lib.fb_set_field(ctx.h, k, ctx.ptr(ctx.to_device(f"field{k}", f.x.array[lp.l2g]))))
-        if spec.adv:
-            raise NotImplementedError("partitioned advection problems need the GMRES path")
+        for k, (_, _, vel) in enumerate(spec.adv):
+            ctx._check(lib.fb_set_velocity(ctx.h, k, ctx.ptr(ctx.to_device(f"vel{k}", vel.array[lp.l2g]))))
         ctx._check(lib.fb_update_load(ctx.h))
 
     def _dot(self, a, b):
@@ -382,9 +387,38 @@ class DistributedNewtonSolver:
         lib.fb_dcg_scalars(ctx.h, ptr(self.out3), ptr(self.state), int(self._max_it))
         lib.fb_dcg_update_dev(ctx.h, ptr(self.state), ptr(x), ptr(r), ptr(u), ptr(w), ptr(p), ptr(s))
 
+    def _gmres(self, J, b, x, rtol, max_it):
+        """Non-symmetric Jacobians (traps, reactions, advection): GMRES(30) + block-Jacobi with the
+        library's owned-row SpMV and preconditioner, one halo exchange and three all-reduces per
+        Arnoldi step (festim_b200/krylov_dist.py)."""
+        from festim_b200.krylov_dist import gmres
+
+        ctx, lib, ptr = self.ctx, self.ctx.lib, self.ctx.ptr
+
+        def apply_A(v):
+            self.halo(v)
+            ctx._check(lib.fb_spmv(ctx.h, ptr(J), ptr(v), ptr(self.w)))
+            return self.w
+
+        def apply_M(r):
+            ctx._check(lib.fb_precond(ctx.h, ptr(r), ptr(self.tmp)))
+            return self.tmp
+
+        def allreduce(t):
+            if self.nranks > 1:
+                self.dist.all_reduce(t)
+            return t
+
+        x.zero_()
+        its, ok = gmres(apply_A, apply_M, allreduce, b, x, self.part.n_owned * self.ns, rtol, 0.0, max_it)
+        self.gmres_iterations += its
+        return its, ok
+
     def linear_solve(self, J, b, x, rtol, max_it):
         torch, ctx, lib, ptr = self.torch, self.ctx, self.ctx.lib, self.ctx.ptr
         ctx._check(lib.fb_bjacobi_setup(ctx.h, ptr(J)))
+        if not self._is_symmetric():
+            return self._gmres(J, b, x, rtol, max_it)
         ctx._check(lib.fb_precond(ctx.h, ptr(b), ptr(self.tmp)))
         thr2 = (rtol * self._norm(self.tmp)) ** 2
         if self.peer:
@@ -436,8 +470,6 @@ class DistributedNewtonSolver:
     # ---- Newton (reference problem.py:271-289, helpers.py:408-426) --------------------
     def solve(self):
         ctx, p = self.ctx, self.problem
-        if not self._is_symmetric():
-            raise NotImplementedError("the partitioned path implements CG (SPD systems) only")
         with self.torch.cuda.stream(self.stream):
             self._push_state()
             u = ctx.to_device("u", p.u.x.array[self.ldofs])
@@ -493,7 +525,9 @@ class DistributedNewtonSolver:
 
     def _is_symmetric(self):
         spec = self.spec
-        return not spec.adv and not spec.diff_udep and all(
+        # as fb_set_spec decides for one GPU (csrc/api.cu): diffusion + mass only; reactions
+        # (structured or point-wise), advection and solution-dependent coefficients are not
+        return spec.struct is None and not spec.adv and not spec.diff_udep and all(
             not t.derivs for t in spec.vterms + spec.fterms)
 
     def _gather(self, u):

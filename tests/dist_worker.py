@@ -21,21 +21,30 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-    m, H, _ = mms_1_mobile_steady(3, n)
+    case = sys.argv[2] if len(sys.argv) > 2 else "diffusion"
+
+    def build():
+        if case == "trap":          # non-symmetric Jacobian: partitioned GMRES
+            from cases import mms_1_mobile_1_trap_steady
+
+            return mms_1_mobile_1_trap_steady(3, n)[:2]
+        return mms_1_mobile_steady(3, n)[:2]
+
+    m, H = build()
     m.solver_backend = DistributedBackend(device=local)
     m.initialise()
     m.run()
     ok = True
     if rank == 0:
-        r, Hr, _ = mms_1_mobile_steady(3, n)
+        r, Hr = build()
         r.solver_backend = OracleBackend()
         r.initialise()
         r.run()
-        a, b = H.post_processing_solution.x.array, Hr.post_processing_solution.x.array
+        a, b = m.u.x.array, r.u.x.array
         rel = np.linalg.norm(a - b) / np.linalg.norm(b)
         ok = rel < 1e-8 and m.solver.solver.getIterationNumber() == r.solver.solver.getIterationNumber()
         print(f"DIST world={dist.get_world_size()} rel={rel:.3e} newton={m.solver.solver.its} "
-              f"cg={m.solver.solver.linear_its} peer={m.solver.peer} ok={ok}", flush=True)
+              f"linear={m.solver.solver.linear_its} gmres={m.solver.gmres_iterations} peer={m.solver.peer} ok={ok}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

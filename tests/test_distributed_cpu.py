@@ -107,3 +107,79 @@ def test_sm_block_ordering_keeps_halo_lists_consistent(world):
         for q, idx in p.send.items():
             a, b = lps[q].recv[p.rank]
             assert np.array_equal(p.l2g[idx], lps[q].l2g[a:b])
+
+
+def _gmres_worker(rank, world, port, ns):
+    """Partitioned GMRES (festim_b200/krylov_dist.py) on a non-symmetric block operator: the
+    recurrence, halo placement and all-reduces are the ones the GPU ranks run; here the owned-row
+    SpMV and the block-Jacobi preconditioner are scipy / numpy."""
+    from festim_b200.krylov_dist import gmres
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mesh = F.create_unit_cube(6, 5, 4)
+        nv = mesh.num_vertices
+        part = partition_rcb(mesh.coords, world)
+        lp = LocalPartition(mesh, part, rank, world)
+        rowptr, colidx = mesh.graph
+        rng = np.random.default_rng(11)     # same stream on every rank: the same global operator
+        Ag = sp.csr_matrix((np.ones(len(colidx)), colidx, rowptr), shape=(nv, nv))
+        # node-block operator: non-symmetric off-diagonal couplings, dominant diagonal blocks
+        B = sp.kron(Ag, np.ones((ns, ns))).tocsr()
+        B.data = rng.uniform(-1.0, 1.0, B.nnz)
+        B = B + sp.diags(np.asarray(abs(B).sum(axis=1)).ravel() * 0.6 + 1.0)
+        B = B.tocsr()
+        assert abs(B - B.T).max() > 0.1
+        rhs = rng.standard_normal(nv * ns)
+        exact = sp.linalg.spsolve(B.tocsc(), rhs)
+
+        ldofs = lp.local_dofs(ns)
+        n_own = lp.n_owned * ns
+        rows = B[ldofs[:n_own]][:, ldofs]                      # owned rows, local columns
+        dinv = [np.linalg.inv(rows[v * ns:(v + 1) * ns, v * ns:(v + 1) * ns].toarray())
+                for v in range(lp.n_owned)]
+        halo = HaloExchange(lp, ns, torch, "cpu")
+        calls = {"A": 0, "reduce": 0}
+
+        def apply_A(v):
+            calls["A"] += 1
+            halo(v)
+            return torch.from_numpy(rows @ v.numpy())
+
+        def apply_M(r):
+            z = np.concatenate([d @ r.numpy()[v * ns:(v + 1) * ns] for v, d in enumerate(dinv)])
+            return torch.from_numpy(z)
+
+        def allreduce(t):
+            calls["reduce"] += 1
+            dist.all_reduce(t)
+            return t
+
+        b = torch.zeros(len(ldofs), dtype=torch.float64)
+        b[:n_own] = torch.from_numpy(rhs[ldofs[:n_own]])
+        x = torch.zeros_like(b)
+        its, ok = gmres(apply_A, apply_M, allreduce, b, x, n_own, rtol=1e-12, max_it=500, restart=12)
+        assert ok and 12 < its < 200, (its, ok)                 # more than one restart cycle
+        assert np.allclose(x.numpy()[:n_own], exact[ldofs[:n_own]], rtol=1e-9, atol=1e-11)
+        # one halo'd SpMV per Arnoldi step (+1 per restart), three reductions per step (+1 per restart)
+        assert calls["A"] <= its + its // 12 + 2 and calls["reduce"] <= 3 * its + its // 12 + 3
+        every = [None] * world
+        dist.all_gather_object(every, its)
+        assert len(set(every)) == 1, "all ranks must take the same decisions"
+        # iteration cap is honoured and reported as not converged
+        x2 = torch.zeros_like(b)
+        its2, ok2 = gmres(apply_A, apply_M, allreduce, b, x2, n_own, rtol=1e-14, max_it=5, restart=12)
+        assert its2 == 5 and not ok2
+        # zero right-hand side: converged at once, x untouched
+        x3 = torch.zeros_like(b)
+        its3, ok3 = gmres(apply_A, apply_M, allreduce, torch.zeros_like(b), x3, n_own, rtol=1e-10)
+        assert its3 == 0 and ok3 and not x3.any()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ns", [(1, 2), (2, 1), (2, 3), (3, 2)])
+def test_partitioned_gmres(world, ns):
+    mp.spawn(_gmres_worker, args=(world, _free_port(), ns), nprocs=world, join=True)
