@@ -509,3 +509,91 @@ def recombination_flux(dim, n):
     m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=True, final_time=0.3)
     m.settings.stepsize = F.Stepsize(0.1)
     return m, (H, D), None
+
+
+def monoblock_coupled_3d(n=4, nsteps=3, dt=0.5):
+    """BASELINE configs[3] (C3) in small: coupled heat transfer + hydrogen transport on a cube
+    tagged into three material slabs W / Cu / CuCrZr (tagged cube standing in for the
+    ITER-like monoblock; ``VolumeSubdomain(locator=...)``, reference volume_subdomain.py:49-56).
+    Heat: per-material conductivity / density / heat capacity, heat flux on the plasma-facing top,
+    fixed temperature on the coolant side.  Hydrogen: continuous problem, mobile H with
+    per-material Arrhenius diffusivity, two traps in W, one in Cu, one in CuCrZr (each reaction
+    restricted to its material through ``Reaction.volume``), fixed concentration on top, zero at
+    the bottom.  ``n`` must be a multiple of 4 (slab borders at z = 1/4 and 1/2).
+
+    Reference quirk kept on both sides of the parity test: the coupled problem hands
+    ``heat_problem.u`` to the hydrogen problem before the first heat solve
+    (coupled_heat_hydrogen_problem.py:119-131), the DG1 diffusivity behind ``SurfaceFlux`` is
+    interpolated once from that all-zero field (hydrogen_transport_problem.py:632-670; refreshed
+    only for a callable T(t), :1049-1056), so the exported surface flux is exactly 0 while the
+    transport itself uses the live temperature."""
+    assert n % 4 == 0
+    raw = F.create_unit_cube(n, n, n)
+    mats = {
+        "W": F.Material(D_0=1.5, E_D=0.10, thermal_conductivity=1.7, density=1.9, heat_capacity=1.3),
+        "Cu": F.Material(D_0=2.4, E_D=0.09, thermal_conductivity=4.0, density=0.9, heat_capacity=3.8),
+        "CuCrZr": F.Material(D_0=1.4, E_D=0.11, thermal_conductivity=3.2, density=0.9, heat_capacity=3.9),
+    }
+    eps = 1e-9
+    W = F.VolumeSubdomain(id=1, material=mats["W"], locator=lambda x: x[2] >= 0.5 - eps)
+    Cu = F.VolumeSubdomain(id=2, material=mats["Cu"],
+                           locator=lambda x: np.logical_and(x[2] >= 0.25 - eps, x[2] <= 0.5 + eps))
+    CuCrZr = F.VolumeSubdomain(id=3, material=mats["CuCrZr"], locator=lambda x: x[2] <= 0.25 + eps)
+    top = F.SurfaceSubdomain(id=4, locator=lambda x: np.isclose(x[2], 1.0))
+    coolant = F.SurfaceSubdomain(id=5, locator=lambda x: np.isclose(x[2], 0.0))
+    subdomains = [W, Cu, CuCrZr, top, coolant]
+    final_time = nsteps * dt
+    heat = F.HeatTransferProblem(
+        mesh=F.Mesh(raw), subdomains=subdomains,
+        boundary_conditions=[F.HeatFluxBC(subdomain=top, value=lambda t: 40.0 + 100.0 * t),
+                             F.FixedTemperatureBC(subdomain=coolant, value=420.0)],
+        initial_condition=F.InitialTemperature(value=lambda x: 420.0 + 30.0 * x[2], volume=W),
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, stepsize=dt, final_time=final_time))
+    H = F.Species("H")
+    traps = [F.Species(nm, mobile=False) for nm in ("W_t1", "W_t2", "Cu_t", "CuCrZr_t")]
+    par = [(W, 20.0, 0.10, 3.0, 0.20, 1.5), (W, 12.0, 0.10, 2.0, 0.30, 0.8),
+           (Cu, 25.0, 0.09, 4.0, 0.15, 0.5), (CuCrZr, 18.0, 0.11, 3.5, 0.25, 0.6)]
+    reactions = []
+    for ts, (vol, k0, Ek, p0, Ep, dens) in zip(traps, par):
+        empty = F.ImplicitSpecies(n=dens, others=[ts])
+        reactions.append(F.Reaction(reactant=[H, empty], product=ts, k_0=k0, E_k=Ek, p_0=p0, E_p=Ep, volume=vol))
+    hyd = F.HydrogenTransportProblem(
+        mesh=F.Mesh(raw), subdomains=subdomains, species=[H] + traps, reactions=reactions,
+        boundary_conditions=[F.FixedConcentrationBC(subdomain=top, value=1.0, species=H),
+                             F.FixedConcentrationBC(subdomain=coolant, value=0.0, species=H)],
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, stepsize=dt, final_time=final_time))
+    hyd.exports = [F.TotalVolume(field=H, volume=W), F.TotalVolume(field=traps[0], volume=W),
+                   F.TotalVolume(field=traps[2], volume=Cu), F.SurfaceFlux(field=H, surface=coolant)]
+    coupled = F.CoupledTransientHeatTransferHydrogenTransport(heat_problem=heat, hydrogen_problem=hyd)
+    return coupled, [H] + traps
+
+
+def permeation_advection_2d(n=8, nsteps=4, dt=2.0, L=3e-4):
+    """BASELINE configs[4] (C4) in small: transient 2D permeation with advection and
+    Sieverts / Henry surface conditions: square of side ``L``, mobile H, Poiseuille-like
+    velocity ``(a y (L - y), 0)`` as in test/system_tests/test_advection_term_integration.py:57-66,
+    ``SievertsBC`` upstream with the parameters of test/test_permeation_problem.py:60-66,
+    ``HenrysBC`` downstream; the outgoing flux and the inventory are recorded."""
+    raw = F.create_rectangle(((0.0, 0.0), (L, L)), (n, n))
+    mat = F.Material(D_0=1.9e-7, E_D=0.2)
+    vol = F.VolumeSubdomain(id=1, material=mat)
+    left = F.SurfaceSubdomain(id=1, locator=lambda x: np.isclose(x[0], 0.0))
+    right = F.SurfaceSubdomain(id=2, locator=lambda x: np.isclose(x[0], L))
+    H = F.Species("H")
+    a = 4.0 * 2e-6 / L**2          # peak velocity 2e-6 m/s: cell Peclet number below one
+
+    def velocity_func(x):
+        values = np.zeros((2, x.shape[1]))
+        values[0] = a * x[1] * (L - x[1])
+        return values
+
+    vel = F.VectorFunction(raw, velocity_func)
+    m = F.HydrogenTransportProblem(
+        mesh=F.Mesh(raw), subdomains=[vol, left, right], species=[H], temperature=500.0,
+        boundary_conditions=[
+            F.SievertsBC(subdomain=left, S_0=4.02e21, E_S=1.04, pressure=100, species=H),
+            F.HenrysBC(subdomain=right, H_0=6.0e17, E_H=0.9, pressure=lambda t: 1.0 + 0.5 * t, species=H)],
+        advection_terms=[F.AdvectionTerm(velocity=vel, subdomain=vol, species=H)],
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, stepsize=dt, final_time=nsteps * dt))
+    m.exports = [F.SurfaceFlux(field=H, surface=right), F.TotalVolume(field=H, volume=vol)]
+    return m, H

@@ -22,6 +22,7 @@ CASES = [
     ("heat_mms", (True, 40)), ("flux_bc_mms", (False, 40)), ("flux_bc_mms", (True, 40)),
     ("coupled_heat_hydrogen_mms", (40, 2)), ("advection_trap_mms_2d", (6,)),
     ("multi_isotope_traps_3d", (3,)), ("complex_reaction", ()), ("recombination_flux", (2, 5)),
+    ("monoblock_coupled_3d", (4,)), ("permeation_advection_2d", (6,)),
 ]
 
 
