@@ -60,9 +60,11 @@ def mms_1_mobile_steady(dim, n):
     return m, H, u_exact(np)
 
 
-def mms_1_mobile_1_trap_steady(dim, n):
+def mms_1_mobile_1_trap_steady(dim, n, reference_solution=False):
     """reference test/system_tests/test_1_mobile_1_trap.py:20-120 (steady MMS with
-    one trap: mobile + trapped species, Arrhenius k and p, constant density)."""
+    one trap: mobile + trapped species, Arrhenius k and p, constant density).
+    ``reference_solution=True`` takes the manufactured solutions of the reference's 2D / 3D
+    versions (:193-421) instead of the smoother ones the parity tests use."""
     D_0, E_D = 2, 0.1
     k_0, E_k, p_0, E_p, n_trap = 2, 1.5, 0.2, 0.1, 3
     if dim == 1:
@@ -77,6 +79,9 @@ def mms_1_mobile_1_trap_steady(dim, n):
         mesh = F.Mesh(raw)
         u_ex = lambda mod: (lambda x: 1 + mod.sin(2 * mod.pi * x[0]) + mod.cos(2 * mod.pi * x[1]))
         v_ex = lambda mod: (lambda x: 1 + mod.cos(2 * mod.pi * x[0]) + mod.sin(2 * mod.pi * x[1]))
+        if reference_solution:
+            u_ex = lambda mod: (lambda x: 1.5 + mod.sin(3 * mod.pi * x[0]) + mod.cos(3 * mod.pi * x[1]))
+            v_ex = lambda mod: (lambda x: mod.sin(3 * mod.pi * x[0]) + mod.cos(3 * mod.pi * x[1]))
         mat = F.Material(D_0=D_0, E_D=E_D)
         vol = F.VolumeSubdomain(id=1, material=mat)
         left = F.SurfaceSubdomain(id=1, locator=lambda x: np.isclose(x[0], 0))
@@ -146,16 +151,19 @@ def mms_1_mobile_transient(n=9999, final_time=0.1, nsteps=50):
     return m, H, (lambda x: u_exact(np)(x, final_time))
 
 
-def permeation_1d(mesh_size=1001, final_time=50, dt=0.3):
+def permeation_1d(mesh_size=1001, final_time=50, dt=0.3, n_volumes=1):
     """reference test/test_permeation_problem.py:35-113: Sieverts BC upstream, c=0
-    downstream, outgassing flux against the series solution (1 % mean error)."""
+    downstream, outgassing flux against the series solution (1 % mean error);
+    ``n_volumes=4``, ``dt=0.4``: the four-subdomain version (:116-204)."""
     L = 3e-04
     m = F.HydrogenTransportProblem()
     m.mesh = F.Mesh1D(np.linspace(0, L, num=mesh_size))
     mat = F.Material(D_0=1.9e-7, E_D=0.2, name="my_mat")
-    vol = F.VolumeSubdomain1D(id=1, borders=[0, L], material=mat)
+    vols = [F.VolumeSubdomain1D(id=i + 1, borders=[i * L / n_volumes, (i + 1) * L / n_volumes], material=mat)
+            for i in range(n_volumes)]
+    vol = vols[0]
     left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=L)
-    m.subdomains = [vol, left, right]
+    m.subdomains = [*vols, left, right]
     H = F.Species("H")
     m.species = [H]
     m.temperature = 500
@@ -597,3 +605,31 @@ def permeation_advection_2d(n=8, nsteps=4, dt=2.0, L=3e-4):
         settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, stepsize=dt, final_time=nsteps * dt))
     m.exports = [F.SurfaceFlux(field=H, surface=right), F.TotalVolume(field=H, volume=vol)]
     return m, H
+
+
+def species_dependent_source_mms(n=9999):
+    """reference test/system_tests/test_1_mobile_species.py:285-347: species A carries a source
+    ``B**2`` of a second species B whose manufactured solution is linear (exact in P1), plus the
+    manufactured source that makes ``A = 1 + sin(2 pi x)`` the solution (L2 < 1e-3)."""
+    A_exact = lambda mod: (lambda x: 1 + mod.sin(2 * mod.pi * x[0]))
+    B_exact = lambda x: 1 + x[0]
+    m = F.HydrogenTransportProblem()
+    m.mesh = F.Mesh1D(np.linspace(0, 1, n + 1))
+    x = ufl.SpatialCoordinate(m.mesh.mesh)
+    vol = F.VolumeSubdomain1D(id=1, borders=[0, 1], material=F.Material(name="mat", D_0=1, E_D=0))
+    left, right = F.SurfaceSubdomain1D(id=1, x=0), F.SurfaceSubdomain1D(id=2, x=1)
+    m.subdomains = [vol, left, right]
+    A, B = F.Species("A"), F.Species("B")
+    m.species = [A, B]
+    m.temperature = 500
+    m.boundary_conditions = [
+        F.DirichletBC(subdomain=left, value=A_exact(ufl), species=A),
+        F.DirichletBC(subdomain=right, value=A_exact(ufl), species=A),
+        F.DirichletBC(subdomain=left, value=B_exact, species=B),
+        F.DirichletBC(subdomain=right, value=B_exact, species=B),
+    ]
+    f = -ufl.div(1 * ufl.grad(A_exact(ufl)(x))) - B_exact(x) ** 2
+    m.sources = [F.ParticleSource(value=lambda B: B**2, volume=vol, species=A, species_dependent_value={"B": B}),
+                 F.ParticleSource(value=f, volume=vol, species=A)]
+    m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    return m, (A, B), (A_exact(np), B_exact)

@@ -55,3 +55,88 @@ def test_c4_permeation_advection_parity():
     assert gm.timesteps == rm.timesteps
     assert _rel(Hg.post_processing_solution.x.array, Hr.post_processing_solution.x.array) < 1e-8
     _same_exports(gm.exports, rm.exports)
+
+
+def test_species_dependent_source_parity():
+    """reference test/system_tests/test_1_mobile_species.py:285-347: a source on A that depends on
+    the concentration of B (a solution-dependent volume term with an off-diagonal Jacobian block)."""
+    from cases import error_L2, species_dependent_source_mms
+
+    gm, (Ag, Bg), (A_exact, _) = species_dependent_source_mms(2000)
+    rm, (Ar, Br), _ = species_dependent_source_mms(2000)
+    rm.solver_backend = OracleBackend()
+    for m in (gm, rm):
+        m.initialise()
+        m.run()
+    assert gm.solver.solver.getIterationNumber() == rm.solver.solver.getIterationNumber()
+    assert _rel(gm.u.x.array, rm.u.x.array) < 1e-8
+    assert error_L2(gm.mesh.mesh, Ag.post_processing_solution.x.array, A_exact) < 1e-3
+
+
+def test_permeation_multi_volume_parity():
+    """reference test/test_permeation_problem.py:116-204 (four volume subdomains, Sieverts
+    upstream): outgassing-flux history against the oracle."""
+    from cases import permeation_1d
+
+    gm, Hg, fg, _, _ = permeation_1d(mesh_size=1001, final_time=8, dt=0.4, n_volumes=4)
+    rm, Hr, fr, _, _ = permeation_1d(mesh_size=1001, final_time=8, dt=0.4, n_volumes=4)
+    rm.solver_backend = OracleBackend()
+    for m in (gm, rm):
+        m.initialise()
+        m.run()
+    assert gm.timesteps == rm.timesteps
+    assert _rel(Hg.post_processing_solution.x.array, Hr.post_processing_solution.x.array) < 1e-8
+    _same_exports(gm.exports, rm.exports)
+
+
+def test_mesh_from_xdmf_and_field_files_through_the_cuda_path(tmp_path):
+    """SURVEY 8f3 / 8f4 on the product path: a tagged mesh read from XDMF files, solved by the CUDA
+    library, fields written as XDMF and as a VTK series; the files hold the device solution and the
+    solution matches the oracle on the same files."""
+    import festim_b200 as F
+    from festim_b200 import field_io
+
+    base = F.create_unit_cube(4, 3, 3)
+    ctag = np.where(base.coords[base.cells].mean(axis=1)[:, 0] < 0.5, 1, 2).astype(np.int32)
+    fx = base.coords[base.bfacets][:, :, 0]
+    ftag = np.where(np.all(fx == 0, axis=1), 10, np.where(np.all(fx == 1, axis=1), 20, 0)).astype(np.int32)
+    tagged = np.nonzero(ftag)[0]
+    with field_io.XDMFFile(tmp_path / "volumes.xdmf", "w") as f:
+        f.write_meshtags(F.MeshTags(base, 3, np.arange(base.num_cells), ctag), name="Grid")
+    with field_io.XDMFFile(tmp_path / "facets.xdmf", "w") as f:
+        f.write_meshtags(F.MeshTags(base, 2, tagged, ftag[tagged]), name="Grid")
+
+    def build(tag):
+        p = F.HydrogenTransportProblem()
+        p.mesh = F.MeshFromXDMF(volume_file=tmp_path / "volumes.xdmf", facet_file=tmp_path / "facets.xdmf")
+        H = F.Species("H")
+        p.species = [H]
+        v1 = F.VolumeSubdomain(id=1, material=F.Material(D_0=2.0, E_D=0.1))
+        v2 = F.VolumeSubdomain(id=2, material=F.Material(D_0=0.5, E_D=0.05))
+        s1, s2 = F.SurfaceSubdomain(id=10), F.SurfaceSubdomain(id=20)
+        p.subdomains = [v1, v2, s1, s2]
+        p.boundary_conditions = [F.FixedConcentrationBC(s1, value=1.0, species=H),
+                                 F.FixedConcentrationBC(s2, value=0.0, species=H)]
+        p.temperature = lambda x: 400.0 + 100.0 * x[0]
+        p.exports = [F.XDMFExport(tmp_path / f"{tag}.xdmf", field=H),
+                     F.VTXSpeciesExport(tmp_path / f"{tag}.bp", field=H),
+                     F.SurfaceFlux(field=H, surface=s2)]
+        p.settings = F.Settings(transient=False, atol=1e-12, rtol=1e-12)
+        return p, H
+
+    gm, Hg = build("gpu")
+    rm, Hr = build("ref")
+    rm.solver_backend = OracleBackend()
+    for m in (gm, rm):
+        m.initialise()
+        m.run()
+    assert _rel(Hg.post_processing_solution.x.array, Hr.post_processing_solution.x.array) < 1e-8
+    _same_exports(gm.exports[2:], rm.exports[2:])
+    _, _, data, _ = field_io.read_vtu(tmp_path / "gpu.bp" / "step_000000.vtu")
+    assert np.array_equal(data["H"], Hg.post_processing_solution.x.array)
+    gm.exports[0]._writer.close()
+    rd = field_io.XDMFFile(tmp_path / "gpu.xdmf", "r")
+    import xml.etree.ElementTree as ET
+
+    item = ET.parse(tmp_path / "gpu.xdmf").getroot().find(".//Attribute/DataItem")
+    assert np.array_equal(rd._read_item(item).ravel(), Hg.post_processing_solution.x.array)

@@ -161,3 +161,43 @@ def test_non_homogeneous_density(name):
     m, total = non_homogeneous_density(func)
     _run(m)
     assert np.isclose(total.value, expected)
+
+
+@pytest.mark.parametrize("dim,n,tol_mobile,tol_trapped", [(2, 50, 4e-3, 2e-3), (3, 20, 3e-2, 9e-3)])
+def test_1_mobile_1_trap_MMS_2D_3D(dim, n, tol_mobile, tol_trapped):
+    """reference test/system_tests/test_1_mobile_1_trap.py:309-421 (2D, 50 x 50: 4e-3 / 2e-3) and
+    :193-306 (3D, 20^3: 3e-2 / 9e-3), with the reference's manufactured solutions."""
+    m, (mobile, trapped), (ue, ve) = mms_1_mobile_1_trap_steady(dim, n, reference_solution=True)
+    m.settings.atol = m.settings.rtol = 1e-10
+    _run(m)
+    assert m.solver.solver.getConvergedReason() > 0
+    mesh = m.mesh.mesh
+    assert error_L2(mesh, mobile.post_processing_solution.x.array, ue) < tol_mobile
+    assert error_L2(mesh, trapped.post_processing_solution.x.array, ve) < tol_trapped
+
+
+def test_species_dependent_source_MMS_steady_state():
+    """reference test/system_tests/test_1_mobile_species.py:285-347 (L2 < 1e-3)."""
+    from cases import species_dependent_source_mms
+
+    m, (A, B), (A_exact, B_exact) = species_dependent_source_mms()
+    _run(m)
+    mesh = m.mesh.mesh
+    assert error_L2(mesh, A.post_processing_solution.x.array, A_exact) < 1e-3
+    assert np.allclose(B.post_processing_solution.x.array, 1 + mesh.coords[:, 0], atol=1e-9)
+
+
+def test_permeation_problem_multi_volume():
+    """reference test/test_permeation_problem.py:116-204: the same permeation problem on four
+    volume subdomains of one material (mean relative error < 1 %)."""
+    from cases import permeation_1d, permeation_relative_error
+
+    import festim_b200 as F
+
+    m, H, flux, mat, L = permeation_1d(dt=0.4, n_volumes=4)
+    _run(m)
+    assert sorted(np.unique(m.volume_meshtags.values)) == [1, 2, 3, 4]
+    D = 1.9e-7 * np.exp(-0.2 / F.k_B / 500)
+    S = 4.02e21 * np.exp(-1.04 / F.k_B / 500)
+    err = permeation_relative_error(D, D * S, np.abs(np.array(flux.data)), L, np.array(flux.t), 100)
+    assert err < 0.01
