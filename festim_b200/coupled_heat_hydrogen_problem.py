@@ -50,16 +50,24 @@ class CoupledTransientHeatTransferHydrogenTransport:
             )
         heat.initialise()
         if self.non_matching_meshes:
-            raise NotImplementedError(
-                "non-matching heat / hydrogen meshes need point location "
-                "(reference helpers.py:345-371) and are not implemented"
-            )
-        hyd.temperature = heat.u  # aliased: the hydrogen kernels see every new T
+            # reference :124-129: T on the hydrogen mesh is a separate field, refreshed from the
+            # heat solution by point location + P1 interpolation before every hydrogen step
+            from festim_b200 import fem
+
+            T_func = fem.Function(fem.functionspace(hyd.mesh.mesh, ("P", 1)))
+            self._locator = fem.interpolate_nonmatching(T_func, heat.u)
+            hyd.temperature = T_func
+        else:
+            hyd.temperature = heat.u  # aliased: the hydrogen kernels see every new T
         hyd.initialise()
 
     def iterate(self):
         heat, hyd = self.heat_problem, self.hydrogen_problem
         heat.iterate()
+        if self.non_matching_meshes:   # reference :136-139
+            from festim_b200 import fem
+
+            fem.interpolate_nonmatching(hyd.temperature_fenics, heat.u, locator=self._locator)
         hyd.iterate()
         next_dt = min(float(hyd.dt), float(heat.dt))
         heat.dt.value = next_dt

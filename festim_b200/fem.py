@@ -196,3 +196,70 @@ def nodal_env(mesh, verts):
         raise NotImplementedError("species-dependent values cannot be interpolated")
 
     return {"x": pts, "field": field, "field_grad": field_grad, "species": species}
+
+
+# ---------------------------------------------------------------------------------------------
+# point location and interpolation between non-matching meshes (reference helpers.py:345-371
+# ``nmm_interpolate`` -> dolfinx ``create_interpolation_data`` / ``interpolate_nonmatching``)
+# ---------------------------------------------------------------------------------------------
+class PointLocator:
+    """Cell and barycentric coordinates of points in a P1 simplex mesh.
+
+    Candidates are the cells around the nearest mesh vertices (k-d tree); the cell whose smallest
+    barycentric coordinate is largest wins, so points on facets / vertices resolve consistently and
+    points a round-off outside the mesh take the linear extension of the closest cell, which is
+    what dolfinx's ``padding`` achieves."""
+
+    def __init__(self, mesh, k=4):
+        from scipy.spatial import cKDTree
+
+        self.mesh = mesh
+        self.k = min(k, mesh.num_vertices)
+        self.tree = cKDTree(mesh.coords)
+        x = mesh.coords[mesh.cells]                       # (nc, d+1, d)
+        self.x0 = x[:, 0, :]
+        self.Jinv = np.linalg.inv(np.transpose(x[:, 1:, :] - x[:, :1, :], (0, 2, 1)))   # (nc, d, d)
+
+    def _bary(self, cells, pts):
+        lam = np.einsum("nij,nj->ni", self.Jinv[cells], pts - self.x0[cells])
+        return np.concatenate([1.0 - lam.sum(axis=1, keepdims=True), lam], axis=1)
+
+    def locate(self, pts):
+        pts = np.atleast_2d(np.asarray(pts, dtype=np.float64))[:, : self.mesh.gdim]
+        n = pts.shape[0]
+        ptr, idx = self.mesh.vertex_to_cell
+        d1 = self.mesh.tdim + 1
+        _, near = self.tree.query(pts, k=self.k)
+        near = near.reshape(n, -1)
+        best_cell = np.full(n, -1, dtype=np.int64)
+        best_min = np.full(n, -np.inf)
+        best_bary = np.zeros((n, d1))
+        for col in range(near.shape[1]):
+            v = near[:, col]
+            counts = ptr[v + 1] - ptr[v]
+            for j in range(int(counts.max())):
+                has = np.nonzero(j < counts)[0]
+                cells = idx[ptr[v[has]] + j] // d1
+                bary = self._bary(cells, pts[has])
+                score = bary.min(axis=1)
+                better = score > best_min[has]
+                sel = has[better]
+                best_cell[sel], best_min[sel], best_bary[sel] = cells[better], score[better], bary[better]
+            if np.all(best_min > -1e-12):
+                break
+        return best_cell, best_bary, best_min
+
+
+def interpolate_nonmatching(f_out, f_in, padding=1e-11, locator=None):
+    """``f_out`` <- P1 interpolant of ``f_in`` at the vertices of ``f_out``'s mesh.  Points a
+    round-off outside ``f_in``'s mesh take the linear extension of the closest cell (the role of
+    dolfinx's ``padding``, accepted for signature compatibility); points farther out raise.
+    Returns the locator so that repeated transfers between the same meshes reuse it."""
+    mesh_in, mesh_out = f_in.function_space.mesh, f_out.function_space.mesh
+    locator = locator or PointLocator(mesh_in)
+    cells, bary, worst = locator.locate(mesh_out.coords)
+    if np.any(worst < -1e-6):      # more than a millionth of a cell outside (barycentric units)
+        raise ValueError("interpolate_nonmatching: some points of the target mesh lie outside the source mesh")
+    vals = f_in.x.array.reshape(mesh_in.num_vertices, -1)[:, 0]
+    f_out.x.array.reshape(mesh_out.num_vertices, -1)[:, 0] = np.einsum("na,na->n", vals[mesh_in.cells[cells]], bary)
+    return locator

@@ -633,3 +633,37 @@ def species_dependent_source_mms(n=9999):
                  F.ParticleSource(value=f, volume=vol, species=A)]
     m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
     return m, (A, B), (A_exact(np), B_exact)
+
+
+def coupled_non_matching_mms(n_heat=499, n_hyd=1999, nsteps=20):
+    """reference test/system_tests/test_coupled_heat_hydrogen.py:210-332: coupled heat + hydrogen
+    MMS with the heat problem on a coarse and the hydrogen problem on a fine mesh (L2 < 2e-7)."""
+    density, heat_capacity, lam = 1.3, 2.3, 4.1
+    D_0, E_D, k_B, final_time = 1.3, 0.2, F.k_B, 5
+    mat = F.Material(D_0=D_0, E_D=E_D, thermal_conductivity=lam, density=density, heat_capacity=heat_capacity)
+    vol = F.VolumeSubdomain1D(id=1, borders=[0, 1], material=mat)
+    left, right = F.SurfaceSubdomain1D(id=2, x=0), F.SurfaceSubdomain1D(id=3, x=1)
+    mobile = F.Species("mobile", mobile=True)
+    exact_T = lambda x, t: 2 * x[0] ** 2 + 5 * t
+    heat = F.HeatTransferProblem(
+        mesh=F.Mesh1D(vertices=np.linspace(0, 1, n_heat + 1)), subdomains=[vol, left, right],
+        boundary_conditions=[F.FixedTemperatureBC(subdomain=left, value=exact_T),
+                             F.FixedTemperatureBC(subdomain=right, value=exact_T)],
+        sources=[F.HeatSource(value=density * heat_capacity * 5 - lam * 4, volume=vol)],
+        initial_condition=F.InitialTemperature(lambda x: exact_T(x, 0), volume=vol),
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, final_time=final_time,
+                            stepsize=final_time / nsteps))
+    exact_c = lambda x, t: 4 * x[0] ** 2 + 10 * t
+    D = lambda x, t: D_0 * ufl.exp(-E_D / (k_B * exact_T(x, t)))
+    source = lambda x, t: 10 - ufl.div(D(x, t) * ufl.grad(exact_c(x, t)))
+    hyd = F.HydrogenTransportProblem(
+        mesh=F.Mesh1D(vertices=np.linspace(0, 1, n_hyd + 1)), subdomains=[vol, left, right],
+        boundary_conditions=[F.FixedConcentrationBC(subdomain=left, value=exact_c, species=mobile),
+                             F.FixedConcentrationBC(subdomain=right, value=exact_c, species=mobile)],
+        species=[mobile],
+        initial_conditions=[F.InitialConcentration(value=lambda x: exact_c(x, t=0), species=mobile, volume=vol)],
+        sources=[F.ParticleSource(value=source, volume=vol, species=mobile)],
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=True, final_time=final_time,
+                            stepsize=final_time / nsteps))
+    coupled = F.CoupledTransientHeatTransferHydrogenTransport(heat_problem=heat, hydrogen_problem=hyd)
+    return coupled, mobile, (lambda x: exact_c(x, final_time))

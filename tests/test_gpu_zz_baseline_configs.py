@@ -140,3 +140,22 @@ def test_mesh_from_xdmf_and_field_files_through_the_cuda_path(tmp_path):
 
     item = ET.parse(tmp_path / "gpu.xdmf").getroot().find(".//Attribute/DataItem")
     assert np.array_equal(rd._read_item(item).ravel(), Hg.post_processing_solution.x.array)
+
+
+def test_coupled_non_matching_meshes_parity():
+    """reference test/system_tests/test_coupled_heat_hydrogen.py:210-332: the temperature field of
+    the hydrogen problem is a separate P1 field refreshed from the heat solution before every step;
+    the device copy must follow the in-place updates."""
+    from cases import coupled_non_matching_mms, error_L2
+
+    cg, mg, exact = coupled_non_matching_mms(199, 499, 10)
+    cr, mr, _ = coupled_non_matching_mms(199, 499, 10)
+    cr.heat_problem.solver_backend = OracleBackend()
+    cr.hydrogen_problem.solver_backend = OracleBackend()
+    for c in (cg, cr):
+        c.initialise()
+        c.run()
+    assert cg.hydrogen_problem.timesteps == cr.hydrogen_problem.timesteps
+    assert _rel(cg.heat_problem.u.x.array, cr.heat_problem.u.x.array) < 1e-8
+    assert _rel(mg.post_processing_solution.x.array, mr.post_processing_solution.x.array) < 1e-8
+    assert error_L2(cg.hydrogen_problem.mesh.mesh, mg.post_processing_solution.x.array, exact) < 1e-5

@@ -201,3 +201,48 @@ def test_permeation_problem_multi_volume():
     S = 4.02e21 * np.exp(-1.04 / F.k_B / 500)
     err = permeation_relative_error(D, D * S, np.abs(np.array(flux.data)), L, np.array(flux.t), 100)
     assert err < 0.01
+
+
+def test_coupled_problem_non_matching_mesh():
+    """reference test/system_tests/test_coupled_heat_hydrogen.py:210-332 (L2 < 2e-7): heat on 499
+    cells, hydrogen on 1999, temperature transferred by point location + P1 interpolation."""
+    from cases import coupled_non_matching_mms
+
+    coupled, mobile, exact = coupled_non_matching_mms()
+    coupled.heat_problem.solver_backend = OracleBackend()
+    coupled.hydrogen_problem.solver_backend = OracleBackend()
+    coupled.initialise()
+    assert coupled.non_matching_meshes
+    coupled.run()
+    mesh = coupled.hydrogen_problem.mesh.mesh
+    assert error_L2(mesh, mobile.post_processing_solution.x.array, exact) < 2e-7
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_interpolate_nonmatching_reproduces_linear_fields(dim):
+    """P1 interpolation between unrelated meshes is exact for affine fields, including at target
+    vertices that sit on source facets, vertices and the boundary."""
+    import festim_b200 as F
+    from festim_b200 import fem
+
+    if dim == 1:
+        src, dst = F.Mesh1D(np.linspace(0, 1, 38)).mesh, F.Mesh1D(np.linspace(0, 1, 101)).mesh
+    elif dim == 2:
+        src, dst = F.create_unit_square(7, 5), F.create_unit_square(14, 11)
+    else:
+        src, dst = F.create_unit_cube(4, 3, 5), F.create_unit_cube(8, 7, 5)
+    coef = np.array([1.5, -2.0, 0.75])[:dim]
+    f_in, f_out = fem.Function(fem.functionspace(src, ("P", 1))), fem.Function(fem.functionspace(dst, ("P", 1)))
+    f_in.x.array[:] = 3.0 + src.coords @ coef
+    fem.interpolate_nonmatching(f_out, f_in)
+    assert np.allclose(f_out.x.array, 3.0 + dst.coords @ coef, rtol=0, atol=1e-12)
+    # a non-affine field: interpolation error of the coarse P1 interpolant only
+    f_in.x.array[:] = np.sin(src.coords[:, 0])
+    fem.interpolate_nonmatching(f_out, f_in)
+    assert np.abs(f_out.x.array - np.sin(dst.coords[:, 0])).max() < 0.02
+    # target points outside the source mesh are an error
+    far = fem.Function(fem.functionspace(F.Mesh1D(np.linspace(0, 2, 5)).mesh if dim == 1 else
+                                         F.create_rectangle(((0, 0), (2, 1)), (3, 3)) if dim == 2 else
+                                         F.create_box(((0, 0, 0), (2, 1, 1)), (2, 2, 2)), ("P", 1)))
+    with pytest.raises(ValueError, match="outside the source mesh"):
+        fem.interpolate_nonmatching(far, f_in)
