@@ -53,6 +53,7 @@ from festim_b200.initial_condition import (
     InitialConcentration,
     InitialConditionBase,
     InitialTemperature,
+    read_function_from_file,
 )
 from festim_b200.material import Material, SolubilityLaw
 from festim_b200.mesh import (

@@ -345,7 +345,9 @@ class XDMFExport(ExportBaseClass):
 
 
 class VTXSpeciesExport(ExportBaseClass):
-    """``vtx.py:83-180``.  ``checkpoint=True`` (adios4dolfinx restart files) is not available."""
+    """``vtx.py:83-180``.  ``checkpoint=True`` writes a restart file (mesh + every field at every
+    export time) that ``read_function_from_file`` reads back - an XDMF document inside the ``.bp``
+    directory instead of adios4dolfinx's ADIOS2 stream."""
 
     def __init__(self, filename, field, subdomain=None, checkpoint=False, times=None):
         super().__init__(filename, ".bp", times)
@@ -366,7 +368,11 @@ class VTXSpeciesExport(ExportBaseClass):
         return [field.post_processing_solution for field in self._field]
 
     def write(self, t):
-        self.writer.write(t, {f.name: f.post_processing_solution.x.array for f in self._field})
+        if self._checkpoint:   # reference hydrogen_transport_problem.py:1069-1076
+            for f in self._field:
+                self.writer.write_function((f.name, f.post_processing_solution.x.array), t)
+        else:
+            self.writer.write(t, {f.name: f.post_processing_solution.x.array for f in self._field})
 
 
 class VTXTemperatureExport(ExportBaseClass):

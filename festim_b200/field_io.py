@@ -289,6 +289,32 @@ class XDMFFile:
         mesh.file_vertex_map = file_to_mesh
         return mesh
 
+    def function_times(self, name):
+        """Time values stored for the named function."""
+        self._require("r")
+        return [float(g.find("Time").get("Value")) for g in self._function_grids(name)]
+
+    def _function_grids(self, name):
+        for coll in self._domain.iter("Grid"):
+            if coll.get("Name") == name and coll.get("GridType") == "Collection":
+                return coll.findall("Grid")
+        names = [g.get("Name") for g in self._domain.iter("Grid") if g.get("GridType") == "Collection"]
+        raise ValueError(f"{self.filename}: no function named {name!r} (found {names})")
+
+    def read_function(self, name, t=None):
+        """Nodal values of the named function at time ``t`` (the last one stored when None)."""
+        self._require("r")
+        grids = self._function_grids(name)
+        if t is None:
+            grid = grids[-1]
+        else:
+            times = np.array([float(g.find("Time").get("Value")) for g in grids])
+            hit = np.nonzero(np.isclose(times, float(t), rtol=1e-9, atol=1e-12))[0]
+            if len(hit) == 0:
+                raise ValueError(f"{self.filename}: function {name!r} has no time {t} (stored: {times.tolist()})")
+            grid = grids[int(hit[-1])]
+        return np.asarray(self._read_item(grid.find("Attribute/DataItem")), dtype=np.float64).reshape(-1)
+
     def read_meshtags(self, mesh, name="Grid"):
         """Tags of the named grid mapped onto ``mesh``: entities are matched by their vertex sets.
         Facet tags are kept for exterior facets (the continuous problem integrates over no others);

@@ -418,10 +418,16 @@ class HydrogenTransportProblem(ProblemBase):
             export.writer = VTUSeriesWriter(export.filename, self.mesh.mesh)
         elif isinstance(export, _exports.VTXSpeciesExport):
             if export._checkpoint:
-                raise NotImplementedError(
-                    "checkpoint=True writes adios4dolfinx restart files, which need ADIOS2 "
-                    "(not in this image); use checkpoint=False or XDMFExport")
-            export.writer = VTUSeriesWriter(export.filename, self.mesh.mesh)
+                # reference :464-469 (io4dolfinx.write_mesh): here the restart file is an XDMF
+                # document with raw side-car data inside the `.bp` directory, read back by
+                # `read_function_from_file`
+                if field_io.is_io_rank():
+                    export.writer = field_io.XDMFFile(export.filename / "checkpoint.xdmf", "w")
+                    export.writer.write_mesh(self.mesh.mesh)
+                else:
+                    export.writer = field_io.NullWriter()
+            else:
+                export.writer = VTUSeriesWriter(export.filename, self.mesh.mesh)
         elif isinstance(export, _exports.CustomFieldExport):
             if export.checkpoint:
                 raise NotImplementedError("checkpoint=True needs ADIOS2 (not in this image)")

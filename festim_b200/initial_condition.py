@@ -68,3 +68,32 @@ class InitialTemperature(InitialConditionBase):
 
     def create_expr_fenics(self, mesh, function_space):
         self._create(mesh)
+
+
+def read_function_from_file(filename, name, timestamp, family="P", order=1, mesh=None):
+    """Reference ``initial_condition.py:238-283``: the named field at ``timestamp`` from a restart
+    file written by ``VTXSpeciesExport(checkpoint=True)`` (or any XDMF file of
+    ``festim_b200.field_io.XDMFFile``), as a P1 function on the file's mesh or - when ``mesh`` is
+    given - interpolated onto that mesh (identical meshes transfer exactly)."""
+    from pathlib import Path
+
+    from festim_b200 import field_io
+
+    if order != 1 or family not in ("P", "CG", "Lagrange"):
+        raise NotImplementedError("the B200 backend implements P1 elements only")
+    path = Path(filename)
+    if path.is_dir():
+        path = path / "checkpoint.xdmf"
+    rd = field_io.XDMFFile(path, "r")
+    mesh_in = rd.read_mesh("mesh")
+    u_in = fem.Function(fem.functionspace(mesh_in, ("P", 1)), name=name)
+    values = rd.read_function(name, timestamp)
+    if values.shape[0] != mesh_in.num_vertices:
+        raise ValueError(f"{path}: {values.shape[0]} values for {mesh_in.num_vertices} vertices")
+    u_in.x.array[:] = values
+    if mesh is None:
+        return u_in
+    target = getattr(mesh, "mesh", mesh) if not hasattr(mesh, "coords") else mesh
+    u = fem.Function(fem.functionspace(target, ("P", 1)), name=name)
+    fem.interpolate_nonmatching(u, u_in)
+    return u

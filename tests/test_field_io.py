@@ -184,9 +184,6 @@ def test_vtx_species_export(tmp_path):
         F.VTXSpeciesExport(tmp_path / "a.bp", field=1)
     with pytest.warns(UserWarning, match="does not have .bp extension"):
         F.VTXTemperatureExport(tmp_path / "a.txt")
-    m2, *_ = _problem_1d([F.VTXSpeciesExport(tmp_path / "c.bp", field=["H"], checkpoint=True)])
-    with pytest.raises(NotImplementedError, match="ADIOS2"):
-        m2.initialise()
 
 
 def test_vtx_last_step_holds_final_fields(tmp_path):
@@ -272,3 +269,67 @@ def test_custom_field_and_reaction_rate_exports(tmp_path):
     m2, *_ = _problem_1d([bad])
     with pytest.raises(AssertionError, match="not found in species_dependent_value"):
         m2.initialise()
+
+
+def test_checkpoint_and_restart(tmp_path):
+    """reference hydrogen_transport_problem.py:464-469, 1069-1076 (write) and
+    initial_condition.py:238-283 / test/test_initial_condition.py:144-270 (read): a run restarted
+    from the checkpoint of t = 0.2 reaches t = 0.3 with the fields of the uninterrupted run."""
+    m, H, trapped, _ = _problem_1d([])
+    m.exports = [F.VTXSpeciesExport(tmp_path / "restart.bp", field=[H, trapped], checkpoint=True)]
+    m.initialise()
+    m.run()
+    m.exports[0].writer.close()
+    assert (tmp_path / "restart.bp" / "checkpoint.xdmf").exists()
+    rd = field_io.XDMFFile(tmp_path / "restart.bp" / "checkpoint.xdmf", "r")
+    assert np.allclose(rd.function_times("H"), [0.1, 0.2, 0.3]) and np.allclose(rd.function_times("trapped"), [0.1, 0.2, 0.3])
+    final = F.read_function_from_file(tmp_path / "restart.bp", name="H", timestamp=0.3)
+    assert np.array_equal(final.x.array, H.post_processing_solution.x.array)
+
+    r, Hr, tr, _ = _problem_1d([])
+    r.settings.final_time = 0.1
+    vol = r.volume_subdomains[0]
+    r.initial_conditions = [
+        F.InitialConcentration(value=F.read_function_from_file(tmp_path / "restart.bp", "H", 0.2, mesh=r.mesh.mesh),
+                               species=Hr, volume=vol),
+        F.InitialConcentration(value=F.read_function_from_file(tmp_path / "restart.bp", "trapped", 0.2),
+                               species=tr, volume=vol)]
+    r.initialise()
+    r.run()
+    assert np.allclose(Hr.post_processing_solution.x.array, H.post_processing_solution.x.array, rtol=1e-8, atol=1e-9)
+    assert np.allclose(tr.post_processing_solution.x.array, trapped.post_processing_solution.x.array, rtol=1e-8, atol=1e-9)
+
+    with pytest.raises(ValueError, match="has no time"):
+        F.read_function_from_file(tmp_path / "restart.bp", "H", 0.25)
+    with pytest.raises(ValueError, match="no function named"):
+        F.read_function_from_file(tmp_path / "restart.bp", "D", 0.2)
+    with pytest.raises(NotImplementedError):
+        F.read_function_from_file(tmp_path / "restart.bp", "H", 0.2, order=2)
+
+
+def test_read_function_onto_another_mesh(tmp_path):
+    """reference test/test_initial_condition.py:144-190: a P1 field written to a file comes back as
+    the initial condition of a problem on its own mesh object."""
+    from festim_b200 import fem
+
+    src = F.create_unit_square(6, 6)
+    u_ref = fem.Function(fem.functionspace(src, ("P", 1)), name="my_function")
+    u_ref.interpolate(lambda x: x[1] ** 2 + 2 * x[0] ** 2)
+    with field_io.XDMFFile(tmp_path / "initial_condition.xdmf", "w") as f:
+        f.write_mesh(src)
+        f.write_function(u_ref, 0.2)
+    dst = F.create_unit_square(6, 6)
+    p = F.HydrogenTransportProblem()
+    Hs = F.Species("H")
+    p.species = [Hs]
+    p.mesh = F.Mesh(dst)
+    vol = F.VolumeSubdomain(id=1, material=F.Material(D_0=1, E_D=0.1, name="dummy_mat"))
+    p.subdomains = [vol]
+    value = F.read_function_from_file(tmp_path / "initial_condition.xdmf", name="my_function", timestamp=0.2, mesh=dst)
+    p.initial_conditions = [F.InitialConcentration(value=value, species=Hs, volume=vol)]
+    p.temperature = 300
+    p.settings = F.Settings(atol=1e-10, rtol=1e-10, final_time=1)
+    p.settings.stepsize = F.Stepsize(0.1)
+    p.solver_backend = OracleBackend()
+    p.initialise()
+    np.testing.assert_allclose(u_ref.x.array, p.u_n.x.array, atol=1e-14)
