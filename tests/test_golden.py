@@ -128,3 +128,51 @@ def test_solubility_laws_match_reference():
         args = (ufl.Const(case["T"]), case["c0"], case["E"], case["P"])
         assert float(ufl.evaluate(sieverts_law(*args), {})) == pytest.approx(case["sieverts"], rel=1e-14)
         assert float(ufl.evaluate(henrys_law(*args), {})) == pytest.approx(case["henry"], rel=1e-14)
+
+
+def _residual_form_problem(gold, transient):
+    """The problem of tests/golden/residual_form.json in the API mirror."""
+    par = gold["parameters"]
+    m = F.HydrogenTransportProblem()
+    m.mesh = F.Mesh1D(np.array(par["vertices"]))
+    species = {"H": F.Species("H"), "D": F.Species("D"), "t1": F.Species("t1", mobile=False),
+               "t2": F.Species("t2", mobile=False)}
+    m.species = [species[n] for n in gold["species"]]
+    vols = {i: F.VolumeSubdomain1D(id=i, borders=b, material=F.Material(D_0=par["D_0"][str(i)], E_D=par["E_D"][str(i)]))
+            for i, b in ((1, [0.0, 0.5]), (2, [0.5, 1.0]))}
+    surfs = {f["surface"]: F.SurfaceSubdomain1D(id=f["surface"], x=f["x"]) for f in par["fluxes"]}
+    m.subdomains = [*vols.values(), *surfs.values()]
+    m.reactions = [
+        F.Reaction(reactant=[species[r["mobile"]], F.ImplicitSpecies(n=r["n"], others=[species[r["trapped"]]])],
+                   product=species[r["trapped"]], k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
+                   volume=vols[r["volume"]]) for r in par["reactions"]]
+    m.sources = [F.ParticleSource(value=s["value"], volume=vols[s["volume"]], species=species[s["species"]])
+                 for s in par["sources"]]
+    m.boundary_conditions = [F.ParticleFluxBC(subdomain=surfs[f["surface"]], value=f["value"], species=species[f["species"]])
+                             for f in par["fluxes"]]
+    m.temperature = par["T"]
+    if transient:
+        m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=True, final_time=1.0, stepsize=par["dt"])
+    else:
+        m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    return m
+
+
+@pytest.mark.parametrize("label", ["transient", "steady"])
+def test_oracle_residual_and_jacobian_match_the_reference_form(label):
+    """reference src/festim/hydrogen_transport_problem.py:870-997, run for real (tools/make_golden.py):
+    the oracle's assembled residual equals the reference's form integrated cell by cell, and its
+    Jacobian (symbolic derivative) reproduces the exact directional difference of that residual."""
+    from oracle.newton import OracleBackend
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, label == "transient")
+    m.solver_backend = OracleBackend()
+    m.initialise()
+    u, u_n, d = (np.array(gold[k]).ravel() for k in ("u", "u_n", "delta"))
+    m.u.x.array[:] = u
+    m.u_n.x.array[:] = u_n
+    Fo, Jo = m.solver.residual_and_jacobian(m.u.x.array)
+    Fg, Jd = np.array(gold[f"F_{label}"]).ravel(), np.array(gold[f"Jdelta_{label}"]).ravel()
+    assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
+    assert np.abs(Jo @ d - Jd).max() <= 1e-12 * np.abs(Jd).max()

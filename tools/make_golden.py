@@ -304,6 +304,128 @@ def main():
                      "henry": float(henrys_law(T, c0, E, P))})
     json.dump(laws, open(os.path.join(out_dir, "solubility_laws.json"), "w"), indent=0)
 
+    # --- the residual form itself: HydrogenTransportProblem.create_formulation --------------
+    # (hydrogen_transport_problem.py:870-997).  The REAL method runs with every species'
+    # solution / previous solution / test function replaced by numbers carrying their gradient
+    # at one quadrature point and dx(id) / ds(id) replaced by the point's weight, so summing
+    # `problem.formulation` over the Gauss points of every cell (and the boundary vertices)
+    # gives the reference's element-by-element assembled residual on a small 1D mesh: diffusion
+    # with per-material, per-species Arrhenius D, mass term, trapping reactions restricted to
+    # their volumes (Arrhenius and constant detrapping), sources, particle fluxes, and the
+    # steady-state `c = 0` filler for immobile species outside their reactions' volumes.  The
+    # temperature is a constant, so all integrands are polynomials (degree <= 3) and 3-point
+    # Gauss-Legendre is exact: any conforming P1 assembly must reproduce these numbers to
+    # round-off.  F is quadratic in u, so (F(u + d) - F(u - d)) / 2 is J(u) d exactly.
+    import ufl as _ufl_stub
+
+    _ufl_stub.dot = lambda a, b: float(np.dot(a, b))
+
+    class PointMeasure:
+        def __init__(self, kind):
+            self.kind = kind
+
+        def __call__(self, subdomain_id):
+            return CTX[self.kind].get(subdomain_id, 0.0)
+
+    verts = np.array([0.0, 0.2, 0.5, 0.8, 1.0])
+    par = {
+        "vertices": verts.tolist(), "T": 500.0, "dt": 0.25,
+        "D_0": {"1": {"H": 2.0, "D": 1.4}, "2": {"H": 0.5, "D": 0.35}},
+        "E_D": {"1": {"H": 0.1, "D": 0.12}, "2": {"H": 0.2, "D": 0.22}},
+        "reactions": [
+            {"volume": 1, "mobile": "H", "trapped": "t1", "n": 3.0, "k_0": 1.5, "E_k": 0.2, "p_0": 0.3, "E_p": 0.1},
+            {"volume": 2, "mobile": "D", "trapped": "t2", "n": 2.0, "k_0": 0.8, "E_k": 0.15, "p_0": 0.05, "E_p": 0.0},
+        ],
+        "sources": [{"volume": 2, "species": "H", "value": 0.7}, {"volume": 1, "species": "t1", "value": 0.2}],
+        "fluxes": [{"surface": 3, "x": 1.0, "species": "H", "value": 0.4},
+                   {"surface": 4, "x": 0.0, "species": "D", "value": -0.3}],
+    }
+    names = ["H", "D", "t1", "t2"]
+    ns, nv = len(names), len(verts)
+    u = rng.uniform(0.2, 1.5, (nv, ns))
+    u_n = u * rng.uniform(0.8, 1.1, (nv, ns))
+    delta = rng.uniform(-0.3, 0.3, (nv, ns))
+
+    def reference_residual(uvals, transient):
+        prob = F.HydrogenTransportProblem()
+        species = [F.Species("H"), F.Species("D"), F.Species("t1", mobile=False), F.Species("t2", mobile=False)]
+        by_name = dict(zip(names, species))
+        prob.species = species
+        vols = {i: F.VolumeSubdomain1D(id=i, borders=b, material=F.Material(D_0=par["D_0"][str(i)], E_D=par["E_D"][str(i)]))
+                for i, b in ((1, [0.0, 0.5]), (2, [0.5, 1.0]))}
+        surfs = {f["surface"]: F.SurfaceSubdomain1D(id=f["surface"], x=f["x"]) for f in par["fluxes"]}
+        prob.subdomains = [*vols.values(), *surfs.values()]
+        reactions = []
+        for r in par["reactions"]:
+            imp = F.ImplicitSpecies(n=r["n"], others=[by_name[r["trapped"]]])
+            imp.value_fenics = r["n"]
+            reactions.append(F.Reaction(reactant=[by_name[r["mobile"]], imp], product=by_name[r["trapped"]],
+                                        k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
+                                        volume=vols[r["volume"]]))
+        prob.reactions = reactions
+        sources = []
+        for sdef in par["sources"]:
+            src = F.ParticleSource(value=1.0, volume=vols[sdef["volume"]], species=by_name[sdef["species"]])
+            src.value.fenics_object = sdef["value"]
+            sources.append(src)
+        prob.sources = sources
+        bcs = []
+        for f in par["fluxes"]:
+            bc = F.ParticleFluxBC(subdomain=surfs[f["surface"]], value=1.0, species=by_name[f["species"]])
+            bc._value_fenics = f["value"]
+            bcs.append(bc)
+        prob.boundary_conditions = bcs
+        prob.settings = F.Settings(atol=1, rtol=1, transient=transient, final_time=1 if transient else None)
+        prob.mesh = F.Mesh.__new__(F.Mesh)
+        prob.mesh._mesh = None
+        prob.mesh.coordinate_system = "cartesian"
+        prob.temperature_fenics = Constant(None, par["T"])
+        prob.dx, prob.ds = PointMeasure("dx"), PointMeasure("ds")
+        prob._dt = Constant(None, par["dt"])
+        prob.advection_terms = []
+
+        def point(values, grads, prev, row_species, phi, gphi, dx, ds):
+            for k, spe in enumerate(species):
+                spe.solution = WithGrad(values[k], [grads[k]])
+                spe.prev_solution = float(prev[k])
+                on = k == row_species
+                spe.test_function = WithGrad(phi if on else 0.0, [gphi if on else 0.0])
+            CTX["dx"], CTX["ds"] = dx, ds
+            prob.create_formulation()
+            return float(prob.formulation)
+
+        res = np.zeros((nv, ns))
+        gx, gw = np.polynomial.legendre.leggauss(3)
+        for c in range(nv - 1):
+            a, b = verts[c], verts[c + 1]
+            h = b - a
+            vol_id = 1 if b <= 0.5 + 1e-12 else 2
+            for xi, w in zip(gx, gw):
+                lam = np.array([0.5 * (1 - xi), 0.5 * (1 + xi)])      # P1 basis at the point
+                glam = np.array([-1.0 / h, 1.0 / h])
+                vals = lam @ uvals[c:c + 2]
+                grads = glam @ uvals[c:c + 2]
+                prev = lam @ u_n[c:c + 2]
+                for loc in range(2):
+                    for srow in range(ns):
+                        res[c + loc, srow] += point(vals, grads, prev, srow, lam[loc], glam[loc],
+                                                    {vol_id: 0.5 * h * w}, {})
+        for f in par["fluxes"]:                                     # boundary vertices: ds = point measure
+            vtx = int(np.argmin(np.abs(verts - f["x"])))
+            cell = min(vtx, nv - 2)
+            h = verts[cell + 1] - verts[cell]
+            grads = np.array([-1.0 / h, 1.0 / h]) @ uvals[cell:cell + 2]
+            for srow in range(ns):
+                res[vtx, srow] += point(uvals[vtx], grads, u_n[vtx], srow, 1.0, 0.0, {}, {f["surface"]: 1.0})
+        return res
+
+    form = {"parameters": par, "species": names, "u": u.tolist(), "u_n": u_n.tolist(), "delta": delta.tolist()}
+    for label, transient in (("transient", True), ("steady", False)):
+        form[f"F_{label}"] = reference_residual(u, transient).tolist()
+        form[f"Jdelta_{label}"] = (0.5 * (reference_residual(u + delta, transient)
+                                          - reference_residual(u - delta, transient))).tolist()
+    json.dump(form, open(os.path.join(out_dir, "residual_form.json"), "w"), indent=0)
+
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
     print("golden vectors written to", out_dir)
