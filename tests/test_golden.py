@@ -176,3 +176,63 @@ def test_oracle_residual_and_jacobian_match_the_reference_form(label):
     Fg, Jd = np.array(gold[f"F_{label}"]).ravel(), np.array(gold[f"Jdelta_{label}"]).ravel()
     assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
     assert np.abs(Jo @ d - Jd).max() <= 1e-12 * np.abs(Jd).max()
+
+
+def test_oracle_advection_term_matches_the_reference_form():
+    """reference hydrogen_transport_problem.py:967-978 on top of the form above: (grad(c) . vel) v dx
+    for H in volume 1 with a P1 velocity (1D, so the velocity is a one-component vector field)."""
+    from oracle.newton import OracleBackend
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, True)
+    vel = F.VectorFunction(m.mesh.mesh, np.array(gold["velocity"])[:, None])
+    m.advection_terms = [F.AdvectionTerm(velocity=vel, subdomain=m.volume_subdomains[0], species=m.species[0])]
+    m.solver_backend = OracleBackend()
+    m.initialise()
+    u, u_n, d = (np.array(gold[k]).ravel() for k in ("u", "u_n", "delta"))
+    m.u.x.array[:] = u
+    m.u_n.x.array[:] = u_n
+    Fo, Jo = m.solver.residual_and_jacobian(m.u.x.array)
+    Fg, Jd = np.array(gold["F_advection"]).ravel(), np.array(gold["Jdelta_advection"]).ravel()
+    assert not np.allclose(Fg, np.array(gold["F_transient"]).ravel())       # the term is there
+    assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
+    assert np.abs(Jo @ d - Jd).max() <= 1e-12 * np.abs(Jd).max()
+
+
+def _heat_form_problem(gold, transient):
+    par = gold["parameters"]
+    p = F.HeatTransferProblem()
+    p.mesh = F.Mesh1D(np.array(par["vertices"]))
+    vols = {}
+    for i, b in ((1, [0.0, 0.5]), (2, [0.5, 1.0])):
+        mp = par["materials"][str(i)]
+        lam = (lambda T, a=mp["lambda_a"], bb=mp["lambda_b"]: a + bb * T) if mp["lambda_b"] else mp["lambda_a"]
+        vols[i] = F.VolumeSubdomain1D(id=i, borders=b, material=F.Material(
+            D_0=1.0, E_D=0.0, thermal_conductivity=lam, density=mp["density"], heat_capacity=mp["heat_capacity"]))
+    surf = F.SurfaceSubdomain1D(id=par["flux"]["surface"], x=par["flux"]["x"])
+    p.subdomains = [*vols.values(), surf]
+    p.sources = [F.HeatSource(value=par["source"]["value"], volume=vols[par["source"]["volume"]])]
+    p.boundary_conditions = [F.HeatFluxBC(subdomain=surf, value=par["flux"]["value"])]
+    if transient:
+        p.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=True, final_time=1.0, stepsize=par["dt"])
+    else:
+        p.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
+    return p
+
+
+@pytest.mark.parametrize("label", ["transient", "steady"])
+def test_oracle_heat_residual_matches_the_reference_form(label):
+    """reference src/festim/heat_transfer_problem.py:175-218 run for real: conductivity a + b T in one
+    material and constant in the other, rho cp dT/dt, source, heat flux."""
+    from oracle.newton import OracleBackend
+
+    gold = load("heat_form.json")
+    p = _heat_form_problem(gold, label == "transient")
+    p.solver_backend = OracleBackend()
+    p.initialise()
+    p.u.x.array[:] = np.array(gold["T"])
+    p.u_n.x.array[:] = np.array(gold["T_n"])
+    Fo, Jo = p.solver.residual_and_jacobian(p.u.x.array)
+    Fg, Jd = np.array(gold[f"F_{label}"]), np.array(gold[f"Jdelta_{label}"])
+    assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
+    assert np.abs(Jo @ np.array(gold["delta"]) - Jd).max() <= 1e-12 * np.abs(Jd).max()

@@ -180,3 +180,21 @@ def test_cuda_residual_and_jacobian_match_the_reference_form(label):
     Fg, Jd = np.array(gold[f"F_{label}"]).ravel(), np.array(gold[f"Jdelta_{label}"]).ravel()
     assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
     assert np.abs(Jc @ d - Jd).max() <= 1e-10 * np.abs(Jd).max()
+
+
+@pytest.mark.parametrize("label", ["transient", "steady"])
+def test_cuda_heat_residual_matches_the_reference_form(label):
+    """tests/golden/heat_form.json: the REAL `HeatTransferProblem.create_formulation`
+    (heat_transfer_problem.py:175-218) integrated cell by cell; `fb_assemble` must reproduce the
+    residual and the exact directional difference J(T) d."""
+    from test_golden import _heat_form_problem, load
+
+    gold = load("heat_form.json")
+    p = _heat_form_problem(gold, label == "transient")
+    p.initialise()
+    p.u.x.array[:] = np.array(gold["T"])
+    p.u_n.x.array[:] = np.array(gold["T_n"])
+    Fc, Jc = p.solver.assemble_host(want_J=True)
+    Fg, Jd = np.array(gold[f"F_{label}"]), np.array(gold[f"Jdelta_{label}"])
+    assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
+    assert np.abs(Jc @ np.array(gold["delta"]) - Jd).max() <= 1e-10 * np.abs(Jd).max()

@@ -346,7 +346,9 @@ def main():
     u_n = u * rng.uniform(0.8, 1.1, (nv, ns))
     delta = rng.uniform(-0.3, 0.3, (nv, ns))
 
-    def reference_residual(uvals, transient):
+    vel_nodal = rng.uniform(-0.8, 0.8, nv)          # P1 velocity of the advection variant
+
+    def reference_residual(uvals, transient, advection=False):
         prob = F.HydrogenTransportProblem()
         species = [F.Species("H"), F.Species("D"), F.Species("t1", mobile=False), F.Species("t2", mobile=False)]
         by_name = dict(zip(names, species))
@@ -383,8 +385,13 @@ def main():
         prob.dx, prob.ds = PointMeasure("dx"), PointMeasure("ds")
         prob._dt = Constant(None, par["dt"])
         prob.advection_terms = []
+        vel_holder = types.SimpleNamespace(fenics_object=np.zeros(1))
+        if advection:   # hydrogen_transport_problem.py:967-978: (grad(c) . vel) v dx on H in volume 1
+            prob.advection_terms = [types.SimpleNamespace(species=[species[0]], velocity=vel_holder,
+                                                          subdomain=vols[1])]
 
-        def point(values, grads, prev, row_species, phi, gphi, dx, ds):
+        def point(values, grads, prev, row_species, phi, gphi, dx, ds, vel=0.0):
+            vel_holder.fenics_object = np.array([vel])
             for k, spe in enumerate(species):
                 spe.solution = WithGrad(values[k], [grads[k]])
                 spe.prev_solution = float(prev[k])
@@ -409,7 +416,7 @@ def main():
                 for loc in range(2):
                     for srow in range(ns):
                         res[c + loc, srow] += point(vals, grads, prev, srow, lam[loc], glam[loc],
-                                                    {vol_id: 0.5 * h * w}, {})
+                                                    {vol_id: 0.5 * h * w}, {}, vel=float(lam @ vel_nodal[c:c + 2]))
         for f in par["fluxes"]:                                     # boundary vertices: ds = point measure
             vtx = int(np.argmin(np.abs(verts - f["x"])))
             cell = min(vtx, nv - 2)
@@ -424,7 +431,72 @@ def main():
         form[f"F_{label}"] = reference_residual(u, transient).tolist()
         form[f"Jdelta_{label}"] = (0.5 * (reference_residual(u + delta, transient)
                                           - reference_residual(u - delta, transient))).tolist()
+    form["velocity"] = vel_nodal.tolist()
+    form["F_advection"] = reference_residual(u, True, advection=True).tolist()
+    form["Jdelta_advection"] = (0.5 * (reference_residual(u + delta, True, advection=True)
+                                       - reference_residual(u - delta, True, advection=True))).tolist()
     json.dump(form, open(os.path.join(out_dir, "residual_form.json"), "w"), indent=0)
+
+    # --- HeatTransferProblem.create_formulation (heat_transfer_problem.py:175-218), same method:
+    # conductivity a + b T in volume 1 (callable of T) and constant in volume 2, rho cp dT/dt,
+    # a volumetric source and a heat flux; quadratic in T, so the central difference is J d exactly.
+    hpar = {"vertices": verts.tolist(), "dt": 0.25,
+            "materials": {"1": {"lambda_a": 1.5, "lambda_b": 0.01, "density": 2.0, "heat_capacity": 3.0},
+                          "2": {"lambda_a": 4.0, "lambda_b": 0.0, "density": 1.2, "heat_capacity": 2.5}},
+            "source": {"volume": 1, "value": 0.9}, "flux": {"surface": 3, "x": 1.0, "value": 0.6}}
+    Tn = rng.uniform(300.0, 400.0, nv)
+    Told = Tn * rng.uniform(0.95, 1.02, nv)
+    dT = rng.uniform(-20.0, 20.0, nv)
+
+    def reference_heat_residual(Tvals, transient):
+        prob = F.HeatTransferProblem()
+        vols = {}
+        for i, b in ((1, [0.0, 0.5]), (2, [0.5, 1.0])):
+            mp = hpar["materials"][str(i)]
+            lam = (lambda T, a=mp["lambda_a"], bb=mp["lambda_b"]: a + bb * T) if mp["lambda_b"] else mp["lambda_a"]
+            vols[i] = F.VolumeSubdomain1D(id=i, borders=b, material=F.Material(
+                D_0=1.0, E_D=0.0, thermal_conductivity=lam, density=mp["density"], heat_capacity=mp["heat_capacity"]))
+        surf = F.SurfaceSubdomain1D(id=hpar["flux"]["surface"], x=hpar["flux"]["x"])
+        prob.subdomains = [*vols.values(), surf]
+        src = F.HeatSource(value=1.0, volume=vols[hpar["source"]["volume"]])
+        src.value.fenics_object = hpar["source"]["value"]
+        prob.sources = [src]
+        bc = F.HeatFluxBC(subdomain=surf, value=1.0)
+        bc._value_fenics = hpar["flux"]["value"]
+        prob.boundary_conditions = [bc]
+        prob.settings = F.Settings(atol=1, rtol=1, transient=transient, final_time=1 if transient else None)
+        prob.dx, prob.ds = PointMeasure("dx"), PointMeasure("ds")
+        prob._dt = Constant(None, hpar["dt"])
+
+        def point(value, grad, prev, phi, gphi, dx, ds):
+            prob.u = WithGrad(value, [grad])
+            prob.u_n = float(prev)
+            prob.test_function = WithGrad(phi, [gphi])
+            CTX["dx"], CTX["ds"] = dx, ds
+            prob.create_formulation()
+            return float(prob.formulation)
+
+        res = np.zeros(nv)
+        gx, gw = np.polynomial.legendre.leggauss(3)
+        for c in range(nv - 1):
+            h = verts[c + 1] - verts[c]
+            vol_id = 1 if verts[c + 1] <= 0.5 + 1e-12 else 2
+            for xi, w in zip(gx, gw):
+                lam = np.array([0.5 * (1 - xi), 0.5 * (1 + xi)])
+                glam = np.array([-1.0 / h, 1.0 / h])
+                for loc in range(2):
+                    res[c + loc] += point(lam @ Tvals[c:c + 2], glam @ Tvals[c:c + 2], lam @ Told[c:c + 2],
+                                          lam[loc], glam[loc], {vol_id: 0.5 * h * w}, {})
+        vtx = int(np.argmin(np.abs(verts - hpar["flux"]["x"])))
+        res[vtx] += point(Tvals[vtx], 0.0, Told[vtx], 1.0, 0.0, {}, {hpar["flux"]["surface"]: 1.0})
+        return res
+
+    heat = {"parameters": hpar, "T": Tn.tolist(), "T_n": Told.tolist(), "delta": dT.tolist()}
+    for label, transient in (("transient", True), ("steady", False)):
+        heat[f"F_{label}"] = reference_heat_residual(Tn, transient).tolist()
+        heat[f"Jdelta_{label}"] = (0.5 * (reference_heat_residual(Tn + dT, transient)
+                                          - reference_heat_residual(Tn - dT, transient))).tolist()
+    json.dump(heat, open(os.path.join(out_dir, "heat_form.json"), "w"), indent=0)
 
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
