@@ -236,3 +236,26 @@ def test_oracle_heat_residual_matches_the_reference_form(label):
     Fg, Jd = np.array(gold[f"F_{label}"]), np.array(gold[f"Jdelta_{label}"])
     assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
     assert np.abs(Jo @ np.array(gold["delta"]) - Jd).max() <= 1e-12 * np.abs(Jd).max()
+
+
+def test_oracle_repeated_reactant_matches_the_reference_form():
+    """SURVEY Appendix B, Q7 (hydrogen_transport_problem.py:913-920): H + H <-> t2 - the species
+    repeated in `reactant` receives the reaction term once per occurrence."""
+    from oracle.newton import OracleBackend
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, True)
+    r = gold["repeated_reactant_reaction"]
+    by_name = {s.name: s for s in m.species}
+    m.reactions.append(F.Reaction(reactant=[by_name[n] for n in r["reactants"]], product=by_name[r["product"]],
+                                  k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
+                                  volume=m.volume_subdomains[r["volume"] - 1]))
+    m.solver_backend = OracleBackend()
+    m.initialise()
+    u, u_n, d = (np.array(gold[k]).ravel() for k in ("u", "u_n", "delta"))
+    m.u.x.array[:] = u
+    m.u_n.x.array[:] = u_n
+    Fo, Jo = m.solver.residual_and_jacobian(m.u.x.array)
+    Fg, Jd = np.array(gold["F_repeated"]).ravel(), np.array(gold["Jdelta_repeated"]).ravel()
+    assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
+    assert np.abs(Jo @ d - Jd).max() <= 1e-12 * np.abs(Jd).max()

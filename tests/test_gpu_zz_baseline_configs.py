@@ -198,3 +198,26 @@ def test_cuda_heat_residual_matches_the_reference_form(label):
     Fg, Jd = np.array(gold[f"F_{label}"]), np.array(gold[f"Jdelta_{label}"])
     assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
     assert np.abs(Jc @ np.array(gold["delta"]) - Jd).max() <= 1e-10 * np.abs(Jd).max()
+
+
+def test_cuda_repeated_reactant_matches_the_reference_form():
+    """H + H <-> t2 (the repeated species receives the term once per
+    occurrence) through the structured reaction kernel, against the real reference form."""
+    import festim_b200 as F
+    from test_golden import _residual_form_problem, load
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, True)
+    r = gold["repeated_reactant_reaction"]
+    by_name = {s.name: s for s in m.species}
+    m.reactions.append(F.Reaction(reactant=[by_name[n] for n in r["reactants"]], product=by_name[r["product"]],
+                                  k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
+                                  volume=m.volume_subdomains[r["volume"] - 1]))
+    m.initialise()
+    u, u_n, d = (np.array(gold[k]).ravel() for k in ("u", "u_n", "delta"))
+    m.u.x.array[:] = u
+    m.u_n.x.array[:] = u_n
+    Fc, Jc = m.solver.assemble_host(want_J=True)
+    Fg, Jd = np.array(gold["F_repeated"]).ravel(), np.array(gold["Jdelta_repeated"]).ravel()
+    assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
+    assert np.abs(Jc @ d - Jd).max() <= 1e-10 * np.abs(Jd).max()

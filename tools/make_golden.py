@@ -348,7 +348,10 @@ def main():
 
     vel_nodal = rng.uniform(-0.8, 0.8, nv)          # P1 velocity of the advection variant
 
-    def reference_residual(uvals, transient, advection=False):
+    # Q7 of SURVEY Appendix B: a species repeated in `reactant` gets the term once per occurrence
+    repeated = {"volume": 2, "reactants": ["H", "H"], "product": "t2", "k_0": 0.6, "E_k": 0.05, "p_0": 0.07, "E_p": 0.02}
+
+    def reference_residual(uvals, transient, advection=False, with_repeated=False):
         prob = F.HydrogenTransportProblem()
         species = [F.Species("H"), F.Species("D"), F.Species("t1", mobile=False), F.Species("t2", mobile=False)]
         by_name = dict(zip(names, species))
@@ -362,6 +365,11 @@ def main():
             imp = F.ImplicitSpecies(n=r["n"], others=[by_name[r["trapped"]]])
             imp.value_fenics = r["n"]
             reactions.append(F.Reaction(reactant=[by_name[r["mobile"]], imp], product=by_name[r["trapped"]],
+                                        k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
+                                        volume=vols[r["volume"]]))
+        if with_repeated:
+            r = repeated
+            reactions.append(F.Reaction(reactant=[by_name[n] for n in r["reactants"]], product=by_name[r["product"]],
                                         k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
                                         volume=vols[r["volume"]]))
         prob.reactions = reactions
@@ -435,6 +443,10 @@ def main():
     form["F_advection"] = reference_residual(u, True, advection=True).tolist()
     form["Jdelta_advection"] = (0.5 * (reference_residual(u + delta, True, advection=True)
                                        - reference_residual(u - delta, True, advection=True))).tolist()
+    form["repeated_reactant_reaction"] = repeated
+    form["F_repeated"] = reference_residual(u, True, with_repeated=True).tolist()
+    form["Jdelta_repeated"] = (0.5 * (reference_residual(u + delta, True, with_repeated=True)
+                                      - reference_residual(u - delta, True, with_repeated=True))).tolist()
     json.dump(form, open(os.path.join(out_dir, "residual_form.json"), "w"), indent=0)
 
     # --- HeatTransferProblem.create_formulation (heat_transfer_problem.py:175-218), same method:
