@@ -76,12 +76,15 @@ class TestIntegral:
         cell gradient of an unknown."""
         return [(key, ufl.diff(self.expr, ("species_grad", key))) for key in ufl.species_grads_in(self.expr)]
 
+    # meta["extra_degree"]: the term was rewritten from an expression UFL estimates higher
+    # (spherical diffusion, see create_formulation); the integration degree follows the original
     def degree_F(self):
-        return ufl.estimate_degree(self.expr) + 1
+        return ufl.estimate_degree(self.expr) + 1 + int(self.meta.get("extra_degree", 0))
 
     def degree_J(self):
-        degs = [ufl.estimate_degree(d) + 2 for _, d in self.derivatives()]
-        degs += [ufl.estimate_degree(d) + 1 for _, d in self.grad_derivatives()]  # trial gradient: degree 0
+        extra = int(self.meta.get("extra_degree", 0))
+        degs = [ufl.estimate_degree(d) + 2 + extra for _, d in self.derivatives()]
+        degs += [ufl.estimate_degree(d) + 1 + extra for _, d in self.grad_derivatives()]  # trial gradient: degree 0
         return max(degs) if degs else None
 
 

@@ -269,8 +269,12 @@ class HydrogenTransportProblem(ProblemBase):
                     if csys != CoordinateSystem.CARTESIAN:
                         m = {CoordinateSystem.CYLINDRICAL: 1.0, CoordinateSystem.SPHERICAL: 2.0}[csys]
                         r = ufl.SpatialCoordinate(self.mesh.mesh)[0]
+                        # UFL's degree estimate of the reference's expression (a
+                        # quotient counts as the sum of degrees, grad lowers by one): r^m . (D u')
+                        # . grad(v / r^m) -> m + 0 + (1 + m - 1) = 2 m, i.e. 2 (cylindrical) and 4
+                        # (spherical); the metric term as written here estimates 2 for both
                         F += forms.TestIntegral(spe, -(m * ufl.as_expr(D) / r) * ufl.SpeciesGrad(spe, 0),
-                                                self.dx(vol.id), {"metric": m})
+                                                self.dx(vol.id), {"metric": m, "extra_degree": 2 * int(m) - 2})
                 if self.settings.transient:
                     F += forms.TestIntegral(spe, (u - u_n) / self.dt, self.dx(vol.id),
                                             {"mass": 1.0})

@@ -510,6 +510,100 @@ def main():
                                           - reference_heat_residual(Tn - dT, transient))).tolist()
     json.dump(heat, open(os.path.join(out_dir, "heat_form.json"), "w"), indent=0)
 
+    # --- cylindrical / spherical diffusion term (hydrogen_transport_problem.py:886-908) -------
+    # r^m D grad(u) . grad(v / r^m): v / r^m needs the quotient rule, so the stand-ins here are
+    # forward-mode dual numbers.  The integrand is rational in r, hence quadrature dependent: the
+    # residual is tabulated for 1..8 Gauss-Legendre points per cell (on an interval a rule is
+    # fixed by its number of points) and the test looks up the size the estimated degree asks for.
+    class Dual:
+        def __init__(self, value, grad):
+            self.value, self.grad = float(value), np.asarray(grad, dtype=float)
+
+        @staticmethod
+        def lift(o):
+            return o if isinstance(o, Dual) else Dual(o, [0.0])
+
+        def __add__(self, o):
+            o = Dual.lift(o)
+            return Dual(self.value + o.value, self.grad + o.grad)
+
+        __radd__ = __add__
+
+        def __neg__(self):
+            return Dual(-self.value, -self.grad)
+
+        def __sub__(self, o):
+            return self + (-Dual.lift(o))
+
+        def __rsub__(self, o):
+            return Dual.lift(o) + (-self)
+
+        def __mul__(self, o):
+            o = Dual.lift(o)
+            return Dual(self.value * o.value, self.grad * o.value + self.value * o.grad)
+
+        __rmul__ = __mul__
+
+        def __truediv__(self, o):
+            o = Dual.lift(o)
+            return Dual(self.value / o.value, (self.grad * o.value - self.value * o.grad) / o.value**2)
+
+        def __rtruediv__(self, o):
+            return Dual.lift(o) / self
+
+        def __pow__(self, n):
+            return Dual(self.value**n, n * self.value ** (n - 1) * self.grad)
+
+        def __float__(self):
+            return self.value
+
+    _ufl_stub.grad = lambda a: a.grad
+    _ufl_stub.SpatialCoordinate = lambda mesh: [Dual(CTX["x"], [1.0])]
+    rverts = 1.0 + verts
+    cpar = {"vertices": rverts.tolist(), "T": 450.0, "D_0": 1.7, "E_D": 0.15, "source": 0.7}
+    cu = rng.uniform(0.5, 1.5, nv)
+
+    def reference_curvilinear(system, npts):
+        prob = F.HydrogenTransportProblem()
+        H = F.Species("H")
+        prob.species = [H]
+        vol = F.VolumeSubdomain1D(id=1, borders=[rverts[0], rverts[-1]], material=F.Material(D_0=cpar["D_0"], E_D=cpar["E_D"]))
+        prob.subdomains = [vol]
+        src = F.ParticleSource(value=1.0, volume=vol, species=H)
+        src.value.fenics_object = cpar["source"]
+        prob.sources = [src]
+        prob.settings = F.Settings(atol=1, rtol=1, transient=False)
+        prob.mesh = F.Mesh.__new__(F.Mesh)
+        prob.mesh._mesh = None
+        prob.mesh.coordinate_system = system
+        prob.temperature_fenics = Constant(None, cpar["T"])
+        prob.dx, prob.ds = PointMeasure("dx"), PointMeasure("ds")
+        prob.advection_terms = []
+        prob.reactions = []
+        prob.boundary_conditions = []
+        res = np.zeros(nv)
+        gx, gw = np.polynomial.legendre.leggauss(npts)
+        for c in range(nv - 1):
+            a, b = rverts[c], rverts[c + 1]
+            h = b - a
+            for xi, w in zip(gx, gw):
+                lam = np.array([0.5 * (1 - xi), 0.5 * (1 + xi)])
+                glam = np.array([-1.0 / h, 1.0 / h])
+                CTX["x"] = float(lam @ rverts[c:c + 2])
+                CTX["dx"], CTX["ds"] = {1: 0.5 * h * w}, {}
+                for loc in range(2):
+                    H.solution = Dual(lam @ cu[c:c + 2], [glam @ cu[c:c + 2]])
+                    H.prev_solution = 0.0
+                    H.test_function = Dual(lam[loc], [glam[loc]])
+                    prob.create_formulation()
+                    res[c + loc] += float(prob.formulation)
+        return res
+
+    curv = {"parameters": cpar, "u": cu.tolist()}
+    for system in ("cylindrical", "spherical"):
+        curv[system] = {str(k): reference_curvilinear(system, k).tolist() for k in range(1, 9)}
+    json.dump(curv, open(os.path.join(out_dir, "curvilinear_form.json"), "w"), indent=0)
+
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
     print("golden vectors written to", out_dir)
