@@ -1,0 +1,73 @@
+"""The CUDA path (`fb_assemble` through the C ABI) against golden vectors computed by the REAL
+reference code (tools/make_golden.py runs `create_formulation` of the reference with its numerical
+dependencies stubbed and integrates the form cell by cell): tests/golden/residual_form.json,
+heat_form.json.  The oracle reproduces the same vectors to 1e-13 (tests/test_golden.py).
+
+Written after the round's GPU budget was spent, so this file has not run on a B200 yet; it is named
+to be collected last so that `-x` cannot hide the suites that have."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("label", ["transient", "steady"])
+def test_cuda_residual_and_jacobian_match_the_reference_form(label):
+    """tests/golden/residual_form.json holds the residual of the REAL reference
+    `create_formulation` (hydrogen_transport_problem.py:870-997, run by tools/make_golden.py)
+    integrated cell by cell on a small two-material 1D mesh, and the exact directional difference
+    J(u) d.  `fb_assemble` through the C ABI must reproduce both (the oracle does to 1e-13,
+    tests/test_golden.py)."""
+    from test_golden import _residual_form_problem, load
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, label == "transient")
+    m.initialise()
+    u, u_n, d = (np.array(gold[k]).ravel() for k in ("u", "u_n", "delta"))
+    m.u.x.array[:] = u
+    m.u_n.x.array[:] = u_n
+    Fc, Jc = m.solver.assemble_host(want_J=True)
+    Fg, Jd = np.array(gold[f"F_{label}"]).ravel(), np.array(gold[f"Jdelta_{label}"]).ravel()
+    assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
+    assert np.abs(Jc @ d - Jd).max() <= 1e-10 * np.abs(Jd).max()
+
+
+@pytest.mark.parametrize("label", ["transient", "steady"])
+def test_cuda_heat_residual_matches_the_reference_form(label):
+    """tests/golden/heat_form.json: the REAL `HeatTransferProblem.create_formulation`
+    (heat_transfer_problem.py:175-218) integrated cell by cell; `fb_assemble` must reproduce the
+    residual and the exact directional difference J(T) d."""
+    from test_golden import _heat_form_problem, load
+
+    gold = load("heat_form.json")
+    p = _heat_form_problem(gold, label == "transient")
+    p.initialise()
+    p.u.x.array[:] = np.array(gold["T"])
+    p.u_n.x.array[:] = np.array(gold["T_n"])
+    Fc, Jc = p.solver.assemble_host(want_J=True)
+    Fg, Jd = np.array(gold[f"F_{label}"]), np.array(gold[f"Jdelta_{label}"])
+    assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
+    assert np.abs(Jc @ np.array(gold["delta"]) - Jd).max() <= 1e-10 * np.abs(Jd).max()
+
+
+def test_cuda_repeated_reactant_matches_the_reference_form():
+    """H + H <-> t2 (the repeated species receives the term once per
+    occurrence) through the structured reaction kernel, against the real reference form."""
+    import festim_b200 as F
+    from test_golden import _residual_form_problem, load
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, True)
+    r = gold["repeated_reactant_reaction"]
+    by_name = {s.name: s for s in m.species}
+    m.reactions.append(F.Reaction(reactant=[by_name[n] for n in r["reactants"]], product=by_name[r["product"]],
+                                  k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
+                                  volume=m.volume_subdomains[r["volume"] - 1]))
+    m.initialise()
+    u, u_n, d = (np.array(gold[k]).ravel() for k in ("u", "u_n", "delta"))
+    m.u.x.array[:] = u
+    m.u_n.x.array[:] = u_n
+    Fc, Jc = m.solver.assemble_host(want_J=True)
+    Fg, Jd = np.array(gold["F_repeated"]).ravel(), np.array(gold["Jdelta_repeated"]).ravel()
+    assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
+    assert np.abs(Jc @ d - Jd).max() <= 1e-10 * np.abs(Jd).max()
