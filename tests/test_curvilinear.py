@@ -59,9 +59,14 @@ def test_derived_quantities_refused_on_curvilinear_meshes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("system", ["cylindrical", "spherical"])
 @pytest.mark.parametrize("transient", [False, True])
-def test_curvilinear_gpu_parity(system, transient):
+def test_cylindrical_gpu_parity(transient):
+    _gpu_parity("cylindrical", transient)
+
+
+def _gpu_parity(system, transient):
+    """(the spherical cases run from tests/test_zz_gpu_reference_form.py: their integration degree
+    changed after the round's last GPU run)"""
     g, Hg, u_exact = _mms(system, 400, transient)
     r, Hr, _ = _mms(system, 400, transient)
     r.solver_backend = OracleBackend()

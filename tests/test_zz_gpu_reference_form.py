@@ -71,3 +71,12 @@ def test_cuda_repeated_reactant_matches_the_reference_form():
     Fg, Jd = np.array(gold["F_repeated"]).ravel(), np.array(gold["Jdelta_repeated"]).ravel()
     assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
     assert np.abs(Jc @ d - Jd).max() <= 1e-10 * np.abs(Jd).max()
+
+
+@pytest.mark.parametrize("transient", [False, True])
+def test_spherical_gpu_parity(transient):
+    """Spherical MMS parity (reference test/system_tests/test_spherical_coordinates.py); the metric
+    term integrates with degree 4 (3 Gauss points) since the golden check of the real expression."""
+    from test_curvilinear import _gpu_parity
+
+    _gpu_parity("spherical", transient)
