@@ -293,3 +293,77 @@ def test_oracle_curvilinear_diffusion_matches_the_reference_form(system):
     # (a quotient counts as the sum of degrees), times r^m: degree 2 + m -> 2-point / 3-point rules
     assert best == {"cylindrical": 2, "spherical": 3}[system], errs
     assert errs[8] < 1e-3
+
+
+class _ScriptedBackend:
+    """A solver backend at the create_solver seam that converges after a scripted number of Newton
+    iterations and leaves the solution untouched."""
+
+    def __init__(self, iterations):
+        self.script = iter(iterations)
+
+    def create_newton_solver(self, problem, petsc_options):
+        import types
+
+        snes = types.SimpleNamespace(getConvergedReason=lambda: 2, getIterationNumber=lambda: next(self.script),
+                                     getLinearSolveIterations=lambda: 0)
+        return types.SimpleNamespace(solve=lambda: 0, solver=snes, rtol=None, atol=None)
+
+
+def test_time_loop_matches_the_reference():
+    """reference src/festim/problem.py:195-255, run for real with a scripted solver
+    (tools/make_golden.py): recorded timesteps, the step size in force during every step, the final
+    time (not clamped) and the final step size agree bit for bit."""
+    for case in load("time_loop.json")[:-1]:
+        cfg = case["config"]
+        kw = dict(cfg["stepsize"])
+        if "max_stepsize_ramp" in cfg:
+            t0, lo, hi = cfg["max_stepsize_ramp"]
+            kw["max_stepsize"] = lambda t, t0=t0, lo=lo, hi=hi: lo if t < t0 else hi
+        m = F.HydrogenTransportProblem()
+        m.mesh = F.Mesh1D(np.linspace(0, 1, 4))
+        m.species = [F.Species("H")]
+        m.subdomains = [F.VolumeSubdomain1D(id=1, borders=[0, 1], material=F.Material(D_0=1, E_D=0))]
+        m.temperature = 400
+        m.settings = F.Settings(atol=1, rtol=1, final_time=cfg["final_time"])
+        m.settings.stepsize = F.Stepsize(**kw)
+        m.solver_backend = _ScriptedBackend(case["iterations"])
+        m.initialise()
+        dts = []
+        post = m.post_processing
+        m.post_processing = lambda: (dts.append(float(m.dt)), post())[1]
+        m.run()
+        assert m.timesteps == case["timesteps"], cfg
+        assert dts == case["dt_during_step"], cfg
+        assert float(m.t) == case["final_t"] and float(m.dt) == case["final_dt"], cfg
+
+
+def test_coupled_time_loop_matches_the_reference():
+    """reference src/festim/coupled_heat_hydrogen_problem.py:133-163, run for real with two
+    scripted solvers: heat step, hydrogen step, then both problems take the smaller new step size."""
+    case = load("time_loop.json")[-1]
+    cfg = case["coupled"]
+    mesh = F.Mesh1D(np.linspace(0, 1, 4))
+    mat = F.Material(D_0=1, E_D=0, thermal_conductivity=1.0, density=1.0, heat_capacity=1.0)
+    vol = F.VolumeSubdomain1D(id=1, borders=[0, 1], material=mat)
+    heat = F.HeatTransferProblem(mesh=mesh, subdomains=[vol],
+                                 initial_condition=F.InitialTemperature(value=400.0, volume=vol),
+                                 settings=F.Settings(atol=1, rtol=1, transient=True,
+                                                     final_time=cfg["heat"]["final_time"]))
+    heat.settings.stepsize = F.Stepsize(**cfg["heat"]["stepsize"])
+    hyd = F.HydrogenTransportProblem(mesh=mesh, subdomains=[vol], species=[F.Species("H")],
+                                     settings=F.Settings(atol=1, rtol=1, transient=True,
+                                                         final_time=cfg["hydrogen"]["final_time"]))
+    hyd.settings.stepsize = F.Stepsize(**cfg["hydrogen"]["stepsize"])
+    heat.solver_backend = _ScriptedBackend(case["iterations_heat"])
+    hyd.solver_backend = _ScriptedBackend(case["iterations_hydrogen"])
+    coupled = F.CoupledTransientHeatTransferHydrogenTransport(heat_problem=heat, hydrogen_problem=hyd)
+    coupled.initialise()
+    dts = {"heat": [], "hyd": []}
+    for key, p in (("heat", heat), ("hyd", hyd)):
+        post = p.post_processing
+        p.post_processing = (lambda p=p, key=key, post=post: (dts[key].append(float(p.dt)), post())[1])
+    coupled.run()
+    assert hyd.timesteps == case["timesteps"] and heat.timesteps == case["timesteps_heat"]
+    assert dts["hyd"] == case["dt_during_step"] and dts["heat"] == case["dt_during_step_heat"]
+    assert float(hyd.t) == case["final_t"] and float(hyd.dt) == case["final_dt"]

@@ -604,6 +604,113 @@ def main():
         curv[system] = {str(k): reference_curvilinear(system, k).tolist() for k in range(1, 9)}
     json.dump(curv, open(os.path.join(out_dir, "curvilinear_form.json"), "w"), indent=0)
 
+    # --- the time loop: ProblemBase.run / iterate (problem.py:195-255) ----------------------
+    # The REAL loop with a scripted solver (Newton iteration counts from a list): recorded
+    # `timesteps`, the step size after every step and the final time pin the bookkeeping order
+    # (t advanced before the solve, modify_value called with the new t, no clamping of the last
+    # step - SURVEY quirk Q1 - milestones, max_stepsize as number or callable of t).
+    class Box:
+        def __init__(self, value):
+            self.value = float(value)
+
+        def __float__(self):
+            return float(self.value)
+
+    class ScriptedProblem(F.problem.ProblemBase):
+        def update_time_dependent_values(self):
+            pass
+
+        def post_processing(self):
+            self.dts.append(float(self._dt.value))
+
+    loops = []
+    loop_configs = [
+        dict(final_time=10.0, stepsize=dict(initial_value=0.5)),
+        dict(final_time=1.0, stepsize=dict(initial_value=0.3)),
+        dict(final_time=20.0, its_high=7, stepsize=dict(initial_value=0.1, growth_factor=1.2, cutback_factor=0.8,
+                                                        target_nb_iterations=4)),
+        dict(final_time=50.0, its_high=5, stepsize=dict(initial_value=0.5, growth_factor=1.5, cutback_factor=0.5,
+                                                        target_nb_iterations=3,
+                                                        milestones=[1.0, 2.5, 7.0, 20.0, 50.0])),
+        dict(final_time=30.0, stepsize=dict(initial_value=0.2, growth_factor=1.2, cutback_factor=0.9,
+                                            target_nb_iterations=5, max_stepsize=3.0,
+                                            milestones=[0.5, 4.0, 9.0])),
+        dict(final_time=40.0, its_high=6, stepsize=dict(initial_value=0.2, growth_factor=1.3, cutback_factor=0.7,
+                                                        target_nb_iterations=4, milestones=[10.0, 25.0]),
+             max_stepsize_ramp=[10.0, 0.5, 5.0]),      # max_stepsize(t) = 0.5 if t < 10 else 5.0
+    ]
+    for cfg in loop_configs:
+        its = [int(v) for v in rng.integers(1, cfg.get("its_high", 9), 20000)]
+        kw = dict(cfg["stepsize"])
+        if "max_stepsize_ramp" in cfg:
+            t0, lo, hi = cfg["max_stepsize_ramp"]
+            kw["max_stepsize"] = lambda t, t0=t0, lo=lo, hi=hi: lo if t < t0 else hi
+        prob = ScriptedProblem()
+        prob.settings = F.Settings(atol=1, rtol=1, final_time=cfg["final_time"])
+        prob.settings.stepsize = F.Stepsize(**kw)
+        prob.show_progress_bar = False
+        prob.t = Box(0.0)
+        prob._dt = Box(prob.settings.stepsize.initial_value)
+        prob.dts = []
+        script = iter(its)
+        snes = types.SimpleNamespace(getConvergedReason=lambda: 2, getIterationNumber=lambda: next(script))
+        prob.solver = types.SimpleNamespace(solve=lambda: None, solver=snes)
+        prob.u = types.SimpleNamespace(x=types.SimpleNamespace(array=np.zeros(3)))
+        prob.u_n = types.SimpleNamespace(x=types.SimpleNamespace(array=np.zeros(3)))
+        prob.run()
+        n = len(prob.timesteps)
+        loops.append({"config": cfg, "iterations": its[:n], "timesteps": list(prob.timesteps),
+                      "dt_during_step": prob.dts, "final_t": float(prob.t), "final_dt": float(prob._dt.value)})
+    # the staggered loop of CoupledTransientHeatTransferHydrogenTransport (coupled_heat_hydrogen_
+    # problem.py:133-163): both problems step, then both take the smaller of the two new step sizes
+    def scripted(cls, cfg, its):
+        class Scripted(cls):
+            def update_time_dependent_values(self):
+                pass
+
+            def post_processing(self):
+                self.dts.append(float(self._dt.value))
+
+        prob = Scripted()
+        prob.settings = F.Settings(atol=1, rtol=1, final_time=cfg["final_time"], transient=True)
+        prob.settings.stepsize = F.Stepsize(**cfg["stepsize"])
+        prob.show_progress_bar = False
+        prob.t = Box(0.0)
+        prob._dt = Box(prob.settings.stepsize.initial_value)
+        prob.dts = []
+        script = iter(its)
+        snes = types.SimpleNamespace(getConvergedReason=lambda: 2, getIterationNumber=lambda: next(script))
+        prob.solver = types.SimpleNamespace(solve=lambda: None, solver=snes)
+        prob.u = types.SimpleNamespace(x=types.SimpleNamespace(array=np.zeros(3)))
+        prob.u_n = types.SimpleNamespace(x=types.SimpleNamespace(array=np.zeros(3)))
+        prob.mesh = F.Mesh.__new__(F.Mesh)
+        prob.mesh._mesh = None
+        return prob
+
+    ccfg = {"heat": dict(final_time=15.0, stepsize=dict(initial_value=0.3, growth_factor=1.25, cutback_factor=0.9,
+                                                        target_nb_iterations=4, milestones=[5.0])),
+            "hydrogen": dict(final_time=15.0, stepsize=dict(initial_value=0.2, growth_factor=1.15, cutback_factor=0.85,
+                                                            target_nb_iterations=3, max_stepsize=1.5))}
+    its_heat = [int(v) for v in rng.integers(1, 6, 5000)]
+    its_hyd = [int(v) for v in rng.integers(1, 4, 5000)]
+    heat_p = scripted(F.HeatTransferProblem, ccfg["heat"], its_heat)
+    hyd_p = scripted(F.HydrogenTransportProblem, ccfg["hydrogen"], its_hyd)
+    coupled = F.CoupledTransientHeatTransferHydrogenTransport.__new__(F.CoupledTransientHeatTransferHydrogenTransport)
+    coupled._heat_problem, coupled._hydrogen_problem = heat_p, hyd_p
+    hyd_p.show_progress_bar = False
+    # what initialise() does before the loop (:103-108): both start from the smaller initial step
+    dt0 = min(heat_p.settings.stepsize.initial_value, hyd_p.settings.stepsize.initial_value)
+    for pr in (heat_p, hyd_p):
+        pr.settings.stepsize.initial_value = dt0
+        pr._dt.value = dt0
+    coupled.run()
+    nsteps = len(hyd_p.timesteps)
+    loops.append({"coupled": ccfg, "iterations_heat": its_heat[:nsteps], "iterations_hydrogen": its_hyd[:nsteps],
+                  "timesteps": list(hyd_p.timesteps), "timesteps_heat": list(heat_p.timesteps),
+                  "dt_during_step": hyd_p.dts, "dt_during_step_heat": heat_p.dts,
+                  "final_t": float(hyd_p.t), "final_dt": float(hyd_p._dt.value)})
+    json.dump(loops, open(os.path.join(out_dir, "time_loop.json"), "w"), indent=0)
+
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
     print("golden vectors written to", out_dir)
