@@ -76,7 +76,13 @@ class XDMFFile:
         self._collections = {}
         self._nbytes = 0
         self._closed = False
+        self._writes = self._next_flush = self.n_flushes = 0
         if self.mode == "w":
+            import atexit
+            import weakref
+
+            ref = weakref.ref(self)
+            atexit.register(lambda: ref() is not None and ref().close())
             ET.register_namespace("xi", _XI)
             self._root = ET.Element("Xdmf", {"Version": "3.0"})
             self._domain = ET.SubElement(self._root, "Domain")
@@ -216,9 +222,16 @@ class XDMFFile:
         ET.SubElement(grid, "Time", {"Value": repr(float(t))})
         att = ET.SubElement(grid, "Attribute", {"Name": name, "AttributeType": "Scalar", "Center": "Node"})
         self._data_item(att, values)
-        self._flush()
+        # the index is rewritten as a whole: do it after each of the first writes, then whenever the
+        # number of writes has grown by a tenth, and at close / interpreter exit - a long transient
+        # costs O(n log n) instead of O(n^2), the side-car data is on disk at once either way
+        self._writes += 1
+        if self._writes <= 16 or self._writes >= self._next_flush:
+            self._flush()
+            self._next_flush = self._writes + max(1, self._writes // 10)
 
     def _flush(self):
+        self.n_flushes += 1
         ET.indent(self._root)
         self.filename.parent.mkdir(parents=True, exist_ok=True)
         with open(self.filename, "wb") as f:
@@ -236,6 +249,12 @@ class XDMFFile:
 
     def __exit__(self, *exc):
         self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # ---- reading ------------------------------------------------------------------------
     def _grid(self, name):

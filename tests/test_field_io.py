@@ -333,3 +333,21 @@ def test_read_function_onto_another_mesh(tmp_path):
     p.solver_backend = OracleBackend()
     p.initialise()
     np.testing.assert_allclose(u_ref.x.array, p.u_n.x.array, atol=1e-14)
+
+
+def test_xdmf_index_of_a_long_series_is_complete_and_cheap(tmp_path):
+    """The XML index is rewritten as a whole, so it is flushed geometrically (plus at close): 400
+    time levels cost a few dozen rewrites, and the closed file lists every one of them."""
+    mesh = F.create_unit_square(3, 3)
+    w = field_io.XDMFFile(tmp_path / "long.xdmf", "w")
+    w.write_mesh(mesh)
+    for k in range(400):
+        w.write_function(("c", np.full(mesh.num_vertices, float(k))), 0.1 * k)
+    before_close = field_io.XDMFFile(tmp_path / "long.xdmf", "r").function_times("c")
+    assert len(before_close) >= 360            # never more than a tenth behind
+    w.close()
+    assert w.n_flushes < 70
+    rd = field_io.XDMFFile(tmp_path / "long.xdmf", "r")
+    assert np.allclose(rd.function_times("c"), 0.1 * np.arange(400))
+    assert np.array_equal(rd.read_function("c", 0.1 * 399), np.full(mesh.num_vertices, 399.0))
+    assert np.array_equal(rd.read_function("c", 0.1 * 17), np.full(mesh.num_vertices, 17.0))
