@@ -466,15 +466,25 @@ class VTUSeriesWriter:
         for old in self.path.glob("step_*.vtu"):
             os.remove(old)
         self.times = []
+        self._next_index = 0
         self._write_index()
+        import atexit
+        import weakref
+
+        ref = weakref.ref(self)
+        atexit.register(lambda: ref() is not None and ref().close())
 
     def write(self, t, point_data):
         name = f"step_{len(self.times):06d}.vtu"
         write_vtu(self.path / name, self.mesh, point_data, t=t)
         self.times.append((float(t), name))
-        self._write_index()
+        n = len(self.times)
+        if n <= 16 or n >= self._next_index:     # same schedule as the XDMF index
+            self._write_index()
+            self._next_index = n + max(1, n // 10)
 
     def _write_index(self):
+        self._indexed = len(self.times)
         root = ET.Element("VTKFile", {"type": "Collection", "version": "0.1", "byte_order": "LittleEndian"})
         coll = ET.SubElement(root, "Collection")
         for t, name in self.times:
@@ -486,4 +496,11 @@ class VTUSeriesWriter:
             f.write(b"\n")
 
     def close(self):
-        pass
+        if getattr(self, "_indexed", 0) != len(self.times):
+            self._write_index()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

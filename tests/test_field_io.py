@@ -351,3 +351,16 @@ def test_xdmf_index_of_a_long_series_is_complete_and_cheap(tmp_path):
     assert np.allclose(rd.function_times("c"), 0.1 * np.arange(400))
     assert np.array_equal(rd.read_function("c", 0.1 * 399), np.full(mesh.num_vertices, 399.0))
     assert np.array_equal(rd.read_function("c", 0.1 * 17), np.full(mesh.num_vertices, 17.0))
+
+
+def test_vtu_series_index_is_complete_after_close(tmp_path):
+    import xml.etree.ElementTree as ET
+
+    mesh = F.create_unit_square(2, 2)
+    w = field_io.VTUSeriesWriter(tmp_path / "series.bp", mesh)
+    for k in range(120):
+        w.write(0.5 * k, {"c": np.full(mesh.num_vertices, float(k))})
+    w.close()
+    sets = ET.parse(tmp_path / "series.bp" / "series.pvd").getroot().findall("Collection/DataSet")
+    assert len(sets) == 120 and float(sets[-1].get("timestep")) == 0.5 * 119
+    assert sets[-1].get("file") == "step_000119.vtu" and (tmp_path / "series.bp" / "step_000119.vtu").exists()
