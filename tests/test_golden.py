@@ -130,7 +130,7 @@ def test_solubility_laws_match_reference():
         assert float(ufl.evaluate(henrys_law(*args), {})) == pytest.approx(case["henry"], rel=1e-14)
 
 
-def _residual_form_problem(gold, transient):
+def _residual_form_problem(gold, transient, first_reaction_only=False):
     """The problem of tests/golden/residual_form.json in the API mirror."""
     par = gold["parameters"]
     m = F.HydrogenTransportProblem()
@@ -145,7 +145,7 @@ def _residual_form_problem(gold, transient):
     m.reactions = [
         F.Reaction(reactant=[species[r["mobile"]], F.ImplicitSpecies(n=r["n"], others=[species[r["trapped"]]])],
                    product=species[r["trapped"]], k_0=r["k_0"], E_k=r["E_k"], p_0=r["p_0"], E_p=r["E_p"],
-                   volume=vols[r["volume"]]) for r in par["reactions"]]
+                   volume=vols[r["volume"]]) for r in par["reactions"][: 1 if first_reaction_only else None]]
     m.sources = [F.ParticleSource(value=s["value"], volume=vols[s["volume"]], species=species[s["species"]])
                  for s in par["sources"]]
     m.boundary_conditions = [F.ParticleFluxBC(subdomain=surfs[f["surface"]], value=f["value"], species=species[f["species"]])
@@ -367,3 +367,23 @@ def test_coupled_time_loop_matches_the_reference():
     assert hyd.timesteps == case["timesteps"] and heat.timesteps == case["timesteps_heat"]
     assert dts["hyd"] == case["dt_during_step"] and dts["heat"] == case["dt_during_step_heat"]
     assert float(hyd.t) == case["final_t"] and float(hyd.dt) == case["final_dt"]
+
+
+def test_oracle_steady_filler_matches_the_reference_form():
+    """reference hydrogen_transport_problem.py:980-997: in a steady run an immobile species gets
+    `c v dx(vol)` in every volume that holds no reaction at all (the check is per volume, not per
+    species - with a reaction in each volume there is no filler, which F_steady above covers)."""
+    from oracle.newton import OracleBackend
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, False, first_reaction_only=True)
+    m.solver_backend = OracleBackend()
+    m.initialise()
+    assert sum("filler" in itg.meta for itg in m.formulation.integrals) == 2      # t1 and t2 in volume 2
+    u, d = (np.array(gold[k]).ravel() for k in ("u", "delta"))
+    m.u.x.array[:] = u
+    Fo, Jo = m.solver.residual_and_jacobian(m.u.x.array)
+    Fg, Jd = np.array(gold["F_steady_filler"]).ravel(), np.array(gold["Jdelta_steady_filler"]).ravel()
+    assert not np.allclose(Fg, np.array(gold["F_steady"]).ravel())
+    assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
+    assert np.abs(Jo @ d - Jd).max() <= 1e-12 * np.abs(Jd).max()

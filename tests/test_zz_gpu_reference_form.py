@@ -80,3 +80,19 @@ def test_spherical_gpu_parity(transient):
     from test_curvilinear import _gpu_parity
 
     _gpu_parity("spherical", transient)
+
+
+def test_cuda_steady_filler_matches_the_reference_form():
+    """Steady state with no reaction in volume 2: the `c v dx` filler of the immobile species
+    (hydrogen_transport_problem.py:980-997) through `fb_assemble`, against the real reference form."""
+    from test_golden import _residual_form_problem, load
+
+    gold = load("residual_form.json")
+    m = _residual_form_problem(gold, False, first_reaction_only=True)
+    m.initialise()
+    u, d = (np.array(gold[k]).ravel() for k in ("u", "delta"))
+    m.u.x.array[:] = u
+    Fc, Jc = m.solver.assemble_host(want_J=True)
+    Fg, Jd = np.array(gold["F_steady_filler"]).ravel(), np.array(gold["Jdelta_steady_filler"]).ravel()
+    assert np.abs(Fc - Fg).max() <= 1e-10 * np.abs(Fg).max()
+    assert np.abs(Jc @ d - Jd).max() <= 1e-10 * np.abs(Jd).max()

@@ -351,7 +351,7 @@ def main():
     # Q7 of SURVEY Appendix B: a species repeated in `reactant` gets the term once per occurrence
     repeated = {"volume": 2, "reactants": ["H", "H"], "product": "t2", "k_0": 0.6, "E_k": 0.05, "p_0": 0.07, "E_p": 0.02}
 
-    def reference_residual(uvals, transient, advection=False, with_repeated=False):
+    def reference_residual(uvals, transient, advection=False, with_repeated=False, first_reaction_only=False):
         prob = F.HydrogenTransportProblem()
         species = [F.Species("H"), F.Species("D"), F.Species("t1", mobile=False), F.Species("t2", mobile=False)]
         by_name = dict(zip(names, species))
@@ -361,7 +361,7 @@ def main():
         surfs = {f["surface"]: F.SurfaceSubdomain1D(id=f["surface"], x=f["x"]) for f in par["fluxes"]}
         prob.subdomains = [*vols.values(), *surfs.values()]
         reactions = []
-        for r in par["reactions"]:
+        for r in par["reactions"][: 1 if first_reaction_only else None]:
             imp = F.ImplicitSpecies(n=r["n"], others=[by_name[r["trapped"]]])
             imp.value_fenics = r["n"]
             reactions.append(F.Reaction(reactant=[by_name[r["mobile"]], imp], product=by_name[r["trapped"]],
@@ -443,6 +443,11 @@ def main():
     form["F_advection"] = reference_residual(u, True, advection=True).tolist()
     form["Jdelta_advection"] = (0.5 * (reference_residual(u + delta, True, advection=True)
                                        - reference_residual(u - delta, True, advection=True))).tolist()
+    # steady state with NO reaction in volume 2: the immobile species get `c v dx(2)` there
+    # (:980-997 looks for any reaction in the volume, not for one involving the species)
+    form["F_steady_filler"] = reference_residual(u, False, first_reaction_only=True).tolist()
+    form["Jdelta_steady_filler"] = (0.5 * (reference_residual(u + delta, False, first_reaction_only=True)
+                                           - reference_residual(u - delta, False, first_reaction_only=True))).tolist()
     form["repeated_reactant_reaction"] = repeated
     form["F_repeated"] = reference_residual(u, True, with_repeated=True).tolist()
     form["Jdelta_repeated"] = (0.5 * (reference_residual(u + delta, True, with_repeated=True)
