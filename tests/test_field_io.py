@@ -364,3 +364,52 @@ def test_vtu_series_index_is_complete_after_close(tmp_path):
     sets = ET.parse(tmp_path / "series.bp" / "series.pvd").getroot().findall("Collection/DataSet")
     assert len(sets) == 120 and float(sets[-1].get("timestep")) == 0.5 * 119
     assert sets[-1].get("file") == "step_000119.vtu" and (tmp_path / "series.bp" / "step_000119.vtu").exists()
+
+
+def test_reads_meshio_style_xdmf(tmp_path):
+    """The layout meshio writes with data_format="XML" (the usual gmsh -> meshio -> FESTIM route):
+    `DataType` / `Precision` attributes, a 2D mesh stored as XYZ with z = 0, tags as a cell-centred
+    attribute with its own name, line elements for the boundary in a second file."""
+    (tmp_path / "mesh.xdmf").write_text("""<Xdmf Version="3.0"><Domain><Grid Name="Grid">
+<Geometry GeometryType="XYZ"><DataItem DataType="Float" Dimensions="4 3" Format="XML" Precision="8">
+0 0 0
+1 0 0
+1 1 0
+0 1 0
+</DataItem></Geometry>
+<Topology NodesPerElement="3" NumberOfElements="2" TopologyType="Triangle">
+<DataItem DataType="Int" Dimensions="2 3" Format="XML" Precision="8">
+0 1 2
+0 2 3
+</DataItem></Topology>
+<Attribute AttributeType="Scalar" Center="Cell" Name="f">
+<DataItem DataType="Int" Dimensions="2" Format="XML" Precision="8">
+6
+7
+</DataItem></Attribute></Grid></Domain></Xdmf>""")
+    (tmp_path / "mf.xdmf").write_text("""<Xdmf Version="3.0"><Domain><Grid Name="Grid">
+<Geometry GeometryType="XYZ"><DataItem DataType="Float" Dimensions="4 3" Format="XML" Precision="8">
+0 0 0
+1 0 0
+1 1 0
+0 1 0
+</DataItem></Geometry>
+<Topology NodesPerElement="2" NumberOfElements="3" TopologyType="Polyline">
+<DataItem DataType="Int" Dimensions="3 2" Format="XML" Precision="8">
+0 1
+2 1
+0 2
+</DataItem></Topology>
+<Attribute AttributeType="Scalar" Center="Cell" Name="f">
+<DataItem DataType="Int" Dimensions="3" Format="XML" Precision="8">
+11
+12
+99
+</DataItem></Attribute></Grid></Domain></Xdmf>""")
+    mesh = F.MeshFromXDMF(volume_file=tmp_path / "mesh.xdmf", facet_file=tmp_path / "mf.xdmf")
+    assert mesh.mesh.tdim == 2 and mesh.mesh.gdim == 2 and mesh.mesh.num_cells == 2
+    assert list(mesh.define_volume_meshtags().values) == [6, 7]
+    ft = mesh.define_surface_meshtags()
+    tags = {tuple(sorted(mesh.mesh.bfacets[i])): int(v) for i, v in zip(ft.indices, ft.values)}
+    # (0, 2) is the interior diagonal: its tag 99 is dropped, untagged boundary edges get 0
+    assert tags == {(0, 1): 11, (1, 2): 12, (2, 3): 0, (0, 3): 0}
