@@ -65,6 +65,8 @@ class FunctionSpace:
     def num_dofs(self):
         if self.family == "DG" and self.degree == 0:
             return self.mesh.num_cells * self.bs
+        if self.family == "DG":      # DG1: one value per (cell, local vertex), cell-major
+            return self.mesh.num_cells * (self.mesh.tdim + 1) * self.bs
         return self.mesh.num_vertices * self.bs
 
     def sub(self, i):

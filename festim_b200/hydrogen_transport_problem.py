@@ -485,6 +485,35 @@ class HydrogenTransportProblem(ProblemBase):
         for fn, D_0, E_D in getattr(self, "_custom_D_fields", []):
             fn.x.array[:] = float(D_0) * np.exp(-float(E_D) / (k_B * Tn))
 
+    def define_D_global(self, species):
+        """Reference :632-670: the DG1 field that holds, in every cell, the Arrhenius diffusivity of
+        the cell's material at the temperatures of the cell's vertices - discontinuous across
+        material interfaces - stored cell-major (``x.array[c * (tdim + 1) + a]``).  It is the field
+        ``SurfaceFlux`` weighs the gradient with; the device evaluates the same values inside
+        ``fb_surface_flux`` from ``diffusivity_tables()`` and the temperature snapshot of
+        ``refresh_D_global`` instead of storing them.  Returns ``(D, None)`` (no separate
+        interpolation expression is needed here)."""
+        assert isinstance(species, _species.Species)
+        if self.volume_subdomains[0].material.D:
+            if len(self.volume_subdomains) > 1:
+                raise NotImplementedError(
+                    "Giving the diffusion coefficient as a function is currently "
+                    "only supported for a single volume subdomain case")
+            return self.volume_subdomains[0].material.D, None
+        mesh = self.mesh.mesh
+        ctag = np.zeros(mesh.num_cells, dtype=np.int64)
+        ctag[self.volume_meshtags.indices] = self.volume_meshtags.values
+        D_0, E_D = np.zeros(mesh.num_cells), np.zeros(mesh.num_cells)
+        for vol in self.volume_subdomains:
+            cells = ctag == vol.id
+            D_0[cells] = vol.material.get_D_0(species=species)
+            E_D[cells] = vol.material.get_E_D(species=species)
+        T = self.temperature_fenics
+        Tc = T.x.array[mesh.cells] if isinstance(T, fem.Function) else np.full(mesh.cells.shape, float(T.value))
+        D = fem.Function(self.V_DG_1, name=f"D_{species.name}")
+        D.x.array[:] = (D_0[:, None] * np.exp(-E_D[:, None] / k_B / Tc)).ravel()
+        return D, None
+
     def refresh_D_global(self):
         self._update_custom_D_fields()
         T = self.temperature_fenics

@@ -303,3 +303,40 @@ def test_custom_quantity_gpu_parity(dim):
     vals_r, _ = _custom_quantity_case(dim, OracleBackend())
     assert np.allclose(vals_g, vals_r, rtol=1e-10)
     assert np.isclose(vals_g[1], vals_g[3], rtol=1e-10)   # custom flux == built-in flux
+
+
+def test_define_D_global_is_the_DG1_field_behind_surface_flux():
+    """reference hydrogen_transport_problem.py:632-670 and test/test_h_transport_problem.py:245-320:
+    per-cell Arrhenius diffusivity of the cell's material at the cell's vertex temperatures -
+    discontinuous at a material interface - and the weight of the gradient in SurfaceFlux."""
+    D_0L, E_DL, D_0R, E_DR = 1.0, 0.1, 2.0, 0.2
+    H = F.Species("H")
+    left, right = F.SurfaceSubdomain1D(id=3, x=0.0), F.SurfaceSubdomain1D(id=4, x=4.0)
+    m = F.HydrogenTransportProblem(
+        mesh=F.Mesh1D(np.linspace(0, 4, num=101)),
+        subdomains=[F.VolumeSubdomain1D(id=1, borders=[0, 2], material=F.Material(D_0=D_0L, E_D=E_DL)),
+                    F.VolumeSubdomain1D(id=2, borders=[2, 4], material=F.Material(D_0=D_0R, E_D=E_DR)),
+                    left, right],
+        species=[H], temperature=lambda x: 100.0 * x[0] + 50,
+        boundary_conditions=[F.FixedConcentrationBC(left, value=1.0, species=H),
+                             F.FixedConcentrationBC(right, value=0.0, species=H)],
+        settings=F.Settings(atol=1e-10, rtol=1e-10, transient=False))
+    flux = F.SurfaceFlux(field=H, surface=right)
+    m.exports = [flux]
+    m.solver_backend = OracleBackend()
+    m.initialise()
+    D, _ = m.define_D_global(H)
+    mesh = m.mesh.mesh
+    vals = D.x.array.reshape(mesh.num_cells, 2)
+    x = mesh.coords[mesh.cells][:, :, 0]
+    in_left = x.mean(axis=1) < 2
+    expected = np.where(in_left[:, None], D_0L * np.exp(-E_DL / (F.k_B * (100 * x + 50))),
+                        D_0R * np.exp(-E_DR / (F.k_B * (100 * x + 50))))
+    assert np.allclose(vals, expected, rtol=1e-14)
+    # two values at the interface vertex x = 2, one per material
+    at_2 = np.isclose(x, 2.0)
+    assert not np.isclose(vals[at_2 & in_left[:, None]][0], vals[at_2 & ~in_left[:, None]][0])
+    m.run()
+    u = m.u.x.array
+    grad = (u[-1] - u[-2]) / (mesh.coords[-1, 0] - mesh.coords[-2, 0])
+    assert np.isclose(flux.data[-1], -vals[-1, -1] * grad, rtol=1e-12)

@@ -106,7 +106,9 @@ def _evaluate_function(u, points):
     """scifem.evaluate_function: P1 interpolation of a fem.Function at points (brute-force
     search of the containing cell)."""
     mesh = u.function_space.mesh
-    vals = np.asarray(u.x.array).reshape(mesh.num_vertices, -1)
+    dg1 = getattr(u.function_space, "family", "") == "DG" and u.function_space.degree == 1
+    vals = None if dg1 else np.asarray(u.x.array).reshape(mesh.num_vertices, -1)
+    cellvals = np.asarray(u.x.array).reshape(mesh.num_cells, mesh.tdim + 1) if dg1 else None
     pts = np.asarray(points, dtype=float).reshape(-1, np.asarray(points).shape[-1])[:, : mesh.gdim]
     X = mesh.coords[mesh.cells]                                   # (nc, d+1, d)
     out = []
@@ -115,7 +117,7 @@ def _evaluate_function(u, points):
         lam = np.linalg.solve(A, (p - X[:, 0])[:, :, None])[:, :, 0]
         bary = np.concatenate([1 - lam.sum(1, keepdims=True), lam], axis=1)
         c = int(np.argmax(bary.min(axis=1)))
-        out.append(bary[c] @ vals[mesh.cells[c]])
+        out.append(bary[c] @ (cellvals[c] if dg1 else vals[mesh.cells[c]]))
     return np.array(out)
 
 sys.modules["scifem"].evaluate_function = _evaluate_function
