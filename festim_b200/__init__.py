@@ -45,7 +45,14 @@ from festim_b200.exports import (
     VTXTemperatureExport,
     XDMFExport,
 )
-from festim_b200.helpers import Value, as_fenics_constant, is_it_time_to_export
+from festim_b200.helpers import (
+    KSPMonitor,
+    SnesMonitor,
+    Value,
+    as_fenics_constant,
+    convergenceTest,
+    is_it_time_to_export,
+)
 from festim_b200.coupled_heat_hydrogen_problem import CoupledTransientHeatTransferHydrogenTransport
 from festim_b200.heat_transfer_problem import HeatTransferProblem
 from festim_b200.hydrogen_transport_problem import HydrogenTransportProblem
@@ -88,3 +95,36 @@ from festim_b200.subdomain import (
     find_volume_from_id,
 )
 from festim_b200.trap import Trap
+
+
+# Names of the reference's public API that are outside this repository's scope (SURVEY section 8:
+# row f1 and section 2): they resolve to classes that say so when used, instead of an
+# AttributeError on import.
+_OUT_OF_SCOPE = {
+    "HydrogenTransportProblemDiscontinuous": "the discontinuous multi-material problem (SURVEY 8f1)",
+    "HydrogenTransportProblemDiscontinuousChangeVar": "the change-of-variable problem (SURVEY 8f1)",
+    "Interface": "interfaces belong to the discontinuous problem (SURVEY 8f1)",
+    "InterfaceMethod": "interfaces belong to the discontinuous problem (SURVEY 8f1)",
+    "Enclosure": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "EnclosureConnection": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "GasPressure": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "GasSpecies": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "OpeningBase": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "PrescribedFlowRate": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "Pump": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "Reservoir": "gas enclosures (0-D unknowns, SURVEY section 2)",
+    "plot": "plotting (pyvista) is not part of the solver path",
+}
+
+
+def __getattr__(name):
+    reason = _OUT_OF_SCOPE.get(name)
+    if reason is None:
+        raise AttributeError(f"module 'festim_b200' has no attribute {name!r}")
+
+    def _refuse(self, *args, **kwargs):
+        raise NotImplementedError(f"festim_b200.{name} is not implemented: {reason}; see DESIGN.md section 7")
+
+    cls = type(name, (), {"__init__": _refuse, "__doc__": f"Out of scope: {reason}."})
+    globals()[name] = cls
+    return cls

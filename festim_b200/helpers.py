@@ -160,3 +160,56 @@ def is_it_time_to_export(times, current_time, atol=0, rtol=1.0e-5):
             del times[i]
             return True
     return False
+
+
+# ---------------------------------------------------------------------------------------------
+# PETSc-style callbacks of the reference (helpers.py:404-454), kept for scripts that install them
+# on `problem.solver.solver` or call them directly.  The solve itself applies the same stopping
+# rule on the device (`fb_newton_solve`, csrc/newton.cu); these are its host-side statement.
+# ---------------------------------------------------------------------------------------------
+_residual0 = 0
+_prev_xnorm = 0
+
+
+def convergenceTest(snes, it, norms):
+    """``helpers.py:408-426``: SNES convergence test ``(snes, it, (xnorm, snorm, fnorm)) -> reason``
+    with the reason codes of ``snes.ConvergedReason``.  As in the reference the residual of
+    iteration 0 is a module global."""
+    global _residual0
+    _xnorm, gnorm, f = norms
+    rtol, atol, stol, max_its = snes.getTolerances()
+    if it == 0:
+        _residual0 = f
+    if it > max_its:
+        return snes.ConvergedReason.DIVERGED_MAX_IT
+    elif f < atol:
+        return snes.ConvergedReason.CONVERGED_FNORM_ABS
+    elif f / _residual0 < rtol:
+        return snes.ConvergedReason.CONVERGED_FNORM_RELATIVE
+    elif gnorm < stol and it > 0:
+        return snes.ConvergedReason.CONVERGED_SNORM_RELATIVE
+    else:
+        return snes.ConvergedReason.ITERATING
+
+
+def SnesMonitor(snes, iter, rnorm):
+    """``helpers.py:429-448``: one INFO line per Newton iteration (Python ``logging`` in place of
+    ``dolfinx.log``)."""
+    import logging
+
+    global _prev_xnorm
+    rtol, atol, stol, _max_its = snes.getTolerances()
+    xnorm = snes.getSolution().norm()
+    stepsize_rel = abs(xnorm - _prev_xnorm) / xnorm if iter > 0 else float("inf")
+    relative_residual = float("inf") if iter == 0 else rnorm / _residual0
+    logging.getLogger("festim_b200").info(
+        f"SNES {iter=} ; {rnorm=:.5e} ({atol=}) ; {relative_residual=:.5e} ({rtol=}) ; "
+        f"{stepsize_rel=:.5e} ({stol=:.5e})")
+    _prev_xnorm = xnorm
+
+
+def KSPMonitor(ksp, iter, rnorm):
+    """``helpers.py:451-454``."""
+    import logging
+
+    logging.getLogger("festim_b200").debug(f"KSP {iter=} {rnorm=:.5e}")

@@ -387,3 +387,34 @@ def test_oracle_steady_filler_matches_the_reference_form():
     assert not np.allclose(Fg, np.array(gold["F_steady"]).ravel())
     assert np.abs(Fo - Fg).max() <= 1e-13 * np.abs(Fg).max()
     assert np.abs(Jo @ d - Jd).max() <= 1e-12 * np.abs(Jd).max()
+
+
+def test_convergenceTest_callback_matches_reference():
+    """reference src/festim/helpers.py:408-426 through the PETSc-style callback kept in
+    festim_b200.helpers (same golden sequences as the oracle's and the device's stopping rule)."""
+    class Reasons:
+        DIVERGED_MAX_IT, CONVERGED_FNORM_ABS, CONVERGED_FNORM_RELATIVE = -5, 2, 3
+        CONVERGED_SNORM_RELATIVE, ITERATING = 4, 0
+
+    class FakeSnes:
+        ConvergedReason = Reasons
+
+        def __init__(self, tol):
+            self.tol = tol
+
+        def getTolerances(self):
+            return self.tol
+
+    for seq in load("convergence_test.json"):
+        snes = FakeSnes((seq["rtol"], seq["atol"], seq["stol"], seq["max_it"]))
+        for row in seq["rows"]:
+            assert F.convergenceTest(snes, row["it"], (1.0, row["snorm"], row["fnorm"])) == row["reason"]
+
+
+def test_out_of_scope_names_say_so():
+    with pytest.raises(NotImplementedError, match="SURVEY 8f1"):
+        F.HydrogenTransportProblemDiscontinuous()
+    with pytest.raises(NotImplementedError, match="gas enclosures"):
+        F.Enclosure(volume=1.0)
+    with pytest.raises(AttributeError):
+        F.NoSuchThing
