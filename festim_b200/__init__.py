@@ -93,6 +93,7 @@ from festim_b200.subdomain import (
     VolumeSubdomain1D,
     find_surface_from_id,
     find_volume_from_id,
+    map_surface_to_volume_subdomains,
 )
 from festim_b200.trap import Trap
 

@@ -83,3 +83,28 @@ def find_volume_from_id(id, volumes):
         if vol.id == id:
             return vol
     raise ValueError(f"id {id} not found in list of volumes")
+
+
+def map_surface_to_volume_subdomains(ft, ct, facet_to_cell, volume_subdomains, surface_subdomains, comm=None):
+    """Reference ``subdomain/volume_subdomain.py:172-260``: which volume subdomain every tagged
+    surface subdomain belongs to, from the facet tags, the cell tags and the facet -> cell
+    connectivity.  Here facets are the exterior facets of a ``SimplexMesh`` and ``facet_to_cell`` is
+    its ``bfacet_cell`` array (one cell per exterior facet).  A surface that touches cells of two
+    volume subdomains is an error, as in the reference."""
+    import numpy as np
+
+    cells = np.asarray(facet_to_cell)[np.asarray(ft.indices)]
+    ctag = dict(zip(np.asarray(ct.indices).tolist(), np.asarray(ct.values).tolist()))
+    pairs = sorted({(int(s), ctag[int(c)]) for s, c in zip(np.asarray(ft.values), cells) if int(c) in ctag})
+    surfaces = {s.id: s for s in surface_subdomains}
+    volumes = {v.id: v for v in volume_subdomains}
+    out = {}
+    for s_tag, v_tag in pairs:
+        s_sub, v_sub = surfaces.get(s_tag), volumes.get(v_tag)
+        if s_sub and v_sub:
+            if s_sub in out:
+                assert out[s_sub] == v_sub, (
+                    f"Surface subdomain {s_sub.id} is connected to multiple volume subdomains: "
+                    f"{out[s_sub].id} and {v_sub.id}")
+            out[s_sub] = v_sub
+    return out

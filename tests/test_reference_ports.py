@@ -340,3 +340,21 @@ def test_define_D_global_is_the_DG1_field_behind_surface_flux():
     u = m.u.x.array
     grad = (u[-1] - u[-2]) / (mesh.coords[-1, 0] - mesh.coords[-2, 0])
     assert np.isclose(flux.data[-1], -vals[-1, -1] * grad, rtol=1e-12)
+
+
+def test_map_surface_to_volume_subdomains():
+    """reference subdomain/volume_subdomain.py:172-260 (test/test_subdomains.py): surfaces map to
+    the volume whose cells they bound; a surface spanning two volumes is an error."""
+    mesh = F.create_unit_square(4, 4)
+    mat = F.Material(D_0=1, E_D=0)
+    vl = F.VolumeSubdomain(id=1, material=mat, locator=lambda x: x[0] <= 0.5 + 1e-12)
+    vr = F.VolumeSubdomain(id=2, material=mat, locator=lambda x: x[0] >= 0.5 - 1e-12)
+    sl = F.SurfaceSubdomain(id=3, locator=lambda x: np.isclose(x[0], 0.0))
+    sr = F.SurfaceSubdomain(id=4, locator=lambda x: np.isclose(x[0], 1.0))
+    ft, ct = F.Mesh(mesh).define_meshtags([sl, sr], [vl, vr])
+    got = F.map_surface_to_volume_subdomains(ft, ct, mesh.bfacet_cell, [vl, vr], [sl, sr])
+    assert got == {sl: vl, sr: vr}
+    top = F.SurfaceSubdomain(id=5, locator=lambda x: np.isclose(x[1], 1.0))
+    ft2, ct2 = F.Mesh(mesh).define_meshtags([top], [vl, vr])
+    with pytest.raises(AssertionError, match="connected to multiple volume subdomains"):
+        F.map_surface_to_volume_subdomains(ft2, ct2, mesh.bfacet_cell, [vl, vr], [top])
