@@ -50,6 +50,8 @@ from festim_b200.helpers import (
     SnesMonitor,
     Value,
     as_fenics_constant,
+    as_fenics_interp_expr_and_function,
+    as_mapped_function,
     convergenceTest,
     is_it_time_to_export,
 )
