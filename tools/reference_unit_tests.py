@@ -87,6 +87,8 @@ dolfinx.fem = _fem
 dmesh = types.ModuleType("dolfinx.mesh")
 dmesh.create_unit_square = lambda comm, nx, ny, *a, **k: _mesh.create_unit_square(nx, ny)
 dmesh.create_unit_cube = lambda comm, nx, ny, nz, *a, **k: _mesh.create_unit_cube(nx, ny, nz)
+dmesh.CellType = types.SimpleNamespace(triangle="triangle", tetrahedron="tetrahedron", interval="interval",
+                                       quadrilateral="quadrilateral", hexahedron="hexahedron")
 dmesh.create_unit_interval = lambda comm, nx, *a, **k: F.Mesh1D(np.linspace(0, 1, nx + 1)).mesh
 dmesh.Mesh = _mesh.SimplexMesh
 dmesh.MeshTags = _mesh.MeshTags
