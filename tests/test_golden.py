@@ -418,3 +418,26 @@ def test_out_of_scope_names_say_so():
         F.Enclosure(volume=1.0)
     with pytest.raises(AttributeError):
         F.NoSuchThing
+
+
+def test_material_property_lookups_match_reference():
+    """reference src/festim/material.py:148-260: D_0 / E_D / K_S_0 / E_K_S as a number or a dict
+    keyed by species object or name - same values, same exception types and messages."""
+    for case in load("material_lookups.json"):
+        attr = case["getter"][4:]
+        A, B, C = F.Species("A"), F.Species("B"), F.Species("missing")
+        species = {"A": A, "B": B, "missing": C, None: None}[case["query"]]
+        value = {"number": 1.25, "by_name": {"A": 1.5, "B": 2.5}, "by_object": {A: 3.5, B: 4.5},
+                 "wrong_type": "oops"}[case["spec"]]
+        kwargs = dict(D_0=1.0, E_D=0.1)
+        kwargs[attr] = value
+        if attr == "D_0" and isinstance(value, dict):
+            kwargs["E_D"] = {k: 0.1 for k in value}
+        if attr == "E_D" and isinstance(value, dict):
+            kwargs["D_0"] = {k: 1.0 for k in value}
+        try:
+            got = {"value": float(getattr(F.Material(**kwargs), case["getter"])(species=species))}
+        except Exception as exc:   # noqa: BLE001
+            got = {"error": type(exc).__name__, "message": str(exc)}
+        expected = {k: case[k] for k in ("value", "error", "message") if k in case}
+        assert got == expected, case

@@ -716,6 +716,33 @@ def main():
                   "final_t": float(hyd_p.t), "final_dt": float(hyd_p._dt.value)})
     json.dump(loops, open(os.path.join(out_dir, "time_loop.json"), "w"), indent=0)
 
+    # --- per-species material properties (material.py:148-260): number or dict keyed by the
+    # species object or its name; what a missing key / missing species / wrong type raises
+    lookups = []
+    getters = ["get_D_0", "get_E_D", "get_K_S_0", "get_E_K_S"]
+    for getter in getters:
+        attr = getter[4:]
+        for spec_kind in ("number", "by_name", "by_object", "wrong_type"):
+            for query in ("A", "B", "missing", None):
+                A, B, C = F.Species("A"), F.Species("B"), F.Species("missing")
+                species = {"A": A, "B": B, "missing": C, None: None}[query]
+                value = {"number": 1.25, "by_name": {"A": 1.5, "B": 2.5}, "by_object": {A: 3.5, B: 4.5},
+                         "wrong_type": "oops"}[spec_kind]
+                kwargs = dict(D_0=1.0, E_D=0.1)
+                kwargs[attr] = value
+                if attr == "D_0" and isinstance(value, dict):
+                    kwargs["E_D"] = {k: 0.1 for k in value}
+                if attr == "E_D" and isinstance(value, dict):
+                    kwargs["D_0"] = {k: 1.0 for k in value}
+                try:
+                    mat = F.Material(**kwargs)
+                    got = getattr(mat, getter)(species=species)
+                    outcome = {"value": float(got)}
+                except Exception as exc:   # noqa: BLE001
+                    outcome = {"error": type(exc).__name__, "message": str(exc)}
+                lookups.append({"getter": getter, "spec": spec_kind, "query": query, **outcome})
+    json.dump(lookups, open(os.path.join(out_dir, "material_lookups.json"), "w"), indent=0)
+
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
     print("golden vectors written to", out_dir)
