@@ -441,3 +441,30 @@ def test_material_property_lookups_match_reference():
             got = {"error": type(exc).__name__, "message": str(exc)}
         expected = {k: case[k] for k in ("value", "error", "message") if k in case}
         assert got == expected, case
+
+
+def test_is_it_time_to_export_matches_reference():
+    """reference src/festim/helpers.py:374-401: tolerance of the match and the
+    consumption of matched times, query by query."""
+    for case in load("host_rules.json")["is_it_time_to_export"]:
+        work = None if case["times"] is None else list(case["times"])
+        for q in case["queries"]:
+            assert F.is_it_time_to_export(times=work, current_time=q["t"]) == q["hit"], (case["times"], q)
+            assert work == q["remaining"]
+
+
+def test_mesh1d_check_borders_matches_reference():
+    """reference src/festim/mesh/mesh_1d.py:109-155: accepted subdomain layouts (single and
+    multi-block meshes), same errors otherwise."""
+    mat = F.Material(D_0=1.0, E_D=0.0)
+    for case in load("host_rules.json")["check_borders"]:
+        vertices = case["vertices"]
+        mesh = F.Mesh1D(vertices=[np.array(b) for b in vertices] if isinstance(vertices[0], list)
+                        else np.array(vertices))
+        vols = [F.VolumeSubdomain1D(id=i + 1, borders=b, material=mat) for i, b in enumerate(case["borders"])]
+        if case["ok"]:
+            mesh.check_borders(vols)
+        else:
+            with pytest.raises(ValueError) as err:
+                mesh.check_borders(vols)
+            assert str(err.value) == case["message"], case

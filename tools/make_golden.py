@@ -743,6 +743,50 @@ def main():
                 lookups.append({"getter": getter, "spec": spec_kind, "query": query, **outcome})
     json.dump(lookups, open(os.path.join(out_dir, "material_lookups.json"), "w"), indent=0)
 
+    # --- small host rules on the path -------------------------------------------------------
+    # is_it_time_to_export (helpers.py:374-401): matching tolerance and consumption of the times;
+    # Mesh1D.check_borders (mesh_1d.py:109-155): which subdomain layouts are accepted.
+    import festim.helpers as H2
+
+    export_cases = []
+    for _ in range(12):
+        times = sorted(float(v) for v in rng.uniform(0.0, 10.0, int(rng.integers(1, 6))))
+        queries = []
+        work = list(times)
+        for _ in range(14):
+            if rng.random() < 0.5 and times:
+                tq = float(rng.choice(times)) * (1.0 + float(rng.choice([0.0, 4e-6, -4e-6, 3e-5, -3e-5])))
+            else:
+                tq = float(rng.uniform(0.0, 10.0))
+            hit = bool(H2.is_it_time_to_export(times=work, current_time=tq))
+            queries.append({"t": tq, "hit": hit, "remaining": list(work)})
+        export_cases.append({"times": times, "queries": queries})
+    export_cases.append({"times": None, "queries": [{"t": 1.0, "hit": bool(H2.is_it_time_to_export(None, 1.0)),
+                                                     "remaining": None}]})
+    border_cases = []
+    layouts = [
+        ([0.0, 1.0, 2.0, 4.0], [[0, 2], [2, 4]]), ([0.0, 1.0, 2.0, 4.0], [[0, 4]]),
+        ([0.0, 1.0, 2.0, 4.0], [[0, 1.5], [2, 4]]), ([0.0, 1.0, 2.0, 4.0], [[0, 2], [2, 3]]),
+        ([0.0, 1.0, 2.0, 4.0], [[1, 2], [2, 4]]), ([0.0, 1.0, 2.0, 4.0], []),
+        ([0.0, 1.0, 2.0, 4.0], [[2, 4], [0, 2]]), ([0.0, 1.0, 2.0, 4.0], [[0, 2], [2, 5]]),
+        ([[0.0, 1.0, 2.0], [3.0, 4.0]], [[0, 2], [3, 4]]), ([[0.0, 1.0, 2.0], [3.0, 4.0]], [[0, 2]]),
+        ([[0.0, 1.0, 2.0], [3.0, 4.0]], [[0, 4]]), ([[0.0, 1.0, 2.0], [3.0, 4.0]], [[0, 1], [1, 2], [3, 4]]),
+    ]
+    mat1 = F.Material(D_0=1.0, E_D=0.0)
+    for vertices, borders in layouts:
+        try:
+            mesh1d = F.Mesh1D.__new__(F.Mesh1D)      # (the constructor needs a real dolfinx mesh)
+            mesh1d.vertices = ([np.array(b) for b in vertices] if isinstance(vertices[0], list)
+                               else np.array(vertices))
+            vols = [F.VolumeSubdomain1D(id=i + 1, borders=b, material=mat1) for i, b in enumerate(borders)]
+            mesh1d.check_borders(vols)
+            outcome = {"ok": True}
+        except Exception as exc:   # noqa: BLE001
+            outcome = {"ok": False, "error": type(exc).__name__, "message": str(exc)}
+        border_cases.append({"vertices": vertices, "borders": borders, **outcome})
+    json.dump({"is_it_time_to_export": export_cases, "check_borders": border_cases},
+              open(os.path.join(out_dir, "host_rules.json"), "w"), indent=0)
+
     json.dump({"k_B": F.k_B, "R": F.R, "k_B_SI": F.k_B_SI},
               open(os.path.join(out_dir, "constants.json"), "w"))
     print("golden vectors written to", out_dir)
