@@ -38,7 +38,16 @@ MAGIC = 0xFB200_0001
  S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
  S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_RSLOT_E, S_FAC_HDR, S_FAC_A0,
  S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
- S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW) = range(1, 46)
+ S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW,
+ S_VX_INTS, S_VX_CQ_PTR, S_VX_CQ, S_VX_CH_PTR, S_VX_CH, S_VX_JT_PTR, S_VX_JT, S_VX_JT_COEF,
+ S_VX_FT_PTR, S_VX_FT, S_VX_FT_COEF) = range(1, 57)
+
+# cell-record quantity kinds / channel types / flags of the vertex-block assembly
+# (csrc/assemble_vtx.cuh)
+CQ_KD, CQ_M1, CQ_M3, CQ_ADV = 0, 1, 2, 3
+CH_MASS, CH_PAIR, CH_TRI, CH_FULL = 0, 1, 2, 3
+USE_F, USE_J = 1, 2
+FLAG_INV_DT = 1
 
 # S_INTS slots
 (I_TDIM, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -196,6 +205,7 @@ class KernelSpec:
         self.struct = None
         if self.struct_reactions:
             self._build_structured(sidx)
+        self._vertex_tables()
 
         # quadrature pools
         self._qb, self._qw = [], []
@@ -261,7 +271,6 @@ class KernelSpec:
         """Tables for the moment-based reaction assembly."""
         from festim_b200.species import ImplicitSpecies
 
-        ns, nvt = self.ns, len(self.vol_ids)
         self.rslot_E = []
         factors = {}      # key -> id
         fac_rows = []     # (a0_kind, a0_scalar, a0_const, [(species, coef)])
@@ -274,7 +283,13 @@ class KernelSpec:
             return self.rslot_E.index(E)
 
         def factor_of(obj):
-            if isinstance(obj, ImplicitSpecies):
+            if isinstance(obj, ImplicitSpecies) and isinstance(obj.n, (int, float)):
+                # a plain number never changes: equal densities over the same species share a factor
+                key = ("impc", float(obj.n), tuple(sidx[o] for o in obj.others))
+                if key not in factors:
+                    factors[key] = len(fac_rows)
+                    fac_rows.append((0, -1, float(obj.n), [(sidx[o], -1.0) for o in obj.others]))
+            elif isinstance(obj, ImplicitSpecies):
                 key = ("imp", id(obj.value_fenics), tuple(sidx[o] for o in obj.others))
                 if key not in factors:
                     factors[key] = len(fac_rows)
@@ -295,94 +310,194 @@ class KernelSpec:
             if mode and reaction.products:
                 monos.append((tag, slot_of(reaction.E_p if mode == 2 else 0.0),
                               [factor_of(pr) for pr in reaction.products], -float(reaction.p_0), rows))
-        # contribution lists
-        fc = [[] for _ in range(nvt * ns)]                 # (mono, sign)
-        jc = [[] for _ in range(nvt * self.npairs)]        # (slot, other factor, coef)
-        for im, (tag, slot, facs, coef, rows) in enumerate(monos):
-            for row, sign in rows:
-                fc[tag * ns + row].append((im, sign))
-                for pos, f in enumerate(facs):
-                    other = facs[1 - pos] if len(facs) == 2 else -1
-                    for spe, a in fac_rows[f][3]:
-                        p = int(self.pair_pp[row]) + int(self.pair_idx[row, spe])
-                        jc[tag * self.npairs + p].append((slot, other, sign * coef * a))
-        self.struct = dict(monos=monos, fac_rows=fac_rows, fc=fc, jc=jc)
+        # a factor that is one species with coefficient one is read from the solution itself;
+        # the others get a column of their own in the per-neighbour value table
+        dev = [i for i, (kind, _, a0, coefs) in enumerate(fac_rows)
+               if not (kind == 0 and a0 == 0.0 and len(coefs) == 1 and coefs[0][1] == 1.0)]
+        self.struct = dict(monos=monos, fac_rows=fac_rows, dev_factors=dev)
 
     def _structured_sections(self):
+        """Affine factors and activation energies of the structured reactions."""
         st = self.struct
-        nsym = (self.tdim + 1) * (self.tdim + 2) // 2
-        d1 = self.tdim + 1
-        fac_hdr = np.zeros((max(len(st["fac_rows"]), 1), 4), dtype=np.int32)
-        fac_a0 = np.zeros(max(len(st["fac_rows"]), 1))
+        rows = [st["fac_rows"][i] for i in st["dev_factors"]]
+        fac_hdr = np.zeros((max(len(rows), 1), 4), dtype=np.int32)
+        fac_a0 = np.zeros(max(len(rows), 1))
         fsp, fco = [], []
-        for i, (kind, scal, a0, coefs) in enumerate(st["fac_rows"]):
+        for i, (kind, scal, a0, coefs) in enumerate(rows):
             fac_hdr[i] = [kind, scal, len(fsp), len(coefs)]
             fac_a0[i] = a0
             for spe, c in coefs:
                 fsp.append(spe)
                 fco.append(c)
-        # (rate slot, factor) combinations whose moment-weighted nodal vectors
-        # V[j] = sum_b fac[b] M[j][b] are shared by residual and Jacobian contributions
-        combos = []
-
-        def combo_of(slot, f):
-            if (slot, f) not in combos:
-                combos.append((slot, f))
-            return combos.index((slot, f))
-
-        mono = np.full((max(len(st["monos"]), 1), 6), -1, dtype=np.int32)
-        mono_coef = np.zeros(max(len(st["monos"]), 1))
-        for i, (tag, slot, facs, coef, rows) in enumerate(st["monos"]):
-            mono[i, :3] = [tag, slot, len(facs)]
-            for k, f in enumerate(facs):
-                mono[i, 3 + k] = f
-            if len(facs) == 2:
-                mono[i, 5] = combo_of(slot, facs[1])
-            mono_coef[i] = coef
-        fc_ptr, fc_mono, fc_sign = [0], [], []
-        for lst in st["fc"]:
-            for im, sg in lst:
-                fc_mono.append(im)
-                fc_sign.append(sg)
-            fc_ptr.append(len(fc_mono))
-        jc_ptr, jc_tab, jc_coef = [0], [], []
-        for lst in st["jc"]:
-            for slot, other, c in lst:
-                # second column: combo index, or -(slot+1) for the plain first-order moment
-                jc_tab.append([slot, combo_of(slot, other) if other >= 0 else -(slot + 1)])
-                jc_coef.append(c)
-            jc_ptr.append(len(jc_coef))
-        # W tables: W[which][i][q][ab] = w_q phi_i phi_a phi_b (a <= b), then its q-sum
-        wtab, woff = [], np.zeros((len(self.vol_ids), 4), dtype=np.int32)
-        sym = [(a, b) for a in range(d1) for b in range(a, d1)]
-        for t, vid in enumerate(self.vol_ids):
-            dF, dJ = self.degrees.get(("dx", vid), (1, None))
-            for which, deg in enumerate((dF, dF if dJ is None else dJ)):
-                bary, w = quadrature.rule(self.tdim, deg)
-                W = np.zeros((d1, len(w), nsym))
-                for i in range(d1):
-                    for k, (a, b) in enumerate(sym):
-                        W[i, :, k] = w * bary[:, i] * bary[:, a] * bary[:, b]
-                if which == 1 and (dJ is None or dJ == dF):
-                    woff[t, 2:4] = woff[t, 0:2]      # same rule: share the table
-                    continue
-                woff[t, 2 * which] = sum(len(x) for x in wtab)
-                woff[t, 2 * which + 1] = len(w)
-                wtab.append(W.ravel())
-                wtab.append(W.sum(axis=1).ravel())
         ints = np.zeros(8, dtype=np.int32)
-        ints[:5] = [len(self.rslot_E), len(st["fac_rows"]), len(st["monos"]), nsym, len(combos)]
-        pair_row = np.repeat(np.arange(self.ns, dtype=np.int32), self.pair_nc)
+        ints[:3] = [len(self.rslot_E), len(rows), len(st["monos"])]
         return {
             S_STRUCT_INTS: ints, S_RSLOT_E: np.array(self.rslot_E, dtype=np.float64),
             S_FAC_HDR: fac_hdr, S_FAC_A0: fac_a0, S_FAC_SPECIES: np.array(fsp, dtype=np.int32),
-            S_FAC_COEF: np.array(fco, dtype=np.float64), S_MONO: mono, S_MONO_COEF: mono_coef,
-            S_FC_PTR: np.array(fc_ptr, dtype=np.int32), S_FC_MONO: np.array(fc_mono, dtype=np.int32),
-            S_FC_SIGN: np.array(fc_sign, dtype=np.float64),
-            S_JC_PTR: np.array(jc_ptr, dtype=np.int32),
-            S_JC: np.array(jc_tab, dtype=np.int32).reshape(-1, 2), S_JC_COEF: np.array(jc_coef, dtype=np.float64),
-            S_WTAB: np.concatenate(wtab) if wtab else np.zeros(0), S_WTAB_OFF: woff,
-            S_COMBO: np.array(combos, dtype=np.int32).reshape(-1, 2), S_PAIR_ROW: pair_row,
+            S_FAC_COEF: np.array(fco, dtype=np.float64),
+        }
+
+    # ------------------------------------------------------------------
+    # vertex-block assembly (csrc/assemble_vtx.cuh).  Every volume term whose integrand is a
+    # product of P1 functions with a cell-wise coefficient is assembled from *channels*:
+    # per-cell (D1 x D1) matrices  C^c_ij  that do not depend on the species pair,
+    #     mass        |K| (1 + delta_ij) / ((d+1)(d+2))
+    #     diffusion   |K| mean_q(exp(-E/kT)) grad(phi_i).grad(phi_j)          (cached per cell)
+    #     first-order rate moment   |K| sum_q w_q rho_m phi_i phi_j            (cached per cell)
+    #     second-order rate moment contracted with an affine factor f of the species,
+    #                 sum_b (|K| sum_q w_q rho_m phi_i phi_j phi_b) f_b        (moment cached)
+    #     advection   |K| sum_q w_q phi_i vel_q.grad(phi_j)                    (cached per cell)
+    # A warp sums the channels of the cells around its vertex per neighbour ("edge channels"
+    # A^c_vw), then every stored Jacobian entry is a short linear combination
+    #     J[(v,s),(w,s')] = sum_e coef_e A^{chan_e}_vw          (table per tag and species pair)
+    # and the residual is  F[(v,s)] = load + sum_e coef_e sum_w A^{chan_e}_vw g_e(w)  with g one
+    # of u_s', (u - u_n)_s', an affine factor, or 1.  Same sums over quadrature points as the
+    # reference's generated kernel (reaction.py:179-224 expanded in the P1 basis), reordered.
+    def _vertex_tables(self):
+        import os
+
+        self.vx = None
+        if os.environ.get("FB_NO_VTX"):
+            return
+        if any(t.u_dependent for t in self.vterms) or self.diff_udep:
+            return   # generic point-wise terms: thread-per-vertex kernel
+        nvt, ns, d1 = len(self.vol_ids), self.ns, self.tdim + 1
+        if nvt > 32:
+            return
+        nsym, nsym3 = d1 * (d1 + 1) // 2, d1 * (d1 + 1) * (d1 + 2) // 6
+        st = self.struct or dict(monos=[], fac_rows=[], dev_factors=[])
+        fac_rows, dev = st["fac_rows"], st["dev_factors"]
+        NF = len(dev)
+        g_u, g_du, g_one = (lambda s: s), (lambda s: ns + s), 2 * ns + NF
+
+        def g_fac(f):   # column of factor f in the per-neighbour value table [u | u - u_n | factors | 1]
+            return 2 * ns + dev.index(f) if f in dev else g_u(fac_rows[f][3][0][0])
+
+        qsize = {CQ_KD: nsym, CQ_M1: nsym, CQ_M3: nsym3, CQ_ADV: d1 * d1}
+        cq_all, ch_all, jt_all, ft_all = [], [], [], []
+        rec_max = 1
+        for tag, vid in enumerate(self.vol_ids):
+            dF, dJ = self.degrees.get(("dx", vid), (1, None))
+            same = dJ is None or dJ == dF
+            rule = (lambda which: 1) if same else (lambda which: which)
+            quantities, cq, size = {}, [], [1]          # record[0] = |K|
+            channels, ch = {}, []
+
+            def quantity(kind, a, r):
+                key = (kind, a, r)
+                if key not in quantities:
+                    quantities[key] = size[0]
+                    cq.append([kind, a, r, size[0]])
+                    size[0] += qsize[kind]
+                return quantities[key]
+
+            def channel(ctype, off, fac, use):
+                key = (ctype, off, fac)
+                if key not in channels:
+                    channels[key] = len(ch)
+                    ch.append([ctype, off, fac, 0])
+                ch[channels[key]][3] |= use
+                return channels[key]
+
+            jt = [dict() for _ in range(self.npairs)]    # pair -> {(chan, flag): coef}
+            ft = [[] for _ in range(ns)]                 # species -> [(chan, gcol, coef, flag)]
+
+            def addJ(row, col, chan, coef, flag=0):
+                p = int(self.pair_pp[row]) + int(self.pair_idx[row, col])
+                jt[p][(chan, flag)] = jt[p].get((chan, flag), 0.0) + coef
+
+            for s in range(ns):
+                ds = int(self.diff_slot[tag, s])
+                if ds >= 0:
+                    D0 = float(self.diff_D0[tag, s])
+                    cF = channel(CH_PAIR, quantity(CQ_KD, ds, rule(0)), -1, USE_F)
+                    ft[s].append((cF, g_u(s), D0, 0))
+                    cJ = channel(CH_PAIR, quantity(CQ_KD, ds, rule(1)), -1, USE_J)
+                    addJ(s, s, cJ, D0)
+                if self.transient and self.mass_dt[tag, s] != 0.0:
+                    c = channel(CH_MASS, 0, -1, USE_F | USE_J)
+                    ft[s].append((c, g_du(s), float(self.mass_dt[tag, s]), FLAG_INV_DT))
+                    addJ(s, s, c, float(self.mass_dt[tag, s]), FLAG_INV_DT)
+                if self.mass_c[tag, s] != 0.0:
+                    c = channel(CH_MASS, 0, -1, USE_F | USE_J)
+                    ft[s].append((c, g_u(s), float(self.mass_c[tag, s]), 0))
+                    addJ(s, s, c, float(self.mass_c[tag, s]))
+            for a, (atag, s, _) in enumerate(self.adv):
+                if atag == tag:
+                    c = channel(CH_FULL, quantity(CQ_ADV, a, 0), -1, USE_F | USE_J)
+                    ft[s].append((c, g_u(s), 1.0, 0))
+                    addJ(s, s, c, 1.0)
+            for mtag, slot, facs, coef, rows in st["monos"]:
+                if mtag != tag:
+                    continue
+
+                def moment(which, other):
+                    r = rule(which)
+                    use = USE_F if which == 0 else USE_J
+                    if other >= 0:
+                        return channel(CH_TRI, quantity(CQ_M3, slot, r), g_fac(other), use)
+                    return channel(CH_PAIR, quantity(CQ_M1, slot, r), -1, use)
+
+                for row, sign in rows:
+                    if len(facs) == 2:
+                        ft[row].append((moment(0, facs[1]), g_fac(facs[0]), sign * coef, 0))
+                    elif len(facs) == 1:
+                        ft[row].append((moment(0, -1), g_fac(facs[0]), sign * coef, 0))
+                    else:
+                        ft[row].append((moment(0, -1), g_one, sign * coef, 0))
+                    for pos, f in enumerate(facs):
+                        other = facs[1 - pos] if len(facs) == 2 else -1
+                        chan = moment(1, other)
+                        for spe, a in fac_rows[f][3]:
+                            addJ(row, spe, chan, sign * coef * a)
+            cq_all.append(cq)
+            ch_all.append(ch)
+            jt_all.append(jt)
+            ft_all.append(ft)
+            rec_max = max(rec_max, size[0])
+        self.vx = dict(nsym=nsym, nsym3=nsym3, rec=rec_max, nbw=g_one + 1, NF=NF,
+                       nch=max(max((len(c) for c in ch_all), default=1), 1),
+                       cq=cq_all, ch=ch_all, jt=jt_all, ft=ft_all)
+
+    def _vertex_sections(self):
+        vx = self.vx
+        nvt, ns = len(self.vol_ids), self.ns
+
+        def csr(lists, width):
+            ptr, flat = [0], []
+            for lst in lists:
+                flat.extend(lst)
+                ptr.append(len(flat))
+            return (np.array(ptr, dtype=np.int32),
+                    np.array(flat, dtype=np.int32).reshape(-1, width))
+
+        cq_ptr, cq = csr(vx["cq"], 4)
+        ch_ptr, ch = csr(vx["ch"], 4)
+        jt_ptr, jt, jt_coef = [0], [], []
+        for tag in range(nvt):
+            for p in range(self.npairs):
+                for (chan, flag), coef in vx["jt"][tag][p].items():
+                    jt.append([chan, flag])
+                    jt_coef.append(coef)
+                jt_ptr.append(len(jt))
+        ft_ptr, ft, ft_coef = [0], [], []
+        for tag in range(nvt):
+            for s in range(ns):
+                for chan, gcol, coef, flag in vx["ft"][tag][s]:
+                    ft.append([chan, gcol, flag])
+                    ft_coef.append(coef)
+                ft_ptr.append(len(ft))
+        ints = np.zeros(8, dtype=np.int32)
+        ints[:7] = [1, vx["nsym"], vx["nsym3"], vx["rec"], vx["nbw"], vx["nch"], vx["NF"]]
+        return {
+            S_VX_INTS: ints, S_VX_CQ_PTR: cq_ptr, S_VX_CQ: cq, S_VX_CH_PTR: ch_ptr, S_VX_CH: ch,
+            S_VX_JT_PTR: np.array(jt_ptr, dtype=np.int32),
+            S_VX_JT: np.array(jt, dtype=np.int32).reshape(-1, 2),
+            S_VX_JT_COEF: np.array(jt_coef, dtype=np.float64),
+            S_VX_FT_PTR: np.array(ft_ptr, dtype=np.int32),
+            S_VX_FT: np.array(ft, dtype=np.int32).reshape(-1, 3),
+            S_VX_FT_COEF: np.array(ft_coef, dtype=np.float64),
+            S_PAIR_ROW: np.repeat(np.arange(self.ns, dtype=np.int32), self.pair_nc),
         }
 
     @staticmethod
@@ -499,6 +614,8 @@ class KernelSpec:
         }
         if self.struct is not None:
             sections.update(self._structured_sections())
+        if self.vx is not None:
+            sections.update(self._vertex_sections())
         return pack_sections(sections)
 
 
