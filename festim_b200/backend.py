@@ -305,6 +305,21 @@ class Context:
         return int(self.lib.fb_launch_count(self.h))
 
 
+def jacobian_index(spec, graph):
+    """(row dof, column dof) of every stored Jacobian scalar in storage order: block CSR of
+    the vertex graph, the ``npairs`` stored species pairs of block ``e`` at ``e * npairs + p``
+    (``p`` = position of (row species, column species) in ``pair_row`` / ``pair_cs``)."""
+    rowptr, colidx = graph
+    ns, npairs = spec.ns, spec.npairs
+    deg = np.diff(rowptr).astype(np.int64)
+    v_of = np.repeat(np.arange(len(deg), dtype=np.int64), deg)          # row vertex of every block
+    pair_row = np.repeat(np.arange(ns, dtype=np.int64), spec.pair_nc)
+    pair_cs = spec.pair_cs.astype(np.int64)
+    R = (v_of[:, None] * ns + pair_row[None, :]).ravel()
+    Cc = (colidx.astype(np.int64)[:, None] * ns + pair_cs[None, :]).ravel()
+    return R, Cc
+
+
 class _Snes:
     def __init__(self):
         self.reason = 0
@@ -445,30 +460,8 @@ class B200NewtonSolver:
     def jacobian_index(self):
         """(rows, cols) of every stored Jacobian scalar, in storage order (the
         layout documented in include/festim_b200.h)."""
-        spec = self.spec
-        rowptr, colidx = self.ctx.dmesh.graph
-        ns, npairs = spec.ns, spec.npairs
-        deg = np.diff(rowptr).astype(np.int64)
-        rows, cols = [], []
-        r0 = rowptr[:-1].astype(np.int64)
-        nv = len(deg)
-        # per vertex block: for s: for k: for j
-        for s in range(ns):
-            nc = int(spec.pair_nc[s])
-            cs = spec.pair_cs[spec.pair_pp[s]: spec.pair_pp[s + 1]].astype(np.int64)
-            # entries of (v, s): deg[v] * nc
-            cnt = deg * nc
-            start = r0 * npairs + deg * int(spec.pair_pp[s])
-            v_of = np.repeat(np.arange(nv, dtype=np.int64), cnt)
-            e = np.arange(cnt.sum(), dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
-            k = e // nc
-            j = e - k * nc
-            pos = np.repeat(start, cnt) + e
-            rows.append((pos, v_of * ns + s, colidx[np.repeat(r0, cnt) + k].astype(np.int64) * ns + cs[j]))
-        pos = np.concatenate([r[0] for r in rows])
-        order = np.argsort(pos)
-        R = np.concatenate([r[1] for r in rows])[order]
-        Cc = np.concatenate([r[2] for r in rows])[order]
+        R, Cc = jacobian_index(self.spec, self.ctx.dmesh.graph)
+        ns = self.spec.ns
         return self.ctx.dofs_to_user_numbering(R, ns), self.ctx.dofs_to_user_numbering(Cc, ns)
 
     def assemble_host(self, want_J=True):

@@ -14,7 +14,9 @@ enum {
   S_FTERM_HDR, S_ROW_SPECIES, S_ROW_COEF, S_DERIV_SPECIES, S_DERIV_PROG, S_QUAD_V, S_QUAD_S,
   S_QUAD_BARY, S_QUAD_W, S_ADV, S_DIFF_PROGS, S_DIFF_UPROG, S_RSLOT_E, S_FAC_HDR, S_FAC_A0,
   S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
-  S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW, S_MAX
+  S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW,
+  S_VX_INTS, S_VX_CQ_PTR, S_VX_CQ, S_VX_CH_PTR, S_VX_CH, S_VX_JT_PTR, S_VX_JT, S_VX_JT_COEF,
+  S_VX_FT_PTR, S_VX_FT, S_VX_FT_COEF, S_MAX
 };
 enum {
   I_TDIM = 0, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -213,27 +215,103 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   UP(S_DERIV_SPECIES, 0, deriv_species); UP(S_DERIV_PROG, 0, deriv_prog);
   UP(S_QUAD_V, 0, quad_v); UP(S_QUAD_S, 0, quad_s); UP(S_QUAD_BARY, 1, quad_bary); UP(S_QUAD_W, 1, quad_w);
   UP(S_ADV, 0, adv); UP(S_DIFF_UPROG, 0, diff_uprog);
-  S.n_rslots = S.n_factors = S.n_monos = S.nsym = S.nq_max = S.n_combos = 0;
+  S.n_rslots = S.n_factors = S.n_monos = 0;
   if (secs[S_STRUCT_INTS].id == S_STRUCT_INTS) {
     const int* si = (const int*)(blob + secs[S_STRUCT_INTS].offset);
-    S.n_rslots = si[0]; S.n_factors = si[1]; S.n_monos = si[2]; S.nsym = si[3]; S.n_combos = si[4];
-    UP(S_COMBO, 0, combo); UP(S_PAIR_ROW, 0, pair_row);
+    S.n_rslots = si[0]; S.n_factors = si[1]; S.n_monos = si[2];
     UP(S_RSLOT_E, 1, rslot_E); UP(S_FAC_HDR, 0, fac_hdr); UP(S_FAC_A0, 1, fac_a0);
-    UP(S_FAC_SPECIES, 0, fac_species); UP(S_FAC_COEF, 1, fac_coef); UP(S_MONO, 0, mono);
-    UP(S_MONO_COEF, 1, mono_coef); UP(S_FC_PTR, 0, fc_ptr); UP(S_FC_MONO, 0, fc_mono);
-    UP(S_FC_SIGN, 1, fc_sign); UP(S_JC_PTR, 0, jc_ptr); UP(S_JC, 0, jc); UP(S_JC_COEF, 1, jc_coef);
-    UP(S_WTAB, 1, wtab); UP(S_WTAB_OFF, 0, wtab_off);
-    const int* wo = (const int*)(blob + secs[S_WTAB_OFF].offset);
-    for (int t = 0; t < S.n_vtags; ++t) {
-      if (wo[4 * t + 1] > S.nq_max) S.nq_max = wo[4 * t + 1];
-      if (wo[4 * t + 3] > S.nq_max) S.nq_max = wo[4 * t + 3];
-    }
+    UP(S_FAC_SPECIES, 0, fac_species); UP(S_FAC_COEF, 1, fac_coef);
     ctx->symmetric = false;
   }
   S.maxdeg = 0;
   for (long long v = 0; v < S.n_vertices; ++v) {
     const int dg = ctx->h_rowptr[v + 1] - ctx->h_rowptr[v];
     if (dg > S.maxdeg) S.maxdeg = dg;
+  }
+  auto magic = [](int d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); };
+  S.vx_m_ns = magic(S.ns); S.vx_m_np = magic(S.npairs); S.vx_m_nf = magic(S.n_factors); S.vx_m_rec = 0u;
+  // ---- vertex-block assembly tables (assemble_vtx.cuh) --------------------------------------
+  S.vx_on = 0;
+  if (secs[S_VX_INTS].id == S_VX_INTS && S.v2c_slot != nullptr && !getenv("FB_NO_VTX")) {
+    const int* vi = (const int*)(blob + secs[S_VX_INTS].offset);
+    S.vx_nsym = vi[1]; S.vx_nsym3 = vi[2]; S.vx_rec = vi[3]; S.vx_nbw = vi[4]; S.vx_nch = vi[5];
+    if (vi[6] != S.n_factors) return fb_fail(ctx, "vertex tables: factor count mismatch");
+    UP(S_PAIR_ROW, 0, pair_row); UP(S_VX_CQ_PTR, 0, vx_cq_ptr); UP(S_VX_CQ, 0, vx_cq);
+    auto sec_i = [&](int id) { return (const int*)(blob + secs[id].offset); };
+    auto sec_d = [&](int id) { return (const double*)(blob + secs[id].offset); };
+    const int nvt = S.n_vtags, ns = S.ns, np = S.npairs;
+    const int* chp = sec_i(S_VX_CH_PTR); const int* ch = sec_i(S_VX_CH);
+    const int* jtp = sec_i(S_VX_JT_PTR); const int* jt = sec_i(S_VX_JT); const double* jtc = sec_d(S_VX_JT_COEF);
+    const int* ftp = sec_i(S_VX_FT_PTR); const int* ft = sec_i(S_VX_FT); const double* ftc = sec_d(S_VX_FT_COEF);
+    if (S.vx_nch > 255 || np > 255) return fb_fail(ctx, "vertex tables: too many channels / species pairs");
+    // lanes per neighbour in the row expansion: as many as fit next to maxdeg neighbours
+    int lpk = 1;
+    while (lpk * 2 * S.maxdeg <= 32 && lpk * 2 <= np) lpk *= 2;
+    S.vx_lpk = lpk;
+    std::vector<int> itab;
+    std::vector<double> dtab;
+    S.vx_o_chptr = (int)itab.size(); itab.insert(itab.end(), chp, chp + nvt + 1);
+    S.vx_o_ch = (int)itab.size(); itab.insert(itab.end(), ch, ch + 4 * chp[nvt]);
+    S.vx_o_ftptr = (int)itab.size(); itab.insert(itab.end(), ftp, ftp + nvt * ns + 1);
+    S.vx_o_ft = (int)itab.size(); itab.insert(itab.end(), ft, ft + 3 * ftp[nvt * ns]);
+    S.vx_o_ftc = (int)dtab.size(); dtab.insert(dtab.end(), ftc, ftc + ftp[nvt * ns]);
+    S.vx_nft_max = 1;
+    for (int t = 0; t < nvt; ++t) S.vx_nft_max = std::max(S.vx_nft_max, ftp[(t + 1) * ns] - ftp[t * ns]);
+    // expansion lists: per tag, lpk sub-lists of (pair | channel << 8 | flags) of equal length;
+    // the entries of a pair are consecutive and the last one carries the STORE flag
+    std::vector<int> xhdr(2 * nvt), xl;
+    std::vector<double> xc;
+    for (int t = 0; t < nvt; ++t) {
+      std::vector<std::vector<int>> sub(lpk);   // pairs of every sub-list
+      std::vector<long long> load(lpk, 0);
+      std::vector<int> order(np);
+      for (int p = 0; p < np; ++p) order[p] = p;
+      auto cnt = [&](int p) { return std::max(1, jtp[t * np + p + 1] - jtp[t * np + p]); };
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt(a) > cnt(b); });
+      for (int p : order) {
+        int best = 0;
+        for (int h = 1; h < lpk; ++h) if (load[h] < load[best]) best = h;
+        sub[best].push_back(p);
+        load[best] += cnt(p);
+      }
+      int Lx = 1;
+      for (int h = 0; h < lpk; ++h) Lx = std::max<long long>(Lx, load[h]);
+      xhdr[2 * t] = (int)xl.size(); xhdr[2 * t + 1] = Lx;
+      for (int h = 0; h < lpk; ++h) {
+        std::sort(sub[h].begin(), sub[h].end());
+        int n = 0;
+        for (int p : sub[h]) {
+          const int a0 = jtp[t * np + p], a1 = jtp[t * np + p + 1];
+          if (a0 == a1) { xl.push_back(p | (1 << 17)); xc.push_back(0.0); ++n; continue; }
+          for (int e = a0; e < a1; ++e) {
+            int ent = p | (jt[2 * e] << 8);
+            if (jt[2 * e + 1] & 1) ent |= 1 << 16;
+            if (e == a1 - 1) ent |= 1 << 17;
+            xl.push_back(ent); xc.push_back(jtc[e]); ++n;
+          }
+        }
+        for (; n < Lx; ++n) { xl.push_back(0); xc.push_back(0.0); }
+      }
+    }
+    S.vx_o_xlhdr = (int)itab.size(); itab.insert(itab.end(), xhdr.begin(), xhdr.end());
+    S.vx_o_xl = (int)itab.size(); itab.insert(itab.end(), xl.begin(), xl.end());
+    S.vx_o_xlc = (int)dtab.size(); dtab.insert(dtab.end(), xc.begin(), xc.end());
+    S.vx_itab_n = (int)itab.size(); S.vx_dtab_n = (int)dtab.size();
+    if ((rc = fb_upload(ctx, &S.vx_itab, itab.data(), itab.size()))) return rc;
+    if ((rc = fb_upload(ctx, &S.vx_dtab, dtab.data(), dtab.size()))) return rc;
+    auto even2mod4 = [](int n) { int m = (n + 1) & ~1; while (m % 4 != 2) m += 2; return m; };
+    S.vx_nchp = even2mod4(S.vx_nch);
+    S.vx_recp = S.vx_rec | 1;
+    S.vx_rbp = np | 1;
+    S.vx_m_rec = magic(S.vx_rec);
+    double* rec = nullptr;
+    if ((rc = fb_alloc(ctx, &rec, (size_t)S.n_cells * S.vx_rec))) return rc;
+    S.cellrec = rec;
+    unsigned* vinfo = nullptr;
+    if ((rc = fb_alloc(ctx, &vinfo, (size_t)S.n_vertices))) return rc;
+    FB_CHECK(ctx, cudaMemsetAsync(vinfo, 0, sizeof(unsigned) * S.n_vertices, ctx->stream));
+    S.vinfo = vinfo;
+    S.vx_on = 1;
   }
   S.n_udiff = 0;
   if (secs[S_DIFF_UPROG].id == S_DIFF_UPROG) {
@@ -242,23 +320,6 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
       if (up[3 * i] >= 0) { S.n_udiff++; ctx->symmetric = false; }
   }
 #undef UP
-  // SpMV gather table (multi-species rows), one line per block-row degree
-  S.spmv_tab = nullptr; S.spmv_tab_stride = 0;
-  if (S.ns > 1 && (long long)S.maxdeg * S.ns < 65536) {
-    std::vector<int> nc(S.ns), pp(S.ns + 1), cs(S.npairs);
-    memcpy(nc.data(), blob + secs[S_PAIR_NC].offset, sizeof(int) * S.ns);
-    memcpy(pp.data(), blob + secs[S_PAIR_PP].offset, sizeof(int) * (S.ns + 1));
-    memcpy(cs.data(), blob + secs[S_PAIR_CS].offset, sizeof(int) * S.npairs);
-    const int stride = S.maxdeg * S.npairs;
-    std::vector<unsigned short> tab((size_t)(S.maxdeg + 1) * stride, 0);
-    for (int d = 1; d <= S.maxdeg; ++d)
-      for (int s = 0; s < S.ns; ++s)
-        for (int k = 0; k < d; ++k)
-          for (int j = 0; j < nc[s]; ++j)
-            tab[(size_t)d * stride + (size_t)d * pp[s] + (size_t)k * nc[s] + j] = (unsigned short)(k * S.ns + cs[pp[s] + j]);
-    if ((rc = fb_upload(ctx, &S.spmv_tab, tab.data(), tab.size()))) return rc;
-    S.spmv_tab_stride = stride;
-  }
   // mutable per-step buffers
   if ((rc = fb_alloc(ctx, &ctx->d_scalars, (size_t)n_scalars + 1))) return rc;
   if ((rc = fb_alloc(ctx, &ctx->d_fields, (size_t)S.n_fields + 1))) return rc;
@@ -292,11 +353,12 @@ extern "C" int fb_set_dirichlet(fb_ctx* ctx, int64_t n_bc, const int64_t* bc_dof
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_bc_map, 0xFF, sizeof(int) * S.n_dofs, ctx->stream));
   ctx->n_bc = n_bc;
   ctx->coarse_masks_dirty = true;
-  if (n_bc == 0) return 0;
+  if (n_bc == 0) return fbi_update_vinfo(ctx);
   const long long* d = nullptr;
   int rc = fb_upload(ctx, &d, (const long long*)bc_dofs, (size_t)n_bc);
   if (rc) return rc;
   FB_LAUNCH(ctx, k_fill_bc_map, (unsigned)((n_bc + 255) / 256), 256, 0, (long long)n_bc, d, ctx->d_bc_map);
+  if ((rc = fbi_update_vinfo(ctx))) return rc;
   FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }

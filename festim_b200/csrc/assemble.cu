@@ -30,7 +30,7 @@
 #include "fb_internal.cuh"
 #include "program.cuh"
 #include "assemble_kernels.cuh"
-#include "assemble_rows.cuh"
+#include "assemble_vtx.cuh"
 #include "reduce.cuh"
 
 // ---------------------------------------------------------------------------
@@ -56,11 +56,18 @@ k_assemble_nodes(DevSpec S, const double* __restrict__ u, const double* __restri
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256, 2)
-k_assemble_rows(DevSpec S, const double* __restrict__ u, const double* __restrict__ un,
-                double* __restrict__ F, double* __restrict__ J, int flags, int per_warp) {
-  extern __shared__ double fb_rows_smem[];
-  fb_assemble_rows_body<DIM>(S, u, un, F, J, flags, fb_rows_smem, per_warp);
+__global__ void __launch_bounds__(128)
+k_cell_records(DevSpec S, double* __restrict__ out) { fb_cell_records_body<DIM>(S, out); }
+
+__global__ void k_vinfo_rows(DevSpec S, unsigned* __restrict__ vinfo) { fb_vinfo_rows_body(S, vinfo); }
+__global__ void k_vinfo_cols(DevSpec S, unsigned* __restrict__ vinfo) { fb_vinfo_cols_body(S, vinfo); }
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_assemble_vtx(DevSpec S, const double* __restrict__ u, const double* __restrict__ un,
+               double* __restrict__ F, double* __restrict__ J, int flags) {
+  extern __shared__ double fb_vtx_smem[];
+  fb_assemble_vtx_body<DIM>(S, u, un, F, J, flags, fb_vtx_smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -154,6 +161,7 @@ static int update_coeffs_dim(fb_ctx* ctx) {
       FB_LAUNCH(ctx, k_cell_coeffs<DIM>, gc, B, 0, S, ctx->d_dbar);
     }
   }
+  if (S.vx_on) FB_LAUNCH(ctx, k_cell_records<DIM>, gc, B, 0, S, (double*)S.cellrec);
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_load, 0, sizeof(double) * S.n_dofs, ctx->stream));
   if (S.n_vterms > 0) {
     if (ctx->have_jit) {
@@ -181,6 +189,16 @@ static int update_coeffs_dim(fb_ctx* ctx) {
   return 0;
 }
 
+int fbi_update_vinfo(fb_ctx* ctx) {
+  const DevSpec& S = ctx->S;
+  if (!S.vx_on) return 0;
+  const unsigned g = (unsigned)((S.n_vertices + 255) / 256);
+  FB_LAUNCH(ctx, k_vinfo_rows, g, 256, 0, S, (unsigned*)S.vinfo);
+  FB_LAUNCH(ctx, k_vinfo_cols, g, 256, 0, S, (unsigned*)S.vinfo);
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
 int fbi_update_coeffs(fb_ctx* ctx) {
   switch (ctx->S.tdim) {
     case 1: return update_coeffs_dim<1>(ctx);
@@ -195,18 +213,26 @@ static int assemble_dim(fb_ctx* ctx, const double* u, const double* un, double* 
   DevSpec& S = ctx->S;
   const unsigned B = 128;
   const unsigned gn = (unsigned)((S.n_vertices + B - 1) / B);
-  const bool structured = S.n_monos > 0 && !ctx->generic_u_vterms && S.n_udiff == 0 &&
-                          !getenv("FB_NO_ROWS_KERNEL");
-  if (structured) {
-    // warp per vertex, block row accumulated in shared memory (assemble_rows.cuh)
-    const int per_warp = fb_rows_per_warp<DIM>(S);
-    int wpb = 8;
-    while (wpb > 1 && (size_t)wpb * per_warp * 8 > 200 * 1024) wpb >>= 1;
-    const size_t smem = (size_t)wpb * per_warp * 8;
-    if (smem > 220 * 1024) return fb_fail(ctx, "block row does not fit in shared memory");
-    FB_CHECK(ctx, cudaFuncSetAttribute(k_assemble_rows<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (S.vx_on) {
+    // warp per vertex, edge channels and the block row in shared memory (assemble_vtx.cuh)
+    const VtxLayout L = fb_vtx_layout<DIM>(S);
+    int smem_max = 0, smem_sm = 0;
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
+    int wpb = 0, best = 0;
+    for (int w = 8; w >= 1; --w) {
+      const size_t bytes = (size_t)(L.warp0 + (size_t)w * L.per_warp) * 8;
+      if (bytes > (size_t)smem_max) continue;
+      int blocks = (int)((size_t)smem_sm / (bytes + 1024));
+      if (blocks * w * 32 > 2048) blocks = 2048 / (w * 32);
+      if (blocks * w > best) { best = blocks * w; wpb = w; }
+    }
+    if (getenv("FB_VTX_WPB")) wpb = atoi(getenv("FB_VTX_WPB"));
+    if (wpb < 1) return fb_fail(ctx, "vertex-block assembly: a block row does not fit in shared memory");
+    const size_t smem = (size_t)(L.warp0 + (size_t)wpb * L.per_warp) * 8;
+    FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_assemble_vtx<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned gr = (unsigned)((S.n_owned + wpb - 1) / wpb);
-    k_assemble_rows<DIM><<<gr, wpb * 32, smem, ctx->stream>>>(S, u, un, F, J, flags, per_warp);
+    k_assemble_vtx<DIM><<<gr, wpb * 32, smem, ctx->stream>>>(S, u, un, F, J, flags);
     ctx->launches++;
   } else if (ctx->have_jit) {
     void* args[] = {(void*)&S, (void*)&u, (void*)&un, (void*)&F, (void*)&J, (void*)&flags};

@@ -225,8 +225,8 @@ __device__ __forceinline__ int fb_find_slot(const DevSpec& S, int row, int col) 
 }
 
 __device__ __forceinline__ long long fb_entry(const DevSpec& S, int row, int s, int k, int j) {
-  const int r0 = S.rowptr[row], deg = S.rowptr[row + 1] - r0;
-  return (long long)r0 * S.npairs + (long long)deg * S.pair_pp[s] + (long long)k * S.pair_nc[s] + j;
+  // block layout: the npairs values of block (row, k) are contiguous
+  return ((long long)S.rowptr[row] + k) * S.npairs + S.pair_pp[s] + j;
 }
 
 // Facet terms.  mode 0: solution-independent terms -> load vector.
@@ -527,7 +527,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
                   if (bcj >= 0) {
                     if (doF) Facc[s] += aij * (S.bc_vals[bcj] - ucl[j][dep]);
                   } else if (doJ) {
-                    J[rowbase + (long long)deg * S.pair_pp[s] + (long long)slot[j] * S.pair_nc[s] + jp2] += aij;
+                    J[rowbase + (long long)slot[j] * S.npairs + S.pair_pp[s] + jp2] += aij;
                   }
                 }
               }
@@ -577,7 +577,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
         if (bcj >= 0) {
           if (doF) Facc[s] += aJ * (S.bc_vals[bcj] - uj);
         } else if (doJ) {
-          J[rowbase + (long long)deg * S.pair_pp[s] + (long long)slot[j] * S.pair_nc[s] + jp] += aJ;
+          J[rowbase + (long long)slot[j] * S.npairs + S.pair_pp[s] + jp] += aJ;
         }
       }
     }
@@ -659,7 +659,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
                   if (bcj >= 0) {
                     if (doF) Facc[s] += aij * (S.bc_vals[bcj] - uc[j][dep]);
                   } else if (doJ) {
-                    J[rowbase + (long long)deg * S.pair_pp[s] + (long long)slot[j] * S.pair_nc[s] + jp] += aij;
+                    J[rowbase + (long long)slot[j] * S.npairs + S.pair_pp[s] + jp] += aij;
                   }
                 }
               }
@@ -677,8 +677,7 @@ __device__ __forceinline__ void fb_assemble_nodes_body(const DevSpec& S, const d
     if (rowbc >> s & 1u) {
       if (doF) F[dof] = u[dof] - S.bc_vals[S.bc_map[dof]];
       if (doJ)
-        J[rowbase + (long long)deg * S.pair_pp[s] + (long long)kself * S.pair_nc[s] +
-          S.pair_idx[s * ns + s]] = 1.0;
+        J[rowbase + (long long)kself * S.npairs + S.pair_pp[s] + S.pair_idx[s * ns + s]] = 1.0;
     } else if (doF) {
       F[dof] = Facc[s] + S.load[dof];
     }

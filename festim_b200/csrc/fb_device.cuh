@@ -59,29 +59,26 @@ struct DevSpec {
   const double* quad_bary;
   const double* quad_w;
   const int* adv;             // [n_adv*2] tag, species
-  // structured reactions (moment-based assembly, assemble_rows.cuh)
-  int n_rslots, n_factors, n_monos, nsym, nq_max, maxdeg, n_combos;
-  const int* combo;           // [n_combos*2] rate slot, factor
+  // affine factors and rate energies of the structured reactions (lowering.py)
+  int n_rslots, n_factors, n_monos, maxdeg;
   const int* pair_row;        // [npairs] row species of every stored pair
   const double* rslot_E;      // [n_rslots] activation energies of the rate slots
   const int* fac_hdr;         // [n_factors*4] a0 kind (0 const, 1 scalar), scalar id, coef offset, count
   const double* fac_a0;
   const int* fac_species;
   const double* fac_coef;
-  const int* mono;            // [n_monos*6] tag, slot, nfac, f1, f2, combo(slot, f2)
-  const double* mono_coef;
-  const int* fc_ptr;          // [n_vtags*ns+1] residual contributions per (tag, row species)
-  const int* fc_mono;
-  const double* fc_sign;
-  const int* jc_ptr;          // [n_vtags*npairs+1] Jacobian contributions per (tag, pair)
-  const int* jc;              // [n*2] slot, combo index or -(slot+1) for the first-order moment
-  const double* jc_coef;
-  const double* wtab;         // per tag and rule: W[i][q][sym] then its q-sum W0[i][sym]
-  const int* wtab_off;        // [n_vtags*4] offF, nqF, offJ, nqJ
-  // SpMV gather table: for a block row of degree d, entry t -> index into the staged
-  // neighbour values (k*ns + column species); [ (maxdeg+1) x maxdeg*npairs ] uint16
-  const unsigned short* spmv_tab;
-  int spmv_tab_stride;
+  // vertex-block assembly (assemble_vtx.cuh): per-cell record, channels, coefficient tables
+  int vx_on, vx_nsym, vx_nsym3, vx_rec, vx_nbw, vx_nch, vx_nchp, vx_recp, vx_rbp, vx_lpk, vx_nft_max;
+  int vx_itab_n, vx_dtab_n;   // sizes of the block-shared tables copied to shared memory
+  int vx_o_chptr, vx_o_ch, vx_o_ftptr, vx_o_ft, vx_o_xlhdr, vx_o_xl;   // offsets into itab
+  int vx_o_ftc, vx_o_xlc;                                               // offsets into dtab
+  unsigned vx_m_ns, vx_m_nf, vx_m_np, vx_m_rec;   // ceil(2^32 / d) for d = ns, n_factors, npairs, vx_rec
+  const int* vx_cq_ptr;       // [n_vtags+1] cell-record quantities per tag
+  const int* vx_cq;           // [n*4] kind, index, rule, offset in the record
+  const int* vx_itab;         // channel / residual / expansion tables (ints)
+  const double* vx_dtab;      // their coefficients
+  const double* cellrec;      // [n_cells][vx_rec]
+  const unsigned* vinfo;      // per vertex: Dirichlet species mask (bits 0-15), any Dirichlet column (bit 16)
   // per-step data
   const double* scalars;
   double T_const;

@@ -133,6 +133,7 @@ int fb_upload(fb_ctx* ctx, const T** dst, const T* host, size_t count) {
 
 // entry points implemented across translation units
 int fbi_update_coeffs(fb_ctx* ctx);
+int fbi_update_vinfo(fb_ctx* ctx);
 int fbi_assemble(fb_ctx* ctx, const double* u, const double* un, double* F, double* J, int flags);
 int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y);
 int fbi_norm2(fb_ctx* ctx, const double* x, double* out_host);

@@ -23,16 +23,18 @@ __device__ __forceinline__ double spmv_row(const DevSpec& S, const double* __res
   const int s = (int)(row - v * ns);
   const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
   const int nc = S.pair_nc[s], pp = S.pair_pp[s];
-  const double* __restrict__ vals = J + (long long)r0 * S.npairs + (long long)deg * pp;
+  // block layout: entry (k, j) of the scalar row at (r0 + k) * npairs + pp + j
+  const int np = S.npairs;
+  const double* __restrict__ vals = J + (long long)r0 * np + pp;
   const int n = deg * nc;
   double sum = 0.0;
   if (nc == 1) {
     const int cs = S.pair_cs[pp];
-    for (int e = lane; e < n; e += G) sum += vals[e] * x[(long long)S.colidx[r0 + e] * ns + cs];
+    for (int e = lane; e < n; e += G) sum += vals[(long long)e * np] * x[(long long)S.colidx[r0 + e] * ns + cs];
   } else {
     for (int e = lane; e < n; e += G) {
       const int k = e / nc, j = e - k * nc;
-      sum += vals[e] * x[(long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]];
+      sum += vals[(long long)k * np + j] * x[(long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]];
     }
   }
   // reduce over the G lanes of this row only: neighbouring groups of the warp may
@@ -53,48 +55,85 @@ k_spmv(DevSpec S, const double* __restrict__ J, const double* __restrict__ x, do
   if (lane == 0) y[row] = sum;
 }
 
-// Multi-species SpMV: one warp per vertex.  The ns values of every neighbour are staged
-// once in shared memory (deg x ns doubles, coalesced 8*ns-byte segments) and reused by all
-// ns scalar rows of the vertex; the row values stream from HBM exactly once, fully
-// coalesced (the block row is contiguous), with the lanes laid out as (neighbour, column
-// species) so no integer division sits in the inner loop.
+// Multi-species SpMV on the block layout: one warp per vertex (= block row).  The ns values
+// of every neighbour are staged once in shared memory (coalesced 8*ns-byte segments) and
+// reused by all stored pairs; lane l owns the species pairs l, l+32, ... of every block, so
+// the npairs values of a block are one contiguous coalesced load per pass, no index
+// arithmetic or division sits in the loop over the neighbours, and 4 x PPL independent
+// streaming loads (ld.global.cs) are in flight per lane.  PRECOND fuses the point-block
+// Jacobi application  y = D_v^-1 (J x)_v  (left preconditioning of GMRES) into the epilogue.
+__device__ __forceinline__ int fb_fastdiv_u(unsigned n, unsigned magic) {
+  return magic ? (int)__umulhi(n, magic) : (int)n;
+}
+
+template <int PPL, bool PRECOND>
 __global__ void __launch_bounds__(256)
-k_spmv_node(DevSpec S, const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y,
-            int xs_stride) {
+k_spmv_blk(DevSpec S, const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y,
+           const double* __restrict__ dinv, int xs_stride, const int* __restrict__ flags) {
   extern __shared__ double xs_all[];
+  if (flags && flags[0]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const long long v = (long long)blockIdx.x * wpb + warp;
   if (v >= S.n_owned) return;
-  const int ns = S.ns;
+  const int ns = S.ns, np = S.npairs;
   double* xs = xs_all + (size_t)warp * xs_stride;
+  double* part = xs + S.maxdeg * ns;            // [np] partial sums, later [ns*ns] products
   const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
   for (int t = lane; t < deg * ns; t += 32) {
-    const int k = t / ns;
+    const int k = fb_fastdiv_u((unsigned)t, S.vx_m_ns);
     xs[t] = x[(long long)S.colidx[r0 + k] * ns + (t - k * ns)];
   }
+  int cs[PPL];
+  double acc[PPL];
+#pragma unroll
+  for (int q = 0; q < PPL; ++q) {
+    const int p = lane + 32 * q;
+    cs[q] = p < np ? S.pair_cs[p] : -1;
+    acc[q] = 0.0;
+  }
   __syncwarp();
-  const double* __restrict__ vals = J + (long long)r0 * S.npairs;
-  for (int s = 0; s < ns; ++s) {
-    const int nc = S.pair_nc[s], pp = S.pair_pp[s];
-    const double* __restrict__ rv = vals + (long long)deg * pp;
-    const int kper = 32 / nc;                 // neighbours handled per sweep
-    const int kl = lane / nc, j = lane - kl * nc;
-    const bool active = kl < kper;
-    const int cs = active ? S.pair_cs[pp + j] : 0;
-    double sum = 0.0;
-    if (active) {
+  const double* __restrict__ Jr = J + (long long)r0 * np + lane;
 #pragma unroll 4
-      for (int k = kl; k < deg; k += kper) sum += rv[k * nc + j] * xs[k * ns + cs];
-    }
-    sum = warp_sum(sum);
-    if (lane == 0) y[v * ns + s] = sum;
+  for (int k = 0; k < deg; ++k) {
+#pragma unroll
+    for (int q = 0; q < PPL; ++q)
+      if (cs[q] >= 0) acc[q] += __ldcs(Jr + (long long)k * np + 32 * q) * xs[k * ns + cs[q]];
+  }
+#pragma unroll
+  for (int q = 0; q < PPL; ++q)
+    if (cs[q] >= 0) part[lane + 32 * q] = acc[q];
+  __syncwarp();
+  double sum = 0.0;
+  if (lane < ns) {
+    const int p0 = S.pair_pp[lane], p1 = S.pair_pp[lane + 1];
+    for (int p = p0; p < p1; ++p) sum += part[p];
+  }
+  if (!PRECOND) {
+    if (lane < ns) y[v * ns + lane] = sum;
+    return;
+  }
+  if (ns == 1) {
+    if (lane == 0) y[v] = dinv[v] * sum;
+    return;
+  }
+  __syncwarp();
+  double* ys = xs;   // the staged iterate is dead: reuse
+  if (lane < ns) ys[lane] = sum;
+  __syncwarp();
+  const double* __restrict__ dv = dinv + v * (long long)(ns * ns);
+  for (int t = lane; t < ns * ns; t += 32) {
+    const int r = fb_fastdiv_u((unsigned)t, S.vx_m_ns);
+    part[t] = __ldcs(dv + t) * ys[t - r * ns];
+  }
+  __syncwarp();
+  if (lane < ns) {
+    double z = 0.0;
+    for (int c = 0; c < ns; ++c) z += part[lane * ns + c];
+    y[v * ns + lane] = z;
   }
 }
 
 static int spmv_group(const DevSpec& S) {
-  // ~ average row length / 2, power of two
-  const double avg = (double)S.npairs / S.ns * 15.0;
-  (void)avg;
   const double len = (S.tdim == 1 ? 3.0 : (S.tdim == 2 ? 7.0 : 15.0)) * S.npairs / S.ns;
   if (len <= 6) return 4;
   if (len <= 20) return 8;
@@ -102,22 +141,41 @@ static int spmv_group(const DevSpec& S) {
   return 32;
 }
 
+template <bool PRECOND>
+static int spmv_blk_launch(fb_ctx* ctx, const double* J, const double* x, double* y, const int* flags) {
+  const DevSpec& S = ctx->S;
+  const int wpb = 8;
+  const int tail = S.npairs > S.ns * S.ns ? S.npairs : S.ns * S.ns;
+  const int stride = (S.maxdeg * S.ns + tail + 1) & ~1;
+  const size_t smem = (size_t)wpb * stride * sizeof(double);
+  const unsigned grid = (unsigned)((S.n_owned + wpb - 1) / wpb);
+  const int ppl = (S.npairs + 31) / 32;
+#define FB_SPMV_CASE(N)                                                                                   \
+  {                                                                                                       \
+    if (smem > 48 * 1024)                                                                                 \
+      FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_spmv_blk<N, PRECOND>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                     \
+    k_spmv_blk<N, PRECOND><<<grid, wpb * 32, smem, ctx->stream>>>(S, J, x, y, ctx->d_dinv, stride, flags);  \
+  }
+  if (ppl <= 1) FB_SPMV_CASE(1)
+  else if (ppl == 2) FB_SPMV_CASE(2)
+  else if (ppl == 3) FB_SPMV_CASE(3)
+  else if (ppl == 4) FB_SPMV_CASE(4)
+  else FB_SPMV_CASE(8)
+#undef FB_SPMV_CASE
+  ctx->launches++;
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+static bool spmv_blk_ok(const DevSpec& S) {
+  const int tail = S.npairs > S.ns * S.ns ? S.npairs : S.ns * S.ns;
+  return S.ns > 1 && (size_t)8 * (S.maxdeg * S.ns + tail + 2) * 8 <= 200 * 1024 && !getenv("FB_SPMV_ROWWISE");
+}
+
 int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y) {
   const DevSpec& S = ctx->S;
-  if (S.ns > 1 && S.spmv_tab != nullptr && !getenv("FB_SPMV_ROWWISE")) {
-    const int wpb = 8;
-    const int stride = (S.maxdeg * S.ns + 1) & ~1;
-    const size_t smem = (size_t)wpb * stride * sizeof(double);
-    if (smem <= 200 * 1024) {
-      if (smem > 48 * 1024)
-        FB_CHECK(ctx, cudaFuncSetAttribute(k_spmv_node, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const unsigned grid = (unsigned)((S.n_owned + wpb - 1) / wpb);
-      k_spmv_node<<<grid, wpb * 32, smem, ctx->stream>>>(S, J, x, y, stride);
-      ctx->launches++;
-      FB_CHECK(ctx, cudaGetLastError());
-      return 0;
-    }
-  }
+  if (spmv_blk_ok(S)) return spmv_blk_launch<false>(ctx, J, x, y, nullptr);
   const int G = spmv_group(S);
   const long long threads = S.n_dofs * G;
   const unsigned grid = (unsigned)((threads + FB_TPB - 1) / FB_TPB);
@@ -213,7 +271,7 @@ __global__ void k_bjacobi_setup(DevSpec S, const double* __restrict__ J, double*
     for (int c = 0; c < ns; ++c) {
       const int jp = S.pair_idx[s * ns + c];
       A[s][c] = jp < 0 ? 0.0
-                       : J[base + (long long)deg * S.pair_pp[s] + (long long)kself * S.pair_nc[s] + jp];
+                       : J[base + (long long)kself * S.npairs + S.pair_pp[s] + jp];
       B[s][c] = (s == c) ? 1.0 : 0.0;
     }
   // Gauss-Jordan with partial pivoting
@@ -633,14 +691,14 @@ k_cg_persistent(DevSpec S, CgArgs A) {
         const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
         const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
-        const int start = (int)((long long)r0 * S.npairs + (long long)deg * pp - e0);
+        const int start = (int)((long long)r0 * S.npairs + pp - e0);   // block layout: entry (k, j) at start + k * npairs + j
         rstart[rr] = start;
         rlen[rr] = deg * nc;
         rbst[rr] = r0 - S.rowptr[v0];
         if (!part)
           for (int e = 0; e < deg * nc; ++e) {
             const int k = e / nc, j = e - k * nc;
-            scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
+            scols[start + k * S.npairs + j] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
           }
       }
     }
@@ -783,24 +841,26 @@ k_cg_persistent(DevSpec S, CgArgs A) {
           const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
           for (int e = gl; e < n; e += G) {
             const int k = e / nc, j = e - k * nc;
-            sum += svals[a0 + e] * su[(int)slcol[bs + k] * ns + S.pair_cs[pp + j]];
+            sum += svals[a0 + k * S.npairs + j] * su[(int)slcol[bs + k] * ns + S.pair_cs[pp + j]];
           }
         }
       } else if (staged) {
         ri = __ldcg(A.r + row); ui = __ldcg(uvec + row);  // issued before the gathers
         const int a0 = rstart[rr], n = rlen[rr];
+        const int ncr = ns == 1 ? 1 : S.pair_nc[rr - (rr / ns) * ns];
+        auto eofs = [&](int e) { return ns == 1 ? e : (e / ncr) * S.npairs + (e - (e / ncr) * ncr); };
         // all gathers of a batch are in flight before the first use (L2 latency once per batch)
         for (int eb = gl; eb < n; eb += 8 * G) {
           double uv[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int e = eb + q * G;
-            uv[q] = e < n ? __ldcg(uvec + scols[a0 + e]) : 0.0;
+            uv[q] = e < n ? __ldcg(uvec + scols[a0 + eofs(e)]) : 0.0;
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int e = eb + q * G;
-            if (e < n) sum += svals[a0 + e] * uv[q];
+            if (e < n) sum += svals[a0 + eofs(e)] * uv[q];
           }
         }
       } else {
@@ -809,16 +869,16 @@ k_cg_persistent(DevSpec S, CgArgs A) {
         const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
         const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
-        const double* __restrict__ vals = A.J + (long long)r0 * S.npairs + (long long)deg * pp;
+        const double* __restrict__ vals = A.J + (long long)r0 * S.npairs + pp;   // entry (k, j) at k * npairs + j
         const int n = deg * nc;
         if (nc == 1) {
           const int cs = S.pair_cs[pp];
           for (int e = gl; e < n; e += G)
-            sum += vals[e] * __ldcg(uvec + (long long)S.colidx[r0 + e] * ns + cs);
+            sum += vals[(long long)e * S.npairs] * __ldcg(uvec + (long long)S.colidx[r0 + e] * ns + cs);
         } else {
           for (int e = gl; e < n; e += G) {
             const int k = e / nc, j = e - k * nc;
-            sum += vals[e] * __ldcg(uvec + (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]);
+            sum += vals[(long long)k * S.npairs + j] * __ldcg(uvec + (long long)S.colidx[r0 + k] * ns + S.pair_cs[pp + j]);
           }
         }
       }
@@ -927,65 +987,95 @@ k_cg_persistent(DevSpec S, CgArgs A) {
 #define GM_G (GM_SN + GM_M)
 #define GM_HD1 (GM_G + GM_M + 1)
 #define GM_HD2 (GM_HD1 + GM_M + 1)
-#define GM_MISC (GM_HD2 + GM_M + 1)  // [0]=norm2 of w, [1]=scale, [2]=residual, [3]=threshold, [4]=beta0
+#define GM_MISC (GM_HD2 + GM_M + 1)  // [0]=norm2 of w, [1]=scale, [2]=residual, [3]=threshold, [4]=beta0, [5]=refined
 #define GM_Y (GM_MISC + 8)
 #define GM_END (GM_Y + GM_M)
 
-// hd[i] = <V_i, w>, i < nv
+// Classical Gram-Schmidt with one refinement pass when needed (PETSc's default for GMRES:
+// KSPGMRESClassicalGramSchmidtOrthogonalization, refine "if needed"), as two or three sweeps:
+//   k_gs_dots    h1[i] = <V_i, w> (i < nv),  n0 = <w, w>
+//   k_gs_update  w -= sum_i h1[i] V_i  and, in the same sweep,  h2[i] = <V_i, w>,  n1 = <w, w>;
+//                the last block decides: refine iff n1 < n0 / 2
+//   k_gs_refine  (only then) w -= sum_i h2[i] V_i,  n2 = <w, w>
+// Every thread keeps its NVB accumulators in registers and reads w once per sweep; the NVB
+// basis loads of an element are independent (one long burst of loads in flight per thread).
+template <int NVB>
 __global__ void __launch_bounds__(FB_TPB)
-k_multidot(long long n, int nv, const double* __restrict__ V, const double* __restrict__ w,
-           double* partials, unsigned* ticket, double* hd, const int* __restrict__ flags) {
+k_gs_dots(long long n, int nv, const double* __restrict__ V, const double* __restrict__ w,
+          double* partials, unsigned* ticket, double* hd, double* n0, const int* __restrict__ flags) {
   if (flags[0]) return;
-  __shared__ double sm[FB_TPB / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i = 0; i < nv; ++i) {
-    const double* __restrict__ vi = V + (size_t)i * n;
-    double acc = 0.0;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
-         k += (long long)gridDim.x * blockDim.x)
-      acc += vi[k] * w[k];
-    acc = warp_sum(acc);
-    if (lane == 0) sm[wid] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (int q = 0; q < nw; ++q) s += sm[q];
-      partials[(size_t)i * gridDim.x + blockIdx.x] = s;
-    }
-    __syncthreads();
-  }
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  for (int i = wid; i < nv; i += nw) {
-    double s = 0.0;
-    for (unsigned b = lane; b < gridDim.x; b += 32) s += partials[(size_t)i * gridDim.x + b];
-    s = warp_sum(s);
-    if (lane == 0) hd[i] = s;
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
-}
-
-// w -= sum_i hd[i] V_i ; out_norm2 = <w, w>
-__global__ void __launch_bounds__(FB_TPB)
-k_multiaxpy_norm(long long n, int nv, const double* __restrict__ V, const double* __restrict__ hd,
-                 double* __restrict__ w, double* partials, unsigned* ticket, double* out_norm2,
-                 const int* __restrict__ flags) {
-  if (flags[0]) return;
-  double v[1] = {0.0}, tot[1];
+  double acc[NVB + 1], tot[NVB + 1];
+#pragma unroll
+  for (int i = 0; i <= NVB; ++i) acc[i] = 0.0;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
        k += (long long)gridDim.x * blockDim.x) {
-    double acc = w[k];
-    for (int i = 0; i < nv; ++i) acc -= hd[i] * V[(size_t)i * n + k];
-    w[k] = acc;
-    v[0] += acc * acc;
+    const double wk = w[k];
+    double vv[NVB];
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * n + k] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) acc[i] += vv[i] * wk;
+    acc[NVB] += wk * wk;
   }
-  if (grid_reduce<1>(v, partials, ticket, tot) && threadIdx.x == 0) out_norm2[0] = tot[0];
+  if (grid_reduce<NVB + 1>(acc, partials, ticket, tot) && threadIdx.x == 0) {
+    for (int i = 0; i < nv; ++i) hd[i] = tot[i];
+    n0[0] = tot[NVB];
+  }
+}
+
+template <int NVB>
+__global__ void __launch_bounds__(FB_TPB)
+k_gs_update(long long n, int nv, const double* __restrict__ V, const double* __restrict__ h1,
+            double* __restrict__ w, double* partials, unsigned* ticket, double* h2, double* misc,
+            const int* __restrict__ flags) {
+  if (flags[0]) return;
+  double acc[NVB + 1], tot[NVB + 1], h[NVB];
+#pragma unroll
+  for (int i = 0; i < NVB; ++i) { acc[i] = 0.0; h[i] = i < nv ? h1[i] : 0.0; }
+  acc[NVB] = 0.0;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    double wk = w[k];
+    double vv[NVB];
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * n + k] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) wk -= h[i] * vv[i];
+    w[k] = wk;
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) acc[i] += vv[i] * wk;
+    acc[NVB] += wk * wk;
+  }
+  if (grid_reduce<NVB + 1>(acc, partials, ticket, tot) && threadIdx.x == 0) {
+    for (int i = 0; i < nv; ++i) h2[i] = tot[i];
+    // misc[0] = <w, w> before (k_gs_dots) -> norm^2 of the orthogonalised vector; misc[5] = refine?
+    const bool refine = tot[NVB] < 0.5 * misc[0];
+    misc[0] = tot[NVB];
+    misc[5] = refine ? 1.0 : 0.0;
+  }
+}
+
+template <int NVB>
+__global__ void __launch_bounds__(FB_TPB)
+k_gs_refine(long long n, int nv, const double* __restrict__ V, const double* __restrict__ h2,
+            double* __restrict__ w, double* partials, unsigned* ticket, double* misc,
+            const int* __restrict__ flags) {
+  if (flags[0] || misc[5] == 0.0) return;
+  double acc[1] = {0.0}, tot[1], h[NVB];
+#pragma unroll
+  for (int i = 0; i < NVB; ++i) h[i] = i < nv ? h2[i] : 0.0;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
+       k += (long long)gridDim.x * blockDim.x) {
+    double wk = w[k];
+    double vv[NVB];
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * n + k] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NVB; ++i) wk -= h[i] * vv[i];
+    w[k] = wk;
+    acc[0] += wk * wk;
+  }
+  if (grid_reduce<1>(acc, partials, ticket, tot) && threadIdx.x == 0) misc[0] = tot[0];
 }
 
 __global__ void k_gmres_givens(int j, double* sc, int* flags) {
@@ -993,7 +1083,8 @@ __global__ void k_gmres_givens(int j, double* sc, int* flags) {
   double* H = sc + GM_H;
   double* cs = sc + GM_CS; double* sn = sc + GM_SN; double* g = sc + GM_G;
   double* col = H + (size_t)j * (GM_M + 1);
-  for (int i = 0; i <= j; ++i) col[i] = sc[GM_HD1 + i] + sc[GM_HD2 + i];
+  const bool refined = sc[GM_MISC + 5] != 0.0;   // second Gram-Schmidt pass applied (k_gs_refine)
+  for (int i = 0; i <= j; ++i) col[i] = sc[GM_HD1 + i] + (refined ? sc[GM_HD2 + i] : 0.0);
   const double hn = sqrt(sc[GM_MISC + 0]);
   col[j + 1] = hn;
   sc[GM_MISC + 1] = hn > 0.0 ? 1.0 / hn : 0.0;
@@ -1089,7 +1180,7 @@ __global__ void k_tri_extract(DevSpec S, const double* __restrict__ J, double* _
     for (int s = 0; s < ns; ++s)
       for (int j = 0; j < S.pair_nc[s]; ++j)
         out[(pos * ns + s) * ns + S.pair_cs[S.pair_pp[s] + j]] =
-            J[base + (long long)deg * S.pair_pp[s] + (long long)k * S.pair_nc[s] + j];
+            J[base + (long long)k * S.npairs + S.pair_pp[s] + j];
   }
 }
 
@@ -1399,12 +1490,28 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     FB_LAUNCH(ctx, k_gmres_begin, 1, 1, 0, sc, ctx->d_flags, thr);
     FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, r, sc + GM_MISC + 1, V, (const int*)nullptr);
     for (int j = 0; j < GM_M; ++j) {
-      if ((rc = fbi_spmv(ctx, J, V + (size_t)j * N, z))) return rc;
-      FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, z, w, ctx->d_flags);
-      FB_LAUNCH(ctx, k_multidot, gv, FB_TPB, 0, N, j + 1, V, w, ctx->d_red, ctx->d_ticket, sc + GM_HD1, ctx->d_flags);
-      FB_LAUNCH(ctx, k_multiaxpy_norm, gv, FB_TPB, 0, N, j + 1, V, sc + GM_HD1, w, ctx->d_red, ctx->d_ticket, sc + GM_MISC, ctx->d_flags);
-      FB_LAUNCH(ctx, k_multidot, gv, FB_TPB, 0, N, j + 1, V, w, ctx->d_red, ctx->d_ticket, sc + GM_HD2, ctx->d_flags);
-      FB_LAUNCH(ctx, k_multiaxpy_norm, gv, FB_TPB, 0, N, j + 1, V, sc + GM_HD2, w, ctx->d_red, ctx->d_ticket, sc + GM_MISC, ctx->d_flags);
+      // w = M^-1 J V_j: SpMV with the block-Jacobi application fused into its epilogue
+      if (spmv_blk_ok(S)) {
+        if ((rc = spmv_blk_launch<true>(ctx, J, V + (size_t)j * N, w, ctx->d_flags))) return rc;
+      } else {
+        if ((rc = fbi_spmv(ctx, J, V + (size_t)j * N, z))) return rc;
+        FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, z, w, ctx->d_flags);
+      }
+      const int nv = j + 1;
+#define FB_GS_CASE(NVB)                                                                                        \
+  {                                                                                                            \
+    FB_LAUNCH(ctx, k_gs_dots<NVB>, gv, FB_TPB, 0, N, nv, V, w, ctx->d_red, ctx->d_ticket, sc + GM_HD1,         \
+              sc + GM_MISC, ctx->d_flags);                                                                     \
+    FB_LAUNCH(ctx, k_gs_update<NVB>, gv, FB_TPB, 0, N, nv, V, sc + GM_HD1, w, ctx->d_red, ctx->d_ticket,       \
+              sc + GM_HD2, sc + GM_MISC, ctx->d_flags);                                                        \
+    FB_LAUNCH(ctx, k_gs_refine<NVB>, gv, FB_TPB, 0, N, nv, V, sc + GM_HD2, w, ctx->d_red, ctx->d_ticket,       \
+              sc + GM_MISC, ctx->d_flags);                                                                     \
+  }
+      if (nv <= 8) FB_GS_CASE(8)
+      else if (nv <= 16) FB_GS_CASE(16)
+      else if (nv <= 24) FB_GS_CASE(24)
+      else FB_GS_CASE(32)
+#undef FB_GS_CASE
       FB_LAUNCH(ctx, k_gmres_givens, 1, 1, 0, j, sc, ctx->d_flags);
       FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, w, sc + GM_MISC + 1, V + (size_t)(j + 1) * N, ctx->d_flags);
       if (j % 10 == 9 || j == GM_M - 1) {
@@ -1723,14 +1830,14 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
         const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
         const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
-        const int start = (int)((long long)r0 * S.npairs + (long long)deg * pp - e0);
+        const int start = (int)((long long)r0 * S.npairs + pp - e0);   // block layout: entry (k, j) at start + k * npairs + j
         rstart[rr] = start;
         rlen[rr] = deg * nc;
         rbst[rr] = r0 - S.rowptr[v0];
         if (!part)
           for (int e = 0; e < deg * nc; ++e) {
             const int k = e / nc, j = e - k * nc;
-            scols[start + e] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
+            scols[start + k * S.npairs + j] = S.colidx[r0 + k] * ns + S.pair_cs[pp + j];
           }
       }
     }
@@ -1887,12 +1994,14 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
           const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
           for (int e = gl; e < n; e += G) {
             const int k = e / nc, j = e - k * nc;
-            sum += svals[a0 + e] * su[(int)slcol[bs + k] * ns + S.pair_cs[pp + j]];
+            sum += svals[a0 + k * S.npairs + j] * su[(int)slcol[bs + k] * ns + S.pair_cs[pp + j]];
           }
         }
       } else if (staged) {
         ri = __ldcg(A.r + row); ui = __ldcg(uvec + row);
         const int a0 = rstart[rr], n = rlen[rr];
+        const int ncr = ns == 1 ? 1 : S.pair_nc[rr - (rr / ns) * ns];
+        auto eofs = [&](int e) { return ns == 1 ? e : (e / ncr) * S.npairs + (e - (e / ncr) * ncr); };
         for (int eb = gl; eb < n; eb += 8 * G) {
           double uv[8];
 #pragma unroll
@@ -1900,7 +2009,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
             const int e = eb + q * G;
             uv[q] = 0.0;
             if (e < n) {
-              const int c = scols[a0 + e];
+              const int c = scols[a0 + eofs(e)];
               if (c < n_own_dofs) uv[q] = __ldcg(uvec + c);
               else if (!ll_load(halo + 2 * (c - n_own_dofs), utag, A.bar, uv[q])) failed = 1;
             }
@@ -1908,7 +2017,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int e = eb + q * G;
-            if (e < n) sum += svals[a0 + e] * uv[q];
+            if (e < n) sum += svals[a0 + eofs(e)] * uv[q];
           }
         }
       } else {
@@ -1917,7 +2026,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
         const long long v = v0 + vl;
         const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
         const int nc = S.pair_nc[sp], pp = S.pair_pp[sp];
-        const double* __restrict__ vals = A.J + (long long)r0 * S.npairs + (long long)deg * pp;
+        const double* __restrict__ vals = A.J + (long long)r0 * S.npairs + pp;   // entry (k, j) at k * npairs + j
         const int n = deg * nc;
         for (int e = gl; e < n; e += G) {
           const int k = e / nc, j = e - k * nc;
@@ -1925,7 +2034,7 @@ k_dcg_persistent(DevSpec S, CgArgs A, PeerArgs P) {
           double uc;
           if (c < n_own_dofs) uc = __ldcg(uvec + c);
           else if (!ll_load(halo + 2 * (c - n_own_dofs), utag, A.bar, uc)) failed = 1;
-          sum += vals[e] * uc;
+          sum += vals[(long long)k * S.npairs + j] * uc;
         }
       }
 #pragma unroll
