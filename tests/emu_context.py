@@ -130,3 +130,32 @@ class EmuSolver:
         x = np.ascontiguousarray(x, dtype=np.float64)
         self.check(self.lib.fb_spmv(self.h, _p(Jvals), _p(x), _p(y)))
         return y
+
+
+def _linear_solve(self, Jvals, b, ksp=2, rtol=1e-12, max_it=2000):
+    """fb_linear_solve on the emulated device (GMRES / tridiagonal; the persistent CG is a
+    cooperative launch and is not emulated)."""
+    y = np.zeros(self.n_dofs)
+    its, rel = C.c_int(0), C.c_double(0.0)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    rc = self.lib.fb_linear_solve(self.h, _p(Jvals), _p(b), _p(y), ksp, 0, C.c_double(rtol), C.c_double(0.0),
+                                  max_it, C.byref(its), C.byref(rel))
+    self.check(rc)
+    return y, its.value, rel.value, rc
+
+
+def _newton(self, u, un, atol, rtol, stol=1.49e-10, max_it=30, ksp=2, ksp_rtol=1e-12):
+    self.push_state()
+    u = np.ascontiguousarray(u, dtype=np.float64).copy()
+    un = np.ascontiguousarray(un, dtype=np.float64)
+    n_its, reason, lin = C.c_int(0), C.c_int(0), C.c_int(0)
+    fnorm = C.c_double(0.0)
+    rc = self.lib.fb_newton_solve(self.h, _p(u), _p(un), C.c_double(atol), C.c_double(rtol), C.c_double(stol),
+                                  max_it, ksp, 0, C.c_double(ksp_rtol), 20000, C.byref(n_its), C.byref(reason),
+                                  C.byref(fnorm), C.byref(lin))
+    self.check(rc)
+    return u, n_its.value, reason.value, lin.value
+
+
+EmuSolver.linear_solve = _linear_solve
+EmuSolver.newton = _newton
