@@ -519,6 +519,12 @@ class B200NewtonSolver:
     def surface_flux(self, species_index, surf_id):
         out = C.c_double(0.0)
         ctx = self.ctx
+        spec = self.spec
+        if any(int(spec.diff_slot[tag, species_index]) >= len(spec.diff_energies) for tag in range(len(spec.vol_ids))):
+            # the reference weights the gradient with material.D itself (define_D_global,
+            # hydrogen_transport_problem.py:497-502); the device kernel only knows Arrhenius laws
+            raise NotImplementedError("SurfaceFlux with a user-defined Material.D is not implemented on the "
+                                      "B200 backend (use a CustomQuantity with D_<species>)")
         Tn, Tc = C.c_void_p(), 0.0
         if isinstance(self._D_T, np.ndarray):
             if self._D_T_dev is None:

@@ -16,7 +16,7 @@ enum {
   S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
   S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW,
   S_VX_INTS, S_VX_CQ_PTR, S_VX_CQ, S_VX_CH_PTR, S_VX_CH, S_VX_JT_PTR, S_VX_JT, S_VX_JT_COEF,
-  S_VX_FT_PTR, S_VX_FT, S_VX_FT_COEF, S_MAX
+  S_VX_FT_PTR, S_VX_FT, S_VX_FT_COEF, S_VX_SP_COMBO, S_VX_SP_PTR, S_VX_SP, S_VX_SP_COEF, S_MAX
 };
 enum {
   I_TDIM = 0, I_NS, I_NVTAGS, I_NSTAGS, I_TRANSIENT, I_TMODE, I_NPROGRAMS, I_NSCALARS, I_NFIELDS,
@@ -229,89 +229,81 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     if (dg > S.maxdeg) S.maxdeg = dg;
   }
   auto magic = [](int d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); };
-  S.vx_m_ns = magic(S.ns); S.vx_m_np = magic(S.npairs); S.vx_m_nf = magic(S.n_factors); S.vx_m_rec = 0u;
-  // ---- vertex-block assembly tables (assemble_vtx.cuh) --------------------------------------
+  S.vx_m_ns = magic(S.ns); S.vx_m_np = magic(S.npairs); S.vx_m_nf = magic(S.n_factors);
+  // ---- channel assembly tables (assemble_edge.cuh) ---------------------------------------------
   S.vx_on = 0;
-  if (secs[S_VX_INTS].id == S_VX_INTS && S.v2c_slot != nullptr && !getenv("FB_NO_VTX")) {
+  if (secs[S_VX_INTS].id == S_VX_INTS && S.v2c_slot != nullptr && S.maxdeg < 255 && !getenv("FB_NO_VTX")) {
     const int* vi = (const int*)(blob + secs[S_VX_INTS].offset);
     S.vx_nsym = vi[1]; S.vx_nsym3 = vi[2]; S.vx_rec = vi[3]; S.vx_nbw = vi[4]; S.vx_nch = vi[5];
-    if (vi[6] != S.n_factors) return fb_fail(ctx, "vertex tables: factor count mismatch");
+    if (vi[6] != S.n_factors) return fb_fail(ctx, "channel tables: factor count mismatch");
+    S.vx_nstat = vi[7]; S.vx_ndyn = vi[8]; S.vx_nts = vi[9]; S.vx_ncombo = vi[10];
     UP(S_PAIR_ROW, 0, pair_row); UP(S_VX_CQ_PTR, 0, vx_cq_ptr); UP(S_VX_CQ, 0, vx_cq);
+    UP(S_VX_SP_COMBO, 0, vx_sp_combo); UP(S_VX_SP_PTR, 0, vx_sp_ptr); UP(S_VX_SP, 0, vx_sp); UP(S_VX_SP_COEF, 1, vx_sp_coef);
     auto sec_i = [&](int id) { return (const int*)(blob + secs[id].offset); };
     auto sec_d = [&](int id) { return (const double*)(blob + secs[id].offset); };
-    const int nvt = S.n_vtags, ns = S.ns, np = S.npairs;
-    const int* chp = sec_i(S_VX_CH_PTR); const int* ch = sec_i(S_VX_CH);
+    const int ns = S.ns, np = S.npairs, nch = S.vx_nch;
+    const int* ch = sec_i(S_VX_CH);
     const int* jtp = sec_i(S_VX_JT_PTR); const int* jt = sec_i(S_VX_JT); const double* jtc = sec_d(S_VX_JT_COEF);
     const int* ftp = sec_i(S_VX_FT_PTR); const int* ft = sec_i(S_VX_FT); const double* ftc = sec_d(S_VX_FT_COEF);
-    if (S.vx_nch > 255 || np > 255) return fb_fail(ctx, "vertex tables: too many channels / species pairs");
-    // lanes per neighbour in the row expansion: as many as fit next to maxdeg neighbours
-    int lpk = 1;
-    while (lpk * 2 * S.maxdeg <= 32 && lpk * 2 <= np) lpk *= 2;
-    S.vx_lpk = lpk;
+    if (secs[S_VX_CH].count != 8LL * nch && !(nch == 1 && secs[S_VX_CH].count == 0))
+      return fb_fail(ctx, "channel tables: channel list size mismatch");
+    if (nch > 255 || np > 255) return fb_fail(ctx, "channel tables: too many channels / species pairs");
+    S.vx_nft = ftp[ns]; S.vx_njt = jtp[np];
     std::vector<int> itab;
     std::vector<double> dtab;
-    S.vx_o_chptr = (int)itab.size(); itab.insert(itab.end(), chp, chp + nvt + 1);
-    S.vx_o_ch = (int)itab.size(); itab.insert(itab.end(), ch, ch + 4 * chp[nvt]);
-    S.vx_o_ftptr = (int)itab.size(); itab.insert(itab.end(), ftp, ftp + nvt * ns + 1);
-    S.vx_o_ft = (int)itab.size(); itab.insert(itab.end(), ft, ft + 3 * ftp[nvt * ns]);
-    S.vx_o_ftc = (int)dtab.size(); dtab.insert(dtab.end(), ftc, ftc + ftp[nvt * ns]);
-    S.vx_nft_max = 1;
-    for (int t = 0; t < nvt; ++t) S.vx_nft_max = std::max(S.vx_nft_max, ftp[(t + 1) * ns] - ftp[t * ns]);
-    // expansion lists: per tag, lpk sub-lists of (pair | channel << 8 | flags) of equal length;
-    // the entries of a pair are consecutive and the last one carries the STORE flag
-    std::vector<int> xhdr(2 * nvt), xl;
-    std::vector<double> xc;
-    for (int t = 0; t < nvt; ++t) {
-      std::vector<std::vector<int>> sub(lpk);   // pairs of every sub-list
-      std::vector<long long> load(lpk, 0);
-      std::vector<int> order(np);
-      for (int p = 0; p < np; ++p) order[p] = p;
-      auto cnt = [&](int p) { return std::max(1, jtp[t * np + p + 1] - jtp[t * np + p]); };
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt(a) > cnt(b); });
-      for (int p : order) {
-        int best = 0;
-        for (int h = 1; h < lpk; ++h) if (load[h] < load[best]) best = h;
-        sub[best].push_back(p);
-        load[best] += cnt(p);
+    S.vx_o_ch = (int)itab.size(); itab.insert(itab.end(), ch, ch + secs[S_VX_CH].count);
+    S.vx_o_ftptr = (int)itab.size(); itab.insert(itab.end(), ftp, ftp + ns + 1);
+    S.vx_o_ft = (int)itab.size(); itab.insert(itab.end(), ft, ft + 3 * S.vx_nft);
+    S.vx_o_ftc = (int)dtab.size(); dtab.insert(dtab.end(), ftc, ftc + S.vx_nft);
+    S.vx_o_jtptr = (int)itab.size(); itab.insert(itab.end(), jtp, jtp + np + 1);
+    S.vx_o_jt = (int)itab.size(); itab.insert(itab.end(), jt, jt + 2 * S.vx_njt);
+    S.vx_o_jtc = (int)dtab.size(); dtab.insert(dtab.end(), jtc, jtc + S.vx_njt);
+    S.vx_o_jtpair = (int)itab.size();
+    for (int p = 0; p < np; ++p)
+      for (int e = jtp[p]; e < jtp[p + 1]; ++e) itab.push_back(p);
+    // solution-dependent channels grouped by the edge tensor they contract: (channel, factor column)
+    S.vx_o_dynptr = (int)itab.size();
+    {
+      std::vector<int> ptr(S.vx_nts + 1, 0), lst;
+      for (int ts = 0; ts < S.vx_nts; ++ts) {
+        for (int c = S.vx_nstat; c < nch; ++c)
+          if (ch[8 * c + 5] == ts) { lst.push_back(c); lst.push_back(ch[8 * c + 3]); }
+        ptr[ts + 1] = (int)lst.size() / 2;
       }
-      int Lx = 1;
-      for (int h = 0; h < lpk; ++h) Lx = std::max<long long>(Lx, load[h]);
-      xhdr[2 * t] = (int)xl.size(); xhdr[2 * t + 1] = Lx;
-      for (int h = 0; h < lpk; ++h) {
-        std::sort(sub[h].begin(), sub[h].end());
-        int n = 0;
-        for (int p : sub[h]) {
-          const int a0 = jtp[t * np + p], a1 = jtp[t * np + p + 1];
-          if (a0 == a1) { xl.push_back(p | (1 << 17)); xc.push_back(0.0); ++n; continue; }
-          for (int e = a0; e < a1; ++e) {
-            int ent = p | (jt[2 * e] << 8);
-            if (jt[2 * e + 1] & 1) ent |= 1 << 16;
-            if (e == a1 - 1) ent |= 1 << 17;
-            xl.push_back(ent); xc.push_back(jtc[e]); ++n;
-          }
-        }
-        for (; n < Lx; ++n) { xl.push_back(0); xc.push_back(0.0); }
-      }
+      if ((int)lst.size() / 2 != S.vx_ndyn) return fb_fail(ctx, "channel tables: dynamic channels without an edge tensor");
+      itab.insert(itab.end(), ptr.begin(), ptr.end());
+      S.vx_o_dyn = (int)itab.size();
+      itab.insert(itab.end(), lst.begin(), lst.end());
     }
-    S.vx_o_xlhdr = (int)itab.size(); itab.insert(itab.end(), xhdr.begin(), xhdr.end());
-    S.vx_o_xl = (int)itab.size(); itab.insert(itab.end(), xl.begin(), xl.end());
-    S.vx_o_xlc = (int)dtab.size(); dtab.insert(dtab.end(), xc.begin(), xc.end());
     S.vx_itab_n = (int)itab.size(); S.vx_dtab_n = (int)dtab.size();
     if ((rc = fb_upload(ctx, &S.vx_itab, itab.data(), itab.size()))) return rc;
     if ((rc = fb_upload(ctx, &S.vx_dtab, dtab.data(), dtab.size()))) return rc;
-    auto even2mod4 = [](int n) { int m = (n + 1) & ~1; while (m % 4 != 2) m += 2; return m; };
-    S.vx_nchp = even2mod4(S.vx_nch);
-    S.vx_recp = S.vx_rec | 1;
-    S.vx_rbp = np | 1;
-    S.vx_m_rec = magic(S.vx_rec);
-    double* rec = nullptr;
-    if ((rc = fb_alloc(ctx, &rec, (size_t)S.n_cells * S.vx_rec))) return rc;
-    S.cellrec = rec;
+    S.vx_nsp = (S.vx_nstat + 1) & ~1;
+    S.vx_ndp = (S.vx_ndyn + 1) & ~1;
+    S.vx_m_nsp = magic(S.vx_nsp); S.vx_m_ndp = magic(S.vx_ndp);
+    S.nnzb = ctx->nnzb;
+    double* p = nullptr;
+    if ((rc = fb_alloc(ctx, &p, (size_t)S.n_cells * S.vx_rec))) return rc;
+    S.cellrec = p;
+    if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_nsp))) return rc;
+    S.et_stat = p;
+    if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_ndp))) return rc;
+    FB_CHECK(ctx, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)ctx->nnzb * S.vx_ndp, ctx->stream));
+    S.et_dyn = p;
+    if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_nts))) return rc;
+    S.et_tv = p;
+    if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_nts))) return rc;
+    S.et_tw = p;
     unsigned* vinfo = nullptr;
     if ((rc = fb_alloc(ctx, &vinfo, (size_t)S.n_vertices))) return rc;
     FB_CHECK(ctx, cudaMemsetAsync(vinfo, 0, sizeof(unsigned) * S.n_vertices, ctx->stream));
     S.vinfo = vinfo;
+    S.et_tz_total = 0; S.et_tz = nullptr; S.et_tzptr = nullptr; S.et_tzslot = nullptr;
+    if (S.vx_nts > 0 && (rc = fbi_et_symbolic(ctx))) return rc;
     S.vx_on = 1;
+    // the Krylov solvers work on the channel operator itself when it is the smaller format
+    ctx->op_channels = (S.vx_nsp + S.vx_ndp < np) && !ctx->tridiag && !ctx->facet_u_terms &&
+                       !getenv("FB_NO_CHANNEL_OP");
   }
   S.n_udiff = 0;
   if (secs[S_DIFF_UPROG].id == S_DIFF_UPROG) {

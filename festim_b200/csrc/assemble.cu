@@ -30,7 +30,7 @@
 #include "fb_internal.cuh"
 #include "program.cuh"
 #include "assemble_kernels.cuh"
-#include "assemble_vtx.cuh"
+#include "assemble_edge.cuh"
 #include "reduce.cuh"
 
 // ---------------------------------------------------------------------------
@@ -63,11 +63,31 @@ __global__ void k_vinfo_rows(DevSpec S, unsigned* __restrict__ vinfo) { fb_vinfo
 __global__ void k_vinfo_cols(DevSpec S, unsigned* __restrict__ vinfo) { fb_vinfo_cols_body(S, vinfo); }
 
 template <int DIM>
+__global__ void k_et_symbolic(DevSpec S, int mode, int* __restrict__ width, const long long* __restrict__ tzptr,
+                              unsigned char* __restrict__ tzslot, int* __restrict__ err) {
+  fb_et_symbolic_body<DIM>(S, mode, width, tzptr, tzslot, err);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_et_setup(DevSpec S, double* __restrict__ stat, double* __restrict__ tv, double* __restrict__ tw,
+           double* __restrict__ tz) {
+  fb_et_setup_body<DIM>(S, stat, tv, tw, tz);
+}
+
+template <int G>
 __global__ void __launch_bounds__(256)
-k_assemble_vtx(DevSpec S, const double* __restrict__ u, const double* __restrict__ un,
-               double* __restrict__ F, double* __restrict__ J, int flags) {
-  extern __shared__ double fb_vtx_smem[];
-  fb_assemble_vtx_body<DIM>(S, u, un, F, J, flags, fb_vtx_smem);
+k_assemble_edge(DevSpec S, const double* __restrict__ u, const double* __restrict__ un, double* __restrict__ F,
+                double* __restrict__ dyn, int flags) {
+  extern __shared__ double fb_et_smem[];
+  fb_assemble_edge_body<G>(S, u, un, F, dyn, flags, fb_et_smem);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_et_expand(DevSpec S, double* __restrict__ J) {
+  extern __shared__ double fb_et_smem[];
+  fb_et_expand_body<G>(S, J, fb_et_smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -161,7 +181,11 @@ static int update_coeffs_dim(fb_ctx* ctx) {
       FB_LAUNCH(ctx, k_cell_coeffs<DIM>, gc, B, 0, S, ctx->d_dbar);
     }
   }
-  if (S.vx_on) FB_LAUNCH(ctx, k_cell_records<DIM>, gc, B, 0, S, (double*)S.cellrec);
+  if (S.vx_on) {
+    FB_LAUNCH(ctx, k_cell_records<DIM>, gc, B, 0, S, (double*)S.cellrec);
+    FB_LAUNCH(ctx, k_et_setup<DIM>, (unsigned)((S.n_owned + B - 1) / B), B, 0, S, (double*)S.et_stat, (double*)S.et_tv,
+              (double*)S.et_tw, (double*)S.et_tz);
+  }
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_load, 0, sizeof(double) * S.n_dofs, ctx->stream));
   if (S.n_vterms > 0) {
     if (ctx->have_jit) {
@@ -208,32 +232,112 @@ int fbi_update_coeffs(fb_ctx* ctx) {
   return fb_fail(ctx, "bad tdim");
 }
 
+// lanes per vertex of the row kernels: the smallest power of two that covers the longest row
+static int et_group(const DevSpec& S) {
+  int G = 4;
+  while (G < 32 && G < S.maxdeg) G *= 2;
+  if (getenv("FB_ET_G")) G = atoi(getenv("FB_ET_G"));
+  return G;
+}
+
+// which = 0: k_assemble_edge, 1: k_et_expand
+static int et_launch(fb_ctx* ctx, int which, const double* u, const double* un, double* F, double* J, int flags) {
+  DevSpec& S = ctx->S;
+  const EtLayout L = fb_et_layout(S, which == 0);
+  const int G = et_group(S);
+  int smem_max = 0;
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+  int tpb = 256;
+  if (getenv("FB_ET_TPB")) tpb = atoi(getenv("FB_ET_TPB"));
+  while (tpb > G && (size_t)(L.grp0 + (size_t)(tpb / G) * L.per_grp) * 8 > (size_t)smem_max) tpb /= 2;
+  const int gpb = tpb / G;
+  const size_t smem = (size_t)(L.grp0 + (size_t)gpb * L.per_grp) * 8;
+  if (gpb < 1 || smem > (size_t)smem_max) return fb_fail(ctx, "channel assembly: a block row does not fit in shared memory");
+  const unsigned grid = (unsigned)((S.n_owned + gpb - 1) / gpb);
+  double* dyn = (double*)S.et_dyn;
+#define FB_ET_CASE(GG)                                                                                          \
+  if (which == 0) {                                                                                             \
+    FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_assemble_edge<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_assemble_edge<GG><<<grid, tpb, smem, ctx->stream>>>(S, u, un, F, dyn, flags);                             \
+  } else {                                                                                                      \
+    FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_et_expand<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_et_expand<GG><<<grid, tpb, smem, ctx->stream>>>(S, J);                                                     \
+  }
+  switch (G) {
+    case 4: FB_ET_CASE(4) break;
+    case 8: FB_ET_CASE(8) break;
+    case 16: FB_ET_CASE(16) break;
+    default: FB_ET_CASE(32) break;
+  }
+#undef FB_ET_CASE
+  ctx->launches++;
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+int fbi_expand(fb_ctx* ctx, double* J) {
+  if (!ctx->S.vx_on) return fb_fail(ctx, "no channel operator to expand");
+  return et_launch(ctx, 1, nullptr, nullptr, nullptr, J, 0);
+}
+
+// structure of the edge tensor (once per mesh + spec): widths, prefix sum on the host, slots
+template <int DIM>
+static int et_symbolic_dim(fb_ctx* ctx) {
+  DevSpec& S = ctx->S;
+  const long long nv = S.n_vertices;
+  int* d_w = nullptr;
+  int* d_err = nullptr;
+  int rc;
+  if ((rc = fb_alloc(ctx, &d_w, (size_t)nv + 1))) return rc;
+  d_err = d_w + nv;
+  FB_CHECK(ctx, cudaMemsetAsync(d_w, 0, sizeof(int) * (nv + 1), ctx->stream));
+  const unsigned g = (unsigned)((nv + 127) / 128);
+  const long long keep_owned = S.n_owned;
+  S.n_owned = nv;
+  FB_LAUNCH(ctx, k_et_symbolic<DIM>, g, 128, 0, S, 0, d_w, (const long long*)nullptr, (unsigned char*)nullptr, d_err);
+  std::vector<int> w((size_t)nv + 1);
+  FB_CHECK(ctx, cudaMemcpyAsync(w.data(), d_w, sizeof(int) * (nv + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (w[nv]) { S.n_owned = keep_owned; return fb_fail(ctx, "edge tensor: more than 64 common neighbours on an edge"); }
+  std::vector<long long> ptr((size_t)nv + 1, 0);
+  for (long long v = 0; v < nv; ++v)
+    ptr[v + 1] = ptr[v] + (long long)w[v] * (ctx->h_rowptr[v + 1] - ctx->h_rowptr[v]);
+  S.et_tz_total = ptr[nv];
+  if ((rc = fb_upload(ctx, &S.et_tzptr, ptr.data(), ptr.size()))) return rc;
+  unsigned char* slots = nullptr;
+  if ((rc = fb_alloc(ctx, &slots, (size_t)S.et_tz_total + 1))) return rc;
+  FB_CHECK(ctx, cudaMemsetAsync(slots, 0xff, (size_t)S.et_tz_total + 1, ctx->stream));
+  FB_LAUNCH(ctx, k_et_symbolic<DIM>, g, 128, 0, S, 1, d_w, S.et_tzptr, slots, d_err);
+  S.et_tzslot = slots;
+  double* tz = nullptr;
+  if ((rc = fb_alloc(ctx, &tz, (size_t)S.et_tz_total * S.vx_nts + 1))) return rc;
+  S.et_tz = tz;
+  S.n_owned = keep_owned;
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+int fbi_et_symbolic(fb_ctx* ctx) {
+  switch (ctx->S.tdim) {
+    case 1: return et_symbolic_dim<1>(ctx);
+    case 2: return et_symbolic_dim<2>(ctx);
+    case 3: return et_symbolic_dim<3>(ctx);
+  }
+  return fb_fail(ctx, "bad tdim");
+}
+
 template <int DIM>
 static int assemble_dim(fb_ctx* ctx, const double* u, const double* un, double* F, double* J, int flags) {
   DevSpec& S = ctx->S;
   const unsigned B = 128;
   const unsigned gn = (unsigned)((S.n_vertices + B - 1) / B);
   if (S.vx_on) {
-    // warp per vertex, edge channels and the block row in shared memory (assemble_vtx.cuh)
-    const VtxLayout L = fb_vtx_layout<DIM>(S);
-    int smem_max = 0, smem_sm = 0;
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
-    int wpb = 0, best = 0;
-    for (int w = 8; w >= 1; --w) {
-      const size_t bytes = (size_t)(L.warp0 + (size_t)w * L.per_warp) * 8;
-      if (bytes > (size_t)smem_max) continue;
-      int blocks = (int)((size_t)smem_sm / (bytes + 1024));
-      if (blocks * w * 32 > 2048) blocks = 2048 / (w * 32);
-      if (blocks * w > best) { best = blocks * w; wpb = w; }
-    }
-    if (getenv("FB_VTX_WPB")) wpb = atoi(getenv("FB_VTX_WPB"));
-    if (wpb < 1) return fb_fail(ctx, "vertex-block assembly: a block row does not fit in shared memory");
-    const size_t smem = (size_t)(L.warp0 + (size_t)wpb * L.per_warp) * 8;
-    FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_assemble_vtx<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned gr = (unsigned)((S.n_owned + wpb - 1) / wpb);
-    k_assemble_vtx<DIM><<<gr, wpb * 32, smem, ctx->stream>>>(S, u, un, F, J, flags);
-    ctx->launches++;
+    // channel assembly (assemble_edge.cuh): dynamic channel values + residual, then - when the
+    // caller wants the block-CSR values - the expansion of the channel operator
+    int rc = et_launch(ctx, 0, u, un, F, nullptr, flags);
+    if (rc) return rc;
+    if ((flags & FB_ASSEMBLE_J) && J && (rc = et_launch(ctx, 1, nullptr, nullptr, nullptr, J, 0))) return rc;
   } else if (ctx->have_jit) {
     void* args[] = {(void*)&S, (void*)&u, (void*)&un, (void*)&F, (void*)&J, (void*)&flags};
     int rc = jit_launch(ctx, JIT_ASSEMBLE_NODES, gn, B, args);
@@ -261,7 +365,7 @@ static int assemble_dim(fb_ctx* ctx, const double* u, const double* un, double* 
 int fbi_assemble(fb_ctx* ctx, const double* u, const double* un, double* F, double* J, int flags) {
   if (!(ctx->have_mesh && ctx->have_pattern && ctx->have_spec)) return fb_fail(ctx, "context not fully defined");
   if ((flags & FB_ASSEMBLE_F) && !F) return fb_fail(ctx, "F is null");
-  if ((flags & FB_ASSEMBLE_J) && !J) return fb_fail(ctx, "J is null");
+  if ((flags & FB_ASSEMBLE_J) && !J && !ctx->S.vx_on) return fb_fail(ctx, "J is null");
   if (!un) un = u;
   switch (ctx->S.tdim) {
     case 1: return assemble_dim<1>(ctx, u, un, F, J, flags);

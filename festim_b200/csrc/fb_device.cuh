@@ -67,18 +67,32 @@ struct DevSpec {
   const double* fac_a0;
   const int* fac_species;
   const double* fac_coef;
-  // vertex-block assembly (assemble_vtx.cuh): per-cell record, channels, coefficient tables
-  int vx_on, vx_nsym, vx_nsym3, vx_rec, vx_nbw, vx_nch, vx_nchp, vx_recp, vx_rbp, vx_lpk, vx_nft_max;
+  // channel assembly (assemble_edge.cuh): per-cell record, channels, coefficient tables, edge
+  // tensors and the channel operator (static / solution-dependent channel values per edge)
+  int vx_on, vx_nsym, vx_nsym3, vx_rec, vx_nbw, vx_nch, vx_nstat, vx_ndyn, vx_nts, vx_nsp, vx_ndp;
+  int vx_ncombo, vx_nft, vx_njt;
   int vx_itab_n, vx_dtab_n;   // sizes of the block-shared tables copied to shared memory
-  int vx_o_chptr, vx_o_ch, vx_o_ftptr, vx_o_ft, vx_o_xlhdr, vx_o_xl;   // offsets into itab
-  int vx_o_ftc, vx_o_xlc;                                               // offsets into dtab
-  unsigned vx_m_ns, vx_m_nf, vx_m_np, vx_m_rec;   // ceil(2^32 / d) for d = ns, n_factors, npairs, vx_rec
+  int vx_o_ch, vx_o_ftptr, vx_o_ft, vx_o_jtptr, vx_o_jt, vx_o_jtpair, vx_o_dynptr, vx_o_dyn;   // offsets into itab
+  int vx_o_ftc, vx_o_jtc;                                                                       // offsets into dtab
+  unsigned vx_m_ns, vx_m_nf, vx_m_np, vx_m_nsp, vx_m_ndp;   // ceil(2^32 / d) for d = ns, n_factors, npairs, nsp, ndp
   const int* vx_cq_ptr;       // [n_vtags+1] cell-record quantities per tag
   const int* vx_cq;           // [n*4] kind, index, rule, offset in the record
-  const int* vx_itab;         // channel / residual / expansion tables (ints)
+  const int* vx_itab;         // channel / residual / Jacobian tables (ints)
   const double* vx_dtab;      // their coefficients
+  const int* vx_sp_combo;     // [ncombo*2] (channel, column species) products the SpMV accumulates
+  const int* vx_sp_ptr;       // [ns+1]
+  const int* vx_sp;           // [n*2] (combo, flag) per row species
+  const double* vx_sp_coef;
   const double* cellrec;      // [n_cells][vx_rec]
   const unsigned* vinfo;      // per vertex: Dirichlet species mask (bits 0-15), any Dirichlet column (bit 16)
+  long long nnzb, et_tz_total;
+  const double* et_stat;      // [nnzb][vx_nsp] static channel values per edge (per temperature update)
+  const double* et_dyn;       // [nnzb][vx_ndp] solution-dependent channel values per edge (per assembly)
+  const double* et_tv;        // [nts][nnzb]  T_vvw: moment sum_K M3[v,v,w]
+  const double* et_tw;        // [nts][nnzb]  T_vww
+  const double* et_tz;        // [nts][et_tz_total]  T_vwz, z a common neighbour of v and w
+  const long long* et_tzptr;  // [n_owned+1] start of the row's (W_v x deg) slab
+  const unsigned char* et_tzslot;   // [et_tz_total] row slot of z (0xff: padding)
   // per-step data
   const double* scalars;
   double T_const;

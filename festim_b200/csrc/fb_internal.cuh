@@ -48,6 +48,7 @@ struct fb_ctx {
   int n_send = 0;
   int n_programs = 0;                  // compiled expressions of the spec (fb_integrate checks its argument)
   bool symmetric = false;
+  bool op_channels = false;    // Krylov solvers use the channel operator (J == nullptr) instead of block-CSR values
   bool facet_u_terms = false;  // any solution-dependent facet term
   bool generic_u_vterms = false;  // any solution-dependent volume term evaluated point-wise
   bool have_jit = false;
@@ -134,6 +135,8 @@ int fb_upload(fb_ctx* ctx, const T** dst, const T* host, size_t count) {
 // entry points implemented across translation units
 int fbi_update_coeffs(fb_ctx* ctx);
 int fbi_update_vinfo(fb_ctx* ctx);
+int fbi_et_symbolic(fb_ctx* ctx);
+int fbi_expand(fb_ctx* ctx, double* J);
 int fbi_assemble(fb_ctx* ctx, const double* u, const double* un, double* F, double* J, int flags);
 int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y);
 int fbi_norm2(fb_ctx* ctx, const double* x, double* out_host);

@@ -133,6 +133,123 @@ k_spmv_blk(DevSpec S, const double* __restrict__ J, const double* __restrict__ x
   }
 }
 
+// SpMV on the channel operator  J = sum_c A^c (x) B_c  (assemble_edge.cuh): one warp per vertex.
+// Lane l owns the products (channel, column species) l, l+32, ...: t[(c, cs)] = sum_w A^c_vw
+// x_(w,cs) streams 8 bytes per channel and edge - the values of an edge are one short contiguous
+// segment shared by the lanes - and the constant tables B_c are applied once per row in the
+// epilogue.  Strong Dirichlet conditions are applied on the fly (eliminated columns read as
+// zero, identity rows copy x), so the operator equals the block-CSR matrix k_et_expand writes.
+template <int PPL, bool PRECOND>
+__global__ void __launch_bounds__(256)
+k_spmv_ch(DevSpec S, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ dinv,
+          int xs_stride, const int* __restrict__ flags) {
+  extern __shared__ double xs_all[];
+  if (flags && flags[0]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long v = (long long)blockIdx.x * wpb + warp;
+  if (v >= S.n_owned) return;
+  const int ns = S.ns, nc = S.vx_ncombo;
+  double* xs = xs_all + (size_t)warp * xs_stride;
+  double* part = xs + S.maxdeg * ns;            // [ncombo] products, later [ns*ns]
+  const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+  const unsigned vi = S.vinfo[v];
+  const unsigned rowbc = vi & 0xffffu;
+  const bool colbc = (vi >> 16) & 1u;
+  for (int t = lane; t < deg * ns; t += 32) {
+    const int k = fb_fastdiv_u((unsigned)t, S.vx_m_ns), s = t - k * ns;
+    const int w = S.colidx[r0 + k];
+    double val = x[(long long)w * ns + s];
+    if (colbc && ((S.vinfo[w] >> s) & 1u)) val = 0.0;
+    xs[t] = val;
+  }
+  const double* base[PPL];
+  int stride[PPL], cs[PPL];
+  double acc[PPL];
+#pragma unroll
+  for (int q = 0; q < PPL; ++q) {
+    const int p = lane + 32 * q;
+    cs[q] = -1; acc[q] = 0.0; base[q] = nullptr; stride[q] = 0;
+    if (p < nc) {
+      const int chan = S.vx_sp_combo[2 * p];
+      cs[q] = S.vx_sp_combo[2 * p + 1];
+      if (chan < S.vx_nstat) { base[q] = S.et_stat + (long long)r0 * S.vx_nsp + chan; stride[q] = S.vx_nsp; }
+      else { base[q] = S.et_dyn + (long long)r0 * S.vx_ndp + (chan - S.vx_nstat); stride[q] = S.vx_ndp; }
+    }
+  }
+  __syncwarp();
+#pragma unroll 4
+  for (int k = 0; k < deg; ++k) {
+#pragma unroll
+    for (int q = 0; q < PPL; ++q)
+      if (cs[q] >= 0) acc[q] += __ldcs(base[q] + (long long)k * stride[q]) * xs[k * ns + cs[q]];
+  }
+#pragma unroll
+  for (int q = 0; q < PPL; ++q)
+    if (cs[q] >= 0) part[lane + 32 * q] = acc[q];
+  __syncwarp();
+  double sum = 0.0;
+  if (lane < ns) {
+    if ((rowbc >> lane) & 1u) sum = x[v * ns + lane];
+    else
+      for (int e = S.vx_sp_ptr[lane]; e < S.vx_sp_ptr[lane + 1]; ++e) {
+        double coef = S.vx_sp_coef[e];
+        if (S.vx_sp[2 * e + 1] & 1) coef *= S.inv_dt;
+        sum += coef * part[S.vx_sp[2 * e]];
+      }
+  }
+  if (!PRECOND) {
+    if (lane < ns) y[v * ns + lane] = sum;
+    return;
+  }
+  if (ns == 1) {
+    if (lane == 0) y[v] = dinv[v] * sum;
+    return;
+  }
+  __syncwarp();
+  double* ys = xs;   // the staged iterate is dead: reuse
+  if (lane < ns) ys[lane] = sum;
+  __syncwarp();
+  const double* __restrict__ dv = dinv + v * (long long)(ns * ns);
+  for (int t = lane; t < ns * ns; t += 32) {
+    const int r = fb_fastdiv_u((unsigned)t, S.vx_m_ns);
+    part[t] = __ldcs(dv + t) * ys[t - r * ns];
+  }
+  __syncwarp();
+  if (lane < ns) {
+    double z = 0.0;
+    for (int c = 0; c < ns; ++c) z += part[lane * ns + c];
+    y[v * ns + lane] = z;
+  }
+}
+
+template <bool PRECOND>
+static int spmv_ch_launch(fb_ctx* ctx, const double* x, double* y, const int* flags) {
+  const DevSpec& S = ctx->S;
+  const int wpb = 8;
+  const int tail = S.vx_ncombo > S.ns * S.ns ? S.vx_ncombo : S.ns * S.ns;
+  const int stride = (S.maxdeg * S.ns + tail + 1) & ~1;
+  const size_t smem = (size_t)wpb * stride * sizeof(double);
+  const unsigned grid = (unsigned)((S.n_owned + wpb - 1) / wpb);
+  const int ppl = (S.vx_ncombo + 31) / 32;
+#define FB_SPMV_CASE(N)                                                                                   \
+  {                                                                                                       \
+    if (smem > 48 * 1024)                                                                                 \
+      FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_spmv_ch<N, PRECOND>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                     \
+    k_spmv_ch<N, PRECOND><<<grid, wpb * 32, smem, ctx->stream>>>(S, x, y, ctx->d_dinv, stride, flags);      \
+  }
+  if (ppl <= 1) FB_SPMV_CASE(1)
+  else if (ppl == 2) FB_SPMV_CASE(2)
+  else if (ppl == 3) FB_SPMV_CASE(3)
+  else if (ppl == 4) FB_SPMV_CASE(4)
+  else if (ppl <= 8) FB_SPMV_CASE(8)
+  else return fb_fail(ctx, "channel SpMV: more than 256 (channel, species) products");
+#undef FB_SPMV_CASE
+  ctx->launches++;
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
 static int spmv_group(const DevSpec& S) {
   const double len = (S.tdim == 1 ? 3.0 : (S.tdim == 2 ? 7.0 : 15.0)) * S.npairs / S.ns;
   if (len <= 6) return 4;
@@ -175,6 +292,10 @@ static bool spmv_blk_ok(const DevSpec& S) {
 
 int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y) {
   const DevSpec& S = ctx->S;
+  if (!J) {
+    if (!S.vx_on) return fb_fail(ctx, "no channel operator: pass the block-CSR values");
+    return spmv_ch_launch<false>(ctx, x, y, nullptr);
+  }
   if (spmv_blk_ok(S)) return spmv_blk_launch<false>(ctx, J, x, y, nullptr);
   const int G = spmv_group(S);
   const long long threads = S.n_dofs * G;
@@ -260,20 +381,51 @@ __global__ void k_bjacobi_setup(DevSpec S, const double* __restrict__ J, double*
   for (int k = 0; k < deg; ++k)
     if (S.colidx[r0 + k] == v) kself = k;
   const long long base = (long long)r0 * S.npairs;
-  if (ns == 1) {
-    const double d = J[base + kself];
-    if (d == 0.0) flags[2] = 1;
-    dinv[v] = 1.0 / d;
-    return;
-  }
   double A[FB_MAX_NS][FB_MAX_NS], B[FB_MAX_NS][FB_MAX_NS];
-  for (int s = 0; s < ns; ++s)
-    for (int c = 0; c < ns; ++c) {
-      const int jp = S.pair_idx[s * ns + c];
-      A[s][c] = jp < 0 ? 0.0
-                       : J[base + (long long)kself * S.npairs + S.pair_pp[s] + jp];
-      B[s][c] = (s == c) ? 1.0 : 0.0;
+  if (!J) {
+    // channel operator: diagonal block from the channel values of the diagonal edge, strong
+    // Dirichlet rows / columns applied as k_et_expand does
+    const unsigned vi = S.vinfo[v] & 0xffffu;
+    const int* __restrict__ jtp = S.vx_itab + S.vx_o_jtptr;
+    const int* __restrict__ jt = S.vx_itab + S.vx_o_jt;
+    const double* __restrict__ jtc = S.vx_dtab + S.vx_o_jtc;
+    const double* __restrict__ st = S.et_stat + (long long)(r0 + kself) * S.vx_nsp;
+    const double* __restrict__ dy = S.et_dyn + (long long)(r0 + kself) * S.vx_ndp;
+    for (int s = 0; s < ns; ++s)
+      for (int c = 0; c < ns; ++c) { A[s][c] = 0.0; B[s][c] = (s == c) ? 1.0 : 0.0; }
+    for (int p = 0; p < S.npairs; ++p) {
+      const int s = S.pair_row[p], c = S.pair_cs[p];
+      double val = 0.0;
+      for (int e = jtp[p]; e < jtp[p + 1]; ++e) {
+        const int chan = jt[2 * e];
+        double coef = jtc[e];
+        if (jt[2 * e + 1] & 1) coef *= S.inv_dt;
+        val += coef * (chan < S.vx_nstat ? st[chan] : dy[chan - S.vx_nstat]);
+      }
+      if ((vi >> c) & 1u) val = 0.0;
+      if ((vi >> s) & 1u) val = (c == s) ? 1.0 : 0.0;
+      A[s][c] = val;
     }
+    if (ns == 1) {
+      if (A[0][0] == 0.0) flags[2] = 1;
+      dinv[v] = 1.0 / A[0][0];
+      return;
+    }
+  } else {
+    if (ns == 1) {
+      const double d = J[base + kself];
+      if (d == 0.0) flags[2] = 1;
+      dinv[v] = 1.0 / d;
+      return;
+    }
+    for (int s = 0; s < ns; ++s)
+      for (int c = 0; c < ns; ++c) {
+        const int jp = S.pair_idx[s * ns + c];
+        A[s][c] = jp < 0 ? 0.0
+                         : J[base + (long long)kself * S.npairs + S.pair_pp[s] + jp];
+        B[s][c] = (s == c) ? 1.0 : 0.0;
+      }
+  }
   // Gauss-Jordan with partial pivoting
   for (int col = 0; col < ns; ++col) {
     int piv = col;
@@ -1491,7 +1643,9 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, r, sc + GM_MISC + 1, V, (const int*)nullptr);
     for (int j = 0; j < GM_M; ++j) {
       // w = M^-1 J V_j: SpMV with the block-Jacobi application fused into its epilogue
-      if (spmv_blk_ok(S)) {
+      if (!J) {
+        if ((rc = spmv_ch_launch<true>(ctx, V + (size_t)j * N, w, ctx->d_flags))) return rc;
+      } else if (spmv_blk_ok(S)) {
         if ((rc = spmv_blk_launch<true>(ctx, J, V + (size_t)j * N, w, ctx->d_flags))) return rc;
       } else {
         if ((rc = fbi_spmv(ctx, J, V + (size_t)j * N, z))) return rc;
@@ -1557,6 +1711,8 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   *iters = 0;
   *relres = 0.0;
   if (ksp == FB_KSP_AUTO) ksp = ctx->tridiag ? FB_KSP_TRIDIAG : (ctx->symmetric ? FB_KSP_CG : FB_KSP_GMRES);
+  if (!J && !S.vx_on) return fb_fail(ctx, "no channel operator: pass the block-CSR values");
+  if (!J && ksp != FB_KSP_GMRES) return fb_fail(ctx, "the channel operator is solved with GMRES");
   if (ksp == FB_KSP_TRIDIAG) {
     if (!ctx->tridiag) return fb_fail(ctx, "tridiagonal solver needs an interval mesh ordered along x");
     return solve_tridiag(ctx, J, b, y);

@@ -15,8 +15,8 @@ static int ensure_newton_buffers(fb_ctx* ctx) {
   if (!ctx->d_F) {
     if ((rc = fb_alloc(ctx, &ctx->d_F, (size_t)ctx->S.n_dofs))) return rc;
     if ((rc = fb_alloc(ctx, &ctx->d_y, (size_t)ctx->S.n_dofs))) return rc;
-    if ((rc = fb_alloc(ctx, &ctx->d_J, (size_t)ctx->nnzb * ctx->S.npairs))) return rc;
   }
+
   return 0;
 }
 
@@ -65,12 +65,17 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
     if (ctx->tridiag) ksp = FB_KSP_TRIDIAG;
     else ksp = ctx->symmetric ? FB_KSP_CG : FB_KSP_GMRES;
   }
+  // channel operator: the residual pass leaves the solution-dependent channel values behind, so
+  // the Jacobian costs nothing extra and the Krylov solver reads the operator in place (J = null)
+  const bool chan = ctx->op_channels && ksp == FB_KSP_GMRES;
+  if (!chan && !ctx->d_J && (rc = fb_alloc(ctx, &ctx->d_J, (size_t)ctx->nnzb * ctx->S.npairs))) return rc;
+  double* Jv = chan ? nullptr : ctx->d_J;
   int it = 0, lin_total = 0, why = 0;
   double snorm = 0.0, f0 = 1.0, fn = 0.0;
   while (true) {
     {
       PhaseTimer t(ctx, it == 0 ? 1 : 0);
-      rc = fbi_assemble(ctx, u, u_n, ctx->d_F, ctx->d_J, it == 0 ? (FB_ASSEMBLE_F | FB_ASSEMBLE_J) : FB_ASSEMBLE_F);
+      rc = fbi_assemble(ctx, u, u_n, ctx->d_F, Jv, (it == 0 && !chan) ? (FB_ASSEMBLE_F | FB_ASSEMBLE_J) : FB_ASSEMBLE_F);
       if (rc) return rc;
       t.stop();
     }
@@ -81,9 +86,9 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
     why = festim_convergence_test(it, snorm, fn, f0, rtol, atol, stol, max_it);
     if (why) break;
     if (it >= max_it) { why = FB_DIVERGED_MAX_IT; break; }
-    if (it > 0) {
+    if (it > 0 && !chan) {
       PhaseTimer t(ctx, 1);
-      rc = fbi_assemble(ctx, u, u_n, nullptr, ctx->d_J, FB_ASSEMBLE_J);
+      rc = fbi_assemble(ctx, u, u_n, nullptr, Jv, FB_ASSEMBLE_J);
       if (rc) return rc;
       t.stop();
     }
@@ -91,7 +96,7 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
     double relres = 0.0;
     {
       PhaseTimer t(ctx, 2);
-      rc = fbi_linear_solve(ctx, ctx->d_J, ctx->d_F, ctx->d_y, ksp, pc, ksp_rtol, 0.0, ksp_max_it, &lin_its, &relres);
+      rc = fbi_linear_solve(ctx, Jv, ctx->d_F, ctx->d_y, ksp, pc, ksp_rtol, 0.0, ksp_max_it, &lin_its, &relres);
       t.stop();
     }
     lin_total += lin_its;

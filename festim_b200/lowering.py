@@ -40,7 +40,7 @@ MAGIC = 0xFB200_0001
  S_FAC_SPECIES, S_FAC_COEF, S_MONO, S_MONO_COEF, S_FC_PTR, S_FC_MONO, S_FC_SIGN, S_JC_PTR, S_JC,
  S_JC_COEF, S_WTAB, S_WTAB_OFF, S_STRUCT_INTS, S_COMBO, S_PAIR_ROW,
  S_VX_INTS, S_VX_CQ_PTR, S_VX_CQ, S_VX_CH_PTR, S_VX_CH, S_VX_JT_PTR, S_VX_JT, S_VX_JT_COEF,
- S_VX_FT_PTR, S_VX_FT, S_VX_FT_COEF) = range(1, 57)
+ S_VX_FT_PTR, S_VX_FT, S_VX_FT_COEF, S_VX_SP_COMBO, S_VX_SP_PTR, S_VX_SP, S_VX_SP_COEF) = range(1, 61)
 
 # cell-record quantity kinds / channel types / flags of the vertex-block assembly
 # (csrc/assemble_vtx.cuh)
@@ -374,14 +374,21 @@ class KernelSpec:
             return 2 * ns + dev.index(f) if f in dev else g_u(fac_rows[f][3][0][0])
 
         qsize = {CQ_KD: nsym, CQ_M1: nsym, CQ_M3: nsym3, CQ_ADV: d1 * d1}
-        cq_all, ch_all, jt_all, ft_all = [], [], [], []
+        cq_all = []
         rec_max = 1
+        channels, ch = {}, []                        # global channel list: [tag, type, offset, factor column, use]
+        jt = [dict() for _ in range(self.npairs)]    # pair -> {(chan, flag): coef}
+        ft = [[] for _ in range(ns)]                 # species -> [(chan, gcol, coef, flag)]
+
+        def addJ(row, col, chan, coef, flag=0):
+            p = int(self.pair_pp[row]) + int(self.pair_idx[row, col])
+            jt[p][(chan, flag)] = jt[p].get((chan, flag), 0.0) + coef
+
         for tag, vid in enumerate(self.vol_ids):
             dF, dJ = self.degrees.get(("dx", vid), (1, None))
             same = dJ is None or dJ == dF
             rule = (lambda which: 1) if same else (lambda which: which)
             quantities, cq, size = {}, [], [1]          # record[0] = |K|
-            channels, ch = {}, []
 
             def quantity(kind, a, r):
                 key = (kind, a, r)
@@ -392,19 +399,12 @@ class KernelSpec:
                 return quantities[key]
 
             def channel(ctype, off, fac, use):
-                key = (ctype, off, fac)
+                key = (tag, ctype, off, fac)
                 if key not in channels:
                     channels[key] = len(ch)
-                    ch.append([ctype, off, fac, 0])
-                ch[channels[key]][3] |= use
+                    ch.append([tag, ctype, off, fac, 0])
+                ch[channels[key]][4] |= use
                 return channels[key]
-
-            jt = [dict() for _ in range(self.npairs)]    # pair -> {(chan, flag): coef}
-            ft = [[] for _ in range(ns)]                 # species -> [(chan, gcol, coef, flag)]
-
-            def addJ(row, col, chan, coef, flag=0):
-                p = int(self.pair_pp[row]) + int(self.pair_idx[row, col])
-                jt[p][(chan, flag)] = jt[p].get((chan, flag), 0.0) + coef
 
             for s in range(ns):
                 ds = int(self.diff_slot[tag, s])
@@ -451,13 +451,36 @@ class KernelSpec:
                         for spe, a in fac_rows[f][3]:
                             addJ(row, spe, chan, sign * coef * a)
             cq_all.append(cq)
-            ch_all.append(ch)
-            jt_all.append(jt)
-            ft_all.append(ft)
             rec_max = max(rec_max, size[0])
+        # static channels (functions of the mesh and the temperature only) first, then the
+        # solution-dependent ones (second-order moments contracted with an affine factor); the
+        # latter read their moments from an edge tensor per distinct (tag, moment) quantity
+        order = [i for i, c in enumerate(ch) if c[1] != CH_TRI] + [i for i, c in enumerate(ch) if c[1] == CH_TRI]
+        new_id = {old: new for new, old in enumerate(order)}
+        nstat = sum(1 for c in ch if c[1] != CH_TRI)
+        tensors = []
+        ch_out = []
+        for old in order:
+            tag, ctype, off, fac, use = ch[old]
+            ts = -1
+            if ctype == CH_TRI:
+                if (tag, off) not in tensors:
+                    tensors.append((tag, off))
+                ts = tensors.index((tag, off))
+            ch_out.append([tag, ctype, off, fac, use, ts, 0, 0])
+        jt = [{(new_id[c], fl): v for (c, fl), v in d.items()} for d in jt]
+        ft = [[(new_id[c], g, v, fl) for c, g, v, fl in lst] for lst in ft]
+        # SpMV on the channel operator: y_s = sum_e coef_e t[combo_e],  t[(chan, cs)] = sum_w A^chan_vw x_(w,cs)
+        pair_row = np.repeat(np.arange(ns), self.pair_nc)
+        combos, sp = {}, [[] for _ in range(ns)]
+        for p in range(self.npairs):
+            for (chan, flag), coef in jt[p].items():
+                key = (chan, int(self.pair_cs[p]))
+                combos.setdefault(key, len(combos))
+                sp[int(pair_row[p])].append((combos[key], flag, coef))
         self.vx = dict(nsym=nsym, nsym3=nsym3, rec=rec_max, nbw=g_one + 1, NF=NF,
-                       nch=max(max((len(c) for c in ch_all), default=1), 1),
-                       cq=cq_all, ch=ch_all, jt=jt_all, ft=ft_all)
+                       nch=max(len(ch_out), 1), nstat=nstat, ndyn=len(ch_out) - nstat, tensors=tensors,
+                       cq=cq_all, ch=ch_out, jt=jt, ft=ft, combos=list(combos), sp=sp)
 
     def _vertex_sections(self):
         vx = self.vx
@@ -472,31 +495,40 @@ class KernelSpec:
                     np.array(flat, dtype=np.int32).reshape(-1, width))
 
         cq_ptr, cq = csr(vx["cq"], 4)
-        ch_ptr, ch = csr(vx["ch"], 4)
         jt_ptr, jt, jt_coef = [0], [], []
-        for tag in range(nvt):
-            for p in range(self.npairs):
-                for (chan, flag), coef in vx["jt"][tag][p].items():
-                    jt.append([chan, flag])
-                    jt_coef.append(coef)
-                jt_ptr.append(len(jt))
+        for p in range(self.npairs):
+            for (chan, flag), coef in vx["jt"][p].items():
+                jt.append([chan, flag])
+                jt_coef.append(coef)
+            jt_ptr.append(len(jt))
         ft_ptr, ft, ft_coef = [0], [], []
-        for tag in range(nvt):
-            for s in range(ns):
-                for chan, gcol, coef, flag in vx["ft"][tag][s]:
-                    ft.append([chan, gcol, flag])
-                    ft_coef.append(coef)
-                ft_ptr.append(len(ft))
-        ints = np.zeros(8, dtype=np.int32)
-        ints[:7] = [1, vx["nsym"], vx["nsym3"], vx["rec"], vx["nbw"], vx["nch"], vx["NF"]]
+        for s in range(ns):
+            for chan, gcol, coef, flag in vx["ft"][s]:
+                ft.append([chan, gcol, flag])
+                ft_coef.append(coef)
+            ft_ptr.append(len(ft))
+        sp_ptr, sp, sp_coef = [0], [], []
+        for s in range(ns):
+            for combo, flag, coef in vx["sp"][s]:
+                sp.append([combo, flag])
+                sp_coef.append(coef)
+            sp_ptr.append(len(sp))
+        ints = np.zeros(16, dtype=np.int32)
+        ints[:11] = [1, vx["nsym"], vx["nsym3"], vx["rec"], vx["nbw"], len(vx["ch"]), vx["NF"],
+                     vx["nstat"], vx["ndyn"], len(vx["tensors"]), len(vx["combos"])]
         return {
-            S_VX_INTS: ints, S_VX_CQ_PTR: cq_ptr, S_VX_CQ: cq, S_VX_CH_PTR: ch_ptr, S_VX_CH: ch,
+            S_VX_INTS: ints, S_VX_CQ_PTR: cq_ptr, S_VX_CQ: cq,
+            S_VX_CH: np.array(vx["ch"], dtype=np.int32).reshape(-1, 8),
             S_VX_JT_PTR: np.array(jt_ptr, dtype=np.int32),
             S_VX_JT: np.array(jt, dtype=np.int32).reshape(-1, 2),
             S_VX_JT_COEF: np.array(jt_coef, dtype=np.float64),
             S_VX_FT_PTR: np.array(ft_ptr, dtype=np.int32),
             S_VX_FT: np.array(ft, dtype=np.int32).reshape(-1, 3),
             S_VX_FT_COEF: np.array(ft_coef, dtype=np.float64),
+            S_VX_SP_COMBO: np.array(vx["combos"], dtype=np.int32).reshape(-1, 2),
+            S_VX_SP_PTR: np.array(sp_ptr, dtype=np.int32),
+            S_VX_SP: np.array(sp, dtype=np.int32).reshape(-1, 2),
+            S_VX_SP_COEF: np.array(sp_coef, dtype=np.float64),
             S_PAIR_ROW: np.repeat(np.arange(self.ns, dtype=np.int32), self.pair_nc),
         }
 

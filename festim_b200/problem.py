@@ -181,6 +181,13 @@ class ProblemBase:
                 self.iterate()
         else:
             self.solver.solve()
+            # the reference sets snes_error_if_not_converged / ksp_error_if_not_converged
+            # (problem.py:287-288): PETSc raises from solve() instead of exporting a diverged field
+            reason = self.solver.solver.getConvergedReason()
+            if reason <= 0:
+                raise RuntimeError(
+                    f"Non-linear solver did not converge. Reason code: {reason}. \n See "
+                    "https://petsc.org/release/manualpages/SNES/SNESConvergedReason/ for more information.")
             self.post_processing()
 
     def iterate(self):

@@ -128,7 +128,7 @@ class EmuSolver:
     def spmv(self, Jvals, x):
         y = np.full(self.n_dofs, np.nan)
         x = np.ascontiguousarray(x, dtype=np.float64)
-        self.check(self.lib.fb_spmv(self.h, _p(Jvals), _p(x), _p(y)))
+        self.check(self.lib.fb_spmv(self.h, _p(Jvals) if Jvals is not None else None, _p(x), _p(y)))
         return y
 
 
@@ -138,7 +138,7 @@ def _linear_solve(self, Jvals, b, ksp=2, rtol=1e-12, max_it=2000):
     y = np.zeros(self.n_dofs)
     its, rel = C.c_int(0), C.c_double(0.0)
     b = np.ascontiguousarray(b, dtype=np.float64)
-    rc = self.lib.fb_linear_solve(self.h, _p(Jvals), _p(b), _p(y), ksp, 0, C.c_double(rtol), C.c_double(0.0),
+    rc = self.lib.fb_linear_solve(self.h, _p(Jvals) if Jvals is not None else None, _p(b), _p(y), ksp, 0, C.c_double(rtol), C.c_double(0.0),
                                   max_it, C.byref(its), C.byref(rel))
     self.check(rc)
     return y, its.value, rel.value, rc

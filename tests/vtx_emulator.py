@@ -1,4 +1,4 @@
-"""numpy model of the vertex-block assembly (festim_b200/csrc/assemble_vtx.cuh): the per-cell
+"""numpy model of the channel assembly (festim_b200/csrc/assemble_edge.cuh): the per-cell
 record, the channels and the coefficient tables of ``KernelSpec.vx`` are evaluated exactly as
 the device kernels do (cell-vectorised instead of warp-per-vertex) and scattered into a sparse
 matrix.  Test infrastructure: it checks the *lowering* (tables) against the oracle on the CPU,
@@ -104,27 +104,29 @@ def neighbour_table(spec, u, un, scalars):
     return nb
 
 
-def channels(spec, rec, nb, tag, sel):
-    """(nsel, nch, d1, d1) channel matrices of the cells ``sel`` (all of tag ``tag``)."""
+def channels(spec, rec, nb):
+    """(n_cells, nch, d1, d1) channel matrices of every cell (zero where the cell's tag is not
+    the channel's)."""
     mesh = spec.mesh
     d1 = mesh.tdim + 1
     s2, s3 = _sym_index(d1), _sym3_index(d1)
-    cells = mesh.cells[sel]
-    ch = spec.vx["ch"][tag]
-    out = np.zeros((len(sel), len(ch), d1, d1))
+    ch = spec.vx["ch"]
+    out = np.zeros((mesh.num_cells, len(ch), d1, d1))
     mscale = 1.0 / (d1 * (d1 + 1))
-    for c, (ctype, off, fac, use) in enumerate(ch):
+    for c, (tag, ctype, off, fac, use, ts, _, _) in enumerate(ch):
+        sel = np.nonzero(spec.cell_tag == tag)[0]
+        cells = mesh.cells[sel]
         for i in range(d1):
             for j in range(d1):
                 if ctype == L.CH_MASS:
-                    out[:, c, i, j] = rec[sel, 0] * mscale * (2.0 if i == j else 1.0)
+                    out[sel, c, i, j] = rec[sel, 0] * mscale * (2.0 if i == j else 1.0)
                 elif ctype == L.CH_PAIR:
-                    out[:, c, i, j] = rec[sel, off + s2[(i, j)]]
+                    out[sel, c, i, j] = rec[sel, off + s2[(i, j)]]
                 elif ctype == L.CH_FULL:
-                    out[:, c, i, j] = rec[sel, off + i * d1 + j]
+                    out[sel, c, i, j] = rec[sel, off + i * d1 + j]
                 else:
                     for b in range(d1):
-                        out[:, c, i, j] += rec[sel, off + s3[(i, j, b)]] * nb[cells[:, b], fac]
+                        out[sel, c, i, j] += rec[sel, off + s3[(i, j, b)]] * nb[cells[:, b], fac]
     return out
 
 
@@ -138,27 +140,23 @@ def assemble(spec, u, un, T, inv_dt=0.0, scalars=(), velocities=(), load=None):
     F = np.zeros(N) if load is None else load.copy()
     rows, cols, vals = [], [], []
     pair_row = np.repeat(np.arange(ns), spec.pair_nc)
-    for tag in range(len(spec.vol_ids)):
-        sel = np.nonzero(spec.cell_tag == tag)[0]
-        if len(sel) == 0:
-            continue
-        cells = mesh.cells[sel]
-        C = channels(spec, rec, nb, tag, sel)
-        for s in range(ns):
-            for chan, gcol, coef, flag in vx["ft"][tag][s]:
-                cf = coef * (inv_dt if flag & L.FLAG_INV_DT else 1.0)
-                g = nb[cells, gcol]                                   # (nsel, d1)
-                contrib = cf * np.einsum("cij,cj->ci", C[:, chan], g)
-                np.add.at(F, cells * ns + s, contrib)
-        for p in range(spec.npairs):
-            s, cs = pair_row[p], spec.pair_cs[p]
-            for (chan, flag), coef in vx["jt"][tag][p].items():
-                cf = coef * (inv_dt if flag & L.FLAG_INV_DT else 1.0)
-                for i in range(d1):
-                    for j in range(d1):
-                        rows.append(cells[:, i] * ns + s)
-                        cols.append(cells[:, j] * ns + cs)
-                        vals.append(cf * C[:, chan, i, j])
+    cells = mesh.cells
+    C = channels(spec, rec, nb)
+    for s in range(ns):
+        for chan, gcol, coef, flag in vx["ft"][s]:
+            cf = coef * (inv_dt if flag & L.FLAG_INV_DT else 1.0)
+            g = nb[cells, gcol]                                   # (nc, d1)
+            contrib = cf * np.einsum("cij,cj->ci", C[:, chan], g)
+            np.add.at(F, cells * ns + s, contrib)
+    for p in range(spec.npairs):
+        s, cs = pair_row[p], spec.pair_cs[p]
+        for (chan, flag), coef in vx["jt"][p].items():
+            cf = coef * (inv_dt if flag & L.FLAG_INV_DT else 1.0)
+            for i in range(d1):
+                for j in range(d1):
+                    rows.append(cells[:, i] * ns + s)
+                    cols.append(cells[:, j] * ns + cs)
+                    vals.append(cf * C[:, chan, i, j])
     if rows:
         J = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
     else:

@@ -65,6 +65,13 @@ def main():
     ms_asm = timed(lambda: ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u), ctx.ptr(un), ctx.ptr(F), ctx.ptr(J), 3)), args.reps)
     ms_asm_F = timed(lambda: ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u), ctx.ptr(un), ctx.ptr(F), ctx.ptr(J), 1)), args.reps)
     ms_spmv = timed(lambda: ctx._check(lib.fb_spmv(ctx.h, ctx.ptr(J), ctx.ptr(x), ctx.ptr(y))), 20)
+    y_bsr = y.clone()
+    ms_asm_ch = timed(lambda: ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u), ctx.ptr(un), ctx.ptr(F), None, 3)), args.reps)
+    ms_spmv_ch = timed(lambda: ctx._check(lib.fb_spmv(ctx.h, None, ctx.ptr(x), ctx.ptr(y))), 20)
+    spmv_diff = float((y - y_bsr).abs().max() / y_bsr.abs().max())
+    vx = spec.vx
+    nsp, ndp = (vx["nstat"] + 1) // 2 * 2, (vx["ndyn"] + 1) // 2 * 2
+    B_spmv_ch = 8 * (nsp + ndp) * nnzb + 4 * nnzb + 4 * (mesh.num_vertices + 1) + 16 * N
     out = {
         "config": f"C2: 3D H/D/T transient, 3 trap types, n={args.n}", "cells": mesh.num_cells,
         "dofs": N, "species": spec.ns, "species_pairs": spec.npairs, "nnz_blocks": nnzb,
@@ -73,7 +80,13 @@ def main():
                  "frac": B_spmv / ms_spmv / 1e6 / peak},
         "assembly_F_and_J": {"ms": ms_asm, "algorithmic_bytes": B_asm, "gbs": B_asm / ms_asm / 1e6,
                              "frac": B_asm / ms_asm / 1e6 / peak},
-        "assembly_F_only": {"ms": ms_asm_F}, "load_and_coefficients": {"ms": ms_load},
+        "assembly_F_only": {"ms": ms_asm_F},
+        "channel_operator": {"static_channels": vx["nstat"], "dynamic_channels": vx["ndyn"],
+                             "edge_tensors": len(vx["tensors"]),
+                             "assembly_F_and_channels_ms": ms_asm_ch,
+                             "spmv_ms": ms_spmv_ch, "spmv_algorithmic_bytes": B_spmv_ch,
+                             "spmv_gbs": B_spmv_ch / ms_spmv_ch / 1e6, "spmv_frac": B_spmv_ch / ms_spmv_ch / 1e6 / peak,
+                             "spmv_rel_diff_vs_block_csr": spmv_diff}, "load_and_coefficients": {"ms": ms_load},
     }
     if args.solve:
         m.u.x.array[:] = 0.0
