@@ -24,7 +24,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfestim_b
 
 FB_ASSEMBLE_F, FB_ASSEMBLE_J = 1, 2
 KSP = {"auto": 0, "preonly": 0, "cg": 1, "gmres": 2, "fgmres": 2, "tridiag": 3}
-PC = {"jacobi": 0, "bjacobi": 0, "pbjacobi": 0, "lu": 0, "chebyshev": 1}
+# "lu" (the reference default, an exact solve) maps to the library's own choice of preconditioner
+PC = {"jacobi": 0, "bjacobi": 0, "pbjacobi": 0, "chebyshev": 1, "lu": 2, "auto": 2}
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -70,6 +71,8 @@ def load_library():
                                 _f64p, C.POINTER(i)]),
         "fb_last_timings": (i, [vp, _f64p]),
         "fb_stepsize_modify": (d, [d, i, d, i, d, d, i, d, i, _f64p, d]),
+        "fb_hessenberg_eigenvalues": (i, [i, _f64p, _f64p, _f64p]),
+        "fb_chebyshev_info": (i, [vp, _f64p]),
         "fb_total_volume": (i, [vp, vp, i, i, _f64p]),
         "fb_total_surface": (i, [vp, vp, i, i, _f64p]),
         "fb_surface_flux": (i, [vp, vp, i, i, d, vp, _f64p]),
@@ -101,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "fb_set_spec", "fb_jit_load", "fb_set_dirichlet", "fb_num_dofs", "fb_jacobian_nnz", "fb_set_scalars",
     "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
     "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
-    "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_total_volume",
+    "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_hessenberg_eigenvalues", "fb_chebyshev_info", "fb_total_volume",
     "fb_total_surface", "fb_surface_flux", "fb_integrate", "fb_set_owned", "fb_set_sm_partition",
     "fb_bjacobi_setup", "fb_precond",
     "fb_peer_alloc", "fb_peer_open", "fb_peer_set_send", "fb_dcg_persistent",
@@ -362,7 +365,9 @@ class B200NewtonSolver:
             warnings.warn(f"ksp_type {ksp} is not implemented, using gmres")
             ksp = "gmres"
         self.ksp = KSP[ksp]
-        self.pc = PC.get(pc, 0)
+        if pc not in PC:
+            warnings.warn(f"pc_type {pc} is not implemented, using the default preconditioner")
+        self.pc = PC.get(pc, 2)
         # the reference's default is an exact LU solve: use a Krylov tolerance far
         # below the Newton tolerance so Newton iteration counts are unchanged
         snes_rtol = self.rtol if isinstance(self.rtol, (int, float)) else 1e-10

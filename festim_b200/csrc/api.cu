@@ -108,7 +108,14 @@ extern "C" int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr, const int32_t*
   cudaSetDevice(ctx->device);
   DevSpec& S = ctx->S;
   int rc;
-  if ((rc = fb_upload(ctx, &S.rowptr, rowptr, (size_t)S.n_vertices + 1))) return rc;
+  {   // padded: the row kernels bulk-copy FB_CHUNK + 4 row pointers at a time
+    int* rp = nullptr;
+    if ((rc = fb_alloc(ctx, &rp, (size_t)S.n_vertices + 1 + FB_CHUNK + 8))) return rc;
+    FB_CHECK(ctx, cudaMemsetAsync(rp, 0, sizeof(int) * ((size_t)S.n_vertices + 1 + FB_CHUNK + 8), ctx->stream));
+    FB_CHECK(ctx, cudaMemcpyAsync(rp, rowptr, sizeof(int) * ((size_t)S.n_vertices + 1), cudaMemcpyHostToDevice, ctx->stream));
+    FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    S.rowptr = rp;
+  }
   if ((rc = fb_upload(ctx, &S.colidx, colidx, (size_t)nnzb))) return rc;
   if ((rc = fb_upload(ctx, &S.v2c_ptr, v2c_ptr, (size_t)S.n_vertices + 1))) return rc;
   if ((rc = fb_upload(ctx, &S.v2c_idx, v2c_idx, (size_t)S.n_cells * (S.tdim + 1)))) return rc;
@@ -132,6 +139,66 @@ extern "C" int fb_set_pattern(fb_ctx* ctx, const int32_t* rowptr, const int32_t*
               S.cells, S.rowptr, S.colidx, S.v2c_ptr, S.v2c_idx, slots);
     FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     S.v2c_slot = slots;
+  }
+  // chunk plan of the TMA-pipelined row kernels (spmv_channels.cuh)
+  {
+    const long long nv = S.n_vertices;
+    const long long nchunks = (nv + FB_CHUNK - 1) / FB_CHUNK;
+    std::vector<int> runptr(nchunks + 1, 0), runs, nx(nchunks, 0), lcolptr(nchunks + 1, 0);
+    int rmax = 1;
+    std::vector<unsigned short> lcol;
+    std::vector<unsigned> rowinfo(((size_t)nv + FB_CHUNK + 15) & ~(size_t)15, 0u);
+    std::vector<int> uniq;
+    int nx_max = 0;
+    bool fits16 = true;
+    for (long long c = 0; c < nchunks; ++c) {
+      const long long c0 = c * FB_CHUNK, c1 = std::min(nv, c0 + FB_CHUNK);
+      const int e0 = rowptr[c0], e1 = rowptr[c1];
+      uniq.assign(colidx + e0, colidx + e1);
+      std::sort(uniq.begin(), uniq.end());
+      uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+      // runs of consecutive vertex ids; the staged list is the concatenation of the runs
+      for (size_t i = 0; i < uniq.size();) {
+        size_t j = i + 1;
+        while (j < uniq.size() && uniq[j] == uniq[j - 1] + 1) ++j;
+        runs.push_back(uniq[i]); runs.push_back((int)(j - i)); runs.push_back((int)i);
+        i = j;
+      }
+      runptr[c + 1] = (int)runs.size() / 3;
+      rmax = std::max(rmax, runptr[c + 1] - runptr[c]);
+      nx[c] = (int)uniq.size();
+      nx_max = std::max(nx_max, nx[c]);
+      if (uniq.size() > 65535) fits16 = false;
+      lcolptr[c] = (int)lcol.size();
+      for (int e = e0; e < e1; ++e)
+        lcol.push_back((unsigned short)(std::lower_bound(uniq.begin(), uniq.end(), colidx[e]) - uniq.begin()));
+      while (lcol.size() % 8) lcol.push_back(0);
+      for (long long v = c0; v < c1; ++v) {
+        const auto it = std::lower_bound(uniq.begin(), uniq.end(), (int)v);
+        rowinfo[v] = (it != uniq.end() && *it == (int)v) ? (unsigned)(it - uniq.begin()) : 0u;
+      }
+    }
+    lcolptr[nchunks] = (int)lcol.size();
+    // few long runs per chunk (compact numbering): TMA-friendly; otherwise no plan and the row
+    // kernels fall back to per-row gathers
+    S.ck_nx_max = (fits16 && (double)runs.size() / 3 <= 40.0 * (double)nchunks) ? nx_max : 0;
+    S.ck_rmax = rmax;
+    // the first 32 runs of every chunk in fixed slots (fetched one chunk ahead by the producer
+    // warp, one per lane); the rare chunk with more reads the rest from the CSR list
+    std::vector<int> slots;   // [chunk][32][3], unused slots have length 0
+    if (S.ck_nx_max > 0) {
+      slots.assign((size_t)nchunks * 32 * 3, 0);
+      for (long long c = 0; c < nchunks; ++c)
+        for (int q = runptr[c]; q < runptr[c + 1] && q < runptr[c] + 32; ++q)
+          for (int w = 0; w < 3; ++w) slots[((size_t)c * 32 + (q - runptr[c])) * 3 + w] = runs[3 * (size_t)q + w];
+    }
+    if ((rc = fb_upload(ctx, &S.ck_slots, slots.data(), slots.size()))) return rc;
+    if ((rc = fb_upload(ctx, &S.ck_runptr, runptr.data(), runptr.size()))) return rc;
+    if ((rc = fb_upload(ctx, &S.ck_runs, runs.data(), runs.size()))) return rc;
+    if ((rc = fb_upload(ctx, &S.ck_nx, nx.data(), nx.size()))) return rc;
+    if ((rc = fb_upload(ctx, &S.ck_lcolptr, lcolptr.data(), lcolptr.size()))) return rc;
+    if ((rc = fb_upload(ctx, &S.ck_lcol, lcol.data(), lcol.size()))) return rc;
+    if ((rc = fb_upload(ctx, &S.ck_rowinfo, rowinfo.data(), rowinfo.size()))) return rc;
   }
   ctx->have_pattern = true;
   return 0;
@@ -249,6 +316,7 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
       return fb_fail(ctx, "channel tables: channel list size mismatch");
     if (nch > 255 || np > 255) return fb_fail(ctx, "channel tables: too many channels / species pairs");
     S.vx_nft = ftp[ns]; S.vx_njt = jtp[np];
+    ctx->n_sp_ent = (int)(secs[S_VX_SP].count / 2);
     std::vector<int> itab;
     std::vector<double> dtab;
     S.vx_o_ch = (int)itab.size(); itab.insert(itab.end(), ch, ch + secs[S_VX_CH].count);
@@ -295,8 +363,9 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_nts))) return rc;
     S.et_tw = p;
     unsigned* vinfo = nullptr;
-    if ((rc = fb_alloc(ctx, &vinfo, (size_t)S.n_vertices))) return rc;
-    FB_CHECK(ctx, cudaMemsetAsync(vinfo, 0, sizeof(unsigned) * S.n_vertices, ctx->stream));
+    const size_t nvi = ((size_t)S.n_vertices + FB_CHUNK + 15) & ~(size_t)15;   // whole chunks are bulk-copied
+    if ((rc = fb_alloc(ctx, &vinfo, nvi))) return rc;
+    FB_CHECK(ctx, cudaMemsetAsync(vinfo, 0, sizeof(unsigned) * nvi, ctx->stream));
     S.vinfo = vinfo;
     S.et_tz_total = 0; S.et_tz = nullptr; S.et_tzptr = nullptr; S.et_tzslot = nullptr;
     if (S.vx_nts > 0 && (rc = fbi_et_symbolic(ctx))) return rc;

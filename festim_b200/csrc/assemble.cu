@@ -224,6 +224,8 @@ int fbi_update_vinfo(fb_ctx* ctx) {
 }
 
 int fbi_update_coeffs(fb_ctx* ctx) {
+  ctx->cheb_valid = false;   // temperature / coefficients moved: re-estimate the spectrum interval
+  ctx->cheb_refused = false;
   switch (ctx->S.tdim) {
     case 1: return update_coeffs_dim<1>(ctx);
     case 2: return update_coeffs_dim<2>(ctx);

@@ -11,6 +11,7 @@
 #define FB_MAX_D1 4
 #define FB_KB 8.6173303e-5  // Boltzmann constant eV/K, reference src/festim/__init__.py:11
 #define FB_STACK 24
+#define FB_CHUNK 16           // block rows staged together by the TMA-pipelined row kernels
 
 // Everything a kernel needs, passed by value (lives in the constant bank).
 struct DevSpec {
@@ -93,6 +94,17 @@ struct DevSpec {
   const double* et_tz;        // [nts][et_tz_total]  T_vwz, z a common neighbour of v and w
   const long long* et_tzptr;  // [n_owned+1] start of the row's (W_v x deg) slab
   const unsigned char* et_tzslot;   // [et_tz_total] row slot of z (0xff: padding)
+  // chunk plan (fb_set_pattern): FB_CHUNK consecutive block rows are staged together - the
+  // distinct neighbour vertices of a chunk as runs of consecutive ids (one bulk copy each)
+  int ck_nx_max;              // largest number of staged vertices of a chunk
+  int ck_rmax;                // most runs of a chunk
+  const int* ck_slots;        // [nchunks][32][3] the first 32 runs: first vertex, length (0: unused), offset in the staged list
+  const int* ck_runptr;       // [nchunks+1] all runs (CSR), same triples
+  const int* ck_runs;
+  const int* ck_nx;           // [nchunks] staged vertices
+  const int* ck_lcolptr;      // [nchunks+1] start of the chunk's edge list in ck_lcol (multiples of 8)
+  const unsigned short* ck_lcol;   // per edge: position of its column vertex in the staged list
+  const unsigned* ck_rowinfo; // [n_vertices, padded] per row: position of the row's own vertex in the staged list
   // per-step data
   const double* scalars;
   double T_const;

@@ -48,7 +48,12 @@ struct fb_ctx {
   int n_send = 0;
   int n_programs = 0;                  // compiled expressions of the spec (fb_integrate checks its argument)
   bool symmetric = false;
-  bool op_channels = false;    // Krylov solvers use the channel operator (J == nullptr) instead of block-CSR values
+  int n_sp_ent = 0;            // entries of the channel SpMV epilogue table (vx_sp)
+  bool op_channels = false;
+  // Chebyshev polynomial preconditioner: interval of D^-1 J from Ritz values, operator applications
+  bool cheb_valid = false, cheb_refused = false;
+  double cheb_lmin = 0.0, cheb_lmax = 0.0, cheb_inv_dt = 0.0;
+  int cheb_steps = 0;    // Krylov solvers use the channel operator (J == nullptr) instead of block-CSR values
   bool facet_u_terms = false;  // any solution-dependent facet term
   bool generic_u_vterms = false;  // any solution-dependent volume term evaluated point-wise
   bool have_jit = false;

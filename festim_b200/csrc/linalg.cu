@@ -7,10 +7,12 @@
 // device: every reduction finishes in the last block of the kernel that produced
 // the partial sums (ticket counter), which also advances the recurrence, so an
 // iteration is two launches for CG and the host only polls a "done" flag.
+#include <cstdint>
 #include <cstdlib>
 
 #include "fb_internal.cuh"
 #include "reduce.cuh"
+#include "spmv_channels.cuh"
 
 // ---------------------------------------------------------------------------
 // SpMV: G lanes per scalar row (v, s); values of the row are contiguous
@@ -250,6 +252,56 @@ static int spmv_ch_launch(fb_ctx* ctx, const double* x, double* y, const int* fl
   return 0;
 }
 
+// TMA-pipelined channel SpMV (spmv_channels.cuh): usable when every bulk copy is 16-byte aligned
+static bool spmv_ch_tma_ok(fb_ctx* ctx, const double* x) {
+  const DevSpec& S = ctx->S;
+  return S.vx_on && (S.ns % 2 == 0) && (((uintptr_t)x & 15) == 0) && S.vx_nch <= 16 && S.ck_nx_max > 0 &&
+         !getenv("FB_NO_TMA_SPMV");
+}
+
+template <int MODE>
+static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
+  const DevSpec& S = ctx->S;
+  a.n_sp_ent = ctx->n_sp_ent;
+  int smem_max = 0;
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+  int nst = 4;
+  if (getenv("FB_SPMV_STAGES")) nst = atoi(getenv("FB_SPMV_STAGES"));
+  if (nst > 8) nst = 8;
+  size_t smem = fb_spmv_ch_layout(S, a, MODE, nst);
+  while (nst > 2 && smem > (size_t)smem_max) smem = fb_spmv_ch_layout(S, a, MODE, --nst);
+  if (smem > (size_t)smem_max) return fb_fail(ctx, "channel SpMV: a chunk does not fit in shared memory");
+  const long long nchunks = (S.n_owned + FB_CHUNK - 1) / FB_CHUNK;
+  long long grid = ctx->sm_count;
+  if (grid > nchunks) grid = nchunks;
+  if (grid < 1) grid = 1;
+  const int mt = (S.vx_nch + 7) / 8, nt = (S.ns + 7) / 8;
+#define FB_SPMV_CASE(M, N)                                                                                   \
+  {                                                                                                          \
+    FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_spmv_ch_tma<M, N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                          \
+    k_spmv_ch_tma<M, N, MODE><<<(unsigned)grid, 32 * FB_CHUNK + 32, smem, ctx->stream>>>(S, a);                   \
+  }
+  if (mt == 1 && nt == 1) FB_SPMV_CASE(1, 1)
+  else if (mt == 1) FB_SPMV_CASE(1, 2)
+  else if (nt == 1) FB_SPMV_CASE(2, 1)
+  else FB_SPMV_CASE(2, 2)
+#undef FB_SPMV_CASE
+  ctx->launches++;
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// y = J x (precond false) or y = D^-1 J x on the channel operator
+static int spmv_ch(fb_ctx* ctx, const double* x, double* y, bool precond, const int* flags) {
+  if (spmv_ch_tma_ok(ctx, x)) {
+    SpmvChArgs a{};
+    a.x = x; a.y = y; a.dinv = ctx->d_dinv; a.flags = flags;
+    return precond ? spmv_ch_tma_launch<1>(ctx, a) : spmv_ch_tma_launch<0>(ctx, a);
+  }
+  return precond ? spmv_ch_launch<true>(ctx, x, y, flags) : spmv_ch_launch<false>(ctx, x, y, flags);
+}
+
 static int spmv_group(const DevSpec& S) {
   const double len = (S.tdim == 1 ? 3.0 : (S.tdim == 2 ? 7.0 : 15.0)) * S.npairs / S.ns;
   if (len <= 6) return 4;
@@ -294,7 +346,7 @@ int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y) {
   const DevSpec& S = ctx->S;
   if (!J) {
     if (!S.vx_on) return fb_fail(ctx, "no channel operator: pass the block-CSR values");
-    return spmv_ch_launch<false>(ctx, x, y, nullptr);
+    return spmv_ch(ctx, x, y, false, nullptr);
   }
   if (spmv_blk_ok(S)) return spmv_blk_launch<false>(ctx, J, x, y, nullptr);
   const int G = spmv_group(S);
@@ -1142,6 +1194,9 @@ k_cg_persistent(DevSpec S, CgArgs A) {
 #define GM_MISC (GM_HD2 + GM_M + 1)  // [0]=norm2 of w, [1]=scale, [2]=residual, [3]=threshold, [4]=beta0, [5]=refined
 #define GM_Y (GM_MISC + 8)
 #define GM_END (GM_Y + GM_M)
+#define GM_HRAW (GM_END + 8)                 // unrotated Hessenberg columns (Ritz values for the Chebyshev bounds)
+#define GM_SC_DOUBLES (GM_HRAW + (GM_M + 1) * GM_M + 8)
+#define GM_NVEC (GM_M + 8)                   // V[GM_M+1], w, z, r, and d0, d1, cr, cz of the Chebyshev recurrence
 
 // Classical Gram-Schmidt with one refinement pass when needed (PETSc's default for GMRES:
 // KSPGMRESClassicalGramSchmidtOrthogonalization, refine "if needed"), as two or three sweeps:
@@ -1239,6 +1294,7 @@ __global__ void k_gmres_givens(int j, double* sc, int* flags) {
   for (int i = 0; i <= j; ++i) col[i] = sc[GM_HD1 + i] + (refined ? sc[GM_HD2 + i] : 0.0);
   const double hn = sqrt(sc[GM_MISC + 0]);
   col[j + 1] = hn;
+  for (int i = 0; i <= j + 1; ++i) sc[GM_HRAW + (size_t)j * (GM_M + 1) + i] = col[i];
   sc[GM_MISC + 1] = hn > 0.0 ? 1.0 / hn : 0.0;
   for (int i = 0; i < j; ++i) {
     const double t = cs[i] * col[i] + sn[i] * col[i + 1];
@@ -1417,7 +1473,7 @@ int fbi_ensure_workspace(fb_ctx* ctx) {
   const DevSpec& S = ctx->S;
   if (ctx->d_sc) return 0;
   int rc;
-  if ((rc = fb_alloc(ctx, &ctx->d_sc, GM_END + 64))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_sc, GM_SC_DOUBLES + 64))) return rc;
   // partial sums: (GM_M + 2) vectors x capped vector grid, or 3 x the SpMV grid
   size_t red = (size_t)FB_RED_SLOTS * ctx->sm_count * 8;
   const size_t spmv_blocks = (size_t)((S.n_dofs * 32 + FB_TPB - 1) / FB_TPB);
@@ -1609,16 +1665,220 @@ static int solve_cg(fb_ctx* ctx, const double* J, const double* b, double* y, do
   return fl[0] ? 0 : 2;     // 2: not converged within max_it
 }
 
+// Eigenvalues of a real upper Hessenberg matrix (Francis double-shift QR with deflation, the
+// EISPACK hqr iteration), a[i * lda + j] row-major, destroyed.  Used on the <= 30 x 30 Arnoldi
+// matrix of a GMRES cycle: its Ritz values give the interval of the Chebyshev preconditioner.
+static int hessenberg_eigenvalues(int n, double* a, int lda, double* wr, double* wi) {
+#define HA(i, j) a[(size_t)((i) - 1) * lda + ((j) - 1)]
+  auto sign = [](double x, double y) { return y >= 0.0 ? std::fabs(x) : -std::fabs(x); };
+  double anorm = 0.0;
+  for (int i = 1; i <= n; ++i)
+    for (int j = (i - 1 > 1 ? i - 1 : 1); j <= n; ++j) anorm += std::fabs(HA(i, j));
+  int nn = n;
+  double t = 0.0, p = 0.0, q = 0.0, r = 0.0, x, y, z, w, u, v, sft;
+  while (nn >= 1) {
+    int its = 0, l;
+    do {
+      for (l = nn; l >= 2; --l) {
+        double sl = std::fabs(HA(l - 1, l - 1)) + std::fabs(HA(l, l));
+        if (sl == 0.0) sl = anorm;
+        if (std::fabs(HA(l, l - 1)) + sl == sl) { HA(l, l - 1) = 0.0; break; }
+      }
+      x = HA(nn, nn);
+      if (l == nn) {   // one root
+        wr[nn - 1] = x + t; wi[nn - 1] = 0.0; --nn;
+      } else {
+        y = HA(nn - 1, nn - 1);
+        w = HA(nn, nn - 1) * HA(nn - 1, nn);
+        if (l == nn - 1) {   // two roots
+          p = 0.5 * (y - x);
+          q = p * p + w;
+          z = std::sqrt(std::fabs(q));
+          x += t;
+          if (q >= 0.0) {
+            z = p + sign(z, p);
+            wr[nn - 2] = wr[nn - 1] = x + z;
+            if (z != 0.0) wr[nn - 1] = x - w / z;
+            wi[nn - 2] = wi[nn - 1] = 0.0;
+          } else {
+            wr[nn - 2] = wr[nn - 1] = x + p;
+            wi[nn - 1] = z; wi[nn - 2] = -z;
+          }
+          nn -= 2;
+        } else {
+          if (its == 60) return -1;
+          if (its == 10 || its == 20 || its == 40) {   // exceptional shift
+            t += x;
+            for (int i = 1; i <= nn; ++i) HA(i, i) -= x;
+            sft = std::fabs(HA(nn, nn - 1)) + std::fabs(HA(nn - 1, nn - 2));
+            y = x = 0.75 * sft;
+            w = -0.4375 * sft * sft;
+          }
+          ++its;
+          int m;
+          for (m = nn - 2; m >= l; --m) {
+            z = HA(m, m);
+            r = x - z;
+            sft = y - z;
+            p = (r * sft - w) / HA(m + 1, m) + HA(m, m + 1);
+            q = HA(m + 1, m + 1) - z - r - sft;
+            r = HA(m + 2, m + 1);
+            sft = std::fabs(p) + std::fabs(q) + std::fabs(r);
+            p /= sft; q /= sft; r /= sft;
+            if (m == l) break;
+            u = std::fabs(HA(m, m - 1)) * (std::fabs(q) + std::fabs(r));
+            v = std::fabs(p) * (std::fabs(HA(m - 1, m - 1)) + std::fabs(z) + std::fabs(HA(m + 1, m + 1)));
+            if (u + v == v) break;
+          }
+          for (int i = m + 2; i <= nn; ++i) {
+            HA(i, i - 2) = 0.0;
+            if (i != m + 2) HA(i, i - 3) = 0.0;
+          }
+          for (int k = m; k <= nn - 1; ++k) {
+            if (k != m) {
+              p = HA(k, k - 1);
+              q = HA(k + 1, k - 1);
+              r = 0.0;
+              if (k != nn - 1) r = HA(k + 2, k - 1);
+              if ((x = std::fabs(p) + std::fabs(q) + std::fabs(r)) != 0.0) { p /= x; q /= x; r /= x; }
+            }
+            const double sg = sign(std::sqrt(p * p + q * q + r * r), p);
+            if (sg != 0.0) {
+              if (k == m) {
+                if (l != m) HA(k, k - 1) = -HA(k, k - 1);
+              } else {
+                HA(k, k - 1) = -sg * x;
+              }
+              p += sg;
+              x = p / sg; y = q / sg; z = r / sg;
+              q /= p; r /= p;
+              for (int j = k; j <= nn; ++j) {
+                p = HA(k, j) + q * HA(k + 1, j);
+                if (k != nn - 1) { p += r * HA(k + 2, j); HA(k + 2, j) -= p * z; }
+                HA(k + 1, j) -= p * y;
+                HA(k, j) -= p * x;
+              }
+              const int mmin = nn < k + 3 ? nn : k + 3;
+              for (int i = l; i <= mmin; ++i) {
+                p = x * HA(i, k) + y * HA(i, k + 1);
+                if (k != nn - 1) { p += z * HA(i, k + 2); HA(i, k + 2) -= p * r; }
+                HA(i, k + 1) -= p * q;
+                HA(i, k) -= p;
+              }
+            }
+          }
+        }
+      }
+    } while (l < nn - 1);
+  }
+#undef HA
+  return 0;
+}
+
+// test hook: eigenvalues of an n x n upper Hessenberg matrix (row-major, n <= 64)
+extern "C" int fb_hessenberg_eigenvalues(int n, const double* a, double* wr, double* wi) {
+  if (n < 1 || n > 64 || !a || !wr || !wi) return -1;
+  std::vector<double> work(a, a + (size_t)n * n);
+  return hessenberg_eigenvalues(n, work.data(), n, wr, wi);
+}
+
+// state of the Chebyshev preconditioner: out = {valid, lmin, lmax, operator applications per use}
+extern "C" int fb_chebyshev_info(fb_ctx* ctx, double* out) {
+  if (!ctx || !out) return -1;
+  out[0] = ctx->cheb_valid ? 1.0 : 0.0; out[1] = ctx->cheb_lmin; out[2] = ctx->cheb_lmax; out[3] = ctx->cheb_steps;
+  return 0;
+}
+
+// Interval of the Chebyshev preconditioner from the Ritz values of the last plain GMRES cycle
+// (nc columns of the unrotated Hessenberg matrix, left on the device by k_gmres_givens).
+static int cheb_estimate(fb_ctx* ctx, int nc) {
+  if (nc < 6) return 0;
+  std::vector<double> raw((size_t)(GM_M + 1) * GM_M);
+  FB_CHECK(ctx, cudaMemcpyAsync(raw.data(), ctx->d_sc + GM_HRAW, raw.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<double> H((size_t)nc * nc, 0.0), wr(nc), wi(nc);
+  for (int j = 0; j < nc; ++j)
+    for (int i = 0; i < nc && i <= j + 1; ++i) H[(size_t)i * nc + j] = raw[(size_t)j * (GM_M + 1) + i];
+  if (hessenberg_eigenvalues(nc, H.data(), nc, wr.data(), wi.data())) return 0;
+  double lo = 1e300, hi = 0.0, im = 0.0;
+  for (int i = 0; i < nc; ++i) {
+    if (!(wr[i] == wr[i])) return 0;
+    const double mod = std::sqrt(wr[i] * wr[i] + wi[i] * wi[i]);
+    if (wr[i] < lo) lo = wr[i];
+    if (mod > hi) hi = mod;
+    if (std::fabs(wi[i]) > im) im = std::fabs(wi[i]);
+  }
+  // a polynomial preconditioner needs the spectrum in the right half plane and close to the real axis
+  if (!(lo > 0.0) || im > 0.3 * hi) { ctx->cheb_valid = false; ctx->cheb_refused = true; return 0; }
+  ctx->cheb_lmax = 1.1 * hi;                 // beyond lmax the polynomial grows: keep a margin
+  ctx->cheb_lmin = 0.9 * lo;
+  if (ctx->cheb_lmin < ctx->cheb_lmax / 100.0) ctx->cheb_lmin = ctx->cheb_lmax / 100.0;
+  const double sigma = (ctx->cheb_lmax + ctx->cheb_lmin) / (ctx->cheb_lmax - ctx->cheb_lmin);
+  int k = (int)std::ceil(std::acosh(20.0) / std::acosh(sigma));   // |residual polynomial| <= 1/20 on the interval
+  if (k < 2) k = 2;
+  if (k > 8) k = 8;
+  if (getenv("FB_CHEB_DEGREE")) k = atoi(getenv("FB_CHEB_DEGREE"));
+  ctx->cheb_steps = k;
+  ctx->cheb_valid = true;
+  ctx->cheb_inv_dt = ctx->S.inv_dt;
+  if (getenv("FB_VERBOSE"))
+    fprintf(stderr, "[fb] Chebyshev interval from %d Ritz values: [%.4g, %.4g] (max |Im| %.3g), %d operator applications\n", nc,
+            ctx->cheb_lmin, ctx->cheb_lmax, im, k);
+  return 0;
+}
+
+__global__ void k_cheb_init(long long n, const double* __restrict__ v, double inv_theta, double* __restrict__ d,
+                            double* __restrict__ z, double* __restrict__ r, const int* __restrict__ flags) {
+  if (flags && flags[0]) return;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const double vk = v[k], dk = vk * inv_theta;
+    d[k] = dk; z[k] = dk; r[k] = vk;
+  }
+}
+
+// z = p(B) v with p the Chebyshev polynomial of the interval (cheb_steps - 1 applications of
+// B = D^-1 J), and - when w is given - w = B z from one more application (w = v - r).
+static int cheb_apply(fb_ctx* ctx, const double* v, double* z, double* w, double* d0, double* d1, double* r,
+                      const int* flags) {
+  const long long N = ctx->S.n_dofs;
+  const double theta = 0.5 * (ctx->cheb_lmax + ctx->cheb_lmin), delta = 0.5 * (ctx->cheb_lmax - ctx->cheb_lmin);
+  const double sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  FB_LAUNCH(ctx, k_cheb_init, vec_grid(ctx, N), FB_TPB, 0, N, v, 1.0 / theta, d0, z, r, flags);
+  const int m = ctx->cheb_steps - 1;
+  const int steps = w ? m + 1 : m;
+  double* din = d0;
+  double* dout = d1;
+  for (int i = 0; i < steps; ++i) {
+    const double rho_n = 1.0 / (2.0 * sigma - rho);
+    SpmvChArgs a{};
+    a.x = din; a.dinv = ctx->d_dinv; a.flags = flags;
+    a.r = r; a.z = z; a.dout = dout; a.vin = v; a.wout = w;
+    a.ca = rho_n * rho; a.cb = 2.0 * rho_n / delta;
+    a.last = (w && i == m) ? 1 : 0;
+    int rc = spmv_ch_tma_launch<2>(ctx, a);
+    if (rc) return rc;
+    rho = rho_n;
+    double* tmp = din; din = dout; dout = tmp;
+  }
+  return 0;
+}
+
 static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y, double thr, int max_it,
-                       int* iters) {
+                       int* iters, bool want_cheb) {
   const DevSpec& S = ctx->S;
-  int rc = ensure_vectors(ctx, GM_M + 4);
+  int rc = ensure_vectors(ctx, GM_NVEC);
   if (rc) return rc;
   const long long N = S.n_dofs;
   double* V = ctx->d_work;                 // (GM_M+1) vectors
   double* w = V + (size_t)(GM_M + 1) * N;
   double* z = w + N;
   double* r = z + N;
+  double* cd0 = r + N;                     // Chebyshev recurrence: direction (ping-pong), residual, sum
+  double* cd1 = cd0 + N;
+  double* cr = cd1 + N;
+  double* cz = cr + N;
   const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
   const unsigned gv = vec_grid(ctx, N);
   double* sc = ctx->d_sc;
@@ -1627,8 +1887,12 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
   int total = 0;
   int fl[4] = {0, 0, 0, 0};
   bool first = true;
+  const bool cheb_possible = want_cheb && !J && spmv_ch_tma_ok(ctx, V) && !ctx->cheb_refused;
   while (total < max_it) {
-    // r = M^-1 (b - A y)   (left preconditioning: the Arnoldi residual is the
+    // right-preconditioned with the Chebyshev polynomial p(B) of B = D^-1 J once its interval is
+    // known (Ritz values of a plain cycle); the Arnoldi residual is the block-Jacobi one either way
+    const bool cheb = cheb_possible && ctx->cheb_valid;
+    // r = D^-1 (b - A y)   (left preconditioning: the Arnoldi residual is the
     // preconditioned one, PETSc's default norm for GMRES)
     if (first) {
       FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, b, r, (const int*)nullptr);
@@ -1641,10 +1905,13 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     FB_LAUNCH(ctx, k_dot, gv, FB_TPB, 0, N, r, r, ctx->d_red, ctx->d_ticket, sc + GM_MISC);
     FB_LAUNCH(ctx, k_gmres_begin, 1, 1, 0, sc, ctx->d_flags, thr);
     FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, r, sc + GM_MISC + 1, V, (const int*)nullptr);
+    const int poll = cheb ? 4 : 10;
     for (int j = 0; j < GM_M; ++j) {
-      // w = M^-1 J V_j: SpMV with the block-Jacobi application fused into its epilogue
-      if (!J) {
-        if ((rc = spmv_ch_launch<true>(ctx, V + (size_t)j * N, w, ctx->d_flags))) return rc;
+      // w = D^-1 J [p(B)] V_j: SpMV with the block-Jacobi application fused into its epilogue
+      if (cheb) {
+        if ((rc = cheb_apply(ctx, V + (size_t)j * N, cz, w, cd0, cd1, cr, ctx->d_flags))) return rc;
+      } else if (!J) {
+        if ((rc = spmv_ch(ctx, V + (size_t)j * N, w, true, ctx->d_flags))) return rc;
       } else if (spmv_blk_ok(S)) {
         if ((rc = spmv_blk_launch<true>(ctx, J, V + (size_t)j * N, w, ctx->d_flags))) return rc;
       } else {
@@ -1668,18 +1935,29 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
 #undef FB_GS_CASE
       FB_LAUNCH(ctx, k_gmres_givens, 1, 1, 0, j, sc, ctx->d_flags);
       FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, w, sc + GM_MISC + 1, V + (size_t)(j + 1) * N, ctx->d_flags);
-      if (j % 10 == 9 || j == GM_M - 1) {
+      if (j % poll == poll - 1 || j == GM_M - 1) {
         FB_CHECK(ctx, cudaGetLastError());
         if ((rc = read_flags(ctx, fl))) return rc;
         if (fl[0]) break;
       }
     }
     total = fl[1];
-    // y += V yk
+    // y += [p(B)] V yk
     if (fl[3] > 0) {
       FB_LAUNCH(ctx, k_gmres_solve_y, 1, 1, 0, sc, ctx->d_flags);
       FB_LAUNCH(ctx, k_combine, gv, FB_TPB, 0, N, V, sc + GM_Y, ctx->d_flags, w);
-      FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, N, 1.0, w, y);
+      if (cheb) {
+        if ((rc = cheb_apply(ctx, w, cz, nullptr, cd0, cd1, cr, (const int*)nullptr))) return rc;
+        FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, N, 1.0, cz, y);
+      } else {
+        FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, N, 1.0, w, y);
+      }
+    }
+    if (cheb_possible && !cheb && !ctx->cheb_valid && (rc = cheb_estimate(ctx, fl[3]))) return rc;
+    if (cheb && !fl[0] && !fl[2]) {
+      // a full cycle without convergence: the interval is off (the operator changed); back to
+      // block-Jacobi for the rest of this solve, which also re-estimates the interval
+      ctx->cheb_valid = false;
     }
     if (fl[0] || fl[2]) break;
   }
@@ -1707,7 +1985,6 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   const DevSpec& S = ctx->S;
   int rc = fbi_ensure_workspace(ctx);
   if (rc) return rc;
-  (void)pc;
   *iters = 0;
   *relres = 0.0;
   if (ksp == FB_KSP_AUTO) ksp = ctx->tridiag ? FB_KSP_TRIDIAG : (ctx->symmetric ? FB_KSP_CG : FB_KSP_GMRES);
@@ -1717,6 +1994,13 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
     if (!ctx->tridiag) return fb_fail(ctx, "tridiagonal solver needs an interval mesh ordered along x");
     return solve_tridiag(ctx, J, b, y);
   }
+  // pc: block-Jacobi (0), Chebyshev polynomial of the block-Jacobi-scaled operator (1), or the
+  // default (2): Chebyshev for large systems held as channel operator, block-Jacobi otherwise
+  const bool want_cheb = ksp == FB_KSP_GMRES && !getenv("FB_NO_CHEBYSHEV") &&
+                         (pc == FB_PC_CHEBYSHEV || (pc == FB_PC_AUTO && S.n_dofs >= 200000));
+  if (ctx->cheb_valid && ctx->cheb_inv_dt > 0.0 &&
+      (S.inv_dt > 2.0 * ctx->cheb_inv_dt || S.inv_dt < 0.5 * ctx->cheb_inv_dt))
+    ctx->cheb_valid = false;   // the time step moved: the spectrum of D^-1 J with it
   double bnorm;
   if ((rc = fbi_norm2(ctx, b, &bnorm))) return rc;
   if (bnorm == 0.0) {
@@ -1729,7 +2013,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   // stopping rule on the preconditioned residual, ||M^-1 r|| <= max(rtol ||M^-1 b||, atol)
   // (PETSc default for left-preconditioned CG/GMRES); block-Jacobi makes it row-scaled,
   // which matters when species equations differ by many orders of magnitude
-  const int base = (ksp == FB_KSP_CG) ? 5 : GM_M + 4;  // Krylov vectors, then Ay, t, corr
+  const int base = (ksp == FB_KSP_CG) ? 5 : GM_NVEC;  // Krylov vectors, then Ay, t, corr
   if ((rc = ensure_vectors(ctx, base + 3))) return rc;
   FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, b, ctx->d_work, (const int*)nullptr);
   double pbnorm;
@@ -1770,7 +2054,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
         }
       }
     }
-    else status = solve_gmres(ctx, J, rhs, sol, thr_r, max_it, &its);
+    else status = solve_gmres(ctx, J, rhs, sol, thr_r, max_it, &its, want_cheb);
     *iters += its;
     if (status < 0) return status;
     if (round > 0) FB_LAUNCH(ctx, k_axpy, vec_grid(ctx, S.n_dofs), FB_TPB, 0, S.n_dofs, 1.0, corr, y);

@@ -51,7 +51,10 @@ typedef struct fb_ctx fb_ctx;
 #define FB_KSP_GMRES 2
 #define FB_KSP_TRIDIAG 3
 #define FB_PC_JACOBI 0    /* point-block Jacobi (ns x ns diagonal blocks) */
-#define FB_PC_CHEBYSHEV 1 /* Chebyshev polynomial smoother on block-Jacobi */
+#define FB_PC_CHEBYSHEV 1 /* GMRES right-preconditioned with a Chebyshev polynomial of the block-Jacobi-scaled operator
+                             (interval from the Ritz values of a first block-Jacobi cycle); channel operator only,
+                             block-Jacobi otherwise */
+#define FB_PC_AUTO 2      /* what pc_type "lu" maps to: Chebyshev for large systems held as channel operator, else Jacobi */
 
 /* SNES converged reasons used (PETSc numbering) */
 #define FB_CONVERGED_FNORM_ABS 2
@@ -110,9 +113,14 @@ int fb_update_load(fb_ctx* ctx);
 /* residual F(u) and/or Jacobian J(u) with strong Dirichlet conditions applied the
  * dolfinx NonlinearProblem way: lifting (alpha=-1), F_B = u_B - g, identity rows and
  * columns in J (replaces assemble_vector/apply_lifting/set_bc/assemble_matrix). */
+/* Systems assembled through channels (mass-action reactions, diffusion, mass, advection: every
+ * BASELINE config) keep the Jacobian as the channel operator  J = sum_c A^c (x) B_c  inside the
+ * context (8 bytes per channel and edge instead of 8 bytes per species pair and edge): every
+ * fb_assemble refreshes it, and Jvals may then be NULL in fb_assemble (no block-CSR values are
+ * written), fb_spmv and fb_linear_solve (they use the operator of the last fb_assemble). */
 int fb_assemble(fb_ctx* ctx, const double* u /*[dev]*/, const double* u_n /*[dev]*/,
                 double* F /*[dev] N or NULL*/, double* Jvals /*[dev] nnz or NULL*/, int flags);
-/* y = J x (vectorised species-sparse BSR SpMV) */
+/* y = J x (species-sparse block-CSR values, or the channel operator when Jvals is NULL) */
 int fb_spmv(fb_ctx* ctx, const double* Jvals /*[dev]*/, const double* x /*[dev]*/,
             double* y /*[dev]*/);
 /* fused vector kernels (warp-shuffle reductions); results land in out[] on host */
@@ -131,6 +139,12 @@ int fb_newton_solve(fb_ctx* ctx, double* u /*[dev]*/, const double* u_n /*[dev]*
 /* timing of the last fb_newton_solve, CUDA events on ctx's stream, milliseconds:
  * out[0]=assembly F, out[1]=assembly J(+F), out[2]=linear solve, out[3]=other */
 int fb_last_timings(fb_ctx* ctx, double* out /*[host] 4*/);
+
+/* state of the Chebyshev preconditioner: out = {valid, lambda_min, lambda_max, operator applications per use} */
+int fb_chebyshev_info(fb_ctx* ctx, double* out /*[host] 4*/);
+/* test hook: eigenvalues of an n x n real upper Hessenberg matrix (row-major), the routine that
+ * turns the Arnoldi matrix of a GMRES cycle into the interval of the Chebyshev preconditioner */
+int fb_hessenberg_eigenvalues(int n, const double* a /*[host]*/, double* wr /*[host]*/, double* wi /*[host]*/);
 
 /* adaptive step size (reference stepsize.py:144-167); milestones sorted ascending */
 double fb_stepsize_modify(double value, int nb_iterations, double t, int adaptive,

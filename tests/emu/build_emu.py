@@ -69,7 +69,7 @@ def build(force=False):
     with open(hdr, "w") as fh:
         fh.write(open(os.path.join(ROOT, "include", "festim_b200.h")).read())
     cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-Wl,-Bsymbolic", "-I", HERE, "-I", cuda_inc,
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-DFB_EMU", "-Wl,-Bsymbolic", "-I", HERE, "-I", cuda_inc,
            "-o", LIB, os.path.join(HERE, "cuda_emu.cpp")] + cpps + ["-ldl"]
     subprocess.run(cmd, check=True)
     return LIB

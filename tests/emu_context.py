@@ -132,13 +132,13 @@ class EmuSolver:
         return y
 
 
-def _linear_solve(self, Jvals, b, ksp=2, rtol=1e-12, max_it=2000):
+def _linear_solve(self, Jvals, b, ksp=2, rtol=1e-12, max_it=2000, pc=0):
     """fb_linear_solve on the emulated device (GMRES / tridiagonal; the persistent CG is a
     cooperative launch and is not emulated)."""
     y = np.zeros(self.n_dofs)
     its, rel = C.c_int(0), C.c_double(0.0)
     b = np.ascontiguousarray(b, dtype=np.float64)
-    rc = self.lib.fb_linear_solve(self.h, _p(Jvals) if Jvals is not None else None, _p(b), _p(y), ksp, 0, C.c_double(rtol), C.c_double(0.0),
+    rc = self.lib.fb_linear_solve(self.h, _p(Jvals) if Jvals is not None else None, _p(b), _p(y), ksp, pc, C.c_double(rtol), C.c_double(0.0),
                                   max_it, C.byref(its), C.byref(rel))
     self.check(rc)
     return y, its.value, rel.value, rc
@@ -157,5 +157,13 @@ def _newton(self, u, un, atol, rtol, stol=1.49e-10, max_it=30, ksp=2, ksp_rtol=1
     return u, n_its.value, reason.value, lin.value
 
 
+def _chebyshev_info(self):
+    out = (C.c_double * 4)()
+    self.lib.fb_chebyshev_info.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    self.lib.fb_chebyshev_info(self.h, out)
+    return list(out)
+
+
 EmuSolver.linear_solve = _linear_solve
+EmuSolver.chebyshev_info = _chebyshev_info
 EmuSolver.newton = _newton

@@ -93,8 +93,17 @@ def main():
         m.u_n.x.array[:] = 0.0
         m.iterate()                      # first step: Krylov workspace allocation (3 GB), warm-up
         first_ms = [float(v) for v in s.timings]
+        first_lin = s.solver.linear_its
+        m.iterate()                      # Chebyshev interval known from the first step's Ritz values
+        second_ms = [float(v) for v in s.timings]
+        second_lin = s.solver.linear_its
         t0 = time.time()
         m.iterate()
+        info = (C.c_double * 4)()
+        lib.fb_chebyshev_info(ctx.h, info)
+        out["chebyshev"] = {"valid": info[0], "lmin": info[1], "lmax": info[2], "applications": info[3],
+                            "first_step_linear_its": first_lin, "second_step_linear_its": second_lin,
+                            "second_step_phase_ms": second_ms}
         out["time_step"] = {"wall_s": time.time() - t0, "newton_its": s.solver.its,
                             "first_step_phase_ms": first_ms,
                             "linear_its": s.solver.linear_its,
