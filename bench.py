@@ -1,23 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the FESTIM hot path on B200: Newton-step DOFs/s.
 
-A "step" is one pass of the hot path over the workload: a full Newton solve of
-the configuration (assemble F and J, Krylov solve, update, residual check),
-timed on the device; the metric is dofs / (solve time / Newton iterations).
-Default workload: BASELINE.json configs[1] (C1), the 3D unit-cube MMS steady
-diffusion problem of reference test_1_mobile_MMS_3D on an n=55 Kuhn mesh
-(998 250 cells, 175 616 dofs).
+Default workload (N=1): BASELINE.json configs[2] (C2), the largest configuration that fits one
+GPU - 3D H/D/T transient with 3 trap types on an n=94 Kuhn cube (4 983 504 cells, 12 species,
+10 288 500 dofs).  A "step" is one implicit-Euler time step of that problem: Newton iterations
+(assemble F and the Jacobian operator, preconditioned GMRES, update, residual check), timed on
+the device; the metric is dofs x Newton iterations / time.  `--workload c1` keeps the round-1
+configuration (3D MMS steady diffusion, n=55).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                  [--workload c1|c1small] [--n 55]
+                  [--workload c2|c1] [--n 94] [--parity-n 16] [--ref-n 12]
+
+The same run checks the answer (parity_rel_l2: GPU vs the CPU oracle on the same problem at
+--parity-n, through the same solver path) and times the oracle on the host (cpu_baseline).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import warnings
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -31,15 +36,34 @@ def proc_grid(world):
     return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
 
 
-def build_workload(name, n, grid=(1, 1, 1)):
+def c2_counts(n):
+    return 6 * n ** 3, (n + 1) ** 3, 12 * (n + 1) ** 3
+
+
+def workload_name(name, n):
+    if name == "c2":
+        cells, nv, dofs = c2_counts(n)
+        return (f"C2: 3D H/D/T transient, 3 trap types (12 species, 9 reactions), P1 tets n={n}, "
+                f"{cells} cells, {dofs} dofs, implicit Euler dt=1e-2")
+    return f"C1: 3D unit-cube MMS steady diffusion (reference test_1_mobile_MMS_3D), P1 tets n={n}"
+
+
+def build_c2(n, chebyshev=False):
+    from cases import multi_isotope_traps_3d
+
+    m, iso, trapped = multi_isotope_traps_3d(n, final_time=1e9)
+    if chebyshev:
+        m.petsc_options = {"pc_type": "chebyshev"}
+    return m
+
+
+def build_c1(n, grid=(1, 1, 1)):
     """C1, or its weak-scaling extension: the same problem on the box
     [0,px] x [0,py] x [0,pz] with n cells per unit length (one C1 per GPU)."""
     from cases import mms_1_mobile_steady
 
-    if name not in ("c1", "c1small"):
-        raise SystemExit(f"unknown workload {name}")
     if grid == (1, 1, 1):
-        return mms_1_mobile_steady(3, n)
+        return mms_1_mobile_steady(3, n)[0]
     import numpy as np
 
     import festim_b200 as F
@@ -66,19 +90,7 @@ def build_workload(name, n, grid=(1, 1, 1)):
                              F.DirichletBC(subdomain=right, value=u_exact(ufl), species=H)]
     m.sources = [F.ParticleSource(value=-ufl.div(D * ufl.grad(u_exact(ufl)(x))), volume=vol, species=H)]
     m.settings = F.Settings(atol=1e-10, rtol=1e-10, transient=False)
-    return m, H, u_exact(np)
-
-
-def spmv_bytes(spec, nnzb):
-    nv, ns = spec.mesh.num_vertices, spec.ns
-    return 8 * spec.npairs * nnzb + 4 * nnzb + 4 * (nv + 1) + 16 * nv * ns
-
-
-def assembly_bytes(spec, nnzb):
-    m = spec.mesh
-    d = m.tdim
-    return (m.num_cells * (4 * (d + 1) + 4) + m.num_vertices * (8 * d + 8 * spec.T_mode + 16 * spec.ns)
-            + 8 * spec.npairs * nnzb + 8 * m.num_vertices * spec.ns)
+    return m
 
 
 class ClockSampler(threading.Thread):
@@ -115,32 +127,340 @@ class ClockSampler(threading.Thread):
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json, copy bandwidth)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_cpu_sample(n_small, steps=1):
-    """Oracle (restated reference path: numpy assembly + SuperLU) on a bounded sample."""
+# ---------------------------------------------------------------------------------------------
+# CPU side: the oracle (restated reference path) on a bounded sample of the workload
+# ---------------------------------------------------------------------------------------------
+def oracle_steps(workload, n, nsteps):
+    """Run `nsteps` steps of the workload at mesh size n through the oracle; returns
+    (dofs, seconds per step list, Newton iterations per step list, final field)."""
     from oracle.newton import OracleBackend
 
-    best = None
-    ndofs = its = 0
-    for _ in range(steps):
-        m, H, _ = build_workload("c1", n_small)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = build_c2(n) if workload == "c2" else build_c1(n)
         m.solver_backend = OracleBackend()
         m.initialise()
+    secs, its = [], []
+    for _ in range(nsteps):
         t0 = time.perf_counter()
-        m.run()
-        dt = time.perf_counter() - t0
-        its = max(m.solver.solver.getIterationNumber(), 1)
-        ndofs = m.u.x.array.size
-        best = dt if best is None else min(best, dt)
-    return ndofs / (best / its), ndofs, best, its
+        if workload == "c2":
+            m.iterate()
+        else:
+            m.u.x.array[:] = 0.0
+            m.solver.solve()
+        secs.append(time.perf_counter() - t0)
+        its.append(max(m.solver.solver.getIterationNumber(), 1))
+    return m.u.x.array.size, secs, its, m.u.x.array.copy()
 
 
+_REF = {}
+
+
+def _ref_init(workload, n):
+    from oracle.newton import OracleBackend
+
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = build_c2(n) if workload == "c2" else build_c1(n)
+        m.solver_backend = OracleBackend()
+        m.initialise()
+    _REF["m"], _REF["workload"] = m, workload
+
+
+def _ref_step(_):
+    m = _REF["m"]
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if _REF["workload"] == "c2":
+            m.iterate()
+        else:
+            m.u.x.array[:] = 0.0
+            m.solver.solve()
+    return m.u.x.array.size, max(m.solver.solver.getIterationNumber(), 1), time.perf_counter() - t0
+
+
+def run_reference(args, config):
+    """`--impl reference`: the restated reference path (oracle: numpy assembly + SuperLU Newton) on
+    the host cores.  The port is single-threaded, so one independent replica of a bounded sample
+    of the workload runs per core; every timed step advances all replicas by one step."""
+    import multiprocessing as mp
+
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    n = args.ref_n
+    with mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(args.workload, n)) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_step, range(cores))
+        t0 = time.perf_counter()
+        work = 0
+        for _ in range(args.steps):
+            for ndofs, its, _ in pool.map(_ref_step, range(cores)):
+                work += ndofs * its
+        wall = time.perf_counter() - t0
+    v = work / wall
+    sample = (f"{cores} independent replicas (one per host core) of the same problem on an n={n} mesh "
+              f"({ndofs} dofs each), every step = one {'time step' if args.workload == 'c2' else 'steady solve'} "
+              f"of every replica: numpy assembly + SuperLU Newton solve (restated reference path, "
+              f"NOT dolfinx+PETSc, which is absent from this image)")
+    cfg = dict(config)
+    cfg["reference_sample"] = {"n": n, "dofs_per_replica": int(ndofs), "replicas": cores}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "strong" if args.workload == "c2" else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------
+# N = 1
+# ---------------------------------------------------------------------------------------------
+def gpu_parity(workload, n, nsteps, ref_field):
+    """The same problem at the oracle's size through the same solver path (channel operator,
+    Chebyshev-preconditioned GMRES): relative L2 distance of the fields."""
+    import numpy as np
+
+    from festim_b200.backend import B200Backend
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = build_c2(n, chebyshev=True) if workload == "c2" else build_c1(n)
+        m.solver_backend = B200Backend()
+        m.initialise()
+    its = []
+    for _ in range(nsteps):
+        if workload == "c2":
+            m.iterate()
+        else:
+            m.u.x.array[:] = 0.0
+            m.solver.solve()
+        its.append(max(m.solver.solver.getIterationNumber(), 1))
+    rel = float(np.linalg.norm(m.u.x.array - ref_field) / np.linalg.norm(ref_field))
+    info = (C.c_double * 4)()
+    m.solver.ctx.lib.fb_chebyshev_info(m.solver.ctx.h, info)
+    return rel, its, bool(info[0]), bool(m.solver.spec.vx is not None)
+
+
+def run_single(args, config):
+    import numpy as np
+    import torch
+
+    import __graft_entry__ as g
+    from festim_b200.backend import B200Backend
+
+    g.build()
+    torch.cuda.set_device(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = build_c2(args.n) if args.workload == "c2" else build_c1(args.n)
+        model.solver_backend = B200Backend(device=0)
+        t0 = time.perf_counter()
+        model.initialise()
+        setup_s = time.perf_counter() - t0
+    solver = model.solver
+    ctx, lib, spec = solver.ctx, solver.ctx.lib, solver.spec
+    N = ctx.n_dofs
+    nnzb = len(ctx.dmesh.graph[1])
+    transient = args.workload == "c2"
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+
+    # ---- device-resident steps ("value") -------------------------------------------------
+    solver._push_state()
+    u_dev, un_dev = ctx.zeros(N), ctx.zeros(N)
+    n_its, reason, lin = C.c_int(0), C.c_int(0), C.c_int(0)
+    fnorm = C.c_double(0.0)
+    tot = {"newton": 0, "linear": 0}
+
+    def device_step():
+        if transient:
+            un_dev.copy_(u_dev)
+        else:
+            u_dev.zero_()
+            ctx._check(lib.fb_update_load(ctx.h))
+        rc = lib.fb_newton_solve(ctx.h, ctx.ptr(u_dev), ctx.ptr(un_dev if transient else u_dev),
+                                 float(solver.atol), float(solver.rtol), solver.stol, solver.max_it,
+                                 solver.ksp, solver.pc, solver.ksp_rtol, solver.ksp_max_it,
+                                 C.byref(n_its), C.byref(reason), C.byref(fnorm), C.byref(lin))
+        ctx._check(rc)
+        assert reason.value > 0, f"Newton did not converge: reason {reason.value}"
+        tot["newton"] += max(n_its.value, 1)
+        tot["linear"] += lin.value
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler()
+    sampler.start()
+    torch.cuda.synchronize()
+    tot["newton"] = tot["linear"] = 0
+    l0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    phase = np.zeros(4)
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        ev[k][0].record()
+        device_step()
+        ev[k][1].record()
+        tm = (C.c_double * 4)()
+        lib.fb_last_timings(ctx.h, tm)
+        phase += np.array(list(tm))
+    torch.cuda.synchronize()
+    launches = ctx.launches - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    newton_per_step = tot["newton"] / args.steps
+    linear_per_step = tot["linear"] / args.steps
+    phase /= args.steps
+    info = (C.c_double * 4)()
+    lib.fb_chebyshev_info(ctx.h, info)
+
+    # ---- end to end through the public API ("e2e"): host arrays in, host arrays out ------
+    e2e_its = []
+
+    def api_step():
+        if transient:
+            model.iterate()
+        else:
+            model.u.x.array[:] = 0.0
+            solver._signature = None  # a fresh steady solve integrates its sources again
+            solver.solve()
+        e2e_its.append(max(solver.solver.getIterationNumber(), 1))
+        return float(model.u.x.array[0])
+
+    api_step()
+    torch.cuda.synchronize()
+    e2e_its.clear()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        api_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d = 8 * N * (2 if transient else 1) + 8 * len(solver._bc_dofs)
+    d2h = 8 * N
+    e2e_val = N * (sum(e2e_its) / len(e2e_its)) / e2e_s
+
+    # ---- roofline of the dominant kernels, timed alone with CUDA events ---------------------
+    peak, peak_src = peaks()
+    rng = np.random.default_rng(0)
+    x = ctx.to_device("bench_x", rng.standard_normal(N))
+    y, Fv = ctx.zeros(N), ctx.zeros(N)
+    channel = spec.vx is not None and bool(getattr(spec, "vx", None))
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    mesh = spec.mesh
+    d = mesh.tdim
+    roofline = None
+    if channel:
+        vx = spec.vx
+        nsp, ndp = (vx["nstat"] + 1) // 2 * 2, (vx["ndyn"] + 1) // 2 * 2
+        ntens = len(vx["tensors"])
+        spmv_ms = timed(lambda: ctx._check(lib.fb_spmv(ctx.h, None, ctx.ptr(x), ctx.ptr(y))), 30)
+        asm_ms = timed(lambda: ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(un_dev), ctx.ptr(Fv), None, 3)), 10)
+        # algorithmic bytes of OUR layout (DESIGN.md section 4): every array touched once
+        B_spmv = 8 * (nsp + ndp) * nnzb + 4 * nnzb + 4 * (mesh.num_vertices + 1) + 16 * N
+        # assembly: static channel values + the edge tensor in, dynamic channel values out, u, u_n, F, load
+        tz_entries = getattr(solver, "_tz_entries", None)
+        B_asm = 8 * nsp * nnzb + 8 * ndp * nnzb + 16 * ntens * nnzb + 4 * nnzb + 8 * N * (4 if transient else 3)
+        # the same operator in the species-sparse block-CSR layout of SURVEY 8d (8 |P| nnzb values)
+        B_spmv_bsr = 8 * spec.npairs * nnzb + 4 * nnzb + 4 * (mesh.num_vertices + 1) + 16 * N
+        B_asm_bsr = (mesh.num_cells * (4 * (d + 1) + 4) + mesh.num_vertices * (8 * d + 8 * spec.T_mode + 16 * spec.ns)
+                     + 8 * spec.npairs * nnzb + 8 * N)
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r2_ncu_spmv_channels.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        ach = B_spmv / (spmv_ms * 1e-3) / 1e9
+        roofline = {
+            "kernel": "k_spmv_ch_tma (channel-operator SpMV: TMA bulk-copy pipeline + fp64 DMMA), the kernel "
+                      "behind every Krylov / Chebyshev operator application",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": B_spmv, "ms": spmv_ms,
+            "note": "algorithmic bytes of the channel-operator layout (8 bytes per channel and edge: "
+                    f"{nsp}+{ndp} channels instead of {spec.npairs} species pairs); timed alone after the steps "
+                    "(burst), inputs larger than L2",
+            "block_csr_equivalent": {
+                "what": "the same products counted with SURVEY 8d's block-CSR bytes (8 |P| nnzb): what a "
+                        "block-CSR SpMV / assembly would have had to move in the same time",
+                "spmv_bytes": B_spmv_bsr, "spmv_gbs": B_spmv_bsr / (spmv_ms * 1e-3) / 1e9,
+                "spmv_frac_of_peak": B_spmv_bsr / (spmv_ms * 1e-3) / 1e9 / peak,
+                "assembly_bytes": B_asm_bsr, "assembly_gbs": B_asm_bsr / (asm_ms * 1e-3) / 1e9,
+                "assembly_frac_of_peak": B_asm_bsr / (asm_ms * 1e-3) / 1e9 / peak},
+            "assembly": {"kernel": "k_assemble_edge (F + solution-dependent channel values, per Newton iteration)",
+                         "algorithmic_bytes": B_asm, "ms": asm_ms, "achieved": B_asm / (asm_ms * 1e-3) / 1e9,
+                         "frac": B_asm / (asm_ms * 1e-3) / 1e9 / peak}}
+    else:
+        J = ctx.zeros(ctx.nnz)
+        ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(u_dev), ctx.ptr(Fv), ctx.ptr(J), 3))
+        spmv_ms = timed(lambda: ctx._check(lib.fb_spmv(ctx.h, ctx.ptr(J), ctx.ptr(x), ctx.ptr(y))), 30)
+        B_spmv = 8 * spec.npairs * nnzb + 4 * nnzb + 4 * (mesh.num_vertices + 1) + 16 * N
+        ach = B_spmv / (spmv_ms * 1e-3) / 1e9
+        roofline = {"kernel": "k_spmv", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes": B_spmv, "ms": spmv_ms}
+
+    out = {
+        "metric": METRIC, "value": N * newton_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if transient else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config,
+        "newton_iterations_per_step": newton_per_step, "linear_iterations_per_step": linear_per_step,
+        "phase_ms": {"assemble_F_later_iterations": phase[0], "assemble_first_iteration": phase[1],
+                     "linear_solve": phase[2], "update": phase[3]},
+        "solver": {"ksp": "gmres(30)", "pc": "chebyshev polynomial of the block-Jacobi-scaled operator"
+                   if info[0] else "block-Jacobi",
+                   "chebyshev_interval": [info[1], info[2]], "operator_applications_per_krylov_iteration": info[3],
+                   "operator": "channel operator" if channel else "block-CSR", "host_setup_s": setup_s},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+    }
+    # ---- the answer: parity with the oracle on a bounded sample, which is also the CPU baseline --
+    nsteps = 2 if transient else 1
+    ndofs, secs, its, ref_field = oracle_steps(args.workload, args.parity_n, nsteps)
+    rel, gits, cheb, chan = gpu_parity(args.workload, args.parity_n, nsteps, ref_field)
+    out["parity_rel_l2"] = rel
+    out["parity"] = {"n": args.parity_n, "dofs": int(ndofs), "steps": nsteps, "newton_iterations_gpu": gits,
+                     "newton_iterations_oracle": its, "chebyshev_path": cheb, "channel_operator": chan,
+                     "tolerance": 1e-8}
+    out["cpu_baseline"] = {
+        "value": ndofs * sum(its) / sum(secs), "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"same problem on an n={args.parity_n} mesh ({ndofs} dofs), {nsteps} "
+                  f"{'time steps' if transient else 'steady solve'}: numpy assembly + SuperLU Newton solve, "
+                  f"{sum(secs):.1f} s; restated reference path, not dolfinx+PETSc"}
+    print(json.dumps(out))
+    assert rel < 1e-8, f"parity with the oracle lost: rel L2 {rel:.3e}"
+    assert gits == its, f"Newton iteration counts differ: GPU {gits}, oracle {its}"
+
+
+# ---------------------------------------------------------------------------------------------
+# N > 1: the mesh partitioned over the ranks
+# ---------------------------------------------------------------------------------------------
 def run_partitioned(args, rank, world, local_rank, config):
-    """N > 1: the mesh is partitioned over the ranks (weak scaling: one C1 per GPU);
-    halo exchange + all-reduce over NCCL, max-over-ranks device timing."""
+    """N > 1: the mesh is partitioned over the ranks (one C1-sized block per GPU, weak scaling);
+    halo exchange + dot products over NVLink peer memory, max-over-ranks device timing."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -148,7 +468,7 @@ def run_partitioned(args, rank, world, local_rank, config):
     from festim_b200.distributed import DistributedBackend
 
     grid = proc_grid(world)
-    model, H, exact = build_workload(args.workload, args.n, grid)
+    model = build_c1(args.n, grid)
     model.solver_backend = DistributedBackend(device=local_rank)
     model.initialise()
     solver = model.solver
@@ -218,7 +538,6 @@ def run_partitioned(args, rank, world, local_rank, config):
         config.update({"parallelism": f"mesh partitioned over {world} GPUs (RCB, grid {grid}), " + how,
                        "cells": 6 * args.n ** 3 * world, "dofs": int(N_global),
                        "halo_bytes_per_exchange_rank0": solver.halo.bytes_per_exchange})
-        nloc = solver.part.n_owned
         print(json.dumps({
             "metric": METRIC, "value": N_global / (ms * 1e-3 / its), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -228,11 +547,10 @@ def run_partitioned(args, rank, world, local_rank, config):
                     "h2d_bytes_per_step": 8 * ctx.n_dofs + 8 * len(solver._bc_dofs),
                     "d2h_bytes_per_step": 8 * int(N_global), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
-            "roofline": None, "owned_vertices_rank0": int(nloc),
-            "cuda_graph": bool(solver._graph is not None), "peer_memory_cg": bool(solver.peer),
+            "roofline": None, "owned_vertices_rank0": int(solver.part.n_owned),
+            "peer_memory_cg": bool(solver.peer),
             "note": "weak scaling: one C1-sized block of the domain per GPU, so the global problem and "
-                    "its CG iteration count grow with N; block-Jacobi preconditioner (the per-SM coarse "
-                    "space of the single-GPU kernel is not used across ranks yet)"}))
+                    "its CG iteration count grow with N"}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -243,276 +561,51 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="c1")
-    ap.add_argument("--n", type=int, default=55)
-    ap.add_argument("--cpu-n", type=int, default=24)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--parity-n", type=int, default=None)
+    ap.add_argument("--ref-n", type=int, default=None)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"C1: 3D unit-cube MMS steady diffusion (reference test_1_mobile_MMS_3D), "
-                          f"P1 tets n={args.n}", "n": args.n,
-              "cells": 6 * args.n ** 3, "dofs": (args.n + 1) ** 3,
-              "l2": "L2 flushed (512 MiB write) between timed steps",
-              "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (weak)"}
+    if args.workload is None:
+        args.workload = "c2" if max(world, args.gpus) == 1 else "c1"
+    if args.workload not in ("c1", "c2"):
+        raise SystemExit(f"unknown workload {args.workload}")
+    if args.n is None:
+        args.n = 94 if args.workload == "c2" else 55
+    if args.parity_n is None:
+        args.parity_n = 16 if args.workload == "c2" else 24
+    if args.ref_n is None:
+        args.ref_n = 12 if args.workload == "c2" else 24
+    config = {"workload": workload_name(args.workload, args.n), "n": args.n,
+              "l2": "L2 flushed (512 MiB write) between timed steps; every streamed array is larger than L2"
+              if args.workload == "c2" else "L2 flushed (512 MiB write) between timed steps",
+              "parallelism": "1 GPU" if world == 1 else f"{world} GPUs"}
+    if args.workload == "c2":
+        cells, nv, dofs = c2_counts(args.n)
+        config.update({"cells": cells, "dofs": dofs, "species": 12})
+    else:
+        config.update({"cells": 6 * args.n ** 3, "dofs": (args.n + 1) ** 3})
 
     if args.impl == "reference":
         if rank != 0:
             return
-        warm = max(args.warmup, 0)
-        for _ in range(min(warm, 1)):
-            run_cpu_sample(8)
-        # all host cores: the port is single-threaded (numpy + SuperLU), so one independent
-        # replica of the sample per core, started together; throughput = work of all / wall
-        import multiprocessing as mp
+        return run_reference(args, config)
 
-        cores = max(1, min(os.cpu_count() or 1, 64))
-        os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
-        reps = max(1, min(args.steps, 3))
-        best = None
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            with mp.get_context("fork").Pool(cores) as pool:
-                vals = pool.map(run_cpu_sample, [args.cpu_n] * cores)
-            wall = time.perf_counter() - t0
-            best = wall if best is None else min(best, wall)
-        ndofs, its = vals[0][1], vals[0][3]
-        secs = best
-        v = cores * ndofs * its / best
-        sample = (f"{cores} independent replicas (one per host core) of the same problem on an "
-                  f"n={args.cpu_n} mesh ({ndofs} dofs each): numpy assembly + SuperLU Newton solve, "
-                  f"{secs:.2f} s wall for all, {its} Newton it")
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / its,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "restated reference path (numpy/scipy SuperLU), NOT dolfinx+PETSc "
-                    "(absent from this image)"}))
-        return
-
-    import numpy as np
     import torch
 
     import __graft_entry__ as g
 
-    g.build()
     if world > 1:
         import torch.distributed as dist
 
+        g.build()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    import ctypes as C
-
-    from festim_b200.backend import B200Backend
-
-    if world > 1:
+        torch.cuda.set_device(local_rank)
         return run_partitioned(args, rank, world, local_rank, config)
-    model, H, exact = build_workload(args.workload, args.n)
-    model.solver_backend = B200Backend(device=local_rank)
-    model.initialise()
-    solver = model.solver
-    ctx = solver.ctx
-    lib = ctx.lib
-    N = ctx.n_dofs
-    nnzb = len(solver.spec.mesh.graph[1])
-    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
-    u0 = np.zeros(N)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident steps ("value") -----------------------------------------
-    solver._push_state()
-    u_dev = ctx.zeros(N)
-    n_its, reason, lin = C.c_int(0), C.c_int(0), C.c_int(0)
-    fnorm = C.c_double(0.0)
-
-    load_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
-
-    def device_step():
-        # the whole hot path of one steady solve: coefficient cache + load vector
-        # (source integration, part of "assemble F"), then Newton
-        u_dev.zero_()
-        load_ev[0].record()
-        ctx._check(lib.fb_update_load(ctx.h))
-        load_ev[1].record()
-        rc = lib.fb_newton_solve(ctx.h, ctx.ptr(u_dev), ctx.ptr(u_dev), float(solver.atol),
-                                 float(solver.rtol), solver.stol, solver.max_it, solver.ksp,
-                                 solver.pc, solver.ksp_rtol, solver.ksp_max_it, C.byref(n_its),
-                                 C.byref(reason), C.byref(fnorm), C.byref(lin))
-        ctx._check(rc)
-        assert reason.value > 0, reason.value
-
-    for _ in range(args.warmup):
-        device_step()
-    sampler = ClockSampler()
-    sampler.start()
-    barrier()
-    l0 = ctx.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    phase = np.zeros(4)
-    load_ms = 0.0
-    for k in range(args.steps):
-        flush.fill_(float(k))
-        ev[k][0].record()
-        device_step()
-        ev[k][1].record()
-        tm = (C.c_double * 4)()
-        lib.fb_last_timings(ctx.h, tm)
-        phase += np.array(list(tm))
-        torch.cuda.synchronize()
-        load_ms += load_ev[0].elapsed_time(load_ev[1])
-    barrier()
-    launches = ctx.launches - l0
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    newton_its = max(n_its.value, 1)
-    lin_its = lin.value
-    phase /= args.steps
-    load_ms /= args.steps
-
-    # ---- end to end through the public API ("e2e") -------------------------------
-    def api_step():
-        model.u.x.array[:] = u0
-        solver._signature = None  # a fresh steady solve integrates its sources again
-        solver.solve()
-        return float(model.u.x.array[0])
-
-    api_step()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(float(k))
-        api_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    h2d = 8 * N + 8 * len(solver._bc_dofs)
-    d2h = 8 * N
-
-    # ---- roofline of the dominant kernel (fused SpMV + dots of the CG iteration) ----
-    J = ctx.zeros(ctx.nnz)
-    Fv = ctx.zeros(N)
-    ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(u_dev), ctx.ptr(Fv), ctx.ptr(J), 3))
-    x = torch.rand(N, dtype=torch.float64, device=ctx.device)
-    y = ctx.zeros(N)
-    reps = 50
-    for _ in range(5):
-        lib.fb_spmv(ctx.h, ctx.ptr(J), ctx.ptr(x), ctx.ptr(y))
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
-        lib.fb_spmv(ctx.h, ctx.ptr(J), ctx.ptr(x), ctx.ptr(y))
-    b.record()
-    torch.cuda.synchronize()
-    spmv_ms = a.elapsed_time(b) / reps
-    a.record()
-    for _ in range(reps):
-        lib.fb_assemble(ctx.h, ctx.ptr(u_dev), ctx.ptr(u_dev), ctx.ptr(Fv), ctx.ptr(J), 3)
-    b.record()
-    torch.cuda.synchronize()
-    asm_ms = a.elapsed_time(b) / reps
-    peak, peak_src = peaks()
-    B_spmv = spmv_bytes(solver.spec, nnzb)
-    B_asm = assembly_bytes(solver.spec, nnzb)
-    # dominant kernel of the timed region: the persistent PCG kernel (one cooperative
-    # launch per linear solve).  Algorithmic bytes per launch = iterations x (SpMV bytes +
-    # 11 vector passes of 8N bytes: p,s,x,r,u read+written, w written+read).
-    its_c, rr_c = C.c_int(0), C.c_double(0.0)
-    yv = ctx.zeros(N)
-    for _ in range(2):
-        lib.fb_linear_solve(ctx.h, ctx.ptr(J), ctx.ptr(Fv), ctx.ptr(yv), solver.ksp, 0, solver.ksp_rtol,
-                            0.0, solver.ksp_max_it, C.byref(its_c), C.byref(rr_c))
-    a.record()
-    for _ in range(5):
-        lib.fb_linear_solve(ctx.h, ctx.ptr(J), ctx.ptr(Fv), ctx.ptr(yv), solver.ksp, 0, solver.ksp_rtol,
-                            0.0, solver.ksp_max_it, C.byref(its_c), C.byref(rr_c))
-    b.record()
-    torch.cuda.synchronize()
-    cg_ms = a.elapsed_time(b) / 5
-    B_cg = max(its_c.value, 1) * (B_spmv + 11 * 8 * N)
-    ach = B_cg / (cg_ms * 1e-3) / 1e9
-    large = os.path.join(ROOT, "profiles", "r1_c2_n94_measure.json")
-    # DRAM bytes of one k_cg_persistent launch from the committed ncu --set full capture
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")) as fh:
-            for e in json.load(fh):
-                if "k_cg_persistent" in e.get("kernel", ""):
-                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-                    traffic = 0.0
-                    for key, val in e.items():
-                        if key.startswith("dram__bytes_read.sum") or key.startswith("dram__bytes_write.sum"):
-                            traffic += float(val) * scale[key[key.index("[") + 1:-1]]
-                    break
-    except (OSError, ValueError, KeyError):
-        traffic = None
-    roofline = {"kernel": "k_cg_persistent (whole two-level PCG solve in one cooperative launch)",
-                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": B_cg, "ms": cg_ms,
-                "iterations": its_c.value,
-                "note": "bytes = iterations x (SpMV bytes + 11 vector passes): what a streaming CG must "
-                        "move; C1's 34 MB operator is L2-resident and this kernel keeps it in shared "
-                        "memory, so the fraction is against the HBM copy peak but nothing here comes "
-                        "from HBM (traffic = DRAM bytes of one launch, profiles/r1_ncu_full_summary.json); "
-                        "the iteration is bound by two grid barriers (see DESIGN.md); ms is the whole "
-                        "fb_linear_solve (kernel + coarse operator set-up + residual check), so the "
-                        "fraction is conservative",
-                "spmv": {"kernel": "k_spmv", "algorithmic_bytes": B_spmv, "ms": spmv_ms,
-                         "achieved": B_spmv / (spmv_ms * 1e-3) / 1e9,
-                         "frac": B_spmv / (spmv_ms * 1e-3) / 1e9 / peak},
-                "assembly": {"kernel": "k_assemble_nodes<3> (F+J gather)", "algorithmic_bytes": B_asm,
-                             "ms": asm_ms, "achieved": B_asm / (asm_ms * 1e-3) / 1e9,
-                             "frac": B_asm / (asm_ms * 1e-3) / 1e9 / peak}}
-    if os.path.exists(large):
-        try:
-            lc = json.loads(open(large).read().strip().splitlines()[-1])
-            roofline["beyond_L2_config"] = {
-                "source": "profiles/r1_c2_n94_measure.json (tools/measure_large.py, C2: 5.0 M cells, "
-                          "10.3 M dofs, 6.7 GB Jacobian)",
-                "spmv_frac": lc["spmv"]["frac"], "spmv_gbs": lc["spmv"]["gbs"],
-                "assembly_frac": lc["assembly_F_and_J"]["frac"], "assembly_ms": lc["assembly_F_and_J"]["ms"]}
-        except Exception:
-            pass
-
-    val = N / (ms * 1e-3 / newton_its)
-    e2e_val = N / (e2e_s / newton_its)
-    if world > 1:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=ctx.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
-        val = world * N / (ms * 1e-3 / newton_its)
-        e2e_val = world * N / (e2e_s / newton_its)
-    if rank != 0:
-        return
-    out = {
-        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-        "newton_iterations_per_step": newton_its, "linear_iterations_per_step": lin_its,
-        "phase_ms": {"load_vector_and_coefficients": load_ms, "assemble_F": phase[0],
-                     "assemble_J": phase[1], "linear_solve": phase[2], "update": phase[3]},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3},
-        "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-    }
-    if world == 1:
-        t0 = time.perf_counter()
-        v, ndofs, secs, its = run_cpu_sample(args.cpu_n)
-        out["cpu_baseline"] = {
-            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"same problem on an n={args.cpu_n} mesh ({ndofs} dofs): numpy assembly + "
-                      f"SuperLU Newton solve, {secs:.2f} s per solve ({its} Newton it); "
-                      "restated reference path, not dolfinx+PETSc"}
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    return run_single(args, config)
 
 
 if __name__ == "__main__":

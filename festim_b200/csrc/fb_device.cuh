@@ -11,7 +11,8 @@
 #define FB_MAX_D1 4
 #define FB_KB 8.6173303e-5  // Boltzmann constant eV/K, reference src/festim/__init__.py:11
 #define FB_STACK 24
-#define FB_CHUNK 16           // block rows staged together by the TMA-pipelined row kernels
+#define FB_CHUNK 12           // block rows staged together by the TMA-pipelined row kernels (multiple of 4)
+#define FB_CHUNK_GROUPS 2     // consumer groups of FB_CHUNK warps working on alternate chunks
 
 // Everything a kernel needs, passed by value (lives in the constant bank).
 struct DevSpec {

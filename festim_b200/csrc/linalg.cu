@@ -265,11 +265,12 @@ static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
   a.n_sp_ent = ctx->n_sp_ent;
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-  int nst = 4;
+  // the ring must hold the chunks the consumer groups work on plus at least one in flight per group
+  int nst = 3 * FB_CHUNK_GROUPS;
   if (getenv("FB_SPMV_STAGES")) nst = atoi(getenv("FB_SPMV_STAGES"));
   if (nst > 8) nst = 8;
   size_t smem = fb_spmv_ch_layout(S, a, MODE, nst);
-  while (nst > 2 && smem > (size_t)smem_max) smem = fb_spmv_ch_layout(S, a, MODE, --nst);
+  while (nst > FB_CHUNK_GROUPS + 1 && smem > (size_t)smem_max) smem = fb_spmv_ch_layout(S, a, MODE, --nst);
   if (smem > (size_t)smem_max) return fb_fail(ctx, "channel SpMV: a chunk does not fit in shared memory");
   const long long nchunks = (S.n_owned + FB_CHUNK - 1) / FB_CHUNK;
   long long grid = ctx->sm_count;
@@ -280,7 +281,7 @@ static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
   {                                                                                                          \
     FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_spmv_ch_tma<M, N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        (int)smem));                                                          \
-    k_spmv_ch_tma<M, N, MODE><<<(unsigned)grid, 32 * FB_CHUNK + 32, smem, ctx->stream>>>(S, a);                   \
+    k_spmv_ch_tma<M, N, MODE><<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, smem, ctx->stream>>>(S, a);                   \
   }
   if (mt == 1 && nt == 1) FB_SPMV_CASE(1, 1)
   else if (mt == 1) FB_SPMV_CASE(1, 2)
@@ -501,6 +502,110 @@ __global__ void k_bjacobi_setup(DevSpec S, const double* __restrict__ J, double*
   }
   for (int s = 0; s < ns; ++s)
     for (int c = 0; c < ns; ++c) dinv[(v * ns + s) * ns + c] = B[s][c];
+}
+
+// The same inversion, G lanes per vertex with the block in shared memory: in-place Gauss-Jordan
+// with row pivoting (row interchanges undone as column interchanges at the end).  The
+// thread-per-vertex kernel above keeps two ns x ns arrays per thread in local memory, which
+// costs 10 ms for 857 k blocks of 12 x 12; this one stays on chip.
+template <int G>
+__global__ void __launch_bounds__(256)
+k_bjacobi_setup_coop(DevSpec S, const double* __restrict__ J, double* __restrict__ dinv, int* __restrict__ flags) {
+  extern __shared__ double bj_smem[];
+  const int g = threadIdx.x & (G - 1), grp = threadIdx.x / G, gpb = blockDim.x / G;
+  const long long v = (long long)blockIdx.x * gpb + grp;
+  if (v >= S.n_owned) return;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  const int ns = S.ns, nn = ns * ns;
+  double* A = bj_smem + (size_t)grp * (nn + 2 * ns + 2);
+  double* prow = A + nn;
+  double* fcol = prow + ns;
+  const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+  int kself = 0;
+  for (int k = g; k < deg; k += G)
+    if (S.colidx[r0 + k] == v) kself = k;
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) { const int t = __shfl_xor_sync(gmask, kself, o); kself = t > kself ? t : kself; }
+  for (int t = g; t < nn; t += G) A[t] = 0.0;
+  __syncwarp(gmask);
+  if (!J) {
+    const unsigned vi = S.vinfo[v] & 0xffffu;
+    const int* __restrict__ jtp = S.vx_itab + S.vx_o_jtptr;
+    const int* __restrict__ jt = S.vx_itab + S.vx_o_jt;
+    const double* __restrict__ jtc = S.vx_dtab + S.vx_o_jtc;
+    const double* __restrict__ st = S.et_stat + (long long)(r0 + kself) * S.vx_nsp;
+    const double* __restrict__ dy = S.et_dyn + (long long)(r0 + kself) * S.vx_ndp;
+    for (int p = g; p < S.npairs; p += G) {
+      const int s = S.pair_row[p], c = S.pair_cs[p];
+      double val = 0.0;
+      for (int e = jtp[p]; e < jtp[p + 1]; ++e) {
+        const int chan = jt[2 * e];
+        double coef = jtc[e];
+        if (jt[2 * e + 1] & 1) coef *= S.inv_dt;
+        val += coef * (chan < S.vx_nstat ? st[chan] : dy[chan - S.vx_nstat]);
+      }
+      if ((vi >> c) & 1u) val = 0.0;
+      if ((vi >> s) & 1u) val = (c == s) ? 1.0 : 0.0;
+      A[s * ns + c] = val;
+    }
+  } else {
+    const long long base = (long long)(r0 + kself) * S.npairs;
+    for (int p = g; p < S.npairs; p += G) A[S.pair_row[p] * ns + S.pair_cs[p]] = J[base + p];
+  }
+  __syncwarp(gmask);
+  unsigned long long perm = 0ull;   // 4 bits per column: the row it was swapped with
+  for (int col = 0; col < ns; ++col) {
+    // pivot: largest |A[r][col]|, r >= col (ties -> smallest r)
+    double best = -1.0;
+    int piv = col;
+    for (int r = col + g; r < ns; r += G) {
+      const double a = fabs(A[r * ns + col]);
+      if (a > best) { best = a; piv = r; }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(gmask, best, o);
+      const int op = __shfl_xor_sync(gmask, piv, o);
+      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    }
+    if (best == 0.0) { if (g == 0) flags[2] = 1; best = 1.0; }
+    perm |= (unsigned long long)piv << (4 * col);
+    if (piv != col)
+      for (int c = g; c < ns; c += G) { const double t = A[col * ns + c]; A[col * ns + c] = A[piv * ns + c]; A[piv * ns + c] = t; }
+    __syncwarp(gmask);
+    const double ip = 1.0 / (A[col * ns + col] == 0.0 ? 1.0 : A[col * ns + col]);
+    __syncwarp(gmask);
+    for (int c = g; c < ns; c += G) prow[c] = (c == col ? 1.0 : A[col * ns + c]) * ip;
+    for (int r = g; r < ns; r += G) fcol[r] = A[r * ns + col];
+    __syncwarp(gmask);
+    for (int t = g; t < nn; t += G) {
+      const int r = t / ns, c = t - r * ns;
+      if (r == col) A[t] = prow[c];
+      else A[t] = (c == col ? 0.0 : A[t]) - fcol[r] * prow[c];
+    }
+    __syncwarp(gmask);
+  }
+  for (int col = ns - 1; col >= 0; --col) {   // undo the row interchanges on the columns
+    const int piv = (int)((perm >> (4 * col)) & 0xfull);
+    if (piv != col) {
+      for (int r = g; r < ns; r += G) { const double t = A[r * ns + col]; A[r * ns + col] = A[r * ns + piv]; A[r * ns + piv] = t; }
+      __syncwarp(gmask);
+    }
+  }
+  double* __restrict__ out = dinv + v * (long long)nn;
+  for (int t = g; t < nn; t += G) out[t] = A[t];
+}
+
+static int bjacobi_setup(fb_ctx* ctx, const double* J) {
+  const DevSpec& S = ctx->S;
+  if (S.ns == 1 || S.ns > 16 || getenv("FB_BJ_THREAD")) {
+    FB_LAUNCH(ctx, k_bjacobi_setup, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, J, ctx->d_dinv, ctx->d_flags);
+    return 0;
+  }
+  const int G = 16, gpb = 256 / G;
+  const size_t smem = (size_t)gpb * (S.ns * S.ns + 2 * S.ns + 2) * sizeof(double);
+  FB_LAUNCH(ctx, k_bjacobi_setup_coop<16>, (unsigned)((S.n_owned + gpb - 1) / gpb), 256, smem, S, J, ctx->d_dinv, ctx->d_flags);
+  return 0;
 }
 
 __device__ __forceinline__ void bjacobi_apply(int ns, const double* __restrict__ dinv, long long v,
@@ -2008,7 +2113,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
     return 0;
   }
   const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
-  FB_LAUNCH(ctx, k_bjacobi_setup, gn, FB_TPB, 0, S, J, ctx->d_dinv, ctx->d_flags);
+  if ((rc = bjacobi_setup(ctx, J))) return rc;
   if (ksp == FB_KSP_CG && (rc = coarse_setup(ctx, J))) return rc;
   // stopping rule on the preconditioned residual, ||M^-1 r|| <= max(rtol ||M^-1 b||, atol)
   // (PETSc default for left-preconditioned CG/GMRES); block-Jacobi makes it row-scaled,
@@ -2594,7 +2699,7 @@ extern "C" int fb_bjacobi_setup(fb_ctx* ctx, const double* J) {
   int rc = fbi_ensure_workspace(ctx);
   if (rc) return rc;
   const DevSpec& S = ctx->S;
-  FB_LAUNCH(ctx, k_bjacobi_setup, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, J, ctx->d_dinv, ctx->d_flags);
+  if (int rc = bjacobi_setup(ctx, J)) return rc;
   FB_CHECK(ctx, cudaGetLastError());
   return 0;
 }

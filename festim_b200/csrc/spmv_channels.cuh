@@ -128,6 +128,8 @@ inline void fb_dmma(double& c0, double& c1, double a, double b) {
 }
 #endif
 
+#define FB_SP_EPL 6   // table entries per lane kept in registers (two lanes per row species)
+
 struct SpmvChArgs {
   const double* x;
   double* y;
@@ -154,13 +156,13 @@ __host__ inline size_t fb_spmv_ch_layout(const DevSpec& S, SpmvChArgs& a, int mo
   size_t o = 0;
   o += up16((size_t)a.n_sp_ent * 8);                       // t_coef
   o += up16((size_t)(ns + 1 + a.n_sp_ent) * 4);            // t_ptr, t_combo
-  const int tail = 256 + a.n_sp_ent;   // the (channel x species) products of a row, then the weighted table entries
-  a.o_part = (int)o; a.part_bytes = (int)up16((size_t)(tail + ns) * 8); o += (size_t)CH * a.part_bytes;
+  // per consumer warp: the (channel x species) product tile of its row, then the row's result
+  a.o_part = (int)o; a.part_bytes = (int)up16((size_t)(256 + ns) * 8); o += (size_t)CH * FB_CHUNK_GROUPS * a.part_bytes;
   a.o_ybuf = 0;
   size_t s = 0;
   s += up16((size_t)CH * md * S.vx_nsp * 8);               // static channel values
   a.s_dyn = (int)s; s += up16((size_t)CH * md * S.vx_ndp * 8);
-  a.s_xs = (int)s; s += up16((size_t)S.ck_nx_max * ns * 8);
+  a.s_xs = (int)s; s += up16((size_t)(S.ck_nx_max + 2) * ns * 8);   // + tile padding read past the last vertex
   a.s_dinv = (int)s; if (mode >= 1) s += up16((size_t)CH * ns * ns * 8);
   a.s_r = (int)s; if (mode == 2) s += up16((size_t)CH * ns * 8);
   a.s_z = (int)s; if (mode == 2) s += up16((size_t)CH * ns * 8);
@@ -177,7 +179,7 @@ __host__ inline size_t fb_spmv_ch_layout(const DevSpec& S, SpmvChArgs& a, int mo
 }
 
 template <int MT, int NT, int MODE>
-__global__ void __launch_bounds__(32 * FB_CHUNK + 32, 1)
+__global__ void __launch_bounds__(32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, 1)
 k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
   extern __shared__ __align__(16) unsigned char fb_sp_smem[];
   if (a.flags && a.flags[0]) return;
@@ -199,12 +201,17 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
   unsigned long long* empty = full + 8;
   if (threadIdx.x == 0)
     for (int q = 0; q < NST; ++q) { fb_mbar_init(&full[q], 1); fb_mbar_init(&empty[q], CH); }
+  // tile padding of the DMMA operands is read from the stages: it must be finite
+  for (size_t t = threadIdx.x; t < (size_t)NST * a.stage_bytes / 16; t += blockDim.x)
+    ((double2*)(fb_sp_smem + a.o_stage0))[t] = make_double2(0.0, 0.0);
+  fb_fence_proxy_async();
   fb_mbar_fence_init();
   __syncthreads();
   const long long nchunks = (S.n_owned + CH - 1) / CH;
   const long long nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == CH) {
+  constexpr int NG = FB_CHUNK_GROUPS;
+  if (warp == CH * NG) {
     // ================= producer warp: every operand of a chunk through the TMA unit ==================
     // descriptors of chunk i+1 are fetched while the copies of chunk i are issued
     int pf_e0, pf_ne, pf_nx, pf_lc, pf_q0 = 0, pf_q1 = 0, pf_run[3];
@@ -262,25 +269,23 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
     return;
   }
 
-  // ================= consumer warps: warp j multiplies row j of every chunk ==========================
+  // ================= consumer warps: group g = warp / CH takes the chunks i = g, g + NG, ...;
+  // its warp j multiplies row j of each of them ======================================================
   double* part = (double*)(fb_sp_smem + a.o_part + (size_t)warp * a.part_bytes);
-  double* wgt = part + 256;
-  double* yrow = wgt + a.n_sp_ent;
+  double* yrow = part + 256;
+  const int grp = warp / CH, wrow = warp - grp * CH;
   // DMMA fragments of this lane: channels 8 mt + (lane >> 2) (A operand), column species
   // 8 nt + (lane >> 2) (B operand); channel values of an edge are strided by nsp / ndp
   const int nch = S.vx_nch;
   int aoff[MT], astr[MT];
-  bool adyn[MT], aok[MT], bok[NT];
+  bool adyn[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int ch = 8 * mt + (lane >> 2);
-    aok[mt] = ch < nch;
-    adyn[mt] = ch >= S.vx_nstat;
-    aoff[mt] = adyn[mt] ? ch - S.vx_nstat : ch;
+    adyn[mt] = ch >= S.vx_nstat && ch < nch;   // padding channels read the static block (values unused)
+    aoff[mt] = adyn[mt] ? ch - S.vx_nstat : (ch < nch ? ch : 0);
     astr[mt] = adyn[mt] ? NDP : NSP;
   }
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) bok[nt] = 8 * nt + (lane >> 2) < ns;
   const int bcol = lane >> 2, kq = lane & 3;
   // the table entries of row species s are added by lanes s and s + 16
   const int srow = lane & 15;
@@ -289,15 +294,16 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
     const int p0 = t_ptr[srow], p1 = t_ptr[srow + 1], mid = (p0 + p1 + 1) >> 1;
     e_lo = lane < 16 ? p0 : mid; e_hi = lane < 16 ? mid : p1;
   }
-  for (long long i = 0; i < nmine; ++i) {
+
+  for (long long i = grp; i < nmine; i += NG) {
     const int sidx = (int)(i % NST);
     const long long c = blockIdx.x + i * (long long)gridDim.x;
     const long long c0 = c * CH;
     const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
     unsigned char* st = fb_sp_smem + a.o_stage0 + (size_t)sidx * a.stage_bytes;
     fb_mbar_wait(&full[sidx], (unsigned)((i / NST) & 1));
-    if (warp < nrow) {
-      const int j = warp;
+    if (wrow < nrow) {
+      const int j = wrow;
       const double* stat_s = (const double*)st;
       const double* dyn_s = (const double*)(st + a.s_dyn);
       const double* xs = (const double*)(st + a.s_xs);
@@ -321,29 +327,38 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
       const double* ap[MT];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) ap[mt] = (adyn[mt] ? dr : sr) + aoff[mt];
+      // Edges beyond the row (k >= deg) are cancelled through the B operand alone: the A operand
+      // then reads finite values of the next row.  Channels >= nch and species >= ns are tile
+      // padding: their products land in entries of T no table refers to.
+      const double* xb = xs + 8 * 0 + bcol;
       for (int kb = 0; kb < deg; kb += 16) {
         // all operand loads of four K steps first, then the sixteen DMMAs
-        int lck[4];
-        bool val[4];
-        unsigned msk[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = kb + 4 * u + kq;
-          val[u] = k < deg;
-          lck[u] = val[u] ? lc[k] : 0;
-          msk[u] = 0u;
-          if (colbc && val[u]) msk[u] = S.vinfo[S.colidx[e0 + rp0 + k]];   // eliminated (Dirichlet) columns read as zero
-        }
         double av[4][MT], bv[4][NT];
+        if (!colbc) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = kb + 4 * u + kq;
+          for (int u = 0; u < 4; ++u) {
+            const int k = kb + 4 * u + kq;
+            const bool val = k < deg;
+            const double* xk = xb + (size_t)lc[val ? k : 0] * ns;
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) av[u][mt] = (val[u] && aok[mt]) ? ap[mt][k * astr[mt]] : 0.0;
+            for (int mt = 0; mt < MT; ++mt) av[u][mt] = ap[mt][k * astr[mt]];
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            const int c2 = 8 * nt + bcol;
-            bv[u][nt] = (val[u] && bok[nt] && !((msk[u] >> c2) & 1u)) ? xs[(size_t)lck[u] * ns + c2] : 0.0;
+            for (int nt = 0; nt < NT; ++nt) { const double xv = xk[8 * nt]; bv[u][nt] = val ? xv : 0.0; }
+          }
+        } else {   // eliminated (Dirichlet) columns read as zero
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = kb + 4 * u + kq;
+            const bool val = k < deg;
+            const unsigned msk = val ? S.vinfo[S.colidx[e0 + rp0 + k]] : 0u;
+            const double* xk = xb + (size_t)lc[val ? k : 0] * ns;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) av[u][mt] = ap[mt][k * astr[mt]];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+              const double xv = xk[8 * nt];
+              bv[u][nt] = (val && !((msk >> (8 * nt + bcol)) & 1u)) ? xv : 0.0;
+            }
           }
         }
 #pragma unroll
@@ -362,8 +377,17 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
         }
       __syncwarp();
       // y_s = sum_e coef_e T[combo_e]: two lanes per row species, one shuffle
-      double sum = 0.0;
-      for (int e = e_lo; e < e_hi; ++e) sum += t_coef[e] * part[t_combo[e]];
+      // (all table loads are independent of the products: issued ahead of the DMMA results)
+      double sum = 0.0, sum2 = 0.0;
+#pragma unroll
+      for (int u = 0; u < FB_SP_EPL; u += 2) {
+        const int ea = e_lo + u, eb = e_lo + u + 1;
+        const double ca = ea < e_hi ? t_coef[ea] : 0.0, cb = eb < e_hi ? t_coef[eb] : 0.0;
+        sum += ca * part[ea < e_hi ? t_combo[ea] : 0];
+        sum2 += cb * part[eb < e_hi ? t_combo[eb] : 0];
+      }
+      for (int e = e_lo + FB_SP_EPL; e < e_hi; ++e) sum += t_coef[e] * part[t_combo[e]];
+      sum += sum2;
       sum += __shfl_xor_sync(FULL, sum, 16);
       const long long dof = (c0 + j) * ns + lane;
       if (lane < ns) {
@@ -379,11 +403,13 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
           if (ns == 1) p = ((const double*)(st + a.s_dinv))[t] * yrow[0];
           else {
             const double2* dv = (const double2*)(st + a.s_dinv) + (size_t)t * (ns / 2);   // row s of the inverse block
-            p = 0.0;
+            double pa = 0.0, pb = 0.0;
             for (int c2 = 0; c2 < ns; c2 += 2) {   // ns is even (16-byte rows)
               const double2 d2 = dv[c2 >> 1];
-              p += d2.x * yrow[c2] + d2.y * yrow[c2 + 1];
+              pa += d2.x * yrow[c2];
+              pb += d2.y * yrow[c2 + 1];
             }
+            p = pa + pb;
           }
           if (MODE == 1) a.y[dof] = p;
           else {
