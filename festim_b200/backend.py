@@ -389,8 +389,10 @@ class B200NewtonSolver:
         self._bc_dofs = np.ascontiguousarray(ctx.dofs_to_device_numbering(uniq, spec.ns), dtype=np.int64)
         ctx._check(ctx.lib.fb_set_dirichlet(ctx.h, len(self._bc_dofs),
                                             _np_ptr(self._bc_dofs, C.c_int64)))
-        self.u_dev = ctx.zeros(ctx.n_dofs)
-        self.un_dev = ctx.zeros(ctx.n_dofs)
+        self.u_dev = None
+        self.un_dev = None
+        self._u_version = self._un_version = -1   # host versions the device copies correspond to
+        self.device_resident = True               # fields stay on the device between solves
         self._signature = None
 
     # -- per-step data -----------------------------------------------------------
@@ -434,12 +436,40 @@ class B200NewtonSolver:
             ctx._check(lib.fb_set_velocity(ctx.h, k, ctx.ptr(ctx.nodal_to_device(f"vel{k}", vel.array, spec.tdim))))
         ctx._check(lib.fb_update_load(ctx.h))
 
+    def _sync_fields(self):
+        """Device copies of u and u_n: uploaded only when the host arrays were touched since the
+        last solve (users set initial conditions or edit ``u.x.array`` in place)."""
+        ctx, p, ns = self.ctx, self.problem, self.spec.ns
+        ux, unx = p.u.x, p.u_n.x
+        if self.u_dev is None or ux.version != self._u_version:
+            self.u_dev = ctx.nodal_to_device("u", ux.array, ns)
+            self._u_version = ux.version
+        if not self.spec.transient:
+            return self.u_dev, self.u_dev
+        if self.un_dev is None or unx.version != self._un_version:
+            self.un_dev = ctx.nodal_to_device("u_n", unx.array, ns)
+            self._un_version = unx.version
+        return self.u_dev, self.un_dev
+
+    def copy_solution_to_previous(self):
+        """u_n <- u on the device (reference problem.py:248); False when the host copy of u is the
+        current one, so that the caller does the plain array copy."""
+        p = self.problem
+        if not self.spec.transient or self.u_dev is None or p.u.x.version != self._u_version:
+            return False
+        if self.un_dev is None:
+            self.un_dev = self.ctx.nodal_to_device("u_n", p.u_n.x._array, self.spec.ns)
+        self.un_dev.copy_(self.u_dev)
+        un_dev, ns, ctx = self.un_dev, self.spec.ns, self.ctx
+        p.u_n.x.defer(lambda out: ctx.nodal_from_device(un_dev, ns, out=out))
+        self._un_version = p.u_n.x.version
+        return True
+
     def solve(self):
         ctx, p = self.ctx, self.problem
         self._push_state()
         ns = self.spec.ns
-        u_dev = ctx.nodal_to_device("u", p.u.x.array, ns)
-        un_dev = ctx.nodal_to_device("u_n", p.u_n.x.array, ns) if self.spec.transient else u_dev
+        u_dev, un_dev = self._sync_fields()
         t = float(p.t) if hasattr(p, "t") else 0.0
         atol = self.atol(t) if callable(self.atol) else self.atol
         rtol = self.rtol(t) if callable(self.rtol) else self.rtol
@@ -450,8 +480,9 @@ class B200NewtonSolver:
             self.max_it, self.ksp, self.pc, self.ksp_rtol, self.ksp_max_it,
             C.byref(n_its), C.byref(reason), C.byref(fnorm), C.byref(lin))
         ctx._check(rc)
-        self.u_dev = u_dev
-        ctx.nodal_from_device(u_dev, ns, out=p.u.x.array)
+        # the solution stays on the device; the host array is refreshed when somebody reads it
+        p.u.x.defer(lambda out: ctx.nodal_from_device(u_dev, ns, out=out))
+        self._u_version = p.u.x.version
         self.solver.its = n_its.value
         self.solver.reason = reason.value
         self.solver.linear_its = lin.value
@@ -496,7 +527,7 @@ class B200NewtonSolver:
         self._D_T_dev = None
 
     def _current_u(self):
-        return self.ctx.nodal_to_device("u", self.problem.u.x.array, self.spec.ns)
+        return self._sync_fields()[0]
 
     def total_volume(self, species_index, vol_id):
         out = C.c_double(0.0)

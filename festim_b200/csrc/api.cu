@@ -358,16 +358,14 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_ndp))) return rc;
     FB_CHECK(ctx, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)ctx->nnzb * S.vx_ndp, ctx->stream));
     S.et_dyn = p;
-    if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_nts))) return rc;
-    S.et_tv = p;
-    if ((rc = fb_alloc(ctx, &p, (size_t)ctx->nnzb * S.vx_nts))) return rc;
-    S.et_tw = p;
+    if ((rc = fb_alloc(ctx, &p, (size_t)2 * ctx->nnzb * S.vx_nts))) return rc;
+    S.et_tvw = p;
     unsigned* vinfo = nullptr;
     const size_t nvi = ((size_t)S.n_vertices + FB_CHUNK + 15) & ~(size_t)15;   // whole chunks are bulk-copied
     if ((rc = fb_alloc(ctx, &vinfo, nvi))) return rc;
     FB_CHECK(ctx, cudaMemsetAsync(vinfo, 0, sizeof(unsigned) * nvi, ctx->stream));
     S.vinfo = vinfo;
-    S.et_tz_total = 0; S.et_tz = nullptr; S.et_tzptr = nullptr; S.et_tzslot = nullptr;
+    S.et_tz_total = 0; S.et_tz_chunk_max = 0; S.et_tz = nullptr; S.et_tzptr = nullptr; S.et_tzslot = nullptr; S.et_tzw = nullptr;
     if (S.vx_nts > 0 && (rc = fbi_et_symbolic(ctx))) return rc;
     S.vx_on = 1;
     // the Krylov solvers work on the channel operator itself when it is the smaller format

@@ -25,12 +25,14 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <cstdint>
 #include <cstdlib>
 
 #include "fb_internal.cuh"
 #include "program.cuh"
 #include "assemble_kernels.cuh"
 #include "assemble_edge.cuh"
+#include "assemble_edge_tma.cuh"
 #include "reduce.cuh"
 
 // ---------------------------------------------------------------------------
@@ -70,9 +72,8 @@ __global__ void k_et_symbolic(DevSpec S, int mode, int* __restrict__ width, cons
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_et_setup(DevSpec S, double* __restrict__ stat, double* __restrict__ tv, double* __restrict__ tw,
-           double* __restrict__ tz) {
-  fb_et_setup_body<DIM>(S, stat, tv, tw, tz);
+k_et_setup(DevSpec S, double* __restrict__ stat, double* __restrict__ tvw, double* __restrict__ tz) {
+  fb_et_setup_body<DIM>(S, stat, tvw, tz);
 }
 
 template <int G>
@@ -183,8 +184,8 @@ static int update_coeffs_dim(fb_ctx* ctx) {
   }
   if (S.vx_on) {
     FB_LAUNCH(ctx, k_cell_records<DIM>, gc, B, 0, S, (double*)S.cellrec);
-    FB_LAUNCH(ctx, k_et_setup<DIM>, (unsigned)((S.n_owned + B - 1) / B), B, 0, S, (double*)S.et_stat, (double*)S.et_tv,
-              (double*)S.et_tw, (double*)S.et_tz);
+    FB_LAUNCH(ctx, k_et_setup<DIM>, (unsigned)((S.n_owned + B - 1) / B), B, 0, S, (double*)S.et_stat, (double*)S.et_tvw,
+              (double*)S.et_tz);
   }
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_load, 0, sizeof(double) * S.n_dofs, ctx->stream));
   if (S.n_vterms > 0) {
@@ -277,6 +278,38 @@ static int et_launch(fb_ctx* ctx, int which, const double* u, const double* un, 
   return 0;
 }
 
+// TMA-pipelined Newton-iteration assembly (assemble_edge_tma.cuh): every bulk copy 16-byte aligned
+static bool asm_tma_ok(fb_ctx* ctx, const double* u, const double* un) {
+  const DevSpec& S = ctx->S;
+  return S.vx_on && (S.ns % 2 == 0) && S.ns <= 32 && (((uintptr_t)u & 15) == 0) && (((uintptr_t)un & 15) == 0) &&
+         S.ck_nx_max > 0 && S.vx_nts <= 11 && S.maxdeg <= 64 && !getenv("FB_NO_TMA_ASSEMBLY");
+}
+
+static int asm_tma_launch(fb_ctx* ctx, const double* u, const double* un, double* F, int flags, bool* done) {
+  DevSpec& S = ctx->S;
+  *done = false;
+  AsmTmaArgs a{};
+  a.u = u; a.un = un; a.F = F; a.dyn = (double*)S.et_dyn; a.flags = flags;
+  int smem_max = 0;
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+  int nst = 2 * FB_CHUNK_GROUPS;
+  if (getenv("FB_ASM_STAGES")) nst = atoi(getenv("FB_ASM_STAGES"));
+  if (nst > 8) nst = 8;
+  size_t smem = fb_asm_tma_layout(S, a, nst);
+  while (nst > FB_CHUNK_GROUPS + 1 && smem > (size_t)smem_max) smem = fb_asm_tma_layout(S, a, --nst);
+  if (smem > (size_t)smem_max) return 0;   // a chunk does not fit: the caller takes the row kernel
+  const long long nchunks = (S.n_owned + FB_CHUNK - 1) / FB_CHUNK;
+  long long grid = ctx->sm_count;
+  if (grid > nchunks) grid = nchunks;
+  if (grid < 1) grid = 1;
+  FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_assemble_edge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_assemble_edge_tma<<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, smem, ctx->stream>>>(S, a);
+  ctx->launches++;
+  FB_CHECK(ctx, cudaGetLastError());
+  *done = true;
+  return 0;
+}
+
 int fbi_expand(fb_ctx* ctx, double* J) {
   if (!ctx->S.vx_on) return fb_fail(ctx, "no channel operator to expand");
   return et_launch(ctx, 1, nullptr, nullptr, nullptr, J, 0);
@@ -290,21 +323,30 @@ static int et_symbolic_dim(fb_ctx* ctx) {
   int* d_w = nullptr;
   int* d_err = nullptr;
   int rc;
-  if ((rc = fb_alloc(ctx, &d_w, (size_t)nv + 1))) return rc;
-  d_err = d_w + nv;
-  FB_CHECK(ctx, cudaMemsetAsync(d_w, 0, sizeof(int) * (nv + 1), ctx->stream));
+  const size_t nw = ((size_t)nv + FB_CHUNK + 16) & ~(size_t)15;   // whole chunks of widths are bulk-copied
+  if ((rc = fb_alloc(ctx, &d_w, nw + 4))) return rc;
+  d_err = d_w + nw;
+  FB_CHECK(ctx, cudaMemsetAsync(d_w, 0, sizeof(int) * (nw + 4), ctx->stream));
   const unsigned g = (unsigned)((nv + 127) / 128);
   const long long keep_owned = S.n_owned;
   S.n_owned = nv;
   FB_LAUNCH(ctx, k_et_symbolic<DIM>, g, 128, 0, S, 0, d_w, (const long long*)nullptr, (unsigned char*)nullptr, d_err);
-  std::vector<int> w((size_t)nv + 1);
-  FB_CHECK(ctx, cudaMemcpyAsync(w.data(), d_w, sizeof(int) * (nv + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<int> w(nw + 4);
+  FB_CHECK(ctx, cudaMemcpyAsync(w.data(), d_w, sizeof(int) * (nw + 4), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (w[nv]) { S.n_owned = keep_owned; return fb_fail(ctx, "edge tensor: more than 64 common neighbours on an edge"); }
-  std::vector<long long> ptr((size_t)nv + 1, 0);
+  if (w[nw]) { S.n_owned = keep_owned; return fb_fail(ctx, "edge tensor: more than 64 common neighbours on an edge"); }
+  // slabs padded to multiples of 16 entries: every chunk's extent is a 16-byte aligned bulk copy
+  std::vector<long long> ptr((size_t)nv + 1 + FB_CHUNK + 8, 0);
   for (long long v = 0; v < nv; ++v)
-    ptr[v + 1] = ptr[v] + (long long)w[v] * (ctx->h_rowptr[v + 1] - ctx->h_rowptr[v]);
+    ptr[v + 1] = ptr[v] + (((long long)w[v] * (ctx->h_rowptr[v + 1] - ctx->h_rowptr[v]) + 15) & ~15LL);
+  for (size_t v = (size_t)nv + 1; v < ptr.size(); ++v) ptr[v] = ptr[nv];
   S.et_tz_total = ptr[nv];
+  S.et_tz_chunk_max = 0;
+  for (long long c0 = 0; c0 < nv; c0 += FB_CHUNK) {
+    const long long c1 = c0 + FB_CHUNK < nv ? c0 + FB_CHUNK : nv;
+    if (ptr[c1] - ptr[c0] > S.et_tz_chunk_max) S.et_tz_chunk_max = ptr[c1] - ptr[c0];
+  }
+  S.et_tzw = d_w;
   if ((rc = fb_upload(ctx, &S.et_tzptr, ptr.data(), ptr.size()))) return rc;
   unsigned char* slots = nullptr;
   if ((rc = fb_alloc(ctx, &slots, (size_t)S.et_tz_total + 1))) return rc;
@@ -337,8 +379,10 @@ static int assemble_dim(fb_ctx* ctx, const double* u, const double* un, double* 
   if (S.vx_on) {
     // channel assembly (assemble_edge.cuh): dynamic channel values + residual, then - when the
     // caller wants the block-CSR values - the expansion of the channel operator
-    int rc = et_launch(ctx, 0, u, un, F, nullptr, flags);
-    if (rc) return rc;
+    bool done = false;
+    int rc = 0;
+    if (asm_tma_ok(ctx, u, un) && (rc = asm_tma_launch(ctx, u, un, F, flags, &done))) return rc;
+    if (!done && (rc = et_launch(ctx, 0, u, un, F, nullptr, flags))) return rc;
     if ((flags & FB_ASSEMBLE_J) && J && (rc = et_launch(ctx, 1, nullptr, nullptr, nullptr, J, 0))) return rc;
   } else if (ctx->have_jit) {
     void* args[] = {(void*)&S, (void*)&u, (void*)&un, (void*)&F, (void*)&J, (void*)&flags};

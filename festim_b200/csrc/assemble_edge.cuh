@@ -220,19 +220,20 @@ __device__ __forceinline__ void fb_et_symbolic_body(const DevSpec& S, int mode, 
 // every sum has a fixed order.
 // ---------------------------------------------------------------------------
 template <int DIM>
-__device__ __forceinline__ void fb_et_setup_body(const DevSpec& S, double* __restrict__ stat, double* __restrict__ tv,
-                                                 double* __restrict__ tw, double* __restrict__ tz) {
+__device__ __forceinline__ void fb_et_setup_body(const DevSpec& S, double* __restrict__ stat, double* __restrict__ tvw,
+                                                 double* __restrict__ tz) {
   constexpr int D1 = DIM + 1;
   const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (v >= S.n_owned) return;
   const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
   const int NSP = S.vx_nsp, nstat = S.vx_nstat, nts = S.vx_nts;
   const long long tz0 = nts ? S.et_tzptr[v] : 0;
-  const int W = (nts && deg) ? (int)((S.et_tzptr[v + 1] - tz0) / deg) : 0;
+  const int W = nts ? S.et_tzw[v] : 0;
+  const int slab = nts ? (int)(S.et_tzptr[v + 1] - tz0) : 0;
   for (int t = 0; t < deg * NSP; ++t) stat[(long long)r0 * NSP + t] = 0.0;
   for (int ts = 0; ts < nts; ++ts) {
-    for (int k = 0; k < deg; ++k) { tv[ts * S.nnzb + r0 + k] = 0.0; tw[ts * S.nnzb + r0 + k] = 0.0; }
-    for (int t = 0; t < W * deg; ++t) tz[ts * S.et_tz_total + tz0 + t] = 0.0;
+    for (int k = 0; k < 2 * deg; ++k) tvw[2 * (ts * S.nnzb + r0) + k] = 0.0;
+    for (int t = 0; t < slab; ++t) tz[ts * S.et_tz_total + tz0 + t] = 0.0;
   }
   const int* __restrict__ ch = S.vx_itab + S.vx_o_ch;
   const double mscale = 1.0 / (double)(D1 * (D1 + 1));
@@ -266,16 +267,15 @@ __device__ __forceinline__ void fb_et_setup_body(const DevSpec& S, double* __res
       for (int c2 = nstat; c2 < c; ++c2) first &= (ch[8 * c2 + 5] != ts);
       if (!first) continue;
       const int off = ch[8 * c + 2];
-      double* __restrict__ Tv = tv + ts * S.nnzb + r0;
-      double* __restrict__ Tw = tw + ts * S.nnzb + r0;
+      double* __restrict__ Tvw = tvw + 2 * (ts * S.nnzb + r0);
       double* __restrict__ Tz = tz + ts * S.et_tz_total + tz0;
       const unsigned char* __restrict__ zs = S.et_tzslot + tz0;
 #pragma unroll
       for (int j = 0; j < D1; ++j) {
         const int k = slot[j];
-        if (j == i) { Tv[k] += rec[off + fb_sym3<D1>(i, i, i)]; continue; }
-        Tv[k] += rec[off + fb_sym3<D1>(i, i, j)];
-        Tw[k] += rec[off + fb_sym3<D1>(i, j, j)];
+        if (j == i) { Tvw[2 * k] += rec[off + fb_sym3<D1>(i, i, i)]; continue; }
+        Tvw[2 * k] += rec[off + fb_sym3<D1>(i, i, j)];
+        Tvw[2 * k + 1] += rec[off + fb_sym3<D1>(i, j, j)];
 #pragma unroll
         for (int b = 0; b < D1; ++b) {
           if (b == i || b == j) continue;
@@ -408,11 +408,10 @@ __device__ __forceinline__ void fb_assemble_edge_body(const DevSpec& S, const do
   // ---- dynamic channel values: A^c_vw = sum_z T_vwz f_c(z) -------------------------------
   if (ndyn > 0) {
     const long long tz0 = S.et_tzptr[v];
-    const int Wd = deg ? (int)((S.et_tzptr[v + 1] - tz0) / deg) : 0;
+    const int Wd = S.et_tzw[v];
     const unsigned char* __restrict__ zs = S.et_tzslot + tz0;
     for (int ts = 0; ts < S.vx_nts; ++ts) {
-      const double* __restrict__ Tv = S.et_tv + ts * S.nnzb + r0;
-      const double* __restrict__ Tw = S.et_tw + ts * S.nnzb + r0;
+      const double* __restrict__ Tvw = S.et_tvw + 2 * (ts * S.nnzb + r0);
       const double* __restrict__ Tz = S.et_tz + ts * S.et_tz_total + tz0;
       const int d0 = itab[S.vx_o_dynptr + ts], d1 = itab[S.vx_o_dynptr + ts + 1];
       for (int kb = 0; kb < deg; kb += G) {
@@ -420,7 +419,7 @@ __device__ __forceinline__ void fb_assemble_edge_body(const DevSpec& S, const do
         const bool act = k < deg && k != kself;
         double tvk = 0.0, twk = 0.0, tj[FB_ET_WREG];
         int zj[FB_ET_WREG];
-        if (act) { tvk = Tv[k]; twk = Tw[k]; }
+        if (act) { tvk = Tvw[2 * k]; twk = Tvw[2 * k + 1]; }
 #pragma unroll
         for (int j = 0; j < FB_ET_WREG; ++j) {
           tj[j] = 0.0; zj[j] = 0;
@@ -446,7 +445,7 @@ __device__ __forceinline__ void fb_assemble_edge_body(const DevSpec& S, const do
       for (int dd = d0; dd < d1; ++dd) {   // diagonal edge: sum over all neighbours z of T_vvz f(z)
         const int c = itab[S.vx_o_dyn + 2 * dd], fc = itab[S.vx_o_dyn + 2 * dd + 1];
         double p = 0.0;
-        for (int k = g; k < deg; k += G) p += Tv[k] * nb[k * NBW + fc];
+        for (int k = g; k < deg; k += G) p += Tvw[2 * k] * nb[k * NBW + fc];
         p = fb_group_sum<G>(p, gmask);
         if (g == 0) A[kself * NCHP + c] = p;
       }

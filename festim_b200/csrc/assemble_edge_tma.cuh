@@ -1,0 +1,320 @@
+// Newton-iteration assembly on the channel operator, TMA-pipelined (sm_100a): the kernel of
+// assemble_edge.cuh (k_assemble_edge: residual + solution-dependent channel values of every
+// block row, strong Dirichlet rows / lifting applied) restructured like the channel SpMV
+// (spmv_channels.cuh).  One persistent block per SM walks chunks of FB_CHUNK consecutive block
+// rows; a producer warp brings everything a chunk reads from HBM into a ring of shared-memory
+// stages with 1D bulk copies (cp.async.bulk) completing on one mbarrier per stage - the static
+// channel values, the edge tensors (T_vvw, T_vww, the T_vwz slabs and their slot bytes), u and
+// u_n at the chunk's distinct neighbour vertices (one copy per run of consecutive ids), the load
+// vector, local column indices, Dirichlet words and row pointers - while FB_CHUNK_GROUPS groups of
+// consumer warps (one warp per row) work on earlier chunks: affine reaction factors at the row's
+// neighbours, dynamic channel values  A^c_vw = sum_z T_vwz f_c(z)  (written to the channel
+// operator, coalesced), then the residual  F_s = load + sum_e coef_e sum_w A^{c_e}_vw g_e(w).
+// Replaces the FFCx kernels + dolfinx assemble_vector / apply_lifting / set_bc behind
+// NonlinearProblem (reference src/festim/problem.py:170-182) for the form of
+// src/festim/hydrogen_transport_problem.py:870-997.
+#pragma once
+#include "assemble_edge.cuh"
+#include "spmv_channels.cuh"
+
+struct AsmTmaArgs {
+  const double* u;
+  const double* un;
+  double* F;
+  double* dyn;
+  int flags;
+  int nst;
+  // shared-memory layout (bytes)
+  int o_tab_i, o_scr, scr_bytes, o_stage0, stage_bytes, o_bar;
+  int s_tvw, s_tz, s_tzs, s_us, s_uns, s_load, s_lcol, s_vinfo, s_rowinfo, s_rowptr, s_tzptr, s_tzw;
+  int tz_stride;   // doubles per tensor inside a stage
+  int w_fv, w_adyn, w_res;   // offsets (doubles) inside a warp's scratch
+};
+
+__host__ inline size_t fb_asm_tma_layout(const DevSpec& S, AsmTmaArgs& a, int nst) {
+  auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  const int md = S.maxdeg, ns = S.ns, CH = FB_CHUNK, nts = S.vx_nts;
+  size_t o = 0;
+  o += up16((size_t)S.vx_dtab_n * 8);
+  a.o_tab_i = (int)o; o += up16((size_t)S.vx_itab_n * 4);
+  int w = 0;
+  a.w_fv = w; w += md * (S.n_factors > 0 ? S.n_factors : 1);
+  a.w_adyn = w; w += md * (S.vx_ndp > 0 ? S.vx_ndp : 1);
+  const int nres = S.vx_nft > S.vx_njt ? S.vx_nft : S.vx_njt;
+  a.w_res = w; w += nres > 0 ? nres : 1;
+  a.o_scr = (int)o; a.scr_bytes = (int)up16((size_t)w * 8); o += (size_t)CH * FB_CHUNK_GROUPS * a.scr_bytes;
+  size_t s = 0;
+  s += up16((size_t)CH * md * S.vx_nsp * 8);                       // static channel values
+  a.s_tvw = (int)s; s += up16((size_t)nts * CH * md * 16);
+  a.tz_stride = (int)((S.et_tz_chunk_max + 1) & ~1LL);
+  a.s_tz = (int)s; s += up16((size_t)nts * a.tz_stride * 8);
+  a.s_tzs = (int)s; s += up16((size_t)S.et_tz_chunk_max + 16);
+  a.s_us = (int)s; s += up16((size_t)(S.ck_nx_max + 2) * ns * 8);
+  a.s_uns = (int)s; if (S.transient) s += up16((size_t)(S.ck_nx_max + 2) * ns * 8);
+  a.s_load = (int)s; s += up16((size_t)CH * ns * 8);
+  a.s_lcol = (int)s; s += up16((size_t)(CH * md + 8) * 2);
+  a.s_vinfo = (int)s; s += up16((size_t)CH * 4);
+  a.s_rowinfo = (int)s; s += up16((size_t)CH * 4);
+  a.s_rowptr = (int)s; s += up16((size_t)(CH + 4) * 4);
+  a.s_tzptr = (int)s; s += up16((size_t)(CH + 4) * 8);
+  a.s_tzw = (int)s; s += up16((size_t)CH * 4);
+  a.stage_bytes = (int)s;
+  a.o_stage0 = (int)o; o += (size_t)nst * s;
+  a.o_bar = (int)o; o += 16 * 8;
+  a.nst = nst;
+  return o;
+}
+
+__global__ void __launch_bounds__(32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, 1)
+k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
+  extern __shared__ __align__(16) unsigned char fb_as_smem[];
+  constexpr int CH = FB_CHUNK, NG = FB_CHUNK_GROUPS;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ns = S.ns, NSP = S.vx_nsp, NDP = S.vx_ndp, NST = a.nst, nts = S.vx_nts, NF = S.n_factors;
+  const int nstat = S.vx_nstat, ndyn = S.vx_ndyn;
+  const bool doF = (a.flags & FB_ASSEMBLE_F) != 0;
+  const bool transient = S.transient != 0;
+  double* dtab = (double*)fb_as_smem;
+  int* itab = (int*)(fb_as_smem + a.o_tab_i);
+  for (int t = threadIdx.x; t < S.vx_dtab_n; t += blockDim.x) dtab[t] = S.vx_dtab[t];
+  for (int t = threadIdx.x; t < S.vx_itab_n; t += blockDim.x) itab[t] = S.vx_itab[t];
+  unsigned long long* full = (unsigned long long*)(fb_as_smem + a.o_bar);
+  unsigned long long* empty = full + 8;
+  if (threadIdx.x == 0)
+    for (int q = 0; q < NST; ++q) { fb_mbar_init(&full[q], 1); fb_mbar_init(&empty[q], CH); }
+  for (size_t t = threadIdx.x; t < (size_t)NST * a.stage_bytes / 16; t += blockDim.x)
+    ((double2*)(fb_as_smem + a.o_stage0))[t] = make_double2(0.0, 0.0);
+  fb_fence_proxy_async();
+  fb_mbar_fence_init();
+  __syncthreads();
+  const long long nchunks = (S.n_owned + CH - 1) / CH;
+  const long long nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == CH * NG) {
+    // ================= producer warp =====================================================================
+    int pf_e0, pf_ne, pf_nx, pf_lc, pf_q0 = 0, pf_q1 = 0, pf_run[3];
+    long long pf_t0, pf_t1;
+    auto prefetch = [&](long long i) {
+      if (i >= nmine) return;
+      const long long c = blockIdx.x + i * (long long)gridDim.x;
+      const long long c0 = c * CH;
+      const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
+      pf_e0 = S.rowptr[c0]; pf_ne = S.rowptr[c0 + nrow]; pf_nx = S.ck_nx[c]; pf_lc = S.ck_lcolptr[c];
+      pf_t0 = nts ? S.et_tzptr[c0] : 0; pf_t1 = nts ? S.et_tzptr[c0 + nrow] : 0;
+      const int* rr = S.ck_slots + ((size_t)c * 32 + lane) * 3;
+      pf_run[0] = rr[0]; pf_run[1] = rr[1]; pf_run[2] = rr[2];
+      if (S.ck_rmax > 32) { pf_q0 = S.ck_runptr[c]; pf_q1 = S.ck_runptr[c + 1]; }
+    };
+    prefetch(0);
+    for (long long i = 0; i < nmine; ++i) {
+      const int sidx = (int)(i % NST);
+      if (i >= NST) fb_mbar_wait(&empty[sidx], (unsigned)(((i / NST) - 1) & 1));
+      const long long c = blockIdx.x + i * (long long)gridDim.x;
+      const long long c0 = c * CH;
+      const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
+      unsigned char* st = fb_as_smem + a.o_stage0 + (size_t)sidx * a.stage_bytes;
+      unsigned long long* b = &full[sidx];
+      const int e0 = pf_e0, ne = pf_ne - pf_e0, nx = pf_nx, lc0 = pf_lc, q0 = pf_q0, q1 = pf_q1;
+      const long long t0 = pf_t0;
+      const int nt = (int)(pf_t1 - pf_t0);   // entries of the chunk's T_vwz slabs (multiple of 16)
+      const int r0v = pf_run[0], r1v = pf_run[1], r2v = pf_run[2];
+      prefetch(i + 1);
+      const int nlc = (ne + 7) & ~7;
+      if (lane == 0) {
+        unsigned bytes = (unsigned)(nx * ns * 8 * (transient ? 2 : 1) + nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
+        if (nts) bytes += (unsigned)(nts * (2 * ne * 8 + nt * 8) + nt + CH * 4 + (CH + 4) * 8);
+        if (doF) bytes += (unsigned)(ne * NSP * 8 + nrow * ns * 8);
+        fb_mbar_expect_tx(b, bytes);
+      }
+      __syncwarp();
+      if (lane == 0 && doF && NSP) fb_bulk_g2s(st, S.et_stat + (long long)e0 * NSP, (unsigned)(ne * NSP * 8), b);
+      if (lane == 1 && doF) fb_bulk_g2s(st + a.s_load, S.load + c0 * ns, (unsigned)(nrow * ns * 8), b);
+      if (lane == 2) fb_bulk_g2s(st + a.s_lcol, S.ck_lcol + lc0, (unsigned)(nlc * 2), b);
+      if (lane == 3) fb_bulk_g2s(st + a.s_vinfo, S.vinfo + c0, (unsigned)(CH * 4), b);
+      if (lane == 4) fb_bulk_g2s(st + a.s_rowinfo, S.ck_rowinfo + c0, (unsigned)(CH * 4), b);
+      if (lane == 5) fb_bulk_g2s(st + a.s_rowptr, S.rowptr + c0, (unsigned)((CH + 4) * 4), b);
+      if (lane == 6 && nts) fb_bulk_g2s(st + a.s_tzptr, S.et_tzptr + c0, (unsigned)((CH + 4) * 8), b);
+      if (lane == 7 && nts) fb_bulk_g2s(st + a.s_tzw, S.et_tzw + c0, (unsigned)(CH * 4), b);
+      if (lane == 8 && nts && nt) fb_bulk_g2s(st + a.s_tzs, S.et_tzslot + t0, (unsigned)nt, b);
+      if (lane >= 9 && lane < 9 + 2 * nts) {   // per tensor: the (T_vvw, T_vww) pairs and the T_vwz slabs
+        const int ts = (lane - 9) >> 1;
+        if (((lane - 9) & 1) == 0)
+          fb_bulk_g2s(st + a.s_tvw + (size_t)ts * CH * S.maxdeg * 16, S.et_tvw + 2 * (ts * S.nnzb + e0), (unsigned)(ne * 16), b);
+        else if (nt)
+          fb_bulk_g2s(st + a.s_tz + (size_t)ts * a.tz_stride * 8, S.et_tz + ts * S.et_tz_total + t0, (unsigned)(nt * 8), b);
+      }
+      // u (and u_n) at the chunk's distinct neighbours, one copy per run of vertex ids
+      if (r1v > 0) {
+        fb_bulk_g2s(st + a.s_us + (size_t)r2v * ns * 8, a.u + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
+        if (transient) fb_bulk_g2s(st + a.s_uns + (size_t)r2v * ns * 8, a.un + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
+      }
+      for (int q = q0 + 32 + lane; q < q1; q += 32) {
+        const int v0 = S.ck_runs[3 * q], len = S.ck_runs[3 * q + 1], lo = S.ck_runs[3 * q + 2];
+        fb_bulk_g2s(st + a.s_us + (size_t)lo * ns * 8, a.u + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
+        if (transient) fb_bulk_g2s(st + a.s_uns + (size_t)lo * ns * 8, a.un + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
+      }
+    }
+    return;
+  }
+
+  // ================= consumer warps ========================================================================
+  double* scr = (double*)(fb_as_smem + a.o_scr + (size_t)warp * a.scr_bytes);
+  double* fv = scr + a.w_fv;
+  double* adyn = scr + a.w_adyn;
+  double* res = scr + a.w_res;
+  const int grp = warp / CH, wrow = warp - grp * CH;
+  const int col_one = 2 * ns + NF;
+  for (long long i = grp; i < nmine; i += NG) {
+    const int sidx = (int)(i % NST);
+    const long long c = blockIdx.x + i * (long long)gridDim.x;
+    const long long c0 = c * CH;
+    const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
+    unsigned char* st = fb_as_smem + a.o_stage0 + (size_t)sidx * a.stage_bytes;
+    fb_mbar_wait(&full[sidx], (unsigned)((i / NST) & 1));
+    if (wrow < nrow) {
+      const int j = wrow;
+      const long long v = c0 + j;
+      const double* stat_s = (const double*)st;
+      const double* us = (const double*)(st + a.s_us);
+      const double* uns = (const double*)(st + a.s_uns);
+      const int* rowptr_s = (const int*)(st + a.s_rowptr);
+      const int e0 = rowptr_s[0];
+      const int rp0 = rowptr_s[j] - e0, deg = rowptr_s[j + 1] - rowptr_s[j];
+      const unsigned short* lc = (const unsigned short*)(st + a.s_lcol) + rp0;
+      const unsigned vi = ((const unsigned*)(st + a.s_vinfo))[j];
+      const int lself = (int)((const unsigned*)(st + a.s_rowinfo))[j];
+      const unsigned rowbc = vi & 0xffffu;
+      const bool colbc = (vi >> 16) & 1u;
+      const double* sr = stat_s + (size_t)rp0 * NSP;
+      // column `col` of the per-vertex table [u | u - u_n | affine factors | 1] at staged vertex lv;
+      // kf = the row's edge index of that vertex (factor values are kept per edge)
+      auto nbval = [&](int col, int lv, int kf) -> double {
+        if (col < ns) return us[(size_t)lv * ns + col];
+        if (col < 2 * ns) return transient ? us[(size_t)lv * ns + col - ns] - uns[(size_t)lv * ns + col - ns] : 0.0;
+        if (col < col_one) return fv[kf * NF + (col - 2 * ns)];
+        return 1.0;
+      };
+      // ---- affine reaction factors at the row's neighbours ------------------------------------------
+      int kself = 0;
+      for (int k = lane; k < deg; k += 32)
+        if ((int)lc[k] == lself) kself = k;
+      kself = __reduce_max_sync(FULL, kself);
+      for (int t = lane; t < deg * NF; t += 32) {
+        const int k = fb_fastdiv((unsigned)t, S.vx_m_nf), f = t - k * NF;
+        const int* h = S.fac_hdr + 4 * f;
+        double val = h[0] ? S.scalars[h[1]] : S.fac_a0[f];
+        const double* uk = us + (size_t)lc[k] * ns;
+        for (int q = 0; q < h[3]; ++q) val += S.fac_coef[h[2] + q] * uk[S.fac_species[h[2] + q]];
+        fv[t] = val;
+      }
+      __syncwarp();
+      // ---- dynamic channel values: A^c_vw = sum_z T_vwz f_c(z) --------------------------------------
+      if (ndyn > 0) {
+        const long long* tzptr_s = (const long long*)(st + a.s_tzptr);
+        const int tzr = (int)(tzptr_s[j] - tzptr_s[0]);
+        const int Wd = ((const int*)(st + a.s_tzw))[j];
+        const unsigned char* zs = (const unsigned char*)(st + a.s_tzs) + tzr;
+        // rows of up to 16 edges use both half-warps: each takes every other dynamic channel
+        const bool split = deg <= 16;
+        const int half = split ? lane >> 4 : 0, nhalf = split ? 2 : 1;
+        for (int ts = 0; ts < nts; ++ts) {
+          const double* Tvw = (const double*)(st + a.s_tvw) + 2 * ((size_t)ts * CH * S.maxdeg + rp0);
+          const double* Tz = (const double*)(st + a.s_tz) + (size_t)ts * a.tz_stride + tzr;
+          const int d0 = itab[S.vx_o_dynptr + ts], d1 = itab[S.vx_o_dynptr + ts + 1];
+          for (int kb = 0; kb < deg; kb += (split ? 16 : 32)) {
+            const int k = kb + (split ? (lane & 15) : lane);
+            const bool act = k < deg && k != kself;
+            double tvk = 0.0, twk = 0.0, tj[FB_ET_WREG];
+            int zj[FB_ET_WREG], zl[FB_ET_WREG];
+            const int lk = act ? lc[k] : 0;
+            if (act) { tvk = Tvw[2 * k]; twk = Tvw[2 * k + 1]; }
+#pragma unroll
+            for (int q = 0; q < FB_ET_WREG; ++q) {
+              tj[q] = 0.0; zj[q] = 0; zl[q] = 0;
+              if (act && q < Wd) {
+                const int zz = zs[q * deg + k];
+                if (zz != 0xff) { zj[q] = zz; zl[q] = lc[zz]; tj[q] = Tz[q * deg + k]; }
+              }
+            }
+            if (act) {
+              for (int dd = d0 + half; dd < d1; dd += nhalf) {
+                const int cch = itab[S.vx_o_dyn + 2 * dd], fc = itab[S.vx_o_dyn + 2 * dd + 1];
+                double av = tvk * nbval(fc, lself, kself) + twk * nbval(fc, lk, k);
+#pragma unroll
+                for (int q = 0; q < FB_ET_WREG; ++q) av += tj[q] * nbval(fc, zl[q], zj[q]);
+                for (int q = FB_ET_WREG; q < Wd; ++q) {
+                  const int zz = zs[q * deg + k];
+                  if (zz != 0xff) av += Tz[q * deg + k] * nbval(fc, lc[zz], zz);
+                }
+                adyn[k * NDP + (cch - nstat)] = av;
+              }
+            }
+          }
+          for (int dd = d0; dd < d1; ++dd) {   // diagonal edge: sum over all neighbours z of T_vvz f(z)
+            const int cch = itab[S.vx_o_dyn + 2 * dd], fc = itab[S.vx_o_dyn + 2 * dd + 1];
+            double p = 0.0;
+            for (int k = lane; k < deg; k += 32) p += Tvw[2 * k] * nbval(fc, lc[k], k);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+            if (lane == 0) adyn[kself * NDP + (cch - nstat)] = p;
+          }
+        }
+        for (int t = lane; t < deg; t += 32)
+          for (int cpad = ndyn; cpad < NDP; ++cpad) adyn[t * NDP + cpad] = 0.0;
+        __syncwarp();
+        double* __restrict__ dst = a.dyn + (long long)(e0 + rp0) * NDP;
+        for (int t = lane; t < deg * NDP; t += 32) dst[t] = adyn[t];
+      }
+      if (doF) {
+        // ---- residual ---------------------------------------------------------------------------------
+        const int nft = S.vx_nft;
+        for (int t = lane; t < nft; t += 32) {
+          const int chan = itab[S.vx_o_ft + 3 * t], gcol = itab[S.vx_o_ft + 3 * t + 1], fl = itab[S.vx_o_ft + 3 * t + 2];
+          double acc = 0.0;
+          if (chan < nstat)
+            for (int k = 0; k < deg; ++k) acc += sr[k * NSP + chan] * nbval(gcol, lc[k], k);
+          else
+            for (int k = 0; k < deg; ++k) acc += adyn[k * NDP + chan - nstat] * nbval(gcol, lc[k], k);
+          res[t] = acc * dtab[S.vx_o_ftc + t] * ((fl & 1) ? S.inv_dt : 1.0);
+        }
+        __syncwarp();
+        double facc = 0.0;
+        if (lane < ns) {
+          facc = ((const double*)(st + a.s_load))[j * ns + lane];
+          const int a0 = itab[S.vx_o_ftptr + lane], a1 = itab[S.vx_o_ftptr + lane + 1];
+          for (int t = a0; t < a1; ++t) facc += res[t];
+        }
+        if (colbc) {   // lifting b += J[:, B] (g - x_B) with the live entries of the Dirichlet columns (rare rows)
+          __syncwarp();
+          const int njt = S.vx_njt;
+          for (int t = lane; t < njt; t += 32) {
+            const int chan = itab[S.vx_o_jt + 2 * t], fl = itab[S.vx_o_jt + 2 * t + 1];
+            const int cs = S.pair_cs[itab[S.vx_o_jtpair + t]];
+            double acc = 0.0;
+            for (int k = 0; k < deg; ++k) {
+              const int w = S.colidx[e0 + rp0 + k];
+              if ((S.vinfo[w] >> cs) & 1u) {
+                const double av = chan < nstat ? sr[k * NSP + chan] : adyn[k * NDP + chan - nstat];
+                acc += av * (S.bc_vals[S.bc_map[(long long)w * ns + cs]] - us[(size_t)lc[k] * ns + cs]);
+              }
+            }
+            res[t] = acc * dtab[S.vx_o_jtc + t] * ((fl & 1) ? S.inv_dt : 1.0);
+          }
+          __syncwarp();
+          if (lane < ns) {
+            const int a0 = itab[S.vx_o_jtptr + S.pair_pp[lane]], a1 = itab[S.vx_o_jtptr + S.pair_pp[lane + 1]];
+            for (int t = a0; t < a1; ++t) facc += res[t];
+          }
+        }
+        if (lane < ns) {
+          const long long dof = v * ns + lane;
+          if ((rowbc >> lane) & 1u) a.F[dof] = us[(size_t)lself * ns + lane] - S.bc_vals[S.bc_map[dof]];
+          else a.F[dof] = facc;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) fb_mbar_arrive(&empty[sidx]);
+  }
+}

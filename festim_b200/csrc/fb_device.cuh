@@ -11,8 +11,8 @@
 #define FB_MAX_D1 4
 #define FB_KB 8.6173303e-5  // Boltzmann constant eV/K, reference src/festim/__init__.py:11
 #define FB_STACK 24
-#define FB_CHUNK 12           // block rows staged together by the TMA-pipelined row kernels (multiple of 4)
-#define FB_CHUNK_GROUPS 2     // consumer groups of FB_CHUNK warps working on alternate chunks
+#define FB_CHUNK 16           // block rows staged together by the TMA-pipelined row kernels (multiple of 4)
+#define FB_CHUNK_GROUPS 1     // consumer groups of FB_CHUNK warps working on alternate chunks
 
 // Everything a kernel needs, passed by value (lives in the constant bank).
 struct DevSpec {
@@ -90,10 +90,11 @@ struct DevSpec {
   long long nnzb, et_tz_total;
   const double* et_stat;      // [nnzb][vx_nsp] static channel values per edge (per temperature update)
   const double* et_dyn;       // [nnzb][vx_ndp] solution-dependent channel values per edge (per assembly)
-  const double* et_tv;        // [nts][nnzb]  T_vvw: moment sum_K M3[v,v,w]
-  const double* et_tw;        // [nts][nnzb]  T_vww
+  const double* et_tvw;       // [nts][nnzb][2]  T_vvw and T_vww: moments sum_K M3[v,v,w], M3[v,w,w]
   const double* et_tz;        // [nts][et_tz_total]  T_vwz, z a common neighbour of v and w
-  const long long* et_tzptr;  // [n_owned+1] start of the row's (W_v x deg) slab
+  long long et_tz_chunk_max;  // largest T_vwz extent of a chunk of FB_CHUNK rows
+  const int* et_tzw;          // [n_vertices, padded] W_v: triples per edge of the row
+  const long long* et_tzptr;  // [n_vertices+1, padded] start of the row's (W_v x deg) slab, padded to multiples of 16
   const unsigned char* et_tzslot;   // [et_tz_total] row slot of z (0xff: padding)
   // chunk plan (fb_set_pattern): FB_CHUNK consecutive block rows are staged together - the
   // distinct neighbour vertices of a chunk as runs of consecutive ids (one bulk copy each)

@@ -41,10 +41,35 @@ class Constant(_ufl.Expr):
 
 
 class _Vec:
-    """``Function.x``: holds ``.array`` like ``dolfinx.la.Vector``."""
+    """``Function.x``: holds ``.array`` like ``dolfinx.la.Vector``.
+
+    A solver backend that keeps the field on its device may ``defer`` the copy back: the host
+    array is then refreshed the first time somebody looks at it.  ``version`` counts the host
+    accesses (each may modify the array in place), so the backend knows whether its device copy
+    is still the current one."""
 
     def __init__(self, n):
-        self.array = np.zeros(n, dtype=np.float64)
+        self._array = np.zeros(n, dtype=np.float64)
+        self._fetch = None
+        self.version = 0
+
+    @property
+    def array(self):
+        if self._fetch is not None:
+            fetch, self._fetch = self._fetch, None
+            fetch(self._array)
+        self.version += 1
+        return self._array
+
+    @array.setter
+    def array(self, value):
+        self._array = np.ascontiguousarray(value, dtype=np.float64)
+        self._fetch = None
+        self.version += 1
+
+    def defer(self, fetch):
+        """The host copy is stale: ``fetch(out)`` fills it when it is next read."""
+        self._fetch = fetch
 
     def scatter_forward(self):
         pass

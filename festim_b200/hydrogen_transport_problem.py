@@ -371,6 +371,14 @@ class HydrogenTransportProblem(ProblemBase):
 
     def update_post_processing_solutions(self):
         ns = len(self.species)
+        if getattr(self.solver, "device_resident", False):
+            # the mixed vector lives on the device: split it when a species field is read
+            for idx, spe in enumerate(self.species):
+                def fetch(out, idx=idx):
+                    out[:] = self.u.x.array.reshape(-1, ns)[:, idx]
+
+                spe.post_processing_solution.x.defer(fetch)
+            return
         arr = self.u.x.array.reshape(-1, ns)
         for idx, spe in enumerate(self.species):
             spe.post_processing_solution.x.array[:] = arr[:, idx]

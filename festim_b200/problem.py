@@ -208,7 +208,10 @@ class ProblemBase:
         nb_its = self.solver.solver.getIterationNumber()
 
         self.post_processing()
-        self.u_n.x.array[:] = self.u.x.array[:]
+        # u_n <- u: on the device when the backend keeps the fields there (no host round trip)
+        advance = getattr(self.solver, "copy_solution_to_previous", None)
+        if advance is None or not advance():
+            self.u_n.x.array[:] = self.u.x.array[:]
 
         if self.settings.stepsize.adaptive:
             self.dt.value = self.settings.stepsize.modify_value(
