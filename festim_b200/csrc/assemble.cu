@@ -282,7 +282,8 @@ static int et_launch(fb_ctx* ctx, int which, const double* u, const double* un, 
 static bool asm_tma_ok(fb_ctx* ctx, const double* u, const double* un) {
   const DevSpec& S = ctx->S;
   return S.vx_on && (S.ns % 2 == 0) && S.ns <= 32 && (((uintptr_t)u & 15) == 0) && (((uintptr_t)un & 15) == 0) &&
-         S.ck_nx_max > 0 && S.vx_nts <= 11 && S.maxdeg <= 64 && !getenv("FB_NO_TMA_ASSEMBLY");
+         S.ck_nx_max > 0 && S.vx_nts <= 11 && S.maxdeg <= 64 && getenv("FB_TMA_ASSEMBLY");   // opt-in: measured slower
+         // than k_assemble_edge at C2 (5.05 vs 4.17 ms: the per-row consumer code is issue-bound)
 }
 
 static int asm_tma_launch(fb_ctx* ctx, const double* u, const double* un, double* F, int flags, bool* done) {

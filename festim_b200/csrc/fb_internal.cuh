@@ -44,6 +44,9 @@ struct fb_ctx {
   void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int peer_rank = 0, peer_n = 0;
   unsigned peer_seq = 1;               // next unused tag of the LL words
+  unsigned xr_seq = 1, halo_seq = 1;   // tags of the cross-rank reductions / halo exchanges of the Krylov kernels
+  long long halo_words = 0;            // u64 words of one parity of the halo area
+  bool peer_ready = false;             // every peer area mapped and the send table set
   const int* d_send_v = nullptr; const int* d_send_rank = nullptr; const int* d_send_dst = nullptr;
   int n_send = 0;
   int n_programs = 0;                  // compiled expressions of the spec (fb_integrate checks its argument)
@@ -148,3 +151,4 @@ int fbi_norm2(fb_ctx* ctx, const double* x, double* out_host);
 int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, int ksp, int pc,
                      double rtol, double atol, int max_it, int* iters, double* relres);
 int fbi_ensure_workspace(fb_ctx* ctx);
+int fbi_halo(fb_ctx* ctx, double* x);

@@ -13,6 +13,7 @@
 #include "fb_internal.cuh"
 #include "reduce.cuh"
 #include "spmv_channels.cuh"
+#include "xrank.cuh"
 
 // ---------------------------------------------------------------------------
 // SpMV: G lanes per scalar row (v, s); values of the row are contiguous
@@ -295,6 +296,7 @@ static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
 
 // y = J x (precond false) or y = D^-1 J x on the channel operator
 static int spmv_ch(fb_ctx* ctx, const double* x, double* y, bool precond, const int* flags) {
+  if (int rc = fbi_halo(ctx, (double*)x)) return rc;
   if (spmv_ch_tma_ok(ctx, x)) {
     SpmvChArgs a{};
     a.x = x; a.y = y; a.dinv = ctx->d_dinv; a.flags = flags;
@@ -349,6 +351,7 @@ int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y) {
     if (!S.vx_on) return fb_fail(ctx, "no channel operator: pass the block-CSR values");
     return spmv_ch(ctx, x, y, false, nullptr);
   }
+  if (int rc = fbi_halo(ctx, (double*)x)) return rc;
   if (spmv_blk_ok(S)) return spmv_blk_launch<false>(ctx, J, x, y, nullptr);
   const int G = spmv_group(S);
   const long long threads = S.n_dofs * G;
@@ -368,18 +371,51 @@ int fbi_spmv(fb_ctx* ctx, const double* J, const double* x, double* y) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(FB_TPB)
 k_dot(long long n, const double* __restrict__ x, const double* __restrict__ y,
-      double* partials, unsigned* ticket, double* out) {
+      double* partials, unsigned* ticket, double* out, XRank X) {
   double v[1] = {0.0}, tot[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     v[0] += x[i] * y[i];
-  if (grid_reduce<1>(v, partials, ticket, tot) && threadIdx.x == 0) out[0] = tot[0];
+  if (grid_reduce<1>(v, partials, ticket, tot)) {
+    xrank_sum<1>(X, tot);
+    if (threadIdx.x == 0) out[0] = tot[0];
+  }
 }
 
 __global__ void k_axpy(long long n, double a, const double* __restrict__ x, double* __restrict__ y) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     y[i] += a * x[i];
+}
+
+// cross-rank context of the next reduction / halo exchange (fb_peer_*); single rank: inert
+static XRank xrank_make(fb_ctx* ctx, unsigned seq) {
+  XRank X{};
+  X.n = ctx->peer_ready ? ctx->peer_n : 1;
+  X.rank = ctx->peer_rank;
+  X.seq = seq;
+  for (int q = 0; q < 8; ++q) X.base[q] = (unsigned long long*)ctx->peer_base[q];
+  X.bar = ctx->d_ticket ? ctx->d_ticket + 64 : nullptr;
+  return X;
+}
+static XRank xr_next(fb_ctx* ctx) { return xrank_make(ctx, ctx->peer_ready ? ctx->xr_seq++ : 0u); }
+
+// owner -> ghost exchange of a node-major vector over peer memory (no-op on a single rank)
+int fbi_halo(fb_ctx* ctx, double* x) {
+  if (!ctx->peer_ready) return 0;
+  const DevSpec& S = ctx->S;
+  int rc = fbi_ensure_workspace(ctx);
+  if (rc) return rc;
+  const XRank X = xrank_make(ctx, ctx->halo_seq++);
+  const long long n_ghost_dofs = S.n_dofs - S.n_owned_dofs;
+  const long long nsend = (long long)ctx->n_send * S.ns;
+  if (nsend > 0)
+    FB_LAUNCH(ctx, k_halo_push, (unsigned)((nsend + 255) / 256), 256, 0, X, S.ns, ctx->n_send, ctx->d_send_v, ctx->d_send_rank,
+              ctx->d_send_dst, ctx->halo_words, (const double*)x);
+  if (n_ghost_dofs > 0)
+    FB_LAUNCH(ctx, k_halo_pull, (unsigned)((n_ghost_dofs + 255) / 256), 256, 0, X, S.n_owned_dofs, n_ghost_dofs, ctx->halo_words, x);
+  FB_CHECK(ctx, cudaGetLastError());
+  return 0;
 }
 
 static unsigned vec_grid(fb_ctx* ctx, long long n) {
@@ -393,7 +429,7 @@ static unsigned vec_grid(fb_ctx* ctx, long long n) {
 static int dot_to_host(fb_ctx* ctx, const double* x, const double* y, double* out) {
   const DevSpec& S = ctx->S;
   FB_LAUNCH(ctx, k_dot, vec_grid(ctx, S.n_owned_dofs), FB_TPB, 0, S.n_owned_dofs, x, y, ctx->d_red, ctx->d_ticket,
-            ctx->d_sc + 60);
+            ctx->d_sc + 60, xr_next(ctx));
   FB_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_sc + 60, sizeof(double), cudaMemcpyDeviceToHost,
                                 ctx->stream));
   FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -743,51 +779,6 @@ struct CgArgs {
 // its generation number in a register, so a barrier costs one atomic round trip plus
 // one poll round trip.  A bounded spin turns a scheduling problem into an error code
 // instead of a hang (bar[64] = abort flag).  Returns false on abort.
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned atom_add_release_u32(unsigned* p, unsigned v) {
-  unsigned old;
-  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-  return old;
-}
-
-// Self-validating 8-byte words {tag : 32 | half a double : 32} (the protocol NCCL calls LL):
-// the writer needs no fence or flag, the reader spins until both halves carry the tag it
-// expects.  Used for data another block (or, over NVLink, another GPU) consumes right after
-// it is produced: it replaces a barrier by point-to-point waiting.
-__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned tag, double v) {
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-  const unsigned long long t = (unsigned long long)tag << 32;
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(t | (bits & 0xffffffffull)) : "memory");
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + 1), "l"(t | (bits >> 32)) : "memory");
-}
-__device__ __forceinline__ unsigned long long ll_word(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// spins until both halves carry `tag`; false on timeout / abort (bar[64])
-__device__ __forceinline__ bool ll_load(const unsigned long long* p, unsigned tag, unsigned* bar, double& out) {
-  unsigned spins = 0;
-  while (true) {
-    const unsigned long long lo = ll_word(p), hi = ll_word(p + 1);
-    if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) {
-      out = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
-      return true;
-    }
-    if ((++spins & 0x3ffu) == 0u) {
-      __nanosleep(64);
-      if (spins > (1u << 23) || ld_acquire_u32(bar + 64)) { atomicExch(bar + 64, 1u); out = 0.0; return false; }
-    }
-  }
-}
-
 __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen,
                                              unsigned base_count) {
   __shared__ int ok_s;
@@ -1313,8 +1304,8 @@ k_cg_persistent(DevSpec S, CgArgs A) {
 // basis loads of an element are independent (one long burst of loads in flight per thread).
 template <int NVB>
 __global__ void __launch_bounds__(FB_TPB)
-k_gs_dots(long long n, int nv, const double* __restrict__ V, const double* __restrict__ w,
-          double* partials, unsigned* ticket, double* hd, double* n0, const int* __restrict__ flags) {
+k_gs_dots(long long n, long long ld, int nv, const double* __restrict__ V, const double* __restrict__ w,
+          double* partials, unsigned* ticket, double* hd, double* n0, const int* __restrict__ flags, XRank X) {
   if (flags[0]) return;
   double acc[NVB + 1], tot[NVB + 1];
 #pragma unroll
@@ -1324,22 +1315,25 @@ k_gs_dots(long long n, int nv, const double* __restrict__ V, const double* __res
     const double wk = w[k];
     double vv[NVB];
 #pragma unroll
-    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * n + k] : 0.0;
+    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * ld + k] : 0.0;
 #pragma unroll
     for (int i = 0; i < NVB; ++i) acc[i] += vv[i] * wk;
     acc[NVB] += wk * wk;
   }
-  if (grid_reduce<NVB + 1>(acc, partials, ticket, tot) && threadIdx.x == 0) {
-    for (int i = 0; i < nv; ++i) hd[i] = tot[i];
-    n0[0] = tot[NVB];
+  if (grid_reduce<NVB + 1>(acc, partials, ticket, tot)) {
+    xrank_sum<NVB + 1>(X, tot);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < nv; ++i) hd[i] = tot[i];
+      n0[0] = tot[NVB];
+    }
   }
 }
 
 template <int NVB>
 __global__ void __launch_bounds__(FB_TPB)
-k_gs_update(long long n, int nv, const double* __restrict__ V, const double* __restrict__ h1,
+k_gs_update(long long n, long long ld, int nv, const double* __restrict__ V, const double* __restrict__ h1,
             double* __restrict__ w, double* partials, unsigned* ticket, double* h2, double* misc,
-            const int* __restrict__ flags) {
+            const int* __restrict__ flags, XRank X) {
   if (flags[0]) return;
   double acc[NVB + 1], tot[NVB + 1], h[NVB];
 #pragma unroll
@@ -1350,7 +1344,7 @@ k_gs_update(long long n, int nv, const double* __restrict__ V, const double* __r
     double wk = w[k];
     double vv[NVB];
 #pragma unroll
-    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * n + k] : 0.0;
+    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * ld + k] : 0.0;
 #pragma unroll
     for (int i = 0; i < NVB; ++i) wk -= h[i] * vv[i];
     w[k] = wk;
@@ -1358,20 +1352,23 @@ k_gs_update(long long n, int nv, const double* __restrict__ V, const double* __r
     for (int i = 0; i < NVB; ++i) acc[i] += vv[i] * wk;
     acc[NVB] += wk * wk;
   }
-  if (grid_reduce<NVB + 1>(acc, partials, ticket, tot) && threadIdx.x == 0) {
-    for (int i = 0; i < nv; ++i) h2[i] = tot[i];
-    // misc[0] = <w, w> before (k_gs_dots) -> norm^2 of the orthogonalised vector; misc[5] = refine?
-    const bool refine = tot[NVB] < 0.5 * misc[0];
-    misc[0] = tot[NVB];
-    misc[5] = refine ? 1.0 : 0.0;
+  if (grid_reduce<NVB + 1>(acc, partials, ticket, tot)) {
+    xrank_sum<NVB + 1>(X, tot);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < nv; ++i) h2[i] = tot[i];
+      // misc[0] = <w, w> before (k_gs_dots) -> norm^2 of the orthogonalised vector; misc[5] = refine?
+      const bool refine = tot[NVB] < 0.5 * misc[0];
+      misc[0] = tot[NVB];
+      misc[5] = refine ? 1.0 : 0.0;
+    }
   }
 }
 
 template <int NVB>
 __global__ void __launch_bounds__(FB_TPB)
-k_gs_refine(long long n, int nv, const double* __restrict__ V, const double* __restrict__ h2,
+k_gs_refine(long long n, long long ld, int nv, const double* __restrict__ V, const double* __restrict__ h2,
             double* __restrict__ w, double* partials, unsigned* ticket, double* misc,
-            const int* __restrict__ flags) {
+            const int* __restrict__ flags, XRank X) {
   if (flags[0] || misc[5] == 0.0) return;
   double acc[1] = {0.0}, tot[1], h[NVB];
 #pragma unroll
@@ -1381,13 +1378,16 @@ k_gs_refine(long long n, int nv, const double* __restrict__ V, const double* __r
     double wk = w[k];
     double vv[NVB];
 #pragma unroll
-    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * n + k] : 0.0;
+    for (int i = 0; i < NVB; ++i) vv[i] = i < nv ? V[(size_t)i * ld + k] : 0.0;
 #pragma unroll
     for (int i = 0; i < NVB; ++i) wk -= h[i] * vv[i];
     w[k] = wk;
     acc[0] += wk * wk;
   }
-  if (grid_reduce<1>(acc, partials, ticket, tot) && threadIdx.x == 0) misc[0] = tot[0];
+  if (grid_reduce<1>(acc, partials, ticket, tot)) {
+    xrank_sum<1>(X, tot);
+    if (threadIdx.x == 0) misc[0] = tot[0];
+  }
 }
 
 __global__ void k_gmres_givens(int j, double* sc, int* flags) {
@@ -1444,13 +1444,13 @@ __global__ void k_gmres_solve_y(double* sc, const int* flags) {
 }
 
 // t = sum_i y[i] V_i (i < ncols read from flags[3])
-__global__ void k_combine(long long n, const double* __restrict__ V, const double* __restrict__ y,
+__global__ void k_combine(long long n, long long ld, const double* __restrict__ V, const double* __restrict__ y,
                           const int* __restrict__ flags, double* __restrict__ t) {
   const int nc = flags[3];
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n;
        k += (long long)gridDim.x * blockDim.x) {
     double acc = 0.0;
-    for (int i = 0; i < nc; ++i) acc += y[i] * V[(size_t)i * n + k];
+    for (int i = 0; i < nc; ++i) acc += y[i] * V[(size_t)i * ld + k];
     t[k] = acc;
   }
 }
@@ -1946,11 +1946,11 @@ __global__ void k_cheb_init(long long n, const double* __restrict__ v, double in
 // B = D^-1 J), and - when w is given - w = B z from one more application (w = v - r).
 static int cheb_apply(fb_ctx* ctx, const double* v, double* z, double* w, double* d0, double* d1, double* r,
                       const int* flags) {
-  const long long N = ctx->S.n_dofs;
+  const long long No = ctx->S.n_owned_dofs;
   const double theta = 0.5 * (ctx->cheb_lmax + ctx->cheb_lmin), delta = 0.5 * (ctx->cheb_lmax - ctx->cheb_lmin);
   const double sigma = theta / delta;
   double rho = 1.0 / sigma;
-  FB_LAUNCH(ctx, k_cheb_init, vec_grid(ctx, N), FB_TPB, 0, N, v, 1.0 / theta, d0, z, r, flags);
+  FB_LAUNCH(ctx, k_cheb_init, vec_grid(ctx, No), FB_TPB, 0, No, v, 1.0 / theta, d0, z, r, flags);
   const int m = ctx->cheb_steps - 1;
   const int steps = w ? m + 1 : m;
   double* din = d0;
@@ -1962,7 +1962,9 @@ static int cheb_apply(fb_ctx* ctx, const double* v, double* z, double* w, double
     a.r = r; a.z = z; a.dout = dout; a.vin = v; a.wout = w;
     a.ca = rho_n * rho; a.cb = 2.0 * rho_n / delta;
     a.last = (w && i == m) ? 1 : 0;
-    int rc = spmv_ch_tma_launch<2>(ctx, a);
+    int rc = fbi_halo(ctx, din);
+    if (rc) return rc;
+    rc = spmv_ch_tma_launch<2>(ctx, a);
     if (rc) return rc;
     rho = rho_n;
     double* tmp = din; din = dout; dout = tmp;
@@ -1975,7 +1977,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
   const DevSpec& S = ctx->S;
   int rc = ensure_vectors(ctx, GM_NVEC);
   if (rc) return rc;
-  const long long N = S.n_dofs;
+  const long long N = S.n_dofs, No = S.n_owned_dofs;   // vector stride / entries this rank owns
   double* V = ctx->d_work;                 // (GM_M+1) vectors
   double* w = V + (size_t)(GM_M + 1) * N;
   double* z = w + N;
@@ -1985,7 +1987,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
   double* cr = cd1 + N;
   double* cz = cr + N;
   const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
-  const unsigned gv = vec_grid(ctx, N);
+  const unsigned gv = vec_grid(ctx, No);
   double* sc = ctx->d_sc;
   FB_CHECK(ctx, cudaMemsetAsync(y, 0, sizeof(double) * N, ctx->stream));
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
@@ -2003,13 +2005,13 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
       FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, b, r, (const int*)nullptr);
     } else {
       if ((rc = fbi_spmv(ctx, J, y, w))) return rc;
-      FB_LAUNCH(ctx, k_residual, gv, FB_TPB, 0, N, b, w, w);
+      FB_LAUNCH(ctx, k_residual, gv, FB_TPB, 0, No, b, w, w);
       FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, w, r, (const int*)nullptr);
     }
     first = false;
-    FB_LAUNCH(ctx, k_dot, gv, FB_TPB, 0, N, r, r, ctx->d_red, ctx->d_ticket, sc + GM_MISC);
+    FB_LAUNCH(ctx, k_dot, gv, FB_TPB, 0, No, r, r, ctx->d_red, ctx->d_ticket, sc + GM_MISC, xr_next(ctx));
     FB_LAUNCH(ctx, k_gmres_begin, 1, 1, 0, sc, ctx->d_flags, thr);
-    FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, r, sc + GM_MISC + 1, V, (const int*)nullptr);
+    FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, No, r, sc + GM_MISC + 1, V, (const int*)nullptr);
     const int poll = cheb ? 4 : 10;
     for (int j = 0; j < GM_M; ++j) {
       // w = D^-1 J [p(B)] V_j: SpMV with the block-Jacobi application fused into its epilogue
@@ -2018,6 +2020,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
       } else if (!J) {
         if ((rc = spmv_ch(ctx, V + (size_t)j * N, w, true, ctx->d_flags))) return rc;
       } else if (spmv_blk_ok(S)) {
+        if ((rc = fbi_halo(ctx, V + (size_t)j * N))) return rc;
         if ((rc = spmv_blk_launch<true>(ctx, J, V + (size_t)j * N, w, ctx->d_flags))) return rc;
       } else {
         if ((rc = fbi_spmv(ctx, J, V + (size_t)j * N, z))) return rc;
@@ -2026,12 +2029,12 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
       const int nv = j + 1;
 #define FB_GS_CASE(NVB)                                                                                        \
   {                                                                                                            \
-    FB_LAUNCH(ctx, k_gs_dots<NVB>, gv, FB_TPB, 0, N, nv, V, w, ctx->d_red, ctx->d_ticket, sc + GM_HD1,         \
-              sc + GM_MISC, ctx->d_flags);                                                                     \
-    FB_LAUNCH(ctx, k_gs_update<NVB>, gv, FB_TPB, 0, N, nv, V, sc + GM_HD1, w, ctx->d_red, ctx->d_ticket,       \
-              sc + GM_HD2, sc + GM_MISC, ctx->d_flags);                                                        \
-    FB_LAUNCH(ctx, k_gs_refine<NVB>, gv, FB_TPB, 0, N, nv, V, sc + GM_HD2, w, ctx->d_red, ctx->d_ticket,       \
-              sc + GM_MISC, ctx->d_flags);                                                                     \
+    FB_LAUNCH(ctx, k_gs_dots<NVB>, gv, FB_TPB, 0, No, N, nv, V, w, ctx->d_red, ctx->d_ticket, sc + GM_HD1,     \
+              sc + GM_MISC, ctx->d_flags, xr_next(ctx));                                                       \
+    FB_LAUNCH(ctx, k_gs_update<NVB>, gv, FB_TPB, 0, No, N, nv, V, sc + GM_HD1, w, ctx->d_red, ctx->d_ticket,   \
+              sc + GM_HD2, sc + GM_MISC, ctx->d_flags, xr_next(ctx));                                          \
+    FB_LAUNCH(ctx, k_gs_refine<NVB>, gv, FB_TPB, 0, No, N, nv, V, sc + GM_HD2, w, ctx->d_red, ctx->d_ticket,   \
+              sc + GM_MISC, ctx->d_flags, xr_next(ctx));                                                       \
   }
       if (nv <= 8) FB_GS_CASE(8)
       else if (nv <= 16) FB_GS_CASE(16)
@@ -2039,7 +2042,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
       else FB_GS_CASE(32)
 #undef FB_GS_CASE
       FB_LAUNCH(ctx, k_gmres_givens, 1, 1, 0, j, sc, ctx->d_flags);
-      FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, N, w, sc + GM_MISC + 1, V + (size_t)(j + 1) * N, ctx->d_flags);
+      FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, No, w, sc + GM_MISC + 1, V + (size_t)(j + 1) * N, ctx->d_flags);
       if (j % poll == poll - 1 || j == GM_M - 1) {
         FB_CHECK(ctx, cudaGetLastError());
         if ((rc = read_flags(ctx, fl))) return rc;
@@ -2050,12 +2053,12 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     // y += [p(B)] V yk
     if (fl[3] > 0) {
       FB_LAUNCH(ctx, k_gmres_solve_y, 1, 1, 0, sc, ctx->d_flags);
-      FB_LAUNCH(ctx, k_combine, gv, FB_TPB, 0, N, V, sc + GM_Y, ctx->d_flags, w);
+      FB_LAUNCH(ctx, k_combine, gv, FB_TPB, 0, No, N, V, sc + GM_Y, ctx->d_flags, w);
       if (cheb) {
         if ((rc = cheb_apply(ctx, w, cz, nullptr, cd0, cd1, cr, (const int*)nullptr))) return rc;
-        FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, N, 1.0, cz, y);
+        FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, No, 1.0, cz, y);
       } else {
-        FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, N, 1.0, w, y);
+        FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, No, 1.0, w, y);
       }
     }
     if (cheb_possible && !cheb && !ctx->cheb_valid && (rc = cheb_estimate(ctx, fl[3]))) return rc;
@@ -2095,6 +2098,8 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   if (ksp == FB_KSP_AUTO) ksp = ctx->tridiag ? FB_KSP_TRIDIAG : (ctx->symmetric ? FB_KSP_CG : FB_KSP_GMRES);
   if (!J && !S.vx_on) return fb_fail(ctx, "no channel operator: pass the block-CSR values");
   if (!J && ksp != FB_KSP_GMRES) return fb_fail(ctx, "the channel operator is solved with GMRES");
+  if (ctx->peer_ready && ksp != FB_KSP_GMRES)
+    return fb_fail(ctx, "partitioned meshes: fb_linear_solve runs GMRES (the partitioned CG is fb_dcg_persistent)");
   if (ksp == FB_KSP_TRIDIAG) {
     if (!ctx->tridiag) return fb_fail(ctx, "tridiagonal solver needs an interval mesh ordered along x");
     return solve_tridiag(ctx, J, b, y);
@@ -2162,9 +2167,9 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
     else status = solve_gmres(ctx, J, rhs, sol, thr_r, max_it, &its, want_cheb);
     *iters += its;
     if (status < 0) return status;
-    if (round > 0) FB_LAUNCH(ctx, k_axpy, vec_grid(ctx, S.n_dofs), FB_TPB, 0, S.n_dofs, 1.0, corr, y);
+    if (round > 0) FB_LAUNCH(ctx, k_axpy, vec_grid(ctx, S.n_owned_dofs), FB_TPB, 0, S.n_owned_dofs, 1.0, corr, y);
     if ((rc = fbi_spmv(ctx, J, y, Ay))) return rc;
-    FB_LAUNCH(ctx, k_residual, vec_grid(ctx, S.n_dofs), FB_TPB, 0, S.n_dofs, b, Ay, t);
+    FB_LAUNCH(ctx, k_residual, vec_grid(ctx, S.n_owned_dofs), FB_TPB, 0, S.n_owned_dofs, b, Ay, t);
     if ((rc = fbi_norm2(ctx, t, &rn))) return rc;
     *relres = rn / bnorm;
     if (status != 0 || *relres <= rtol || !(rn == rn)) break;
@@ -2223,7 +2228,6 @@ k_dcg_update(DevSpec S, const double* __restrict__ dinv, double alpha, double be
 // no host round trip inside the solve.
 // ---------------------------------------------------------------------------
 #define FB_XR 0       // u64 words: reduction slots [2 parities][8 ranks][3 values][2 halves]
-#define FB_XH 128     // u64 words: halo, two per ghost dof
 struct PeerArgs {
   int rank, nranks;
   unsigned seq;               // tag of version 0 of this solve (tags never repeat across solves)
@@ -2807,7 +2811,8 @@ extern "C" int fb_peer_alloc(fb_ctx* ctx, int rank, int nranks, unsigned char* h
   if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fb_fail(ctx, "1..8 ranks on one node");
   cudaSetDevice(ctx->device);
   if (!ctx->d_xchg) {
-    ctx->xchg_u_doubles = 2 * (ctx->S.n_dofs - ctx->S.n_owned * (long long)ctx->S.ns);  // two words per ghost dof
+    ctx->halo_words = 2 * (ctx->S.n_dofs - ctx->S.n_owned * (long long)ctx->S.ns);   // two words per ghost dof
+    ctx->xchg_u_doubles = 2 * ctx->halo_words;                                       // two parities
     const size_t n = (size_t)FB_XH + (size_t)ctx->xchg_u_doubles + 2;
     int rc = fb_alloc(ctx, &ctx->d_xchg, n);  // its own cudaMalloc block: exportable as a whole
     if (rc) return rc;
@@ -2853,6 +2858,7 @@ extern "C" int fb_peer_set_send(fb_ctx* ctx, int64_t n, const int32_t* v, const 
   if ((rc = fb_upload(ctx, &ctx->d_send_rank, (const int*)rank, (size_t)n))) return rc;
   if ((rc = fb_upload(ctx, &ctx->d_send_dst, (const int*)dst, (size_t)n))) return rc;
   ctx->n_send = (int)n;
+  ctx->peer_ready = ctx->peer_n > 1;   // every peer area is mapped (fb_peer_open) before the send table is set
   return 0;
 }
 

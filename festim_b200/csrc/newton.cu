@@ -72,7 +72,10 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
   double* Jv = chan ? nullptr : ctx->d_J;
   int it = 0, lin_total = 0, why = 0;
   double snorm = 0.0, f0 = 1.0, fn = 0.0;
+  // partitioned mesh: ghost entries of the fields come from their owners over peer memory
+  if (u_n != u && (rc = fbi_halo(ctx, (double*)u_n))) return rc;
   while (true) {
+    if ((rc = fbi_halo(ctx, u))) return rc;
     {
       PhaseTimer t(ctx, it == 0 ? 1 : 0);
       rc = fbi_assemble(ctx, u, u_n, ctx->d_F, Jv, (it == 0 && !chan) ? (FB_ASSEMBLE_F | FB_ASSEMBLE_J) : FB_ASSEMBLE_F);
@@ -107,9 +110,10 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
     if (rc > 0) { why = FB_DIVERGED_LINEAR_SOLVE; break; }
     {
       PhaseTimer t(ctx, 3);
-      long long g = (N + 255) / 256;
+      const long long No = ctx->S.n_owned_dofs;
+      long long g = (No + 255) / 256;
       if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
-      FB_LAUNCH(ctx, k_sub, (unsigned)g, 256, 0, N, ctx->d_y, u);
+      FB_LAUNCH(ctx, k_sub, (unsigned)g, 256, 0, No, ctx->d_y, u);
       if ((rc = fbi_norm2(ctx, ctx->d_y, &snorm))) return rc;
       t.stop();
     }
@@ -117,6 +121,14 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
   }
   FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   FB_CHECK(ctx, cudaGetLastError());
+  if (ctx->peer_ready) {   // a peer that never answered leaves the abort flag behind
+    unsigned aborted = 0;
+    FB_CHECK(ctx, cudaMemcpy(&aborted, ctx->d_ticket + 128, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (aborted) {
+      FB_CHECK(ctx, cudaMemset(ctx->d_ticket + 128, 0, sizeof(unsigned)));
+      return fb_fail(ctx, "partitioned solve: a peer rank never answered (exchange timed out)");
+    }
+  }
   if (n_its) *n_its = it;
   if (reason) *reason = why;
   if (fnorm_out) *fnorm_out = fn;

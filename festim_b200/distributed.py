@@ -292,10 +292,18 @@ class DistributedNewtonSolver:
         self.cg_iterations = 0
         self.gmres_iterations = 0
         self.launches_python = 0
-        # whole-solve persistent CG over peer memory (NVLink): default for ranks of one node
+        # peer memory (NVLink): the whole-solve persistent CG for symmetric Jacobians, and for the
+        # others the library's own Newton-GMRES with halo exchange and cross-rank reductions done by
+        # its kernels (fb_newton_solve on a partitioned mesh: no NCCL call inside the solve)
+        from festim_b200.backend import PC
+
+        pc = str(petsc_options.get("pc_type", "lu")).lower()
+        self.pc = PC.get(pc, 2)
         self.peer = False
-        if self.nranks > 1 and not os.environ.get("FB_NO_PEER_CG") and self._is_symmetric():
+        self.native = False
+        if self.nranks > 1 and not os.environ.get("FB_NO_PEER_CG"):
             self._setup_peer()
+            self.native = self.peer and not self._is_symmetric() and not os.environ.get("FB_NO_NATIVE_GMRES")
 
     def _setup_peer(self):
         """Exchange CUDA IPC handles of the per-rank exchange areas and build the send
@@ -486,6 +494,16 @@ class DistributedNewtonSolver:
     def newton_device(self, u, un, atol, rtol):
         """Newton iteration on device-resident local vectors (no host copies of fields)."""
         ctx, lib, ptr = self.ctx, self.ctx.lib, self.ctx.ptr
+        if self.native:
+            # the library's Newton-GMRES, partitioned: halos and reductions cross NVLink inside its kernels
+            n_its, reason, lin = C.c_int(0), C.c_int(0), C.c_int(0)
+            fnorm = C.c_double(0.0)
+            ctx._check(lib.fb_newton_solve(ctx.h, ptr(u), ptr(un), float(atol), float(rtol), self.stol, self.max_it,
+                                           2, self.pc, self.ksp_rtol, self.ksp_max_it, C.byref(n_its),
+                                           C.byref(reason), C.byref(fnorm), C.byref(lin)))
+            self.solver.its, self.solver.reason = n_its.value, reason.value
+            self.solver.linear_its, self.solver.fnorm = lin.value, fnorm.value
+            return n_its.value
         it, snorm, f0, lin_total, reason = 0, 0.0, 1.0, 0, 0
         while True:
             self.halo(u)

@@ -28,6 +28,12 @@ def main():
             from cases import mms_1_mobile_1_trap_steady
 
             return mms_1_mobile_1_trap_steady(3, n)[:2]
+        if case == "c2":            # BASELINE configs[2] in small: channel operator, Chebyshev-preconditioned GMRES
+            from cases import multi_isotope_traps_3d
+
+            m, iso, _ = multi_isotope_traps_3d(n, final_time=2e-2)
+            m.petsc_options = {"pc_type": "chebyshev"}
+            return m, iso[0]
         return mms_1_mobile_steady(3, n)[:2]
 
     m, H = build()
@@ -44,7 +50,7 @@ def main():
         rel = np.linalg.norm(a - b) / np.linalg.norm(b)
         ok = rel < 1e-8 and m.solver.solver.getIterationNumber() == r.solver.solver.getIterationNumber()
         print(f"DIST world={dist.get_world_size()} rel={rel:.3e} newton={m.solver.solver.its} "
-              f"linear={m.solver.solver.linear_its} gmres={m.solver.gmres_iterations} peer={m.solver.peer} ok={ok}", flush=True)
+              f"linear={m.solver.solver.linear_its} gmres={m.solver.gmres_iterations} peer={m.solver.peer} native={m.solver.native} ok={ok}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
