@@ -697,7 +697,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=None)
-    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=None)
     ap.add_argument("--parity-n", type=int, default=None)
     ap.add_argument("--ref-n", type=int, default=None)
     args = ap.parse_args()

@@ -476,12 +476,39 @@ class DistributedNewtonSolver:
         return it, bool(sth[4] == 1.0)
 
     # ---- Newton (reference problem.py:271-289, helpers.py:408-426) --------------------
+    def _sync_fields(self):
+        """Local device copies of u and u_n (owned + ghost entries): uploaded only when the host
+        arrays were touched since the last solve."""
+        ctx, p = self.ctx, self.problem
+        ux, unx = p.u.x, p.u_n.x
+        if getattr(self, "_u_loc", None) is None or ux.version != self._u_version:
+            self._u_loc = ctx.to_device("u", ux.array[self.ldofs])
+            self._u_version = ux.version
+        if not self.spec.transient:
+            return self._u_loc, self._u_loc
+        if getattr(self, "_un_loc", None) is None or unx.version != self._un_version:
+            self._un_loc = ctx.to_device("u_n", unx.array[self.ldofs])
+            self._un_version = unx.version
+        return self._u_loc, self._un_loc
+
+    def copy_solution_to_previous(self):
+        """u_n <- u on the device and on the host copy (no upload at the next solve)."""
+        p = self.problem
+        if not self.spec.transient or getattr(self, "_u_loc", None) is None or p.u.x.version != self._u_version:
+            return False
+        if getattr(self, "_un_loc", None) is None:
+            self._un_loc = self.ctx.to_device("u_n", p.u_n.x._array[self.ldofs])
+        with self.torch.cuda.stream(self.stream):
+            self._un_loc.copy_(self._u_loc)
+        p.u_n.x._array[:] = p.u.x._array
+        self._un_version = p.u_n.x.version
+        return True
+
     def solve(self):
         ctx, p = self.ctx, self.problem
         with self.torch.cuda.stream(self.stream):
             self._push_state()
-            u = ctx.to_device("u", p.u.x.array[self.ldofs])
-            un = ctx.to_device("u_n", p.u_n.x.array[self.ldofs]) if self.spec.transient else u
+            u, un = self._sync_fields()
             t = float(p.t) if hasattr(p, "t") else 0.0
             atol = self.atol(t) if callable(self.atol) else self.atol
             rtol = self.rtol(t) if callable(self.rtol) else self.rtol
@@ -489,6 +516,7 @@ class DistributedNewtonSolver:
             self.u_dev = u
             self._gather(u)
             self.stream.synchronize()
+        self._u_version = p.u.x.version   # _gather wrote the host copy itself
         return it
 
     def newton_device(self, u, un, atol, rtol):
@@ -555,13 +583,13 @@ class DistributedNewtonSolver:
         torch, dist, p = self.torch, self.dist, self.problem
         n_own = self.part.n_owned * self.ns
         if self.nranks == 1:
-            p.u.x.array[self.owned_gdofs] = u[:n_own].cpu().numpy()
+            p.u.x._array[self.owned_gdofs] = u[:n_own].cpu().numpy()
             return
         if not hasattr(self, "_gather_perm"):
             counts = [None] * self.nranks
             dist.all_gather_object(counts, self.owned_gdofs)
             pad = max(len(c) for c in counts)
-            n_glob = p.u.x.array.size
+            n_glob = p.u.x._array.size
             perm = np.full(pad * self.nranks, n_glob, dtype=np.int64)   # padding -> a dummy slot
             for q, c in enumerate(counts):
                 perm[q * pad: q * pad + len(c)] = c
@@ -576,7 +604,7 @@ class DistributedNewtonSolver:
         self._gather_glob.index_copy_(0, self._gather_perm, self._gather_recv)
         self._gather_host.copy_(self._gather_glob, non_blocking=True)
         torch.cuda.current_stream(u.device).synchronize()
-        p.u.x.array[:] = self._gather_host.numpy()[:-1]
+        p.u.x._array[:] = self._gather_host.numpy()[:-1]
 
 
 class _ProblemView:
