@@ -44,7 +44,7 @@ struct fb_ctx {
   void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int peer_rank = 0, peer_n = 0;
   unsigned peer_seq = 1;               // next unused tag of the LL words
-  unsigned xr_seq = 1, halo_seq = 1;   // tags of the cross-rank reductions / halo exchanges of the Krylov kernels
+  unsigned xr_seq = 1, halo_seq = 0x40000001u;   // tags of the cross-rank reductions / halo exchanges of the Krylov kernels
   long long halo_words = 0;            // u64 words of one parity of the halo area
   bool peer_ready = false;             // every peer area mapped and the send table set
   const int* d_send_v = nullptr; const int* d_send_rank = nullptr; const int* d_send_dst = nullptr;

@@ -105,8 +105,8 @@ __global__ void k_halo_push(XRank X, int ns, int n_send, const int* __restrict__
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)n_send * ns) return;
   const int q = (int)(t / ns), s = (int)(t - (long long)q * ns);
-  unsigned long long* dst = X.base[send_rank[q]] + FB_XH + (size_t)(X.seq & 1u) * halo_words +
-                            ((size_t)send_dst[q] * ns + s) * 2;
+  // [ghost dof][parity][2 halves]: the position does not depend on the receiver's ghost count
+  unsigned long long* dst = X.base[send_rank[q]] + FB_XH + (((size_t)send_dst[q] * ns + s) * 2 + (X.seq & 1u)) * 2;
   ll_store(dst, X.seq, x[(long long)send_v[q] * ns + s]);
 }
 __global__ void k_halo_pull(XRank X, long long n_owned_dofs, long long n_ghost_dofs, long long halo_words,
@@ -114,6 +114,6 @@ __global__ void k_halo_pull(XRank X, long long n_owned_dofs, long long n_ghost_d
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n_ghost_dofs) return;
   double v = 0.0;
-  ll_load(X.base[X.rank] + FB_XH + (size_t)(X.seq & 1u) * halo_words + (size_t)t * 2, X.seq, X.bar, v);
+  ll_load(X.base[X.rank] + FB_XH + ((size_t)t * 2 + (X.seq & 1u)) * 2, X.seq, X.bar, v);
   x[n_owned_dofs + t] = v;
 }
