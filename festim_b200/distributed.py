@@ -275,6 +275,7 @@ class DistributedNewtonSolver:
         self._bc_pick = pick[loc]
         self._bc_dofs = np.ascontiguousarray(lv[loc] * ns + uniq[loc] % ns, dtype=np.int64)
         ctx._check(ctx.lib.fb_set_dirichlet(ctx.h, len(self._bc_dofs), _np_ptr(self._bc_dofs, C.c_int64)))
+        self.device_resident = True
         self.ldofs = lp.local_dofs(ns)
         self.owned_gdofs = self.ldofs[: lp.n_owned * ns]
         self._signature = None
@@ -500,9 +501,46 @@ class DistributedNewtonSolver:
             self._un_loc = self.ctx.to_device("u_n", p.u_n.x._array[self.ldofs])
         with self.torch.cuda.stream(self.stream):
             self._un_loc.copy_(self._u_loc)
-        p.u_n.x._array[:] = p.u.x._array
+        un = self._un_loc
+        p.u_n.x.defer(lambda out: self._gather(un, out))
         self._un_version = p.u_n.x.version
         return True
+
+    # ---- derived quantities (device reductions over the cells this rank owns + one all-reduce) ------
+    def total_volume(self, species_index, vol_id):
+        """int u_s dx over the volume (reference exports/total_volume.py:23-33): every cell is
+        integrated by the rank that owns its first vertex."""
+        torch = self.torch
+        key = ("tv", vol_id)
+        cache = self.__dict__.setdefault("_dq_cache", {})
+        if key not in cache:
+            lp, mesh = self.part, self.part.mesh
+            gcells = self.problem.mesh.mesh.cells[lp.local_cells]
+            mine = self.part_of[gcells[:, 0]] == self.rank
+            tag = self.spec.cell_tag == self.spec.vol_ids.index(vol_id)
+            sel = np.nonzero(mine & tag)[0]
+            x = mesh.coords[mesh.cells[sel]]
+            J = x[:, 1:, :] - x[:, :1, :]
+            fact = {1: 1.0, 2: 2.0, 3: 6.0}[mesh.tdim]
+            w = np.abs(np.linalg.det(J)) / fact / (mesh.tdim + 1)
+            cache[key] = (torch.as_tensor(mesh.cells[sel].astype(np.int64), device=self.ctx.device),
+                          torch.as_tensor(w, device=self.ctx.device))
+        cells, w = cache[key]
+        with torch.cuda.stream(self.stream):
+            u = self._sync_fields()[0].view(-1, self.ns)[:, species_index]
+            val = (u[cells].sum(dim=1) * w).sum().reshape(1)
+            if self.nranks > 1:
+                self.dist.all_reduce(val)
+            out = float(val.cpu()[0])
+        return out
+
+    def measure_volume(self, vol_id):
+        mesh = self.problem.mesh.mesh
+        cells = self.problem.volume_meshtags.find(vol_id)
+        x = mesh.coords[mesh.cells[cells]]
+        J = x[:, 1:, :] - x[:, :1, :]
+        fact = {1: 1.0, 2: 2.0, 3: 6.0}[mesh.tdim]
+        return float(np.sum(np.abs(np.linalg.det(J))) / fact)
 
     def solve(self):
         ctx, p = self.ctx, self.problem
@@ -514,9 +552,11 @@ class DistributedNewtonSolver:
             rtol = self.rtol(t) if callable(self.rtol) else self.rtol
             it = self.newton_device(u, un, atol, rtol)
             self.u_dev = u
-            self._gather(u)
             self.stream.synchronize()
-        self._u_version = p.u.x.version   # _gather wrote the host copy itself
+        # the global host field is assembled when somebody reads it.  On a partitioned run reading
+        # `u.x.array` is therefore a collective (every rank runs the same script, as under mpirun).
+        p.u.x.defer(lambda out: self._gather(u, out))
+        self._u_version = p.u.x.version
         return it
 
     def newton_device(self, u, un, atol, rtol):
@@ -576,14 +616,16 @@ class DistributedNewtonSolver:
         return spec.struct is None and not spec.adv and not spec.diff_udep and all(
             not t.derivs for t in spec.vterms + spec.fterms)
 
-    def _gather(self, u):
-        """Owned values of every rank -> the global host vector on every rank: one padded
-        NCCL all-gather, a device-side scatter into global dof order and one copy through a
-        pinned buffer (no per-rank host indexing)."""
+    def _gather(self, u, out=None):
+        """Owned values of every rank -> the global host vector (`out`, default the problem's u)
+        on every rank: one padded NCCL all-gather, a device-side scatter into global dof order and
+        one copy through a pinned buffer (no per-rank host indexing).  Collective."""
         torch, dist, p = self.torch, self.dist, self.problem
+        if out is None:
+            out = p.u.x._array
         n_own = self.part.n_owned * self.ns
         if self.nranks == 1:
-            p.u.x._array[self.owned_gdofs] = u[:n_own].cpu().numpy()
+            out[self.owned_gdofs] = u[:n_own].cpu().numpy()
             return
         if not hasattr(self, "_gather_perm"):
             counts = [None] * self.nranks
@@ -599,12 +641,13 @@ class DistributedNewtonSolver:
             self._gather_recv = torch.empty(pad * self.nranks, dtype=torch.float64, device=u.device)
             self._gather_glob = torch.empty(n_glob + 1, dtype=torch.float64, device=u.device)
             self._gather_host = torch.empty(n_glob + 1, dtype=torch.float64).pin_memory()
-        self._gather_send[:n_own] = u[:n_own]
-        dist.all_gather_into_tensor(self._gather_recv, self._gather_send)
-        self._gather_glob.index_copy_(0, self._gather_perm, self._gather_recv)
-        self._gather_host.copy_(self._gather_glob, non_blocking=True)
-        torch.cuda.current_stream(u.device).synchronize()
-        p.u.x._array[:] = self._gather_host.numpy()[:-1]
+        with torch.cuda.stream(self.stream):
+            self._gather_send[:n_own] = u[:n_own]
+            dist.all_gather_into_tensor(self._gather_recv, self._gather_send)
+            self._gather_glob.index_copy_(0, self._gather_perm, self._gather_recv)
+            self._gather_host.copy_(self._gather_glob, non_blocking=True)
+        self.stream.synchronize()
+        out[:] = self._gather_host.numpy()[:-1]
 
 
 class _ProblemView:
