@@ -594,7 +594,7 @@ def run_partitioned_c2(args, rank, world, local_rank, config):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         model = build_c2(args.n)
-        model.solver_backend = DistributedBackend(device=local_rank)
+        model.solver_backend = DistributedBackend(device=local_rank, lazy_gather=True)
         t0 = time.perf_counter()
         model.initialise()
         setup_s = time.perf_counter() - t0

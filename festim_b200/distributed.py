@@ -219,7 +219,8 @@ class _Snes:
 
 
 class DistributedNewtonSolver:
-    def __init__(self, problem, petsc_options, device=0):
+    def __init__(self, problem, petsc_options, device=0, lazy_gather=False):
+        self.lazy_gather = lazy_gather
         import torch
         import torch.distributed as dist
 
@@ -502,7 +503,10 @@ class DistributedNewtonSolver:
         with self.torch.cuda.stream(self.stream):
             self._un_loc.copy_(self._u_loc)
         un = self._un_loc
-        p.u_n.x.defer(lambda out: self._gather(un, out))
+        if self.lazy_gather:
+            p.u_n.x.defer(lambda out: self._gather(un, out))
+        else:
+            p.u_n.x._array[:] = p.u.x._array
         self._un_version = p.u_n.x.version
         return True
 
@@ -553,9 +557,12 @@ class DistributedNewtonSolver:
             it = self.newton_device(u, un, atol, rtol)
             self.u_dev = u
             self.stream.synchronize()
-        # the global host field is assembled when somebody reads it.  On a partitioned run reading
-        # `u.x.array` is therefore a collective (every rank runs the same script, as under mpirun).
-        p.u.x.defer(lambda out: self._gather(u, out))
+        if self.lazy_gather:
+            # the global host field is assembled when somebody reads it: reading `u.x.array` is then
+            # a collective (every rank must do it, as every rank runs the same script under mpirun)
+            p.u.x.defer(lambda out: self._gather(u, out))
+        else:
+            self._gather(u)
         self._u_version = p.u.x.version
         return it
 
@@ -664,8 +671,13 @@ class _ProblemView:
 
 
 class DistributedBackend:
-    def __init__(self, device=0):
+    """``lazy_gather=True`` leaves the fields on the devices after a solve and assembles the global
+    host array only when ``u.x.array`` is read - which every rank must then do together.  The
+    default gathers after every solve, so that any rank may look at the field on its own."""
+
+    def __init__(self, device=0, lazy_gather=False):
         self.device = device
+        self.lazy_gather = lazy_gather
 
     def create_newton_solver(self, problem, petsc_options):
-        return DistributedNewtonSolver(problem, petsc_options, self.device)
+        return DistributedNewtonSolver(problem, petsc_options, self.device, self.lazy_gather)
