@@ -69,6 +69,8 @@ def load_library():
         "fb_linear_solve": (i, [vp, vp, vp, vp, i, i, d, d, i, C.POINTER(i), _f64p]),
         "fb_newton_solve": (i, [vp, vp, vp, d, d, d, i, i, i, d, i, C.POINTER(i), C.POINTER(i),
                                 _f64p, C.POINTER(i)]),
+        "fb_run_steps": (i, [vp, vp, vp, _f64p, _f64p, d, i, d, d, d, i, i, i, d, i, i, d, d, i, d, i, _f64p, d,
+                             C.POINTER(i), _f64p, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "fb_last_timings": (i, [vp, _f64p]),
         "fb_stepsize_modify": (d, [d, i, d, i, d, d, i, d, i, _f64p, d]),
         "fb_hessenberg_eigenvalues": (i, [i, _f64p, _f64p, _f64p]),
@@ -104,7 +106,7 @@ EXPORTED_SYMBOLS = [
     "fb_set_spec", "fb_jit_load", "fb_set_dirichlet", "fb_num_dofs", "fb_jacobian_nnz", "fb_set_scalars",
     "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
     "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
-    "fb_newton_solve", "fb_last_timings", "fb_stepsize_modify", "fb_hessenberg_eigenvalues", "fb_chebyshev_info", "fb_total_volume",
+    "fb_newton_solve", "fb_run_steps", "fb_last_timings", "fb_stepsize_modify", "fb_hessenberg_eigenvalues", "fb_chebyshev_info", "fb_total_volume",
     "fb_total_surface", "fb_surface_flux", "fb_integrate", "fb_set_owned", "fb_set_sm_partition",
     "fb_bjacobi_setup", "fb_precond",
     "fb_peer_alloc", "fb_peer_open", "fb_peer_set_send", "fb_dcg_persistent",
@@ -491,6 +493,41 @@ class B200NewtonSolver:
         ctx.lib.fb_last_timings(ctx.h, tm)
         self.timings = np.array(list(tm))
         return n_its.value
+
+    def run_steps(self, t_stop, max_steps=4096):
+        """Device-resident time stepping until ``t_stop`` (fb_run_steps): the implicit-Euler loop of
+        reference problem.py:195-255 with the step-size rule of stepsize.py:144-167 inside the library.
+        Only for problems where nothing but t and dt changes between steps (the caller checks).
+        Returns (times at the start of every step, Newton iterations per step)."""
+        ctx, p = self.ctx, self.problem
+        self._push_state()
+        u_dev, un_dev = self._sync_fields()
+        st = p.settings.stepsize
+        ms = np.ascontiguousarray(sorted(st.milestones or []), dtype=np.float64)
+        t, dt = C.c_double(float(p.t)), C.c_double(float(p.dt.value))
+        n, lin, reason = C.c_int(0), C.c_int(0), C.c_int(0)
+        times = np.zeros(max_steps)
+        its = np.zeros(max_steps, dtype=np.int32)
+        mx = st.max_stepsize if isinstance(st.max_stepsize, (int, float)) and st.max_stepsize else 0.0
+        rc = ctx.lib.fb_run_steps(
+            ctx.h, ctx.ptr(u_dev), ctx.ptr(un_dev), C.byref(t), C.byref(dt), float(t_stop), int(max_steps),
+            float(self.atol), float(self.rtol), self.stol, self.max_it, self.ksp, self.pc, self.ksp_rtol,
+            self.ksp_max_it, int(bool(st.adaptive)), float(st.growth_factor or 1.0), float(st.cutback_factor or 1.0),
+            int(st.target_nb_iterations or 0), float(mx), len(ms), _np_ptr(ms, C.c_double) if len(ms) else None,
+            float(st.milestone_tolerance),
+            C.byref(n), _np_ptr(times, C.c_double), its.ctypes.data_as(C.POINTER(C.c_int)), C.byref(lin), C.byref(reason))
+        ctx._check(rc)
+        ns = self.spec.ns
+        p.t.value = t.value
+        p.dt.value = dt.value
+        p.u.x.defer(lambda out: ctx.nodal_from_device(u_dev, ns, out=out))
+        p.u_n.x.defer(lambda out: ctx.nodal_from_device(un_dev, ns, out=out))
+        self._u_version, self._un_version = p.u.x.version, p.u_n.x.version
+        self.library_steps = getattr(self, "library_steps", 0) + n.value
+        self.solver.its = int(its[n.value - 1]) if n.value else 0
+        self.solver.reason = reason.value
+        self.solver.linear_its = lin.value
+        return times[: n.value].tolist(), its[: n.value].tolist()
 
     # -- low-level access used by the parity tests and the benchmark -----------------
     def jacobian_index(self):

@@ -163,6 +163,53 @@ extern "C" double fb_stepsize_modify(double value, int nb_iterations, double t, 
   return updated;
 }
 
+// Device-resident implicit-Euler time stepping (reference src/festim/problem.py:195-255 with the
+// step-size rule of src/festim/stepsize.py:144-167): the whole loop "t += dt; Newton solve;
+// u_n <- u; adapt dt" runs inside the library, the fields never leave the device and no Python runs
+// between steps.  Valid while nothing but t and dt changes from step to step (time-independent
+// boundary values, sources and temperature, no per-step exports): the caller passes the time at
+// which it has to look again (next milestone / export time / final time) as t_stop.  Like the
+// reference, the last step is not clamped to t_stop unless a milestone says so.
+extern "C" int fb_run_steps(fb_ctx* ctx, double* u, double* u_n, double* t, double* dt, double t_stop,
+                            int max_steps, double atol, double rtol, double stol, int max_it, int ksp, int pc,
+                            double ksp_rtol, int ksp_max_it, int adaptive, double growth_factor,
+                            double cutback_factor, int target_nb_iterations, double max_stepsize,
+                            int n_milestones, const double* milestones, double milestone_tolerance,
+                            int* n_steps, double* times, int* newton_its, int* total_linear_its, int* reason) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  if (!ctx->S.transient || ctx->dt_scalar < 0) return fb_fail(ctx, "fb_run_steps needs a transient problem");
+  if (!u || !u_n || u == u_n || !t || !dt) return fb_fail(ctx, "fb_run_steps: bad arguments");
+  cudaSetDevice(ctx->device);
+  int rc = fbi_ensure_workspace(ctx);
+  if (rc) return rc;
+  int steps = 0, lin_total = 0, why = 1;
+  while (*t < t_stop && steps < max_steps) {
+    if (times) times[steps] = *t;
+    *t += *dt;
+    // the time step is a scalar of the compiled expressions and the 1/dt of the mass terms
+    ctx->S.inv_dt = 1.0 / *dt;
+    ctx->h_pinned[16] = *dt;
+    FB_CHECK(ctx, cudaMemcpyAsync(ctx->d_scalars + ctx->dt_scalar, ctx->h_pinned + 16, sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    int its = 0, lin = 0;
+    double fn = 0.0;
+    rc = fb_newton_solve(ctx, u, u_n, atol, rtol, stol, max_it, ksp, pc, ksp_rtol, ksp_max_it, &its, &why, &fn, &lin);
+    if (rc) return rc;
+    if (newton_its) newton_its[steps] = its;
+    lin_total += lin;
+    ++steps;
+    if (why <= 0) break;   // the caller raises, as the reference does (problem.py:238-241)
+    FB_CHECK(ctx, cudaMemcpyAsync(u_n, u, sizeof(double) * ctx->S.n_dofs, cudaMemcpyDeviceToDevice, ctx->stream));
+    *dt = fb_stepsize_modify(*dt, its, *t, adaptive, growth_factor, cutback_factor, target_nb_iterations,
+                             max_stepsize, n_milestones, milestones, milestone_tolerance);
+  }
+  FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_steps) *n_steps = steps;
+  if (total_linear_its) *total_linear_its = lin_total;
+  if (reason) *reason = why;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // derived quantities
 // ---------------------------------------------------------------------------

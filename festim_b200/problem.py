@@ -175,8 +175,44 @@ class ProblemBase:
             backend = B200Backend()
         self.solver = backend.create_newton_solver(self, petsc_options)
 
+    def _device_resident_stepping_ok(self):
+        """True when nothing but t and dt changes between time steps and nobody looks at the
+        fields in between: the whole loop can then run inside the library (fb_run_steps)."""
+        import os
+
+        st = self.settings.stepsize
+        if os.environ.get("FB_NO_RUN_STEPS") or not hasattr(self.solver, "run_steps"):
+            return False
+        if getattr(self, "exports", None) or callable(self.settings.atol) or callable(self.settings.rtol):
+            return False
+        if callable(getattr(st, "max_stepsize", None)) or type(self).iterate is not ProblemBase.iterate:
+            return False
+        if getattr(self, "temperature_time_dependent", False) or isinstance(getattr(self, "temperature", None), fem.Function):
+            return False
+        if any(getattr(bc, "time_dependent", False) for bc in getattr(self, "boundary_conditions", [])):
+            return False
+        if any(src.value.explicit_time_dependent for src in getattr(self, "sources", [])):
+            return False
+        if any(getattr(bc, "temperature_dependent", False) and self.temperature_time_dependent
+               for bc in getattr(self, "boundary_conditions", [])):
+            return False
+        return True
+
     def run(self):
         if self.settings.transient:
+            if self._device_resident_stepping_ok():
+                # device-resident stepping: same loop, same step-size rule, inside the library
+                while self.t.value < self.settings.final_time:
+                    times, its = self.solver.run_steps(self.settings.final_time)
+                    self._timesteps.extend(times)
+                    reason = self.solver.solver.getConvergedReason()
+                    assert reason > 0, (
+                        f"Non-linear solver did not converge. Reason code: {reason}. \n See https://petsc.org/release/manualpages/SNES/SNESConvergedReason/ for more information."
+                    )
+                    if not times:
+                        break
+                self.post_processing()
+                return
             while self.t.value < self.settings.final_time:
                 self.iterate()
         else:

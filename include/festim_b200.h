@@ -136,6 +136,17 @@ int fb_newton_solve(fb_ctx* ctx, double* u /*[dev]*/, const double* u_n /*[dev]*
                     double rtol, double stol, int max_it, int ksp, int pc, double ksp_rtol,
                     int ksp_max_it, int* n_its, int* reason, double* fnorm,
                     int* total_linear_its);
+/* Device-resident implicit-Euler stepping (reference problem.py:195-255, stepsize.py:144-167):
+ * "t += dt; Newton solve; u_n <- u; adapt dt" repeated inside the library until t >= t_stop, a
+ * solve fails or max_steps is reached.  Valid while only t and dt change between steps; u, u_n
+ * stay on the device.  times[k], newton_its[k] describe step k; *reason is the last solve's. */
+int fb_run_steps(fb_ctx* ctx, double* u /*[dev]*/, double* u_n /*[dev]*/, double* t /*[host] in/out*/,
+                 double* dt /*[host] in/out*/, double t_stop, int max_steps, double atol, double rtol,
+                 double stol, int max_it, int ksp, int pc, double ksp_rtol, int ksp_max_it, int adaptive,
+                 double growth_factor, double cutback_factor, int target_nb_iterations,
+                 double max_stepsize /*<=0: none*/, int n_milestones, const double* milestones /*[host]*/,
+                 double milestone_tolerance, int* n_steps, double* times /*[host] max_steps or NULL*/,
+                 int* newton_its /*[host] max_steps or NULL*/, int* total_linear_its, int* reason);
 /* timing of the last fb_newton_solve, CUDA events on ctx's stream, milliseconds:
  * out[0]=assembly F, out[1]=assembly J(+F), out[2]=linear solve, out[3]=other */
 int fb_last_timings(fb_ctx* ctx, double* out /*[host] 4*/);

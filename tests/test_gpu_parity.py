@@ -302,3 +302,75 @@ def test_recombination_flux_parity(dim, n):
     assert gm.solver.solver.getIterationNumber() == rm.solver.solver.getIterationNumber()
     for a, b in zip(sg, sr):
         assert _rel(a.post_processing_solution.x.array, b.post_processing_solution.x.array) < 1e-8
+
+
+def test_device_resident_stepping_matches_the_python_loop(monkeypatch):
+    """fb_run_steps (the implicit-Euler loop with the adaptive step-size rule inside the library, fields
+    on the device throughout) against the same run driven step by step from Python: identical time
+    steps (reference stepsize.py:144-167 incl. milestones) and the same field."""
+    from cases import multi_isotope_traps_3d
+
+    def run(python_loop):
+        m, _, _ = multi_isotope_traps_3d(3, dt=1e-2, final_time=0.2)
+        m.settings.stepsize = F.Stepsize(initial_value=1e-2, growth_factor=1.5, cutback_factor=0.8,
+                                         target_nb_iterations=3, milestones=[0.05, 0.11])
+        if python_loop:
+            monkeypatch.setenv("FB_NO_RUN_STEPS", "1")
+        else:
+            monkeypatch.delenv("FB_NO_RUN_STEPS", raising=False)
+        m.initialise()
+        m.run()
+        return m
+
+    lib, py = run(False), run(True)
+    assert getattr(lib.solver, "library_steps", 0) == len(lib.timesteps) > 3
+    assert getattr(py.solver, "library_steps", 0) == 0
+    assert lib.timesteps == py.timesteps
+    assert float(lib.t) == float(py.t) and float(lib.dt.value) == float(py.dt.value)
+    assert _rel(lib.u.x.array, py.u.x.array) < 1e-12
+    assert _rel(lib.u_n.x.array, py.u_n.x.array) < 1e-12
+
+
+def test_chebyshev_preconditioned_gmres_parity():
+    """C2 in small with pc_type=chebyshev (what large channel-operator systems get by default):
+    the polynomially preconditioned GMRES reproduces the oracle's fields and Newton iteration counts."""
+    from cases import multi_isotope_traps_3d
+
+    gm, _, _ = multi_isotope_traps_3d(5, final_time=3e-2)
+    gm.petsc_options = {"pc_type": "chebyshev"}
+    rm, _, _ = multi_isotope_traps_3d(5, final_time=3e-2)
+    rm.solver_backend = OracleBackend()
+    nit_g, nit_r = [], []
+    for m, its in ((gm, nit_g), (rm, nit_r)):
+        m.initialise()
+        while float(m.t) < m.settings.final_time:
+            m.iterate()
+            its.append(m.solver.solver.getIterationNumber())
+    import ctypes as C
+
+    info = (C.c_double * 4)()
+    gm.solver.ctx.lib.fb_chebyshev_info(gm.solver.ctx.h, info)
+    assert info[0] == 1.0 and 0 < info[1] < info[2]
+    assert nit_g == nit_r
+    assert _rel(gm.u.x.array, rm.u.x.array) < 1e-8
+
+
+def test_host_arrays_follow_the_device_fields():
+    """The fields stay on the device between solves: the host arrays are refreshed when read, and
+    an in-place edit of u.x.array by the user is picked up by the next solve."""
+    from cases import multi_isotope_traps_3d
+
+    a, _, _ = multi_isotope_traps_3d(3, final_time=1e9)
+    b, _, _ = multi_isotope_traps_3d(3, final_time=1e9)
+    for m in (a, b):
+        m.initialise()
+        m.iterate()
+    assert _rel(a.u.x.array, b.u.x.array) < 1e-14
+    # a user edit on the host between two steps
+    for m in (a, b):
+        m.u.x.array[:] *= 1.5
+    a.iterate()
+    b.u_n.x.array[:] = b.u_n.x.array      # touching u_n as well must not change anything
+    b.iterate()
+    assert _rel(a.u.x.array, b.u.x.array) < 1e-13
+    assert np.array_equal(a.u_n.x.array, a.u.x.array)
