@@ -79,8 +79,6 @@ struct fb_ctx {
   double* d_work = nullptr;  // Krylov vectors
   long long work_doubles = 0;
   double* d_dinv = nullptr;  // block-Jacobi inverse blocks [n_vertices][ns][ns]
-  float* d_dinv32 = nullptr; // the same blocks in single precision (streamed by the TMA channel kernels)
-  bool dinv32 = false, dinv32_refused = false;
   double* d_red = nullptr;   // reduction partials
   long long red_doubles = 0;
   double* d_sc = nullptr;    // device scalars of the Krylov loops

@@ -299,7 +299,7 @@ static int spmv_ch(fb_ctx* ctx, const double* x, double* y, bool precond, const 
   if (int rc = fbi_halo(ctx, (double*)x)) return rc;
   if (spmv_ch_tma_ok(ctx, x)) {
     SpmvChArgs a{};
-    a.x = x; a.y = y; a.dinv = ctx->d_dinv; a.dinv32 = ctx->dinv32 ? ctx->d_dinv32 : nullptr; a.flags = flags;
+    a.x = x; a.y = y; a.dinv = ctx->d_dinv; a.flags = flags;
     return precond ? spmv_ch_tma_launch<1>(ctx, a) : spmv_ch_tma_launch<0>(ctx, a);
   }
   return precond ? spmv_ch_launch<true>(ctx, x, y, flags) : spmv_ch_launch<false>(ctx, x, y, flags);
@@ -546,8 +546,7 @@ __global__ void k_bjacobi_setup(DevSpec S, const double* __restrict__ J, double*
 // costs 10 ms for 857 k blocks of 12 x 12; this one stays on chip.
 template <int G>
 __global__ void __launch_bounds__(256)
-k_bjacobi_setup_coop(DevSpec S, const double* __restrict__ J, double* __restrict__ dinv, float* __restrict__ dinv32,
-                     int* __restrict__ flags) {
+k_bjacobi_setup_coop(DevSpec S, const double* __restrict__ J, double* __restrict__ dinv, int* __restrict__ flags) {
   extern __shared__ double bj_smem[];
   const int g = threadIdx.x & (G - 1), grp = threadIdx.x / G, gpb = blockDim.x / G;
   const long long v = (long long)blockIdx.x * gpb + grp;
@@ -590,12 +589,6 @@ k_bjacobi_setup_coop(DevSpec S, const double* __restrict__ J, double* __restrict
     for (int p = g; p < S.npairs; p += G) A[S.pair_row[p] * ns + S.pair_cs[p]] = J[base + p];
   }
   __syncwarp(gmask);
-  double norm_a = 0.0;   // max |entry| of the block: with the inverse's, a bound on its conditioning
-  if (dinv32) {
-    for (int t = g; t < nn; t += G) norm_a = fmax(norm_a, fabs(A[t]));
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) norm_a = fmax(norm_a, __shfl_xor_sync(gmask, norm_a, o));
-  }
   unsigned long long perm = 0ull;   // 4 bits per column: the row it was swapped with
   for (int col = 0; col < ns; ++col) {
     // pivot: largest |A[r][col]|, r >= col (ties -> smallest r)
@@ -636,28 +629,7 @@ k_bjacobi_setup_coop(DevSpec S, const double* __restrict__ J, double* __restrict
     }
   }
   double* __restrict__ out = dinv + v * (long long)nn;
-  if (!dinv32) {
-    for (int t = g; t < nn; t += G) out[t] = A[t];
-    return;
-  }
-  // single-precision copy for the streaming kernels (it is a preconditioner: the solve's accuracy
-  // is set by the true residual).  Both copies hold the SAME rounded values, so that every
-  // application of D^-1 in a solve is the same operator.  Out-of-range or badly conditioned blocks
-  // raise flags[5]: the host then keeps double precision.
-  float* __restrict__ out32 = dinv32 + v * (long long)nn;
-  double norm_i = 0.0;
-  bool bad = false;
-  for (int t = g; t < nn; t += G) {
-    const double a = A[t];
-    norm_i = fmax(norm_i, fabs(a));
-    if (a != 0.0 && (fabs(a) > 1e30 || fabs(a) < 1e-30)) bad = true;
-    const float f = (float)a;
-    out32[t] = f;
-    out[t] = (double)f;
-  }
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) norm_i = fmax(norm_i, __shfl_xor_sync(gmask, norm_i, o));
-  if (bad || !(norm_a * norm_i * (double)nn < 1e7)) flags[5] = 1;
+  for (int t = g; t < nn; t += G) out[t] = A[t];
 }
 
 static int bjacobi_setup(fb_ctx* ctx, const double* J) {
@@ -668,30 +640,7 @@ static int bjacobi_setup(fb_ctx* ctx, const double* J) {
   }
   const int G = 16, gpb = 256 / G;
   const size_t smem = (size_t)gpb * (S.ns * S.ns + 2 * S.ns + 2) * sizeof(double);
-  // single-precision inverse blocks for the TMA-pipelined channel kernels (half the bytes of the
-  // largest stream of a preconditioned operator application)
-  bool want32 = !J && S.vx_on && S.ns % 2 == 0 && S.ck_nx_max > 0 && !ctx->dinv32_refused && !getenv("FB_NO_DINV_FP32") &&
-                !getenv("FB_NO_TMA_SPMV");
-  ctx->dinv32 = false;
-  if (want32 && !ctx->d_dinv32) {
-    int rc = fb_alloc(ctx, &ctx->d_dinv32, (size_t)S.n_vertices * S.ns * S.ns + 64);
-    if (rc) return rc;
-  }
-  if (want32) FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags + 5, 0, sizeof(int), ctx->stream));
-  FB_LAUNCH(ctx, k_bjacobi_setup_coop<16>, (unsigned)((S.n_owned + gpb - 1) / gpb), 256, smem, S, J, ctx->d_dinv,
-            want32 ? ctx->d_dinv32 : (float*)nullptr, ctx->d_flags);
-  if (want32) {
-    int bad = 0;
-    FB_CHECK(ctx, cudaMemcpyAsync(&bad, ctx->d_flags + 5, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (bad) {   // keep double precision for this problem
-      ctx->dinv32_refused = true;
-      FB_LAUNCH(ctx, k_bjacobi_setup_coop<16>, (unsigned)((S.n_owned + gpb - 1) / gpb), 256, smem, S, J, ctx->d_dinv,
-                (float*)nullptr, ctx->d_flags);
-    } else {
-      ctx->dinv32 = true;
-    }
-  }
+  FB_LAUNCH(ctx, k_bjacobi_setup_coop<16>, (unsigned)((S.n_owned + gpb - 1) / gpb), 256, smem, S, J, ctx->d_dinv, ctx->d_flags);
   return 0;
 }
 
@@ -2009,7 +1958,7 @@ static int cheb_apply(fb_ctx* ctx, const double* v, double* z, double* w, double
   for (int i = 0; i < steps; ++i) {
     const double rho_n = 1.0 / (2.0 * sigma - rho);
     SpmvChArgs a{};
-    a.x = din; a.dinv = ctx->d_dinv; a.dinv32 = ctx->dinv32 ? ctx->d_dinv32 : nullptr; a.flags = flags;
+    a.x = din; a.dinv = ctx->d_dinv; a.flags = flags;
     a.r = r; a.z = z; a.dout = dout; a.vin = v; a.wout = w;
     a.ca = rho_n * rho; a.cb = 2.0 * rho_n / delta;
     a.last = (w && i == m) ? 1 : 0;

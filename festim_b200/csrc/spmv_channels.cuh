@@ -134,7 +134,6 @@ struct SpmvChArgs {
   const double* x;
   double* y;
   const double* dinv;
-  const float* dinv32;   // single-precision copy of the same blocks, or null
   const int* flags;
   // Chebyshev step (MODE 2)
   double* r;
@@ -241,7 +240,7 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
       const int nlc = (ne + 7) & ~7;
       if (lane == 0) {
         unsigned bytes = (unsigned)(ne * (NSP + NDP) * 8 + nx * ns * 8 + nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
-        if (MODE >= 1) bytes += (unsigned)(nrow * ns * ns * (a.dinv32 ? 4 : 8));
+        if (MODE >= 1) bytes += (unsigned)(nrow * ns * ns * 8);
         if (MODE == 2) bytes += (unsigned)((a.last ? 3 : 2) * nrow * ns * 8);
         fb_mbar_expect_tx(b, bytes);
       }
@@ -252,10 +251,8 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
       if (lane == 3) fb_bulk_g2s(st + a.s_vinfo, S.vinfo + c0, (unsigned)(CH * 4), b);
       if (lane == 4) fb_bulk_g2s(st + a.s_rowinfo, S.ck_rowinfo + c0, (unsigned)(CH * 4), b);
       if (lane == 9) fb_bulk_g2s(st + a.s_rowptr, S.rowptr + c0, (unsigned)((CH + 4) * 4), b);
-      if (MODE >= 1 && lane == 5) {
-        if (a.dinv32) fb_bulk_g2s(st + a.s_dinv, a.dinv32 + c0 * ns * ns, (unsigned)(nrow * ns * ns * 4), b);
-        else fb_bulk_g2s(st + a.s_dinv, a.dinv + c0 * ns * ns, (unsigned)(nrow * ns * ns * 8), b);
-      }
+      if (MODE >= 1 && lane == 5)
+        fb_bulk_g2s(st + a.s_dinv, a.dinv + c0 * ns * ns, (unsigned)(nrow * ns * ns * 8), b);
       if (MODE == 2) {
         if (lane == 6) fb_bulk_g2s(st + a.s_r, a.r + c0 * ns, (unsigned)(nrow * ns * 8), b);
         if (lane == 7) fb_bulk_g2s(st + a.s_z, a.z + c0 * ns, (unsigned)(nrow * ns * 8), b);
@@ -404,16 +401,7 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
           double p;
           const int t = j * ns + lane;
           if (ns == 1) p = ((const double*)(st + a.s_dinv))[t] * yrow[0];
-          else if (a.dinv32) {
-            const float2* dv = (const float2*)(st + a.s_dinv) + (size_t)t * (ns / 2);   // row s of the inverse block
-            double pa = 0.0, pb = 0.0;
-            for (int c2 = 0; c2 < ns; c2 += 2) {
-              const float2 d2 = dv[c2 >> 1];
-              pa += (double)d2.x * yrow[c2];
-              pb += (double)d2.y * yrow[c2 + 1];
-            }
-            p = pa + pb;
-          } else {
+          else {
             const double2* dv = (const double2*)(st + a.s_dinv) + (size_t)t * (ns / 2);   // row s of the inverse block
             double pa = 0.0, pb = 0.0;
             for (int c2 = 0; c2 < ns; c2 += 2) {   // ns is even (16-byte rows)
