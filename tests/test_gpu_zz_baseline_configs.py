@@ -159,3 +159,61 @@ def test_coupled_non_matching_meshes_parity():
     assert _rel(cg.heat_problem.u.x.array, cr.heat_problem.u.x.array) < 1e-8
     assert _rel(mg.post_processing_solution.x.array, mr.post_processing_solution.x.array) < 1e-8
     assert error_L2(cg.hydrogen_problem.mesh.mesh, mg.post_processing_solution.x.array, exact) < 1e-5
+
+
+def test_c2_parity_beyond_one_block_per_sm():
+    """C2 at n=12 (2197 vertices, 26364 dofs): more vertices than 4 x 148, so the per-SM RCB
+    renumbering, the chunk plan with many runs and the channel-operator kernels (TMA / DMMA SpMV,
+    Chebyshev-preconditioned GMRES when forced) run on a partition, not on a toy mesh.  Fields and
+    the inventory export against the oracle, two time steps."""
+    import festim_b200 as F
+    from cases import multi_isotope_traps_3d
+
+    def build(cheb):
+        m, iso, _ = multi_isotope_traps_3d(12, final_time=2e-2)
+        m.exports = [F.TotalVolume(field=iso[0], volume=m.subdomains[0])]
+        if cheb:
+            m.petsc_options = {"pc_type": "chebyshev"}
+        return m
+
+    ref = build(False)
+    ref.solver_backend = OracleBackend()
+    ref.initialise()
+    ref.run()
+    for cheb in (False, True):
+        g = build(cheb)
+        g.initialise()
+        assert g.solver.ctx.perm is not None          # renumbered into per-SM parts
+        g.run()
+        assert g.timesteps == ref.timesteps
+        assert _rel(g.u.x.array, ref.u.x.array) < 1e-8
+        _same_exports(g.exports, ref.exports)
+
+
+def test_c1_parity_at_150k_vertices():
+    """C1 at n=53 (157 464 vertices: the persistent two-level CG with the operator in shared memory
+    at its real size, > 48 KB per block) against the oracle's discrete system.  The problem is
+    linear, so the oracle's Newton step is one solve of its assembled system; a sparse LU of a 3D
+    system of this size takes minutes, so the oracle's matrix and right-hand side are solved here
+    with scipy's CG to 1e-13 instead (test infrastructure, same discrete equations)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    from cases import error_L2, mms_1_mobile_steady
+
+    g, Hg, exact = mms_1_mobile_steady(3, 53)
+    g.initialise()
+    g.run()
+    assert g.solver.solver.getIterationNumber() == 1 and g.solver.solver.getConvergedReason() > 0
+    r, Hr, _ = mms_1_mobile_steady(3, 53)
+    r.solver_backend = OracleBackend()
+    r.initialise()
+    x0 = r.u.x.array.copy()
+    b, J = r.solver.residual_and_jacobian(x0)
+    d = J.diagonal()
+    M = spla.LinearOperator(J.shape, matvec=lambda v: v / d)
+    y, info = spla.cg(sp.csr_matrix(J), b, rtol=1e-13, atol=0.0, maxiter=5000, M=M)
+    assert info == 0
+    u_ref = x0 - y
+    assert _rel(g.u.x.array, u_ref) < 1e-8
+    assert error_L2(g.mesh.mesh, Hg.post_processing_solution.x.array, exact) < 1e-2
