@@ -282,8 +282,8 @@ static int et_launch(fb_ctx* ctx, int which, const double* u, const double* un, 
 static bool asm_tma_ok(fb_ctx* ctx, const double* u, const double* un) {
   const DevSpec& S = ctx->S;
   return S.vx_on && (S.ns % 2 == 0) && S.ns <= 32 && (((uintptr_t)u & 15) == 0) && (((uintptr_t)un & 15) == 0) &&
-         S.ck_nx_max > 0 && S.vx_nts <= 11 && S.maxdeg <= 64 && getenv("FB_TMA_ASSEMBLY");   // opt-in: measured slower
-         // than k_assemble_edge at C2 (5.05 vs 4.17 ms: the per-row consumer code is issue-bound)
+         S.ck_nx_max > 0 && S.vx_nts <= 11 && S.maxdeg <= 16 && S.vx_nch <= 16 && S.vx_nbw <= 64 &&
+         !getenv("FB_NO_TMA_ASSEMBLY");   // rows of up to 16 edges: both contractions run as DMMA tiles
 }
 
 static int asm_tma_launch(fb_ctx* ctx, const double* u, const double* un, double* F, int flags, bool* done) {
@@ -293,7 +293,7 @@ static int asm_tma_launch(fb_ctx* ctx, const double* u, const double* un, double
   a.u = u; a.un = un; a.F = F; a.dyn = (double*)S.et_dyn; a.flags = flags;
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-  int nst = 2 * FB_CHUNK_GROUPS;
+  int nst = 3 * FB_CHUNK_GROUPS;
   if (getenv("FB_ASM_STAGES")) nst = atoi(getenv("FB_ASM_STAGES"));
   if (nst > 8) nst = 8;
   size_t smem = fb_asm_tma_layout(S, a, nst);

@@ -28,7 +28,7 @@ struct AsmTmaArgs {
   int o_tab_i, o_scr, scr_bytes, o_stage0, stage_bytes, o_bar;
   int s_tvw, s_tz, s_tzs, s_us, s_uns, s_load, s_lcol, s_vinfo, s_rowinfo, s_rowptr, s_tzptr, s_tzw;
   int tz_stride;   // doubles per tensor inside a stage
-  int w_fv, w_adyn, w_res;   // offsets (doubles) inside a warp's scratch
+  int w_fv, w_adyn, w_res, w_tf, rts;   // offsets (doubles) inside a warp's scratch; row stride of the R tile
 };
 
 __host__ inline size_t fb_asm_tma_layout(const DevSpec& S, AsmTmaArgs& a, int nst) {
@@ -42,6 +42,9 @@ __host__ inline size_t fb_asm_tma_layout(const DevSpec& S, AsmTmaArgs& a, int ns
   a.w_adyn = w; w += md * (S.vx_ndp > 0 ? S.vx_ndp : 1);
   const int nres = S.vx_nft > S.vx_njt ? S.vx_nft : S.vx_njt;
   a.w_res = w; w += nres > 0 ? nres : 1;
+  // expanded tensor row (16 x 17), later the residual products R[channel][table column] (16 x rts)
+  a.rts = 8 * ((S.vx_nbw + 7) / 8) + 1;
+  a.w_tf = w; w += 16 * (a.rts > 17 ? a.rts : 17);
   a.o_scr = (int)o; a.scr_bytes = (int)up16((size_t)w * 8); o += (size_t)CH * FB_CHUNK_GROUPS * a.scr_bytes;
   size_t s = 0;
   s += up16((size_t)CH * md * S.vx_nsp * 8);                       // static channel values
@@ -209,56 +212,60 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
         fv[t] = val;
       }
       __syncwarp();
-      // ---- dynamic channel values: A^c_vw = sum_z T_vwz f_c(z) --------------------------------------
+      // Rows of up to 16 edges (every row of a structured simplex mesh) do both contractions on the
+      // fp64 tensor cores (DMMA m8n8k4: lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2],
+      // C[l >> 2][2 (l & 3) + {0, 1}]); the launcher only selects this kernel when maxdeg <= 16.
+      const int krow = lane & 3, bcol = lane >> 2;
+      double* tf = scr + a.w_tf;
+      // ---- dynamic channel values: A^c[k] = sum_z T[k][z] f_c(z), T the row's tensor expanded to 16 x 16 --
       if (ndyn > 0) {
         const long long* tzptr_s = (const long long*)(st + a.s_tzptr);
         const int tzr = (int)(tzptr_s[j] - tzptr_s[0]);
         const int Wd = ((const int*)(st + a.s_tzw))[j];
         const unsigned char* zs = (const unsigned char*)(st + a.s_tzs) + tzr;
-        // rows of up to 16 edges use both half-warps: each takes every other dynamic channel
-        const bool split = deg <= 16;
-        const int half = split ? lane >> 4 : 0, nhalf = split ? 2 : 1;
         for (int ts = 0; ts < nts; ++ts) {
           const double* Tvw = (const double*)(st + a.s_tvw) + 2 * ((size_t)ts * CH * S.maxdeg + rp0);
           const double* Tz = (const double*)(st + a.s_tz) + (size_t)ts * a.tz_stride + tzr;
-          const int d0 = itab[S.vx_o_dynptr + ts], d1 = itab[S.vx_o_dynptr + ts + 1];
-          for (int kb = 0; kb < deg; kb += (split ? 16 : 32)) {
-            const int k = kb + (split ? (lane & 15) : lane);
-            const bool act = k < deg && k != kself;
-            double tvk = 0.0, twk = 0.0, tj[FB_ET_WREG];
-            int zj[FB_ET_WREG], zl[FB_ET_WREG];
-            const int lk = act ? lc[k] : 0;
-            if (act) { tvk = Tvw[2 * k]; twk = Tvw[2 * k + 1]; }
-#pragma unroll
-            for (int q = 0; q < FB_ET_WREG; ++q) {
-              tj[q] = 0.0; zj[q] = 0; zl[q] = 0;
-              if (act && q < Wd) {
+          for (int t = lane; t < 16 * 17; t += 32) tf[t] = 0.0;
+          __syncwarp();
+          if (lane < deg) {
+            const int k = lane;
+            const double tvk = Tvw[2 * k];
+            tf[kself * 17 + k] = tvk;                       // diagonal edge: T_vvz, z = k
+            if (k != kself) {
+              tf[k * 17 + kself] = tvk;                     // z = v
+              tf[k * 17 + k] = Tvw[2 * k + 1];              // z = w
+              for (int q = 0; q < Wd; ++q) {
                 const int zz = zs[q * deg + k];
-                if (zz != 0xff) { zj[q] = zz; zl[q] = lc[zz]; tj[q] = Tz[q * deg + k]; }
-              }
-            }
-            if (act) {
-              for (int dd = d0 + half; dd < d1; dd += nhalf) {
-                const int cch = itab[S.vx_o_dyn + 2 * dd], fc = itab[S.vx_o_dyn + 2 * dd + 1];
-                double av = tvk * nbval(fc, lself, kself) + twk * nbval(fc, lk, k);
-#pragma unroll
-                for (int q = 0; q < FB_ET_WREG; ++q) av += tj[q] * nbval(fc, zl[q], zj[q]);
-                for (int q = FB_ET_WREG; q < Wd; ++q) {
-                  const int zz = zs[q * deg + k];
-                  if (zz != 0xff) av += Tz[q * deg + k] * nbval(fc, lc[zz], zz);
-                }
-                adyn[k * NDP + (cch - nstat)] = av;
+                if (zz != 0xff) tf[k * 17 + zz] = Tz[q * deg + k];
               }
             }
           }
-          for (int dd = d0; dd < d1; ++dd) {   // diagonal edge: sum over all neighbours z of T_vvz f(z)
-            const int cch = itab[S.vx_o_dyn + 2 * dd], fc = itab[S.vx_o_dyn + 2 * dd + 1];
-            double p = 0.0;
-            for (int k = lane; k < deg; k += 32) p += Tvw[2 * k] * nbval(fc, lc[k], k);
+          __syncwarp();
+          const int d0 = itab[S.vx_o_dynptr + ts], d1 = itab[S.vx_o_dynptr + ts + 1];
+          for (int n0 = 0; n0 < d1 - d0; n0 += 8) {
+            // B operand: factor of column n0 + bcol at the neighbours z = 4 u + krow
+            const bool cok = n0 + bcol < d1 - d0;
+            const int fc = cok ? itab[S.vx_o_dyn + 2 * (d0 + n0 + bcol) + 1] : 0;
+            double bv[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
-            if (lane == 0) adyn[kself * NDP + (cch - nstat)] = p;
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const int z = 4 * u4 + krow;
+              bv[u4] = (cok && z < deg) ? nbval(fc, lc[z], z) : 0.0;
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4)
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) fb_dmma(acc[mt][0], acc[mt][1], tf[(8 * mt + bcol) * 17 + 4 * u4 + krow], bv[u4]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int k = 8 * mt + bcol, cc = n0 + 2 * krow + h2;
+                if (k < deg && cc < d1 - d0) adyn[k * NDP + (itab[S.vx_o_dyn + 2 * (d0 + cc)] - nstat)] = acc[mt][h2];
+              }
           }
+          __syncwarp();
         }
         for (int t = lane; t < deg; t += 32)
           for (int cpad = ndyn; cpad < NDP; ++cpad) adyn[t * NDP + cpad] = 0.0;
@@ -267,16 +274,46 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
         for (int t = lane; t < deg * NDP; t += 32) dst[t] = adyn[t];
       }
       if (doF) {
-        // ---- residual ---------------------------------------------------------------------------------
+        // ---- residual: R[c][g] = sum_k A^c[k] nb[k][g] (table column g), then F_s = load + sum_e coef_e R[c_e][g_e]
+        const int RTS = a.rts, ntg = (S.vx_nbw + 7) / 8, mtc = (S.vx_nch + 7) / 8;
+        double av[4][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int ch = 8 * mt + bcol;
+          const bool cok = ch < S.vx_nch;
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            const int k = 4 * u4 + krow;
+            double v = 0.0;
+            if (cok && k < deg) v = ch < nstat ? sr[k * NSP + ch] : adyn[k * NDP + ch - nstat];
+            av[u4][mt] = v;
+          }
+        }
+        __syncwarp();   // tf is free: it becomes the R tile
+        for (int nt = 0; nt < ntg; ++nt) {
+          const int gcol = 8 * nt + bcol;
+          double bv[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            const int k = 4 * u4 + krow;
+            bv[u4] = (gcol < S.vx_nbw && k < deg) ? nbval(gcol, lc[k], k) : 0.0;
+          }
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            fb_dmma(acc[0][0], acc[0][1], av[u4][0], bv[u4]);
+            if (mtc > 1) fb_dmma(acc[1][0], acc[1][1], av[u4][1], bv[u4]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            tf[(8 * mt + bcol) * RTS + 8 * nt + 2 * krow] = acc[mt][0];
+            tf[(8 * mt + bcol) * RTS + 8 * nt + 2 * krow + 1] = acc[mt][1];
+          }
+        }
+        __syncwarp();
         const int nft = S.vx_nft;
         for (int t = lane; t < nft; t += 32) {
           const int chan = itab[S.vx_o_ft + 3 * t], gcol = itab[S.vx_o_ft + 3 * t + 1], fl = itab[S.vx_o_ft + 3 * t + 2];
-          double acc = 0.0;
-          if (chan < nstat)
-            for (int k = 0; k < deg; ++k) acc += sr[k * NSP + chan] * nbval(gcol, lc[k], k);
-          else
-            for (int k = 0; k < deg; ++k) acc += adyn[k * NDP + chan - nstat] * nbval(gcol, lc[k], k);
-          res[t] = acc * dtab[S.vx_o_ftc + t] * ((fl & 1) ? S.inv_dt : 1.0);
+          res[t] = tf[chan * RTS + gcol] * dtab[S.vx_o_ftc + t] * ((fl & 1) ? S.inv_dt : 1.0);
         }
         __syncwarp();
         double facc = 0.0;

@@ -145,8 +145,9 @@ def test_emulated_chebyshev_preconditioned_gmres():
 
 
 def test_emulated_tma_assembly_matches_the_row_kernel(monkeypatch):
-    """The TMA-pipelined Newton-iteration assembly (assemble_edge_tma.cuh, opt-in through
-    FB_TMA_ASSEMBLY) writes the same residual and channel operator as the row kernel."""
+    """The TMA-pipelined Newton-iteration assembly (assemble_edge_tma.cuh: bulk-copy pipeline, both
+    contractions as DMMA tiles) writes the same residual and channel operator as the row kernel
+    (k_assemble_edge, selected with FB_NO_TMA_ASSEMBLY)."""
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         m = cases.multi_isotope_traps_3d(2)[0]
@@ -158,7 +159,7 @@ def test_emulated_tma_assembly_matches_the_row_kernel(monkeypatch):
     u = rng.uniform(0.5, 1.5, N) * 1e18
     un = rng.uniform(0.5, 1.5, N) * 1e18
     F0, J0 = es.assemble(u, un, 3)
-    monkeypatch.setenv("FB_TMA_ASSEMBLY", "1")
+    monkeypatch.setenv("FB_NO_TMA_ASSEMBLY", "1")
     F1, J1 = es.assemble(u, un, 3)
     assert np.abs(F1 - F0).max() <= 1e-13 * np.abs(F0).max()
     assert np.abs((J1 - J0).tocoo().data).max(initial=0.0) <= 1e-13 * np.abs(J0.data).max()
