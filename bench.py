@@ -9,7 +9,7 @@ the device; the metric is dofs x Newton iterations / time.  `--workload c1` keep
 configuration (3D MMS steady diffusion, n=55).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                  [--workload c2|c1] [--n 94] [--parity-n 12] [--ref-n 12]
+                  [--workload c2|c1] [--n 94] [--parity-n 12] [--ref-n 8]
 
 The same run checks the answer (parity_rel_l2: GPU vs the CPU oracle on the same problem at
 --parity-n, through the same solver path) and times the oracle on the host (cpu_baseline).
@@ -213,6 +213,8 @@ def run_reference(args, config):
               f"of every replica: numpy assembly + SuperLU Newton solve (restated reference path, "
               f"NOT dolfinx+PETSc, which is absent from this image)")
     cfg = dict(config)
+    cfg["parallelism"] = f"{cores} host cores, one replica of the sample each"
+    cfg.pop("l2", None)
     cfg["reference_sample"] = {"n": n, "dofs_per_replica": int(ndofs), "replicas": cores}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
@@ -740,7 +742,7 @@ def main():
     if args.parity_n is None:
         args.parity_n = 12 if args.workload == "c2" else 24
     if args.ref_n is None:
-        args.ref_n = 12 if args.workload == "c2" else 24
+        args.ref_n = 8 if args.workload == "c2" else 24
     config = {"workload": workload_name(args.workload, args.n), "n": args.n,
               "l2": "L2 flushed (512 MiB write) between timed steps; every streamed array is larger than L2"
               if args.workload == "c2" else "L2 flushed (512 MiB write) between timed steps",

@@ -282,10 +282,11 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   UP(S_DERIV_SPECIES, 0, deriv_species); UP(S_DERIV_PROG, 0, deriv_prog);
   UP(S_QUAD_V, 0, quad_v); UP(S_QUAD_S, 0, quad_s); UP(S_QUAD_BARY, 1, quad_bary); UP(S_QUAD_W, 1, quad_w);
   UP(S_ADV, 0, adv); UP(S_DIFF_UPROG, 0, diff_uprog);
-  S.n_rslots = S.n_factors = S.n_monos = 0;
+  S.n_rslots = S.n_factors = S.n_monos = S.n_fac_terms = 0;
   if (secs[S_STRUCT_INTS].id == S_STRUCT_INTS) {
     const int* si = (const int*)(blob + secs[S_STRUCT_INTS].offset);
     S.n_rslots = si[0]; S.n_factors = si[1]; S.n_monos = si[2];
+    S.n_fac_terms = (int)secs[S_FAC_COEF].count;
     UP(S_RSLOT_E, 1, rslot_E); UP(S_FAC_HDR, 0, fac_hdr); UP(S_FAC_A0, 1, fac_a0);
     UP(S_FAC_SPECIES, 0, fac_species); UP(S_FAC_COEF, 1, fac_coef);
     ctx->symmetric = false;

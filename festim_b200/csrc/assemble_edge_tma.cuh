@@ -25,7 +25,7 @@ struct AsmTmaArgs {
   int flags;
   int nst;
   // shared-memory layout (bytes)
-  int o_tab_i, o_scr, scr_bytes, o_stage0, stage_bytes, o_bar;
+  int o_tab_i, o_fac_d, o_fac_i, o_scr, scr_bytes, o_stage0, stage_bytes, o_bar;
   int s_tvw, s_tz, s_tzs, s_us, s_uns, s_load, s_lcol, s_vinfo, s_rowinfo, s_rowptr, s_tzptr, s_tzw;
   int tz_stride;   // doubles per tensor inside a stage
   int w_fv, w_adyn, w_res, w_tf, rts;   // offsets (doubles) inside a warp's scratch; row stride of the R tile
@@ -37,6 +37,9 @@ __host__ inline size_t fb_asm_tma_layout(const DevSpec& S, AsmTmaArgs& a, int ns
   size_t o = 0;
   o += up16((size_t)S.vx_dtab_n * 8);
   a.o_tab_i = (int)o; o += up16((size_t)S.vx_itab_n * 4);
+  // affine reaction factors: constant term and coefficients (doubles), then offset / count / species (ints)
+  a.o_fac_d = (int)o; o += up16((size_t)(S.n_factors + S.n_fac_terms + 1) * 8);
+  a.o_fac_i = (int)o; o += up16((size_t)(2 * S.n_factors + S.n_fac_terms + 1) * 4);
   int w = 0;
   a.w_fv = w; w += md * (S.n_factors > 0 ? S.n_factors : 1);
   a.w_adyn = w; w += md * (S.vx_ndp > 0 ? S.vx_ndp : 1);
@@ -82,6 +85,17 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
   int* itab = (int*)(fb_as_smem + a.o_tab_i);
   for (int t = threadIdx.x; t < S.vx_dtab_n; t += blockDim.x) dtab[t] = S.vx_dtab[t];
   for (int t = threadIdx.x; t < S.vx_itab_n; t += blockDim.x) itab[t] = S.vx_itab[t];
+  double* fac_d = (double*)(fb_as_smem + a.o_fac_d);   // [NF] constant terms, then the coefficients
+  int* fac_i = (int*)(fb_as_smem + a.o_fac_i);         // [NF][2] offset, count; then the species
+  for (int t = threadIdx.x; t < NF; t += blockDim.x) {
+    const int* h = S.fac_hdr + 4 * t;
+    fac_d[t] = h[0] ? S.scalars[h[1]] : S.fac_a0[t];
+    fac_i[2 * t] = h[2]; fac_i[2 * t + 1] = h[3];
+  }
+  for (int t = threadIdx.x; t < S.n_fac_terms; t += blockDim.x) {
+    fac_d[NF + t] = S.fac_coef[t];
+    fac_i[2 * NF + t] = S.fac_species[t];
+  }
   unsigned long long* full = (unsigned long long*)(fb_as_smem + a.o_bar);
   unsigned long long* empty = full + 8;
   if (threadIdx.x == 0)
@@ -205,10 +219,10 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
       kself = __reduce_max_sync(FULL, kself);
       for (int t = lane; t < deg * NF; t += 32) {
         const int k = fb_fastdiv((unsigned)t, S.vx_m_nf), f = t - k * NF;
-        const int* h = S.fac_hdr + 4 * f;
-        double val = h[0] ? S.scalars[h[1]] : S.fac_a0[f];
+        double val = fac_d[f];
         const double* uk = us + (size_t)lc[k] * ns;
-        for (int q = 0; q < h[3]; ++q) val += S.fac_coef[h[2] + q] * uk[S.fac_species[h[2] + q]];
+        const int q0 = fac_i[2 * f], q1 = q0 + fac_i[2 * f + 1];
+        for (int q = q0; q < q1; ++q) val += fac_d[NF + q] * uk[fac_i[2 * NF + q]];
         fv[t] = val;
       }
       __syncwarp();

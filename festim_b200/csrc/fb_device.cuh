@@ -62,7 +62,7 @@ struct DevSpec {
   const double* quad_w;
   const int* adv;             // [n_adv*2] tag, species
   // affine factors and rate energies of the structured reactions (lowering.py)
-  int n_rslots, n_factors, n_monos, maxdeg;
+  int n_rslots, n_factors, n_monos, maxdeg, n_fac_terms;
   const int* pair_row;        // [npairs] row species of every stored pair
   const double* rslot_E;      // [n_rslots] activation energies of the rate slots
   const int* fac_hdr;         // [n_factors*4] a0 kind (0 const, 1 scalar), scalar id, coef offset, count
