@@ -409,11 +409,10 @@ int fbi_halo(fb_ctx* ctx, double* x) {
   const XRank X = xrank_make(ctx, ctx->halo_seq++);
   const long long n_ghost_dofs = S.n_dofs - S.n_owned_dofs;
   const long long nsend = (long long)ctx->n_send * S.ns;
-  if (nsend > 0)
-    FB_LAUNCH(ctx, k_halo_push, (unsigned)((nsend + 255) / 256), 256, 0, X, S.ns, ctx->n_send, ctx->d_send_v, ctx->d_send_rank,
-              ctx->d_send_dst, ctx->halo_words, (const double*)x);
-  if (n_ghost_dofs > 0)
-    FB_LAUNCH(ctx, k_halo_pull, (unsigned)((n_ghost_dofs + 255) / 256), 256, 0, X, S.n_owned_dofs, n_ghost_dofs, ctx->halo_words, x);
+  const long long nthr = nsend > n_ghost_dofs ? nsend : n_ghost_dofs;
+  if (nthr > 0)
+    FB_LAUNCH(ctx, k_halo_exchange, (unsigned)((nthr + 255) / 256), 256, 0, X, S.ns, ctx->n_send, ctx->d_send_v,
+              ctx->d_send_rank, ctx->d_send_dst, S.n_owned_dofs, n_ghost_dofs, x);
   FB_CHECK(ctx, cudaGetLastError());
   return 0;
 }

@@ -109,6 +109,23 @@ __global__ void k_halo_push(XRank X, int ns, int n_send, const int* __restrict__
   unsigned long long* dst = X.base[send_rank[q]] + FB_XH + (((size_t)send_dst[q] * ns + s) * 2 + (X.seq & 1u)) * 2;
   ll_store(dst, X.seq, x[(long long)send_v[q] * ns + s]);
 }
+// both directions in one launch: the first n_send * ns threads push, every thread below
+// n_ghost_dofs pulls (a pull only waits for remote pushes, never for the local ones)
+__global__ void k_halo_exchange(XRank X, int ns, int n_send, const int* __restrict__ send_v,
+                                const int* __restrict__ send_rank, const int* __restrict__ send_dst,
+                                long long n_owned_dofs, long long n_ghost_dofs, double* __restrict__ x) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < (long long)n_send * ns) {
+    const int q = (int)(t / ns), s = (int)(t - (long long)q * ns);
+    unsigned long long* dst = X.base[send_rank[q]] + FB_XH + (((size_t)send_dst[q] * ns + s) * 2 + (X.seq & 1u)) * 2;
+    ll_store(dst, X.seq, x[(long long)send_v[q] * ns + s]);
+  }
+  if (t < n_ghost_dofs) {
+    double v = 0.0;
+    ll_load(X.base[X.rank] + FB_XH + ((size_t)t * 2 + (X.seq & 1u)) * 2, X.seq, X.bar, v);
+    x[n_owned_dofs + t] = v;
+  }
+}
 __global__ void k_halo_pull(XRank X, long long n_owned_dofs, long long n_ghost_dofs, long long halo_words,
                             double* __restrict__ x) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
