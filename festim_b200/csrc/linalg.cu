@@ -1972,7 +1972,7 @@ static int cheb_apply(fb_ctx* ctx, const double* v, double* z, double* w, double
 }
 
 static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y, double thr, int max_it,
-                       int* iters, bool want_cheb) {
+                       int* iters, bool want_cheb, bool use_guess) {
   const DevSpec& S = ctx->S;
   int rc = ensure_vectors(ctx, GM_NVEC);
   if (rc) return rc;
@@ -1988,11 +1988,13 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
   const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
   const unsigned gv = vec_grid(ctx, No);
   double* sc = ctx->d_sc;
-  FB_CHECK(ctx, cudaMemsetAsync(y, 0, sizeof(double) * N, ctx->stream));
+  // use_guess: y holds an initial guess (KSPSetInitialGuessNonzero), e.g. the Newton update of the
+  // previous time step; the stopping threshold is absolute, so a guess only saves iterations
+  if (!use_guess) FB_CHECK(ctx, cudaMemsetAsync(y, 0, sizeof(double) * N, ctx->stream));
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
   int total = 0;
   int fl[4] = {0, 0, 0, 0};
-  bool first = true;
+  bool first = !use_guess;
   const bool cheb_possible = want_cheb && !J && spmv_ch_tma_ok(ctx, V) && !ctx->cheb_refused;
   while (total < max_it) {
     // right-preconditioned with the Chebyshev polynomial p(B) of B = D^-1 J once its interval is
@@ -2163,7 +2165,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
         }
       }
     }
-    else status = solve_gmres(ctx, J, rhs, sol, thr_r, max_it, &its, want_cheb);
+    else status = solve_gmres(ctx, J, rhs, sol, thr_r, max_it, &its, want_cheb, round == 0 && ctx->use_guess);
     *iters += its;
     if (status < 0) return status;
     if (round > 0) FB_LAUNCH(ctx, k_axpy, vec_grid(ctx, S.n_owned_dofs), FB_TPB, 0, S.n_owned_dofs, 1.0, corr, y);

@@ -20,6 +20,12 @@ static int ensure_newton_buffers(fb_ctx* ctx) {
   return 0;
 }
 
+__global__ void k_axpy_n(long long n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+
 __global__ void k_sub(long long n, const double* __restrict__ y, double* __restrict__ u) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -72,6 +78,11 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
   double* Jv = chan ? nullptr : ctx->d_J;
   int it = 0, lin_total = 0, why = 0;
   double snorm = 0.0, f0 = 1.0, fn = 0.0;
+  const bool guess_ok = ctx->S.transient && ctx->S.inv_dt > 0.0 && ksp == FB_KSP_GMRES && !getenv("FB_NO_KSP_GUESS");
+  if (guess_ok && !ctx->d_yprev) {
+    if ((rc = fb_alloc(ctx, &ctx->d_yprev, (size_t)N))) return rc;
+    ctx->yprev_valid = false;
+  }
   // partitioned mesh: ghost entries of the fields come from their owners over peer memory
   if (u_n != u && (rc = fbi_halo(ctx, (double*)u_n))) return rc;
   while (true) {
@@ -99,7 +110,24 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
     double relres = 0.0;
     {
       PhaseTimer t(ctx, 2);
+      // transient runs: the first Newton update of a step is close to that of the previous step
+      // (scaled by the ratio of the time steps): start the Krylov solve from it
+      const bool guess = guess_ok && it == 0 && ctx->yprev_valid && ctx->yprev_dt > 0.0;
+      if (guess) {
+        const double sc = (1.0 / ctx->S.inv_dt) / ctx->yprev_dt;
+        FB_CHECK(ctx, cudaMemsetAsync(ctx->d_y, 0, sizeof(double) * N, ctx->stream));
+        long long g = (ctx->S.n_owned_dofs + 255) / 256;
+        if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+        FB_LAUNCH(ctx, k_axpy_n, (unsigned)g, 256, 0, ctx->S.n_owned_dofs, sc, ctx->d_yprev, ctx->d_y);
+      }
+      ctx->use_guess = guess;
       rc = fbi_linear_solve(ctx, Jv, ctx->d_F, ctx->d_y, ksp, pc, ksp_rtol, 0.0, ksp_max_it, &lin_its, &relres);
+      ctx->use_guess = false;
+      if (guess_ok && it == 0 && rc == 0) {
+        FB_CHECK(ctx, cudaMemcpyAsync(ctx->d_yprev, ctx->d_y, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->yprev_valid = true;
+        ctx->yprev_dt = 1.0 / ctx->S.inv_dt;
+      }
       t.stop();
     }
     lin_total += lin_its;
