@@ -227,7 +227,7 @@ int fbi_update_vinfo(fb_ctx* ctx) {
 int fbi_update_coeffs(fb_ctx* ctx) {
   ctx->cheb_valid = false;   // temperature / coefficients moved: re-estimate the spectrum interval
   ctx->cheb_refused = false;
-  ctx->yprev_valid = false;  // the initial guess of the Krylov solve comes from another problem
+  ctx->yprev_n = 0;          // the initial guess of the Krylov solve comes from another problem
   switch (ctx->S.tdim) {
     case 1: return update_coeffs_dim<1>(ctx);
     case 2: return update_coeffs_dim<2>(ctx);

@@ -76,8 +76,9 @@ struct fb_ctx {
   double* d_F = nullptr;
   double* d_J = nullptr;
   double* d_y = nullptr;
-  double* d_yprev = nullptr;   // first Newton update of the previous time step: initial guess of the next one
-  bool yprev_valid = false, use_guess = false;
+  double* d_yprev = nullptr;   // first Newton updates of the last three time steps (ring): initial guess of the next one
+  int yprev_n = 0, yprev_head = 0;
+  bool use_guess = false;
   double yprev_dt = 0.0;
   double* d_work = nullptr;  // Krylov vectors
   long long work_doubles = 0;

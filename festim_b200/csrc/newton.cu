@@ -80,8 +80,8 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
   double snorm = 0.0, f0 = 1.0, fn = 0.0;
   const bool guess_ok = ctx->S.transient && ctx->S.inv_dt > 0.0 && ksp == FB_KSP_GMRES && !getenv("FB_NO_KSP_GUESS");
   if (guess_ok && !ctx->d_yprev) {
-    if ((rc = fb_alloc(ctx, &ctx->d_yprev, (size_t)N))) return rc;
-    ctx->yprev_valid = false;
+    if ((rc = fb_alloc(ctx, &ctx->d_yprev, (size_t)3 * N))) return rc;
+    ctx->yprev_n = 0;
   }
   // partitioned mesh: ghost entries of the fields come from their owners over peer memory
   if (u_n != u && (rc = fbi_halo(ctx, (double*)u_n))) return rc;
@@ -112,21 +112,32 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
       PhaseTimer t(ctx, 2);
       // transient runs: the first Newton update of a step is close to that of the previous step
       // (scaled by the ratio of the time steps): start the Krylov solve from it
-      const bool guess = guess_ok && it == 0 && ctx->yprev_valid && ctx->yprev_dt > 0.0;
+      // (polynomial extrapolation through the last 1-3 updates while the time step is unchanged)
+      const double dt_now = 1.0 / ctx->S.inv_dt;
+      const bool guess = guess_ok && it == 0 && ctx->yprev_n > 0 && ctx->yprev_dt > 0.0;
       if (guess) {
-        const double sc = (1.0 / ctx->S.inv_dt) / ctx->yprev_dt;
+        const bool same_dt = std::fabs(dt_now - ctx->yprev_dt) <= 1e-12 * dt_now;
+        const int order = same_dt ? ctx->yprev_n : 1;
+        static const double w[3][3] = {{1.0, 0.0, 0.0}, {2.0, -1.0, 0.0}, {3.0, -3.0, 1.0}};
         FB_CHECK(ctx, cudaMemsetAsync(ctx->d_y, 0, sizeof(double) * N, ctx->stream));
         long long g = (ctx->S.n_owned_dofs + 255) / 256;
         if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
-        FB_LAUNCH(ctx, k_axpy_n, (unsigned)g, 256, 0, ctx->S.n_owned_dofs, sc, ctx->d_yprev, ctx->d_y);
+        for (int q = 0; q < order; ++q) {
+          const double wq = same_dt ? w[order - 1][q] : dt_now / ctx->yprev_dt;
+          FB_LAUNCH(ctx, k_axpy_n, (unsigned)g, 256, 0, ctx->S.n_owned_dofs, wq,
+                    ctx->d_yprev + (size_t)((ctx->yprev_head + 3 - q) % 3) * N, ctx->d_y);
+        }
       }
       ctx->use_guess = guess;
       rc = fbi_linear_solve(ctx, Jv, ctx->d_F, ctx->d_y, ksp, pc, ksp_rtol, 0.0, ksp_max_it, &lin_its, &relres);
       ctx->use_guess = false;
       if (guess_ok && it == 0 && rc == 0) {
-        FB_CHECK(ctx, cudaMemcpyAsync(ctx->d_yprev, ctx->d_y, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
-        ctx->yprev_valid = true;
-        ctx->yprev_dt = 1.0 / ctx->S.inv_dt;
+        if (ctx->yprev_n > 0 && std::fabs(dt_now - ctx->yprev_dt) > 1e-12 * dt_now) ctx->yprev_n = 0;   // new step size: restart the history
+        ctx->yprev_head = (ctx->yprev_head + 1) % 3;
+        FB_CHECK(ctx, cudaMemcpyAsync(ctx->d_yprev + (size_t)ctx->yprev_head * N, ctx->d_y, sizeof(double) * N,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+        if (ctx->yprev_n < 3) ctx->yprev_n++;
+        ctx->yprev_dt = dt_now;
       }
       t.stop();
     }
