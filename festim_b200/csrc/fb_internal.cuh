@@ -79,6 +79,7 @@ struct fb_ctx {
   double* d_yprev = nullptr;   // first Newton updates of the last three time steps (ring): initial guess of the next one
   int yprev_n = 0, yprev_head = 0;
   bool use_guess = false;
+  double guess_guard = 0.0;
   double yprev_dt = 0.0;
   double* d_work = nullptr;  // Krylov vectors
   long long work_doubles = 0;

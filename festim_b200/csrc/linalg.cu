@@ -9,6 +9,7 @@
 // iteration is two launches for CG and the host only polls a "done" flag.
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 
 #include "fb_internal.cuh"
 #include "reduce.cuh"
@@ -1461,9 +1462,11 @@ __global__ void k_residual(long long n, const double* __restrict__ b, const doub
     r[k] = b[k] - Ax[k];
 }
 
-__global__ void k_gmres_begin(double* sc, int* flags, double thr) {
+__global__ void k_gmres_begin(double* sc, int* flags, double thr, double guess_guard) {
   // sc[GM_MISC+0] holds ||r||^2 from the preceding reduction
   const double beta = sqrt(sc[GM_MISC + 0]);
+  // an initial guess that leaves a larger residual than the zero vector would is dropped (flags[4])
+  flags[4] = (guess_guard > 0.0 && beta > guess_guard) ? 1 : 0;
   sc[GM_MISC + 4] = beta;
   sc[GM_MISC + 1] = beta > 0.0 ? 1.0 / beta : 0.0;
   sc[GM_MISC + 3] = thr;
@@ -1994,7 +1997,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
   int total = 0;
   int fl[4] = {0, 0, 0, 0};
-  bool first = !use_guess;
+  bool first = !use_guess, guess_checked = false;
   const bool cheb_possible = want_cheb && !J && spmv_ch_tma_ok(ctx, V) && !ctx->cheb_refused;
   while (total < max_it) {
     // right-preconditioned with the Chebyshev polynomial p(B) of B = D^-1 J once its interval is
@@ -2011,7 +2014,20 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     }
     first = false;
     FB_LAUNCH(ctx, k_dot, gv, FB_TPB, 0, No, r, r, ctx->d_red, ctx->d_ticket, sc + GM_MISC, xr_next(ctx));
-    FB_LAUNCH(ctx, k_gmres_begin, 1, 1, 0, sc, ctx->d_flags, thr);
+    FB_LAUNCH(ctx, k_gmres_begin, 1, 1, 0, sc, ctx->d_flags, thr, (use_guess && total == 0 && !first) ? ctx->guess_guard : 0.0);
+    if (use_guess && total == 0 && !first && !guess_checked) {
+      guess_checked = true;
+      int f5[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      FB_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 24, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      memcpy(f5, ctx->h_pinned + 24, sizeof(f5));
+      if (f5[4]) {   // worse than starting from zero: do that
+        FB_CHECK(ctx, cudaMemsetAsync(y, 0, sizeof(double) * N, ctx->stream));
+        FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
+        first = true;
+        continue;
+      }
+    }
     FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, No, r, sc + GM_MISC + 1, V, (const int*)nullptr);
     const int poll = cheb ? 4 : 10;
     for (int j = 0; j < GM_M; ++j) {
@@ -2131,6 +2147,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   if ((rc = fbi_norm2(ctx, ctx->d_work, &pbnorm))) return rc;
   double thr = rtol * pbnorm;
   if (atol > thr) thr = atol;
+  ctx->guess_guard = pbnorm;   // the residual of the zero vector
   // Krylov solve + iterative refinement on the true residual: the Newton test is on
   // the unpreconditioned ||F||, so the true relative residual must also reach rtol
   // (the reference's LU solve leaves ~1e-15); each round solves J d = b - J y.
