@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "fb_internal.cuh"
+#include "spmv_channels.cuh"
 
 // spec section ids / int slots, shared with festim_b200/lowering.py
 enum {
@@ -318,6 +319,16 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     if (nch > 255 || np > 255) return fb_fail(ctx, "channel tables: too many channels / species pairs");
     S.vx_nft = ftp[ns]; S.vx_njt = jtp[np];
     ctx->n_sp_ent = (int)(secs[S_VX_SP].count / 2);
+    {
+      const SpmvEpPlan P = fb_spmv_ep_plan(ns, sec_i(S_VX_SP_PTR), sec_i(S_VX_SP), sec_d(S_VX_SP_COEF), sec_i(S_VX_SP_COMBO));
+      ctx->ep_epl = P.epl;
+      if (P.epl) {
+        int rc2;
+        if ((rc2 = fb_upload(ctx, &ctx->d_ep_coef, P.coef.data(), P.coef.size()))) return rc2;
+        if ((rc2 = fb_upload(ctx, &ctx->d_ep_pos, P.pos.data(), P.pos.size()))) return rc2;
+        if ((rc2 = fb_upload(ctx, &ctx->d_ep_lane, P.lane.data(), P.lane.size()))) return rc2;
+      }
+    }
     std::vector<int> itab;
     std::vector<double> dtab;
     S.vx_o_ch = (int)itab.size(); itab.insert(itab.end(), ch, ch + secs[S_VX_CH].count);

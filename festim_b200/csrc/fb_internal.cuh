@@ -52,6 +52,9 @@ struct fb_ctx {
   int n_programs = 0;                  // compiled expressions of the spec (fb_integrate checks its argument)
   bool symmetric = false;
   int n_sp_ent = 0;            // entries of the channel SpMV epilogue table (vx_sp)
+  // lane plan of the TMA channel SpMV's row epilogue (spmv_channels.cuh: fb_spmv_ep_plan); epl 0 = none
+  int ep_epl = 0;
+  const double* d_ep_coef = nullptr; const int* d_ep_pos = nullptr; const int* d_ep_lane = nullptr;
   bool op_channels = false;
   // Chebyshev polynomial preconditioner: interval of D^-1 J from Ritz values, operator applications
   bool cheb_valid = false, cheb_refused = false;

@@ -257,14 +257,14 @@ static int spmv_ch_launch(fb_ctx* ctx, const double* x, double* y, const int* fl
 // TMA-pipelined channel SpMV (spmv_channels.cuh): usable when every bulk copy is 16-byte aligned
 static bool spmv_ch_tma_ok(fb_ctx* ctx, const double* x) {
   const DevSpec& S = ctx->S;
-  return S.vx_on && (S.ns % 2 == 0) && (((uintptr_t)x & 15) == 0) && S.vx_nch <= 16 && S.ck_nx_max > 0 &&
-         !getenv("FB_NO_TMA_SPMV");
+  return S.vx_on && (S.ns % 2 == 0) && S.ns <= 16 && (((uintptr_t)x & 15) == 0) && S.vx_nch <= 16 && S.ck_nx_max > 0 &&
+         ctx->ep_epl > 0 && !getenv("FB_NO_TMA_SPMV");
 }
 
 template <int MODE>
 static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
   const DevSpec& S = ctx->S;
-  a.n_sp_ent = ctx->n_sp_ent;
+  a.ep_coef = ctx->d_ep_coef; a.ep_pos = ctx->d_ep_pos; a.ep_lane = ctx->d_ep_lane;
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
   // the ring must hold the chunks the consumer groups work on plus at least one in flight per group
@@ -279,16 +279,25 @@ static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
   if (grid > nchunks) grid = nchunks;
   if (grid < 1) grid = 1;
   const int mt = (S.vx_nch + 7) / 8, nt = (S.ns + 7) / 8;
-#define FB_SPMV_CASE(M, N)                                                                                   \
-  {                                                                                                          \
-    FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_spmv_ch_tma<M, N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem));                                                          \
-    k_spmv_ch_tma<M, N, MODE><<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, smem, ctx->stream>>>(S, a);                   \
+#define FB_SPMV_CASE_E(M, N, E)                                                                                 \
+  {                                                                                                             \
+    FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_spmv_ch_tma<M, N, MODE, E>,                               \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+    k_spmv_ch_tma<M, N, MODE, E><<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, smem, ctx->stream>>>(S, a); \
+  }
+  // the plan's entries per lane select the instantiation (registers)
+#define FB_SPMV_CASE(M, N)                                                                                      \
+  {                                                                                                             \
+    if (ctx->ep_epl == 2) FB_SPMV_CASE_E(M, N, 2)                                                               \
+    else if (ctx->ep_epl == 4) FB_SPMV_CASE_E(M, N, 4)                                                          \
+    else if (ctx->ep_epl == 6) FB_SPMV_CASE_E(M, N, 6)                                                          \
+    else FB_SPMV_CASE_E(M, N, 8)                                                                                \
   }
   if (mt == 1 && nt == 1) FB_SPMV_CASE(1, 1)
   else if (mt == 1) FB_SPMV_CASE(1, 2)
   else if (nt == 1) FB_SPMV_CASE(2, 1)
   else FB_SPMV_CASE(2, 2)
+#undef FB_SPMV_CASE_E
 #undef FB_SPMV_CASE
   ctx->launches++;
   FB_CHECK(ctx, cudaGetLastError());

@@ -25,6 +25,7 @@
 // rows copy x), so the operator equals the block-CSR matrix k_et_expand writes.
 #pragma once
 #include "fb_device.cuh"
+#include <vector>
 
 #ifndef FB_EMU
 __device__ __forceinline__ unsigned fb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -128,7 +129,84 @@ inline void fb_dmma(double& c0, double& c1, double a, double b) {
 }
 #endif
 
-#define FB_SP_EPL 6   // table entries per lane kept in registers (two lanes per row species)
+// Lane plan of the row epilogue y_s = sum_e coef_e T[combo_e]: the entries of row species s are dealt
+// to an aligned group of 1, 2, 4 or 8 lanes (at most EPL entries per lane, kept in registers for the
+// whole launch); the group's partial sums meet in xor shuffles and its first lane owns y_s.
+#define FB_SP_EPL_MAX 8
+struct SpmvEpPlan {
+  int epl = 0;                      // entries per lane (0: no plan - too many entries for 32 lanes)
+  std::vector<double> coef;         // [32 * epl]
+  std::vector<int> pos;             // [32 * epl]  tile position | inv_dt flag << 16
+  std::vector<int> lane;            // [32]  species | log2(group) << 8 | leader << 12   (species 0xff: idle lane)
+};
+// sp_ptr [ns+1], sp [n*2] (combo, flag), sp_coef [n], sp_combo [ncombo*2] (channel, column species)
+inline SpmvEpPlan fb_spmv_ep_plan(int ns, const int* sp_ptr, const int* sp, const double* sp_coef, const int* sp_combo) {
+  SpmvEpPlan P;
+  if (ns > 16) return P;
+  for (int epl = 2; epl <= FB_SP_EPL_MAX; epl += 2) {   // the kernel is instantiated for 2, 4, 6, 8
+    int lanes = 0;
+    std::vector<int> g(ns);
+    for (int s = 0; s < ns; ++s) {
+      const int n = sp_ptr[s + 1] - sp_ptr[s];
+      int need = (n + epl - 1) / epl, gs = 1;
+      if (need < 1) need = 1;
+      while (gs < need) gs *= 2;
+      g[s] = gs; lanes += gs;
+    }
+    if (lanes > 32) continue;
+    P.epl = epl;
+    P.coef.assign((size_t)32 * epl, 0.0); P.pos.assign((size_t)32 * epl, 0); P.lane.assign(32, 0xff);
+    // the product tile is stored fragment-major (DMMA accumulator (mt, nt) of lane l at double2 unit
+    // (mt NT + nt) 32 + l): position of T[c][cs] in doubles
+    const int NT = (ns + 7) / 8;
+    auto tpos = [&](int c, int cs) {
+      const int mt = c >> 3, r = c & 7, nt = cs >> 3, col = cs & 7;
+      return ((mt * NT + nt) * 32 + 4 * r + (col >> 1)) * 2 + (col & 1);
+    };
+    std::vector<std::vector<std::pair<double, int>>> ent(32);
+    int at = 0;
+    for (int gs = 8; gs >= 1; gs /= 2)   // larger groups first: every group starts at a multiple of its size
+      for (int s = 0; s < ns; ++s) {
+        if (g[s] != gs) continue;
+        int lg = 0;
+        while ((1 << lg) < gs) ++lg;
+        const int n = sp_ptr[s + 1] - sp_ptr[s];
+        for (int q = 0; q < gs; ++q) P.lane[at + q] = s | (lg << 8) | ((q == 0) << 12);
+        for (int t = 0; t < n; ++t) {   // dealt round-robin over the group's lanes
+          const int e = sp_ptr[s] + t, combo = sp[2 * e];
+          ent[at + t % gs].push_back({sp_coef[e], tpos(sp_combo[2 * combo], sp_combo[2 * combo + 1]) | ((sp[2 * e + 1] & 1) << 16)});
+        }
+        at += gs;
+      }
+    // order of a lane's entries: the 16 lanes of a half warp read 8-byte words in the same instruction,
+    // word w from bank pair w mod 16 - greedily pick, per instruction, entries of unused bank pairs
+    for (int u = 0; u < epl; ++u)
+      for (int h = 0; h < 2; ++h) {
+        int used[16] = {0};
+        for (int l = 16 * h; l < 16 * h + 16; ++l) {
+          auto& E = ent[l];
+          if (E.empty()) continue;
+          size_t best = 0;
+          for (size_t q = 1; q < E.size(); ++q)
+            if (used[(E[q].second & 0xffff) & 15] < used[(E[best].second & 0xffff) & 15]) best = q;
+          P.coef[(size_t)l * epl + u] = E[best].first;
+          P.pos[(size_t)l * epl + u] = E[best].second;
+          used[(E[best].second & 0xffff) & 15]++;
+          E.erase(E.begin() + best);
+        }
+        for (int l = 16 * h; l < 16 * h + 16; ++l) {   // idle slots (coefficient 0) read a word of the least used bank pair
+          if (P.coef[(size_t)l * epl + u] != 0.0 || P.pos[(size_t)l * epl + u] != 0) continue;
+          int w = 0;
+          for (int q = 1; q < 16; ++q)
+            if (used[q] < used[w]) w = q;
+          P.pos[(size_t)l * epl + u] = w;
+          used[w]++;
+        }
+      }
+    return P;
+  }
+  return P;
+}
 
 struct SpmvChArgs {
   const double* x;
@@ -143,8 +221,12 @@ struct SpmvChArgs {
   double* wout;
   double ca, cb;
   int last;
-  // shared-memory layout (bytes): block-shared tables, per-warp scratch, chunk results, stages
-  int n_sp_ent, nst;
+  // lane plan of the row epilogue (fb_spmv_ep_plan)
+  const double* ep_coef;
+  const int* ep_pos;
+  const int* ep_lane;
+  // shared-memory layout (bytes): per-warp scratch, stages
+  int nst, zslot;
   int o_part, part_bytes, o_ybuf, o_stage0, stage_bytes, o_bar;
   int s_dyn, s_xs, s_dinv, s_r, s_z, s_vin, s_lcol, s_vinfo, s_rowinfo, s_rowptr;   // offsets inside a stage
 };
@@ -154,15 +236,15 @@ __host__ inline size_t fb_spmv_ch_layout(const DevSpec& S, SpmvChArgs& a, int mo
   auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
   const int md = S.maxdeg, ns = S.ns, CH = FB_CHUNK;
   size_t o = 0;
-  o += up16((size_t)a.n_sp_ent * 8);                       // t_coef
-  o += up16((size_t)(ns + 1 + a.n_sp_ent) * 4);            // t_ptr, t_combo
   // per consumer warp: the (channel x species) product tile of its row, then the row's result
   a.o_part = (int)o; a.part_bytes = (int)up16((size_t)(256 + ns) * 8); o += (size_t)CH * FB_CHUNK_GROUPS * a.part_bytes;
   a.o_ybuf = 0;
   size_t s = 0;
   s += up16((size_t)CH * md * S.vx_nsp * 8);               // static channel values
   a.s_dyn = (int)s; s += up16((size_t)CH * md * S.vx_ndp * 8);
-  a.s_xs = (int)s; s += up16((size_t)(S.ck_nx_max + 2) * ns * 8);   // + tile padding read past the last vertex
+  // + a slot of zeros for the edges of the K padding (zslot) and the tile padding read past a vertex
+  a.zslot = S.ck_nx_max + 2;
+  a.s_xs = (int)s; s += up16((size_t)(S.ck_nx_max + 4) * ns * 8);
   a.s_dinv = (int)s; if (mode >= 1) s += up16((size_t)CH * ns * ns * 8);
   a.s_r = (int)s; if (mode == 2) s += up16((size_t)CH * ns * 8);
   a.s_z = (int)s; if (mode == 2) s += up16((size_t)CH * ns * 8);
@@ -178,44 +260,34 @@ __host__ inline size_t fb_spmv_ch_layout(const DevSpec& S, SpmvChArgs& a, int mo
   return o;
 }
 
-template <int MT, int NT, int MODE>
+template <int MT, int NT, int MODE, int EPL>
 __global__ void __launch_bounds__(32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, 1)
 k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
   extern __shared__ __align__(16) unsigned char fb_sp_smem[];
   if (a.flags && a.flags[0]) return;
   constexpr int CH = FB_CHUNK;
+  constexpr int NG = FB_CHUNK_GROUPS;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ns = S.ns, NSP = S.vx_nsp, NDP = S.vx_ndp, NST = a.nst;
-  // ---- block-shared epilogue tables: sp_coef (inv_dt folded), sp_ptr, positions in the product tile
-  double* t_coef = (double*)fb_sp_smem;
-  int* t_ptr = (int*)(fb_sp_smem + (((size_t)a.n_sp_ent * 8 + 15) & ~(size_t)15));
-  int* t_combo = t_ptr + ns + 1;
-  for (int t = threadIdx.x; t < a.n_sp_ent; t += blockDim.x) {
-    t_coef[t] = S.vx_sp_coef[t] * ((S.vx_sp[2 * t + 1] & 1) ? S.inv_dt : 1.0);
-    const int combo = S.vx_sp[2 * t];   // (channel, column species) -> position in the row's product tile
-    t_combo[t] = S.vx_sp_combo[2 * combo] * (8 * NT) + S.vx_sp_combo[2 * combo + 1];
-  }
-  for (int t = threadIdx.x; t <= ns; t += blockDim.x) t_ptr[t] = S.vx_sp_ptr[t];
   unsigned long long* full = (unsigned long long*)(fb_sp_smem + a.o_bar);
   unsigned long long* empty = full + 8;
   if (threadIdx.x == 0)
     for (int q = 0; q < NST; ++q) { fb_mbar_init(&full[q], 1); fb_mbar_init(&empty[q], CH); }
-  // tile padding of the DMMA operands is read from the stages: it must be finite
+  // tile padding of the DMMA operands and the zero slot are read from the stages: they must be finite / zero
   for (size_t t = threadIdx.x; t < (size_t)NST * a.stage_bytes / 16; t += blockDim.x)
     ((double2*)(fb_sp_smem + a.o_stage0))[t] = make_double2(0.0, 0.0);
   fb_fence_proxy_async();
   fb_mbar_fence_init();
   __syncthreads();
-  const long long nchunks = (S.n_owned + CH - 1) / CH;
-  const long long nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nchunks = (int)((S.n_owned + CH - 1) / CH);
+  const int nmine = (int)blockIdx.x < nchunks ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  constexpr int NG = FB_CHUNK_GROUPS;
   if (warp == CH * NG) {
     // ================= producer warp: every operand of a chunk through the TMA unit ==================
     // descriptors of chunk i+1 are fetched while the copies of chunk i are issued
-    int pf_e0, pf_ne, pf_nx, pf_lc, pf_q0 = 0, pf_q1 = 0, pf_run[3];
-    auto prefetch = [&](long long i) {
+    int pf_e0 = 0, pf_ne = 0, pf_nx = 0, pf_lc = 0, pf_q0 = 0, pf_q1 = 0, pf_run[3] = {0, 0, 0};
+    auto prefetch = [&](int i) {
       if (i >= nmine) return;
       const long long c = blockIdx.x + i * (long long)gridDim.x;
       const long long c0 = c * CH;
@@ -226,9 +298,10 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
       if (S.ck_rmax > 32) { pf_q0 = S.ck_runptr[c]; pf_q1 = S.ck_runptr[c + 1]; }
     };
     prefetch(0);
-    for (long long i = 0; i < nmine; ++i) {
-      const int sidx = (int)(i % NST);
-      if (i >= NST) fb_mbar_wait(&empty[sidx], (unsigned)(((i / NST) - 1) & 1));   // all rows of its last chunk done
+    int sidx = 0;
+    unsigned eph = 1;   // parity of the stage's previous use: the first NST waits pass at once
+    for (int i = 0; i < nmine; ++i) {
+      fb_mbar_wait(&empty[sidx], eph);   // all rows of the stage's last chunk done
       const long long c = blockIdx.x + i * (long long)gridDim.x;
       const long long c0 = c * CH;
       const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
@@ -265,6 +338,7 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
         const int v0 = S.ck_runs[3 * q], len = S.ck_runs[3 * q + 1], lo = S.ck_runs[3 * q + 2];
         fb_bulk_g2s(st + a.s_xs + (size_t)lo * ns * 8, a.x + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
       }
+      if (++sidx == NST) { sidx = 0; eph ^= 1u; }
     }
     return;
   }
@@ -273,153 +347,183 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
   // its warp j multiplies row j of each of them ======================================================
   double* part = (double*)(fb_sp_smem + a.o_part + (size_t)warp * a.part_bytes);
   double* yrow = part + 256;
-  const int grp = warp / CH, wrow = warp - grp * CH;
+  const int grp = warp / CH, j = warp - grp * CH;
   // DMMA fragments of this lane: channels 8 mt + (lane >> 2) (A operand), column species
   // 8 nt + (lane >> 2) (B operand); channel values of an edge are strided by nsp / ndp
   const int nch = S.vx_nch;
-  int aoff[MT], astr[MT];
+  const int bcol = lane >> 2, kq = lane & 3;
+  int aoff[MT], astr[MT];   // byte offset of (edge 2 kq, this lane's channel) in the row's values; bytes per edge
   bool adyn[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int ch = 8 * mt + (lane >> 2);
     adyn[mt] = ch >= S.vx_nstat && ch < nch;   // padding channels read the static block (values unused)
-    aoff[mt] = adyn[mt] ? ch - S.vx_nstat : (ch < nch ? ch : 0);
-    astr[mt] = adyn[mt] ? NDP : NSP;
+    const int str = adyn[mt] ? NDP : NSP;
+    aoff[mt] = ((adyn[mt] ? ch - S.vx_nstat : (ch < nch ? ch : 0)) + 2 * kq * str) * 8 + (adyn[mt] ? a.s_dyn : 0);
+    astr[mt] = str * 8;
   }
-  const int bcol = lane >> 2, kq = lane & 3;
-  // the table entries of row species s are added by lanes s and s + 16
-  const int srow = lane & 15;
-  int e_lo = 0, e_hi = 0;
-  if (srow < ns) {
-    const int p0 = t_ptr[srow], p1 = t_ptr[srow + 1], mid = (p0 + p1 + 1) >> 1;
-    e_lo = lane < 16 ? p0 : mid; e_hi = lane < 16 ? mid : p1;
+  // epilogue plan of this lane, in registers for the whole launch
+  double ecoef[EPL];
+  int epos[EPL];
+#pragma unroll
+  for (int u = 0; u < EPL; ++u) {
+    const int w = a.ep_pos[lane * EPL + u];
+    ecoef[u] = a.ep_coef[lane * EPL + u] * (((w >> 16) & 1) ? S.inv_dt : 1.0);
+    epos[u] = (w & 0xffff) * 8;
   }
+  const int linfo = a.ep_lane[lane];
+  const int esp = linfo & 0xff, elg = (linfo >> 8) & 0xf;
+  const bool eleader = ((linfo >> 12) & 1) && esp < ns;
+  // D^-1 y: lane (s, h) = (lane >> 1, lane & 1) adds half of the double2 pairs of row s (rows of
+  // 96 bytes: the eight lanes of a quarter warp then read eight different groups of four banks)
+  const int np2 = ns >> 1, hp = (np2 + 1) >> 1;
+  const int dq0 = (lane & 1) ? hp : 0, dq1 = (lane & 1) ? np2 : hp;
+  const int srow = lane >> 1;
+  const bool sown = !(lane & 1) && srow < ns;   // the lane that finishes dof s of the row
+  const int zoff = a.zslot * ns;
 
-  for (long long i = grp; i < nmine; i += NG) {
-    const int sidx = (int)(i % NST);
-    const long long c = blockIdx.x + i * (long long)gridDim.x;
-    const long long c0 = c * CH;
-    const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
+  int sidx = grp % NST;
+  unsigned fph = (unsigned)((grp / NST) & 1);
+  long long c0 = ((long long)blockIdx.x + (long long)grp * gridDim.x) * CH;
+  const long long cstep = (long long)NG * gridDim.x * CH;
+  long long dof = (c0 + j) * ns;   // first dof of this warp's row
+  const long long dofstep = cstep * ns;
+  for (int i = grp; i < nmine; i += NG, c0 += cstep, dof += dofstep) {
+    const int nrow = (int)blockIdx.x + i * (int)gridDim.x == nchunks - 1
+                         ? (int)(S.n_owned - (long long)(nchunks - 1) * CH) : CH;   // only the last chunk is short
     unsigned char* st = fb_sp_smem + a.o_stage0 + (size_t)sidx * a.stage_bytes;
-    fb_mbar_wait(&full[sidx], (unsigned)((i / NST) & 1));
-    if (wrow < nrow) {
-      const int j = wrow;
-      const double* stat_s = (const double*)st;
-      const double* dyn_s = (const double*)(st + a.s_dyn);
+    fb_mbar_wait(&full[sidx], fph);
+    if (j < nrow) {
       const double* xs = (const double*)(st + a.s_xs);
-      const unsigned short* lcol_s = (const unsigned short*)(st + a.s_lcol);
       const int* rowptr_s = (const int*)(st + a.s_rowptr);
-      const int e0 = rowptr_s[0];
-      const int rp0 = rowptr_s[j] - e0, deg = rowptr_s[j + 1] - rowptr_s[j];
+      const int rpj = rowptr_s[j], rpj1 = rowptr_s[j + 1], e0 = rowptr_s[0];
       const unsigned vi = ((const unsigned*)(st + a.s_vinfo))[j];
       const int lself = (int)((const unsigned*)(st + a.s_rowinfo))[j];
+      const int rp0 = rpj - e0, deg = rpj1 - rpj;
       const unsigned rowbc = vi & 0xffffu;
       const bool colbc = (vi >> 16) & 1u;
-      const double* sr = stat_s + (size_t)rp0 * NSP;
-      const double* dr = dyn_s + (size_t)rp0 * NDP;
-      const unsigned short* lc = lcol_s + rp0;
-      // T[c][cs] = sum_k A^c[k] x[k][cs] on the fp64 tensor cores: K = edges in steps of 4
+      const unsigned short* lc = (const unsigned short*)(st + a.s_lcol) + rp0;
+      // T[c][cs] = sum_k A^c[k] x[k][cs] on the fp64 tensor cores: a K step takes the edges
+      // kb + {0, 2, 4, 6} + u (with six channel values per edge their rows are 96 bytes apart: the
+      // four 32-byte segments a half warp reads fall into four different groups of eight banks)
       double acc[MT][NT][2];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-      const double* ap[MT];
+      const unsigned char* ap[MT];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) ap[mt] = (adyn[mt] ? dr : sr) + aoff[mt];
-      // Edges beyond the row (k >= deg) are cancelled through the B operand alone: the A operand
-      // then reads finite values of the next row.  Channels >= nch and species >= ns are tile
-      // padding: their products land in entries of T no table refers to.
-      const double* xb = xs + 8 * 0 + bcol;
-      for (int kb = 0; kb < deg; kb += 16) {
-        // all operand loads of four K steps first, then the sixteen DMMAs
-        double av[4][MT], bv[4][NT];
+      for (int mt = 0; mt < MT; ++mt) ap[mt] = st + aoff[mt] + rp0 * astr[mt];
+      // Edges beyond the row (k >= deg) multiply the zero slot of xs: the A operand then reads finite
+      // values of the next row.  Channels >= nch and species >= ns are tile padding: their products
+      // land in entries of T no table refers to.
+      const double* xb = xs + bcol;
+      for (int kb = 0; kb < deg; kb += 8) {
+        // the operand loads of two K steps (8 edges) first, then their DMMAs
+        double av[2][MT], bv[2][NT];
         if (!colbc) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k = kb + 4 * u + kq;
-            const bool val = k < deg;
-            const double* xk = xb + (size_t)lc[val ? k : 0] * ns;
+          for (int u = 0; u < 2; ++u) {
+            const int k = kb + 2 * kq + u;
+            const int lk = lc[k];
+            const double* xk = xb + (k < deg ? lk * ns : zoff);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) av[u][mt] = ap[mt][k * astr[mt]];
+            for (int mt = 0; mt < MT; ++mt) av[u][mt] = *(const double*)(ap[mt] + u * astr[mt]);
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) { const double xv = xk[8 * nt]; bv[u][nt] = val ? xv : 0.0; }
+            for (int nt = 0; nt < NT; ++nt) bv[u][nt] = xk[8 * nt];
           }
         } else {   // eliminated (Dirichlet) columns read as zero
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k = kb + 4 * u + kq;
+          for (int u = 0; u < 2; ++u) {
+            const int k = kb + 2 * kq + u;
             const bool val = k < deg;
-            const unsigned msk = val ? S.vinfo[S.colidx[e0 + rp0 + k]] : 0u;
-            const double* xk = xb + (size_t)lc[val ? k : 0] * ns;
+            const unsigned msk = val ? S.vinfo[S.colidx[rpj + k]] : 0u;
+            const double* xk = xb + (val ? lc[k] * ns : zoff);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) av[u][mt] = ap[mt][k * astr[mt]];
+            for (int mt = 0; mt < MT; ++mt) av[u][mt] = *(const double*)(ap[mt] + u * astr[mt]);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
               const double xv = xk[8 * nt];
-              bv[u][nt] = (val && !((msk >> (8 * nt + bcol)) & 1u)) ? xv : 0.0;
+              bv[u][nt] = ((msk >> (8 * nt + bcol)) & 1u) ? 0.0 : xv;
             }
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int mt = 0; mt < MT; ++mt) ap[mt] += 8 * astr[mt];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) fb_dmma(acc[mt][nt][0], acc[mt][nt][1], av[u][mt], bv[u][nt]);
+      }
+      // vectors of the fused epilogue: issued ahead of the tile store (no later load can pass it)
+      const int t = j * ns + srow;
+      double xself = 0.0, rr = 0.0, zz = 0.0, vv = 0.0;
+      if (sown) {
+        xself = xs[lself * ns + srow];
+        if (MODE == 2) {
+          rr = ((const double*)(st + a.s_r))[t];
+          if (a.last) vv = ((const double*)(st + a.s_vin))[t];
+          else zz = ((const double*)(st + a.s_z))[t];
+        }
       }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           double2 v2; v2.x = acc[mt][nt][0]; v2.y = acc[mt][nt][1];
-          *(double2*)(part + (8 * mt + (lane >> 2)) * (8 * NT) + 8 * nt + 2 * (lane & 3)) = v2;
+          *(double2*)(part + ((mt * NT + nt) * 32 + lane) * 2) = v2;   // fragment-major: no bank conflicts
         }
       __syncwarp();
-      // y_s = sum_e coef_e T[combo_e]: two lanes per row species, one shuffle
-      // (all table loads are independent of the products: issued ahead of the DMMA results)
+      // y_s = sum_e coef_e T[combo_e]: the lanes of a species' group add their entries, xor shuffles
+      // join them (lanes of smaller groups ignore what they receive)
       double sum = 0.0, sum2 = 0.0;
 #pragma unroll
-      for (int u = 0; u < FB_SP_EPL; u += 2) {
-        const int ea = e_lo + u, eb = e_lo + u + 1;
-        const double ca = ea < e_hi ? t_coef[ea] : 0.0, cb = eb < e_hi ? t_coef[eb] : 0.0;
-        sum += ca * part[ea < e_hi ? t_combo[ea] : 0];
-        sum2 += cb * part[eb < e_hi ? t_combo[eb] : 0];
+      for (int u = 0; u < EPL; u += 2) {
+        sum += ecoef[u] * *(const double*)((const unsigned char*)part + epos[u]);
+        if (u + 1 < EPL) sum2 += ecoef[u + 1] * *(const double*)((const unsigned char*)part + epos[u + 1]);
       }
-      for (int e = e_lo + FB_SP_EPL; e < e_hi; ++e) sum += t_coef[e] * part[t_combo[e]];
       sum += sum2;
-      sum += __shfl_xor_sync(FULL, sum, 16);
-      const long long dof = (c0 + j) * ns + lane;
-      if (lane < ns) {
-        if ((rowbc >> lane) & 1u) sum = xs[(size_t)lself * ns + lane];
-        if (MODE == 0) a.y[dof] = sum;
-        else yrow[lane] = sum;
+      {
+        double o1 = __shfl_xor_sync(FULL, sum, 1);
+        if (elg >= 1) sum += o1;
+        o1 = __shfl_xor_sync(FULL, sum, 2);
+        if (elg >= 2) sum += o1;
+        o1 = __shfl_xor_sync(FULL, sum, 4);
+        if (elg >= 3) sum += o1;
+      }
+      if (eleader) {
+        if ((rowbc >> esp) & 1u) sum = xs[lself * ns + esp];   // identity row of a Dirichlet dof
+        if (MODE == 0) a.y[dof + esp] = sum;
+        else yrow[esp] = sum;
       }
       if (MODE >= 1) {
         __syncwarp();
-        if (lane < ns) {
-          double p;
-          const int t = j * ns + lane;
-          if (ns == 1) p = ((const double*)(st + a.s_dinv))[t] * yrow[0];
-          else {
-            const double2* dv = (const double2*)(st + a.s_dinv) + (size_t)t * (ns / 2);   // row s of the inverse block
-            double pa = 0.0, pb = 0.0;
-            for (int c2 = 0; c2 < ns; c2 += 2) {   // ns is even (16-byte rows)
-              const double2 d2 = dv[c2 >> 1];
-              pa += d2.x * yrow[c2];
-              pb += d2.y * yrow[c2 + 1];
+        double pa = 0.0, pb = 0.0;
+        if (srow < ns) {
+          const double2* dv = (const double2*)(st + a.s_dinv) + (size_t)(j * ns + srow) * np2;   // row s of the inverse block
+          const double2* y2 = (const double2*)yrow;
+#pragma unroll
+          for (int q = 0; q < 2 * NT; ++q)
+            if (dq0 + q < dq1) {
+              const double2 d2 = dv[dq0 + q], yv = y2[dq0 + q];
+              pa += d2.x * yv.x;
+              pb += d2.y * yv.y;
             }
-            p = pa + pb;
-          }
-          if (MODE == 1) a.y[dof] = p;
+        }
+        double p = pa + pb;
+        p += __shfl_xor_sync(FULL, p, 1);
+        if (sown) {
+          if (MODE == 1) a.y[dof + srow] = p;
           else {
-            const double rn = ((const double*)(st + a.s_r))[t] - p;
-            if (a.last) a.wout[dof] = ((const double*)(st + a.s_vin))[t] - rn;
+            const double rn = rr - p;
+            if (a.last) a.wout[dof + srow] = vv - rn;
             else {
-              const double dn = a.ca * xs[(size_t)lself * ns + lane] + a.cb * rn;
-              a.r[dof] = rn;
-              a.dout[dof] = dn;
-              a.z[dof] = ((const double*)(st + a.s_z))[t] + dn;
+              const double dn = a.ca * xself + a.cb * rn;
+              a.r[dof + srow] = rn;
+              a.dout[dof + srow] = dn;
+              a.z[dof + srow] = zz + dn;
             }
           }
         }
@@ -427,5 +531,7 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
     }
     __syncwarp();
     if (lane == 0) fb_mbar_arrive(&empty[sidx]);   // this warp is done with the stage
+    sidx += NG;
+    if (sidx >= NST) { sidx -= NST; fph ^= 1u; }
   }
 }
