@@ -283,7 +283,7 @@ static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
   {                                                                                                             \
     FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_spmv_ch_tma<M, N, MODE, E>,                               \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-    k_spmv_ch_tma<M, N, MODE, E><<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, smem, ctx->stream>>>(S, a); \
+    k_spmv_ch_tma<M, N, MODE, E><<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 64, smem, ctx->stream>>>(S, a); \
   }
   // the plan's entries per lane select the instantiation (registers)
 #define FB_SPMV_CASE(M, N)                                                                                      \

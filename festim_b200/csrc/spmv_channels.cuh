@@ -261,7 +261,7 @@ __host__ inline size_t fb_spmv_ch_layout(const DevSpec& S, SpmvChArgs& a, int mo
 }
 
 template <int MT, int NT, int MODE, int EPL>
-__global__ void __launch_bounds__(32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, 1)
+__global__ void __launch_bounds__(32 * FB_CHUNK * FB_CHUNK_GROUPS + 64, 1)
 k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
   extern __shared__ __align__(16) unsigned char fb_sp_smem[];
   if (a.flags && a.flags[0]) return;
@@ -273,7 +273,7 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
   unsigned long long* full = (unsigned long long*)(fb_sp_smem + a.o_bar);
   unsigned long long* empty = full + 8;
   if (threadIdx.x == 0)
-    for (int q = 0; q < NST; ++q) { fb_mbar_init(&full[q], 1); fb_mbar_init(&empty[q], CH); }
+    for (int q = 0; q < NST; ++q) { fb_mbar_init(&full[q], 2); fb_mbar_init(&empty[q], CH); }   // full: one arrival per producer warp
   // tile padding of the DMMA operands and the zero slot are read from the stages: they must be finite / zero
   for (size_t t = threadIdx.x; t < (size_t)NST * a.stage_bytes / 16; t += blockDim.x)
     ((double2*)(fb_sp_smem + a.o_stage0))[t] = make_double2(0.0, 0.0);
@@ -283,19 +283,25 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
   const int nchunks = (int)((S.n_owned + CH - 1) / CH);
   const int nmine = (int)blockIdx.x < nchunks ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp == CH * NG) {
-    // ================= producer warp: every operand of a chunk through the TMA unit ==================
-    // descriptors of chunk i+1 are fetched while the copies of chunk i are issued
+  if (warp >= CH * NG) {
+    // ================= two producer warps: every operand of a chunk through the TMA unit ==============
+    // (a single warp issuing all ~22 copies of a chunk was the slowest warp of the block: warp 0 takes the
+    // row data, warp 1 the runs of x).  Descriptors of chunk i+1 are fetched while the copies of chunk i are issued.
+    const bool px = warp > CH * NG;
     int pf_e0 = 0, pf_ne = 0, pf_nx = 0, pf_lc = 0, pf_q0 = 0, pf_q1 = 0, pf_run[3] = {0, 0, 0};
     auto prefetch = [&](int i) {
       if (i >= nmine) return;
       const long long c = blockIdx.x + i * (long long)gridDim.x;
       const long long c0 = c * CH;
-      const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
-      pf_e0 = S.rowptr[c0]; pf_ne = S.rowptr[c0 + nrow]; pf_nx = S.ck_nx[c]; pf_lc = S.ck_lcolptr[c];
-      const int* rr = S.ck_slots + ((size_t)c * 32 + lane) * 3;
-      pf_run[0] = rr[0]; pf_run[1] = rr[1]; pf_run[2] = rr[2];
-      if (S.ck_rmax > 32) { pf_q0 = S.ck_runptr[c]; pf_q1 = S.ck_runptr[c + 1]; }
+      if (!px) {
+        const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
+        pf_e0 = S.rowptr[c0]; pf_ne = S.rowptr[c0 + nrow]; pf_lc = S.ck_lcolptr[c];
+      } else {
+        pf_nx = S.ck_nx[c];
+        const int* rr = S.ck_slots + ((size_t)c * 32 + lane) * 3;
+        pf_run[0] = rr[0]; pf_run[1] = rr[1]; pf_run[2] = rr[2];
+        if (S.ck_rmax > 32) { pf_q0 = S.ck_runptr[c]; pf_q1 = S.ck_runptr[c + 1]; }
+      }
     };
     prefetch(0);
     int sidx = 0;
@@ -310,33 +316,38 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
       const int e0 = pf_e0, ne = pf_ne - pf_e0, nx = pf_nx, lc0 = pf_lc, q0 = pf_q0, q1 = pf_q1;
       const int r0v = pf_run[0], r1v = pf_run[1], r2v = pf_run[2];
       prefetch(i + 1);
-      const int nlc = (ne + 7) & ~7;
-      if (lane == 0) {
-        unsigned bytes = (unsigned)(ne * (NSP + NDP) * 8 + nx * ns * 8 + nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
-        if (MODE >= 1) bytes += (unsigned)(nrow * ns * ns * 8);
-        if (MODE == 2) bytes += (unsigned)((a.last ? 3 : 2) * nrow * ns * 8);
-        fb_mbar_expect_tx(b, bytes);
-      }
-      __syncwarp();
-      if (lane == 0 && NSP) fb_bulk_g2s(st, S.et_stat + (long long)e0 * NSP, (unsigned)(ne * NSP * 8), b);
-      if (lane == 1 && NDP) fb_bulk_g2s(st + a.s_dyn, S.et_dyn + (long long)e0 * NDP, (unsigned)(ne * NDP * 8), b);
-      if (lane == 2) fb_bulk_g2s(st + a.s_lcol, S.ck_lcol + lc0, (unsigned)(nlc * 2), b);
-      if (lane == 3) fb_bulk_g2s(st + a.s_vinfo, S.vinfo + c0, (unsigned)(CH * 4), b);
-      if (lane == 4) fb_bulk_g2s(st + a.s_rowinfo, S.ck_rowinfo + c0, (unsigned)(CH * 4), b);
-      if (lane == 9) fb_bulk_g2s(st + a.s_rowptr, S.rowptr + c0, (unsigned)((CH + 4) * 4), b);
-      if (MODE >= 1 && lane == 5)
-        fb_bulk_g2s(st + a.s_dinv, a.dinv + c0 * ns * ns, (unsigned)(nrow * ns * ns * 8), b);
-      if (MODE == 2) {
-        if (lane == 6) fb_bulk_g2s(st + a.s_r, a.r + c0 * ns, (unsigned)(nrow * ns * 8), b);
-        if (lane == 7) fb_bulk_g2s(st + a.s_z, a.z + c0 * ns, (unsigned)(nrow * ns * 8), b);
-        if (lane == 8 && a.last) fb_bulk_g2s(st + a.s_vin, a.vin + c0 * ns, (unsigned)(nrow * ns * 8), b);
-      }
-      // x at the chunk's distinct neighbours, one copy per run of vertex ids
-      if (r1v > 0)
-        fb_bulk_g2s(st + a.s_xs + (size_t)r2v * ns * 8, a.x + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
-      for (int q = q0 + 32 + lane; q < q1; q += 32) {
-        const int v0 = S.ck_runs[3 * q], len = S.ck_runs[3 * q + 1], lo = S.ck_runs[3 * q + 2];
-        fb_bulk_g2s(st + a.s_xs + (size_t)lo * ns * 8, a.x + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
+      if (!px) {
+        const int nlc = (ne + 7) & ~7;
+        if (lane == 0) {
+          unsigned bytes = (unsigned)(ne * (NSP + NDP) * 8 + nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
+          if (MODE >= 1) bytes += (unsigned)(nrow * ns * ns * 8);
+          if (MODE == 2) bytes += (unsigned)((a.last ? 3 : 2) * nrow * ns * 8);
+          fb_mbar_expect_tx(b, bytes);
+        }
+        __syncwarp();
+        if (lane == 0 && NSP) fb_bulk_g2s(st, S.et_stat + (long long)e0 * NSP, (unsigned)(ne * NSP * 8), b);
+        if (lane == 1 && NDP) fb_bulk_g2s(st + a.s_dyn, S.et_dyn + (long long)e0 * NDP, (unsigned)(ne * NDP * 8), b);
+        if (lane == 2) fb_bulk_g2s(st + a.s_lcol, S.ck_lcol + lc0, (unsigned)(nlc * 2), b);
+        if (lane == 3) fb_bulk_g2s(st + a.s_vinfo, S.vinfo + c0, (unsigned)(CH * 4), b);
+        if (lane == 4) fb_bulk_g2s(st + a.s_rowinfo, S.ck_rowinfo + c0, (unsigned)(CH * 4), b);
+        if (lane == 9) fb_bulk_g2s(st + a.s_rowptr, S.rowptr + c0, (unsigned)((CH + 4) * 4), b);
+        if (MODE >= 1 && lane == 5)
+          fb_bulk_g2s(st + a.s_dinv, a.dinv + c0 * ns * ns, (unsigned)(nrow * ns * ns * 8), b);
+        if (MODE == 2) {
+          if (lane == 6) fb_bulk_g2s(st + a.s_r, a.r + c0 * ns, (unsigned)(nrow * ns * 8), b);
+          if (lane == 7) fb_bulk_g2s(st + a.s_z, a.z + c0 * ns, (unsigned)(nrow * ns * 8), b);
+          if (lane == 8 && a.last) fb_bulk_g2s(st + a.s_vin, a.vin + c0 * ns, (unsigned)(nrow * ns * 8), b);
+        }
+      } else {
+        // x at the chunk's distinct neighbours, one copy per run of vertex ids
+        if (lane == 0) fb_mbar_expect_tx(b, (unsigned)(nx * ns * 8));
+        __syncwarp();
+        if (r1v > 0)
+          fb_bulk_g2s(st + a.s_xs + (size_t)r2v * ns * 8, a.x + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
+        for (int q = q0 + 32 + lane; q < q1; q += 32) {
+          const int v0 = S.ck_runs[3 * q], len = S.ck_runs[3 * q + 1], lo = S.ck_runs[3 * q + 2];
+          fb_bulk_g2s(st + a.s_xs + (size_t)lo * ns * 8, a.x + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
+        }
       }
       if (++sidx == NST) { sidx = 0; eph ^= 1u; }
     }
