@@ -405,21 +405,37 @@ def run_single(args, config):
         B_asm_bsr = (mesh.num_cells * (4 * (d + 1) + 4) + mesh.num_vertices * (8 * d + 8 * spec.T_mode + 16 * spec.ns)
                      + 8 * spec.npairs * nnzb + 8 * N)
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r2_ncu_spmv_channels.json")
+        prof = os.path.join(ROOT, "profiles", "r2_ncu_spmv_cheb_step.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         ach = B_spmv / (spmv_ms * 1e-3) / 1e9
+        # the launch the time step is made of: one step of the Chebyshev recurrence (same kernel, MODE 2) -
+        # operator, block-Jacobi inverse blocks (4-byte mantissas + row scales) and the three vectors of the
+        # recurrence in one pass
+        ctx._check(lib.fb_bjacobi_setup(ctx.h, None))
+        cr, cz, cd = ctx.zeros(N), ctx.zeros(N), ctx.zeros(N)
+        bufs = [x, cd]
+
+        def cheb_step():
+            ctx._check(lib.fb_chebyshev_step(ctx.h, ctx.ptr(bufs[0]), ctx.ptr(cr), ctx.ptr(cz), ctx.ptr(bufs[1]), 0.25, 0.05))
+            bufs.reverse()
+        cheb_ms = timed(cheb_step, 30)
+        B_cheb = B_spmv + (40 + 4 * spec.ns) * N   # - y, + r, z, row scales in, + r, d, z out, + 4 ns^2 per vertex
+        ach2 = B_cheb / (cheb_ms * 1e-3) / 1e9
         roofline = {
-            "kernel": "k_spmv_ch_tma (channel-operator SpMV: TMA bulk-copy pipeline + fp64 DMMA), the kernel "
-                      "behind every Krylov / Chebyshev operator application",
-            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": B_spmv, "ms": spmv_ms,
+            "kernel": "k_spmv_ch_tma<.,.,2> (one step of the Chebyshev recurrence on D^-1 J: channel-operator SpMV "
+                      "through the TMA bulk-copy pipeline and fp64 DMMA, fused with the block-Jacobi application and "
+                      "the vector updates): the launch behind 5 of every 6 operator applications of a time step",
+            "bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
+            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": B_cheb, "ms": cheb_ms,
             "note": "algorithmic bytes of the channel-operator layout (8 bytes per channel and edge: "
-                    f"{nsp}+{ndp} channels instead of {spec.npairs} species pairs); timed alone after the steps "
-                    "(burst), inputs larger than L2",
+                    f"{nsp}+{ndp} channels instead of {spec.npairs} species pairs) + 4 ns^2 + 8 ns bytes of inverse "
+                    "block per vertex + 7 vector passes (x, r, z, scales in; r, d, z out); timed alone after the steps (burst), inputs larger than L2",
+            "operator_only": {"kernel": "k_spmv_ch_tma<.,.,0> (y = J x)", "algorithmic_bytes": B_spmv, "ms": spmv_ms,
+                              "achieved": ach, "frac": ach / peak},
             "block_csr_equivalent": {
                 "what": "the same products counted with SURVEY 8d's block-CSR bytes (8 |P| nnzb): what a "
                         "block-CSR SpMV / assembly would have had to move in the same time",

@@ -355,6 +355,20 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
       S.vx_o_dyn = (int)itab.size();
       itab.insert(itab.end(), lst.begin(), lst.end());
     }
+    {   // diagonal-block entries grouped by channel (k_bjacobi_setup_slab): A[s][c] += coef * value(channel)
+      const int* prow = sec_i(S_PAIR_ROW); const int* pcs = sec_i(S_PAIR_CS);
+      std::vector<int> bptr(nch + 1, 0), bpos;
+      std::vector<double> bcoef;
+      for (int c = 0; c < nch; ++c) {
+        for (int p = 0; p < np; ++p)
+          for (int e = jtp[p]; e < jtp[p + 1]; ++e)
+            if (jt[2 * e] == c) { bpos.push_back((prow[p] * ns + pcs[p]) | ((jt[2 * e + 1] & 1) << 16)); bcoef.push_back(jtc[e]); }
+        bptr[c + 1] = (int)bpos.size();
+      }
+      if ((rc = fb_upload(ctx, &ctx->d_bj_ptr, bptr.data(), bptr.size()))) return rc;
+      if ((rc = fb_upload(ctx, &ctx->d_bj_pos, bpos.data(), bpos.size()))) return rc;
+      if ((rc = fb_upload(ctx, &ctx->d_bj_coef, bcoef.data(), bcoef.size()))) return rc;
+    }
     S.vx_itab_n = (int)itab.size(); S.vx_dtab_n = (int)dtab.size();
     if ((rc = fb_upload(ctx, &S.vx_itab, itab.data(), itab.size()))) return rc;
     if ((rc = fb_upload(ctx, &S.vx_dtab, dtab.data(), dtab.size()))) return rc;

@@ -54,6 +54,8 @@ struct fb_ctx {
   int n_sp_ent = 0;            // entries of the channel SpMV epilogue table (vx_sp)
   // lane plan of the TMA channel SpMV's row epilogue (spmv_channels.cuh: fb_spmv_ep_plan); epl 0 = none
   int ep_epl = 0;
+  // block-Jacobi fill table of the channel operator, grouped by channel: ptr [nch+1], pos | flag << 16 [n], coef [n]
+  const int* d_bj_ptr = nullptr; const int* d_bj_pos = nullptr; const double* d_bj_coef = nullptr;
   const double* d_ep_coef = nullptr; const int* d_ep_pos = nullptr; const int* d_ep_lane = nullptr;
   bool op_channels = false;
   // Chebyshev polynomial preconditioner: interval of D^-1 J from Ritz values, operator applications
@@ -87,6 +89,11 @@ struct fb_ctx {
   double* d_work = nullptr;  // Krylov vectors
   long long work_doubles = 0;
   double* d_dinv = nullptr;  // block-Jacobi inverse blocks [n_vertices][ns][ns]
+  // the same blocks as single-precision mantissas with one power-of-two scale per row (k_bjacobi_setup_slab):
+  // inverse[v][s][c] = dscale[v][s] * dinv32[v][s][c] holds exactly - d_dinv carries these rounded values
+  float* d_dinv32 = nullptr;
+  double* d_dscale = nullptr;
+  bool dinv32_valid = false;
   double* d_red = nullptr;   // reduction partials
   long long red_doubles = 0;
   double* d_sc = nullptr;    // device scalars of the Krylov loops

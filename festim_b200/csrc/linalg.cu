@@ -268,7 +268,9 @@ static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
   // the ring must hold the chunks the consumer groups work on plus at least one in flight per group
-  int nst = 3 * FB_CHUNK_GROUPS;
+  // as deep a ring as shared memory holds (up to 6): the copies of a chunk are issued when the chunk
+  // nst places ahead of it has been consumed, and must hide the HBM latency behind nst - 1 chunks of work
+  int nst = 6;
   if (getenv("FB_SPMV_STAGES")) nst = atoi(getenv("FB_SPMV_STAGES"));
   if (nst > 8) nst = 8;
   size_t smem = fb_spmv_ch_layout(S, a, MODE, nst);
@@ -307,9 +309,9 @@ static int spmv_ch_tma_launch(fb_ctx* ctx, SpmvChArgs a) {
 // y = J x (precond false) or y = D^-1 J x on the channel operator
 static int spmv_ch(fb_ctx* ctx, const double* x, double* y, bool precond, const int* flags) {
   if (int rc = fbi_halo(ctx, (double*)x)) return rc;
-  if (spmv_ch_tma_ok(ctx, x)) {
+  if (spmv_ch_tma_ok(ctx, x) && (!precond || ctx->dinv32_valid)) {
     SpmvChArgs a{};
-    a.x = x; a.y = y; a.dinv = ctx->d_dinv; a.flags = flags;
+    a.x = x; a.y = y; a.dinv32 = ctx->d_dinv32; a.dscale = ctx->d_dscale; a.flags = flags;
     return precond ? spmv_ch_tma_launch<1>(ctx, a) : spmv_ch_tma_launch<0>(ctx, a);
   }
   return precond ? spmv_ch_launch<true>(ctx, x, y, flags) : spmv_ch_launch<false>(ctx, x, y, flags);
@@ -641,10 +643,166 @@ k_bjacobi_setup_coop(DevSpec S, const double* __restrict__ J, double* __restrict
   for (int t = g; t < nn; t += G) out[t] = A[t];
 }
 
+// Thread-per-vertex inversion with every matrix in its own shared-memory slab: element e of the
+// matrix of thread t at bj_smem[e * (TPB + 1) + t], so the 32 threads of a warp always hit 32
+// different banks whatever rows their pivots select, and the inverse blocks leave through a coalesced
+// transposed copy.  Same arithmetic (Gauss-Jordan, partial pivoting, ties -> smallest row) as the
+// cooperative kernel above, which spent ~4300 warp instructions per two vertices on shuffles and
+// warp barriers (C2: 3.8 ms).  NS > 0: compile-time block size (pivot row in registers).
+template <int TPB, int NS>
+__global__ void __launch_bounds__(TPB) k_bjacobi_setup_slab(DevSpec S, const double* __restrict__ J, double* __restrict__ dinv,
+                                                            int* __restrict__ flags, const int* __restrict__ bj_ptr,
+                                                            const int* __restrict__ bj_pos, const double* __restrict__ bj_coef,
+                                                            float* __restrict__ dinv32, double* __restrict__ dscale) {
+  extern __shared__ double bj_smem[];
+  constexpr int LD = TPB + 1;
+  const int ns = NS > 0 ? NS : S.ns, nn = ns * ns;
+  const long long v0 = (long long)blockIdx.x * TPB;
+  const long long v = v0 + threadIdx.x;
+  double* A = bj_smem + threadIdx.x;
+  short* sexp = (short*)(bj_smem + (size_t)nn * LD);   // [ns][LD] exponents of the row scales
+#define BJ(r, c) A[((r) * ns + (c)) * LD]
+  if (v < S.n_owned) {
+    const int r0 = S.rowptr[v], deg = S.rowptr[v + 1] - r0;
+    int kself = 0;
+    for (int k = 0; k < deg; ++k)
+      if (S.colidx[r0 + k] == v) kself = k;
+    for (int t = 0; t < nn; ++t) A[t * LD] = 0.0;
+    if (!J) {
+      // entries grouped by channel: one load of the channel value, uniform table reads
+      const double* __restrict__ st = S.et_stat + (long long)(r0 + kself) * S.vx_nsp;
+      const double* __restrict__ dy = S.et_dyn + (long long)(r0 + kself) * S.vx_ndp;
+      const int nch = S.vx_nch, nstat = S.vx_nstat;
+      for (int ch = 0; ch < nch; ++ch) {
+        const double val = ch < nstat ? st[ch] : dy[ch - nstat];
+        const int e1 = __ldg(bj_ptr + ch + 1);
+#pragma unroll 4
+        for (int e = __ldg(bj_ptr + ch); e < e1; ++e) {
+          const int w = __ldg(bj_pos + e);
+          const double coef = __ldg(bj_coef + e) * ((w >> 16) ? S.inv_dt : 1.0);
+          A[(w & 0xffff) * LD] += coef * val;
+        }
+      }
+      const unsigned vi = S.vinfo[v] & 0xffffu;
+      if (vi) {   // Dirichlet dofs: eliminated columns, identity rows
+        for (int s = 0; s < ns; ++s)
+          for (int c = 0; c < ns; ++c) {
+            if ((vi >> c) & 1u) BJ(s, c) = 0.0;
+            if ((vi >> s) & 1u) BJ(s, c) = (c == s) ? 1.0 : 0.0;
+          }
+      }
+    } else {
+      const long long base = (long long)(r0 + kself) * S.npairs;
+      for (int p = 0; p < S.npairs; ++p) BJ(S.pair_row[p], S.pair_cs[p]) = J[base + p];
+    }
+    unsigned long long perm = 0ull;   // 4 bits per column: the row it was swapped with
+#pragma unroll 1
+    for (int col = 0; col < ns; ++col) {
+      double best = -1.0;
+      int piv = col;
+      for (int r = col; r < ns; ++r) {
+        const double a = fabs(BJ(r, col));
+        if (a > best) { best = a; piv = r; }
+      }
+      if (best == 0.0) flags[2] = 1;
+      perm |= (unsigned long long)piv << (4 * col);
+      if (NS > 0) {
+        // pivot row (after the interchange) scaled into registers, the row it displaces moves to row piv
+        double prow[NS > 0 ? NS : 1];
+        const double pd = BJ(piv, col);
+        const double ip = 1.0 / (pd == 0.0 ? 1.0 : pd);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) {
+          const double pv = BJ(piv, c), cv = BJ(col, c);
+          if (piv != col) BJ(piv, c) = cv;
+          prow[c] = (c == col ? 1.0 : pv) * ip;
+        }
+#pragma unroll
+        for (int r = 0; r < NS; ++r) {
+          if (r == col) {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) BJ(r, c) = prow[c];
+          } else {
+            const double f = BJ(r, col);
+#pragma unroll
+            for (int c = 0; c < NS; ++c) BJ(r, c) = (c == col ? 0.0 : BJ(r, c)) - f * prow[c];
+          }
+        }
+      } else {
+        if (piv != col)
+          for (int c = 0; c < ns; ++c) { const double t = BJ(col, c); BJ(col, c) = BJ(piv, c); BJ(piv, c) = t; }
+        const double pd = BJ(col, col);
+        const double ip = 1.0 / (pd == 0.0 ? 1.0 : pd);
+        for (int c = 0; c < ns; ++c) BJ(col, c) = (c == col ? 1.0 : BJ(col, c)) * ip;
+        for (int r = 0; r < ns; ++r) {
+          if (r == col) continue;
+          const double f = BJ(r, col);
+          for (int c = 0; c < ns; ++c) BJ(r, c) = (c == col ? 0.0 : BJ(r, c)) - f * BJ(col, c);
+        }
+      }
+    }
+    for (int col = ns - 1; col >= 0; --col) {   // undo the row interchanges on the columns
+      const int piv = (int)((perm >> (4 * col)) & 0xfull);
+      if (piv != col)
+        for (int r = 0; r < ns; ++r) { const double t = BJ(r, col); BJ(r, col) = BJ(r, piv); BJ(r, piv) = t; }
+    }
+    // every row rounded to single-precision mantissas times a power of two (the scale of the row):
+    // the channel SpMV streams the 4-byte copy, every other kernel reads the same values in double
+    for (int s = 0; s < ns; ++s) {
+      double mx = 0.0;
+      for (int c = 0; c < ns; ++c) mx = fmax(mx, fabs(BJ(s, c)));
+      int ex = 0;
+      if (mx > 0.0) (void)frexp(mx, &ex);
+      ex = ex < -1000 ? -1000 : (ex > 1000 ? 1000 : ex);
+      const double up = ldexp(1.0, ex), dn = ldexp(1.0, -ex);
+      for (int c = 0; c < ns; ++c) BJ(s, c) = (double)(float)(BJ(s, c) * dn) * up;
+      sexp[s * LD + threadIdx.x] = (short)ex;
+    }
+  }
+#undef BJ
+  __syncthreads();
+  const long long left = S.n_owned - v0;
+  const int nvalid = (int)(left < TPB ? left : TPB);
+  double* __restrict__ out = dinv + v0 * nn;
+  float* __restrict__ out32 = dinv32 + v0 * nn;
+  for (int i = threadIdx.x; i < nvalid * nn; i += TPB) {
+    const int m = i / nn, e = i - m * nn;
+    const double val = bj_smem[e * LD + m];
+    const int ex = sexp[(e / ns) * LD + m];
+    out[i] = val;
+    out32[i] = (float)ldexp(val, -ex);   // exact
+  }
+  double* __restrict__ outs = dscale + v0 * ns;
+  for (int i = threadIdx.x; i < nvalid * ns; i += TPB) {
+    const int m = i / ns, s = i - m * ns;
+    outs[i] = ldexp(1.0, (int)sexp[s * LD + m]);
+  }
+}
+
 static int bjacobi_setup(fb_ctx* ctx, const double* J) {
   const DevSpec& S = ctx->S;
+  ctx->dinv32_valid = false;
   if (S.ns == 1 || S.ns > 16 || getenv("FB_BJ_THREAD")) {
     FB_LAUNCH(ctx, k_bjacobi_setup, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, J, ctx->d_dinv, ctx->d_flags);
+    return 0;
+  }
+  if (!getenv("FB_BJ_COOP") && (J || ctx->d_bj_ptr)) {
+    constexpr int TPB = 64;
+    const size_t smem = (size_t)S.ns * S.ns * (TPB + 1) * sizeof(double) + (size_t)S.ns * (TPB + 1) * sizeof(short);
+    const unsigned grid = (unsigned)((S.n_owned + TPB - 1) / TPB);
+    ctx->dinv32_valid = true;
+#define FB_BJ_CASE(N)                                                                                                   \
+    {                                                                                                                   \
+      FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_bjacobi_setup_slab<TPB, N>,                                     \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+      FB_LAUNCH(ctx, (k_bjacobi_setup_slab<TPB, N>), grid, TPB, smem, S, J, ctx->d_dinv, ctx->d_flags, ctx->d_bj_ptr,    \
+                ctx->d_bj_pos, ctx->d_bj_coef, ctx->d_dinv32, ctx->d_dscale);                 \
+    }
+    if (S.ns == 12) FB_BJ_CASE(12)
+    else if (S.ns == 4) FB_BJ_CASE(4)
+    else if (S.ns == 6) FB_BJ_CASE(6)
+    else FB_BJ_CASE(0)
+#undef FB_BJ_CASE
     return 0;
   }
   const int G = 16, gpb = 256 / G;
@@ -1599,6 +1757,8 @@ int fbi_ensure_workspace(fb_ctx* ctx) {
   if ((rc = fb_alloc(ctx, &ctx->d_ticket, 256))) return rc;
   if ((rc = fb_alloc(ctx, &ctx->d_flags, 8))) return rc;
   if ((rc = fb_alloc(ctx, &ctx->d_dinv, (size_t)S.n_vertices * S.ns * S.ns))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_dinv32, (size_t)S.n_vertices * S.ns * S.ns + 8))) return rc;
+  if ((rc = fb_alloc(ctx, &ctx->d_dscale, (size_t)S.n_vertices * S.ns + 8))) return rc;
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_ticket, 0, 256 * sizeof(unsigned), ctx->stream));
   FB_CHECK(ctx, cudaMemsetAsync(ctx->d_flags, 0, 32, ctx->stream));
   FB_CHECK(ctx, cudaMallocHost((void**)&ctx->h_pinned, 64 * sizeof(double)));
@@ -1969,7 +2129,7 @@ static int cheb_apply(fb_ctx* ctx, const double* v, double* z, double* w, double
   for (int i = 0; i < steps; ++i) {
     const double rho_n = 1.0 / (2.0 * sigma - rho);
     SpmvChArgs a{};
-    a.x = din; a.dinv = ctx->d_dinv; a.flags = flags;
+    a.x = din; a.dinv32 = ctx->d_dinv32; a.dscale = ctx->d_dscale; a.flags = flags;
     a.r = r; a.z = z; a.dout = dout; a.vin = v; a.wout = w;
     a.ca = rho_n * rho; a.cb = 2.0 * rho_n / delta;
     a.last = (w && i == m) ? 1 : 0;
@@ -2007,7 +2167,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
   int total = 0;
   int fl[4] = {0, 0, 0, 0};
   bool first = !use_guess, guess_checked = false;
-  const bool cheb_possible = want_cheb && !J && spmv_ch_tma_ok(ctx, V) && !ctx->cheb_refused;
+  const bool cheb_possible = want_cheb && !J && spmv_ch_tma_ok(ctx, V) && ctx->dinv32_valid && !ctx->cheb_refused;
   while (total < max_it) {
     // right-preconditioned with the Chebyshev polynomial p(B) of B = D^-1 J once its interval is
     // known (Ritz values of a plain cycle); the Arnoldi residual is the block-Jacobi one either way
@@ -2989,4 +3149,17 @@ extern "C" int fb_dcg_persistent(fb_ctx* ctx, const double* J, const double* b, 
             ph[1] / fl[1], ph[2] / fl[1], ph[3] / fl[1], ph[4] / fl[1]);
   }
   return 0;
+}
+
+extern "C" int fb_chebyshev_step(fb_ctx* ctx, const double* d_in, double* r, double* z, double* d_out, double ca, double cb) {
+  if (!ctx || !ctx->have_spec) return ctx ? fb_fail(ctx, "fb_set_spec first") : -1;
+  cudaSetDevice(ctx->device);
+  if (!ctx->d_dinv || !ctx->dinv32_valid) return fb_fail(ctx, "fb_chebyshev_step: fb_bjacobi_setup(ctx, NULL) on the channel operator first");
+  if (!spmv_ch_tma_ok(ctx, d_in)) return fb_fail(ctx, "fb_chebyshev_step: the TMA channel SpMV does not apply to this problem");
+  SpmvChArgs a{};
+  a.x = d_in; a.dinv32 = ctx->d_dinv32; a.dscale = ctx->d_dscale; a.flags = nullptr;
+  a.r = r; a.z = z; a.dout = d_out; a.vin = nullptr; a.wout = nullptr;
+  a.ca = ca; a.cb = cb; a.last = 0;
+  if (int rc = fbi_halo(ctx, (double*)d_in)) return rc;
+  return spmv_ch_tma_launch<2>(ctx, a);
 }

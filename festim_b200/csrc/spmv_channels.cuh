@@ -211,7 +211,8 @@ inline SpmvEpPlan fb_spmv_ep_plan(int ns, const int* sp_ptr, const int* sp, cons
 struct SpmvChArgs {
   const double* x;
   double* y;
-  const double* dinv;
+  const float* dinv32;      // inverse diagonal blocks: single-precision mantissas ...
+  const double* dscale;     // ... times one power-of-two scale per row (k_bjacobi_setup_slab)
   const int* flags;
   // Chebyshev step (MODE 2)
   double* r;
@@ -228,7 +229,7 @@ struct SpmvChArgs {
   // shared-memory layout (bytes): per-warp scratch, stages
   int nst, zslot;
   int o_part, part_bytes, o_ybuf, o_stage0, stage_bytes, o_bar;
-  int s_dyn, s_xs, s_dinv, s_r, s_z, s_vin, s_lcol, s_vinfo, s_rowinfo, s_rowptr;   // offsets inside a stage
+  int s_dyn, s_xs, s_dinv, s_dscale, s_r, s_z, s_vin, s_lcol, s_vinfo, s_rowinfo, s_rowptr;   // offsets inside a stage
 };
 
 // fills the layout for MODE; returns the bytes of dynamic shared memory with nst stages
@@ -245,7 +246,8 @@ __host__ inline size_t fb_spmv_ch_layout(const DevSpec& S, SpmvChArgs& a, int mo
   // + a slot of zeros for the edges of the K padding (zslot) and the tile padding read past a vertex
   a.zslot = S.ck_nx_max + 2;
   a.s_xs = (int)s; s += up16((size_t)(S.ck_nx_max + 4) * ns * 8);
-  a.s_dinv = (int)s; if (mode >= 1) s += up16((size_t)CH * ns * ns * 8);
+  a.s_dinv = (int)s; if (mode >= 1) s += up16((size_t)CH * ns * ns * 4);
+  a.s_dscale = (int)s; if (mode >= 1) s += up16((size_t)CH * ns * 8);
   a.s_r = (int)s; if (mode == 2) s += up16((size_t)CH * ns * 8);
   a.s_z = (int)s; if (mode == 2) s += up16((size_t)CH * ns * 8);
   a.s_vin = (int)s; if (mode == 2) s += up16((size_t)CH * ns * 8);
@@ -320,7 +322,7 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
         const int nlc = (ne + 7) & ~7;
         if (lane == 0) {
           unsigned bytes = (unsigned)(ne * (NSP + NDP) * 8 + nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
-          if (MODE >= 1) bytes += (unsigned)(nrow * ns * ns * 8);
+          if (MODE >= 1) bytes += (unsigned)(nrow * ns * ns * 4 + nrow * ns * 8);
           if (MODE == 2) bytes += (unsigned)((a.last ? 3 : 2) * nrow * ns * 8);
           fb_mbar_expect_tx(b, bytes);
         }
@@ -332,7 +334,8 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
         if (lane == 4) fb_bulk_g2s(st + a.s_rowinfo, S.ck_rowinfo + c0, (unsigned)(CH * 4), b);
         if (lane == 9) fb_bulk_g2s(st + a.s_rowptr, S.rowptr + c0, (unsigned)((CH + 4) * 4), b);
         if (MODE >= 1 && lane == 5)
-          fb_bulk_g2s(st + a.s_dinv, a.dinv + c0 * ns * ns, (unsigned)(nrow * ns * ns * 8), b);
+          fb_bulk_g2s(st + a.s_dinv, a.dinv32 + c0 * ns * ns, (unsigned)(nrow * ns * ns * 4), b);
+        if (MODE >= 1 && lane == 10) fb_bulk_g2s(st + a.s_dscale, a.dscale + c0 * ns, (unsigned)(nrow * ns * 8), b);
         if (MODE == 2) {
           if (lane == 6) fb_bulk_g2s(st + a.s_r, a.r + c0 * ns, (unsigned)(nrow * ns * 8), b);
           if (lane == 7) fb_bulk_g2s(st + a.s_z, a.z + c0 * ns, (unsigned)(nrow * ns * 8), b);
@@ -470,9 +473,10 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
       }
       // vectors of the fused epilogue: issued ahead of the tile store (no later load can pass it)
       const int t = j * ns + srow;
-      double xself = 0.0, rr = 0.0, zz = 0.0, vv = 0.0;
+      double xself = 0.0, rr = 0.0, zz = 0.0, vv = 0.0, dsc = 0.0;
       if (sown) {
         xself = xs[lself * ns + srow];
+        if (MODE >= 1) dsc = ((const double*)(st + a.s_dscale))[t];
         if (MODE == 2) {
           rr = ((const double*)(st + a.s_r))[t];
           if (a.last) vv = ((const double*)(st + a.s_vin))[t];
@@ -513,18 +517,22 @@ k_spmv_ch_tma(DevSpec S, SpmvChArgs a) {
         __syncwarp();
         double pa = 0.0, pb = 0.0;
         if (srow < ns) {
-          const double2* dv = (const double2*)(st + a.s_dinv) + (size_t)(j * ns + srow) * np2;   // row s of the inverse block
+          // row s of the inverse block: 4-byte mantissas (rows of 48 bytes at ns = 12: the 16 lanes of a
+          // half warp read 16 different bank pairs), the row's scale is applied to the sum
+          const float2* dv = (const float2*)(st + a.s_dinv) + (size_t)(j * ns + srow) * np2;
           const double2* y2 = (const double2*)yrow;
 #pragma unroll
           for (int q = 0; q < 2 * NT; ++q)
             if (dq0 + q < dq1) {
-              const double2 d2 = dv[dq0 + q], yv = y2[dq0 + q];
-              pa += d2.x * yv.x;
-              pb += d2.y * yv.y;
+              const float2 d2 = dv[dq0 + q];
+              const double2 yv = y2[dq0 + q];
+              pa += (double)d2.x * yv.x;
+              pb += (double)d2.y * yv.y;
             }
         }
         double p = pa + pb;
         p += __shfl_xor_sync(FULL, p, 1);
+        p *= dsc;
         if (sown) {
           if (MODE == 1) a.y[dof + srow] = p;
           else {

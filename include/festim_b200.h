@@ -153,6 +153,11 @@ int fb_last_timings(fb_ctx* ctx, double* out /*[host] 4*/);
 
 /* state of the Chebyshev preconditioner: out = {valid, lambda_min, lambda_max, operator applications per use} */
 int fb_chebyshev_info(fb_ctx* ctx, double* out /*[host] 4*/);
+/* one step of the Chebyshev recurrence on B = D^-1 J (channel operator, after fb_bjacobi_setup(ctx, NULL)),
+ * the single kernel launch the polynomial preconditioner repeats (PETSc analogue: one KSPCHEBYSHEV iteration
+ * inside PCKSP, reference options seam src/festim/problem.py:132-168):
+ *   r <- r - B d_in ;  d_out = ca d_in + cb r ;  z <- z + d_out        (all [dev], n_dofs doubles) */
+int fb_chebyshev_step(fb_ctx* ctx, const double* d_in, double* r, double* z, double* d_out, double ca, double cb);
 /* test hook: eigenvalues of an n x n real upper Hessenberg matrix (row-major), the routine that
  * turns the Arnoldi matrix of a GMRES cycle into the interval of the Chebyshev preconditioner */
 int fb_hessenberg_eigenvalues(int n, const double* a /*[host]*/, double* wr /*[host]*/, double* wi /*[host]*/);

@@ -69,6 +69,15 @@ def main():
     ms_asm_ch = timed(lambda: ctx._check(lib.fb_assemble(ctx.h, ctx.ptr(u), ctx.ptr(un), ctx.ptr(F), None, 3)), args.reps)
     ms_spmv_ch = timed(lambda: ctx._check(lib.fb_spmv(ctx.h, None, ctx.ptr(x), ctx.ptr(y))), 20)
     spmv_diff = float((y - y_bsr).abs().max() / y_bsr.abs().max())
+    # one step of the Chebyshev recurrence (MODE 2 of the same kernel) and the block-Jacobi set-up
+    ms_bj = timed(lambda: ctx._check(lib.fb_bjacobi_setup(ctx.h, None)), 5)
+    cr, cz, cd = ctx.zeros(N), ctx.zeros(N), ctx.zeros(N)
+    bufs = [x, cd]
+
+    def cheb_step():
+        ctx._check(lib.fb_chebyshev_step(ctx.h, ctx.ptr(bufs[0]), ctx.ptr(cr), ctx.ptr(cz), ctx.ptr(bufs[1]), 0.25, 0.05))
+        bufs.reverse()
+    ms_cheb = timed(cheb_step, 20)
     vx = spec.vx
     nsp, ndp = (vx["nstat"] + 1) // 2 * 2, (vx["ndyn"] + 1) // 2 * 2
     B_spmv_ch = 8 * (nsp + ndp) * nnzb + 4 * nnzb + 4 * (mesh.num_vertices + 1) + 16 * N
@@ -86,7 +95,8 @@ def main():
                              "assembly_F_and_channels_ms": ms_asm_ch,
                              "spmv_ms": ms_spmv_ch, "spmv_algorithmic_bytes": B_spmv_ch,
                              "spmv_gbs": B_spmv_ch / ms_spmv_ch / 1e6, "spmv_frac": B_spmv_ch / ms_spmv_ch / 1e6 / peak,
-                             "spmv_rel_diff_vs_block_csr": spmv_diff}, "load_and_coefficients": {"ms": ms_load},
+                             "spmv_rel_diff_vs_block_csr": spmv_diff,
+                             "chebyshev_step_ms": ms_cheb, "bjacobi_setup_ms": ms_bj}, "load_and_coefficients": {"ms": ms_load},
     }
     if args.solve:
         m.u.x.array[:] = 0.0
