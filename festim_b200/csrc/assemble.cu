@@ -305,7 +305,7 @@ static int asm_tma_launch(fb_ctx* ctx, const double* u, const double* un, double
   if (grid > nchunks) grid = nchunks;
   if (grid < 1) grid = 1;
   FB_CHECK(ctx, cudaFuncSetAttribute((const void*)k_assemble_edge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_assemble_edge_tma<<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, smem, ctx->stream>>>(S, a);
+  k_assemble_edge_tma<<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 64, smem, ctx->stream>>>(S, a);
   ctx->launches++;
   FB_CHECK(ctx, cudaGetLastError());
   *done = true;

@@ -71,7 +71,7 @@ __host__ inline size_t fb_asm_tma_layout(const DevSpec& S, AsmTmaArgs& a, int ns
   return o;
 }
 
-__global__ void __launch_bounds__(32 * FB_CHUNK * FB_CHUNK_GROUPS + 32, 1)
+__global__ void __launch_bounds__(32 * FB_CHUNK * FB_CHUNK_GROUPS + 64, 1)
 k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
   extern __shared__ __align__(16) unsigned char fb_as_smem[];
   constexpr int CH = FB_CHUNK, NG = FB_CHUNK_GROUPS;
@@ -99,34 +99,41 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
   unsigned long long* full = (unsigned long long*)(fb_as_smem + a.o_bar);
   unsigned long long* empty = full + 8;
   if (threadIdx.x == 0)
-    for (int q = 0; q < NST; ++q) { fb_mbar_init(&full[q], 1); fb_mbar_init(&empty[q], CH); }
+    for (int q = 0; q < NST; ++q) { fb_mbar_init(&full[q], 2); fb_mbar_init(&empty[q], CH); }   // full: one arrival per producer warp
   for (size_t t = threadIdx.x; t < (size_t)NST * a.stage_bytes / 16; t += blockDim.x)
     ((double2*)(fb_as_smem + a.o_stage0))[t] = make_double2(0.0, 0.0);
   fb_fence_proxy_async();
   fb_mbar_fence_init();
   __syncthreads();
-  const long long nchunks = (S.n_owned + CH - 1) / CH;
-  const long long nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nchunks = (int)((S.n_owned + CH - 1) / CH);
+  const int nmine = (int)blockIdx.x < nchunks ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp == CH * NG) {
-    // ================= producer warp =====================================================================
-    int pf_e0, pf_ne, pf_nx, pf_lc, pf_q0 = 0, pf_q1 = 0, pf_run[3];
-    long long pf_t0, pf_t1;
-    auto prefetch = [&](long long i) {
+  if (warp >= CH * NG) {
+    // ================= two producer warps: warp 0 the row data, warp 1 the runs of u / u_n ================
+    const bool px = warp > CH * NG;
+    int pf_e0 = 0, pf_ne = 0, pf_nx = 0, pf_lc = 0, pf_q0 = 0, pf_q1 = 0, pf_run[3] = {0, 0, 0};
+    long long pf_t0 = 0, pf_t1 = 0;
+    auto prefetch = [&](int i) {
       if (i >= nmine) return;
       const long long c = blockIdx.x + i * (long long)gridDim.x;
       const long long c0 = c * CH;
-      const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
-      pf_e0 = S.rowptr[c0]; pf_ne = S.rowptr[c0 + nrow]; pf_nx = S.ck_nx[c]; pf_lc = S.ck_lcolptr[c];
-      pf_t0 = nts ? S.et_tzptr[c0] : 0; pf_t1 = nts ? S.et_tzptr[c0 + nrow] : 0;
-      const int* rr = S.ck_slots + ((size_t)c * 32 + lane) * 3;
-      pf_run[0] = rr[0]; pf_run[1] = rr[1]; pf_run[2] = rr[2];
-      if (S.ck_rmax > 32) { pf_q0 = S.ck_runptr[c]; pf_q1 = S.ck_runptr[c + 1]; }
+      if (!px) {
+        const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
+        pf_e0 = S.rowptr[c0]; pf_ne = S.rowptr[c0 + nrow]; pf_lc = S.ck_lcolptr[c];
+        pf_t0 = nts ? S.et_tzptr[c0] : 0; pf_t1 = nts ? S.et_tzptr[c0 + nrow] : 0;
+      } else {
+        pf_nx = S.ck_nx[c];
+        const int* rr = S.ck_slots + ((size_t)c * 32 + lane) * 3;
+        pf_run[0] = rr[0]; pf_run[1] = rr[1]; pf_run[2] = rr[2];
+        if (S.ck_rmax > 32) { pf_q0 = S.ck_runptr[c]; pf_q1 = S.ck_runptr[c + 1]; }
+      }
     };
     prefetch(0);
-    for (long long i = 0; i < nmine; ++i) {
-      const int sidx = (int)(i % NST);
-      if (i >= NST) fb_mbar_wait(&empty[sidx], (unsigned)(((i / NST) - 1) & 1));
+    int sidx = 0;
+    unsigned eph = 1;   // parity of the stage's previous use: the first NST waits pass at once
+    for (int i = 0; i < nmine; ++i, sidx = (sidx + 1 == NST ? 0 : sidx + 1)) {
+      if (i && sidx == 0) eph ^= 1u;
+      fb_mbar_wait(&empty[sidx], eph);
       const long long c = blockIdx.x + i * (long long)gridDim.x;
       const long long c0 = c * CH;
       const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
@@ -138,8 +145,23 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
       const int r0v = pf_run[0], r1v = pf_run[1], r2v = pf_run[2];
       prefetch(i + 1);
       const int nlc = (ne + 7) & ~7;
+      if (px) {
+        // u (and u_n) at the chunk's distinct neighbours, one copy per run of vertex ids
+        if (lane == 0) fb_mbar_expect_tx(b, (unsigned)(nx * ns * 8 * (transient ? 2 : 1)));
+        __syncwarp();
+        if (r1v > 0) {
+          fb_bulk_g2s(st + a.s_us + (size_t)r2v * ns * 8, a.u + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
+          if (transient) fb_bulk_g2s(st + a.s_uns + (size_t)r2v * ns * 8, a.un + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
+        }
+        for (int q = q0 + 32 + lane; q < q1; q += 32) {
+          const int v0 = S.ck_runs[3 * q], len = S.ck_runs[3 * q + 1], lo = S.ck_runs[3 * q + 2];
+          fb_bulk_g2s(st + a.s_us + (size_t)lo * ns * 8, a.u + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
+          if (transient) fb_bulk_g2s(st + a.s_uns + (size_t)lo * ns * 8, a.un + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
+        }
+        continue;
+      }
       if (lane == 0) {
-        unsigned bytes = (unsigned)(nx * ns * 8 * (transient ? 2 : 1) + nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
+        unsigned bytes = (unsigned)(nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
         if (nts) bytes += (unsigned)(nts * (2 * ne * 8 + nt * 8) + nt + CH * 4 + (CH + 4) * 8);
         if (doF) bytes += (unsigned)(ne * NSP * 8 + nrow * ns * 8);
         fb_mbar_expect_tx(b, bytes);
@@ -161,16 +183,6 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
         else if (nt)
           fb_bulk_g2s(st + a.s_tz + (size_t)ts * a.tz_stride * 8, S.et_tz + ts * S.et_tz_total + t0, (unsigned)(nt * 8), b);
       }
-      // u (and u_n) at the chunk's distinct neighbours, one copy per run of vertex ids
-      if (r1v > 0) {
-        fb_bulk_g2s(st + a.s_us + (size_t)r2v * ns * 8, a.u + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
-        if (transient) fb_bulk_g2s(st + a.s_uns + (size_t)r2v * ns * 8, a.un + (long long)r0v * ns, (unsigned)(r1v * ns * 8), b);
-      }
-      for (int q = q0 + 32 + lane; q < q1; q += 32) {
-        const int v0 = S.ck_runs[3 * q], len = S.ck_runs[3 * q + 1], lo = S.ck_runs[3 * q + 2];
-        fb_bulk_g2s(st + a.s_us + (size_t)lo * ns * 8, a.u + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
-        if (transient) fb_bulk_g2s(st + a.s_uns + (size_t)lo * ns * 8, a.un + (long long)v0 * ns, (unsigned)(len * ns * 8), b);
-      }
     }
     return;
   }
@@ -182,13 +194,15 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
   double* res = scr + a.w_res;
   const int grp = warp / CH, wrow = warp - grp * CH;
   const int col_one = 2 * ns + NF;
-  for (long long i = grp; i < nmine; i += NG) {
-    const int sidx = (int)(i % NST);
-    const long long c = blockIdx.x + i * (long long)gridDim.x;
-    const long long c0 = c * CH;
-    const int nrow = (int)((S.n_owned - c0) < CH ? (S.n_owned - c0) : CH);
+  int sidx = grp % NST;
+  unsigned fph = (unsigned)((grp / NST) & 1);
+  long long c0 = ((long long)blockIdx.x + (long long)grp * gridDim.x) * CH;
+  const long long cstep = (long long)NG * gridDim.x * CH;
+  for (int i = grp; i < nmine; i += NG, c0 += cstep) {
+    const int nrow = (int)blockIdx.x + i * (int)gridDim.x == nchunks - 1
+                         ? (int)(S.n_owned - (long long)(nchunks - 1) * CH) : CH;   // only the last chunk is short
     unsigned char* st = fb_as_smem + a.o_stage0 + (size_t)sidx * a.stage_bytes;
-    fb_mbar_wait(&full[sidx], (unsigned)((i / NST) & 1));
+    fb_mbar_wait(&full[sidx], fph);
     if (wrow < nrow) {
       const int j = wrow;
       const long long v = c0 + j;
@@ -367,5 +381,7 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
     }
     __syncwarp();
     if (lane == 0) fb_mbar_arrive(&empty[sidx]);
+    sidx += NG;
+    if (sidx >= NST) { sidx -= NST; fph ^= 1u; }
   }
 }

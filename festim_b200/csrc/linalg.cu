@@ -832,6 +832,44 @@ __global__ void k_precond(DevSpec S, const double* __restrict__ dinv, const doub
   for (int s = 0; s < S.ns; ++s) z[v * S.ns + s] = zo[s];
 }
 
+// z = D^-1 r from the single-precision mantissas + row scales of k_bjacobi_setup_slab (same values as
+// the double blocks, 5/8 of their bytes less): one thread per dof, the ns threads of a vertex read
+// consecutive rows of the block (coalesced) and share the vertex' entries of r through L1.
+__global__ void k_precond32(long long n_owned, int ns, const float* __restrict__ dinv32, const double* __restrict__ dscale,
+                            const double* __restrict__ r, double* __restrict__ z, const int* __restrict__ flags) {
+  if (flags && flags[0]) return;
+  const int vpb = blockDim.x / ns;
+  const int vl = threadIdx.x / ns, s = threadIdx.x - vl * ns;
+  const long long v = (long long)blockIdx.x * vpb + vl;
+  if (vl >= vpb || v >= n_owned) return;
+  const long long i = v * ns + s;
+  const float* __restrict__ row = dinv32 + i * ns;
+  const double* __restrict__ rv = r + v * ns;
+  double a0 = 0.0, a1 = 0.0;
+  int c = 0;
+  if ((ns & 3) == 0) {
+    for (; c < ns; c += 4) {
+      const float4 d4 = *(const float4*)(row + c);
+      a0 += (double)d4.x * rv[c] + (double)d4.z * rv[c + 2];
+      a1 += (double)d4.y * rv[c + 1] + (double)d4.w * rv[c + 3];
+    }
+  } else {
+    for (; c < ns; ++c) a0 += (double)row[c] * rv[c];
+  }
+  z[i] = dscale[i] * (a0 + a1);
+}
+
+static int precond_launch(fb_ctx* ctx, const double* r, double* z, const int* flags) {
+  const DevSpec& S = ctx->S;
+  if (ctx->dinv32_valid && S.ns <= 32) {
+    const int vpb = 256 / S.ns;
+    FB_LAUNCH(ctx, k_precond32, (unsigned)((S.n_owned + vpb - 1) / vpb), 256, 0, S.n_owned, S.ns, ctx->d_dinv32, ctx->d_dscale, r, z, flags);
+  } else {
+    FB_LAUNCH(ctx, k_precond, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, ctx->d_dinv, r, z, flags);
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // CG, Chronopoulos-Gear single-reduction form, block-Jacobi preconditioned.
 //   sc[0]=alpha sc[1]=beta sc[2]=gamma sc[3]=rr sc[4]=threshold^2 sc[5]=rr0
@@ -2175,11 +2213,11 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     // r = D^-1 (b - A y)   (left preconditioning: the Arnoldi residual is the
     // preconditioned one, PETSc's default norm for GMRES)
     if (first) {
-      FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, b, r, (const int*)nullptr);
+      precond_launch(ctx, b, r, (const int*)nullptr);
     } else {
       if ((rc = fbi_spmv(ctx, J, y, w))) return rc;
       FB_LAUNCH(ctx, k_residual, gv, FB_TPB, 0, No, b, w, w);
-      FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, w, r, (const int*)nullptr);
+      precond_launch(ctx, w, r, (const int*)nullptr);
     }
     first = false;
     FB_LAUNCH(ctx, k_dot, gv, FB_TPB, 0, No, r, r, ctx->d_red, ctx->d_ticket, sc + GM_MISC, xr_next(ctx));
@@ -2210,7 +2248,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
         if ((rc = spmv_blk_launch<true>(ctx, J, V + (size_t)j * N, w, ctx->d_flags))) return rc;
       } else {
         if ((rc = fbi_spmv(ctx, J, V + (size_t)j * N, z))) return rc;
-        FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, z, w, ctx->d_flags);
+        precond_launch(ctx, z, w, ctx->d_flags);
       }
       const int nv = j + 1;
 #define FB_GS_CASE(NVB)                                                                                        \
@@ -2311,7 +2349,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   // which matters when species equations differ by many orders of magnitude
   const int base = (ksp == FB_KSP_CG) ? 5 : GM_NVEC;  // Krylov vectors, then Ay, t, corr
   if ((rc = ensure_vectors(ctx, base + 3))) return rc;
-  FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, b, ctx->d_work, (const int*)nullptr);
+  precond_launch(ctx, b, ctx->d_work, (const int*)nullptr);
   double pbnorm;
   if ((rc = fbi_norm2(ctx, ctx->d_work, &pbnorm))) return rc;
   double thr = rtol * pbnorm;
@@ -2333,7 +2371,7 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
     if (round > 0) {
       // correction equation J d = b - J y, solved to 1e-3 of its own preconditioned norm
       rhs = t; sol = corr;
-      FB_LAUNCH(ctx, k_precond, gn, FB_TPB, 0, S, ctx->d_dinv, t, corr, (const int*)nullptr);
+      precond_launch(ctx, t, corr, (const int*)nullptr);
       double pn;
       if ((rc = fbi_norm2(ctx, corr, &pn))) return rc;
       thr_r = 1e-3 * pn;
@@ -2898,7 +2936,7 @@ extern "C" int fb_bjacobi_setup(fb_ctx* ctx, const double* J) {
 extern "C" int fb_precond(fb_ctx* ctx, const double* r, double* z) {
   if (!ctx || !ctx->d_dinv) return ctx ? fb_fail(ctx, "fb_bjacobi_setup first") : -1;
   const DevSpec& S = ctx->S;
-  FB_LAUNCH(ctx, k_precond, (unsigned)((S.n_owned + FB_TPB - 1) / FB_TPB), FB_TPB, 0, S, ctx->d_dinv, r, z, (const int*)nullptr);
+  precond_launch(ctx, r, z, (const int*)nullptr);
   FB_CHECK(ctx, cudaGetLastError());
   return 0;
 }
