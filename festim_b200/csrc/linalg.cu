@@ -2195,7 +2195,10 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
   double* cd1 = cd0 + N;
   double* cr = cd1 + N;
   double* cz = cr + N;
-  const unsigned gn = (unsigned)((S.n_vertices + FB_TPB - 1) / FB_TPB);
+  // flexible storage: Z_j = p(B) V_j is what the Chebyshev recurrence leaves in its sum vector anyway -
+  // kept per Krylov vector (behind the three vectors of the refinement loop) the update y += Z yk needs no
+  // second application of the polynomial (4 operator applications less per solve)
+  double* Zf = ctx->work_doubles >= (long long)(GM_NVEC + 3 + GM_M) * N ? V + (size_t)(GM_NVEC + 3) * N : nullptr;
   const unsigned gv = vec_grid(ctx, No);
   double* sc = ctx->d_sc;
   // use_guess: y holds an initial guess (KSPSetInitialGuessNonzero), e.g. the Newton update of the
@@ -2240,7 +2243,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     for (int j = 0; j < GM_M; ++j) {
       // w = D^-1 J [p(B)] V_j: SpMV with the block-Jacobi application fused into its epilogue
       if (cheb) {
-        if ((rc = cheb_apply(ctx, V + (size_t)j * N, cz, w, cd0, cd1, cr, ctx->d_flags))) return rc;
+        if ((rc = cheb_apply(ctx, V + (size_t)j * N, Zf ? Zf + (size_t)j * N : cz, w, cd0, cd1, cr, ctx->d_flags))) return rc;
       } else if (!J) {
         if ((rc = spmv_ch(ctx, V + (size_t)j * N, w, true, ctx->d_flags))) return rc;
       } else if (spmv_blk_ok(S)) {
@@ -2277,8 +2280,8 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
     // y += [p(B)] V yk
     if (fl[3] > 0) {
       FB_LAUNCH(ctx, k_gmres_solve_y, 1, 1, 0, sc, ctx->d_flags);
-      FB_LAUNCH(ctx, k_combine, gv, FB_TPB, 0, No, N, V, sc + GM_Y, ctx->d_flags, w);
-      if (cheb) {
+      FB_LAUNCH(ctx, k_combine, gv, FB_TPB, 0, No, N, (cheb && Zf) ? Zf : V, sc + GM_Y, ctx->d_flags, w);
+      if (cheb && !Zf) {
         if ((rc = cheb_apply(ctx, w, cz, nullptr, cd0, cd1, cr, (const int*)nullptr))) return rc;
         FB_LAUNCH(ctx, k_axpy, gv, FB_TPB, 0, No, 1.0, cz, y);
       } else {
@@ -2348,7 +2351,8 @@ int fbi_linear_solve(fb_ctx* ctx, const double* J, const double* b, double* y, i
   // (PETSc default for left-preconditioned CG/GMRES); block-Jacobi makes it row-scaled,
   // which matters when species equations differ by many orders of magnitude
   const int base = (ksp == FB_KSP_CG) ? 5 : GM_NVEC;  // Krylov vectors, then Ay, t, corr
-  if ((rc = ensure_vectors(ctx, base + 3))) return rc;
+  const int flex = (ksp == FB_KSP_GMRES && !J && !getenv("FB_NO_FLEX")) ? GM_M : 0;   // Z_j = p(B) V_j of the polynomial preconditioner
+  if ((rc = ensure_vectors(ctx, base + 3 + flex))) return rc;
   precond_launch(ctx, b, ctx->d_work, (const int*)nullptr);
   double pbnorm;
   if ((rc = fbi_norm2(ctx, ctx->d_work, &pbnorm))) return rc;
