@@ -643,6 +643,15 @@ k_bjacobi_setup_coop(DevSpec S, const double* __restrict__ J, double* __restrict
   for (int t = g; t < nn; t += G) out[t] = A[t];
 }
 
+// 2^e as a double (|e| <= 1000)
+__device__ __forceinline__ double fb_pow2(int e) {
+#ifndef FB_EMU
+  return __hiloint2double((e + 1023) << 20, 0);
+#else
+  return ldexp(1.0, e);
+#endif
+}
+
 // Thread-per-vertex inversion with every matrix in its own shared-memory slab: element e of the
 // matrix of thread t at bj_smem[e * (TPB + 1) + t], so the 32 threads of a warp always hit 32
 // different banks whatever rows their pivots select, and the inverse blocks leave through a coalesced
@@ -673,8 +682,13 @@ __global__ void __launch_bounds__(TPB) k_bjacobi_setup_slab(DevSpec S, const dou
       const double* __restrict__ st = S.et_stat + (long long)(r0 + kself) * S.vx_nsp;
       const double* __restrict__ dy = S.et_dyn + (long long)(r0 + kself) * S.vx_ndp;
       const int nch = S.vx_nch, nstat = S.vx_nstat;
-      for (int ch = 0; ch < nch; ++ch) {
-        const double val = ch < nstat ? st[ch] : dy[ch - nstat];
+      double cv[16];   // all channel values of the diagonal edge in flight at once (nch <= 16)
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) cv[ch] = ch < nch ? (ch < nstat ? st[ch] : dy[ch - nstat]) : 0.0;
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {
+        if (ch >= nch) break;
+        const double val = cv[ch];
         const int e1 = __ldg(bj_ptr + ch + 1);
 #pragma unroll 4
         for (int e = __ldg(bj_ptr + ch); e < e1; ++e) {
@@ -723,9 +737,11 @@ __global__ void __launch_bounds__(TPB) k_bjacobi_setup_slab(DevSpec S, const dou
 #pragma unroll
             for (int c = 0; c < NS; ++c) BJ(r, c) = prow[c];
           } else {
+            // new row = row - f * (scaled pivot row), except column col: (0 - f / pivot), fixed up afterwards
             const double f = BJ(r, col);
 #pragma unroll
-            for (int c = 0; c < NS; ++c) BJ(r, c) = (c == col ? 0.0 : BJ(r, c)) - f * prow[c];
+            for (int c = 0; c < NS; ++c) BJ(r, c) = BJ(r, c) - f * prow[c];
+            BJ(r, col) = 0.0 - f * ip;
           }
         }
       } else {
@@ -754,7 +770,7 @@ __global__ void __launch_bounds__(TPB) k_bjacobi_setup_slab(DevSpec S, const dou
       int ex = 0;
       if (mx > 0.0) (void)frexp(mx, &ex);
       ex = ex < -1000 ? -1000 : (ex > 1000 ? 1000 : ex);
-      const double up = ldexp(1.0, ex), dn = ldexp(1.0, -ex);
+      const double up = fb_pow2(ex), dn = fb_pow2(-ex);
       for (int c = 0; c < ns; ++c) BJ(s, c) = (double)(float)(BJ(s, c) * dn) * up;
       sexp[s * LD + threadIdx.x] = (short)ex;
     }
@@ -770,12 +786,12 @@ __global__ void __launch_bounds__(TPB) k_bjacobi_setup_slab(DevSpec S, const dou
     const double val = bj_smem[e * LD + m];
     const int ex = sexp[(e / ns) * LD + m];
     out[i] = val;
-    out32[i] = (float)ldexp(val, -ex);   // exact
+    out32[i] = (float)(val * fb_pow2(-ex));   // exact
   }
   double* __restrict__ outs = dscale + v0 * ns;
   for (int i = threadIdx.x; i < nvalid * ns; i += TPB) {
     const int m = i / ns, s = i - m * ns;
-    outs[i] = ldexp(1.0, (int)sexp[s * LD + m]);
+    outs[i] = fb_pow2((int)sexp[s * LD + m]);
   }
 }
 
