@@ -223,6 +223,7 @@ int upload_section(fb_ctx* ctx, const char* blob, size_t nbytes, const Section* 
 extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
   if (!ctx || !ctx->have_pattern) return ctx ? fb_fail(ctx, "fb_set_pattern first") : -1;
   cudaSetDevice(ctx->device);
+  ctx->dyn_saved = false;
   const char* blob = (const char*)blob_;
   if (nbytes < 16) return fb_fail(ctx, "spec blob too small");
   long long hdr[2];
@@ -289,6 +290,13 @@ extern "C" int fb_set_spec(fb_ctx* ctx, const void* blob_, size_t nbytes) {
     S.n_rslots = si[0]; S.n_factors = si[1]; S.n_monos = si[2];
     S.n_fac_terms = (int)secs[S_FAC_COEF].count;
     UP(S_RSLOT_E, 1, rslot_E); UP(S_FAC_HDR, 0, fac_hdr); UP(S_FAC_A0, 1, fac_a0);
+    {
+      const int* fh = (const int*)(blob + secs[S_FAC_HDR].offset);
+      ctx->fac_scalar_idx.clear();
+      for (int f = 0; f < S.n_factors; ++f)
+        if (fh[4 * f]) ctx->fac_scalar_idx.push_back(fh[4 * f + 1]);
+      ctx->fac_scalar_last.assign(ctx->fac_scalar_idx.size(), 0.0);
+    }
     UP(S_FAC_SPECIES, 0, fac_species); UP(S_FAC_COEF, 1, fac_coef);
     ctx->symmetric = false;
   }
@@ -456,6 +464,13 @@ extern "C" int fb_set_scalars(fb_ctx* ctx, int n, const double* scalars) {
     FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // scalars is caller stack/heap memory
   }
   if (ctx->dt_scalar >= 0 && ctx->dt_scalar < n) ctx->S.inv_dt = 1.0 / scalars[ctx->dt_scalar];
+  // the stored solution-dependent channels depend on the scalars the affine factors read
+  for (size_t q = 0; q < ctx->fac_scalar_idx.size(); ++q) {
+    const int k = ctx->fac_scalar_idx[q];
+    const double v = k < n ? scalars[k] : 0.0;
+    if (!(v == ctx->fac_scalar_last[q])) ctx->dyn_saved = false;
+    ctx->fac_scalar_last[q] = v;
+  }
   return 0;
 }
 

@@ -225,6 +225,7 @@ int fbi_update_vinfo(fb_ctx* ctx) {
 }
 
 int fbi_update_coeffs(fb_ctx* ctx) {
+  ctx->dyn_saved = false;    // edge tensors rebuilt: the stored solution-dependent channels are stale
   ctx->cheb_valid = false;   // temperature / coefficients moved: re-estimate the spectrum interval
   ctx->cheb_refused = false;
   ctx->yprev_n = 0;          // the initial guess of the Krylov solve comes from another problem
@@ -287,11 +288,36 @@ static bool asm_tma_ok(fb_ctx* ctx, const double* u, const double* un) {
          !getenv("FB_NO_TMA_ASSEMBLY");   // rows of up to 16 edges: both contractions run as DMMA tiles
 }
 
+// *mismatch = 1 if the two vectors differ anywhere (caller zeroes it)
+__global__ void k_vec_differs(long long n, const double* __restrict__ a, const double* __restrict__ b, int* mismatch) {
+  bool diff = false;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    diff |= !(a[k] == b[k]) && !(a[k] != a[k] && b[k] != b[k]);   // NaNs in the same place count as equal
+  if (diff) *mismatch = 1;   // every writer stores the same value
+}
+
 static int asm_tma_launch(fb_ctx* ctx, const double* u, const double* un, double* F, int flags, bool* done) {
   DevSpec& S = ctx->S;
   *done = false;
   AsmTmaArgs a{};
   a.u = u; a.un = un; a.F = F; a.dyn = (double*)S.et_dyn; a.flags = flags;
+  // reuse mode: the solution-dependent channels in memory were computed from this very solution (checked
+  // on the device, entry by entry): stream them instead of the edge tensors
+  a.mismatch = nullptr;
+  if (S.vx_ndyn > 0 && S.vx_nts > 0 && !getenv("FB_NO_DYN_REUSE")) {
+    if (!ctx->d_u_saved) {
+      int rc0 = fb_alloc(ctx, &ctx->d_u_saved, (size_t)S.n_dofs);
+      if (!rc0) rc0 = fb_alloc(ctx, &ctx->d_mismatch, 4);
+      if (rc0) return rc0;
+    }
+    if (ctx->dyn_saved) {
+      FB_CHECK(ctx, cudaMemsetAsync(ctx->d_mismatch, 0, sizeof(int), ctx->stream));
+      long long g = (S.n_dofs + 4 * FB_TPB - 1) / (4 * FB_TPB);
+      if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+      FB_LAUNCH(ctx, k_vec_differs, (unsigned)(g < 1 ? 1 : g), FB_TPB, 0, S.n_dofs, u, (const double*)ctx->d_u_saved, ctx->d_mismatch);
+      a.mismatch = ctx->d_mismatch;
+    }
+  }
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
   int nst = 3 * FB_CHUNK_GROUPS;
@@ -308,6 +334,10 @@ static int asm_tma_launch(fb_ctx* ctx, const double* u, const double* un, double
   k_assemble_edge_tma<<<(unsigned)grid, 32 * FB_CHUNK * FB_CHUNK_GROUPS + 64, smem, ctx->stream>>>(S, a);
   ctx->launches++;
   FB_CHECK(ctx, cudaGetLastError());
+  if (ctx->d_u_saved) {   // et_dyn now belongs to this solution
+    FB_CHECK(ctx, cudaMemcpyAsync(ctx->d_u_saved, u, sizeof(double) * (size_t)S.n_dofs, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->dyn_saved = true;
+  }
   *done = true;
   return 0;
 }
@@ -384,6 +414,7 @@ static int assemble_dim(fb_ctx* ctx, const double* u, const double* un, double* 
     bool done = false;
     int rc = 0;
     if (asm_tma_ok(ctx, u, un) && (rc = asm_tma_launch(ctx, u, un, F, flags, &done))) return rc;
+    if (!done) ctx->dyn_saved = false;   // the row kernel rewrites et_dyn without recording the solution
     if (!done && (rc = et_launch(ctx, 0, u, un, F, nullptr, flags))) return rc;
     if ((flags & FB_ASSEMBLE_J) && J && (rc = et_launch(ctx, 1, nullptr, nullptr, nullptr, J, 0))) return rc;
   } else if (ctx->have_jit) {

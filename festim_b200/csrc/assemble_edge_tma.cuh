@@ -24,6 +24,7 @@ struct AsmTmaArgs {
   double* dyn;
   int flags;
   int nst;
+  const int* mismatch;   // reuse mode when non-null and zero: et_dyn already holds the channels of this solution
   // shared-memory layout (bytes)
   int o_tab_i, o_fac_d, o_fac_i, o_scr, scr_bytes, o_stage0, stage_bytes, o_bar;
   int s_tvw, s_tz, s_tzs, s_us, s_uns, s_load, s_lcol, s_vinfo, s_rowinfo, s_rowptr, s_tzptr, s_tzw;
@@ -53,7 +54,10 @@ __host__ inline size_t fb_asm_tma_layout(const DevSpec& S, AsmTmaArgs& a, int ns
   s += up16((size_t)CH * md * S.vx_nsp * 8);                       // static channel values
   a.s_tvw = (int)s; s += up16((size_t)nts * CH * md * 16);
   a.tz_stride = (int)((S.et_tz_chunk_max + 1) & ~1LL);
-  a.s_tz = (int)s; s += up16((size_t)nts * a.tz_stride * 8);
+  {   // the T_vwz slabs - or, in reuse mode, the stored solution-dependent channel values of the chunk
+    const size_t tzb = (size_t)nts * a.tz_stride * 8, dyb = (size_t)CH * md * S.vx_ndp * 8;
+    a.s_tz = (int)s; s += up16(tzb > dyb ? tzb : dyb);
+  }
   a.s_tzs = (int)s; s += up16((size_t)S.et_tz_chunk_max + 16);
   a.s_us = (int)s; s += up16((size_t)(S.ck_nx_max + 2) * ns * 8);
   a.s_uns = (int)s; if (S.transient) s += up16((size_t)(S.ck_nx_max + 2) * ns * 8);
@@ -81,6 +85,7 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
   const int nstat = S.vx_nstat, ndyn = S.vx_ndyn;
   const bool doF = (a.flags & FB_ASSEMBLE_F) != 0;
   const bool transient = S.transient != 0;
+  const bool reuse = a.mismatch && a.mismatch[0] == 0 && ndyn > 0;
   double* dtab = (double*)fb_as_smem;
   int* itab = (int*)(fb_as_smem + a.o_tab_i);
   for (int t = threadIdx.x; t < S.vx_dtab_n; t += blockDim.x) dtab[t] = S.vx_dtab[t];
@@ -162,21 +167,23 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
       }
       if (lane == 0) {
         unsigned bytes = (unsigned)(nlc * 2 + 2 * CH * 4 + (CH + 4) * 4);
-        if (nts) bytes += (unsigned)(nts * (2 * ne * 8 + nt * 8) + nt + CH * 4 + (CH + 4) * 8);
+        if (nts && !reuse) bytes += (unsigned)(nts * (2 * ne * 8 + nt * 8) + nt + CH * 4 + (CH + 4) * 8);
+        if (reuse) bytes += (unsigned)(ne * NDP * 8);
         if (doF) bytes += (unsigned)(ne * NSP * 8 + nrow * ns * 8);
         fb_mbar_expect_tx(b, bytes);
       }
       __syncwarp();
+      if (reuse && lane == 6) fb_bulk_g2s(st + a.s_tz, a.dyn + (long long)e0 * NDP, (unsigned)(ne * NDP * 8), b);
       if (lane == 0 && doF && NSP) fb_bulk_g2s(st, S.et_stat + (long long)e0 * NSP, (unsigned)(ne * NSP * 8), b);
       if (lane == 1 && doF) fb_bulk_g2s(st + a.s_load, S.load + c0 * ns, (unsigned)(nrow * ns * 8), b);
       if (lane == 2) fb_bulk_g2s(st + a.s_lcol, S.ck_lcol + lc0, (unsigned)(nlc * 2), b);
       if (lane == 3) fb_bulk_g2s(st + a.s_vinfo, S.vinfo + c0, (unsigned)(CH * 4), b);
       if (lane == 4) fb_bulk_g2s(st + a.s_rowinfo, S.ck_rowinfo + c0, (unsigned)(CH * 4), b);
       if (lane == 5) fb_bulk_g2s(st + a.s_rowptr, S.rowptr + c0, (unsigned)((CH + 4) * 4), b);
-      if (lane == 6 && nts) fb_bulk_g2s(st + a.s_tzptr, S.et_tzptr + c0, (unsigned)((CH + 4) * 8), b);
-      if (lane == 7 && nts) fb_bulk_g2s(st + a.s_tzw, S.et_tzw + c0, (unsigned)(CH * 4), b);
-      if (lane == 8 && nts && nt) fb_bulk_g2s(st + a.s_tzs, S.et_tzslot + t0, (unsigned)nt, b);
-      if (lane >= 9 && lane < 9 + 2 * nts) {   // per tensor: the (T_vvw, T_vww) pairs and the T_vwz slabs
+      if (lane == 6 && nts && !reuse) fb_bulk_g2s(st + a.s_tzptr, S.et_tzptr + c0, (unsigned)((CH + 4) * 8), b);
+      if (lane == 7 && nts && !reuse) fb_bulk_g2s(st + a.s_tzw, S.et_tzw + c0, (unsigned)(CH * 4), b);
+      if (lane == 8 && nts && nt && !reuse) fb_bulk_g2s(st + a.s_tzs, S.et_tzslot + t0, (unsigned)nt, b);
+      if (lane >= 9 && lane < 9 + 2 * nts && !reuse) {   // per tensor: the (T_vvw, T_vww) pairs and the T_vwz slabs
         const int ts = (lane - 9) >> 1;
         if (((lane - 9) & 1) == 0)
           fb_bulk_g2s(st + a.s_tvw + (size_t)ts * CH * S.maxdeg * 16, S.et_tvw + 2 * (ts * S.nnzb + e0), (unsigned)(ne * 16), b);
@@ -246,7 +253,9 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
       const int krow = lane & 3, bcol = lane >> 2;
       double* tf = scr + a.w_tf;
       // ---- dynamic channel values: A^c[k] = sum_z T[k][z] f_c(z), T the row's tensor expanded to 16 x 16 --
-      if (ndyn > 0) {
+      // solution-dependent channel values of the row: computed below, or (reuse mode) as they arrived
+      const double* adp = reuse ? (const double*)(st + a.s_tz) + (size_t)rp0 * NDP : adyn;
+      if (ndyn > 0 && !reuse) {
         const long long* tzptr_s = (const long long*)(st + a.s_tzptr);
         const int tzr = (int)(tzptr_s[j] - tzptr_s[0]);
         const int Wd = ((const int*)(st + a.s_tzw))[j];
@@ -313,7 +322,7 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
           for (int u4 = 0; u4 < 4; ++u4) {
             const int k = 4 * u4 + krow;
             double v = 0.0;
-            if (cok && k < deg) v = ch < nstat ? sr[k * NSP + ch] : adyn[k * NDP + ch - nstat];
+            if (cok && k < deg) v = ch < nstat ? sr[k * NSP + ch] : adp[k * NDP + ch - nstat];
             av[u4][mt] = v;
           }
         }
@@ -360,7 +369,7 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
             for (int k = 0; k < deg; ++k) {
               const int w = S.colidx[e0 + rp0 + k];
               if ((S.vinfo[w] >> cs) & 1u) {
-                const double av = chan < nstat ? sr[k * NSP + chan] : adyn[k * NDP + chan - nstat];
+                const double av = chan < nstat ? sr[k * NSP + chan] : adp[k * NDP + chan - nstat];
                 acc += av * (S.bc_vals[S.bc_map[(long long)w * ns + cs]] - us[(size_t)lc[k] * ns + cs]);
               }
             }

@@ -91,6 +91,14 @@ struct fb_ctx {
   double* d_dinv = nullptr;  // block-Jacobi inverse blocks [n_vertices][ns][ns]
   // the same blocks as single-precision mantissas with one power-of-two scale per row (k_bjacobi_setup_slab):
   // inverse[v][s][c] = dscale[v][s] * dinv32[v][s][c] holds exactly - d_dinv carries these rounded values
+  // the solution the stored solution-dependent channel values (et_dyn) were computed from: an assembly at the
+  // same solution (the first of a time step, after the residual check of the last one) streams them instead
+  // of contracting the edge tensors again (k_assemble_edge_tma, reuse mode)
+  double* d_u_saved = nullptr;
+  bool dyn_saved = false;
+  int* d_mismatch = nullptr;
+  std::vector<int> fac_scalar_idx;       // scalars the affine reaction factors read
+  std::vector<double> fac_scalar_last;
   float* d_dinv32 = nullptr;
   double* d_dscale = nullptr;
   bool dinv32_valid = false;
