@@ -103,3 +103,39 @@ def test_channel_spmv_with_the_register_plan_matches_the_block_csr_product():
     ctx._check(ctx.lib.fb_spmv(ctx.h, None, ctx.ptr(xd), ctx.ptr(yd)))
     ref = J @ x
     assert np.abs(ctx.nodal_from_device(yd, ns) - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_stored_channels_are_reused_only_at_the_same_solution(monkeypatch):
+    """The first assembly of a time step happens at the solution whose solution-dependent channels the last
+    residual check left in memory: the library streams them instead of contracting the edge tensors again.
+    Same solution -> same residual as a full assembly; a changed solution -> channels recomputed (residual and
+    operator equal to those of a context that never reuses)."""
+    m, ctx, J, N, rng = _setup(n=6)
+    ns = m.solver.spec.ns
+    u1 = m.u.x.array.copy()
+    un = m.u_n.x.array.copy()
+    u2 = u1.copy()
+    u2[::7] *= 2.0
+    x = rng.standard_normal(N)
+    xd = ctx.nodal_to_device("test_x", x, ns)
+
+    def assemble(uh):
+        ud, und = ctx.nodal_to_device("test_u", uh, ns), ctx.nodal_to_device("test_un", un, ns)
+        Fd, yd = ctx.zeros(N), ctx.zeros(N)
+        ctx._check(ctx.lib.fb_assemble(ctx.h, ctx.ptr(ud), ctx.ptr(und), ctx.ptr(Fd), None, 3))
+        ctx._check(ctx.lib.fb_spmv(ctx.h, None, ctx.ptr(xd), ctx.ptr(yd)))
+        return ctx.nodal_from_device(Fd, ns), ctx.nodal_from_device(yd, ns)
+
+    F_first, y_first = assemble(u1)          # _setup assembled at u1 already: this call reuses
+    F_again, y_again = assemble(u1)
+    F_moved, y_moved = assemble(u2)          # must notice the change
+    monkeypatch.setenv("FB_NO_DYN_REUSE", "1")
+    F_ref1, y_ref1 = assemble(u1)
+    F_ref2, y_ref2 = assemble(u2)
+    for a, b in ((F_first, F_ref1), (F_again, F_ref1), (F_moved, F_ref2)):
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+    for a, b in ((y_first, y_ref1), (y_again, y_ref1), (y_moved, y_ref2)):
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+    # the operator does depend on the solution by far more than the tolerance above: stale channels would show
+    assert np.abs(y_ref2 - y_ref1).max() > 1e-10 * np.abs(y_ref1).max()
+    assert np.abs(F_ref2 - F_ref1).max() > 1e-6 * np.abs(F_ref1).max()
