@@ -2167,6 +2167,39 @@ __global__ void k_cheb_init(long long n, const double* __restrict__ v, double in
   }
 }
 
+// Operator applications per Krylov iteration for a solve that has to reduce the (preconditioned) residual
+// by `reduction`: with the interval known, m Krylov iterations with k applications each reduce it by about
+// 1 / T_k(sigma)^m.  Measured on C2 (needed reduction 6e-8): k = 5 -> 5 iterations (as the bound says), k = 7 ->
+// 3 (bound: 9.9e-8, 4 in one solve of six), k = 10 -> 2 (bound: 1.2e-7, 3 in one solve of three) - GMRES runs
+// up to a factor 2 ahead of the bound, with a rising chance of one more iteration; but k = 11 and 12 (bound^2 well
+// below the target) still took 3 iterations in half of the solves: eigenvalues outside the Ritz interval are not
+// damped by the polynomial and cost a Krylov iteration each.  The rule takes the (m, k), m >= 3, k <= 12, of the least
+// expected cost, an orthogonalisation step counted as 0.7 applications; *m_out = the iterations expected.
+static int cheb_choose_steps(const fb_ctx* ctx, double reduction, int* m_out) {
+  const double sigma = (ctx->cheb_lmax + ctx->cheb_lmin) / (ctx->cheb_lmax - ctx->cheb_lmin);
+  const double a = std::acosh(sigma);
+  if (!(reduction < 0.5)) reduction = 0.5;
+  if (reduction < 1e-16) reduction = 1e-16;
+  int best_k = ctx->cheb_steps, best_m = 0;
+  double best_cost = 1e300;
+  for (int m = 3; m <= 8; ++m)
+    for (int k = 2; k <= 12; ++k) {   // longer recurrences would trust the interval too much
+      // bound on the reduction of m iterations, relative to what is needed; the chance that one more
+      // iteration is needed rises steeply once the bound alone does not reach the target
+      const double ratio = std::exp(-m * std::log(std::cosh(k * a))) / reduction;
+      double miss;
+      if (ratio <= 1.0) miss = 0.0;
+      else if (ratio <= 1.7) miss = 0.2;
+      else if (ratio <= 2.5) miss = 0.5;
+      else continue;
+      const double cost = (m + miss) * (k + 0.7);
+      if (cost < best_cost) { best_cost = cost; best_k = k; best_m = m; }
+    }
+  if (best_m == 0) { best_k = 12; best_m = 8; }
+  *m_out = best_m;
+  return best_k;
+}
+
 // z = p(B) v with p the Chebyshev polynomial of the interval (cheb_steps - 1 applications of
 // B = D^-1 J), and - when w is given - w = B z from one more application (w = v - r).
 static int cheb_apply(fb_ctx* ctx, const double* v, double* z, double* w, double* d0, double* d1, double* r,
@@ -2254,8 +2287,20 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
         continue;
       }
     }
+    int poll = cheb ? 4 : 10;
+    if (cheb && !getenv("FB_CHEB_DEGREE")) {
+      // degree of the polynomial from the reduction this solve still needs (|r0| from the device, one word)
+      FB_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 40, sc + GM_MISC, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      const double r0 = std::sqrt(ctx->h_pinned[40] > 0.0 ? ctx->h_pinned[40] : 0.0);
+      int m_exp = 4;
+      ctx->cheb_steps = cheb_choose_steps(ctx, r0 > 0.0 ? thr / r0 : 1.0, &m_exp);
+      poll = m_exp;   // first look at the flags when the solve is expected to be done
+      if (getenv("FB_VERBOSE"))
+        fprintf(stderr, "[fb] Chebyshev: reduction %.2e needed -> %d applications x %d Krylov iterations expected\n",
+                r0 > 0.0 ? thr / r0 : 1.0, ctx->cheb_steps, m_exp);
+    }
     FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, No, r, sc + GM_MISC + 1, V, (const int*)nullptr);
-    const int poll = cheb ? 4 : 10;
     for (int j = 0; j < GM_M; ++j) {
       // w = D^-1 J [p(B)] V_j: SpMV with the block-Jacobi application fused into its epilogue
       if (cheb) {
@@ -2286,7 +2331,7 @@ static int solve_gmres(fb_ctx* ctx, const double* J, const double* b, double* y,
 #undef FB_GS_CASE
       FB_LAUNCH(ctx, k_gmres_givens, 1, 1, 0, j, sc, ctx->d_flags);
       FB_LAUNCH(ctx, k_scale_to, gv, FB_TPB, 0, No, w, sc + GM_MISC + 1, V + (size_t)(j + 1) * N, ctx->d_flags);
-      if (j % poll == poll - 1 || j == GM_M - 1) {
+      if (j % poll == poll - 1 || j == GM_M - 1 || (cheb && j >= poll)) {
         FB_CHECK(ctx, cudaGetLastError());
         if ((rc = read_flags(ctx, fl))) return rc;
         if (fl[0]) break;
