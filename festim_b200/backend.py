@@ -76,6 +76,7 @@ def load_library():
         "fb_hessenberg_eigenvalues": (i, [i, _f64p, _f64p, _f64p]),
         "fb_chebyshev_info": (i, [vp, _f64p]),
         "fb_chebyshev_step": (i, [vp, vp, vp, vp, vp, d, d]),
+        "fb_chebyshev_steps": (i, [d, d, d, C.POINTER(i)]),
         "fb_total_volume": (i, [vp, vp, i, i, _f64p]),
         "fb_total_surface": (i, [vp, vp, i, i, _f64p]),
         "fb_surface_flux": (i, [vp, vp, i, i, d, vp, _f64p]),
@@ -107,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "fb_set_spec", "fb_jit_load", "fb_set_dirichlet", "fb_num_dofs", "fb_jacobian_nnz", "fb_set_scalars",
     "fb_set_temperature", "fb_set_field", "fb_set_velocity", "fb_set_dirichlet_values",
     "fb_update_load", "fb_assemble", "fb_spmv", "fb_dot", "fb_axpy", "fb_linear_solve",
-    "fb_newton_solve", "fb_run_steps", "fb_last_timings", "fb_stepsize_modify", "fb_hessenberg_eigenvalues", "fb_chebyshev_info", "fb_chebyshev_step", "fb_total_volume",
+    "fb_newton_solve", "fb_run_steps", "fb_last_timings", "fb_stepsize_modify", "fb_hessenberg_eigenvalues", "fb_chebyshev_info", "fb_chebyshev_step", "fb_chebyshev_steps", "fb_total_volume",
     "fb_total_surface", "fb_surface_flux", "fb_integrate", "fb_set_owned", "fb_set_sm_partition",
     "fb_bjacobi_setup", "fb_precond",
     "fb_peer_alloc", "fb_peer_open", "fb_peer_set_send", "fb_dcg_persistent",

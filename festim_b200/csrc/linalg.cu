@@ -2175,12 +2175,12 @@ __global__ void k_cheb_init(long long n, const double* __restrict__ v, double in
 // below the target) still took 3 iterations in half of the solves: eigenvalues outside the Ritz interval are not
 // damped by the polynomial and cost a Krylov iteration each.  The rule takes the (m, k), m >= 3, k <= 12, of the least
 // expected cost, an orthogonalisation step counted as 0.7 applications; *m_out = the iterations expected.
-static int cheb_choose_steps(const fb_ctx* ctx, double reduction, int* m_out) {
-  const double sigma = (ctx->cheb_lmax + ctx->cheb_lmin) / (ctx->cheb_lmax - ctx->cheb_lmin);
+static int cheb_choose_steps_interval(double lmin, double lmax, int fallback_k, double reduction, int* m_out) {
+  const double sigma = (lmax + lmin) / (lmax - lmin);
   const double a = std::acosh(sigma);
   if (!(reduction < 0.5)) reduction = 0.5;
   if (reduction < 1e-16) reduction = 1e-16;
-  int best_k = ctx->cheb_steps, best_m = 0;
+  int best_k = fallback_k, best_m = 0;
   double best_cost = 1e300;
   for (int m = 3; m <= 8; ++m)
     for (int k = 2; k <= 12; ++k) {   // longer recurrences would trust the interval too much
@@ -2198,6 +2198,15 @@ static int cheb_choose_steps(const fb_ctx* ctx, double reduction, int* m_out) {
   if (best_m == 0) { best_k = 12; best_m = 8; }
   *m_out = best_m;
   return best_k;
+}
+
+static int cheb_choose_steps(const fb_ctx* ctx, double reduction, int* m_out) {
+  return cheb_choose_steps_interval(ctx->cheb_lmin, ctx->cheb_lmax, ctx->cheb_steps, reduction, m_out);
+}
+
+extern "C" int fb_chebyshev_steps(double lambda_min, double lambda_max, double reduction, int* krylov_iterations) {
+  if (!(lambda_min > 0.0) || !(lambda_max > lambda_min) || !krylov_iterations) return -1;
+  return cheb_choose_steps_interval(lambda_min, lambda_max, 5, reduction, krylov_iterations);
 }
 
 // z = p(B) v with p the Chebyshev polynomial of the interval (cheb_steps - 1 applications of

@@ -153,6 +153,10 @@ int fb_last_timings(fb_ctx* ctx, double* out /*[host] 4*/);
 
 /* state of the Chebyshev preconditioner: out = {valid, lambda_min, lambda_max, operator applications per use} */
 int fb_chebyshev_info(fb_ctx* ctx, double* out /*[host] 4*/);
+/* test hook: operator applications per Krylov iteration the solver picks for a spectrum interval of D^-1 J and the
+ * residual reduction a solve still needs (least expected cost under the Chebyshev bound, >= 3 Krylov iterations,
+ * <= 12 applications); *krylov_iterations = the iterations it expects.  Returns the applications, < 0 on bad input. */
+int fb_chebyshev_steps(double lambda_min, double lambda_max, double reduction, int* krylov_iterations /*[host]*/);
 /* one step of the Chebyshev recurrence on B = D^-1 J (channel operator, after fb_bjacobi_setup(ctx, NULL)),
  * the single kernel launch the polynomial preconditioner repeats (PETSc analogue: one KSPCHEBYSHEV iteration
  * inside PCKSP, reference options seam src/festim/problem.py:132-168):
