@@ -327,6 +327,53 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
           }
         }
         __syncwarp();   // tf is free: it becomes the R tile
+        if (ns <= 16) {
+          // B operand by tiles of the table [u | u - u_n | factors | 1] laid out on 8-column boundaries: tiles
+          // 0-1 = u (16 columns, the ones >= ns unused), 2-3 = u - u_n, 4.. = factors and the column of ones -
+          // every tile loads the same way for all lanes (no per-element case analysis); results go to the
+          // table's own column numbering.  Rows k >= deg of the A operand are zero, so their B entries are free.
+          int ub[4];
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            const int k = 4 * u4 + krow;
+            ub[u4] = k < deg ? (int)lc[k] * ns : 0;
+          }
+          const int ntf = (NF + 1 + 7) >> 3;
+          for (int t5 = 0; t5 < 4 + ntf; ++t5) {
+            const int sub = t5 < 4 ? (t5 & 1) : t5 - 4;
+            if (t5 < 4 && 8 * sub >= ns) continue;
+            double bv[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            if (t5 < 2) {
+#pragma unroll
+              for (int u4 = 0; u4 < 4; ++u4) bv[u4] = us[ub[u4] + 8 * sub + bcol];
+            } else if (t5 < 4) {
+#pragma unroll
+              for (int u4 = 0; u4 < 4; ++u4)
+                bv[u4] = transient ? us[ub[u4] + 8 * sub + bcol] - uns[ub[u4] + 8 * sub + bcol] : 0.0;
+            } else {
+              const int f = 8 * sub + bcol;
+#pragma unroll
+              for (int u4 = 0; u4 < 4; ++u4) {
+                const int k = 4 * u4 + krow;
+                bv[u4] = f < NF ? (k < deg ? fv[k * NF + f] : 0.0) : (f == NF ? 1.0 : 0.0);
+              }
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              fb_dmma(acc[0][0], acc[0][1], av[u4][0], bv[u4]);
+              if (mtc > 1) fb_dmma(acc[1][0], acc[1][1], av[u4][1], bv[u4]);
+            }
+            // columns 2 krow, 2 krow + 1 of the tile -> table column (entries outside the table are dropped)
+            const int c0 = 8 * sub + 2 * krow;
+            const int lim = t5 < 4 ? ns : NF + 1;
+            const int g0 = (t5 < 2 ? 0 : (t5 < 4 ? ns : 2 * ns)) + c0;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              if (c0 < lim) tf[(8 * mt + bcol) * RTS + g0] = acc[mt][0];
+              if (c0 + 1 < lim) tf[(8 * mt + bcol) * RTS + g0 + 1] = acc[mt][1];
+            }
+          }
+        } else {
         for (int nt = 0; nt < ntg; ++nt) {
           const int gcol = 8 * nt + bcol;
           double bv[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -345,6 +392,7 @@ k_assemble_edge_tma(DevSpec S, AsmTmaArgs a) {
             tf[(8 * mt + bcol) * RTS + 8 * nt + 2 * krow] = acc[mt][0];
             tf[(8 * mt + bcol) * RTS + 8 * nt + 2 * krow + 1] = acc[mt][1];
           }
+        }
         }
         __syncwarp();
         const int nft = S.vx_nft;
