@@ -73,6 +73,7 @@ extern "C" void fb_destroy(fb_ctx* ctx) {
   for (void* p : ctx->owned) cudaFree(p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
 }
 

@@ -111,6 +111,10 @@ struct fb_ctx {
   double* d_tri = nullptr;   // dense block-tridiagonal workspace
   double timings[4] = {0, 0, 0, 0};
   cudaEvent_t ev[8];
+  // phase timing of fb_newton_solve without host synchronisation: event pairs recorded in stream order,
+  // turned into milliseconds after the solve's last (already needed) synchronisation
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_slot;
 };
 
 #define FB_CHECK(ctx, call)                                                                 \

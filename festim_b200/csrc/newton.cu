@@ -42,18 +42,33 @@ static int festim_convergence_test(int it, double snorm, double fnorm, double f0
   return 0;
 }
 
+// Phase timing without a host synchronisation of its own: start / stop events go into a pool in stream order
+// and are turned into milliseconds by resolve_phase_timings() after the last synchronisation of the solve.
 struct PhaseTimer {
   fb_ctx* ctx;
-  int slot;
-  PhaseTimer(fb_ctx* c, int s) : ctx(c), slot(s) { cudaEventRecord(ctx->ev[0], ctx->stream); }
-  void stop() {
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    cudaEventSynchronize(ctx->ev[1]);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->timings[slot] += ms;
+  size_t idx;
+  PhaseTimer(fb_ctx* c, int s) : ctx(c), idx(2 * c->ev_slot.size()) {
+    while (ctx->ev_pool.size() < idx + 2) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ctx->ev_pool.push_back(e);
+    }
+    ctx->ev_slot.push_back(s);
+    cudaEventRecord(ctx->ev_pool[idx], ctx->stream);
   }
+  void stop() { cudaEventRecord(ctx->ev_pool[idx + 1], ctx->stream); }
 };
+
+static void resolve_phase_timings(fb_ctx* ctx) {
+  for (size_t q = 0; q < ctx->ev_slot.size(); ++q) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev_pool[2 * q + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ctx->ev_pool[2 * q], ctx->ev_pool[2 * q + 1]) == cudaSuccess)
+      ctx->timings[ctx->ev_slot[q]] += ms;
+  }
+  ctx->ev_slot.clear();
+  (void)cudaGetLastError();   // an event of a phase left by an early return was never recorded: not an error of the solve
+}
 
 extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double atol, double rtol,
                                double stol, int max_it, int ksp, int pc, double ksp_rtol,
@@ -66,6 +81,7 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
   if (rc) return rc;
   const long long N = ctx->S.n_dofs;
   for (int i = 0; i < 4; ++i) ctx->timings[i] = 0.0;
+  ctx->ev_slot.clear();
   if (!u_n) u_n = u;
   if (ksp == FB_KSP_AUTO) {
     if (ctx->tridiag) ksp = FB_KSP_TRIDIAG;
@@ -160,6 +176,7 @@ extern "C" int fb_newton_solve(fb_ctx* ctx, double* u, const double* u_n, double
   }
   FB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   FB_CHECK(ctx, cudaGetLastError());
+  resolve_phase_timings(ctx);
   if (ctx->peer_ready) {   // a peer that never answered leaves the abort flag behind
     unsigned aborted = 0;
     FB_CHECK(ctx, cudaMemcpy(&aborted, ctx->d_ticket + 128, sizeof(unsigned), cudaMemcpyDeviceToHost));
